@@ -1,0 +1,166 @@
+/* wavenet_b200.h - C ABI of libwavenet_b200.so
+ *
+ * B200 (sm_100a) implementation of the WaveNet dilated-causal-convolution hot path of
+ * deep-art-project/Music.  The reference is pure Python on PyTorch and has no FFI of its own;
+ * the boundary it exposes is its Python surface.  Each entry point below cites the reference
+ * interface (file:line, relative to the reference root) whose arithmetic it replaces; the
+ * Python layer in music_b200/ re-creates that surface on top of these calls.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / C++ types in any signature.
+ *  - every function returns 0 on success, a negative wn_status otherwise;
+ *    wn_last_error() returns a thread-local message for the last failure.
+ *  - every pointer named d_* is a DEVICE pointer owned by the caller; the library never
+ *    allocates device memory: sizes come from the *_bytes queries.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it and
+ *    the library never synchronises.
+ *  - there is no CPU fallback: without an sm_100 device wn_init() fails and nothing else runs.
+ *
+ * Layouts
+ *  - parameters: ONE flat fp32 vector in the reference state_dict order
+ *    (wavenet/model.py:46-84): causal_layer.weight (R,Q,2) [.bias (R)], then per layer
+ *    filter (D,R,2), gate (D,R,2), dense (R,D,1), skip (S,D,1) [each followed by its bias],
+ *    post_process_1 (S,S,1), post_process_2 (Q,S,1).  Gradients use the same flat layout.
+ *  - dense input  : (B,Q,L) fp32 contiguous, as `wavenet.forward` takes it (model.py:86-98).
+ *  - index input  : (B,L) int64 mu-law codes == a true one-hot (B,Q,L) input.
+ *  - logits       : (B,Q,W) fp32 contiguous, W = L - rf + 1: the output of post_process_2
+ *    (model.py:138), i.e. the tensor `forward` views as (-1,Q) before its softmax (:142-144).
+ */
+#ifndef WAVENET_B200_H_
+#define WAVENET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  WN_OK = 0,
+  WN_ERR_INVALID = -1,      /* bad argument */
+  WN_ERR_CUDA = -2,         /* CUDA runtime / driver error */
+  WN_ERR_UNSUPPORTED = -3,  /* valid request this build cannot serve (e.g. not sm_100) */
+  WN_ERR_SHAPE = -4         /* "wave sample not long enough" (model.py:100-101) and friends */
+} wn_status;
+
+/* arithmetic mode of the conv stack */
+enum { WN_MODE_FP32 = 0,    /* fp32 SIMT check mode (1e-4 parity) */
+       WN_MODE_BF16 = 1 };  /* tcgen05/TMEM bf16 tensor-core path, fp32 accumulate */
+
+/* softmax row order + loss definition */
+enum { WN_ROWS_REFERENCE = 0,   /* rows = flat Q-chunks of the (B,Q,W) buffer (model.py:142-143) and
+                                   CrossEntropyLoss applied to probabilities (train.py:146,179) */
+       WN_ROWS_CORRECTED = 1 }; /* rows = time steps, single softmax (extension) */
+
+/* which vector a block pushes into its generation queue */
+enum { WN_PUSH_OUTPUT = 0,      /* block output: what fast_generate.py:128-129 does */
+       WN_PUSH_INPUT = 1 };     /* block input: consistent with the full forward (extension) */
+
+typedef struct {
+  int32_t n_layers;
+  const int32_t* dilations;        /* host array, n_layers entries */
+  int32_t residual_channels;       /* R */
+  int32_t dilation_channels;       /* D */
+  int32_t skip_channels;           /* S */
+  int32_t quantization_channels;   /* Q */
+  int32_t use_bias;
+  int32_t filter_width;            /* must be 2 (the only width the reference ships or tests) */
+} wn_config;
+
+typedef struct wn_model wn_model;  /* host-side plan: shapes, offsets, cached TMA descriptors */
+
+/* ---- lifecycle ---------------------------------------------------------------------- */
+int wn_version(void);
+const char* wn_last_error(void);
+/* Selects `device`, checks compute capability 10.x, resolves the driver entry points used for
+ * TMA descriptors.  Must be called once per process before any launch. */
+int wn_init(int device);
+
+/* ---- mu-law codec : wavenet/audio_func.py:5-22 (encode), :24-39 (decode) -------------- */
+/* bit-exact with the reference's torch-CPU fp32 arithmetic via threshold / value tables
+ * (d_thresholds: Q floats, [0] unused; d_values: Q floats) evaluated once on the host. */
+int wn_mulaw_encode(const float* d_audio, int64_t n, int32_t q, const float* d_thresholds,
+                    int64_t* d_codes, void* stream);
+int wn_mulaw_decode(const int64_t* d_codes, int64_t n, int32_t q, const float* d_values,
+                    float* d_audio, void* stream);
+
+/* ---- model plan : wavenet.__init__ / calc_receptive_field, wavenet/model.py:8-84 ------ */
+int wn_model_create(const wn_config* cfg, wn_model** out);
+int wn_model_destroy(wn_model* m);
+int64_t wn_model_param_count(const wn_model* m);
+int32_t wn_model_receptive_field(const wn_model* m);          /* model.py:43-44 */
+
+/* kernel-side weight images derived from the flat fp32 parameters (refresh after every
+ * optimizer step).  fp32 mode: transposed fp32 copies; bf16 mode: bf16 K-major matrices that
+ * TMA loads straight into the UMMA shared-memory layout. */
+int wn_packed_bytes(const wn_model* m, int32_t mode, size_t* bytes);
+int wn_pack_weights(wn_model* m, int32_t mode, const float* d_params, void* d_packed, void* stream);
+
+/* ---- training forward / backward : wavenet.forward, wavenet/model.py:86-138 ----------- */
+int wn_workspace_bytes(const wn_model* m, int32_t mode, int32_t B, int32_t L, size_t* bytes);
+/* Exactly one of d_x (dense (B,Q,L) fp32) / d_idx ((B,L) int64) is non-NULL.
+ * Writes d_logits (B,Q,W) fp32 and keeps what backward needs inside d_workspace (which must be
+ * zero-filled once when allocated and must not be touched between forward and backward). */
+int wn_forward(wn_model* m, int32_t mode, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx,
+               const void* d_packed, void* d_workspace, float* d_logits, void* stream);
+/* Gradient of a scalar loss w.r.t. the flat parameters given d_dlogits (B,Q,W) fp32.
+ * d_grads (param_count floats) is OVERWRITTEN.  Same d_x/d_idx/d_workspace as the forward.
+ * d_dlogits may be clobbered. */
+int wn_backward(wn_model* m, int32_t mode, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx,
+                const void* d_packed, void* d_workspace, float* d_dlogits, float* d_grads, void* stream);
+
+/* ---- softmax + loss : model.py:142-144 (nn.Softmax on the (-1,Q) view),
+ *                       train.py:146,177-179 (CrossEntropyLoss on the probabilities) ------ */
+int wn_softmax_fwd(const float* d_logits, int32_t B, int32_t Q, int32_t W, int32_t rows,
+                   float* d_probs /* (B*W,Q) */, void* stream);
+int wn_softmax_bwd(const float* d_probs, const float* d_dprobs, int32_t B, int32_t Q, int32_t W,
+                   int32_t rows, float* d_dlogits /* (B,Q,W) */, void* stream);
+/* Fused: probabilities, loss (mean over the B*W rows, written to d_loss[0]) and, if
+ * d_dlogits != NULL, grad_scale * dloss/dlogits.  d_scratch: wn_loss_scratch_bytes(). */
+int wn_loss_scratch_bytes(int32_t B, int32_t W, size_t* bytes);
+int wn_loss_fwd_bwd(const float* d_logits, const int64_t* d_target /* (B,W) */, int32_t B, int32_t Q,
+                    int32_t W, int32_t rows, float grad_scale, float* d_loss, float* d_dlogits,
+                    void* d_scratch, void* stream);
+
+/* ---- optimizers : get_optimizer, wavenet/train.py:28-42 (torch.optim defaults) --------- */
+int wn_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n, float lr,
+                 float beta1, float beta2, float eps, int32_t step, void* stream);
+int wn_sgd_step(float* d_params, const float* d_grads, float* d_momentum_buf, int64_t n, float lr,
+                float momentum, int32_t first_step, void* stream);
+int wn_rmsprop_step(float* d_params, const float* d_grads, float* d_square_avg, float* d_momentum_buf,
+                    int64_t n, float lr, float alpha, float eps, float momentum, void* stream);
+
+/* ---- incremental generation : fast_generate.predict_next, wavenet/fast_generate.py:13-141 -- */
+/* Per-stream state: ring buffers replacing the reference's shift-copied queues. */
+int wn_gen_state_bytes(const wn_model* m, int32_t mode, int32_t n_streams, size_t* bytes);
+/* Prime branch (:29-65): d_prime_idx (n_streams, rf) int64 codes of the priming one-hot piece.
+ * Fills the queues and writes the first pick per stream to d_out[n_streams]. */
+int wn_gen_prime(wn_model* m, int32_t mode, int32_t n_streams, const int64_t* d_prime_idx,
+                 const void* d_packed, void* d_state, void* d_workspace, size_t workspace_bytes,
+                 const float* d_uniforms /* n_streams or NULL=greedy */, int64_t* d_out,
+                 float* d_logits /* (n_streams,Q) or NULL */, void* stream);
+/* Step branch (:66-141), n_steps times per stream, feeding each pick back as the next one-hot
+ * note (generate(), :166-172).  d_first_note (n_streams) = the note fed to the first step.
+ * d_out is (n_steps, n_streams); d_uniforms (n_steps, n_streams) or NULL for the reference's
+ * greedy topk(1); d_logits (n_steps, n_streams, Q) or NULL. */
+int wn_gen_steps(wn_model* m, int32_t mode, int32_t n_streams, int32_t n_steps, int32_t push,
+                 const int64_t* d_first_note, const void* d_packed, void* d_state,
+                 const float* d_uniforms, int64_t* d_out, float* d_logits, void* stream);
+/* Queue interchange with the reference's OrderedDict layout ('causal_layer': (1,Q,1) as a code,
+ * 'block_k': (1,R,d_k) oldest first): d_queues is (n_streams, sum(d_k), R) fp32 time-major,
+ * d_last_note (n_streams) int64. */
+int wn_gen_export(const wn_model* m, int32_t mode, int32_t n_streams, const void* d_state,
+                  float* d_queues, int64_t* d_last_note, void* stream);
+int wn_gen_import(const wn_model* m, int32_t mode, int32_t n_streams, void* d_state,
+                  const float* d_queues, const int64_t* d_last_note, void* stream);
+
+/* ---- self tests of the tcgen05 / TMA building blocks (used by tests/, not by the product) -- */
+/* Runs D = A*B^T tiles through TMA -> UMMA -> TMEM -> registers for the operand layouts the
+ * kernels rely on; writes max |err| vs. an in-kernel fp32 SIMT product to h_maxerr[case]. */
+int wn_selftest_umma(float* h_maxerr, int32_t n_cases, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVENET_B200_H_ */

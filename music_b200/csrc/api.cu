@@ -1,0 +1,448 @@
+// api.cu - C-ABI entry points: lifecycle, model plan, weight packing, training forward/backward.
+// The fp32 check mode is orchestrated here from the generic kernels of check_kernels.cu; the bf16
+// tensor-core mode is dispatched to fast_*.cu.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "check_kernels.cuh"
+#include "common.cuh"
+#include "fast.cuh"
+
+namespace wn {
+
+int g_device = -1;
+int g_sm_count = 148;
+bool g_inited = false;
+
+static thread_local char t_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- fp32 packed image: per conv Wt[k][in][out], Wtt[k][out][in], bias copy ----
+static int64_t conv_elems(const ConvP& c) { return (int64_t)c.out * c.in * c.k; }
+
+std::vector<const ConvP*> all_convs(const Model& m) {
+  std::vector<const ConvP*> v;
+  v.push_back(&m.causal);
+  for (auto& l : m.layers) {
+    v.push_back(&l.filt);
+    v.push_back(&l.gate);
+    v.push_back(&l.dense);
+    v.push_back(&l.skip);
+  }
+  v.push_back(&m.post1);
+  v.push_back(&m.post2);
+  return v;
+}
+
+Pack32 pack32_of(const Model& m, const ConvP* target, int64_t* total) {
+  int64_t off = 0;
+  Pack32 res{-1, -1, -1};
+  for (const ConvP* c : all_convs(m)) {
+    Pack32 p;
+    p.wt = off;
+    off += conv_elems(*c);
+    p.wtt = off;
+    off += conv_elems(*c);
+    p.b = off;
+    off += (c->out + 3) / 4 * 4;
+    if (c == target) res = p;
+  }
+  if (total) *total = off;
+  return res;
+}
+
+// ---- fp32 workspace ----
+struct Ws32 {
+  float *X, *FG, *Z, *SK, *H1, *DX, *DZ, *DFG, *DSK, *DH1;
+  int64_t x_stride, fg_stride;   // per-layer strides (floats)
+  size_t bytes;
+};
+static Ws32 ws32_layout(const Model& m, int B, int L, void* base) {
+  const int W = L - m.rf + 1;
+  Ws32 w{};
+  size_t off = 0;
+  auto take = [&](int64_t n) {
+    float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+    off += align_up((size_t)n * sizeof(float), 256);
+    return p;
+  };
+  w.x_stride = (int64_t)align_up((size_t)B * L * m.R * sizeof(float), 256) / 4;
+  w.fg_stride = (int64_t)align_up((size_t)B * L * 2 * m.D * sizeof(float), 256) / 4;
+  w.X = take(w.x_stride * m.n_layers);
+  w.FG = take(w.fg_stride * m.n_layers);
+  w.Z = take((int64_t)B * L * m.D);
+  w.SK = take((int64_t)B * W * m.S);
+  w.H1 = take((int64_t)B * W * m.S);
+  w.DX = take((int64_t)B * L * m.R);
+  w.DZ = take((int64_t)B * L * m.D);
+  w.DFG = take((int64_t)B * L * 2 * m.D);
+  w.DSK = take((int64_t)B * W * m.S);
+  w.DH1 = take((int64_t)B * W * m.S);
+  w.bytes = off;
+  return w;
+}
+
+static TensorView tv(const float* p, int64_t sb, int64_t st, int64_t sc, int shift = 0) {
+  TensorView v;
+  v.p = p;
+  v.sb = sb;
+  v.st = st;
+  v.sc = sc;
+  v.shift = shift;
+  return v;
+}
+
+static int forward32(const Model& m, int B, int L, const float* d_x, const int64_t* d_idx, const float* P, void* ws, float* logits,
+                     cudaStream_t s) {
+  const int W = L - m.rf + 1, R = m.R, D = m.D, S = m.S, Q = m.Q, N = m.n_layers;
+  Ws32 w = ws32_layout(m, B, L, ws);
+  auto bias = [&](const ConvP& c) { return c.b >= 0 ? P + pack32_of(m, &c).b : nullptr; };
+  auto wt = [&](const ConvP& c) { return P + pack32_of(m, &c).wt; };
+  // causal layer (model.py:104)
+  if (d_idx) {
+    WN_PROPAGATE(launch_causal_idx_fwd(d_idx, wt(m.causal), bias(m.causal), w.X, B, L, R, Q, s));
+  } else {
+    PwArgs a;
+    a.X = tv(d_x, (int64_t)Q * L, 1, L);
+    a.x_lo = 0; a.x_hi = L; a.n_in = Q; a.n_taps = 2; a.off[0] = -1; a.off[1] = 0;
+    a.Wt = wt(m.causal); a.bias = bias(m.causal);
+    a.Y = tv(w.X, (int64_t)L * R, R, 1); a.n_out = R;
+    a.B = B; a.t0 = 1; a.t1 = L;
+    WN_PROPAGATE(launch_pw_gemm(a, s));
+  }
+  int s_in = 1;
+  for (int i = 0; i < N; ++i) {
+    const LayerP& l = m.layers[i];
+    const int d = l.dilation, s_out = s_in + d;
+    float* Xi = w.X + w.x_stride * i;
+    float* FGi = w.FG + w.fg_stride * i;
+    for (int part = 0; part < 2; ++part) {          // filter (model.py:118), gate (:119)
+      const ConvP& c = part == 0 ? l.filt : l.gate;
+      PwArgs a;
+      a.X = tv(Xi, (int64_t)L * R, R, 1);
+      a.x_lo = s_in; a.x_hi = L; a.n_in = R; a.n_taps = 2; a.off[0] = -d; a.off[1] = 0;
+      a.Wt = wt(c); a.bias = bias(c);
+      a.Y = tv(FGi + part * D, (int64_t)L * 2 * D, 2 * D, 1); a.n_out = D;
+      a.B = B; a.t0 = s_out; a.t1 = L;
+      WN_PROPAGATE(launch_pw_gemm(a, s));
+    }
+    WN_PROPAGATE(launch_gate_fwd(FGi, w.Z, B, L, D, s_out, L, s));     // :120
+    if (i + 1 < N) {                                                    // dense + residual (:121-124)
+      PwArgs a;
+      a.X = tv(w.Z, (int64_t)L * D, D, 1);
+      a.x_lo = s_out; a.x_hi = L; a.n_in = D;
+      a.Wt = wt(l.dense); a.bias = bias(l.dense);
+      a.Res = tv(Xi, (int64_t)L * R, R, 1);
+      a.Y = tv(w.X + w.x_stride * (i + 1), (int64_t)L * R, R, 1); a.n_out = R;
+      a.B = B; a.t0 = s_out; a.t1 = L;
+      WN_PROPAGATE(launch_pw_gemm(a, s));
+    }
+    {                                                                   // skip (:127-129), summed (:134)
+      PwArgs a;
+      a.X = tv(w.Z, (int64_t)L * D, D, 1);
+      a.x_lo = L - W; a.x_hi = L; a.n_in = D;
+      a.Wt = wt(l.skip); a.bias = bias(l.skip);
+      a.Y = tv(w.SK, (int64_t)W * S, S, 1, -(L - W)); a.n_out = S; a.accumulate = i > 0;
+      a.B = B; a.t0 = L - W; a.t1 = L;
+      WN_PROPAGATE(launch_pw_gemm(a, s));
+    }
+    s_in = s_out;
+  }
+  {   // relu -> post_process_1 (:135-136)
+    PwArgs a;
+    a.X = tv(w.SK, (int64_t)W * S, S, 1, -(L - W));
+    a.x_lo = L - W; a.x_hi = L; a.n_in = S; a.x_relu = 1;
+    a.Wt = wt(m.post1); a.bias = bias(m.post1);
+    a.Y = tv(w.H1, (int64_t)W * S, S, 1, -(L - W)); a.n_out = S;
+    a.B = B; a.t0 = L - W; a.t1 = L;
+    WN_PROPAGATE(launch_pw_gemm(a, s));
+  }
+  {   // relu -> post_process_2 (:137-138), written as (B,Q,W)
+    PwArgs a;
+    a.X = tv(w.H1, (int64_t)W * S, S, 1, -(L - W));
+    a.x_lo = L - W; a.x_hi = L; a.n_in = S; a.x_relu = 1;
+    a.Wt = wt(m.post2); a.bias = bias(m.post2);
+    a.Y = tv(logits, (int64_t)Q * W, 1, W, -(L - W)); a.n_out = Q;
+    a.B = B; a.t0 = L - W; a.t1 = L;
+    WN_PROPAGATE(launch_pw_gemm(a, s));
+  }
+  return WN_OK;
+}
+
+static int backward32(const Model& m, int B, int L, const float* d_x, const int64_t* d_idx, const float* P, void* ws,
+                      const float* dlogits, float* G, cudaStream_t s) {
+  const int W = L - m.rf + 1, R = m.R, D = m.D, S = m.S, Q = m.Q, N = m.n_layers;
+  Ws32 w = ws32_layout(m, B, L, ws);
+  auto wtt = [&](const ConvP& c) { return P + pack32_of(m, &c).wtt; };
+  WN_CHECK_CUDA(cudaMemsetAsync(G, 0, (size_t)m.n_params * sizeof(float), s));
+  const int tw = L - W;
+  TensorView dLg = tv(dlogits, (int64_t)Q * W, 1, W, -tw);
+  TensorView H1v = tv(w.H1, (int64_t)W * S, S, 1, -tw), SKv = tv(w.SK, (int64_t)W * S, S, 1, -tw);
+  TensorView DH1v = tv(w.DH1, (int64_t)W * S, S, 1, -tw), DSKv = tv(w.DSK, (int64_t)W * S, S, 1, -tw);
+  // post_process_2
+  {
+    WgArgs g;
+    g.X = H1v; g.x_lo = tw; g.x_hi = L; g.n_in = S; g.x_relu = 1;
+    g.dY = dLg; g.n_out = Q; g.dW = G + m.post2.w; g.s_out = S; g.s_in = 1;
+    g.B = B; g.t0 = tw; g.t1 = L;
+    WN_PROPAGATE(launch_wgrad(g, s));
+    if (m.post2.b >= 0) WN_PROPAGATE(launch_colsum(dLg, Q, B, tw, L, G + m.post2.b, s));
+    PwArgs a;
+    a.X = dLg; a.x_lo = tw; a.x_hi = L; a.n_in = Q; a.Wt = wtt(m.post2);
+    a.Mask = H1v; a.Y = DH1v; a.n_out = S; a.B = B; a.t0 = tw; a.t1 = L;
+    WN_PROPAGATE(launch_pw_gemm(a, s));
+  }
+  // post_process_1
+  {
+    WgArgs g;
+    g.X = SKv; g.x_lo = tw; g.x_hi = L; g.n_in = S; g.x_relu = 1;
+    g.dY = DH1v; g.n_out = S; g.dW = G + m.post1.w; g.s_out = S; g.s_in = 1;
+    g.B = B; g.t0 = tw; g.t1 = L;
+    WN_PROPAGATE(launch_wgrad(g, s));
+    if (m.post1.b >= 0) WN_PROPAGATE(launch_colsum(DH1v, S, B, tw, L, G + m.post1.b, s));
+    PwArgs a;
+    a.X = DH1v; a.x_lo = tw; a.x_hi = L; a.n_in = S; a.Wt = wtt(m.post1);
+    a.Mask = SKv; a.Y = DSKv; a.n_out = S; a.B = B; a.t0 = tw; a.t1 = L;
+    WN_PROPAGATE(launch_pw_gemm(a, s));
+  }
+  WN_CHECK_CUDA(cudaMemsetAsync(w.DX, 0, (size_t)B * L * R * sizeof(float), s));
+  TensorView DXv = tv(w.DX, (int64_t)L * R, R, 1), DZv = tv(w.DZ, (int64_t)L * D, D, 1), Zv = tv(w.Z, (int64_t)L * D, D, 1);
+  for (int i = N - 1; i >= 0; --i) {
+    const LayerP& l = m.layers[i];
+    const int d = l.dilation, s_out = l.start, s_in = s_out - d;
+    float* Xi = w.X + w.x_stride * i;
+    float* FGi = w.FG + w.fg_stride * i;
+    TensorView Xv = tv(Xi, (int64_t)L * R, R, 1);
+    // dZ = Wd^T dX_{i+1} + Ws^T dSkip
+    if (i + 1 < N) {
+      PwArgs a;
+      a.X = DXv; a.x_lo = s_out; a.x_hi = L; a.n_in = R; a.Wt = wtt(l.dense);
+      a.Y = DZv; a.n_out = D; a.B = B; a.t0 = s_out; a.t1 = L;
+      WN_PROPAGATE(launch_pw_gemm(a, s));
+    }
+    {
+      PwArgs a;
+      a.X = DSKv; a.x_lo = tw; a.x_hi = L; a.n_in = S; a.Wt = wtt(l.skip);
+      a.Y = DZv; a.n_out = D; a.accumulate = (i + 1 < N); a.B = B; a.t0 = tw; a.t1 = L;
+      WN_PROPAGATE(launch_pw_gemm(a, s));
+    }
+    WN_PROPAGATE(launch_gate_fwd(FGi, w.Z, B, L, D, s_out, L, s));     // recompute z
+    if (i + 1 < N) {
+      WgArgs g;
+      g.X = Zv; g.x_lo = s_out; g.x_hi = L; g.n_in = D; g.dY = DXv; g.n_out = R;
+      g.dW = G + l.dense.w; g.s_out = D; g.s_in = 1; g.B = B; g.t0 = s_out; g.t1 = L;
+      WN_PROPAGATE(launch_wgrad(g, s));
+      if (l.dense.b >= 0) WN_PROPAGATE(launch_colsum(DXv, R, B, s_out, L, G + l.dense.b, s));
+    }
+    {
+      WgArgs g;
+      g.X = Zv; g.x_lo = tw; g.x_hi = L; g.n_in = D; g.dY = DSKv; g.n_out = S;
+      g.dW = G + l.skip.w; g.s_out = D; g.s_in = 1; g.B = B; g.t0 = tw; g.t1 = L;
+      WN_PROPAGATE(launch_wgrad(g, s));
+      if (l.skip.b >= 0) WN_PROPAGATE(launch_colsum(DSKv, S, B, tw, L, G + l.skip.b, s));
+    }
+    WN_PROPAGATE(launch_gate_bwd(FGi, w.DZ, w.DFG, B, L, D, s_out, L, s));
+    for (int part = 0; part < 2; ++part) {
+      const ConvP& c = part == 0 ? l.filt : l.gate;
+      TensorView dFGv = tv(w.DFG + part * D, (int64_t)L * 2 * D, 2 * D, 1);
+      for (int tap = 0; tap < 2; ++tap) {
+        WgArgs g;
+        g.X = Xv; g.x_lo = s_in; g.x_hi = L; g.n_in = R; g.off = tap == 0 ? -d : 0;
+        g.dY = dFGv; g.n_out = D; g.dW = G + c.w + tap; g.s_out = (int64_t)R * 2; g.s_in = 2;
+        g.B = B; g.t0 = s_out; g.t1 = L;
+        WN_PROPAGATE(launch_wgrad(g, s));
+      }
+      if (c.b >= 0) WN_PROPAGATE(launch_colsum(dFGv, D, B, s_out, L, G + c.b, s));
+      // dX_i[tau] += W[:, :, 1]^T dFG[tau] + W[:, :, 0]^T dFG[tau + d]
+      PwArgs a;
+      a.X = dFGv; a.x_lo = s_out; a.x_hi = L; a.n_in = D; a.n_taps = 2; a.off[0] = d; a.off[1] = 0;
+      a.Wt = wtt(c); a.Y = DXv; a.n_out = R; a.accumulate = 1; a.B = B; a.t0 = s_in; a.t1 = L;
+      WN_PROPAGATE(launch_pw_gemm(a, s));
+    }
+  }
+  // causal layer
+  if (d_idx) {
+    WN_PROPAGATE(launch_causal_idx_bwd(d_idx, w.DX, G + m.causal.w, B, L, R, Q, s));
+  } else {
+    for (int tap = 0; tap < 2; ++tap) {
+      WgArgs g;
+      g.X = tv(d_x, (int64_t)Q * L, 1, L); g.x_lo = 0; g.x_hi = L; g.n_in = Q; g.off = tap == 0 ? -1 : 0;
+      g.dY = DXv; g.n_out = R; g.dW = G + m.causal.w + tap; g.s_out = (int64_t)Q * 2; g.s_in = 2;
+      g.B = B; g.t0 = 1; g.t1 = L;
+      WN_PROPAGATE(launch_wgrad(g, s));
+    }
+  }
+  if (m.causal.b >= 0) WN_PROPAGATE(launch_colsum(DXv, R, B, 1, L, G + m.causal.b, s));
+  return WN_OK;
+}
+
+}  // namespace wn
+
+using namespace wn;
+
+extern "C" int wn_version(void) { return 100; }
+extern "C" const char* wn_last_error(void) { return t_err; }
+
+extern "C" int wn_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("wn_init: no CUDA device visible (%s); libwavenet_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return WN_ERR_UNSUPPORTED;
+  }
+  WN_REQUIRE(device >= 0 && device < n, WN_ERR_INVALID, "wn_init: device %d out of range (%d visible)", device, n);
+  cudaDeviceProp p;
+  WN_CHECK_CUDA(cudaGetDeviceProperties(&p, device));
+  WN_REQUIRE(p.major == 10, WN_ERR_UNSUPPORTED, "wn_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
+             p.major, p.minor);
+  WN_CHECK_CUDA(cudaSetDevice(device));
+  g_device = device;
+  g_sm_count = p.multiProcessorCount;
+  WN_PROPAGATE(fast_init());
+  g_inited = true;
+  return WN_OK;
+}
+
+extern "C" int wn_model_create(const wn_config* cfg, wn_model** out) {
+  WN_REQUIRE(cfg && out, WN_ERR_INVALID, "wn_model_create: null argument");
+  WN_REQUIRE(cfg->filter_width == 2, WN_ERR_UNSUPPORTED, "wn_model_create: filter_width %d (only 2 is supported)", cfg->filter_width);
+  WN_REQUIRE(cfg->n_layers > 0 && cfg->dilations, WN_ERR_INVALID, "wn_model_create: no layers");
+  WN_REQUIRE(cfg->residual_channels > 0 && cfg->dilation_channels > 0 && cfg->skip_channels > 0 && cfg->quantization_channels > 1,
+             WN_ERR_INVALID, "wn_model_create: bad channel counts");
+  WN_REQUIRE(cfg->quantization_channels <= 1024, WN_ERR_UNSUPPORTED, "wn_model_create: Q > 1024");
+  wn_model* h = new wn_model();
+  Model& m = h->m;
+  m.n_layers = cfg->n_layers;
+  m.R = cfg->residual_channels;
+  m.D = cfg->dilation_channels;
+  m.S = cfg->skip_channels;
+  m.Q = cfg->quantization_channels;
+  m.use_bias = cfg->use_bias ? 1 : 0;
+  m.fw = 2;
+  int64_t off = 0;
+  auto add = [&](ConvP& c, int o, int i, int k) {
+    c.out = o; c.in = i; c.k = k;
+    c.w = off;
+    off += (int64_t)o * i * k;
+    if (m.use_bias) { c.b = off; off += o; }
+  };
+  add(m.causal, m.R, m.Q, 2);
+  int start = 1, sum = 0;
+  m.layers.resize(m.n_layers);
+  for (int i = 0; i < m.n_layers; ++i) {
+    int d = cfg->dilations[i];
+    if (d <= 0) { delete h; set_error("wn_model_create: dilation %d", d); return WN_ERR_INVALID; }
+    m.dil.push_back(d);
+    LayerP& l = m.layers[i];
+    l.dilation = d;
+    start += d;
+    sum += d;
+    l.start = start;
+    add(l.filt, m.D, m.R, 2);
+    add(l.gate, m.D, m.R, 2);
+    add(l.dense, m.R, m.D, 1);
+    add(l.skip, m.S, m.D, 1);
+  }
+  add(m.post1, m.S, m.S, 1);
+  add(m.post2, m.Q, m.S, 1);
+  m.n_params = off;
+  m.rf = sum + 2;          // (fw-1)*(sum+1)+1, model.py:43-44
+  m.fast_ok = fast_supported(m);
+  *out = h;
+  return WN_OK;
+}
+
+extern "C" int wn_model_destroy(wn_model* h) {
+  if (h) {
+    fast_release(h->m);
+    delete h;
+  }
+  return WN_OK;
+}
+extern "C" int64_t wn_model_param_count(const wn_model* h) { return h ? h->m.n_params : -1; }
+extern "C" int32_t wn_model_receptive_field(const wn_model* h) { return h ? h->m.rf : -1; }
+
+extern "C" int wn_packed_bytes(const wn_model* h, int32_t mode, size_t* bytes) {
+  WN_REQUIRE(h && bytes, WN_ERR_INVALID, "wn_packed_bytes: null argument");
+  if (mode == WN_MODE_FP32) {
+    int64_t total = 0;
+    pack32_of(h->m, nullptr, &total);
+    *bytes = (size_t)total * sizeof(float);
+    return WN_OK;
+  }
+  if (mode == WN_MODE_BF16) return fast_packed_bytes(h->m, bytes);
+  set_error("wn_packed_bytes: unknown mode %d", mode);
+  return WN_ERR_INVALID;
+}
+
+extern "C" int wn_pack_weights(wn_model* h, int32_t mode, const float* d_params, void* d_packed, void* stream) {
+  WN_REQUIRE(g_inited, WN_ERR_UNSUPPORTED, "wn_init() has not succeeded: no sm_100 device, no fallback");
+  WN_REQUIRE(h && d_params && d_packed, WN_ERR_INVALID, "wn_pack_weights: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const Model& m = h->m;
+  if (mode == WN_MODE_FP32) {
+    float* P = (float*)d_packed;
+    for (const ConvP* c : all_convs(m)) {
+      Pack32 p = pack32_of(m, c);
+      WN_PROPAGATE(launch_pack_f32(d_params + c->w, P + p.wt, P + p.wtt, c->out, c->in, c->k, s));
+      if (c->b >= 0) WN_CHECK_CUDA(cudaMemcpyAsync(P + p.b, d_params + c->b, c->out * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return WN_OK;
+  }
+  if (mode == WN_MODE_BF16) return fast_pack(h->m, d_params, d_packed, s);
+  set_error("wn_pack_weights: unknown mode %d", mode);
+  return WN_ERR_INVALID;
+}
+
+static int check_shape(const Model& m, int B, int L) {
+  WN_REQUIRE(B > 0 && L > 0, WN_ERR_INVALID, "bad batch/length B=%d L=%d", B, L);
+  WN_REQUIRE(L - m.rf + 1 > 0, WN_ERR_SHAPE, "wave sample not long enough");   // model.py:100-101
+  return WN_OK;
+}
+
+extern "C" int wn_workspace_bytes(const wn_model* h, int32_t mode, int32_t B, int32_t L, size_t* bytes) {
+  WN_REQUIRE(h && bytes, WN_ERR_INVALID, "wn_workspace_bytes: null argument");
+  WN_PROPAGATE(check_shape(h->m, B, L));
+  if (mode == WN_MODE_FP32) {
+    *bytes = ws32_layout(h->m, B, L, nullptr).bytes;
+    return WN_OK;
+  }
+  if (mode == WN_MODE_BF16) return fast_workspace_bytes(h->m, B, L, bytes);
+  set_error("wn_workspace_bytes: unknown mode %d", mode);
+  return WN_ERR_INVALID;
+}
+
+extern "C" int wn_forward(wn_model* h, int32_t mode, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx,
+                          const void* d_packed, void* d_workspace, float* d_logits, void* stream) {
+  WN_REQUIRE(g_inited, WN_ERR_UNSUPPORTED, "wn_init() has not succeeded: no sm_100 device, no fallback");
+  WN_REQUIRE(h && d_packed && d_workspace && d_logits, WN_ERR_INVALID, "wn_forward: null argument");
+  WN_REQUIRE((d_x != nullptr) != (d_idx != nullptr), WN_ERR_INVALID, "wn_forward: exactly one of d_x / d_idx must be given");
+  WN_PROPAGATE(check_shape(h->m, B, L));
+  if (mode == WN_MODE_FP32) return forward32(h->m, B, L, d_x, d_idx, (const float*)d_packed, d_workspace, d_logits, (cudaStream_t)stream);
+  if (mode == WN_MODE_BF16) return fast_forward(h->m, B, L, d_x, d_idx, d_packed, d_workspace, d_logits, (cudaStream_t)stream);
+  set_error("wn_forward: unknown mode %d", mode);
+  return WN_ERR_INVALID;
+}
+
+extern "C" int wn_backward(wn_model* h, int32_t mode, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx,
+                           const void* d_packed, void* d_workspace, float* d_dlogits, float* d_grads, void* stream) {
+  WN_REQUIRE(g_inited, WN_ERR_UNSUPPORTED, "wn_init() has not succeeded: no sm_100 device, no fallback");
+  WN_REQUIRE(h && d_packed && d_workspace && d_dlogits && d_grads, WN_ERR_INVALID, "wn_backward: null argument");
+  WN_REQUIRE((d_x != nullptr) != (d_idx != nullptr), WN_ERR_INVALID, "wn_backward: exactly one of d_x / d_idx must be given");
+  WN_PROPAGATE(check_shape(h->m, B, L));
+  if (mode == WN_MODE_FP32)
+    return backward32(h->m, B, L, d_x, d_idx, (const float*)d_packed, d_workspace, d_dlogits, d_grads, (cudaStream_t)stream);
+  if (mode == WN_MODE_BF16)
+    return fast_backward(h->m, B, L, d_x, d_idx, d_packed, d_workspace, d_dlogits, d_grads, (cudaStream_t)stream);
+  set_error("wn_backward: unknown mode %d", mode);
+  return WN_ERR_INVALID;
+}

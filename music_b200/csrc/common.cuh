@@ -1,0 +1,84 @@
+// common.cuh - shared host/device helpers for libwavenet_b200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/wavenet_b200.h"
+
+namespace wn {
+
+void set_error(const char* fmt, ...);
+
+#define WN_CHECK_CUDA(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      wn::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return WN_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define WN_CHECK_LAUNCH() WN_CHECK_CUDA(cudaGetLastError())
+
+#define WN_REQUIRE(cond, code, ...)   \
+  do {                                \
+    if (!(cond)) {                    \
+      wn::set_error(__VA_ARGS__);     \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define WN_PROPAGATE(expr)      \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != WN_OK) return _s; \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- parameter table: offsets into the flat fp32 vector (reference state_dict order) ----
+struct ConvP {
+  int64_t w = -1;   // offset of weight (out,in,k)
+  int64_t b = -1;   // offset of bias (out) or -1
+  int out = 0, in = 0, k = 0;
+};
+
+struct LayerP {
+  ConvP filt, gate, dense, skip;
+  int dilation = 1;
+  int start = 0;   // first valid absolute time index of this layer's OUTPUT (s_{i+1})
+};
+
+struct Model {
+  int n_layers = 0, R = 0, D = 0, S = 0, Q = 0, use_bias = 0, fw = 2;
+  std::vector<int> dil;
+  ConvP causal, post1, post2;
+  std::vector<LayerP> layers;
+  int64_t n_params = 0;
+  int rf = 0;
+  bool fast_ok = false;   // shapes supported by the tcgen05 kernels
+  void* tmaps = nullptr;  // FastPlan cache (fast_plan.cu)
+};
+
+// fp32 packed image: per conv Wt[k][in][out], Wtt[k][out][in], bias copy (offsets in floats)
+struct Pack32 {
+  int64_t wt, wtt, b;
+};
+std::vector<const ConvP*> all_convs(const Model& m);
+Pack32 pack32_of(const Model& m, const ConvP* target, int64_t* total = nullptr);
+
+extern int g_device;
+extern int g_sm_count;
+extern bool g_inited;
+
+}  // namespace wn
+
+struct wn_model {
+  wn::Model m;
+};

@@ -1,0 +1,398 @@
+// fast_fwd.cu - bf16 tensor-core forward of the WaveNet stack (R = D = 64, S = Q = 256).
+//
+// block_fwd_kernel  : one residual block (wavenet/model.py:118-129) for a [128 time x 64 ch] tile:
+//     TMA: x_i[tau-d], x_i[tau] tiles + W_fg (both taps) + W_dense          -> shared memory (SW128)
+//     UMMA #1 (M128 N128 K128): [f|g] = x[tau-d] W0^T + x[tau] W1^T         -> TMEM cols [0,128)
+//     epilogue #1: z = sigmoid(g) * tanh(f) -> bf16 -> shared (A operand of #2) and TMA-stored into
+//                  the skip operand matrix Zcat[:, 64 i : 64 i + 64] for rows in the last W
+//     UMMA #2 (M128 N64 K64): dense = z Wd^T                                -> TMEM cols [128,192)
+//     epilogue #2: x_{i+1} = dense + x_i[tau] (residual read back from the shared x tile) -> TMA store
+// skip_head_kernel  : for a [128 rows of B*W] tile, chained GEMMs with TMEM-resident accumulators
+//     acc1 = Zcat[128 x 64N] Wskip_cat^T  (= sum_i skip_i, model.py:127-134; K = 64 N_layers)
+//     h0 = relu(acc1) -> smem/HBM ; acc2 = h0 P1^T ; h1 = relu(acc2) -> smem/HBM ; acc1 = h1 P2^T
+//     logits (fp32) -> (B,Q,W).   Warp-specialised: warps 0-3 epilogue, warp 4 TMA, warp 5 MMA.
+#include "fast_kernels.cuh"
+#include "tc05.cuh"
+
+namespace wn {
+using namespace tc;
+
+// ======================================================================================= block
+namespace {
+
+constexpr int BF_THREADS = 128;
+constexpr uint32_t TILE_BYTES = 128 * 128;     // [128 rows][64 bf16]
+constexpr uint32_t WD_BYTES = 64 * 128;
+
+struct BlockSmem {
+  // offsets from the 1024-aligned base
+  static constexpr uint32_t A0 = 0, A1 = TILE_BYTES, W0 = 2 * TILE_BYTES, W1 = 3 * TILE_BYTES, WD = 4 * TILE_BYTES,
+                            Z = 4 * TILE_BYTES + WD_BYTES, TOTAL = 5 * TILE_BYTES + WD_BYTES;
+};
+
+__global__ void __launch_bounds__(BF_THREADS, 2)
+block_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_xo,
+                 const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+                 const __grid_constant__ CUtensorMap tm_wd, const __grid_constant__ CUtensorMap tm_z, BlockFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar_ld, bar_m1, bar_m2;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.x / p.tiles_per_batch;
+  const int tile = p.tile0 + blockIdx.x % p.tiles_per_batch;
+  const int tau0 = tile * 128;
+
+  if (tid == 0) {
+    mbar_init(&bar_ld, 1);
+    mbar_init(&bar_m1, 1);
+    mbar_init(&bar_m2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t sbase = smem_u32(sm);
+
+  if (tid == 0) {
+    mbar_expect_tx(&bar_ld, 4 * TILE_BYTES + (p.has_dense ? WD_BYTES : 0));
+    tma_load_3d(sm + BlockSmem::A0, &tm_x, &bar_ld, 0, tau0 - p.d, b);
+    tma_load_3d(sm + BlockSmem::A1, &tm_x, &bar_ld, 0, tau0, b);
+    tma_load_2d(sm + BlockSmem::W0, &tm_w0, &bar_ld, 0, 0);
+    tma_load_2d(sm + BlockSmem::W1, &tm_w1, &bar_ld, 0, 0);
+    if (p.has_dense) tma_load_2d(sm + BlockSmem::WD, &tm_wd, &bar_ld, 0, 0);
+    mbar_wait(&bar_ld, 0);
+    tc_fence_after();
+    constexpr uint32_t id1 = idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem, desc_kmajor(sbase + BlockSmem::A0, k), desc_kmajor(sbase + BlockSmem::W0, k), id1, k > 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem, desc_kmajor(sbase + BlockSmem::A1, k), desc_kmajor(sbase + BlockSmem::W1, k), id1, true);
+    umma_commit(&bar_m1);
+  }
+  __syncwarp();
+
+  // ---- epilogue 1: gate ----
+  mbar_wait(&bar_m1, 0);
+  tc_fence_after();
+  const int row = tid;                       // TMEM lane == tile row
+  const int tau = tau0 + row;
+  const bool valid = (tau >= p.s_out) && (tau < p.L);
+  const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t f[32], g[32];
+    tmem_ld32(lane_addr + c * 32, f);
+    tmem_ld32(lane_addr + 64 + c * 32, g);
+    tmem_ld_wait();
+    uint32_t packed[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float f0 = __uint_as_float(f[2 * j]), f1 = __uint_as_float(f[2 * j + 1]);
+      float g0 = __uint_as_float(g[2 * j]), g1 = __uint_as_float(g[2 * j + 1]);
+      if (p.bias_fg) {
+        f0 += p.bias_fg[c * 32 + 2 * j];
+        f1 += p.bias_fg[c * 32 + 2 * j + 1];
+        g0 += p.bias_fg[64 + c * 32 + 2 * j];
+        g1 += p.bias_fg[64 + c * 32 + 2 * j + 1];
+      }
+      float z0 = valid ? sigmoid_fast(g0) * tanh_fast(f0) : 0.f;
+      float z1 = valid ? sigmoid_fast(g1) * tanh_fast(f1) : 0.f;
+      packed[j] = pack_bf16(z0, z1);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 v = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+      *reinterpret_cast<uint4*>(sm + BlockSmem::Z + sw128_chunk(row, c * 4 + q)) = v;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc_fence_after();
+    if (p.has_dense) {
+      constexpr uint32_t id2 = idesc_bf16(128, 64, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem + 128, desc_kmajor(sbase + BlockSmem::Z, k), desc_kmajor(sbase + BlockSmem::WD, k), id2, k > 0);
+      umma_commit(&bar_m2);
+    }
+    if (tau0 + 128 > p.tw0) {   // tile touches the last W time steps: z feeds the skip GEMM
+      tma_store_3d(&tm_z, sm + BlockSmem::Z, p.zcol, tau0 - p.tw0, b);
+      tma_store_commit();
+    }
+  }
+  __syncwarp();
+
+  // ---- epilogue 2: dense + residual ----
+  if (p.has_dense) {
+    mbar_wait(&bar_m2, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t dv[32];
+      tmem_ld32(lane_addr + 128 + c * 32, dv);
+      tmem_ld_wait();
+      uint32_t packed[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(sm + BlockSmem::A1 + sw128_chunk(row, c * 4 + q));
+        const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * q + e;     // pair index inside this 32-col chunk
+          __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
+          float x0 = __uint_as_float(dv[2 * j]) + __low2float(r2);
+          float x1 = __uint_as_float(dv[2 * j + 1]) + __high2float(r2);
+          if (p.bias_d) {
+            x0 += p.bias_d[c * 32 + 2 * j];
+            x1 += p.bias_d[c * 32 + 2 * j + 1];
+          }
+          packed[j] = valid ? pack_bf16(x0, x1) : 0u;
+        }
+      }
+      // stage x_{i+1} in the (now free) tap-0 tile
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 v = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + BlockSmem::A0 + sw128_chunk(row, c * 4 + q)) = v;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_3d(&tm_xo, sm + BlockSmem::A0, 0, tau0, b);
+      tma_store_commit();
+    }
+  }
+  if (tid == 0) tma_store_wait_read();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+}  // namespace
+
+int launch_block_fwd(const BlockFwdMaps& m, const BlockFwdParams& p, int n_ctas, cudaStream_t s) {
+  static bool attr_set = false;
+  const int smem = BlockSmem::TOTAL + 1024;
+  if (!attr_set) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  block_fwd_kernel<<<n_ctas, BF_THREADS, smem, s>>>(m.x, m.xo, m.w0, m.w1, m.wd, m.z, p);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+// ================================================================================== skip + head
+namespace {
+
+constexpr int SH_THREADS = 192;
+constexpr int SH_STAGES = 3;
+constexpr uint32_t SH_A_BYTES = TILE_BYTES;          // [128][64]
+constexpr uint32_t SH_B_BYTES = 256 * 128;           // [256][64]
+constexpr uint32_t SH_STAGE_BYTES = SH_A_BYTES + SH_B_BYTES;
+constexpr uint32_t SH_H_OFF = SH_STAGES * SH_STAGE_BYTES;
+constexpr uint32_t SH_TOTAL = SH_H_OFF + 4 * TILE_BYTES;
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(SH_THREADS, 1)
+skip_head_kernel(const __grid_constant__ CUtensorMap tm_zcat, const __grid_constant__ CUtensorMap tm_wsk,
+                 const __grid_constant__ CUtensorMap tm_p1, const __grid_constant__ CUtensorMap tm_p2,
+                 const __grid_constant__ CUtensorMap tm_h0, const __grid_constant__ CUtensorMap tm_h1, SkipHeadParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full[SH_STAGES], empty[SH_STAGES];
+  __shared__ __align__(8) uint64_t acc_full[3], h_ready[2], tmem_free;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < SH_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) mbar_init(&acc_full[i], 1);
+    mbar_init(&h_ready[0], 1);
+    mbar_init(&h_ready[1], 1);
+    mbar_init(&tmem_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t sbase = smem_u32(sm);
+  const int kc_skip = p.k_skip / 64;
+
+  if (warp == 4) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int row0 = tile * 128;
+        for (int kc = 0; kc < kc_skip + 8; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = sm + stage * SH_STAGE_BYTES;
+          uint8_t* sb = sa + SH_A_BYTES;
+          if (kc < kc_skip) {
+            mbar_expect_tx(&full[stage], SH_STAGE_BYTES);
+            tma_load_2d(sa, &tm_zcat, &full[stage], kc * 64, row0);
+            tma_load_2d(sb, &tm_wsk, &full[stage], kc * 64, 0);
+          } else {
+            mbar_expect_tx(&full[stage], SH_B_BYTES);
+            const int k2 = kc - kc_skip;
+            tma_load_2d(sb, k2 < 4 ? &tm_p1 : &tm_p2, &full[stage], (k2 & 3) * 64, 0);
+          }
+          if (++stage == SH_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      constexpr uint32_t idn = idesc_bf16(128, 256, 0, 0);
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t tph = it & 1;
+        mbar_wait(&tmem_free, tph ^ 1);            // epilogue of the previous tile has drained acc1
+        tc_fence_after();
+        for (int kc = 0; kc < kc_skip; ++kc) {     // acc1 = Zcat * Wskip_cat^T
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * SH_STAGE_BYTES, sb = sa + SH_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_kmajor(sa, k), desc_kmajor(sb, k), idn, (kc | k) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == SH_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[0]);
+        for (int g = 0; g < 2; ++g) {              // acc2 = h0 P1^T ; acc1 = h1 P2^T
+          mbar_wait(&h_ready[g], tph);
+          tc_fence_after();
+          const uint32_t dst = g == 0 ? tmem + 256 : tmem;
+          for (int kc = 0; kc < 4; ++kc) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = sbase + SH_H_OFF + kc * TILE_BYTES;
+            const uint32_t sb = sbase + stage * SH_STAGE_BYTES + SH_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(dst, desc_kmajor(sa, k), desc_kmajor(sb, k), idn, (kc | k) != 0);
+            umma_commit(&empty[stage]);
+            if (++stage == SH_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&acc_full[1 + g]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps 0-3
+    uint32_t it = 0;
+    const int row = tid;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t tph = it & 1;
+      const int row0 = tile * 128;
+      const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
+      for (int g = 0; g < 2; ++g) {
+        // relu(acc) -> bf16 H tile in shared memory (A operand of the next GEMM) and to HBM for backward
+        mbar_wait(&acc_full[g], tph);
+        tc_fence_after();
+        const uint32_t src = lane_addr + (g == 0 ? 0 : 256);
+        const float* bias = g == 0 ? p.bias_skip : p.bias_p1;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t v[32];
+          tmem_ld32(src + c * 32, v);
+          tmem_ld_wait();
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
+            if (bias) {
+              a0 += bias[c * 32 + 2 * j];
+              a1 += bias[c * 32 + 2 * j + 1];
+            }
+            packed[j] = pack_bf16(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+          }
+          uint8_t* ht = sm + SH_H_OFF + (c >> 1) * TILE_BYTES;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 val = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            *reinterpret_cast<uint4*>(ht + sw128_chunk(row, (c & 1) * 4 + q)) = val;
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        epi_bar_sync();
+        if (tid == 0) {
+          mbar_arrive(&h_ready[g]);
+          for (int kc = 0; kc < 4; ++kc)
+            tma_store_2d(g == 0 ? &tm_h0 : &tm_h1, sm + SH_H_OFF + kc * TILE_BYTES, kc * 64, row0);
+          tma_store_commit();
+          tma_store_wait_read();       // H tile may be overwritten once the stores have read it ...
+        }
+        // ... and once the GEMM that consumes it has completed (acc_full[g+1], waited below / next loop)
+        if (g == 0) {
+          // nothing: epilogue g=1 waits acc_full[1], which implies the MMAs reading h0 are done
+        }
+        epi_bar_sync();
+      }
+      // logits
+      mbar_wait(&acc_full[2], tph);
+      tc_fence_after();
+      const int r = row0 + row;
+      const bool ok = r < p.n_rows;
+      const int bb = ok ? r / p.W : 0, tw = ok ? r % p.W : 0;
+      float* out = p.logits + ((int64_t)bb * p.Q) * p.W + tw;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(v[j]);
+            if (p.bias_p2) a += p.bias_p2[c * 32 + j];
+            out[(int64_t)(c * 32 + j) * p.W] = a;
+          }
+        }
+      }
+      tc_fence_before();
+      epi_bar_sync();
+      if (tid == 0) mbar_arrive(&tmem_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+int launch_skip_head(const SkipHeadMaps& m, const SkipHeadParams& p, cudaStream_t s) {
+  static bool attr_set = false;
+  const int smem = SH_TOTAL + 1024;
+  if (!attr_set) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(skip_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  int grid = std::min(p.n_tiles, g_sm_count);
+  skip_head_kernel<<<grid, SH_THREADS, smem, s>>>(m.zcat, m.wsk, m.p1, m.p2, m.h0, m.h1, p);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+}  // namespace wn

@@ -1,0 +1,425 @@
+// fast_host.cu - host side of the bf16 tensor-core path: driver entry points, weight packing,
+// workspace layout, TMA descriptor cache and the forward / backward launch sequences.
+#include <map>
+#include <tuple>
+
+#include "check_kernels.cuh"
+#include "fast.cuh"
+#include "fast_kernels.cuh"
+#include "fast_layout.cuh"
+
+namespace wn {
+
+// ------------------------------------------------------------------ driver entry point
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled g_encode = nullptr;
+
+int fast_init() {
+  if (g_encode) return WN_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  WN_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  WN_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, WN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  g_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
+  return WN_OK;
+}
+
+// bf16 tensor map, rank 2 or 3, innermost box = 64 elements (128 B) with 128B swizzle
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
+  WN_REQUIRE(g_encode, WN_ERR_UNSUPPORTED, "fast path not initialised (wn_init)");
+  cuuint64_t gd[3], gs[2];
+  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WN_REQUIRE(r == CUDA_SUCCESS, WN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu box=%u,%u", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+  return WN_OK;
+}
+
+int tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems, uint32_t box_rows) {
+  uint64_t dims[2] = {cols, rows}, strides[1] = {pitch_elems * 2};
+  uint32_t box[2] = {64, box_rows};
+  return make_tmap(out, base, 2, dims, strides, box);
+}
+int tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batches, uint64_t pitch_elems,
+            uint64_t batch_pitch_elems, uint32_t box_rows) {
+  uint64_t dims[3] = {cols, rows, batches}, strides[2] = {pitch_elems * 2, batch_pitch_elems * 2};
+  uint32_t box[3] = {64, box_rows, 1};
+  return make_tmap(out, base, 3, dims, strides, box);
+}
+
+bool fast_supported(const Model& m) {
+  return m.R == 64 && m.D == 64 && m.S == 256 && m.Q == 256 && m.n_layers >= 1 && m.n_layers <= 64;
+}
+
+static int require_supported(const Model& m) {
+  WN_REQUIRE(fast_supported(m), WN_ERR_UNSUPPORTED,
+             "bf16 tensor-core mode is specialised for residual=dilation=64, skip=quantization=256 channels "
+             "(got R=%d D=%d S=%d Q=%d); use mode fp32 for other shapes",
+             m.R, m.D, m.S, m.Q);
+  return WN_OK;
+}
+
+// ------------------------------------------------------------------ packed image
+PackLayout pack_layout(const Model& m) {
+  PackLayout p{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 1024);
+    return o;
+  };
+  const int N = m.n_layers;
+  p.jobs = take(sizeof(PackJob) * (size_t)(16 * N + 32) + sizeof(int64_t) * (size_t)N);
+  p.wc_t = take((size_t)2 * m.Q * m.R * 4);
+  p.bias_c = take(64 * 4);
+  p.bias_fg = take((size_t)N * 128 * 4);
+  p.bias_d = take((size_t)N * 64 * 4);
+  p.bias_skip = take(256 * 4);
+  p.bias_p1 = take(256 * 4);
+  p.bias_p2 = take(256 * 4);
+  p.wfg0 = take((size_t)N * 128 * 64 * 2);
+  p.wfg1 = take((size_t)N * 128 * 64 * 2);
+  p.wd = take((size_t)N * 64 * 64 * 2);
+  p.wscat = take((size_t)256 * 64 * N * 2);
+  p.p1 = take(256 * 256 * 2);
+  p.p2 = take(256 * 256 * 2);
+  // transposed images for the data-gradient GEMMs
+  p.wfgT0 = take((size_t)N * 64 * 128 * 2);     // [64 r][128 o]
+  p.wfgT1 = take((size_t)N * 64 * 128 * 2);
+  p.wdT = take((size_t)N * 64 * 64 * 2);        // [64 d][64 r]
+  p.wsT = take((size_t)N * 64 * 256 * 2);       // [64 d][256 s]
+  p.p1T = take(256 * 256 * 2);
+  p.p2T = take(256 * 256 * 2);
+  p.total = off;
+  return p;
+}
+
+int fast_packed_bytes(const Model& m, size_t* bytes) {
+  WN_PROPAGATE(require_supported(m));
+  *bytes = pack_layout(m).total;
+  return WN_OK;
+}
+
+namespace {
+
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restrict__ jobs, const float* __restrict__ params,
+                                                        uint8_t* __restrict__ packed) {
+  const PackJob j = jobs[blockIdx.y];
+  const int64_t n = (int64_t)j.out * j.in;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(e / j.in), i = (int)(e % j.in);
+    if (j.kind == PJ_BF16 || j.kind == PJ_BF16_T) {
+      const float v = params[j.src + ((int64_t)o * j.in + i) * j.k + j.tap];
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(packed + j.dst);
+      if (j.kind == PJ_BF16) dst[(int64_t)(j.row0 + o) * j.pitch + j.col0 + i] = __float2bfloat16(v);
+      else dst[(int64_t)(j.row0 + i) * j.pitch + j.col0 + o] = __float2bfloat16(v);
+    } else if (j.kind == PJ_F32_T) {       // (out,in,k) -> [tap][in][out] fp32
+      const float v = params[j.src + ((int64_t)o * j.in + i) * j.k + j.tap];
+      reinterpret_cast<float*>(packed + j.dst)[((int64_t)j.tap * j.in + i) * j.out + o] = v;
+    } else if (j.kind == PJ_COPY) {        // bias copy: out floats (in == 1)
+      reinterpret_cast<float*>(packed + j.dst)[j.col0 + o] = params[j.src + o];
+    }
+  }
+}
+
+// skip biases summed over layers (the skip contributions are summed, model.py:134)
+__global__ void bias_skip_sum_kernel(const float* __restrict__ params, const int64_t* __restrict__ offs, int n_layers,
+                                     float* __restrict__ out) {
+  int s = threadIdx.x;
+  float acc = 0.f;
+  for (int i = 0; i < n_layers; ++i) acc += params[offs[i] + s];
+  out[s] = acc;
+}
+
+}  // namespace
+
+struct FastPlan {
+  std::vector<PackJob> jobs;
+  const void* jobs_uploaded_to = nullptr;
+  // tensor-map cache
+  const void* key_ws = nullptr;
+  const void* key_packed = nullptr;
+  int key_B = 0, key_L = 0;
+  std::vector<BlockFwdMaps> block;
+  SkipHeadMaps head;
+  BwdMaps bwd;
+};
+
+static FastPlan* plan_of(Model& m) {
+  if (!m.tmaps) m.tmaps = new FastPlan();
+  return reinterpret_cast<FastPlan*>(m.tmaps);
+}
+void fast_release(Model& m) {
+  if (m.tmaps) delete reinterpret_cast<FastPlan*>(m.tmaps);
+  m.tmaps = nullptr;
+}
+
+static void build_jobs(const Model& m, const PackLayout& pl, std::vector<PackJob>& jobs) {
+  jobs.clear();
+  auto add = [&](int kind, const ConvP& c, int tap, size_t dst, int pitch, int row0, int col0) {
+    PackJob j{};
+    j.kind = kind; j.src = c.w; j.out = c.out; j.in = c.in; j.k = c.k; j.tap = tap;
+    j.dst = (int64_t)dst; j.pitch = pitch; j.row0 = row0; j.col0 = col0;
+    jobs.push_back(j);
+  };
+  auto add_bias = [&](const ConvP& c, size_t dst, int col0) {
+    if (c.b < 0) return;
+    PackJob j{};
+    j.kind = PJ_COPY; j.src = c.b; j.out = c.out; j.in = 1; j.k = 1; j.dst = (int64_t)dst; j.col0 = col0;
+    jobs.push_back(j);
+  };
+  const int N = m.n_layers;
+  add(PJ_F32_T, m.causal, 0, pl.wc_t, 0, 0, 0);
+  add(PJ_F32_T, m.causal, 1, pl.wc_t, 0, 0, 0);
+  add_bias(m.causal, pl.bias_c, 0);
+  for (int i = 0; i < N; ++i) {
+    const LayerP& l = m.layers[i];
+    const size_t w0 = pl.wfg0 + (size_t)i * 128 * 64 * 2, w1 = pl.wfg1 + (size_t)i * 128 * 64 * 2;
+    add(PJ_BF16, l.filt, 0, w0, 64, 0, 0);
+    add(PJ_BF16, l.gate, 0, w0, 64, 64, 0);
+    add(PJ_BF16, l.filt, 1, w1, 64, 0, 0);
+    add(PJ_BF16, l.gate, 1, w1, 64, 64, 0);
+    add(PJ_BF16, l.dense, 0, pl.wd + (size_t)i * 64 * 64 * 2, 64, 0, 0);
+    add(PJ_BF16, l.skip, 0, pl.wscat, 64 * N, 0, 64 * i);
+    // transposes: [in][out]
+    const size_t t0 = pl.wfgT0 + (size_t)i * 64 * 128 * 2, t1 = pl.wfgT1 + (size_t)i * 64 * 128 * 2;
+    add(PJ_BF16_T, l.filt, 0, t0, 128, 0, 0);
+    add(PJ_BF16_T, l.gate, 0, t0, 128, 0, 64);
+    add(PJ_BF16_T, l.filt, 1, t1, 128, 0, 0);
+    add(PJ_BF16_T, l.gate, 1, t1, 128, 0, 64);
+    add(PJ_BF16_T, l.dense, 0, pl.wdT + (size_t)i * 64 * 64 * 2, 64, 0, 0);
+    add(PJ_BF16_T, l.skip, 0, pl.wsT + (size_t)i * 64 * 256 * 2, 256, 0, 0);
+    add_bias(l.filt, pl.bias_fg, i * 128);
+    add_bias(l.gate, pl.bias_fg, i * 128 + 64);
+    add_bias(l.dense, pl.bias_d, i * 64);
+  }
+  add(PJ_BF16, m.post1, 0, pl.p1, 256, 0, 0);
+  add(PJ_BF16, m.post2, 0, pl.p2, 256, 0, 0);
+  add(PJ_BF16_T, m.post1, 0, pl.p1T, 256, 0, 0);
+  add(PJ_BF16_T, m.post2, 0, pl.p2T, 256, 0, 0);
+  add_bias(m.post1, pl.bias_p1, 0);
+  add_bias(m.post2, pl.bias_p2, 0);
+}
+
+int fast_pack(Model& m, const float* d_params, void* d_packed, cudaStream_t s) {
+  WN_PROPAGATE(require_supported(m));
+  FastPlan* fp = plan_of(m);
+  const PackLayout pl = pack_layout(m);
+  uint8_t* P = reinterpret_cast<uint8_t*>(d_packed);
+  if (fp->jobs.empty()) build_jobs(m, pl, fp->jobs);
+  WN_REQUIRE(fp->jobs.size() <= (size_t)(16 * m.n_layers + 32), WN_ERR_INVALID, "pack job table overflow");
+  if (fp->jobs_uploaded_to != d_packed) {
+    // the job table is a constant of (model, packed buffer): uploaded once per buffer
+    WN_CHECK_CUDA(cudaMemcpyAsync(P + pl.jobs, fp->jobs.data(), fp->jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, s));
+    if (m.use_bias) {
+      std::vector<int64_t> offs;
+      for (auto& l : m.layers) offs.push_back(l.skip.b);
+      // skip-bias offsets live right behind the job table
+      WN_CHECK_CUDA(cudaMemcpyAsync(P + pl.jobs + fp->jobs.size() * sizeof(PackJob), offs.data(), offs.size() * sizeof(int64_t),
+                                    cudaMemcpyHostToDevice, s));
+    }
+    fp->jobs_uploaded_to = d_packed;
+  }
+  dim3 grid(16, (unsigned)fp->jobs.size());
+  pack_jobs_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const PackJob*>(P + pl.jobs), d_params, P);
+  WN_CHECK_LAUNCH();
+  if (m.use_bias) {
+    bias_skip_sum_kernel<<<1, 256, 0, s>>>(d_params, reinterpret_cast<const int64_t*>(P + pl.jobs + fp->jobs.size() * sizeof(PackJob)),
+                                           m.n_layers, reinterpret_cast<float*>(P + pl.bias_skip));
+    WN_CHECK_LAUNCH();
+  }
+  return WN_OK;
+}
+
+// ------------------------------------------------------------------ workspace
+WsLayout ws_layout(const Model& m, int B, int L) {
+  WsLayout w{};
+  const int W = L - m.rf + 1, N = m.n_layers;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 1024);
+    return o;
+  };
+  w.x_stride = align_up((size_t)B * L * 64 * 2, 1024);
+  w.X = take(w.x_stride * N);
+  w.Zcat = take((size_t)B * W * 64 * N * 2);
+  w.H0 = take((size_t)B * W * 256 * 2);
+  w.H1 = take((size_t)B * W * 256 * 2);
+  w.X0f = take((size_t)B * L * 64 * 4);         // fp32 causal output (dense-input path only)
+  // backward
+  w.DLG = take((size_t)B * W * 256 * 2);
+  w.DH1 = take((size_t)B * W * 256 * 2);
+  w.DSK = take((size_t)B * W * 256 * 2);
+  w.DXa = take((size_t)B * L * 64 * 2);
+  w.DXb = take((size_t)B * L * 64 * 2);
+  w.DFG = take((size_t)B * L * 128 * 2);
+  w.Zf = take((size_t)B * L * 64 * 2);
+  w.DX0f = take((size_t)B * L * 64 * 4);
+  w.total = off;
+  return w;
+}
+
+int fast_workspace_bytes(const Model& m, int B, int L, size_t* bytes) {
+  WN_PROPAGATE(require_supported(m));
+  *bytes = ws_layout(m, B, L).total;
+  return WN_OK;
+}
+
+// ------------------------------------------------------------------ tensor maps
+static int build_maps(Model& m, FastPlan* fp, int B, int L, const void* d_packed, void* d_ws) {
+  if (fp->key_ws == d_ws && fp->key_packed == d_packed && fp->key_B == B && fp->key_L == L) return WN_OK;
+  const PackLayout pl = pack_layout(m);
+  const WsLayout wl = ws_layout(m, B, L);
+  const int W = L - m.rf + 1, N = m.n_layers;
+  const uint8_t* P = reinterpret_cast<const uint8_t*>(d_packed);
+  uint8_t* Wp = reinterpret_cast<uint8_t*>(d_ws);
+  fp->block.assign(N, BlockFwdMaps{});
+  CUtensorMap zmap;
+  WN_PROPAGATE(tmap_3d(&zmap, Wp + wl.Zcat, 64 * N, W, B, 64 * N, (uint64_t)W * 64 * N, 128));
+  std::vector<CUtensorMap> xm(N);
+  for (int i = 0; i < N; ++i) WN_PROPAGATE(tmap_3d(&xm[i], Wp + wl.X + wl.x_stride * i, 64, L, B, 64, (uint64_t)L * 64, 128));
+  for (int i = 0; i < N; ++i) {
+    BlockFwdMaps& bm = fp->block[i];
+    bm.x = xm[i];
+    bm.xo = xm[i + 1 < N ? i + 1 : i];
+    WN_PROPAGATE(tmap_2d(&bm.w0, P + pl.wfg0 + (size_t)i * 128 * 64 * 2, 64, 128, 64, 128));
+    WN_PROPAGATE(tmap_2d(&bm.w1, P + pl.wfg1 + (size_t)i * 128 * 64 * 2, 64, 128, 64, 128));
+    WN_PROPAGATE(tmap_2d(&bm.wd, P + pl.wd + (size_t)i * 64 * 64 * 2, 64, 64, 64, 64));
+    bm.z = zmap;
+  }
+  SkipHeadMaps& h = fp->head;
+  WN_PROPAGATE(tmap_2d(&h.zcat, Wp + wl.Zcat, 64 * N, (uint64_t)B * W, 64 * N, 128));
+  WN_PROPAGATE(tmap_2d(&h.wsk, P + pl.wscat, 64 * N, 256, 64 * N, 256));
+  WN_PROPAGATE(tmap_2d(&h.p1, P + pl.p1, 256, 256, 256, 256));
+  WN_PROPAGATE(tmap_2d(&h.p2, P + pl.p2, 256, 256, 256, 256));
+  WN_PROPAGATE(tmap_2d(&h.h0, Wp + wl.H0, 256, (uint64_t)B * W, 256, 128));
+  WN_PROPAGATE(tmap_2d(&h.h1, Wp + wl.H1, 256, (uint64_t)B * W, 256, 128));
+  WN_PROPAGATE(build_bwd_maps(m, pl, wl, B, L, P, Wp, xm, &fp->bwd));
+  fp->key_ws = d_ws;
+  fp->key_packed = d_packed;
+  fp->key_B = B;
+  fp->key_L = L;
+  return WN_OK;
+}
+
+namespace {
+
+// x0[b,tau,:] = Wc[:, idx[tau-1], 0] + Wc[:, idx[tau], 1]  (true one-hot input: the causal conv is a gather)
+__global__ void __launch_bounds__(256) causal_gather_bf16_kernel(const int64_t* __restrict__ idx, const float* __restrict__ wc_t,
+                                                                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ X0,
+                                                                 int L, int Q) {
+  const int b = blockIdx.y;
+  const int64_t n = (int64_t)L * 32;          // 32 channel pairs per row
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tau = (int)(e >> 5), c2 = (int)(e & 31) * 2;
+    float v0 = 0.f, v1 = 0.f;
+    if (tau >= 1) {
+      const int q0 = (int)idx[(int64_t)b * L + tau - 1], q1 = (int)idx[(int64_t)b * L + tau];
+      const float2 a = *reinterpret_cast<const float2*>(wc_t + (int64_t)q0 * 64 + c2);
+      const float2 c = *reinterpret_cast<const float2*>(wc_t + ((int64_t)Q + q1) * 64 + c2);
+      v0 = a.x + c.x;
+      v1 = a.y + c.y;
+      if (bias) {
+        v0 += bias[c2];
+        v1 += bias[c2 + 1];
+      }
+    }
+    *reinterpret_cast<__nv_bfloat162*>(X0 + ((int64_t)b * L + tau) * 64 + c2) = __floats2bfloat162_rn(v0, v1);
+  }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                               int64_t n_pairs, int L, int t0) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_pairs; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e >> 5;
+    const int tau = (int)(row % L);
+    float2 v = *reinterpret_cast<const float2*>(src + e * 2);
+    if (tau < t0) v = make_float2(0.f, 0.f);
+    *reinterpret_cast<__nv_bfloat162*>(dst + e * 2) = __floats2bfloat162_rn(v.x, v.y);
+  }
+}
+
+}  // namespace
+
+int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx, const void* d_packed, void* d_ws, float* d_logits,
+                 cudaStream_t s) {
+  WN_PROPAGATE(require_supported(m));
+  FastPlan* fp = plan_of(m);
+  WN_PROPAGATE(build_maps(m, fp, B, L, d_packed, d_ws));
+  const PackLayout pl = pack_layout(m);
+  const WsLayout wl = ws_layout(m, B, L);
+  const int W = L - m.rf + 1, N = m.n_layers;
+  const uint8_t* P = reinterpret_cast<const uint8_t*>(d_packed);
+  uint8_t* Wp = reinterpret_cast<uint8_t*>(d_ws);
+  const float* bias_c = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_c) : nullptr;
+  __nv_bfloat16* X0 = reinterpret_cast<__nv_bfloat16*>(Wp + wl.X);
+  if (d_idx) {
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div((int64_t)L * 32, 256), 2048), (unsigned)B);
+    causal_gather_bf16_kernel<<<grid, 256, 0, s>>>(d_idx, reinterpret_cast<const float*>(P + pl.wc_t), bias_c, X0, L, m.Q);
+    WN_CHECK_LAUNCH();
+  } else {
+    // dense (B,Q,L) input: fp32 SIMT causal GEMM (2.9 % of the FLOPs), then one rounding to bf16
+    PwArgs a;
+    a.X.p = d_x; a.X.sb = (int64_t)m.Q * L; a.X.st = 1; a.X.sc = L;
+    a.x_lo = 0; a.x_hi = L; a.n_in = m.Q; a.n_taps = 2; a.off[0] = -1; a.off[1] = 0;
+    a.Wt = reinterpret_cast<const float*>(P + pl.wc_t); a.bias = bias_c;
+    a.Y.p = reinterpret_cast<float*>(Wp + wl.X0f); a.Y.sb = (int64_t)L * 64; a.Y.st = 64; a.Y.sc = 1; a.n_out = 64;
+    a.B = B; a.t0 = 1; a.t1 = L;
+    WN_PROPAGATE(launch_pw_gemm(a, s));
+    const int64_t n_pairs = (int64_t)B * L * 32;
+    f32_to_bf16_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_pairs, 256), 4096), 256, 0, s>>>(
+        reinterpret_cast<const float*>(Wp + wl.X0f), X0, n_pairs, L, 1);
+    WN_CHECK_LAUNCH();
+  }
+  const int tiles_total = (int)ceil_div(L, 128);
+  for (int i = 0; i < N; ++i) {
+    const LayerP& l = m.layers[i];
+    BlockFwdParams p{};
+    p.L = L; p.d = l.dilation; p.s_out = l.start;
+    p.tile0 = l.start / 128;
+    p.tiles_per_batch = tiles_total - p.tile0;
+    p.tw0 = L - W;
+    p.zcol = 64 * i;
+    p.has_dense = (i + 1 < N) ? 1 : 0;
+    p.bias_fg = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
+    p.bias_d = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_d) + i * 64 : nullptr;
+    WN_PROPAGATE(launch_block_fwd(fp->block[i], p, B * p.tiles_per_batch, s));
+  }
+  SkipHeadParams hp{};
+  hp.n_rows = B * W;
+  hp.n_tiles = (int)ceil_div(hp.n_rows, 128);
+  hp.W = W; hp.Q = m.Q; hp.k_skip = 64 * N;
+  hp.logits = d_logits;
+  hp.bias_skip = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_skip) : nullptr;
+  hp.bias_p1 = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_p1) : nullptr;
+  hp.bias_p2 = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_p2) : nullptr;
+  WN_PROPAGATE(launch_skip_head(fp->head, hp, s));
+  return WN_OK;
+}
+
+int fast_backward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx, const void* d_packed, void* d_ws, float* d_dlogits,
+                  float* d_grads, cudaStream_t s) {
+  WN_PROPAGATE(require_supported(m));
+  FastPlan* fp = plan_of(m);
+  WN_PROPAGATE(build_maps(m, fp, B, L, d_packed, d_ws));
+  return fast_backward_impl(m, fp->bwd, B, L, d_x, d_idx, d_packed, d_ws, d_dlogits, d_grads, s);
+}
+
+int fast_gen_steps(Model& m, int, int, int, const int64_t*, const void*, void*, const float*, int64_t*, float*, cudaStream_t) {
+  (void)m;
+  set_error("wn_gen_steps: bf16 generation kernel not built yet; use mode fp32");
+  return WN_ERR_UNSUPPORTED;
+}
+
+}  // namespace wn

@@ -1,0 +1,47 @@
+// fast_kernels.cuh - parameter blocks and launchers of the tcgen05 kernels (fast_fwd.cu, fast_bwd.cu).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace wn {
+
+// ---------------------------------------------------------------- forward: residual block
+struct BlockFwdMaps {
+  CUtensorMap x;    // x_i      (C=64, L, B) bf16, box {64,128,1}, SW128 : load (both taps)
+  CUtensorMap xo;   // x_{i+1}  same geometry                               : store
+  CUtensorMap w0;   // W_fg tap 0 [128 rows (f|g)][64]   box {64,128}
+  CUtensorMap w1;   // W_fg tap 1
+  CUtensorMap wd;   // W_dense [64][64]                  box {64,64}
+  CUtensorMap z;    // Zcat (C=64*N, W, B), box {64,128,1}                  : store
+};
+struct BlockFwdParams {
+  int L, d, s_out;          // length, dilation, first valid output time index
+  int tile0, tiles_per_batch;
+  int tw0;                  // L - W: first time index that feeds the skip path
+  int zcol;                 // 64 * layer
+  int has_dense;            // 0 for the last layer (its dense output is discarded, model.py:121-124)
+  const float* bias_fg;     // [128] or null
+  const float* bias_d;      // [64] or null
+};
+int launch_block_fwd(const BlockFwdMaps& m, const BlockFwdParams& p, int n_ctas, cudaStream_t s);
+
+// ---------------------------------------------------------------- forward: skip GEMM + head
+struct SkipHeadMaps {
+  CUtensorMap zcat;  // (64*N, B*W) box {64,128}   load
+  CUtensorMap wsk;   // Wskip_cat [256][64*N] box {64,256}
+  CUtensorMap p1;    // [256][256] box {64,256}
+  CUtensorMap p2;    // [256][256] box {64,256}
+  CUtensorMap h0;    // (256, B*W) box {64,128}    store
+  CUtensorMap h1;
+};
+struct SkipHeadParams {
+  int n_tiles, n_rows, W, Q, k_skip;
+  float* logits;            // (B,Q,W) fp32
+  const float* bias_skip;   // [256] = sum over layers of skip biases, or null
+  const float* bias_p1;
+  const float* bias_p2;
+};
+int launch_skip_head(const SkipHeadMaps& m, const SkipHeadParams& p, cudaStream_t s);
+
+}  // namespace wn

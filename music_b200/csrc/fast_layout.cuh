@@ -1,0 +1,57 @@
+// fast_layout.cuh - byte layouts of the bf16 packed-weight image and of the training workspace, plus the
+// backward-side descriptor bundle (shared between fast_host.cu and fast_bwd.cu).
+#pragma once
+#include <cuda.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace wn {
+
+enum { PJ_BF16 = 0, PJ_BF16_T = 1, PJ_F32_T = 2, PJ_COPY = 3 };
+struct PackJob {
+  int32_t kind, out, in, k, tap, pitch, row0, col0;
+  int64_t src;   // float offset into the flat parameter vector
+  int64_t dst;   // byte offset into the packed image
+};
+
+struct PackLayout {     // byte offsets
+  size_t jobs, wc_t, bias_c, bias_fg, bias_d, bias_skip, bias_p1, bias_p2;
+  size_t wfg0, wfg1, wd, wscat, p1, p2;          // K-major [out][in] bf16 (forward B operands)
+  size_t wfgT0, wfgT1, wdT, wsT, p1T, p2T;       // [in][out] bf16 (data-gradient B operands)
+  size_t total;
+};
+PackLayout pack_layout(const Model& m);
+
+struct WsLayout {       // byte offsets
+  size_t X, x_stride, Zcat, H0, H1, X0f;
+  size_t DLG, DH1, DSK, DXa, DXb, DFG, Zf, DX0f;
+  size_t total;
+};
+WsLayout ws_layout(const Model& m, int B, int L);
+
+int tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems, uint32_t box_rows);
+int tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batches, uint64_t pitch_elems,
+            uint64_t batch_pitch_elems, uint32_t box_rows);
+
+struct BwdLayerMaps {
+  CUtensorMap x;              // x_i (64, L, B)
+  CUtensorMap w0, w1;         // W_fg taps [128][64]        (recompute)
+  CUtensorMap wdT;            // [64 d][64 r]   box {64,64}
+  CUtensorMap wsT;            // [64 d][256 s]  box {64,64}
+  CUtensorMap wfgT0, wfgT1;   // [64 r][128 o]  box {64,64}
+};
+struct BwdMaps {
+  std::vector<BwdLayerMaps> layer;
+  CUtensorMap dlg, h0, h1, dh1, dsk;     // (256, B*W) box {64,128}
+  CUtensorMap dsk3;                      // (256, W, B) box {64,128,1}
+  CUtensorMap p1T, p2T;                  // [256][256] box {64,256}
+  CUtensorMap dxa, dxb, dfg, zf;         // (64|128, L, B)
+};
+int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int B, int L, const uint8_t* P, uint8_t* Wp,
+                   const std::vector<CUtensorMap>& xm, BwdMaps* out);
+int fast_backward_impl(Model& m, const BwdMaps& maps, int B, int L, const float* d_x, const int64_t* d_idx, const void* d_packed,
+                       void* d_ws, float* d_dlogits, float* d_grads, cudaStream_t s);
+
+}  // namespace wn

@@ -1,0 +1,224 @@
+"""Drop-in for the reference's `wavenet/train.py`: optimizer factory, checkpoint helpers, the
+train loop - plus `Trainer`, the fused data-parallel step the loop uses.
+
+Reference: get_optimizer :28-42, save_model :45-50, load_model :53-73, train :76-222 (hot loop
+:169-182).  The reference wraps the net in nn.DataParallel (:121); here it is one process per GPU
+with ONE NCCL all-reduce (avg) of the flat gradient vector per step, which is arithmetically the
+same thing because every rank holds the same number of loss rows.
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+from collections import OrderedDict
+from functools import cmp_to_key
+
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+from .. import _lib as L
+from .._engine import fused_loss
+from .model import wavenet
+
+
+def get_params(json_dir):
+    with open(json_dir, 'r') as f:
+        params = json.load(f)
+    return params
+
+
+def get_arguments(base='./params/'):
+    train_params = get_params(os.path.join(base, 'train_params.json'))
+    wavenet_params = get_params(os.path.join(base, 'wavenet_params.json'))
+    dataset_params = get_params(os.path.join(base, 'dataset_params.json'))
+    return train_params, wavenet_params, dataset_params
+
+
+def get_optimizer(model, optimizer_type, learning_rate, momentum):
+    """torch.optim objects exactly as the reference builds them (train.py:28-42); they work on the
+    module's parameters (views into the flat vector).  `Trainer` below is the fused equivalent."""
+    if optimizer_type == 'sgd':
+        return optim.SGD(model.parameters(), lr=learning_rate, momentum=momentum)
+    if optimizer_type == 'rmsprop':
+        return optim.RMSprop(model.parameters(), lr=learning_rate, momentum=momentum)
+    if optimizer_type == 'adam':
+        return optim.Adam(model.parameters(), lr=learning_rate)
+
+
+def save_model(model, num_iter, path):
+    model_name = "wavenet" + str(num_iter) + ".model"
+    checkpoint_path = path + model_name
+    print("Storing checkpoint to {} ...".format(path))
+    sd = OrderedDict((k, v.detach().cpu().clone()) for k, v in model.state_dict().items())
+    torch.save(sd, checkpoint_path)
+    print("Done!")
+
+
+def load_model(model, path, model_name):
+    checkpoint_path = path + model_name
+    print("Trying to restore saved checkpoint from ", "{}".format(checkpoint_path))
+    if os.path.exists(checkpoint_path):
+        print("Checkpoint found, restoring!")
+        state_dict = torch.load(checkpoint_path, map_location="cpu")
+        keys = list(state_dict.keys())
+        if keys[0][:6] == 'module':                       # saved from nn.DataParallel (train.py:61-69)
+            new_state_dict = OrderedDict()
+            for k, v in state_dict.items():
+                new_state_dict[k[7:]] = v
+            state_dict = new_state_dict
+        model.load_state_dict(state_dict)
+        return model
+    else:
+        print("No checkpoint found!")
+        return None
+
+
+class Trainer:
+    """Fused train step: zero_grad -> forward -> CrossEntropyLoss(probabilities) -> backward ->
+    [all-reduce] -> optimizer.step, i.e. wavenet/train.py:171-182, with no autograd graph.
+
+    step(piece, target): `piece` is either the dense (B,Q,L) float tensor the reference feeds or a
+    (B,L) integer tensor of mu-law codes (true one-hot input); `target` is (B,W) int64.  Returns
+    the loss as a 1-element device tensor (no host sync).
+    """
+
+    def __init__(self, net: wavenet, optimizer_type: str = "adam", learning_rate: float = 1e-4,
+                 momentum: float = 0.9, process_group=None, distributed=None):
+        if optimizer_type not in ("adam", "sgd", "rmsprop"):
+            raise ValueError(optimizer_type)
+        self.net, self.kind, self.lr, self.momentum = net, optimizer_type, learning_rate, momentum
+        self.step_count = 0
+        self.state = {}
+        import torch.distributed as dist
+        self.dist = dist if (distributed if distributed is not None else (dist.is_available() and dist.is_initialized())) else None
+        self.group = process_group
+        self._comm_stream = None
+
+    def _buf(self, name):
+        e = self.net.engine
+        t = self.state.get(name)
+        if t is None or t.device != e.flat.device or t.numel() != e.n_params:
+            t = torch.zeros(e.n_params, dtype=torch.float32, device=e.flat.device)
+            self.state[name] = t
+        return t
+
+    def forward_backward(self, piece, target):
+        net, e = self.net, self.net.engine
+        params = net._params()
+        e.ensure_flat(params)
+        mode, rows = L.MODES[net.mode], L.ROWS[net.parity]
+        packed = e.packed(mode, params)
+        x = idx = None
+        if piece.dtype.is_floating_point:
+            x = piece.detach().float().contiguous()
+        else:
+            idx = piece.detach().to(torch.int64).contiguous()
+        src = x if x is not None else idx
+        ws = e.workspace(mode, src.shape[0], src.shape[-1])
+        logits = e.forward_logits(mode, x, idx, packed, ws)
+        loss, dlogits = fused_loss(logits, target, rows, True, 1.0, e.scratch("loss", 4 * logits.shape[0] * logits.shape[2] + 256))
+        e.backward(mode, x, idx, packed, ws, dlogits, e.gflat)
+        return loss
+
+    def all_reduce(self):
+        if self.dist is None:
+            return
+        g = self.net.engine.gflat
+        ws = self.dist.get_world_size(self.group)
+        if ws == 1:
+            return
+        if self.dist.get_backend(self.group) == "nccl":
+            self.dist.all_reduce(g, op=self.dist.ReduceOp.AVG, group=self.group)
+        else:
+            self.dist.all_reduce(g, op=self.dist.ReduceOp.SUM, group=self.group)
+            g.div_(ws)
+
+    def apply(self):
+        e, lib = self.net.engine, L.load()
+        self.step_count += 1
+        n, s = e.n_params, L.stream_ptr()
+        if self.kind == "adam":
+            L.check(lib.wn_adam_step(L.ptr(e.flat), L.ptr(e.gflat), L.ptr(self._buf("m")), L.ptr(self._buf("v")), n,
+                                     self.lr, 0.9, 0.999, 1e-8, self.step_count, s))
+        elif self.kind == "sgd":
+            L.check(lib.wn_sgd_step(L.ptr(e.flat), L.ptr(e.gflat), L.ptr(self._buf("buf")), n, self.lr, self.momentum,
+                                    int(self.step_count == 1), s))
+        else:
+            L.check(lib.wn_rmsprop_step(L.ptr(e.flat), L.ptr(e.gflat), L.ptr(self._buf("sq")), L.ptr(self._buf("buf")), n,
+                                        self.lr, 0.99, 1e-8, self.momentum, s))
+        e.invalidate_packed()
+
+    def step(self, piece, target):
+        loss = self.forward_backward(piece, target)
+        self.all_reduce()
+        self.apply()
+        params = self.net._params()
+        for p, g in zip(params, self.net.engine.grad_views(params)):
+            p.grad = g
+        return loss
+
+
+def train(base='./params/', dataloader=None, rank=0):
+    """The reference loop (train.py:76-222): JSON configs, resume, loss / store logs, checkpoint
+    rotation.  One process per GPU; launch under torchrun for data parallelism."""
+    from .faster_audio_data import audio_data_loader
+    if not torch.cuda.is_available():
+        raise L.WavenetB200Error("music_b200 trains on a B200 only (no CPU fallback)")
+    train_params, wavenet_params, dataset_params = get_arguments(base)
+    net = wavenet(**wavenet_params)
+    epoch_trained = 0
+    if train_params["restore_model"]:
+        restored = load_model(net, train_params["restore_dir"], train_params["restore_model"])
+        if restored is None:
+            print("Initialize network and train from scratch.")
+        else:
+            epoch_trained = int(train_params["restore_model"].split('.')[0][7:])
+    if dataloader is None:
+        dataloader = audio_data_loader(**dataset_params)
+    net = net.cuda()
+    print("Start training.")
+    print("Writing logging information to ", "{}".format(train_params["log_dir"]))
+    print("Models are saved in {}".format(train_params["restore_dir"]))
+    trainer = Trainer(net, train_params["optimizer"], train_params["learning_rate"], train_params["momentum"])
+    os.makedirs(train_params["log_dir"], exist_ok=True)
+    os.makedirs(train_params["restore_dir"], exist_ok=True)
+    loss_log_file = open(train_params["log_dir"] + 'loss_log.log', 'a')
+    store_log_file = open(train_params["log_dir"] + 'store_log.log', 'a')
+    with open(train_params["log_dir"] + 'loss_log.log', 'r') as f:
+        lines = f.readlines()
+        num_trained = int(lines[-1].split(' ')[2]) if len(lines) > 0 else 0
+    total_loss = torch.zeros(1, device="cuda")
+    for epoch in range(train_params["num_epochs"]):
+        for i_batch, sampled_batch in enumerate(dataloader):
+            piece = sampled_batch["audio_piece"].cuda(non_blocking=True)
+            target = sampled_batch["audio_target"].cuda(non_blocking=True)
+            total_loss += trainer.step(piece, target)         # accumulated on device: no per-step sync
+            num_trained += 1
+            if num_trained % train_params["print_every"] == 0:
+                avg_loss = float(total_loss) / train_params["print_every"]
+                line = "Trained over " + str(num_trained) + " pieces," + "Average loss is " + str(avg_loss) + "\n"
+                if rank == 0:
+                    loss_log_file.writelines(line)
+                    loss_log_file.flush()
+                total_loss.zero_()
+        if (epoch + 1) % train_params["check_point_every"] == 0 and rank == 0:
+            stored_models = glob.glob(train_params["restore_dir"] + "*.model")
+            if len(stored_models) == train_params["max_check_points"]:
+                def cmp(x, y):
+                    x = int(x.split('/')[-1].split('.')[0][7:])
+                    y = int(y.split('/')[-1].split('.')[0][7:])
+                    return x - y
+                stored_models = sorted(stored_models, key=cmp_to_key(cmp))
+                os.remove(stored_models[0])
+            save_model(net, epoch_trained + epoch + 1, train_params["restore_dir"])
+            store_log_file.writelines("Epoch " + str(epoch_trained + epoch + 1) + ", model saved!\n")
+            store_log_file.flush()
+    loss_log_file.close()
+    store_log_file.close()
+    return net
+
+
+if __name__ == '__main__':
+    train()
