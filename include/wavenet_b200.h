@@ -155,6 +155,11 @@ int wn_gen_export(const wn_model* m, int32_t mode, int32_t n_streams, const void
 int wn_gen_import(const wn_model* m, int32_t mode, int32_t n_streams, void* d_state,
                   const float* d_queues, const int64_t* d_last_note, void* stream);
 
+/* ---- instrumentation (bench.py): kernel-launch counter and per-kernel CUDA-event profiler ---------- */
+uint64_t wn_launch_count(void);                 /* kernels launched by this library so far */
+int wn_profile_enable(int32_t on);              /* bracket every launch with CUDA events on its stream */
+int wn_profile_report(char* buf, size_t cap);   /* sync; "name count total_ms" lines, longest first; clears */
+
 /* ---- self tests of the tcgen05 / TMA building blocks (used by tests/, not by the product) -- */
 /* Runs D = A*B^T tiles through TMA -> UMMA -> TMEM -> registers for the operand layouts the
  * kernels rely on; writes max |err| vs. an in-kernel fp32 SIMT product to h_maxerr[case]. */

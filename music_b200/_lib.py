@@ -60,6 +60,9 @@ SIGNATURES = {
     "wn_gen_export": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p]),
     "wn_gen_import": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p]),
     "wn_selftest_umma": (C.c_int, [_p, _i32, _p]),
+    "wn_launch_count": (C.c_uint64, []),
+    "wn_profile_enable": (C.c_int, [_i32]),
+    "wn_profile_report": (C.c_int, [C.c_char_p, _sz]),
 }
 
 _lib = None
@@ -111,6 +114,18 @@ def init(device_index: int = 0) -> C.CDLL:
         check(lib.wn_init(int(device_index)))
         _inited_device = device_index
     return lib
+
+
+def profile_report():
+    """[(kernel name, launches, total ms)] since wn_profile_enable(1), longest first."""
+    lib = load()
+    buf = C.create_string_buffer(1 << 16)
+    check(lib.wn_profile_report(buf, len(buf)))
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(" ", 2)
+        out.append((name, int(cnt), float(ms)))
+    return out
 
 
 def ptr(t) -> C.c_void_p:

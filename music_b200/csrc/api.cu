@@ -3,6 +3,7 @@
 // tensor-core mode is dispatched to fast_*.cu.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -23,6 +24,47 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(t_err, sizeof(t_err), fmt, ap);
   va_end(ap);
+}
+
+unsigned long long g_launches = 0;
+
+// ---- optional per-kernel profiler (CUDA events on the launching stream) ----
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(const char* name, cudaStream_t s) {
+  if (!g_prof_on) return;
+  ProfRec r{name, prof_event(), prof_event()};
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t s) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().b, s);
+}
+
+int debug_sync(const char* what, cudaStream_t s) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("WN_DEBUG_SYNC");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!on) return WN_OK;
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    set_error("WN_DEBUG_SYNC: %s failed: %s", what, cudaGetErrorString(e));
+    fprintf(stderr, "WN_DEBUG_SYNC: %s failed: %s\n", what, cudaGetErrorString(e));
+    return WN_ERR_CUDA;
+  }
+  fprintf(stderr, "WN_DEBUG_SYNC: %s ok\n", what);
+  return WN_OK;
 }
 
 // ---- fp32 packed image: per conv Wt[k][in][out], Wtt[k][out][in], bias copy ----
@@ -289,6 +331,37 @@ static int backward32(const Model& m, int B, int L, const float* d_x, const int6
 using namespace wn;
 
 extern "C" int wn_version(void) { return 100; }
+extern "C" uint64_t wn_launch_count(void) { return g_launches; }
+extern "C" int wn_profile_enable(int32_t on) {
+  g_prof_on = on != 0;
+  return WN_OK;
+}
+// Synchronises the device, then writes "name count total_ms\n" lines (sorted by total time) and clears the log.
+extern "C" int wn_profile_report(char* buf, size_t cap) {
+  WN_REQUIRE(buf && cap > 0, WN_ERR_INVALID, "wn_profile_report: bad buffer");
+  WN_CHECK_CUDA(cudaDeviceSynchronize());
+  std::vector<std::pair<std::string, std::pair<int, double>>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    bool found = false;
+    for (auto& a : agg)
+      if (a.first == r.name) { a.second.first++; a.second.second += ms; found = true; break; }
+    if (!found) agg.push_back({r.name, {1, (double)ms}});
+    g_prof_pool.push_back(r.a);
+    g_prof_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  std::sort(agg.begin(), agg.end(), [](auto& x, auto& y) { return x.second.second > y.second.second; });
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& a : agg) {
+    int n = snprintf(buf + off, cap - off, "%s %d %.6f\n", a.first.c_str(), a.second.first, a.second.second);
+    if (n < 0 || (size_t)n >= cap - off) break;
+    off += n;
+  }
+  return WN_OK;
+}
 extern "C" const char* wn_last_error(void) { return t_err; }
 
 extern "C" int wn_init(int device) {

@@ -23,7 +23,22 @@ void set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
-#define WN_CHECK_LAUNCH() WN_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this: counts launches (wn_launch_count) and, when the
+// profiler is on (wn_profile_enable), brackets the launch with CUDA events on its stream.
+void prof_begin(const char* name, cudaStream_t s);
+void prof_end(cudaStream_t s);
+extern unsigned long long g_launches;
+#define WN_CHECK_LAUNCH()                \
+  do {                                   \
+    ++wn::g_launches;                    \
+    WN_CHECK_CUDA(cudaGetLastError());   \
+  } while (0)
+struct ProfScope {
+  cudaStream_t s;
+  ProfScope(const char* name, cudaStream_t st) : s(st) { prof_begin(name, st); }
+  ~ProfScope() { prof_end(s); }
+};
+#define WN_PROF(name, stream) wn::ProfScope _prof_scope_(name, stream)
 
 #define WN_REQUIRE(cond, code, ...)   \
   do {                                \
@@ -38,6 +53,10 @@ void set_error(const char* fmt, ...);
     int _s = (expr);            \
     if (_s != WN_OK) return _s; \
   } while (0)
+
+// WN_DEBUG_SYNC=1 in the environment: synchronise after every tensor-core kernel and name the one that failed
+int debug_sync(const char* what, cudaStream_t s);
+#define WN_DEBUG_SYNC(what, stream) WN_PROPAGATE(wn::debug_sync(what, stream))
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -1,18 +1,786 @@
-// fast_bwd.cu - bf16 tensor-core backward (placeholder until the kernels land).
-#include "fast_kernels.cuh"
+// fast_bwd.cu - bf16 tensor-core backward of the WaveNet stack (mirror of fast_fwd.cu).
+//
+//  gemm_nt_kernel<NT> : data-gradient GEMMs  OUT = epi(A W)   (head backward, dskip -> dz, dFG -> dx)
+//                       warp-specialised (TMA producer / MMA issuer / 4 epilogue warps), smem ring,
+//                       double-buffered TMEM accumulators, epilogue fuses ReLU mask / residual add.
+//  gemm_tn_kernel<NB> : weight-gradient GEMMs dW = A^T B with the reduction over time; both operands are
+//                       the same [time][64 ch] swizzled tiles, consumed MN-major; persistent CTAs keep
+//                       their partial sum in TMEM and flush it once with fp32 atomics.
+//  block_bwd_kernel   : per residual block: recompute [f|g] (UMMA), dz = dx_{i+1} Wd (UMMA) + dzs,
+//                       gate backward in the epilogue -> dFG and z tiles (TMA stores).
+#include "check_kernels.cuh"
+#include "fast_bwd_kernels.cuh"
 #include "fast_layout.cuh"
+#include "tc05.cuh"
 
 namespace wn {
+using namespace tc;
 
-int build_bwd_maps(const Model&, const PackLayout&, const WsLayout&, int, int, const uint8_t*, uint8_t*,
-                   const std::vector<CUtensorMap>&, BwdMaps*) {
+namespace {
+
+constexpr uint32_t TILE = 16384;   // [128 rows][64 bf16]
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ============================================================================================ gemm_nt
+template <int NT>
+struct NtCfg {
+  static constexpr int STAGES = NT == 256 ? 3 : 4;
+  static constexpr uint32_t A_BYTES = TILE, B_BYTES = NT * 128, STAGE = A_BYTES + B_BYTES;
+  static constexpr uint32_t OUT_OFF = STAGES * STAGE, TOTAL = OUT_OFF + (NT / 64) * TILE;
+  static constexpr int TMEM_COLS = NT == 256 ? 512 : 128;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(192, 1)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ CUtensorMap tmOut, GemmNtParams p) {
+  using Cfg = NtCfg<NT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full[Cfg::STAGES], empty[Cfg::STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t sbase = smem_u32(sm);
+  const int n_items = p.n_batches * p.tiles_per_batch * p.n_ntiles;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nt = item % p.n_ntiles, rt = item / p.n_ntiles;
+        const int b = rt / p.tiles_per_batch, row0 = (p.tile0 + rt % p.tiles_per_batch) * 128;
+        for (int seg = 0; seg < 2; ++seg) {
+          for (int k = 0; k < p.nk[seg]; ++k) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = sm + stage * Cfg::STAGE;
+            mbar_expect_tx(&full[stage], Cfg::STAGE);
+            tma_load_3d(sa, seg == 0 ? &tmA0 : &tmA1, &full[stage], p.a_col0[seg] + 64 * k, row0 + p.a_row_off[seg], b);
+            tma_load_2d(sa + Cfg::A_BYTES, seg == 0 ? &tmB0 : &tmB1, &full[stage], p.b_col0[seg] + 64 * k, nt * NT);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      constexpr uint32_t idn = idesc_bf16(128, NT, 0, 0);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t dst = tmem + as * NT;
+        const int nk = p.nk[0] + p.nk[1];
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(dst, desc_kmajor(sa, k), desc_kmajor(sb, k), idn, (kc | k) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const int nt = item % p.n_ntiles, rt = item / p.n_ntiles;
+      const int b = rt / p.tiles_per_batch, row0 = (p.tile0 + rt % p.tiles_per_batch) * 128;
+      const int row = row0 + tid;
+      const bool valid = row >= p.row_lo && row < p.row_hi;
+      mbar_wait(&acc_full[as], aph);
+      tc_fence_after();
+      const uint32_t src = tmem_addr(tmem, warp * 32, as * NT);
+      const __nv_bfloat16* auxp =
+          p.aux ? p.aux + (int64_t)b * p.aux_bstride + (int64_t)row * p.aux_rstride + p.aux_col0 + nt * NT : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < NT / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(src + c * 32, v);
+        tmem_ld_wait();
+        uint32_t packed[16];
+        uint32_t ax[16];
+        if (p.epi != EPI_PLAIN && valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 a4 = *reinterpret_cast<const uint4*>(auxp + c * 32 + q * 8);
+            ax[4 * q] = a4.x; ax[4 * q + 1] = a4.y; ax[4 * q + 2] = a4.z; ax[4 * q + 3] = a4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ax[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
+          const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&ax[j]);
+          if (p.epi == EPI_MASK) {
+            a0 = __low2float(x2) > 0.f ? a0 : 0.f;
+            a1 = __high2float(x2) > 0.f ? a1 : 0.f;
+          } else if (p.epi == EPI_ADD) {
+            a0 += __low2float(x2);
+            a1 += __high2float(x2);
+          }
+          packed[j] = valid ? pack_bf16(a0, a1) : 0u;
+        }
+        uint8_t* ot = sm + Cfg::OUT_OFF + (c >> 1) * TILE;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 val = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+          *reinterpret_cast<uint4*>(ot + sw128_chunk(tid, (c & 1) * 4 + q)) = val;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      epi_bar_sync();
+      if (tid == 0) {
+        mbar_arrive(&acc_empty[as]);
+        for (int j = 0; j < NT / 64; ++j)
+          tma_store_3d(&tmOut, sm + Cfg::OUT_OFF + j * TILE, p.out_col0 + nt * NT + 64 * j, row0, b);
+        tma_store_commit();
+        tma_store_wait_read();
+      }
+      epi_bar_sync();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ============================================================================================ gemm_tn
+template <int NB>
+struct TnCfg {
+  static constexpr int STAGES = NB == 4 ? 2 : (NB == 2 ? 3 : 4);
+  static constexpr uint32_t A_BYTES = 2 * TILE, B_BYTES = NB * TILE, STAGE = A_BYTES + B_BYTES;
+  static constexpr uint32_t TOTAL = STAGES * STAGE;
+  static constexpr int TMEM_COLS = NB == 4 ? 256 : (NB == 2 ? 128 : 64);
+};
+
+template <int NB>
+__global__ void __launch_bounds__(192, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+               const __grid_constant__ CUtensorMap tmB1, GemmTnParams p) {
+  using Cfg = TnCfg<NB>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full[Cfg::STAGES], empty[Cfg::STAGES], acc_full;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t sbase = smem_u32(sm);
+  const int n_items = p.n_batches * p.tiles_per_batch;
+  const bool have_work = (int)blockIdx.x < n_items;
+  const bool two_a = p.m_valid > 64;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = item / p.tiles_per_batch, row0 = (p.tile0 + item % p.tiles_per_batch) * 128;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = sm + stage * Cfg::STAGE;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        mbar_expect_tx(&full[stage], (two_a ? 2 : 1) * TILE + NB * TILE);
+        tma_load_3d(sa, &tmA, &full[stage], p.a_col0, row0, b);
+        if (two_a) tma_load_3d(sa + TILE, &tmA, &full[stage], p.a_col0 + 64, row0, b);
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          tma_load_3d(sb + j * TILE, p.b_map[j] == 0 ? &tmB0 : &tmB1, &full[stage], p.b_col[j], row0 + p.b_row_off[j], b);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && have_work) {
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      constexpr uint32_t idn = idesc_bf16(128, 64 * NB, 1, 1);
+      const uint32_t lbo_a = two_a ? TILE : 0u;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem, desc_mnmajor(sa, k, lbo_a), desc_mnmajor(sb, k, TILE), idn, (it | (uint32_t)k) != 0);
+        umma_commit(&empty[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&acc_full);
+    }
+  } else if (have_work) {
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const int m = tid;
+    float* base = (m < 64 ? p.out0 : p.out1) + (int64_t)(m & 63) * p.s_m;
+    const uint32_t src = tmem_addr(tmem, warp * 32, 0);
+#pragma unroll 1
+    for (int c = 0; c < 2 * NB; ++c) {
+      uint32_t v[32];
+      tmem_ld32(src + c * 32, v);
+      tmem_ld_wait();
+      if (m < p.m_valid) {
+        float* ob = base + p.blk_off[c >> 1] + (int64_t)((c & 1) * 32) * p.s_n;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(ob + (int64_t)j * p.s_n, __uint_as_float(v[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ========================================================================================== block_bwd
+struct BwdSmem {
+  static constexpr uint32_t A0 = 0, A1 = TILE, W0 = 2 * TILE, W1 = 3 * TILE, DX = 4 * TILE, WDT = 5 * TILE, TOTAL = 5 * TILE + 8192;
+};
+
+__global__ void __launch_bounds__(128, 2)
+block_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
+                 const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_dx,
+                 const __grid_constant__ CUtensorMap tm_wdT, const __grid_constant__ CUtensorMap tm_dfg,
+                 const __grid_constant__ CUtensorMap tm_zf, BlockBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar_ld, bar_m;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.x / p.tiles_per_batch;
+  const int tau0 = (p.tile0 + blockIdx.x % p.tiles_per_batch) * 128;
+  if (tid == 0) {
+    mbar_init(&bar_ld, 1);
+    mbar_init(&bar_m, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t sbase = smem_u32(sm);
+
+  if (tid == 0) {
+    mbar_expect_tx(&bar_ld, 4 * TILE + (p.has_dense ? TILE + 8192 : 0));
+    tma_load_3d(sm + BwdSmem::A0, &tm_x, &bar_ld, 0, tau0 - p.d, b);
+    tma_load_3d(sm + BwdSmem::A1, &tm_x, &bar_ld, 0, tau0, b);
+    tma_load_2d(sm + BwdSmem::W0, &tm_w0, &bar_ld, 0, 0);
+    tma_load_2d(sm + BwdSmem::W1, &tm_w1, &bar_ld, 0, 0);
+    if (p.has_dense) {
+      tma_load_3d(sm + BwdSmem::DX, &tm_dx, &bar_ld, 0, tau0, b);
+      tma_load_2d(sm + BwdSmem::WDT, &tm_wdT, &bar_ld, 0, 0);
+    }
+    mbar_wait(&bar_ld, 0);
+    tc_fence_after();
+    constexpr uint32_t id1 = idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem, desc_kmajor(sbase + BwdSmem::A0, k), desc_kmajor(sbase + BwdSmem::W0, k), id1, k > 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem, desc_kmajor(sbase + BwdSmem::A1, k), desc_kmajor(sbase + BwdSmem::W1, k), id1, true);
+    if (p.has_dense) {
+      constexpr uint32_t id2 = idesc_bf16(128, 64, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem + 128, desc_kmajor(sbase + BwdSmem::DX, k), desc_kmajor(sbase + BwdSmem::WDT, k), id2, k > 0);
+    }
+    umma_commit(&bar_m);
+  }
+  __syncwarp();
+  mbar_wait(&bar_m, 0);
+  tc_fence_after();
+
+  const int row = tid, tau = tau0 + row;
+  const bool valid = tau >= p.s_out && tau < p.L;
+  const bool in_w = valid && tau >= p.tw0;
+  const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
+  const __nv_bfloat16* dzs_row =
+      p.dzs + ((int64_t)b * p.Wp + (tau - p.tw_al)) * p.dzs_pitch + p.dzs_col;     // only dereferenced when in_w
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t f[32], g[32], dzv[32];
+    tmem_ld32(lane_addr + c * 32, f);
+    tmem_ld32(lane_addr + 64 + c * 32, g);
+    if (p.has_dense) tmem_ld32(lane_addr + 128 + c * 32, dzv);
+    tmem_ld_wait();
+    uint32_t zs[16];
+    if (in_w) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 a4 = *reinterpret_cast<const uint4*>(dzs_row + c * 32 + q * 8);
+        zs[4 * q] = a4.x; zs[4 * q + 1] = a4.y; zs[4 * q + 2] = a4.z; zs[4 * q + 3] = a4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) zs[j] = 0u;
+    }
+    uint32_t pz[16], pf[16], pg[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float fv[2] = {__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1])};
+      float gv[2] = {__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1])};
+      const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
+      float dz[2] = {__low2float(s2), __high2float(s2)};
+      if (p.has_dense) {
+        dz[0] += __uint_as_float(dzv[2 * j]);
+        dz[1] += __uint_as_float(dzv[2 * j + 1]);
+      }
+      float zo[2], df[2], dg[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (p.bias_fg) {
+          fv[e] += p.bias_fg[c * 32 + 2 * j + e];
+          gv[e] += p.bias_fg[64 + c * 32 + 2 * j + e];
+        }
+        const float t = tanh_fast(fv[e]), sg = sigmoid_fast(gv[e]);
+        zo[e] = valid ? t * sg : 0.f;
+        df[e] = valid ? dz[e] * sg * (1.f - t * t) : 0.f;
+        dg[e] = valid ? dz[e] * t * sg * (1.f - sg) : 0.f;
+      }
+      pz[j] = pack_bf16(zo[0], zo[1]);
+      pf[j] = pack_bf16(df[0], df[1]);
+      pg[j] = pack_bf16(dg[0], dg[1]);
+    }
+    // staging: z over the dx tile, dF over the tap-0 tile, dG over the tap-1 tile (all MMAs have completed)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t o = sw128_chunk(row, c * 4 + q);
+      *reinterpret_cast<uint4*>(sm + BwdSmem::DX + o) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
+      *reinterpret_cast<uint4*>(sm + BwdSmem::A0 + o) = make_uint4(pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
+      *reinterpret_cast<uint4*>(sm + BwdSmem::A1 + o) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_3d(&tm_zf, sm + BwdSmem::DX, 0, tau0, b);
+    tma_store_3d(&tm_dfg, sm + BwdSmem::A0, 0, tau0, b);
+    tma_store_3d(&tm_dfg, sm + BwdSmem::A1, 64, tau0, b);
+    tma_store_commit();
+    tma_store_wait_read();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// ============================================================================================ SIMT helpers
+// dlogits (B,Q,W) fp32 -> DLG [B][Wp][Q] bf16 in the padded skip row space (pad rows = 0)
+__global__ void __launch_bounds__(256) dlogits_transpose_kernel(const float* __restrict__ dl, __nv_bfloat16* __restrict__ out, int Q,
+                                                                int W, int Wp, int pad) {
+  __shared__ float tile[32][257];
+  const int b = blockIdx.y, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 8 warps
+  for (int q = ty; q < Q; q += 8) {
+    const int tw = j0 + tx - pad;
+    tile[tx][q] = (tw >= 0 && tw < W) ? dl[((int64_t)b * Q + q) * W + tw] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int j = j0 + r;
+    if (j >= Wp) continue;
+    __nv_bfloat16* o = out + ((int64_t)b * Wp + j) * Q;
+    for (int q = tx * 2; q < Q; q += 64)
+      *reinterpret_cast<__nv_bfloat162*>(o + q) = __floats2bfloat162_rn(tile[r][q], tile[r][q + 1]);
+  }
+}
+
+// dWc (R=64, Q, 2) += scatter of dx0 rows: shared-memory privatised histogram of 64-vectors
+__global__ void __launch_bounds__(256) causal_scatter_bwd_kernel(const int64_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dx0,
+                                                                 float* __restrict__ dW, int L, int Q, int rows_per_cta) {
+  extern __shared__ float acc[];       // [2][Q][64]
+  const int b = blockIdx.y;
+  const int t_begin = 1 + blockIdx.x * rows_per_cta, t_end = min(L, t_begin + rows_per_cta);
+  for (int e = threadIdx.x; e < 2 * Q * 64; e += blockDim.x) acc[e] = 0.f;
+  __syncthreads();
+  const int r = threadIdx.x & 63, sub = threadIdx.x >> 6;     // 4 rows in flight
+  for (int tau = t_begin + sub; tau < t_end; tau += 4) {
+    const float g = __bfloat162float(dx0[((int64_t)b * L + tau) * 64 + r]);
+    const int q0 = (int)idx[(int64_t)b * L + tau - 1], q1 = (int)idx[(int64_t)b * L + tau];
+    atomicAdd(&acc[(0 * Q + q0) * 64 + r], g);
+    atomicAdd(&acc[(1 * Q + q1) * 64 + r], g);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * Q * 64; e += blockDim.x) {
+    const float v = acc[e];
+    if (v != 0.f) {
+      const int k = e / (Q * 64), q = (e / 64) % Q, rr = e % 64;
+      atomicAdd(dW + ((int64_t)rr * Q + q) * 2 + k, v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    dst[e] = __bfloat162float(src[e]);
+}
+
+// out[c] += sum over b, rows in [row_lo,row_hi) of src[b][row][c]   (bias gradients); C in {64,128,256}
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int C, int64_t bstride, int row_lo,
+                                                          int row_hi, float* __restrict__ out, float* __restrict__ out_hi) {
+  const int b = blockIdx.y;
+  const int col = threadIdx.x % C, rsub = threadIdx.x / C, nsub = 256 / C;
+  const int r0 = row_lo + blockIdx.x * 512, r1 = min(row_hi, r0 + 512);
+  float acc = 0.f;
+  for (int r = r0 + rsub; r < r1; r += nsub) acc += __bfloat162float(src[(int64_t)b * bstride + (int64_t)r * C + col]);
+  if (out_hi && col >= 64) atomicAdd(out_hi + col - 64, acc);      // split output: columns [64,128) go to a second vector
+  else atomicAdd(out + col, acc);
+}
+// every layer's skip bias receives the same gradient (the skip outputs are summed): copy slot 0 to the others
+__global__ void replicate_kernel(float* __restrict__ G, const int64_t* __restrict__ offs, int n, int C) {
+  const int i = blockIdx.x + 1, c = threadIdx.x;
+  if (i < n && c < C) G[offs[i] + c] = G[offs[0] + c];
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  WN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return WN_OK;
 }
 
-int fast_backward_impl(Model&, const BwdMaps&, int, int, const float*, const int64_t*, const void*, void*, float*, float*,
-                       cudaStream_t) {
-  set_error("wn_backward: bf16 backward kernels not built yet");
-  return WN_ERR_UNSUPPORTED;
+int launch_colsum_bf16(const void* src, int C, int B, int64_t rows_per_batch, int row_lo, int row_hi, float* out, cudaStream_t s) {
+  if (row_hi <= row_lo) return WN_OK;
+  dim3 grid((unsigned)ceil_div(row_hi - row_lo, 512), (unsigned)B);
+  WN_PROF("colsum_bias", s);
+  colsum_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), C, rows_per_batch * C, row_lo, row_hi, out,
+                                          nullptr);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+// dFG (128 columns): filter-bias gradient from columns [0,64), gate-bias gradient from [64,128)
+int launch_colsum_bf16_split(const void* src, int B, int64_t rows_per_batch, int row_lo, float* out_f, float* out_g, cudaStream_t s) {
+  const int row_hi = (int)rows_per_batch;
+  if (row_hi <= row_lo) return WN_OK;
+  dim3 grid((unsigned)ceil_div(row_hi - row_lo, 512), (unsigned)B);
+  WN_PROF("colsum_bias", s);
+  colsum_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), 128, rows_per_batch * 128, row_lo, row_hi,
+                                          out_f, out_g);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+}  // namespace
+
+int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStream_t s) {
+  const int n_items = p.n_batches * p.tiles_per_batch * p.n_ntiles;
+  if (n_items <= 0) return WN_OK;
+  const int grid = std::min(n_items, g_sm_count);
+  WN_PROF(p.tag ? p.tag : "gemm_nt", s);
+  if (NT == 256) {
+    static bool once = false;
+    const int smem = NtCfg<256>::TOTAL + 1024;
+    if (!once) { WN_PROPAGATE(set_smem(gemm_nt_kernel<256>, smem)); once = true; }
+    gemm_nt_kernel<256><<<grid, 192, smem, s>>>(m.a[0], m.a[1], m.b[0], m.b[1], m.out, p);
+  } else if (NT == 64) {
+    static bool once = false;
+    const int smem = NtCfg<64>::TOTAL + 1024;
+    if (!once) { WN_PROPAGATE(set_smem(gemm_nt_kernel<64>, smem)); once = true; }
+    gemm_nt_kernel<64><<<grid, 192, smem, s>>>(m.a[0], m.a[1], m.b[0], m.b[1], m.out, p);
+  } else {
+    set_error("launch_gemm_nt: NT=%d", NT);
+    return WN_ERR_INVALID;
+  }
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+int launch_gemm_tn(int NB, const GemmTnMaps& m, const GemmTnParams& p, cudaStream_t s) {
+  const int n_items = p.n_batches * p.tiles_per_batch;
+  if (n_items <= 0) return WN_OK;
+  const int grid = std::min(n_items, g_sm_count);
+  WN_PROF(p.tag ? p.tag : "gemm_tn", s);
+  if (NB == 4) {
+    static bool once = false;
+    const int smem = TnCfg<4>::TOTAL + 1024;
+    if (!once) { WN_PROPAGATE(set_smem(gemm_tn_kernel<4>, smem)); once = true; }
+    gemm_tn_kernel<4><<<grid, 192, smem, s>>>(m.a, m.b[0], m.b[1], p);
+  } else if (NB == 2) {
+    static bool once = false;
+    const int smem = TnCfg<2>::TOTAL + 1024;
+    if (!once) { WN_PROPAGATE(set_smem(gemm_tn_kernel<2>, smem)); once = true; }
+    gemm_tn_kernel<2><<<grid, 192, smem, s>>>(m.a, m.b[0], m.b[1], p);
+  } else if (NB == 1) {
+    static bool once = false;
+    const int smem = TnCfg<1>::TOTAL + 1024;
+    if (!once) { WN_PROPAGATE(set_smem(gemm_tn_kernel<1>, smem)); once = true; }
+    gemm_tn_kernel<1><<<grid, 192, smem, s>>>(m.a, m.b[0], m.b[1], p);
+  } else {
+    set_error("launch_gemm_tn: NB=%d", NB);
+    return WN_ERR_INVALID;
+  }
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+int launch_block_bwd(const BlockBwdMaps& m, const BlockBwdParams& p, int n_ctas, cudaStream_t s) {
+  static bool once = false;
+  const int smem = BwdSmem::TOTAL + 1024;
+  if (!once) { WN_PROPAGATE(set_smem(block_bwd_kernel, smem)); once = true; }
+  WN_PROF("block_bwd", s);
+  block_bwd_kernel<<<n_ctas, 128, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, m.zf, p);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+// =============================================================================================== host
+int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int B, int L, const uint8_t* P, uint8_t* Wp,
+                   const std::vector<CUtensorMap>& xm, BwdMaps* out) {
+  const int N = m.n_layers, Wpad = skip_wp(m, L);
+  out->layer.assign(N, BwdLayerMaps{});
+  for (int i = 0; i < N; ++i) {
+    BwdLayerMaps& l = out->layer[i];
+    l.x = xm[i];
+    WN_PROPAGATE(tmap_2d(&l.w0, P + pl.wfg0 + (size_t)i * 128 * 64 * 2, 64, 128, 64, 128));
+    WN_PROPAGATE(tmap_2d(&l.w1, P + pl.wfg1 + (size_t)i * 128 * 64 * 2, 64, 128, 64, 128));
+    WN_PROPAGATE(tmap_2d(&l.wdT, P + pl.wdT + (size_t)i * 64 * 64 * 2, 64, 64, 64, 64));
+    WN_PROPAGATE(tmap_2d(&l.wfgT0, P + pl.wfgT0 + (size_t)i * 64 * 128 * 2, 128, 64, 128, 64));
+    WN_PROPAGATE(tmap_2d(&l.wfgT1, P + pl.wfgT1 + (size_t)i * 64 * 128 * 2, 128, 64, 128, 64));
+  }
+  auto skip3 = [&](CUtensorMap* t, size_t off, int cols) {
+    return tmap_3d(t, Wp + off, cols, Wpad, B, cols, (uint64_t)Wpad * cols, 128);
+  };
+  WN_PROPAGATE(skip3(&out->dlg, wl.DLG, 256));
+  WN_PROPAGATE(skip3(&out->h0, wl.H0, 256));
+  WN_PROPAGATE(skip3(&out->h1, wl.H1, 256));
+  WN_PROPAGATE(skip3(&out->dh1, wl.DH1, 256));
+  WN_PROPAGATE(skip3(&out->dsk, wl.DSK, 256));
+  WN_PROPAGATE(skip3(&out->zcat, wl.Zcat, 64 * N));
+  WN_PROPAGATE(skip3(&out->dzcat, wl.DZcat, 64 * N));
+  WN_PROPAGATE(tmap_2d(&out->p1T, P + pl.p1T, 256, 256, 256, 256));
+  WN_PROPAGATE(tmap_2d(&out->p2T, P + pl.p2T, 256, 256, 256, 256));
+  WN_PROPAGATE(tmap_2d(&out->wsTcat, P + pl.wsT, 256, (uint64_t)64 * N, 256, 256));
+  WN_PROPAGATE(tmap_3d(&out->dxa, Wp + wl.DXa, 64, L, B, 64, (uint64_t)L * 64, 128));
+  WN_PROPAGATE(tmap_3d(&out->dxb, Wp + wl.DXb, 64, L, B, 64, (uint64_t)L * 64, 128));
+  WN_PROPAGATE(tmap_3d(&out->dfg, Wp + wl.DFG, 128, L, B, 128, (uint64_t)L * 128, 128));
+  WN_PROPAGATE(tmap_3d(&out->zf, Wp + wl.Zf, 64, L, B, 64, (uint64_t)L * 64, 128));
+  return WN_OK;
+}
+
+int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_x, const int64_t* d_idx, const void* d_packed,
+                       void* d_ws, float* d_dlogits, float* G, cudaStream_t s) {
+  const PackLayout pl = pack_layout(m);
+  const WsLayout wl = ws_layout(m, B, L);
+  const int W = L - m.rf + 1, N = m.n_layers, Wpad = skip_wp(m, L), tw_al = skip_tw_al(m, L), pad = (L - W) - tw_al;
+  const uint8_t* P = reinterpret_cast<const uint8_t*>(d_packed);
+  uint8_t* Wp = reinterpret_cast<uint8_t*>(d_ws);
+  const bool bias = m.use_bias != 0;
+  WN_CHECK_CUDA(cudaMemsetAsync(G, 0, (size_t)m.n_params * sizeof(float), s));
+  WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXa, 0, (size_t)B * L * 64 * 2, s));
+  WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXb, 0, (size_t)B * L * 64 * 2, s));
+  WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DFG, 0, (size_t)B * L * 128 * 2, s));
+  WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.Zf, 0, (size_t)B * L * 64 * 2, s));
+  {
+    dim3 grid((unsigned)ceil_div(Wpad, 32), (unsigned)B);
+    WN_PROF("dlogits_transpose", s);
+    dlogits_transpose_kernel<<<grid, 256, 0, s>>>(d_dlogits, reinterpret_cast<__nv_bfloat16*>(Wp + wl.DLG), m.Q, W, Wpad, pad);
+    WN_CHECK_LAUNCH();
+  }
+  WN_DEBUG_SYNC("dlogits_transpose", s);
+  const int skip_tiles = (int)ceil_div(Wpad, 128);
+  // ---- head: dH1 = mask_{h1}(dLg P2), dSK = mask_{h0}(dH1 P1)            (model.py:135-138 backwards)
+  {
+    GemmNtMaps gm{};
+    gm.a[0] = M.dlg; gm.a[1] = M.dlg; gm.b[0] = M.p2T; gm.b[1] = M.p2T; gm.out = M.dh1;
+    GemmNtParams gp{};
+    gp.n_batches = B; gp.tile0 = 0; gp.tiles_per_batch = skip_tiles; gp.n_ntiles = 1;
+    gp.nk[0] = 4; gp.nk[1] = 0;
+    gp.epi = EPI_MASK; gp.aux = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.H1);
+    gp.aux_bstride = (int64_t)Wpad * 256; gp.aux_rstride = 256; gp.aux_col0 = 0;
+    gp.row_lo = 0; gp.row_hi = Wpad; gp.tag = "gemm_nt_dH1";
+    WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
+    WN_DEBUG_SYNC("gemm_nt dH1", s);
+    gm.a[0] = M.dh1; gm.a[1] = M.dh1; gm.b[0] = M.p1T; gm.b[1] = M.p1T; gm.out = M.dsk;
+    gp.aux = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.H0); gp.tag = "gemm_nt_dSK";
+    WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
+    WN_DEBUG_SYNC("gemm_nt dSK", s);
+  }
+  if (bias) {   // bias gradients = column sums of the matching output gradients (pad rows are zero)
+    WN_PROPAGATE(launch_colsum_bf16(Wp + wl.DLG, 256, B, Wpad, 0, Wpad, G + m.post2.b, s));
+    WN_PROPAGATE(launch_colsum_bf16(Wp + wl.DH1, 256, B, Wpad, 0, Wpad, G + m.post1.b, s));
+    WN_PROPAGATE(launch_colsum_bf16(Wp + wl.DSK, 256, B, Wpad, 0, Wpad, G + m.layers[0].skip.b, s));
+    if (N > 1) {   // offsets of the skip biases were uploaded behind the pack-job table by fast_pack
+      replicate_kernel<<<N - 1, 256, 0, s>>>(G, reinterpret_cast<const int64_t*>(P + pl.jobs + skip_bias_offs_pos(m)), N, 256);
+      WN_CHECK_LAUNCH();
+    }
+    WN_DEBUG_SYNC("head bias grads", s);
+  }
+  // ---- head weight gradients: dP2 = dLg^T relu(h1), dP1 = dH1^T relu(h0)
+  for (int which = 0; which < 2; ++which) {
+    for (int mt = 0; mt < 2; ++mt) {
+      GemmTnMaps tm{};
+      tm.a = which == 0 ? M.dlg : M.dh1;
+      tm.b[0] = which == 0 ? M.h1 : M.h0; tm.b[1] = tm.b[0];
+      GemmTnParams tp{};
+      tp.n_batches = B; tp.tile0 = 0; tp.tiles_per_batch = skip_tiles;
+      tp.a_col0 = 128 * mt; tp.m_valid = 128;
+      for (int j = 0; j < 4; ++j) { tp.b_map[j] = 0; tp.b_row_off[j] = 0; tp.b_col[j] = 64 * j; tp.blk_off[j] = 64 * j; }
+      float* base = G + (which == 0 ? m.post2.w : m.post1.w) + (int64_t)128 * mt * 256;
+      tp.out0 = base; tp.out1 = base + 64 * 256; tp.s_m = 256; tp.s_n = 1; tp.tag = "gemm_tn_head";
+      WN_PROPAGATE(launch_gemm_tn(4, tm, tp, s));
+      WN_DEBUG_SYNC("gemm_tn head", s);
+    }
+  }
+  // ---- dZcat = dSK Wskip_cat (every layer's skip data-gradient at once; dSK is read once)
+  {
+    GemmNtMaps gm{};
+    gm.a[0] = M.dsk; gm.a[1] = M.dsk; gm.b[0] = M.wsTcat; gm.b[1] = M.wsTcat; gm.out = M.dzcat;
+    GemmNtParams gp{};
+    gp.n_batches = B; gp.tile0 = 0; gp.tiles_per_batch = skip_tiles; gp.n_ntiles = (int)ceil_div(64 * N, 256);
+    gp.nk[0] = 4; gp.nk[1] = 0; gp.epi = EPI_PLAIN; gp.row_lo = 0; gp.row_hi = Wpad; gp.tag = "gemm_nt_dZcat";
+    WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
+    WN_DEBUG_SYNC("gemm_nt dZcat", s);
+  }
+  // ---- skip weight gradients for all layers: dWs_i = dSK^T Zcat[:, 64 i : 64 i + 64]
+  for (int mt = 0; mt < 2; ++mt) {
+    for (int n0 = 0; n0 < N; n0 += 4) {
+      GemmTnMaps tm{};
+      tm.a = M.dsk; tm.b[0] = M.zcat; tm.b[1] = M.zcat;
+      GemmTnParams tp{};
+      tp.n_batches = B; tp.tile0 = 0; tp.tiles_per_batch = skip_tiles;
+      tp.a_col0 = 128 * mt; tp.m_valid = 128;
+      const int nb = std::min(4, N - n0);
+      const int NB = nb >= 3 ? 4 : nb;       // kernel variants: 1, 2, 4 column blocks
+      float* base = G + (int64_t)128 * mt * 64;
+      for (int j = 0; j < 4; ++j) {
+        const int li = std::min(n0 + j, N - 1);
+        tp.b_map[j] = 0; tp.b_row_off[j] = 0;
+        tp.b_col[j] = (n0 + j < N) ? 64 * (n0 + j) : 64 * N;      // past the last layer: TMA zero fill -> adds 0
+        tp.blk_off[j] = m.layers[li].skip.w;
+      }
+      tp.out0 = base; tp.out1 = base + 64 * 64; tp.s_m = 64; tp.s_n = 1; tp.tag = "gemm_tn_dWs";
+      WN_PROPAGATE(launch_gemm_tn(NB, tm, tp, s));
+      WN_DEBUG_SYNC("gemm_tn dWs", s);
+    }
+  }
+  // ---- residual blocks, last to first
+  const int tiles_total = (int)ceil_div(L, 128);
+  for (int i = N - 1; i >= 0; --i) {
+    const LayerP& l = m.layers[i];
+    const int d = l.dilation, s_out = l.start, s_in = s_out - d;
+    const bool has_dense = i + 1 < N;
+    const CUtensorMap& dx_next = ((i + 1) & 1) ? M.dxb : M.dxa;       // dx_{i+1}
+    const CUtensorMap& dx_cur = (i & 1) ? M.dxb : M.dxa;              // dx_i
+    const size_t dx_next_off = ((i + 1) & 1) ? wl.DXb : wl.DXa;
+    const int tile0 = s_out / 128, tpb = tiles_total - tile0;
+    {
+      BlockBwdMaps bm{};
+      bm.x = M.layer[i].x; bm.w0 = M.layer[i].w0; bm.w1 = M.layer[i].w1; bm.dx = dx_next; bm.wdT = M.layer[i].wdT;
+      bm.dfg = M.dfg; bm.zf = M.zf;
+      BlockBwdParams bp{};
+      bp.L = L; bp.d = d; bp.s_out = s_out; bp.tile0 = tile0; bp.tiles_per_batch = tpb; bp.has_dense = has_dense;
+      bp.tw0 = L - W; bp.tw_al = tw_al; bp.Wp = Wpad;
+      bp.dzs = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DZcat); bp.dzs_pitch = 64 * N; bp.dzs_col = 64 * i;
+      bp.bias_fg = bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
+      WN_PROPAGATE(launch_block_bwd(bm, bp, B * tpb, s));
+      WN_DEBUG_SYNC("block_bwd", s);
+    }
+    if (bias) {   // dFG columns [0,64) = filter, [64,128) = gate: two separate bias vectors in the flat layout
+      WN_PROPAGATE(launch_colsum_bf16_split(Wp + wl.DFG, B, L, s_out, G + l.filt.b, G + l.gate.b, s));
+      if (has_dense) WN_PROPAGATE(launch_colsum_bf16(Wp + dx_next_off, 64, B, L, s_out, L, G + l.dense.b, s));
+    }
+    {   // dW_filter / dW_gate, both taps: dFG^T x_i[tau - d], dFG^T x_i[tau]
+      GemmTnMaps tm{};
+      tm.a = M.dfg; tm.b[0] = M.layer[i].x; tm.b[1] = M.layer[i].x;
+      GemmTnParams tp{};
+      tp.n_batches = B; tp.tile0 = tile0; tp.tiles_per_batch = tpb; tp.a_col0 = 0; tp.m_valid = 128;
+      tp.b_map[0] = 0; tp.b_row_off[0] = -d; tp.b_col[0] = 0; tp.blk_off[0] = 0;
+      tp.b_map[1] = 0; tp.b_row_off[1] = 0; tp.b_col[1] = 0; tp.blk_off[1] = 1;
+      tp.out0 = G + l.filt.w; tp.out1 = G + l.gate.w; tp.s_m = 128; tp.s_n = 2; tp.tag = "gemm_tn_dWfg";
+      WN_PROPAGATE(launch_gemm_tn(2, tm, tp, s));
+      WN_DEBUG_SYNC("gemm_tn dWfg", s);
+    }
+    if (has_dense) {   // dW_dense = dx_{i+1}^T z
+      GemmTnMaps tm{};
+      tm.a = dx_next; tm.b[0] = M.zf; tm.b[1] = M.zf;
+      GemmTnParams tp{};
+      tp.n_batches = B; tp.tile0 = tile0; tp.tiles_per_batch = tpb; tp.a_col0 = 0; tp.m_valid = 64;
+      tp.b_map[0] = 0; tp.b_row_off[0] = 0; tp.b_col[0] = 0; tp.blk_off[0] = 0;
+      tp.out0 = G + l.dense.w; tp.out1 = tp.out0; tp.s_m = 64; tp.s_n = 1; tp.tag = "gemm_tn_dWd";
+      WN_PROPAGATE(launch_gemm_tn(1, tm, tp, s));
+      WN_DEBUG_SYNC("gemm_tn dWd", s);
+    }
+    {   // dx_i[tau] = dx_{i+1}[tau] + W1^T dFG[tau] + W0^T dFG[tau + d]
+      GemmNtMaps gm{};
+      gm.a[0] = M.dfg; gm.a[1] = M.dfg; gm.b[0] = M.layer[i].wfgT1; gm.b[1] = M.layer[i].wfgT0; gm.out = dx_cur;
+      GemmNtParams gp{};
+      const int t0 = s_in / 128;
+      gp.n_batches = B; gp.tile0 = t0; gp.tiles_per_batch = tiles_total - t0; gp.n_ntiles = 1;
+      gp.nk[0] = 2; gp.nk[1] = 2; gp.a_row_off[0] = 0; gp.a_row_off[1] = d;
+      gp.epi = EPI_ADD; gp.aux = reinterpret_cast<const __nv_bfloat16*>(Wp + dx_next_off);
+      gp.aux_bstride = (int64_t)L * 64; gp.aux_rstride = 64; gp.aux_col0 = 0;
+      gp.row_lo = s_in; gp.row_hi = L; gp.tag = "gemm_nt_dx";
+      WN_PROPAGATE(launch_gemm_nt(64, gm, gp, s));
+      WN_DEBUG_SYNC("gemm_nt dx", s);
+    }
+  }
+  // ---- causal layer
+  const __nv_bfloat16* dx0 = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DXa);
+  if (bias) WN_PROPAGATE(launch_colsum_bf16(dx0, 64, B, L, 1, L, G + m.causal.b, s));
+  if (d_idx) {
+    static bool once = false;
+    const int smem = 2 * m.Q * 64 * 4;
+    if (!once) { WN_PROPAGATE(set_smem(causal_scatter_bwd_kernel, smem)); once = true; }
+    const int per_batch = std::max(1, (g_sm_count + B - 1) / B);
+    const int rows_per_cta = (int)ceil_div(L - 1, per_batch);
+    dim3 grid((unsigned)ceil_div(L - 1, rows_per_cta), (unsigned)B);
+    {
+      WN_PROF("causal_scatter_bwd", s);
+      causal_scatter_bwd_kernel<<<grid, 256, smem, s>>>(d_idx, dx0, G + m.causal.w, L, m.Q, rows_per_cta);
+      WN_CHECK_LAUNCH();
+    }
+    WN_DEBUG_SYNC("causal_scatter", s);
+  } else {
+    float* dx0f = reinterpret_cast<float*>(Wp + wl.DX0f);
+    const int64_t n = (int64_t)B * L * 64;
+    bf16_to_f32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 4096), 256, 0, s>>>(dx0, dx0f, n);
+    WN_CHECK_LAUNCH();
+    for (int tap = 0; tap < 2; ++tap) {      // dense (B,Q,L) input: fp32 SIMT weight gradient of the causal conv
+      WgArgs g;
+      g.X.p = d_x; g.X.sb = (int64_t)m.Q * L; g.X.st = 1; g.X.sc = L;
+      g.x_lo = 0; g.x_hi = L; g.n_in = m.Q; g.off = tap == 0 ? -1 : 0;
+      g.dY.p = dx0f; g.dY.sb = (int64_t)L * 64; g.dY.st = 64; g.dY.sc = 1;
+      g.n_out = 64; g.dW = G + m.causal.w + tap; g.s_out = (int64_t)m.Q * 2; g.s_in = 2;
+      g.B = B; g.t0 = 1; g.t1 = L;
+      WN_PROPAGATE(launch_wgrad(g, s));
+    }
+  }
+  return WN_OK;
 }
 
 }  // namespace wn

@@ -1,0 +1,74 @@
+// fast_bwd_kernels.cuh - parameter blocks of the backward tensor-core kernels (fast_bwd.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace wn {
+
+// ---------------------------------------------------------------------------------------------
+// gemm_nt:  OUT[b, row, n] = epi( sum_seg sum_k A_seg[b, row + a_row_off[seg], a_col0[seg] + k] *
+//                                               B_seg[n0 + n, b_col0[seg] + k] )            (bf16 out)
+// rows are tiled by 128 inside each batch of a 3-D tensor (cols, rows, batches); n0 = NT * n-tile.
+// ---------------------------------------------------------------------------------------------
+enum { EPI_PLAIN = 0, EPI_MASK = 1, EPI_ADD = 2 };
+struct GemmNtMaps {
+  CUtensorMap a[2];   // 3-D (cols, rows, batches) box {64,128,1}
+  CUtensorMap b[2];   // 2-D [N rows][K cols]       box {64, NT}
+  CUtensorMap out;    // 3-D box {64,128,1}
+};
+struct GemmNtParams {
+  int n_batches, tile0, tiles_per_batch, n_ntiles;
+  int nk[2], a_row_off[2], a_col0[2], b_col0[2];
+  int out_col0;
+  int epi;
+  const __nv_bfloat16* aux;     // EPI_MASK: out = aux > 0 ? acc : 0 ; EPI_ADD: out = acc + aux
+  int64_t aux_bstride, aux_rstride;
+  int aux_col0;
+  int row_lo, row_hi;           // rows outside are written as zeros
+  const char* tag;              // profiler label (host only)
+};
+int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// gemm_tn:  OUT[m, j, n] += sum_{b,row} A[b, row, a_col0 + m] * B_j[b, row + b_row_off[j], b_col[j] + n]
+// (weight gradients: the reduction runs over time).  m in [0,128) (m_valid 64 or 128), j < NB blocks
+// of 64 columns.  fp32 atomics into  out[(m < 64 ? out0 : out1) + (m % 64) * s_m + blk_off[j] + n * s_n].
+// ---------------------------------------------------------------------------------------------
+struct GemmTnMaps {
+  CUtensorMap a;      // 3-D box {64,128,1}
+  CUtensorMap b[2];   // 3-D box {64,128,1}
+};
+struct GemmTnParams {
+  int n_batches, tile0, tiles_per_batch;
+  int a_col0, m_valid;
+  int b_map[4], b_row_off[4], b_col[4];
+  float* out0;
+  float* out1;
+  int64_t s_m, s_n, blk_off[4];
+  const char* tag;              // profiler label (host only)
+};
+int launch_gemm_tn(int NB, const GemmTnMaps& m, const GemmTnParams& p, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// block_bwd: recompute [f|g] of block i, dz = dx_{i+1} Wd + dzs, gate backward -> dFG, z  (one tile / CTA)
+// ---------------------------------------------------------------------------------------------
+struct BlockBwdMaps {
+  CUtensorMap x;      // x_i (64, L, B)
+  CUtensorMap w0, w1; // W_fg taps [128][64]
+  CUtensorMap dx;     // dx_{i+1} (64, L, B)
+  CUtensorMap wdT;    // [64 d][64 r]
+  CUtensorMap dfg;    // (128, L, B) store
+  CUtensorMap zf;     // (64, L, B) store
+};
+struct BlockBwdParams {
+  int L, d, s_out, tile0, tiles_per_batch, has_dense;
+  int tw0, tw_al, Wp;
+  const __nv_bfloat16* dzs;     // [B*Wp][dzs_pitch], this layer's 64 columns start at dzs_col
+  int dzs_pitch, dzs_col;
+  const float* bias_fg;
+};
+int launch_block_bwd(const BlockBwdMaps& m, const BlockBwdParams& p, int n_ctas, cudaStream_t s);
+
+}  // namespace wn

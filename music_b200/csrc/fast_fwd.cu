@@ -6,7 +6,9 @@
 //     epilogue #1: z = sigmoid(g) * tanh(f) -> bf16 -> shared (A operand of #2) and TMA-stored into
 //                  the skip operand matrix Zcat[:, 64 i : 64 i + 64] for rows in the last W
 //     UMMA #2 (M128 N64 K64): dense = z Wd^T                                -> TMEM cols [128,192)
-//     epilogue #2: x_{i+1} = dense + x_i[tau] (residual read back from the shared x tile) -> TMA store
+//     epilogue #2: x_{i+1} = dense + x_i[tau] (residual read back from the shared x tile) -> TMA store.
+//                  The residual stream is carried as hi + lo bf16 pairs (hi feeds the MMAs, hi+lo the
+//                  residual add) so that 30 layers of bf16 rounding do not accumulate in x.
 // skip_head_kernel  : for a [128 rows of B*W] tile, chained GEMMs with TMEM-resident accumulators
 //     acc1 = Zcat[128 x 64N] Wskip_cat^T  (= sum_i skip_i, model.py:127-134; K = 64 N_layers)
 //     h0 = relu(acc1) -> smem/HBM ; acc2 = h0 P1^T ; h1 = relu(acc2) -> smem/HBM ; acc1 = h1 P2^T
@@ -27,13 +29,14 @@ constexpr uint32_t WD_BYTES = 64 * 128;
 struct BlockSmem {
   // offsets from the 1024-aligned base
   static constexpr uint32_t A0 = 0, A1 = TILE_BYTES, W0 = 2 * TILE_BYTES, W1 = 3 * TILE_BYTES, WD = 4 * TILE_BYTES,
-                            Z = 4 * TILE_BYTES + WD_BYTES, TOTAL = 5 * TILE_BYTES + WD_BYTES;
+                            Z = 4 * TILE_BYTES + WD_BYTES, LO = 5 * TILE_BYTES + WD_BYTES, TOTAL = 6 * TILE_BYTES + WD_BYTES;
 };
 
 __global__ void __launch_bounds__(BF_THREADS, 2)
 block_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_xo,
                  const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
-                 const __grid_constant__ CUtensorMap tm_wd, const __grid_constant__ CUtensorMap tm_z, BlockFwdParams p) {
+                 const __grid_constant__ CUtensorMap tm_wd, const __grid_constant__ CUtensorMap tm_z,
+                 const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_loo, BlockFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bar_ld, bar_m1, bar_m2;
@@ -58,12 +61,15 @@ block_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const uint32_t sbase = smem_u32(sm);
 
   if (tid == 0) {
-    mbar_expect_tx(&bar_ld, 4 * TILE_BYTES + (p.has_dense ? WD_BYTES : 0));
+    mbar_expect_tx(&bar_ld, 4 * TILE_BYTES + (p.has_dense ? WD_BYTES + TILE_BYTES : 0));
     tma_load_3d(sm + BlockSmem::A0, &tm_x, &bar_ld, 0, tau0 - p.d, b);
     tma_load_3d(sm + BlockSmem::A1, &tm_x, &bar_ld, 0, tau0, b);
     tma_load_2d(sm + BlockSmem::W0, &tm_w0, &bar_ld, 0, 0);
     tma_load_2d(sm + BlockSmem::W1, &tm_w1, &bar_ld, 0, 0);
-    if (p.has_dense) tma_load_2d(sm + BlockSmem::WD, &tm_wd, &bar_ld, 0, 0);
+    if (p.has_dense) {
+      tma_load_2d(sm + BlockSmem::WD, &tm_wd, &bar_ld, 0, 0);
+      tma_load_3d(sm + BlockSmem::LO, &tm_lo, &bar_ld, 0, tau0, b);     // low half of the residual stream
+    }
     mbar_wait(&bar_ld, 0);
     tc_fence_after();
     constexpr uint32_t id1 = idesc_bf16(128, 128, 0, 0);
@@ -124,8 +130,9 @@ block_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         umma_bf16(tmem + 128, desc_kmajor(sbase + BlockSmem::Z, k), desc_kmajor(sbase + BlockSmem::WD, k), id2, k > 0);
       umma_commit(&bar_m2);
     }
-    if (tau0 + 128 > p.tw0) {   // tile touches the last W time steps: z feeds the skip GEMM
-      tma_store_3d(&tm_z, sm + BlockSmem::Z, p.zcol, tau0 - p.tw0, b);
+    if (tau0 >= p.tw_al) {      // tile touches the last W time steps: z feeds the skip GEMM
+      // (TMA stores trap on negative coordinates, hence the tile-aligned row space)
+      tma_store_3d(&tm_z, sm + BlockSmem::Z, p.zcol, tau0 - p.tw_al, b);
       tma_store_commit();
     }
   }
@@ -140,35 +147,45 @@ block_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       uint32_t dv[32];
       tmem_ld32(lane_addr + 128 + c * 32, dv);
       tmem_ld_wait();
-      uint32_t packed[16];
+      uint32_t packed[16], packed_lo[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint4 rv = *reinterpret_cast<const uint4*>(sm + BlockSmem::A1 + sw128_chunk(row, c * 4 + q));
+        const uint4 lv = *reinterpret_cast<const uint4*>(sm + BlockSmem::LO + sw128_chunk(row, c * 4 + q));
         const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+        const uint32_t ll[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int j = 4 * q + e;     // pair index inside this 32-col chunk
           __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
-          float x0 = __uint_as_float(dv[2 * j]) + __low2float(r2);
-          float x1 = __uint_as_float(dv[2 * j + 1]) + __high2float(r2);
+          __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[e]);
+          // residual stream carried as hi + lo (two bf16): x = dense + (hi + lo), fp32
+          float x0 = __uint_as_float(dv[2 * j]) + (__low2float(r2) + __low2float(l2));
+          float x1 = __uint_as_float(dv[2 * j + 1]) + (__high2float(r2) + __high2float(l2));
           if (p.bias_d) {
             x0 += p.bias_d[c * 32 + 2 * j];
             x1 += p.bias_d[c * 32 + 2 * j + 1];
           }
-          packed[j] = valid ? pack_bf16(x0, x1) : 0u;
+          if (!valid) { x0 = 0.f; x1 = 0.f; }
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+          packed[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          packed_lo[j] = pack_bf16(x0 - __low2float(h2), x1 - __high2float(h2));
         }
       }
-      // stage x_{i+1} in the (now free) tap-0 tile
+      // stage x_{i+1}: hi in the (now free) tap-0 tile, lo in place over the lo tile
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 v = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
         *reinterpret_cast<uint4*>(sm + BlockSmem::A0 + sw128_chunk(row, c * 4 + q)) = v;
+        uint4 w = make_uint4(packed_lo[4 * q], packed_lo[4 * q + 1], packed_lo[4 * q + 2], packed_lo[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + BlockSmem::LO + sw128_chunk(row, c * 4 + q)) = w;
       }
     }
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
       tma_store_3d(&tm_xo, sm + BlockSmem::A0, 0, tau0, b);
+      tma_store_3d(&tm_loo, sm + BlockSmem::LO, 0, tau0, b);
       tma_store_commit();
     }
   }
@@ -187,7 +204,8 @@ int launch_block_fwd(const BlockFwdMaps& m, const BlockFwdParams& p, int n_ctas,
     WN_CHECK_CUDA(cudaFuncSetAttribute(block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  block_fwd_kernel<<<n_ctas, BF_THREADS, smem, s>>>(m.x, m.xo, m.w0, m.w1, m.wd, m.z, p);
+  WN_PROF("block_fwd", s);
+  block_fwd_kernel<<<n_ctas, BF_THREADS, smem, s>>>(m.x, m.xo, m.w0, m.w1, m.wd, m.z, m.lo, m.loo, p);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -353,8 +371,8 @@ skip_head_kernel(const __grid_constant__ CUtensorMap tm_zcat, const __grid_const
       mbar_wait(&acc_full[2], tph);
       tc_fence_after();
       const int r = row0 + row;
-      const bool ok = r < p.n_rows;
-      const int bb = ok ? r / p.W : 0, tw = ok ? r % p.W : 0;
+      const int bb = r / p.Wp, tw = r % p.Wp - p.pad;
+      const bool ok = r < p.n_rows && tw >= 0;
       float* out = p.logits + ((int64_t)bb * p.Q) * p.W + tw;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
@@ -390,6 +408,7 @@ int launch_skip_head(const SkipHeadMaps& m, const SkipHeadParams& p, cudaStream_
     attr_set = true;
   }
   int grid = std::min(p.n_tiles, g_sm_count);
+  WN_PROF("skip_head", s);
   skip_head_kernel<<<grid, SH_THREADS, smem, s>>>(m.zcat, m.wsk, m.p1, m.p2, m.h0, m.h1, p);
   WN_CHECK_LAUNCH();
   return WN_OK;

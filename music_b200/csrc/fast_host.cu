@@ -225,16 +225,18 @@ int fast_pack(Model& m, const float* d_params, void* d_packed, cudaStream_t s) {
       std::vector<int64_t> offs;
       for (auto& l : m.layers) offs.push_back(l.skip.b);
       // skip-bias offsets live right behind the job table
-      WN_CHECK_CUDA(cudaMemcpyAsync(P + pl.jobs + fp->jobs.size() * sizeof(PackJob), offs.data(), offs.size() * sizeof(int64_t),
+      WN_CHECK_CUDA(cudaMemcpyAsync(P + pl.jobs + skip_bias_offs_pos(m), offs.data(), offs.size() * sizeof(int64_t),
                                     cudaMemcpyHostToDevice, s));
     }
     fp->jobs_uploaded_to = d_packed;
   }
   dim3 grid(16, (unsigned)fp->jobs.size());
+  WN_PROF("pack_weights", s);
   pack_jobs_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const PackJob*>(P + pl.jobs), d_params, P);
   WN_CHECK_LAUNCH();
+  WN_DEBUG_SYNC("pack_jobs", s);
   if (m.use_bias) {
-    bias_skip_sum_kernel<<<1, 256, 0, s>>>(d_params, reinterpret_cast<const int64_t*>(P + pl.jobs + fp->jobs.size() * sizeof(PackJob)),
+    bias_skip_sum_kernel<<<1, 256, 0, s>>>(d_params, reinterpret_cast<const int64_t*>(P + pl.jobs + skip_bias_offs_pos(m)),
                                            m.n_layers, reinterpret_cast<float*>(P + pl.bias_skip));
     WN_CHECK_LAUNCH();
   }
@@ -244,7 +246,7 @@ int fast_pack(Model& m, const float* d_params, void* d_packed, cudaStream_t s) {
 // ------------------------------------------------------------------ workspace
 WsLayout ws_layout(const Model& m, int B, int L) {
   WsLayout w{};
-  const int W = L - m.rf + 1, N = m.n_layers;
+  const int W = skip_wp(m, L), N = m.n_layers;     // padded row space of everything downstream of the skips
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -253,6 +255,7 @@ WsLayout ws_layout(const Model& m, int B, int L) {
   };
   w.x_stride = align_up((size_t)B * L * 64 * 2, 1024);
   w.X = take(w.x_stride * N);
+  w.XLO = take(w.x_stride * 2);
   w.Zcat = take((size_t)B * W * 64 * N * 2);
   w.H0 = take((size_t)B * W * 256 * 2);
   w.H1 = take((size_t)B * W * 256 * 2);
@@ -261,6 +264,7 @@ WsLayout ws_layout(const Model& m, int B, int L) {
   w.DLG = take((size_t)B * W * 256 * 2);
   w.DH1 = take((size_t)B * W * 256 * 2);
   w.DSK = take((size_t)B * W * 256 * 2);
+  w.DZcat = take((size_t)B * W * 64 * N * 2);
   w.DXa = take((size_t)B * L * 64 * 2);
   w.DXb = take((size_t)B * L * 64 * 2);
   w.DFG = take((size_t)B * L * 128 * 2);
@@ -281,7 +285,7 @@ static int build_maps(Model& m, FastPlan* fp, int B, int L, const void* d_packed
   if (fp->key_ws == d_ws && fp->key_packed == d_packed && fp->key_B == B && fp->key_L == L) return WN_OK;
   const PackLayout pl = pack_layout(m);
   const WsLayout wl = ws_layout(m, B, L);
-  const int W = L - m.rf + 1, N = m.n_layers;
+  const int W = skip_wp(m, L), N = m.n_layers;
   const uint8_t* P = reinterpret_cast<const uint8_t*>(d_packed);
   uint8_t* Wp = reinterpret_cast<uint8_t*>(d_ws);
   fp->block.assign(N, BlockFwdMaps{});
@@ -289,6 +293,8 @@ static int build_maps(Model& m, FastPlan* fp, int B, int L, const void* d_packed
   WN_PROPAGATE(tmap_3d(&zmap, Wp + wl.Zcat, 64 * N, W, B, 64 * N, (uint64_t)W * 64 * N, 128));
   std::vector<CUtensorMap> xm(N);
   for (int i = 0; i < N; ++i) WN_PROPAGATE(tmap_3d(&xm[i], Wp + wl.X + wl.x_stride * i, 64, L, B, 64, (uint64_t)L * 64, 128));
+  CUtensorMap lom[2];
+  for (int i = 0; i < 2; ++i) WN_PROPAGATE(tmap_3d(&lom[i], Wp + wl.XLO + wl.x_stride * i, 64, L, B, 64, (uint64_t)L * 64, 128));
   for (int i = 0; i < N; ++i) {
     BlockFwdMaps& bm = fp->block[i];
     bm.x = xm[i];
@@ -297,6 +303,8 @@ static int build_maps(Model& m, FastPlan* fp, int B, int L, const void* d_packed
     WN_PROPAGATE(tmap_2d(&bm.w1, P + pl.wfg1 + (size_t)i * 128 * 64 * 2, 64, 128, 64, 128));
     WN_PROPAGATE(tmap_2d(&bm.wd, P + pl.wd + (size_t)i * 64 * 64 * 2, 64, 64, 64, 64));
     bm.z = zmap;
+    bm.lo = lom[i & 1];
+    bm.loo = lom[(i + 1) & 1];
   }
   SkipHeadMaps& h = fp->head;
   WN_PROPAGATE(tmap_2d(&h.zcat, Wp + wl.Zcat, 64 * N, (uint64_t)B * W, 64 * N, 128));
@@ -318,7 +326,7 @@ namespace {
 // x0[b,tau,:] = Wc[:, idx[tau-1], 0] + Wc[:, idx[tau], 1]  (true one-hot input: the causal conv is a gather)
 __global__ void __launch_bounds__(256) causal_gather_bf16_kernel(const int64_t* __restrict__ idx, const float* __restrict__ wc_t,
                                                                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ X0,
-                                                                 int L, int Q) {
+                                                                 __nv_bfloat16* __restrict__ X0lo, int L, int Q) {
   const int b = blockIdx.y;
   const int64_t n = (int64_t)L * 32;          // 32 channel pairs per row
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
@@ -335,18 +343,23 @@ __global__ void __launch_bounds__(256) causal_gather_bf16_kernel(const int64_t* 
         v1 += bias[c2 + 1];
       }
     }
-    *reinterpret_cast<__nv_bfloat162*>(X0 + ((int64_t)b * L + tau) * 64 + c2) = __floats2bfloat162_rn(v0, v1);
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+    *reinterpret_cast<__nv_bfloat162*>(X0 + ((int64_t)b * L + tau) * 64 + c2) = h2;
+    *reinterpret_cast<__nv_bfloat162*>(X0lo + ((int64_t)b * L + tau) * 64 + c2) =
+        __floats2bfloat162_rn(v0 - __low2float(h2), v1 - __high2float(h2));
   }
 }
 
 __global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                               int64_t n_pairs, int L, int t0) {
+                                                               __nv_bfloat16* __restrict__ dst_lo, int64_t n_pairs, int L, int t0) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_pairs; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = e >> 5;
     const int tau = (int)(row % L);
     float2 v = *reinterpret_cast<const float2*>(src + e * 2);
     if (tau < t0) v = make_float2(0.f, 0.f);
-    *reinterpret_cast<__nv_bfloat162*>(dst + e * 2) = __floats2bfloat162_rn(v.x, v.y);
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<__nv_bfloat162*>(dst + e * 2) = h2;
+    *reinterpret_cast<__nv_bfloat162*>(dst_lo + e * 2) = __floats2bfloat162_rn(v.x - __low2float(h2), v.y - __high2float(h2));
   }
 }
 
@@ -364,9 +377,11 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
   uint8_t* Wp = reinterpret_cast<uint8_t*>(d_ws);
   const float* bias_c = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_c) : nullptr;
   __nv_bfloat16* X0 = reinterpret_cast<__nv_bfloat16*>(Wp + wl.X);
+  __nv_bfloat16* X0lo = reinterpret_cast<__nv_bfloat16*>(Wp + wl.XLO);
   if (d_idx) {
     dim3 grid((unsigned)std::min<int64_t>(ceil_div((int64_t)L * 32, 256), 2048), (unsigned)B);
-    causal_gather_bf16_kernel<<<grid, 256, 0, s>>>(d_idx, reinterpret_cast<const float*>(P + pl.wc_t), bias_c, X0, L, m.Q);
+    WN_PROF("causal_gather", s);
+    causal_gather_bf16_kernel<<<grid, 256, 0, s>>>(d_idx, reinterpret_cast<const float*>(P + pl.wc_t), bias_c, X0, X0lo, L, m.Q);
     WN_CHECK_LAUNCH();
   } else {
     // dense (B,Q,L) input: fp32 SIMT causal GEMM (2.9 % of the FLOPs), then one rounding to bf16
@@ -379,9 +394,10 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
     WN_PROPAGATE(launch_pw_gemm(a, s));
     const int64_t n_pairs = (int64_t)B * L * 32;
     f32_to_bf16_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_pairs, 256), 4096), 256, 0, s>>>(
-        reinterpret_cast<const float*>(Wp + wl.X0f), X0, n_pairs, L, 1);
+        reinterpret_cast<const float*>(Wp + wl.X0f), X0, X0lo, n_pairs, L, 1);
     WN_CHECK_LAUNCH();
   }
+  WN_DEBUG_SYNC("causal", s);
   const int tiles_total = (int)ceil_div(L, 128);
   for (int i = 0; i < N; ++i) {
     const LayerP& l = m.layers[i];
@@ -390,14 +406,18 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
     p.tile0 = l.start / 128;
     p.tiles_per_batch = tiles_total - p.tile0;
     p.tw0 = L - W;
+    p.tw_al = skip_tw_al(m, L);
     p.zcol = 64 * i;
     p.has_dense = (i + 1 < N) ? 1 : 0;
     p.bias_fg = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
     p.bias_d = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_d) + i * 64 : nullptr;
     WN_PROPAGATE(launch_block_fwd(fp->block[i], p, B * p.tiles_per_batch, s));
+    WN_DEBUG_SYNC("block_fwd", s);
   }
   SkipHeadParams hp{};
-  hp.n_rows = B * W;
+  hp.Wp = skip_wp(m, L);
+  hp.pad = (L - W) - skip_tw_al(m, L);
+  hp.n_rows = B * hp.Wp;
   hp.n_tiles = (int)ceil_div(hp.n_rows, 128);
   hp.W = W; hp.Q = m.Q; hp.k_skip = 64 * N;
   hp.logits = d_logits;
@@ -405,6 +425,7 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
   hp.bias_p1 = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_p1) : nullptr;
   hp.bias_p2 = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_p2) : nullptr;
   WN_PROPAGATE(launch_skip_head(fp->head, hp, s));
+  WN_DEBUG_SYNC("skip_head", s);
   return WN_OK;
 }
 

@@ -13,12 +13,15 @@ struct BlockFwdMaps {
   CUtensorMap w0;   // W_fg tap 0 [128 rows (f|g)][64]   box {64,128}
   CUtensorMap w1;   // W_fg tap 1
   CUtensorMap wd;   // W_dense [64][64]                  box {64,64}
-  CUtensorMap z;    // Zcat (C=64*N, W, B), box {64,128,1}                  : store
+  CUtensorMap z;    // Zcat (C=64*N, Wp, B), box {64,128,1}                 : store (Wp = L - tw_al)
+  CUtensorMap lo;   // low half of x_i (ping-pong buffer)                    : load
+  CUtensorMap loo;  // low half of x_{i+1}                                   : store
 };
 struct BlockFwdParams {
   int L, d, s_out;          // length, dilation, first valid output time index
   int tile0, tiles_per_batch;
   int tw0;                  // L - W: first time index that feeds the skip path
+  int tw_al;                // tw0 rounded down to a tile boundary: row 0 of the (padded) skip row space
   int zcol;                 // 64 * layer
   int has_dense;            // 0 for the last layer (its dense output is discarded, model.py:121-124)
   const float* bias_fg;     // [128] or null
@@ -36,7 +39,8 @@ struct SkipHeadMaps {
   CUtensorMap h1;
 };
 struct SkipHeadParams {
-  int n_tiles, n_rows, W, Q, k_skip;
+  int n_tiles, n_rows;      // rows of the padded skip row space, B * Wp
+  int Wp, pad, W, Q, k_skip; // row j of a batch is time step tw = j - pad (pad = tw0 - tw_al leading rows are unused)
   float* logits;            // (B,Q,W) fp32
   const float* bias_skip;   // [256] = sum over layers of skip biases, or null
   const float* bias_p1;

@@ -23,13 +23,18 @@ struct PackLayout {     // byte offsets
   size_t total;
 };
 PackLayout pack_layout(const Model& m);
+// the flat-vector offsets of the N skip biases (int64) live behind the job table, at pl.jobs + this
+inline size_t skip_bias_offs_pos(const Model& m) { return sizeof(PackJob) * (size_t)(16 * m.n_layers + 32); }
 
 struct WsLayout {       // byte offsets
-  size_t X, x_stride, Zcat, H0, H1, X0f;
-  size_t DLG, DH1, DSK, DXa, DXb, DFG, Zf, DX0f;
+  size_t X, x_stride, XLO, Zcat, H0, H1, X0f;     // XLO: 2 ping-pong buffers of x_stride bytes
+  size_t DLG, DH1, DSK, DZcat, DXa, DXb, DFG, Zf, DX0f;
   size_t total;
 };
 WsLayout ws_layout(const Model& m, int B, int L);
+// padded skip row space: rows per batch Wp = L - tw_al, tw_al = floor((L-W)/128)*128
+inline int skip_tw_al(const Model& m, int L) { return ((m.rf - 1) / 128) * 128; }
+inline int skip_wp(const Model& m, int L) { return L - skip_tw_al(m, L); }
 
 int tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems, uint32_t box_rows);
 int tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batches, uint64_t pitch_elems,
@@ -39,14 +44,14 @@ struct BwdLayerMaps {
   CUtensorMap x;              // x_i (64, L, B)
   CUtensorMap w0, w1;         // W_fg taps [128][64]        (recompute)
   CUtensorMap wdT;            // [64 d][64 r]   box {64,64}
-  CUtensorMap wsT;            // [64 d][256 s]  box {64,64}
   CUtensorMap wfgT0, wfgT1;   // [64 r][128 o]  box {64,64}
 };
 struct BwdMaps {
   std::vector<BwdLayerMaps> layer;
-  CUtensorMap dlg, h0, h1, dh1, dsk;     // (256, B*W) box {64,128}
-  CUtensorMap dsk3;                      // (256, W, B) box {64,128,1}
+  CUtensorMap dlg, h0, h1, dh1, dsk;     // (256, Wp, B) box {64,128,1}   (padded skip row space)
+  CUtensorMap zcat, dzcat;               // (64 N, Wp, B)
   CUtensorMap p1T, p2T;                  // [256][256] box {64,256}
+  CUtensorMap wsTcat;                    // [64 N rows (layer, d)][256 s] box {64,256}
   CUtensorMap dxa, dxb, dfg, zf;         // (64|128, L, B)
 };
 int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int B, int L, const uint8_t* P, uint8_t* Wp,

@@ -9,6 +9,8 @@
 //   case 4  TMA store of a swizzled tile                        (round trip)
 //   case 5  M128 N64 K64 K-major                                (dense / dgrad shape)
 //   case 6  K-major A x MN-major B ([K rows][N cols] weights used untransposed)
+//   case 7  3-D TMA load with a negative row coordinate (zero fill, no bleed from the previous batch)
+//   case 8  3-D TMA store with rows clipped at the end of a batch (negative store coordinates TRAP: never used)
 #include "fast.cuh"
 #include "fast_layout.cuh"
 #include "tc05.cuh"
@@ -17,7 +19,7 @@ namespace wn {
 using namespace tc;
 namespace {
 
-constexpr int NCASE = 7;
+constexpr int NCASE = 9;
 
 __global__ void fill_kernel(__nv_bfloat16* p, int64_t n, uint32_t seed) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -32,6 +34,7 @@ __global__ void fill_kernel(__nv_bfloat16* p, int64_t n, uint32_t seed) {
 __global__ void __launch_bounds__(128, 1)
 selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB256,
                 const __grid_constant__ CUtensorMap tmB64, const __grid_constant__ CUtensorMap tmOut,
+                const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmOut3,
                 const __nv_bfloat16* __restrict__ gA, int mode, float* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -90,6 +93,14 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_expect_tx(&bar_ld, 16384);
         tma_load_2d(sA0, &tmA, &bar_ld, 64, 128);
         break;
+      case 7:
+        mbar_expect_tx(&bar_ld, 16384);
+        tma_load_3d(sA0, &tmA3, &bar_ld, 64, -8, 1);
+        break;
+      case 8:
+        mbar_expect_tx(&bar_ld, 16384);
+        tma_load_2d(sA0, &tmA, &bar_ld, 64, 128);
+        break;
       case 5:
         mbar_expect_tx(&bar_ld, 16384 + 8192);
         tma_load_2d(sA0, &tmA, &bar_ld, 0, 0);
@@ -121,8 +132,13 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_kmajor(a0, k), desc_mnmajor(b0, k, 8192), id, k > 0);
     }
     umma_commit(&bar_mma);
-    if (mode == 4) {
+    if (mode == 4 || mode == 7) {
       tma_store_2d(&tmOut, sA0, 0, 0);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+    if (mode == 8) {
+      tma_store_3d(&tmOut3, sA0, 0, 8, 1);       // rows 8..135 of batch 1 (64 rows): tile rows 0..55 land
       tma_store_commit();
       tma_store_wait_all();
     }
@@ -132,7 +148,7 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (mode == 3 || mode == 5 || mode == 6) N = 64;
   mbar_wait(&bar_mma, 0);
   tc_fence_after();
-  if (mode != 4) {
+  if (mode != 4 && mode < 7) {
     for (int c = 0; c < N / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_addr(tmem, warp * 32, c * 32), v);
@@ -164,6 +180,17 @@ __global__ void ref_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloa
   } else if (mode == 4) {
     if (n >= 64) active = false;
     else { ref = a(128 + m, 64 + n); got = __bfloat162float(out_bf[(int64_t)m * 64 + n]); }
+  } else if (mode == 7) {
+    if (n >= 64) active = false;
+    else { ref = m < 8 ? 0.f : a(128 + m - 8, 64 + n); got = __bfloat162float(out_bf[(int64_t)m * 64 + n]); }
+  } else if (mode == 8) {
+    if (n >= 64) active = false;
+    else {
+      // out_bf viewed as (2 batches, 64 rows, 64 cols); batch 1 row r >= 8 <- tile row r - 8; the rest untouched (0xFFFF)
+      const unsigned short bits = reinterpret_cast<const unsigned short*>(out_bf)[(int64_t)m * 64 + n];
+      if (m < 64 + 8) { ref = 0.f; got = bits == 0xFFFFu ? 0.f : 1.f; }
+      else { ref = a(128 + (m - 64) - 8, 64 + n); got = __bfloat162float(out_bf[(int64_t)m * 64 + n]); }
+    }
   } else if (mode == 5) {
     if (n >= 64) active = false;
     else for (int k = 0; k < 64; ++k) ref += a(m, k) * bq(n, k);
@@ -172,7 +199,7 @@ __global__ void ref_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloa
     else for (int k = 0; k < 64; ++k) ref += a(m, k) * bq(k, n);
   }
   if (!active) return;
-  if (mode != 4) got = out[(int64_t)m * 256 + n];
+  if (mode != 4 && mode < 7) got = out[(int64_t)m * 256 + n];
   float d = fabsf(got - ref);
   if (!(d == d)) d = 1e30f;
   atomicMax(reinterpret_cast<int*>(err), __float_as_int(d));
@@ -193,7 +220,9 @@ int fast_selftest(float* h_maxerr, int n_cases, cudaStream_t s) {
   WN_CHECK_CUDA(cudaMemsetAsync(err, 0, NCASE * 4, s));
   fill_kernel<<<64, 256, 0, s>>>(A, 256 * 128, 17u);
   fill_kernel<<<64, 256, 0, s>>>(B, 256 * 128, 91u);
-  CUtensorMap tmA, tmB256, tmB64, tmOut;
+  CUtensorMap tmA, tmB256, tmB64, tmOut, tmA3, tmOut3;
+  WN_PROPAGATE(tmap_3d(&tmA3, A, 128, 128, 2, 128, 128 * 128, 128));
+  WN_PROPAGATE(tmap_3d(&tmOut3, obf, 64, 64, 2, 64, 64 * 64, 128));
   WN_PROPAGATE(tmap_2d(&tmA, A, 128, 256, 128, 128));
   WN_PROPAGATE(tmap_2d(&tmB256, B, 128, 256, 128, 256));
   WN_PROPAGATE(tmap_2d(&tmB64, B, 128, 256, 128, 64));
@@ -203,7 +232,7 @@ int fast_selftest(float* h_maxerr, int n_cases, cudaStream_t s) {
   for (int c = 0; c < NCASE && c < n_cases; ++c) {
     WN_CHECK_CUDA(cudaMemsetAsync(out, 0xFF, 128 * 256 * 4, s));
     WN_CHECK_CUDA(cudaMemsetAsync(obf, 0xFF, 128 * 64 * 2, s));
-    selftest_kernel<<<1, 128, smem, s>>>(tmA, tmB256, tmB64, tmOut, A, c, out);
+    selftest_kernel<<<1, 128, smem, s>>>(tmA, tmB256, tmB64, tmOut, tmA3, tmOut3, A, c, out);
     WN_CHECK_LAUNCH();
     ref_kernel<<<128, 256, 0, s>>>(A, B, c, out, obf, err + c);
     WN_CHECK_LAUNCH();

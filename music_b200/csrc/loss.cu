@@ -218,6 +218,7 @@ extern "C" int wn_loss_fwd_bwd(const float* d_logits, const int64_t* d_target, i
   RowMap m{Q, W, rows};
   int64_t n_rows = (int64_t)B * W;
   cudaStream_t s = (cudaStream_t)stream;
+  WN_PROF("loss_fwd_bwd", s);
   loss_fwd_bwd_kernel<<<(unsigned)ceil_div(n_rows, 8), 256, 0, s>>>(d_logits, d_target, m, n_rows, grad_scale,
                                                                     (float*)d_scratch, d_dlogits);
   WN_CHECK_LAUNCH();

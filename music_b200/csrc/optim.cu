@@ -65,6 +65,7 @@ extern "C" int wn_adam_step(float* d_params, const float* d_grads, float* d_m, f
   WN_REQUIRE(n > 0 && step >= 1, WN_ERR_INVALID, "wn_adam_step: bad n/step");
   double bc1 = 1.0 - pow((double)beta1, (double)step);
   double bc2 = 1.0 - pow((double)beta2, (double)step);
+  WN_PROF("adam", (cudaStream_t)stream);
   adam_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(d_params, d_grads, d_m, d_v, n, lr, beta1, beta2, eps, (float)bc1,
                                                                (float)sqrt(bc2));
   WN_CHECK_LAUNCH();

@@ -84,10 +84,10 @@ def test_forward_grads_subsampled_golden(golden, name):
     x, idx, tgt = _inputs(z)
     net = make_net(z, st)
     sub = int(z["rows"][1] - z["rows"][0])
-    logits = net.forward_logits(indices=idx.cuda())
-    assert max_rel(logits.detach().cpu().numpy()[:, :, ::sub], z["logits_cols"]) < TOL
     probs = net.forward_indices(idx.cuda())
     assert max_rel(probs.detach().cpu().numpy()[z["rows"]], z["probs_rows"]) < TOL
+    logits = net.forward_logits(indices=idx.cuda())
+    assert max_rel(logits.detach().cpu().numpy()[:, :, ::sub], z["logits_cols"]) < TOL
     loss, dlogits = fused_loss(logits.detach(), tgt.cuda(), L.ROWS_REFERENCE, True)
     assert abs(float(loss) - float(z["loss"])) < 1e-5
     logits.backward(dlogits)
