@@ -8,6 +8,8 @@
 //                       their partial sum in TMEM and flush it once with fp32 atomics.
 //  block_bwd_kernel   : per residual block: recompute [f|g] (UMMA), dz = dx_{i+1} Wd (UMMA) + dzs,
 //                       gate backward in the epilogue -> dFG and z tiles (TMA stores).
+#include <stdlib.h>
+
 #include "check_kernels.cuh"
 #include "fast_bwd_kernels.cuh"
 #include "fast_layout.cuh"
@@ -400,6 +402,222 @@ block_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+// ========================================================================================= block_bwd2
+// Persistent CTA per SM, 10 warps: 0-7 epilogue (two warps per TMEM lane quarter, each a 32-column half),
+// 8 TMA producer, 9 MMA issuer.  TMEM: [0,128) f|g, [128,192) dz, [192,320) dW_fg (both taps), [320,384) dW_dense.
+struct Bwd2Smem {
+  static constexpr uint32_t W0 = 0, W1 = TILE, WDT = 2 * TILE;                 // resident weights (40 KB)
+  static constexpr uint32_t IN = 2 * TILE + 8192, IN_STAGE = 3 * TILE;         // 2 x {x tap0, x tap1, dx_{i+1}}
+  static constexpr uint32_t DF = IN + 2 * IN_STAGE, DG = DF + TILE, Z = DG + TILE;
+  static constexpr uint32_t TOTAL = Z + TILE;                                  // 184 KB
+};
+__device__ __forceinline__ void epi8_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(320, 1)
+block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
+                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_dx,
+                  const __grid_constant__ CUtensorMap tm_wdT, const __grid_constant__ CUtensorMap tm_dfg, BlockBwd2Params pp) {
+  const BlockBwdParams& p = pp.b;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t w_full, in_full[2], in_empty[2], acc_full, acc_empty, out_full, out_empty, wg_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&in_full[i], 1);
+      mbar_init(&in_empty[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, 1);
+    mbar_init(&out_full, 1);
+    mbar_init(&out_empty, 1);
+    mbar_init(&wg_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t sbase = smem_u32(sm);
+  const int n_items = pp.n_batches * p.tiles_per_batch;
+  const bool dense = p.has_dense != 0;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(&w_full, 2 * TILE + (dense ? 8192 : 0));
+      tma_load_2d(sm + Bwd2Smem::W0, &tm_w0, &w_full, 0, 0);
+      tma_load_2d(sm + Bwd2Smem::W1, &tm_w1, &w_full, 0, 0);
+      if (dense) tma_load_2d(sm + Bwd2Smem::WDT, &tm_wdT, &w_full, 0, 0);
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t sph = (it >> 1) & 1;
+        const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
+        mbar_wait(&in_empty[st], sph ^ 1);
+        uint8_t* si = sm + Bwd2Smem::IN + st * Bwd2Smem::IN_STAGE;
+        mbar_expect_tx(&in_full[st], (dense ? 3 : 2) * TILE);
+        tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b);
+        tma_load_3d(si + TILE, &tm_x, &in_full[st], 0, tau0, b);
+        if (dense) tma_load_3d(si + 2 * TILE, &tm_dx, &in_full[st], 0, tau0, b);
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0 && (int)blockIdx.x < n_items) {
+      constexpr uint32_t id_fg = idesc_bf16(128, 128, 0, 0), id_dz = idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t id_wfg = idesc_bf16(128, 128, 1, 1), id_wd = idesc_bf16(128, 64, 1, 1);
+      mbar_wait(&w_full, 0);
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t sph = (it >> 1) & 1, ph = it & 1;
+        const uint32_t si = sbase + Bwd2Smem::IN + st * Bwd2Smem::IN_STAGE;
+        mbar_wait(&in_full[st], sph);
+        mbar_wait(&acc_empty, ph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_kmajor(si, k), desc_kmajor(sbase + Bwd2Smem::W0, k), id_fg, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_kmajor(si + TILE, k), desc_kmajor(sbase + Bwd2Smem::W1, k), id_fg, true);
+        if (dense) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + 128, desc_kmajor(si + 2 * TILE, k), desc_kmajor(sbase + Bwd2Smem::WDT, k), id_dz, k > 0);
+        }
+        umma_commit(&acc_full);
+        // weight gradients of this tile once the epilogue has produced dF | dG and z in shared memory
+        mbar_wait(&out_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
+          umma_bf16(tmem + 192, desc_mnmajor(sbase + Bwd2Smem::DF, k, TILE), desc_mnmajor(si, k, TILE), id_wfg, (it | (uint32_t)k) != 0);
+        if (dense) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dW_dense[r, d] += sum_t dx_{i+1}[t, r] * z[t, d]   (rows 64..127 of the tile are unused)
+            umma_bf16(tmem + 320, desc_mnmajor(si + 2 * TILE, k, 0), desc_mnmajor(sbase + Bwd2Smem::Z, k, TILE), id_wd,
+                      (it | (uint32_t)k) != 0);
+        }
+        umma_commit(&in_empty[st]);
+        umma_commit(&out_empty);
+      }
+      umma_commit(&wg_done);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps 0-7
+    const int q4 = warp & 3, half = warp >> 2;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, 0);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
+      const int tau = tau0 + row;
+      const bool valid = tau >= p.s_out && tau < p.L;
+      const bool in_w = valid && tau >= p.tw0;
+      uint32_t zs[16];
+      if (in_w) {       // issue the global read of the skip-path gradient before waiting on the MMA
+        const __nv_bfloat16* dzs_row = p.dzs + ((int64_t)b * p.Wp + (tau - p.tw_al)) * p.dzs_pitch + p.dzs_col + half * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 a4 = *reinterpret_cast<const uint4*>(dzs_row + q * 8);
+          zs[4 * q] = a4.x; zs[4 * q + 1] = a4.y; zs[4 * q + 2] = a4.z; zs[4 * q + 3] = a4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) zs[j] = 0u;
+      }
+      mbar_wait(&acc_full, ph);
+      tc_fence_after();
+      uint32_t f[32], g[32], dzv[32];
+      tmem_ld32(lane_addr + half * 32, f);
+      tmem_ld32(lane_addr + 64 + half * 32, g);
+      if (dense) tmem_ld32(lane_addr + 128 + half * 32, dzv);
+      tmem_ld_wait();
+      uint32_t pz[16], pf[16], pg[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float fv[2] = {__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1])};
+        float gv[2] = {__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1])};
+        const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
+        float dz[2] = {__low2float(s2), __high2float(s2)};
+        if (dense) {
+          dz[0] += __uint_as_float(dzv[2 * j]);
+          dz[1] += __uint_as_float(dzv[2 * j + 1]);
+        }
+        float zo[2], df[2], dg[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (p.bias_fg) {
+            fv[e] += p.bias_fg[half * 32 + 2 * j + e];
+            gv[e] += p.bias_fg[64 + half * 32 + 2 * j + e];
+          }
+          const float t = tanh_fast(fv[e]), sg = sigmoid_fast(gv[e]);
+          zo[e] = valid ? t * sg : 0.f;
+          df[e] = valid ? dz[e] * sg * (1.f - t * t) : 0.f;
+          dg[e] = valid ? dz[e] * t * sg * (1.f - sg) : 0.f;
+        }
+        pz[j] = pack_bf16(zo[0], zo[1]);
+        pf[j] = pack_bf16(df[0], df[1]);
+        pg[j] = pack_bf16(dg[0], dg[1]);
+      }
+      if (it > 0) mbar_wait(&out_empty, ph ^ 1);     // the previous tile's weight-gradient MMAs have read dF | dG | z
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t o = sw128_chunk(row, half * 4 + q);
+        *reinterpret_cast<uint4*>(sm + Bwd2Smem::Z + o) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + Bwd2Smem::DF + o) = make_uint4(pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + Bwd2Smem::DG + o) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      epi8_bar_sync();
+      if (tid == 0) {
+        mbar_arrive(&acc_empty);
+        mbar_arrive(&out_full);
+        tma_store_3d(&tm_dfg, sm + Bwd2Smem::DF, 0, tau0, b);
+        tma_store_3d(&tm_dfg, sm + Bwd2Smem::DG, 64, tau0, b);
+        tma_store_commit();
+        tma_store_wait_read();
+      }
+      epi8_bar_sync();
+    }
+    // ---- flush the weight-gradient accumulators (fp32 atomics into the flat gradient vector)
+    if ((int)blockIdx.x < n_items) {
+      mbar_wait(&wg_done, 0);
+      tc_fence_after();
+      const int m = row;                       // accumulator row
+      {   // dW_fg: columns [64 half, 64 half + 64) = tap `half`, r = column % 64
+        float* base = (m < 64 ? pp.g_filt : pp.g_gate) + (int64_t)(m & 63) * 128 + half;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + 192 + half * 64 + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(base + (c * 32 + j) * 2, __uint_as_float(v[j]));
+        }
+      }
+      if (dense) {   // dW_dense[r = m][d]: columns [32 half, 32 half + 32)
+        uint32_t v[32];
+        tmem_ld32(lane_addr + 320 + half * 32, v);
+        tmem_ld_wait();
+        if (m < 64) {
+          float* base = pp.g_dense + (int64_t)m * 64 + half * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(base + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 // ============================================================================================ SIMT helpers
 // dlogits (B,Q,W) fp32 -> DLG [B][Wp][Q] bf16 in the padded skip row space (pad rows = 0)
 __global__ void __launch_bounds__(256) dlogits_transpose_kernel(const float* __restrict__ dl, __nv_bfloat16* __restrict__ out, int Q,
@@ -558,6 +776,18 @@ int launch_block_bwd(const BlockBwdMaps& m, const BlockBwdParams& p, int n_ctas,
   return WN_OK;
 }
 
+int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStream_t s) {
+  static bool once = false;
+  const int smem = Bwd2Smem::TOTAL + 1024;
+  if (!once) { WN_PROPAGATE(set_smem(block_bwd2_kernel, smem)); once = true; }
+  const int n_items = p.n_batches * p.b.tiles_per_batch;
+  if (n_items <= 0) return WN_OK;
+  WN_PROF("block_bwd2", s);
+  block_bwd2_kernel<<<std::min(n_items, g_sm_count), 320, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
 // =============================================================================================== host
 int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int B, int L, const uint8_t* P, uint8_t* Wp,
                    const std::vector<CUtensorMap>& xm, BwdMaps* out) {
@@ -689,6 +919,12 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     }
   }
   // ---- residual blocks, last to first
+  static int unfused_env = -1;
+  if (unfused_env < 0) {
+    const char* e = getenv("WN_BWD_UNFUSED");
+    unfused_env = (e && e[0] == '1') ? 1 : 0;
+  }
+  const bool fused = unfused_env == 0;   // block_bwd2: weight gradients accumulated inside the block kernel
   const int tiles_total = (int)ceil_div(L, 128);
   for (int i = N - 1; i >= 0; --i) {
     const LayerP& l = m.layers[i];
@@ -707,14 +943,22 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       bp.tw0 = L - W; bp.tw_al = tw_al; bp.Wp = Wpad;
       bp.dzs = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DZcat); bp.dzs_pitch = 64 * N; bp.dzs_col = 64 * i;
       bp.bias_fg = bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
-      WN_PROPAGATE(launch_block_bwd(bm, bp, B * tpb, s));
-      WN_DEBUG_SYNC("block_bwd", s);
+      if (fused) {
+        BlockBwd2Params b2{};
+        b2.b = bp; b2.n_batches = B;
+        b2.g_filt = G + l.filt.w; b2.g_gate = G + l.gate.w; b2.g_dense = has_dense ? G + l.dense.w : nullptr;
+        WN_PROPAGATE(launch_block_bwd2(bm, b2, s));
+        WN_DEBUG_SYNC("block_bwd2", s);
+      } else {
+        WN_PROPAGATE(launch_block_bwd(bm, bp, B * tpb, s));
+        WN_DEBUG_SYNC("block_bwd", s);
+      }
     }
     if (bias) {   // dFG columns [0,64) = filter, [64,128) = gate: two separate bias vectors in the flat layout
       WN_PROPAGATE(launch_colsum_bf16_split(Wp + wl.DFG, B, L, s_out, G + l.filt.b, G + l.gate.b, s));
       if (has_dense) WN_PROPAGATE(launch_colsum_bf16(Wp + dx_next_off, 64, B, L, s_out, L, G + l.dense.b, s));
     }
-    {   // dW_filter / dW_gate, both taps: dFG^T x_i[tau - d], dFG^T x_i[tau]
+    if (!fused) {   // dW_filter / dW_gate, both taps: dFG^T x_i[tau - d], dFG^T x_i[tau]
       GemmTnMaps tm{};
       tm.a = M.dfg; tm.b[0] = M.layer[i].x; tm.b[1] = M.layer[i].x;
       GemmTnParams tp{};
@@ -725,7 +969,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       WN_PROPAGATE(launch_gemm_tn(2, tm, tp, s));
       WN_DEBUG_SYNC("gemm_tn dWfg", s);
     }
-    if (has_dense) {   // dW_dense = dx_{i+1}^T z
+    if (has_dense && !fused) {   // dW_dense = dx_{i+1}^T z
       GemmTnMaps tm{};
       tm.a = dx_next; tm.b[0] = M.zf; tm.b[1] = M.zf;
       GemmTnParams tp{};

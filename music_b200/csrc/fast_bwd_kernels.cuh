@@ -71,4 +71,17 @@ struct BlockBwdParams {
 };
 int launch_block_bwd(const BlockBwdMaps& m, const BlockBwdParams& p, int n_ctas, cudaStream_t s);
 
+// ---------------------------------------------------------------------------------------------
+// block_bwd2: persistent, warp-specialised version that also accumulates the block's weight gradients
+// (dW_filter, dW_gate for both taps and dW_dense) in TMEM while the operands are in shared memory.
+// ---------------------------------------------------------------------------------------------
+struct BlockBwd2Params {
+  BlockBwdParams b;
+  int n_batches;
+  float* g_filt;      // dW filter (D,R,2) in the flat gradient vector
+  float* g_gate;      // dW gate
+  float* g_dense;     // dW dense (R,D,1) or null
+};
+int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStream_t s);
+
 }  // namespace wn

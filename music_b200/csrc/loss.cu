@@ -162,6 +162,56 @@ __global__ void __launch_bounds__(256) loss_fwd_bwd_kernel(const float* __restri
   }
 }
 
+// Q == 256, reference rows (contiguous): one warp per row, 8 contiguous floats per lane (two 16-byte loads),
+// small register footprint so that >= 32 warps per SM are in flight: HBM-bound (1 KB read + 1 KB written per row).
+__global__ void __launch_bounds__(256, 4) loss_fwd_bwd_q256_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
+                                                                   int64_t n_rows, float grad_scale, float* __restrict__ row_loss,
+                                                                   float* __restrict__ dlogits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const float4* src = reinterpret_cast<const float4*>(logits + r * 256 + lane * 8);
+  const float4 a = src[0], b4 = src[1];
+  float p[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+  float mx = p[0];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) mx = fmaxf(mx, p[j]);
+  mx = warp_max(mx);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    p[j] = expf(p[j] - mx);
+    s += p[j];
+  }
+  s = warp_sum(s);
+  const float inv = 1.f / s;
+  const int y = (int)target[r];
+  float py = 0.f, s2 = 0.f, q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    p[j] *= inv;
+    if (lane * 8 + j == y) py = p[j];
+    q[j] = expf(p[j]);
+    s2 += q[j];
+  }
+  py = warp_sum(py);
+  s2 = warp_sum(s2);
+  if (lane == 0) row_loss[r] = logf(s2) - py;
+  if (dlogits) {
+    const float inv2 = 1.f / s2, inv_n = grad_scale / (float)n_rows;
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      q[j] = (q[j] * inv2 - ((lane * 8 + j == y) ? 1.f : 0.f)) * inv_n;
+      dot += q[j] * p[j];
+    }
+    dot = warp_sum(dot);
+    float4* dst = reinterpret_cast<float4*>(dlogits + r * 256 + lane * 8);
+    dst[0] = make_float4(p[0] * (q[0] - dot), p[1] * (q[1] - dot), p[2] * (q[2] - dot), p[3] * (q[3] - dot));
+    dst[1] = make_float4(p[4] * (q[4] - dot), p[5] * (q[5] - dot), p[6] * (q[6] - dot), p[7] * (q[7] - dot));
+  }
+}
+
 // deterministic mean of n floats (single block, fixed order)
 __global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ v, int64_t n, float* __restrict__ out) {
   __shared__ double sh[32];
@@ -219,8 +269,12 @@ extern "C" int wn_loss_fwd_bwd(const float* d_logits, const int64_t* d_target, i
   int64_t n_rows = (int64_t)B * W;
   cudaStream_t s = (cudaStream_t)stream;
   WN_PROF("loss_fwd_bwd", s);
-  loss_fwd_bwd_kernel<<<(unsigned)ceil_div(n_rows, 8), 256, 0, s>>>(d_logits, d_target, m, n_rows, grad_scale,
-                                                                    (float*)d_scratch, d_dlogits);
+  if (Q == 256 && rows == WN_ROWS_REFERENCE)
+    loss_fwd_bwd_q256_kernel<<<(unsigned)ceil_div(n_rows, 8), 256, 0, s>>>(d_logits, d_target, n_rows, grad_scale,
+                                                                           (float*)d_scratch, d_dlogits);
+  else
+    loss_fwd_bwd_kernel<<<(unsigned)ceil_div(n_rows, 8), 256, 0, s>>>(d_logits, d_target, m, n_rows, grad_scale,
+                                                                      (float*)d_scratch, d_dlogits);
   WN_CHECK_LAUNCH();
   mean_kernel<<<1, 1024, 0, s>>>((const float*)d_scratch, n_rows, d_loss);
   WN_CHECK_LAUNCH();
