@@ -26,14 +26,15 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 // ============================================================================================ gemm_nt
 template <int NT>
 struct NtCfg {
-  static constexpr int STAGES = NT == 256 ? 3 : 4;
+  static constexpr int STAGES = NT == 256 ? 3 : 2;
   static constexpr uint32_t A_BYTES = TILE, B_BYTES = NT * 128, STAGE = A_BYTES + B_BYTES;
   static constexpr uint32_t OUT_OFF = STAGES * STAGE, TOTAL = OUT_OFF + (NT / 64) * TILE;
   static constexpr int TMEM_COLS = NT == 256 ? 512 : 128;
+  static constexpr int CTAS_PER_SM = NT == 256 ? 1 : 3;      // NT=64: 65 KB smem, 128 TMEM columns per CTA
 };
 
 template <int NT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, NtCfg<NT>::CTAS_PER_SM)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                const __grid_constant__ CUtensorMap tmOut, GemmNtParams p) {
@@ -186,6 +187,18 @@ __global__ void __launch_bounds__(192, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmB1, GemmTnParams p) {
   using Cfg = TnCfg<NB>;
+  if (p.y_layers > 0) {      // derive this y-slice's operands (uniform over the CTA)
+    const int mt = blockIdx.y & 1, g = blockIdx.y >> 1;
+    p.a_col0 = 128 * mt;
+    p.out0 += (int64_t)128 * mt * p.s_m;
+    p.out1 += (int64_t)128 * mt * p.s_m;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int li = 4 * g + j;
+      p.b_col[j] = 64 * li;                                   // past the last layer: outside the tensor -> zero fill
+      p.blk_off[j] = p.y_off0 + (int64_t)min(li, p.y_layers - 1) * p.y_stride;
+    }
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full[Cfg::STAGES], empty[Cfg::STAGES], acc_full;
@@ -403,17 +416,17 @@ block_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 }
 
 // ========================================================================================= block_bwd2
-// Persistent CTA per SM, 10 warps: 0-7 epilogue (two warps per TMEM lane quarter, each a 32-column half),
-// 8 TMA producer, 9 MMA issuer.  TMEM: [0,128) f|g, [128,192) dz, [192,320) dW_fg (both taps), [320,384) dW_dense.
+// Persistent CTA per SM, 18 warps: 0-15 epilogue (four warps per TMEM lane quarter, 16 columns each),
+// 16 TMA producer, 17 MMA issuer.  TMEM: [0,128) f|g, [128,192) dz, [192,320) dW_fg (both taps), [320,384) dW_dense.
 struct Bwd2Smem {
   static constexpr uint32_t W0 = 0, W1 = TILE, WDT = 2 * TILE;                 // resident weights (40 KB)
   static constexpr uint32_t IN = 2 * TILE + 8192, IN_STAGE = 3 * TILE;         // 2 x {x tap0, x tap1, dx_{i+1}}
   static constexpr uint32_t DF = IN + 2 * IN_STAGE, DG = DF + TILE, Z = DG + TILE;
   static constexpr uint32_t TOTAL = Z + TILE;                                  // 184 KB
 };
-__device__ __forceinline__ void epi8_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi8_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
                   const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_dx,
                   const __grid_constant__ CUtensorMap tm_wdT, const __grid_constant__ CUtensorMap tm_dfg, BlockBwd2Params pp) {
@@ -445,7 +458,7 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const int n_items = pp.n_batches * p.tiles_per_batch;
   const bool dense = p.has_dense != 0;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(&w_full, 2 * TILE + (dense ? 8192 : 0));
@@ -465,7 +478,7 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (dense) tma_load_3d(si + 2 * TILE, &tm_dx, &in_full[st], 0, tau0, b);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && (int)blockIdx.x < n_items) {
       constexpr uint32_t id_fg = idesc_bf16(128, 128, 0, 0), id_dz = idesc_bf16(128, 64, 0, 0);
@@ -507,8 +520,8 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       umma_commit(&wg_done);
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps 0-7
-    const int q4 = warp & 3, half = warp >> 2;
+    // ------------------------------------------------------------ epilogue warps 0-15
+    const int q4 = warp & 3, cg = warp >> 2;          // TMEM lane quarter, 16-column group
     const int row = q4 * 32 + lane;
     const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, 0);
     uint32_t it = 0;
@@ -518,28 +531,28 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int tau = tau0 + row;
       const bool valid = tau >= p.s_out && tau < p.L;
       const bool in_w = valid && tau >= p.tw0;
-      uint32_t zs[16];
+      uint32_t zs[8];
       if (in_w) {       // issue the global read of the skip-path gradient before waiting on the MMA
-        const __nv_bfloat16* dzs_row = p.dzs + ((int64_t)b * p.Wp + (tau - p.tw_al)) * p.dzs_pitch + p.dzs_col + half * 32;
+        const __nv_bfloat16* dzs_row = p.dzs + ((int64_t)b * p.Wp + (tau - p.tw_al)) * p.dzs_pitch + p.dzs_col + cg * 16;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           const uint4 a4 = *reinterpret_cast<const uint4*>(dzs_row + q * 8);
           zs[4 * q] = a4.x; zs[4 * q + 1] = a4.y; zs[4 * q + 2] = a4.z; zs[4 * q + 3] = a4.w;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) zs[j] = 0u;
+        for (int j = 0; j < 8; ++j) zs[j] = 0u;
       }
       mbar_wait(&acc_full, ph);
       tc_fence_after();
-      uint32_t f[32], g[32], dzv[32];
-      tmem_ld32(lane_addr + half * 32, f);
-      tmem_ld32(lane_addr + 64 + half * 32, g);
-      if (dense) tmem_ld32(lane_addr + 128 + half * 32, dzv);
+      uint32_t f[16], g[16], dzv[16];
+      tmem_ld16(lane_addr + cg * 16, f);
+      tmem_ld16(lane_addr + 64 + cg * 16, g);
+      if (dense) tmem_ld16(lane_addr + 128 + cg * 16, dzv);
       tmem_ld_wait();
-      uint32_t pz[16], pf[16], pg[16];
+      uint32_t pz[8], pf[8], pg[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 8; ++j) {
         float fv[2] = {__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1])};
         float gv[2] = {__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1])};
         const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
@@ -552,13 +565,14 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           if (p.bias_fg) {
-            fv[e] += p.bias_fg[half * 32 + 2 * j + e];
-            gv[e] += p.bias_fg[64 + half * 32 + 2 * j + e];
+            fv[e] += p.bias_fg[cg * 16 + 2 * j + e];
+            gv[e] += p.bias_fg[64 + cg * 16 + 2 * j + e];
           }
           const float t = tanh_fast(fv[e]), sg = sigmoid_fast(gv[e]);
-          zo[e] = valid ? t * sg : 0.f;
+          const float zz = t * sg;
+          zo[e] = valid ? zz : 0.f;
           df[e] = valid ? dz[e] * sg * (1.f - t * t) : 0.f;
-          dg[e] = valid ? dz[e] * t * sg * (1.f - sg) : 0.f;
+          dg[e] = valid ? dz[e] * zz * (1.f - sg) : 0.f;
         }
         pz[j] = pack_bf16(zo[0], zo[1]);
         pf[j] = pack_bf16(df[0], df[1]);
@@ -566,8 +580,8 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       if (it > 0) mbar_wait(&out_empty, ph ^ 1);     // the previous tile's weight-gradient MMAs have read dF | dG | z
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t o = sw128_chunk(row, half * 4 + q);
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t o = sw128_chunk(row, cg * 2 + q);
         *reinterpret_cast<uint4*>(sm + Bwd2Smem::Z + o) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
         *reinterpret_cast<uint4*>(sm + Bwd2Smem::DF + o) = make_uint4(pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
         *reinterpret_cast<uint4*>(sm + Bwd2Smem::DG + o) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
@@ -590,25 +604,23 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_wait(&wg_done, 0);
       tc_fence_after();
       const int m = row;                       // accumulator row
-      {   // dW_fg: columns [64 half, 64 half + 64) = tap `half`, r = column % 64
-        float* base = (m < 64 ? pp.g_filt : pp.g_gate) + (int64_t)(m & 63) * 128 + half;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(lane_addr + 192 + half * 64 + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(base + (c * 32 + j) * 2, __uint_as_float(v[j]));
-        }
-      }
-      if (dense) {   // dW_dense[r = m][d]: columns [32 half, 32 half + 32)
+      {   // dW_fg: 128 columns = (tap, r); this warp flushes columns [32 cg, 32 cg + 32): tap = cg / 2
+        const int tap = cg >> 1, r0 = (cg & 1) * 32;
+        float* base = (m < 64 ? pp.g_filt : pp.g_gate) + (int64_t)(m & 63) * 128 + tap + r0 * 2;
         uint32_t v[32];
-        tmem_ld32(lane_addr + 320 + half * 32, v);
+        tmem_ld32(lane_addr + 192 + cg * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(base + j * 2, __uint_as_float(v[j]));
+      }
+      if (dense) {   // dW_dense[r = m][d]: columns [16 cg, 16 cg + 16)
+        uint32_t v[16];
+        tmem_ld16(lane_addr + 320 + cg * 16, v);
         tmem_ld_wait();
         if (m < 64) {
-          float* base = pp.g_dense + (int64_t)m * 64 + half * 32;
+          float* base = pp.g_dense + (int64_t)m * 64 + cg * 16;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(base + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 16; ++j) atomicAdd(base + j, __uint_as_float(v[j]));
         }
       }
     }
@@ -718,7 +730,7 @@ int launch_colsum_bf16_split(const void* src, int B, int64_t rows_per_batch, int
 int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStream_t s) {
   const int n_items = p.n_batches * p.tiles_per_batch * p.n_ntiles;
   if (n_items <= 0) return WN_OK;
-  const int grid = std::min(n_items, g_sm_count);
+  const int grid = std::min(n_items, g_sm_count * (NT == 64 ? NtCfg<64>::CTAS_PER_SM : 1));
   WN_PROF(p.tag ? p.tag : "gemm_nt", s);
   if (NT == 256) {
     static bool once = false;
@@ -741,7 +753,12 @@ int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStrea
 int launch_gemm_tn(int NB, const GemmTnMaps& m, const GemmTnParams& p, cudaStream_t s) {
   const int n_items = p.n_batches * p.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
-  const int grid = std::min(n_items, g_sm_count);
+  int gx = std::min(n_items, g_sm_count), gy = 1;
+  if (p.y_layers > 0) {
+    gy = 2 * (int)ceil_div(p.y_layers, 4);
+    gx = std::max(1, std::min(n_items, g_sm_count / gy));
+  }
+  const dim3 grid((unsigned)gx, (unsigned)gy);
   WN_PROF(p.tag ? p.tag : "gemm_tn", s);
   if (NB == 4) {
     static bool once = false;
@@ -783,7 +800,7 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   const int n_items = p.n_batches * p.b.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
   WN_PROF("block_bwd2", s);
-  block_bwd2_kernel<<<std::min(n_items, g_sm_count), 320, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p);
+  block_bwd2_kernel<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -896,27 +913,19 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
     WN_DEBUG_SYNC("gemm_nt dZcat", s);
   }
-  // ---- skip weight gradients for all layers: dWs_i = dSK^T Zcat[:, 64 i : 64 i + 64]
-  for (int mt = 0; mt < 2; ++mt) {
-    for (int n0 = 0; n0 < N; n0 += 4) {
-      GemmTnMaps tm{};
-      tm.a = M.dsk; tm.b[0] = M.zcat; tm.b[1] = M.zcat;
-      GemmTnParams tp{};
-      tp.n_batches = B; tp.tile0 = 0; tp.tiles_per_batch = skip_tiles;
-      tp.a_col0 = 128 * mt; tp.m_valid = 128;
-      const int nb = std::min(4, N - n0);
-      const int NB = nb >= 3 ? 4 : nb;       // kernel variants: 1, 2, 4 column blocks
-      float* base = G + (int64_t)128 * mt * 64;
-      for (int j = 0; j < 4; ++j) {
-        const int li = std::min(n0 + j, N - 1);
-        tp.b_map[j] = 0; tp.b_row_off[j] = 0;
-        tp.b_col[j] = (n0 + j < N) ? 64 * (n0 + j) : 64 * N;      // past the last layer: TMA zero fill -> adds 0
-        tp.blk_off[j] = m.layers[li].skip.w;
-      }
-      tp.out0 = base; tp.out1 = base + 64 * 64; tp.s_m = 64; tp.s_n = 1; tp.tag = "gemm_tn_dWs";
-      WN_PROPAGATE(launch_gemm_tn(NB, tm, tp, s));
-      WN_DEBUG_SYNC("gemm_tn dWs", s);
-    }
+  // ---- skip weight gradients for all layers in ONE launch: dWs_i = dSK^T Zcat[:, 64 i : 64 i + 64]
+  //      (grid.y = 2 m-tiles x ceil(N/4) layer groups run concurrently, so dSK and Zcat tiles are shared through L2)
+  {
+    GemmTnMaps tm{};
+    tm.a = M.dsk; tm.b[0] = M.zcat; tm.b[1] = M.zcat;
+    GemmTnParams tp{};
+    tp.n_batches = B; tp.tile0 = 0; tp.tiles_per_batch = skip_tiles; tp.m_valid = 128;
+    tp.out0 = G; tp.out1 = G + 64 * 64; tp.s_m = 64; tp.s_n = 1;
+    tp.y_layers = N; tp.y_off0 = m.layers[0].skip.w;
+    tp.y_stride = N > 1 ? m.layers[1].skip.w - m.layers[0].skip.w : 0;
+    tp.tag = "gemm_tn_dWs";
+    WN_PROPAGATE(launch_gemm_tn(4, tm, tp, s));
+    WN_DEBUG_SYNC("gemm_tn dWs", s);
   }
   // ---- residual blocks, last to first
   static int unfused_env = -1;

@@ -47,6 +47,11 @@ struct GemmTnParams {
   float* out0;
   float* out1;
   int64_t s_m, s_n, blk_off[4];
+  // "all layers" mode (skip weight gradients): blockIdx.y = m_tile + 2 * group; group g covers layers 4g..4g+3:
+  // a_col0 = 128 m_tile, b_col[j] = 64 (4g + j), blk_off[j] = y_off0 + min(4g + j, y_layers - 1) * y_stride,
+  // out0/out1 shifted by 128 m_tile * s_m.  y_layers == 0: disabled.
+  int y_layers;
+  int64_t y_off0, y_stride;
   const char* tag;              // profiler label (host only)
 };
 int launch_gemm_tn(int NB, const GemmTnMaps& m, const GemmTnParams& p, cudaStream_t s);

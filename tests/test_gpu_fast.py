@@ -102,29 +102,33 @@ def _grad_errors(net, g_ref):
     return errs
 
 
-@pytest.mark.parametrize("positive", [True, False])
+@pytest.mark.parametrize("noflip", [True, False])
 @pytest.mark.parametrize("dil,B,W", [([1, 2, 4, 8, 16, 32], 2, 300), ([2 ** i for i in range(10)] * 3, 2, 200)])
-def test_backward_gradients_vs_oracle(dil, B, W, positive):
+def test_backward_gradients_vs_oracle(dil, B, W, noflip):
     """bf16 tensor-core backward (recompute + dgrad + wgrad kernels) against autograd on the oracle.
 
-    positive=True : all weights made positive, so every ReLU input is positive and no ReLU mask can flip
-                    between the bf16 forward and the fp32 oracle: isolates the kernels' own accuracy
-                    (bf16 operands through up to 30 layers): 3e-2 relative l2 per parameter tensor.
-    positive=False: ordinary random weights.  ~0.5 % of the head's ReLU inputs sit within bf16 forward error
-                    of zero and flip their mask, each flip is a full-size error on that element, so the
-                    gradient error is ~sqrt(flip fraction) ~ 7 % however accurate the kernels are:
-                    bound 0.12 per tensor and cosine similarity of the whole gradient > 0.99."""
+    noflip=True : biased model whose two ReLU inputs (skip sum, post_process_1 output) are pushed well above
+                  zero, so no ReLU mask can differ between the bf16 forward and the fp32 oracle.  This isolates
+                  the kernels' own accuracy (bf16 operands through up to 30 layers): 4e-2 relative l2 per tensor.
+    noflip=False: ordinary unbiased random weights.  ~0.5 % of the head's ReLU inputs sit within bf16 forward
+                  error of zero and flip their mask; each flip is a full-size error on that element, so the
+                  gradient error is ~sqrt(flip fraction) ~ 7 % however accurate the kernels are:
+                  bound 0.12 per tensor and cosine similarity of the whole gradient > 0.99."""
     from music_b200.wavenet.train import Trainer
-    st = O.init_wavenet_state(dil, 64, 64, 256, 256, False, seed=5, scale=1.0)
-    if positive:
-        st = {k: v.abs() * (0.5 if "dilation_layer_stack" in k else 1.0) for k, v in st.items()}
+    bias = noflip
+    st = O.init_wavenet_state(dil, 64, 64, 256, 256, bias, seed=5, scale=1.0)
+    if noflip:
+        for i in range(len(dil)):
+            st[f"dilation_layer_stack.{4 * i + 3}.bias"] = torch.full((256,), 0.3)
+        st["post_process_1.bias"] = torch.full((256,), 2.0)
+        st["post_process_1.weight"] = st["post_process_1.weight"] * 0.1
     rf = O.receptive_field(2, dil)
     L = rf + W - 1
     g = torch.Generator().manual_seed(5)
     idx = torch.randint(0, 256, (B, L + 1), generator=g)
     tgt = idx[:, rf:rf + W].contiguous()
     loss_ref, g_ref = O.grads(st, dil, O.one_hot(idx[:, :L], 256), tgt)
-    net = build_net(dil, 64, 64, 256, 256, False, st, mode="bf16")
+    net = build_net(dil, 64, 64, 256, 256, bias, st, mode="bf16")
     tr = Trainer(net, "adam", distributed=False)
     loss = float(tr.forward_backward(idx[:, :L].cuda(), tgt.cuda()))
     assert abs(loss - loss_ref) < 1e-4
@@ -133,9 +137,9 @@ def test_backward_gradients_vs_oracle(dil, B, W, positive):
     gflat = net.engine.gflat.cpu().double()
     rflat = torch.cat([g_ref[k].reshape(-1) for k, _ in net.named_parameters()]).double()
     cos = float((gflat @ rflat) / (gflat.norm() * rflat.norm()))
-    print("positive" if positive else "random", "worst grad rel-l2:", worst, errs[worst], "cosine:", cos)
-    assert errs[worst] < (3e-2 if positive else 0.12), (worst, errs[worst])
-    assert cos > (0.999 if positive else 0.99)
+    print("noflip" if noflip else "random", "worst grad rel-l2:", worst, errs[worst], "cosine:", cos)
+    assert errs[worst] < (4e-2 if noflip else 0.12), (worst, errs[worst])
+    assert cos > (0.999 if noflip else 0.99)
 
 
 def test_train_steps_bf16_track_fp32_oracle():
