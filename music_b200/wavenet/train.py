@@ -75,6 +75,26 @@ def load_model(model, path, model_name):
         return None
 
 
+def all_reduce_mean_(flat_grad: torch.Tensor, dist=None, group=None) -> torch.Tensor:
+    """Average one flat gradient vector over the data-parallel ranks, in place: ONE collective per step
+    (NCCL `avg` on GPUs; gloo has no avg, so sum then divide).  Every rank holds the same number of loss
+    rows, so the mean of per-rank mean-loss gradients equals the reference's DataParallel gradient of the
+    mean loss over the gathered batch (wavenet/train.py:121,178-181)."""
+    if dist is None:
+        import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat_grad
+    ws = dist.get_world_size(group)
+    if ws == 1:
+        return flat_grad
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        flat_grad.div_(ws)
+    return flat_grad
+
+
 class Trainer:
     """Fused train step: zero_grad -> forward -> CrossEntropyLoss(probabilities) -> backward ->
     [all-reduce] -> optimizer.step, i.e. wavenet/train.py:171-182, with no autograd graph.
@@ -125,15 +145,7 @@ class Trainer:
     def all_reduce(self):
         if self.dist is None:
             return
-        g = self.net.engine.gflat
-        ws = self.dist.get_world_size(self.group)
-        if ws == 1:
-            return
-        if self.dist.get_backend(self.group) == "nccl":
-            self.dist.all_reduce(g, op=self.dist.ReduceOp.AVG, group=self.group)
-        else:
-            self.dist.all_reduce(g, op=self.dist.ReduceOp.SUM, group=self.group)
-            g.div_(ws)
+        all_reduce_mean_(self.net.engine.gflat, self.dist, self.group)
 
     def apply(self):
         e, lib = self.net.engine, L.load()
