@@ -262,12 +262,14 @@ def main():
     # ---------------- per-kernel breakdown: dominant kernel -> roofline
     roofline = None
     breakdown = None
+    lib = L.load()
+    n_prof = 3
     if rank == 0:
-        lib = L.load()
         lib.wn_profile_enable(1)
-        n_prof = 3
-        for i in range(n_prof):
-            trainer.step(pieces[i % n_batches], targets[i % n_batches])
+    for i in range(n_prof):          # every rank steps (the step contains a collective); only rank 0 records events
+        trainer.step(pieces[i % n_batches], targets[i % n_batches])
+    barrier()
+    if rank == 0:
         rep = L.profile_report()
         lib.wn_profile_enable(0)
         kf = kernel_flops(B)
