@@ -140,6 +140,44 @@ def cpu_reference_rate(steps, warmup, n_threads=None):
     return WINDOW / dt, n_threads, dt
 
 
+def bench_generation(net, n_streams, n_steps, dev):
+    """BASELINE.json configs[3]: fast_generate incremental sampling, 30-layer model, 64 parallel streams.
+    Prime every stream with one-hot(128) x rf (fast_generate.py:158-161), then time n_steps greedy steps per stream
+    on the device (CUDA events).  Bytes: per step a CTA streams the 2.4 MB bf16 weight image once for its 2 streams
+    and each stream reads + writes one 64-float vector per block."""
+    import torch
+    from music_b200.wavenet import fast_generate as FG
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    with torch.no_grad():
+        first, state, _ = FG._prime(net, torch.full((n_streams, net.receptive_field), Q // 2, dtype=torch.int64, device=dev))
+        FG._steps(net, state, first, 50)                       # warm-up
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        codes, _ = FG._steps(net, state, first, n_steps)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    n_layers = len(DIL)
+    w_bytes = 2 * (n_layers * (2 * 64 * 128 + 64 * 64 + 64 * 256) + 2 * 256 * 256) + 4 * 2 * Q * R
+    n_ctas = (n_streams + 1) // 2
+    ring_bytes = n_layers * 64 * 4 * 2
+    moved = n_steps * (n_ctas * w_bytes + n_streams * ring_bytes)
+    gbs = moved / (ms * 1e-3) / 1e9
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"workload": f"fast_generate incremental sampling, 30-layer 64/64/256 model, {n_streams} streams x {n_steps} steps "
+                        "(greedy, queue_push=output as the reference)",
+            "samples_per_s_per_stream": n_steps / (ms * 1e-3), "samples_per_s_total": n_streams * n_steps / (ms * 1e-3),
+            "us_per_step": ms * 1e3 / n_steps, "dtype": "bf16 weights, f32 state",
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                         "note": "achieved = bytes the kernel requests from L2 (weight image per CTA per step + ring vectors); "
+                                 "the weight image is L2-resident, so this is an L2->SM figure quoted against the HBM copy peak"}}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -167,6 +205,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--gen-steps", type=int, default=2000, help="incremental-generation steps timed per stream (0 = skip)")
+    ap.add_argument("--gen-streams", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -302,6 +342,10 @@ def main():
                "sample": f"oracle port of wavenet/model.py + train.py:171-182 step, torch CPU fp32, cfg-2 model, "
                          f"1 clip x {WINDOW} targets per step, {n} steps ({dt:.2f} s/step)"}
 
+    gen = None
+    if rank == 0 and world == 1 and args.gen_steps > 0:
+        gen = bench_generation(net, args.gen_streams, args.gen_steps, dev)
+
     if rank == 0:
         out = {"metric": "training audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -314,7 +358,8 @@ def main():
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": ms_e2e / K},
                "gpu_launches": int(launches), "loss": last_loss, "clocks": clocks, "roofline": roofline,
-               "cpu_baseline": cpu, "train_flops_per_sample": 3 * flops_per_sample(), "kernels": breakdown}
+               "cpu_baseline": cpu, "train_flops_per_sample": 3 * flops_per_sample(), "generation": gen,
+               "kernels": breakdown}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -437,10 +437,4 @@ int fast_backward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx
   return fast_backward_impl(m, fp->bwd, B, L, d_x, d_idx, d_packed, d_ws, d_dlogits, d_grads, s);
 }
 
-int fast_gen_steps(Model& m, int, int, int, const int64_t*, const void*, void*, const float*, int64_t*, float*, cudaStream_t) {
-  (void)m;
-  set_error("wn_gen_steps: bf16 generation kernel not built yet; use mode fp32");
-  return WN_ERR_UNSUPPORTED;
-}
-
 }  // namespace wn

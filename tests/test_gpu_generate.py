@@ -107,3 +107,31 @@ def test_import_reference_layout_state(golden):
         note = torch.zeros(1, Q, 1)
         note[:, cont[-1], :] = 1.0
     assert picks + cont == [int(p) for p in z["picks"][:20]]
+
+
+def test_bf16_generation_kernel_teacher_forced_vs_oracle():
+    """bf16-weight generation kernel (two streams per CTA): per-step logits against the fp32 oracle driven
+    by the GPU's own picks (teacher forcing, so one flipped argmax cannot hide later agreement).
+    Tolerance 1e-2 relative (bf16 weights, fp32 state)."""
+    from music_b200.wavenet.fast_generate import generate_codes
+    dil = [1, 2, 4, 8, 16, 1, 2, 4, 8, 16]
+    Q = 256
+    for bias in (False, True):
+        st = O.init_wavenet_state(dil, 64, 64, 256, Q, bias, seed=9, scale=2.5)
+        rf = O.receptive_field(2, dil)
+        net = build_net(dil, 64, 64, 256, Q, bias, st, mode="bf16")
+        g = torch.Generator().manual_seed(10)
+        primes = torch.randint(0, Q, (3, rf), generator=g)           # odd stream count: one CTA has a single stream
+        n = 24
+        codes, logits = generate_codes(net, n, primes.cuda(), return_logits=True)
+        codes, logits = codes.cpu(), logits.cpu()
+        agree = 0
+        for s in range(3):
+            note, queues = O.one_hot(primes[s:s + 1], Q), None
+            for i in range(n):
+                lg, queues = (O.gen_prime(st, dil, note) if queues is None else O.gen_step(st, dil, note, queues))
+                assert max_rel(logits[i, s].numpy(), lg.numpy()) < 1e-2, (bias, s, i)
+                agree += int(O.pick_greedy(lg) == int(codes[i, s]))
+                note = torch.zeros(1, Q, 1)
+                note[:, int(codes[i, s]), :] = 1.0
+        assert agree >= 0.9 * 3 * n, agree
