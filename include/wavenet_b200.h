@@ -155,6 +155,32 @@ int wn_gen_export(const wn_model* m, int32_t mode, int32_t n_streams, const void
 int wn_gen_import(const wn_model* m, int32_t mode, int32_t n_streams, void* d_state,
                   const float* d_queues, const int64_t* d_last_note, void* stream);
 
+/* ---- autoencoder : wavenet_autoencoder.forward, wavenet_autoencoder/model1.py:137-268 (fp32 check mode) ----
+ * Parameters: one flat fp32 vector in the reference state_dict order (model1.py:55-58: en_dilation_layer_stack.*,
+ * en_dense_layer_stack.*, de_dilation_layer_stack.{3i,3i+1,3i+2}, en_causal_layer, bottleneck_layer, de_causal_layer,
+ * connection_1, connection_2).  The N+1 conditioning convs the reference creates at random on every call
+ * (:178-179, :216-217; always biased) are a second flat vector d_cond: N x [(2Dd,BW,1) weight, (2Dd) bias] then
+ * [(Sd,BW,1), (Sd)].  d_logits is (B,Q,W) = the output of connection_2 (:221); d_encoding, if non-NULL, receives the
+ * pooled encoding channels-last (B, frames, BW), frames = W / pool. */
+typedef struct {
+  int32_t n_layers;
+  const int32_t* dilations;
+  int32_t quantization_channel;
+  int32_t en_residual_channel, en_dilation_channel, en_bottleneck_width, en_pool_kernel_size;
+  int32_t de_residual_channel, de_dilation_channel, de_skip_channel;
+  int32_t use_bias;
+  int32_t filter_width;            /* must be 2 */
+} wn_ae_config;
+typedef struct wn_ae wn_ae;
+int wn_ae_create(const wn_ae_config* cfg, wn_ae** out);
+int wn_ae_destroy(wn_ae* a);
+int64_t wn_ae_param_count(const wn_ae* a);
+int64_t wn_ae_cond_param_count(const wn_ae* a);
+int32_t wn_ae_receptive_field(const wn_ae* a);
+int wn_ae_workspace_bytes(const wn_ae* a, int32_t B, int32_t L, size_t* bytes);
+int wn_ae_forward(wn_ae* a, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx, const float* d_params,
+                  const float* d_cond, void* d_workspace, float* d_logits, float* d_encoding, void* stream);
+
 /* ---- instrumentation (bench.py): kernel-launch counter and per-kernel CUDA-event profiler ---------- */
 uint64_t wn_launch_count(void);                 /* kernels launched by this library so far */
 int wn_profile_enable(int32_t on);              /* bracket every launch with CUDA events on its stream */

@@ -28,6 +28,14 @@ class wn_config(C.Structure):
                 ("use_bias", C.c_int32), ("filter_width", C.c_int32)]
 
 
+class wn_ae_config(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dilations", C.POINTER(C.c_int32)), ("quantization_channel", C.c_int32),
+                ("en_residual_channel", C.c_int32), ("en_dilation_channel", C.c_int32),
+                ("en_bottleneck_width", C.c_int32), ("en_pool_kernel_size", C.c_int32),
+                ("de_residual_channel", C.c_int32), ("de_dilation_channel", C.c_int32), ("de_skip_channel", C.c_int32),
+                ("use_bias", C.c_int32), ("filter_width", C.c_int32)]
+
+
 _p, _i32, _i64, _f, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 _psz = C.POINTER(C.c_size_t)
 
@@ -60,6 +68,13 @@ SIGNATURES = {
     "wn_gen_export": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p]),
     "wn_gen_import": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p]),
     "wn_selftest_umma": (C.c_int, [_p, _i32, _p]),
+    "wn_ae_create": (C.c_int, [_p, C.POINTER(_p)]),
+    "wn_ae_destroy": (C.c_int, [_p]),
+    "wn_ae_param_count": (C.c_int64, [_p]),
+    "wn_ae_cond_param_count": (C.c_int64, [_p]),
+    "wn_ae_receptive_field": (C.c_int32, [_p]),
+    "wn_ae_workspace_bytes": (C.c_int, [_p, _i32, _i32, _psz]),
+    "wn_ae_forward": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "wn_launch_count": (C.c_uint64, []),
     "wn_profile_enable": (C.c_int, [_i32]),
     "wn_profile_report": (C.c_int, [C.c_char_p, _sz]),

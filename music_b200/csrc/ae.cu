@@ -1,0 +1,289 @@
+// ae.cu - wavenet_autoencoder forward (wavenet_autoencoder/model1.py:137-268), fp32 check mode.
+//
+//   _encode  (:137-156): en_causal(k=2) -> N x [relu -> dilated conv(k=2) -> relu -> 1x1 -> + residual] -> bottleneck 1x1
+//                        -> AvgPool1d(pool)                         => encoding (B, BW, frames), frames = floor(W / pool)
+//   _decode  (:158-225): de_causal(k=2) -> N x [filter_gate conv (2D out) + cond_i(encoding) -> gate = FIRST half,
+//                        filter = second half -> z = tanh(xf) sigmoid(xg) -> dense + residual ; skip on the last W]
+//                        -> relu(sum skips) -> connection_1 -> + cond_N(encoding) -> relu -> connection_2
+//   _conditon(:227-247): when len % frames == 0 every frame is held for len/frames steps (broadcast), otherwise the
+//                        whole encoding is TILED along time: index = t mod frames.
+// The reference creates the N+1 conditioning convs (bias=True) afresh, at random, on every call (:178,216); here they
+// are an explicit second parameter vector so that results are reproducible.
+//
+// Activations are (B, L, C) fp32 in absolute time coordinates like the WaveNet check mode; everything is composed from
+// the generic tap-GEMM of check_kernels.cu plus three element-wise kernels below.
+#include "check_kernels.cuh"
+#include "common.cuh"
+
+struct wn_ae {
+  int N = 0, Q = 0, Re = 0, De = 0, BW = 0, pool = 0, Rd = 0, Dd = 0, Sd = 0, use_bias = 0, rf = 0;
+  std::vector<int> dil, start;                 // start[i] = first valid time index of layer i's output
+  // offsets into the flat parameter vector (reference state_dict order, model1.py:55-58)
+  std::vector<wn::ConvP> en_dil, en_dense, de_fg, de_dense, de_skip;
+  wn::ConvP en_causal, bottleneck, de_causal, conn1, conn2;
+  std::vector<wn::ConvP> cond;                 // offsets into the conditioning vector (always biased)
+  int64_t n_params = 0, n_cond = 0;
+};
+
+namespace wn {
+namespace {
+
+// encoding[b, f, c] = mean_{j<pool} Hb[b, t0 + f*pool + j, c]            (nn.AvgPool1d(pool), model1.py:154-155)
+__global__ void avgpool_kernel(const float* __restrict__ Hb, float* __restrict__ enc, int L, int C, int t0, int pool, int frames) {
+  const int b = blockIdx.y;
+  const int64_t n = (int64_t)frames * C;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(e / C), c = (int)(e % C);
+    float s = 0.f;
+    for (int j = 0; j < pool; ++j) s += Hb[((int64_t)b * L + t0 + f * pool + j) * C + c];
+    enc[((int64_t)b * frames + f) * C + c] = s / (float)pool;
+  }
+}
+
+__device__ __forceinline__ int cond_frame(int t_local, int len, int frames) {
+  return (len % frames == 0) ? t_local / (len / frames) : t_local % frames;      // model1.py:233-246
+}
+
+// Y (B,L,2D) pre-activation + cond (B,frames,2D) -> Z (B,L,D) = tanh(Y[D:2D]) * sigmoid(Y[0:D])        (model1.py:183-192)
+__global__ void ae_gate_kernel(const float* __restrict__ Y, const float* __restrict__ cond, float* __restrict__ Z, int L, int D,
+                               int t0, int t1, int frames) {
+  const int b = blockIdx.y, len = t1 - t0;
+  const int64_t n = (int64_t)len * D;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tl = (int)(e / D), d = (int)(e % D);
+    const int f = cond_frame(tl, len, frames);
+    const float* y = Y + ((int64_t)b * L + t0 + tl) * 2 * D;
+    const float* c = cond + ((int64_t)b * frames + f) * 2 * D;
+    const float xg = y[d] + c[d], xf = y[D + d] + c[D + d];
+    Z[((int64_t)b * L + t0 + tl) * D + d] = tanhf(xf) * (1.f / (1.f + expf(-xg)));
+  }
+}
+
+// H (B,W,S) += cond (B,frames,S) with the same frame rule (model1.py:218)
+__global__ void ae_cond_add_kernel(float* __restrict__ H, const float* __restrict__ cond, int W, int S, int frames) {
+  const int b = blockIdx.y;
+  const int64_t n = (int64_t)W * S;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tl = (int)(e / S), s = (int)(e % S);
+    H[((int64_t)b * W + tl) * S + s] += cond[((int64_t)b * frames + cond_frame(tl, W, frames)) * S + s];
+  }
+}
+
+__global__ void onehot_rows_kernel(const int64_t* __restrict__ idx, float* __restrict__ X, int64_t n_rows, int Q) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_rows * Q; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / Q;
+    X[e] = ((int)(e % Q) == (int)idx[r]) ? 1.f : 0.f;
+  }
+}
+
+inline int ew_blocks(int64_t n) { return (int)std::min<int64_t>(ceil_div(n, 256), 148 * 16); }
+
+struct AeWs {
+  float *Xin, *S0, *S1, *T, *HB, *ENC, *COND, *Y, *Z, *SK, *H1, *WT;
+  size_t bytes;
+};
+int64_t conv_elems(const ConvP& c) { return (int64_t)c.out * c.in * c.k; }
+
+AeWs ae_ws(const wn_ae& a, int B, int L, bool need_onehot, void* base) {
+  const int W = L - a.rf + 1, frames = std::max(1, W / a.pool);
+  AeWs w{};
+  size_t off = 0;
+  auto take = [&](int64_t n) {
+    float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+    off += align_up((size_t)std::max<int64_t>(n, 1) * sizeof(float), 256);
+    return p;
+  };
+  const int Cmax = std::max(std::max(a.Re, a.De), std::max(a.Rd, 2 * a.Dd));
+  w.Xin = take(need_onehot ? (int64_t)B * L * a.Q : 0);
+  w.S0 = take((int64_t)B * L * Cmax);
+  w.S1 = take((int64_t)B * L * Cmax);
+  w.T = take((int64_t)B * L * Cmax);
+  w.HB = take((int64_t)B * L * a.BW);
+  w.ENC = take((int64_t)B * frames * a.BW);
+  w.COND = take((int64_t)B * frames * std::max(2 * a.Dd, a.Sd));
+  w.Y = take((int64_t)B * L * 2 * a.Dd);
+  w.Z = take((int64_t)B * L * a.Dd);
+  w.SK = take((int64_t)B * W * a.Sd);
+  w.H1 = take((int64_t)B * W * a.Sd);
+  int64_t wmax = 0;
+  for (auto* v : {&a.en_dil, &a.en_dense, &a.de_fg, &a.de_dense, &a.de_skip, &a.cond})
+    for (auto& c : *v) wmax = std::max(wmax, conv_elems(c));
+  for (const ConvP* c : {&a.en_causal, &a.bottleneck, &a.de_causal, &a.conn1, &a.conn2}) wmax = std::max(wmax, conv_elems(*c));
+  w.WT = take(2 * wmax);      // Wt + Wtt of the conv being applied (repacked per call; check mode)
+  w.bytes = off;
+  return w;
+}
+
+TensorView tv(const float* p, int64_t sb, int64_t st, int64_t sc, int shift = 0) {
+  TensorView v;
+  v.p = p; v.sb = sb; v.st = st; v.sc = sc; v.shift = shift;
+  return v;
+}
+
+// Y = conv(X) for one Conv1d taken from a flat vector: repack (out,in,k) -> [k][in][out], then the generic tap-GEMM
+int apply_conv(const float* params, const ConvP& c, float* wt_scratch, PwArgs a, int dilation, cudaStream_t s) {
+  WN_PROPAGATE(launch_pack_f32(params + c.w, wt_scratch, wt_scratch + conv_elems(c), c.out, c.in, c.k, s));
+  a.Wt = wt_scratch;
+  a.bias = c.b >= 0 ? params + c.b : nullptr;
+  a.n_in = c.in; a.n_out = c.out;
+  a.n_taps = c.k;
+  if (c.k == 2) { a.off[0] = -dilation; a.off[1] = 0; } else { a.off[0] = 0; }
+  return launch_pw_gemm(a, s);
+}
+
+}  // namespace
+}  // namespace wn
+
+using namespace wn;
+
+extern "C" int wn_ae_create(const wn_ae_config* cfg, wn_ae** out) {
+  WN_REQUIRE(cfg && out, WN_ERR_INVALID, "wn_ae_create: null argument");
+  WN_REQUIRE(cfg->filter_width == 2, WN_ERR_UNSUPPORTED, "wn_ae_create: filter_width %d (only 2 is supported)", cfg->filter_width);
+  WN_REQUIRE(cfg->n_layers > 0 && cfg->dilations && cfg->en_pool_kernel_size > 0, WN_ERR_INVALID, "wn_ae_create: bad config");
+  wn_ae* a = new wn_ae();
+  a->N = cfg->n_layers; a->Q = cfg->quantization_channel;
+  a->Re = cfg->en_residual_channel; a->De = cfg->en_dilation_channel; a->BW = cfg->en_bottleneck_width;
+  a->pool = cfg->en_pool_kernel_size; a->Rd = cfg->de_residual_channel; a->Dd = cfg->de_dilation_channel;
+  a->Sd = cfg->de_skip_channel; a->use_bias = cfg->use_bias ? 1 : 0;
+  int64_t off = 0;
+  auto add = [&](ConvP& c, int o, int i, int k, bool bias, int64_t& cursor) {
+    c.out = o; c.in = i; c.k = k;
+    c.w = cursor; cursor += (int64_t)o * i * k;
+    if (bias) { c.b = cursor; cursor += o; }
+  };
+  const bool ub = a->use_bias != 0;
+  a->en_dil.resize(a->N); a->en_dense.resize(a->N); a->de_fg.resize(a->N); a->de_dense.resize(a->N); a->de_skip.resize(a->N);
+  int st = 1, sum = 0;
+  for (int i = 0; i < a->N; ++i) {
+    a->dil.push_back(cfg->dilations[i]);
+    st += cfg->dilations[i]; sum += cfg->dilations[i];
+    a->start.push_back(st);
+  }
+  // registration order of the reference constructor: _init_encoding, _init_decoding, _init_causal_layer, _init_connection
+  for (int i = 0; i < a->N; ++i) add(a->en_dil[i], a->De, a->Re, 2, ub, off);
+  for (int i = 0; i < a->N; ++i) add(a->en_dense[i], a->Re, a->De, 1, ub, off);
+  for (int i = 0; i < a->N; ++i) {
+    add(a->de_fg[i], 2 * a->Dd, a->Rd, 2, ub, off);
+    add(a->de_dense[i], a->Rd, a->Dd, 1, ub, off);
+    add(a->de_skip[i], a->Sd, a->Dd, 1, ub, off);
+  }
+  add(a->en_causal, a->Re, a->Q, 2, ub, off);
+  add(a->bottleneck, a->BW, a->Re, 1, ub, off);
+  add(a->de_causal, a->Rd, a->Q, 2, ub, off);
+  add(a->conn1, a->Sd, a->Sd, 1, ub, off);
+  add(a->conn2, a->Q, a->Sd, 1, ub, off);
+  a->n_params = off;
+  int64_t coff = 0;
+  a->cond.resize(a->N + 1);
+  for (int i = 0; i < a->N; ++i) add(a->cond[i], 2 * a->Dd, a->BW, 1, true, coff);
+  add(a->cond[a->N], a->Sd, a->BW, 1, true, coff);
+  a->n_cond = coff;
+  a->rf = sum + 2;
+  *out = a;
+  return WN_OK;
+}
+extern "C" int wn_ae_destroy(wn_ae* a) { delete a; return WN_OK; }
+extern "C" int64_t wn_ae_param_count(const wn_ae* a) { return a ? a->n_params : -1; }
+extern "C" int64_t wn_ae_cond_param_count(const wn_ae* a) { return a ? a->n_cond : -1; }
+extern "C" int32_t wn_ae_receptive_field(const wn_ae* a) { return a ? a->rf : -1; }
+
+extern "C" int wn_ae_workspace_bytes(const wn_ae* a, int32_t B, int32_t L, size_t* bytes) {
+  WN_REQUIRE(a && bytes && B > 0, WN_ERR_INVALID, "wn_ae_workspace_bytes: bad argument");
+  WN_REQUIRE(L - a->rf + 1 > 0, WN_ERR_SHAPE, "wave sample not long enough");
+  *bytes = ae_ws(*a, B, L, true, nullptr).bytes;
+  return WN_OK;
+}
+
+extern "C" int wn_ae_forward(wn_ae* a, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx, const float* d_params,
+                             const float* d_cond, void* d_workspace, float* d_logits, float* d_encoding, void* stream) {
+  WN_REQUIRE(g_inited, WN_ERR_UNSUPPORTED, "wn_init() has not succeeded: no sm_100 device, no fallback");
+  WN_REQUIRE(a && d_params && d_cond && d_workspace && d_logits, WN_ERR_INVALID, "wn_ae_forward: null argument");
+  WN_REQUIRE((d_x != nullptr) != (d_idx != nullptr), WN_ERR_INVALID, "wn_ae_forward: exactly one of d_x / d_idx must be given");
+  const int W = L - a->rf + 1;
+  WN_REQUIRE(W > 0, WN_ERR_SHAPE, "wave sample not long enough");
+  const int frames = W / a->pool;
+  WN_REQUIRE(frames >= 1, WN_ERR_SHAPE, "output width %d shorter than the pooling window %d", W, a->pool);
+  cudaStream_t s = (cudaStream_t)stream;
+  AeWs w = ae_ws(*a, B, L, true, d_workspace);
+  const int N = a->N, Q = a->Q, tw = L - W;
+  TensorView Xin;
+  if (d_x) {
+    Xin = tv(d_x, (int64_t)Q * L, 1, L);                                  // (B,Q,L) as the reference takes it
+  } else {
+    onehot_rows_kernel<<<ew_blocks((int64_t)B * L * Q), 256, 0, s>>>(d_idx, w.Xin, (int64_t)B * L, Q);
+    WN_CHECK_LAUNCH();
+    Xin = tv(w.Xin, (int64_t)L * Q, Q, 1);
+  }
+  auto view = [&](const float* p, int C) { return tv(p, (int64_t)L * C, C, 1); };
+  // ------------------------------------------------------------------ encoder (model1.py:137-156)
+  {
+    PwArgs p; p.X = Xin; p.x_lo = 0; p.x_hi = L; p.Y = view(w.S0, a->Re); p.B = B; p.t0 = 1; p.t1 = L;
+    WN_PROPAGATE(apply_conv(d_params, a->en_causal, w.WT, p, 1, s));
+  }
+  float* cur = w.S0;
+  float* nxt = w.S1;
+  int s_in = 1;
+  for (int i = 0; i < N; ++i) {
+    const int d = a->dil[i], s_out = s_in + d;
+    PwArgs p1; p1.X = view(cur, a->Re); p1.x_lo = s_in; p1.x_hi = L; p1.x_relu = 1; p1.Y = view(w.T, a->De);
+    p1.B = B; p1.t0 = s_out; p1.t1 = L;
+    WN_PROPAGATE(apply_conv(d_params, a->en_dil[i], w.WT, p1, d, s));
+    PwArgs p2; p2.X = view(w.T, a->De); p2.x_lo = s_out; p2.x_hi = L; p2.x_relu = 1; p2.Res = view(cur, a->Re);
+    p2.Y = view(nxt, a->Re); p2.B = B; p2.t0 = s_out; p2.t1 = L;
+    WN_PROPAGATE(apply_conv(d_params, a->en_dense[i], w.WT, p2, 1, s));
+    std::swap(cur, nxt);
+    s_in = s_out;
+  }
+  {
+    PwArgs p; p.X = view(cur, a->Re); p.x_lo = tw; p.x_hi = L; p.Y = view(w.HB, a->BW); p.B = B; p.t0 = tw; p.t1 = L;
+    WN_PROPAGATE(apply_conv(d_params, a->bottleneck, w.WT, p, 1, s));
+    dim3 grid((unsigned)ew_blocks((int64_t)frames * a->BW), (unsigned)B);
+    avgpool_kernel<<<grid, 256, 0, s>>>(w.HB, w.ENC, L, a->BW, tw, a->pool, frames);
+    WN_CHECK_LAUNCH();
+    if (d_encoding)        // channels-last copy (B, frames, BW); `_encode` returns its transpose (B, BW, frames)
+      WN_CHECK_CUDA(cudaMemcpyAsync(d_encoding, w.ENC, (size_t)B * frames * a->BW * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  // ------------------------------------------------------------------ decoder (model1.py:158-225)
+  {
+    PwArgs p; p.X = Xin; p.x_lo = 0; p.x_hi = L; p.Y = view(w.S0, a->Rd); p.B = B; p.t0 = 1; p.t1 = L;
+    WN_PROPAGATE(apply_conv(d_params, a->de_causal, w.WT, p, 1, s));
+  }
+  cur = w.S0; nxt = w.S1; s_in = 1;
+  TensorView ENCv = tv(w.ENC, (int64_t)frames * a->BW, a->BW, 1);
+  for (int i = 0; i < N; ++i) {
+    const int d = a->dil[i], s_out = s_in + d;
+    PwArgs pc; pc.X = ENCv; pc.x_lo = 0; pc.x_hi = frames; pc.Y = tv(w.COND, (int64_t)frames * 2 * a->Dd, 2 * a->Dd, 1);
+    pc.B = B; pc.t0 = 0; pc.t1 = frames;
+    WN_PROPAGATE(apply_conv(d_cond, a->cond[i], w.WT, pc, 1, s));                       // fresh conv on the encoding (:178-179)
+    PwArgs p1; p1.X = view(cur, a->Rd); p1.x_lo = s_in; p1.x_hi = L; p1.Y = view(w.Y, 2 * a->Dd); p1.B = B; p1.t0 = s_out; p1.t1 = L;
+    WN_PROPAGATE(apply_conv(d_params, a->de_fg[i], w.WT, p1, d, s));                    // filter_gate conv (:175)
+    {
+      dim3 grid((unsigned)ew_blocks((int64_t)(L - s_out) * a->Dd), (unsigned)B);
+      ae_gate_kernel<<<grid, 256, 0, s>>>(w.Y, w.COND, w.Z, L, a->Dd, s_out, L, frames);   // _conditon + gate (:183-192)
+      WN_CHECK_LAUNCH();
+    }
+    PwArgs p2; p2.X = view(w.Z, a->Dd); p2.x_lo = s_out; p2.x_hi = L; p2.Res = view(cur, a->Rd); p2.Y = view(nxt, a->Rd);
+    p2.B = B; p2.t0 = s_out; p2.t1 = L;
+    WN_PROPAGATE(apply_conv(d_params, a->de_dense[i], w.WT, p2, 1, s));                 // dense + residual (:194-202)
+    PwArgs p3; p3.X = view(w.Z, a->Dd); p3.x_lo = tw; p3.x_hi = L; p3.Y = tv(w.SK, (int64_t)W * a->Sd, a->Sd, 1, -tw);
+    p3.accumulate = i > 0; p3.B = B; p3.t0 = tw; p3.t1 = L;
+    WN_PROPAGATE(apply_conv(d_params, a->de_skip[i], w.WT, p3, 1, s));                  // skip on the last W (:204-208)
+    std::swap(cur, nxt);
+    s_in = s_out;
+  }
+  TensorView SKv = tv(w.SK, (int64_t)W * a->Sd, a->Sd, 1, -tw), H1v = tv(w.H1, (int64_t)W * a->Sd, a->Sd, 1, -tw);
+  {
+    PwArgs p; p.X = SKv; p.x_lo = tw; p.x_hi = L; p.x_relu = 1; p.Y = H1v; p.B = B; p.t0 = tw; p.t1 = L;
+    WN_PROPAGATE(apply_conv(d_params, a->conn1, w.WT, p, 1, s));                        // relu -> connection_1 (:210-213)
+    PwArgs pc; pc.X = ENCv; pc.x_lo = 0; pc.x_hi = frames; pc.Y = tv(w.COND, (int64_t)frames * a->Sd, a->Sd, 1);
+    pc.B = B; pc.t0 = 0; pc.t1 = frames;
+    WN_PROPAGATE(apply_conv(d_cond, a->cond[N], w.WT, pc, 1, s));                       // second fresh conv (:216-217)
+    dim3 grid((unsigned)ew_blocks((int64_t)W * a->Sd), (unsigned)B);
+    ae_cond_add_kernel<<<grid, 256, 0, s>>>(w.H1, w.COND, W, a->Sd, frames);            // _conditon (:218)
+    WN_CHECK_LAUNCH();
+    PwArgs p2; p2.X = H1v; p2.x_lo = tw; p2.x_hi = L; p2.x_relu = 1; p2.Y = tv(d_logits, (int64_t)Q * W, 1, W, -tw);
+    p2.B = B; p2.t0 = tw; p2.t1 = L;
+    WN_PROPAGATE(apply_conv(d_params, a->conn2, w.WT, p2, 1, s));                       // relu -> connection_2 (:219-221)
+  }
+  return WN_OK;
+}

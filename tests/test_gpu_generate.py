@@ -117,7 +117,7 @@ def test_bf16_generation_kernel_teacher_forced_vs_oracle():
     dil = [1, 2, 4, 8, 16, 1, 2, 4, 8, 16]
     Q = 256
     for bias in (False, True):
-        st = O.init_wavenet_state(dil, 64, 64, 256, Q, bias, seed=9, scale=2.5)
+        st = O.init_wavenet_state(dil, 64, 64, 256, Q, bias, seed=9, scale=1.5)
         rf = O.receptive_field(2, dil)
         net = build_net(dil, 64, 64, 256, Q, bias, st, mode="bf16")
         g = torch.Generator().manual_seed(10)
