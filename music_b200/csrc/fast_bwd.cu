@@ -599,35 +599,53 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       epi8_bar_sync();
     }
-    // ---- flush the weight-gradient accumulators (fp32 atomics into the flat gradient vector)
-    if ((int)blockIdx.x < n_items) {
-      mbar_wait(&wg_done, 0);
-      tc_fence_after();
-      const int m = row;                       // accumulator row
-      {   // dW_fg: 128 columns = (tap, r); this warp flushes columns [32 cg, 32 cg + 32): tap = cg / 2
-        const int tap = cg >> 1, r0 = (cg & 1) * 32;
-        float* base = (m < 64 ? pp.g_filt : pp.g_gate) + (int64_t)(m & 63) * 128 + tap + r0 * 2;
+    // ---- flush the weight-gradient accumulators as a per-CTA partial tile [128][192] (plain 16-byte stores; a
+    //      second small kernel sums the tiles: 3 M fp32 atomics per launch saturated the L2 atomic units)
+    {
+      float* prow = pp.partial + ((int64_t)blockIdx.x * 128 + row) * 192;
+      if ((int)blockIdx.x < n_items) {
+        mbar_wait(&wg_done, 0);
+        tc_fence_after();
         uint32_t v[32];
-        tmem_ld32(lane_addr + 192 + cg * 32, v);
+        tmem_ld32(lane_addr + 192 + cg * 32, v);           // dW_fg columns [32 cg, 32 cg + 32)
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(base + j * 2, __uint_as_float(v[j]));
-      }
-      if (dense) {   // dW_dense[r = m][d]: columns [16 cg, 16 cg + 16)
-        uint32_t v[16];
-        tmem_ld16(lane_addr + 320 + cg * 16, v);
-        tmem_ld_wait();
-        if (m < 64) {
-          float* base = pp.g_dense + (int64_t)m * 64 + cg * 16;
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(prow + cg * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        uint32_t u[16];
+        if (dense) {
+          tmem_ld16(lane_addr + 320 + cg * 16, u);         // dW_dense columns [16 cg, 16 cg + 16)
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(base + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 16; ++j) u[j] = 0u;
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(prow + 128 + cg * 16 + q * 4) = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// dW = sum over CTAs of the partial tiles written by block_bwd2 (fixed summation order: deterministic)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, float* __restrict__ g_filt,
+                                                           float* __restrict__ g_gate, float* __restrict__ g_dense) {
+  const int e = blockIdx.x * 256 + threadIdx.x;           // element of the [128][192] tile
+  if (e >= 128 * 192) return;
+  const int m = e / 192, c = e % 192;
+  if (c >= 128 && (m >= 64 || g_dense == nullptr)) return;
+  float s = 0.f;
+  for (int k = 0; k < n_ctas; ++k) s += partial[(int64_t)k * 128 * 192 + e];
+  if (c < 128) {          // column = (tap, r): tap = c / 64, r = c % 64 ; row m = output channel (filter 0..63 | gate 64..127)
+    float* base = m < 64 ? g_filt : g_gate;
+    base[(int64_t)(m & 63) * 128 + (c & 63) * 2 + (c >> 6)] = s;
+  } else {
+    g_dense[(int64_t)m * 64 + (c - 128)] = s;
+  }
 }
 
 // ============================================================================================ SIMT helpers
@@ -799,9 +817,17 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   if (!once) { WN_PROPAGATE(set_smem(block_bwd2_kernel, smem)); once = true; }
   const int n_items = p.n_batches * p.b.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
-  WN_PROF("block_bwd2", s);
-  block_bwd2_kernel<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p);
-  WN_CHECK_LAUNCH();
+  const int n_ctas = std::min(n_items, g_sm_count);
+  {
+    WN_PROF("block_bwd2", s);
+    block_bwd2_kernel<<<n_ctas, 576, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p);
+    WN_CHECK_LAUNCH();
+  }
+  {
+    WN_PROF("wgrad_reduce", s);
+    wgrad_reduce_kernel<<<(128 * 192) / 256, 256, 0, s>>>(p.partial, n_ctas, p.g_filt, p.g_gate, p.g_dense);
+    WN_CHECK_LAUNCH();
+  }
   return WN_OK;
 }
 
@@ -956,6 +982,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
         BlockBwd2Params b2{};
         b2.b = bp; b2.n_batches = B;
         b2.g_filt = G + l.filt.w; b2.g_gate = G + l.gate.w; b2.g_dense = has_dense ? G + l.dense.w : nullptr;
+        b2.partial = reinterpret_cast<float*>(Wp + wl.WGP);
         WN_PROPAGATE(launch_block_bwd2(bm, b2, s));
         WN_DEBUG_SYNC("block_bwd2", s);
       } else {

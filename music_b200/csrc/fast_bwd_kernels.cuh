@@ -86,6 +86,7 @@ struct BlockBwd2Params {
   float* g_filt;      // dW filter (D,R,2) in the flat gradient vector
   float* g_gate;      // dW gate
   float* g_dense;     // dW dense (R,D,1) or null
+  float* partial;     // [n_ctas][128][192] fp32 per-CTA weight-gradient tiles (reduced by wgrad_reduce_kernel)
 };
 int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStream_t s);
 

@@ -28,7 +28,7 @@ inline size_t skip_bias_offs_pos(const Model& m) { return sizeof(PackJob) * (siz
 
 struct WsLayout {       // byte offsets
   size_t X, x_stride, XLO, Zcat, H0, H1, X0f;     // XLO: 2 ping-pong buffers of x_stride bytes
-  size_t DLG, DH1, DSK, DZcat, DXa, DXb, DFG, Zf, DX0f;
+  size_t DLG, DH1, DSK, DZcat, DXa, DXb, DFG, Zf, DX0f, WGP;   // WGP: per-CTA weight-gradient partial tiles
   size_t total;
 };
 WsLayout ws_layout(const Model& m, int B, int L);
