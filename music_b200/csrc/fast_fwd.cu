@@ -210,6 +210,229 @@ int launch_block_fwd(const BlockFwdMaps& m, const BlockFwdParams& p, int n_ctas,
   return WN_OK;
 }
 
+// ====================================================================================== block (persistent)
+// 18 warps: 0-15 epilogue (4 per TMEM lane quarter, 16 columns each), 16 TMA producer, 17 MMA issuer.
+// TMEM: two accumulator buffers {f|g: 128 cols, dense: 64 cols} so UMMA #1 of tile n+1 overlaps the epilogues of tile n.
+namespace {
+
+struct Fwd2Smem {
+  static constexpr uint32_t W0 = 0, W1 = TILE_BYTES, WD = 2 * TILE_BYTES;
+  static constexpr uint32_t IN = 2 * TILE_BYTES + WD_BYTES, IN_STAGE = 3 * TILE_BYTES;     // {x tap0, x tap1, lo}
+  static constexpr uint32_t Z = IN + 2 * IN_STAGE, XO = Z + TILE_BYTES, LOO = XO + TILE_BYTES;
+  static constexpr uint32_t TOTAL = LOO + TILE_BYTES;                                      // 184 KB
+};
+__device__ __forceinline__ void epi16_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__global__ void __launch_bounds__(576, 1)
+block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_xo,
+                  const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+                  const __grid_constant__ CUtensorMap tm_wd, const __grid_constant__ CUtensorMap tm_z,
+                  const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_loo, BlockFwdParams p,
+                  int n_batches) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t w_full, in_full[2], in_empty[2], fg_full[2], dense_full[2], acc_empty[2], z_ready, z_free;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&in_full[i], 1);
+      mbar_init(&in_empty[i], 2);       // UMMA #1 commit + epilogue (residual / lo tiles read)
+      mbar_init(&fg_full[i], 1);
+      mbar_init(&dense_full[i], 1);
+      mbar_init(&acc_empty[i], 1);
+    }
+    mbar_init(&z_ready, 1);
+    mbar_init(&z_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t sbase = smem_u32(sm);
+  const int n_items = n_batches * p.tiles_per_batch;
+  const bool dense = p.has_dense != 0;
+  const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 16) {
+    if (lane == 0 && n_mine > 0) {
+      mbar_expect_tx(&w_full, 2 * TILE_BYTES + (dense ? WD_BYTES : 0));
+      tma_load_2d(sm + Fwd2Smem::W0, &tm_w0, &w_full, 0, 0);
+      tma_load_2d(sm + Fwd2Smem::W1, &tm_w1, &w_full, 0, 0);
+      if (dense) tma_load_2d(sm + Fwd2Smem::WD, &tm_wd, &w_full, 0, 0);
+      for (int it = 0; it < n_mine; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int st = it & 1;
+        const uint32_t ph2 = (it >> 1) & 1;
+        const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
+        mbar_wait(&in_empty[st], ph2 ^ 1);
+        uint8_t* si = sm + Fwd2Smem::IN + st * Fwd2Smem::IN_STAGE;
+        mbar_expect_tx(&in_full[st], (dense ? 3 : 2) * TILE_BYTES);
+        tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b);
+        tma_load_3d(si + TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);
+        if (dense) tma_load_3d(si + 2 * TILE_BYTES, &tm_lo, &in_full[st], 0, tau0, b);
+      }
+    }
+  } else if (warp == 17) {
+    if (lane == 0 && n_mine > 0) {
+      constexpr uint32_t id1 = idesc_bf16(128, 128, 0, 0), id2 = idesc_bf16(128, 64, 0, 0);
+      mbar_wait(&w_full, 0);
+      auto mma1 = [&](int k) {
+        const int st = k & 1;
+        const uint32_t ph2 = (k >> 1) & 1;
+        const uint32_t si = sbase + Fwd2Smem::IN + st * Fwd2Smem::IN_STAGE, acc = tmem + st * 192;
+        mbar_wait(&in_full[st], ph2);
+        mbar_wait(&acc_empty[st], ph2 ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si, kk), desc_kmajor(sbase + Fwd2Smem::W0, kk), id1, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si + TILE_BYTES, kk), desc_kmajor(sbase + Fwd2Smem::W1, kk), id1, true);
+        umma_commit(&fg_full[st]);
+        umma_commit(&in_empty[st]);
+      };
+      mma1(0);
+      for (int it = 0; it < n_mine; ++it) {
+        if (it + 1 < n_mine) mma1(it + 1);
+        if (dense) {
+          mbar_wait(&z_ready, it & 1);
+          tc_fence_after();
+          const uint32_t acc = tmem + (it & 1) * 192 + 128;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(acc, desc_kmajor(sbase + Fwd2Smem::Z, kk), desc_kmajor(sbase + Fwd2Smem::WD, kk), id2, kk > 0);
+          umma_commit(&dense_full[it & 1]);
+          umma_commit(&z_free);
+        }
+      }
+    }
+  } else {
+    const int q4 = warp & 3, cg = warp >> 2;
+    const int row = q4 * 32 + lane;
+    for (int it = 0; it < n_mine; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int st = it & 1;
+      const uint32_t ph2 = (it >> 1) & 1;
+      const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
+      const int tau = tau0 + row;
+      const bool valid = (tau >= p.s_out) && (tau < p.L);
+      const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, st * 192);
+      const uint8_t* si = sm + Fwd2Smem::IN + st * Fwd2Smem::IN_STAGE;
+      // ---- epilogue 1: gate
+      mbar_wait(&fg_full[st], ph2);
+      tc_fence_after();
+      uint32_t f[16], g[16];
+      tmem_ld16(lane_addr + cg * 16, f);
+      tmem_ld16(lane_addr + 64 + cg * 16, g);
+      tmem_ld_wait();
+      uint32_t pz[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float f0 = __uint_as_float(f[2 * j]), f1 = __uint_as_float(f[2 * j + 1]);
+        float g0 = __uint_as_float(g[2 * j]), g1 = __uint_as_float(g[2 * j + 1]);
+        if (p.bias_fg) {
+          f0 += p.bias_fg[cg * 16 + 2 * j];
+          f1 += p.bias_fg[cg * 16 + 2 * j + 1];
+          g0 += p.bias_fg[64 + cg * 16 + 2 * j];
+          g1 += p.bias_fg[64 + cg * 16 + 2 * j + 1];
+        }
+        const float z0 = valid ? sigmoid_fast(g0) * tanh_fast(f0) : 0.f;
+        const float z1 = valid ? sigmoid_fast(g1) * tanh_fast(f1) : 0.f;
+        pz[j] = pack_bf16(z0, z1);
+      }
+      if (dense && it > 0) mbar_wait(&z_free, (it & 1) ^ 1);      // UMMA #2 of the previous tile has read the z tile
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        *reinterpret_cast<uint4*>(sm + Fwd2Smem::Z + sw128_chunk(row, cg * 2 + q)) =
+            make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      epi16_bar_sync();
+      if (tid == 0) {
+        if (dense) mbar_arrive(&z_ready);
+        if (tau0 >= p.tw_al) {
+          tma_store_3d(&tm_z, sm + Fwd2Smem::Z, p.zcol, tau0 - p.tw_al, b);
+          tma_store_commit();
+        }
+      }
+      // ---- epilogue 2: dense + residual (hi + lo)
+      if (dense) {
+        mbar_wait(&dense_full[st], ph2);
+        tc_fence_after();
+        uint32_t dv[16];
+        tmem_ld16(lane_addr + 128 + cg * 16, dv);
+        tmem_ld_wait();
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint4 rv = *reinterpret_cast<const uint4*>(si + TILE_BYTES + sw128_chunk(row, cg * 2 + q));
+          const uint4 lv = *reinterpret_cast<const uint4*>(si + 2 * TILE_BYTES + sw128_chunk(row, cg * 2 + q));
+          const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w}, ll[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * q + e;
+            const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
+            const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[e]);
+            float x0 = __uint_as_float(dv[2 * j]) + (__low2float(r2) + __low2float(l2));
+            float x1 = __uint_as_float(dv[2 * j + 1]) + (__high2float(r2) + __high2float(l2));
+            if (p.bias_d) {
+              x0 += p.bias_d[cg * 16 + 2 * j];
+              x1 += p.bias_d[cg * 16 + 2 * j + 1];
+            }
+            if (!valid) { x0 = 0.f; x1 = 0.f; }
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+            ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            pl[j] = pack_bf16(x0 - __low2float(h2), x1 - __high2float(h2));
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t o = sw128_chunk(row, cg * 2 + q);
+          *reinterpret_cast<uint4*>(sm + Fwd2Smem::XO + o) = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+          *reinterpret_cast<uint4*>(sm + Fwd2Smem::LOO + o) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+        }
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      epi16_bar_sync();
+      if (tid == 0) {
+        mbar_arrive(&in_empty[st]);
+        mbar_arrive(&acc_empty[st]);
+        if (dense) {
+          tma_store_3d(&tm_xo, sm + Fwd2Smem::XO, 0, tau0, b);
+          tma_store_3d(&tm_loo, sm + Fwd2Smem::LOO, 0, tau0, b);
+          tma_store_commit();
+        }
+        tma_store_wait_read();           // z / x_{i+1} staging tiles may be rewritten by the next tile
+      }
+      epi16_bar_sync();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, int n_batches, cudaStream_t s) {
+  static bool attr_set = false;
+  const int smem = Fwd2Smem::TOTAL + 1024;
+  if (!attr_set) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(block_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int n_items = n_batches * p.tiles_per_batch;
+  if (n_items <= 0) return WN_OK;
+  WN_PROF("block_fwd", s);
+  block_fwd2_kernel<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.xo, m.w0, m.w1, m.wd, m.z, m.lo, m.loo, p, n_batches);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
 // ================================================================================== skip + head
 namespace {
 

@@ -1,5 +1,7 @@
 // fast_host.cu - host side of the bf16 tensor-core path: driver entry points, weight packing,
 // workspace layout, TMA descriptor cache and the forward / backward launch sequences.
+#include <stdlib.h>
+
 #include <map>
 #include <tuple>
 
@@ -412,7 +414,13 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
     p.has_dense = (i + 1 < N) ? 1 : 0;
     p.bias_fg = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
     p.bias_d = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_d) + i * 64 : nullptr;
-    WN_PROPAGATE(launch_block_fwd(fp->block[i], p, B * p.tiles_per_batch, s));
+    static int simple_env = -1;
+    if (simple_env < 0) {
+      const char* e = getenv("WN_FWD_SIMPLE");
+      simple_env = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (simple_env) WN_PROPAGATE(launch_block_fwd(fp->block[i], p, B * p.tiles_per_batch, s));     // one tile per CTA
+    else WN_PROPAGATE(launch_block_fwd2(fp->block[i], p, B, s));                                    // persistent
     WN_DEBUG_SYNC("block_fwd", s);
   }
   SkipHeadParams hp{};

@@ -28,6 +28,8 @@ struct BlockFwdParams {
   const float* bias_d;      // [64] or null
 };
 int launch_block_fwd(const BlockFwdMaps& m, const BlockFwdParams& p, int n_ctas, cudaStream_t s);
+// persistent, warp-specialised variant (one CTA per SM loops over the (batch, tile) items)
+int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, int n_batches, cudaStream_t s);
 
 // ---------------------------------------------------------------- forward: skip GEMM + head
 struct SkipHeadMaps {
