@@ -273,7 +273,10 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         mbar_expect_tx(&in_full[st], (dense ? 3 : 2) * TILE_BYTES);
         tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b);
         tma_load_3d(si + TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);
-        if (dense) tma_load_3d(si + 2 * TILE_BYTES, &tm_lo, &in_full[st], 0, tau0, b);
+        if (dense) {
+          if (p.dbg & 4) tma_load_3d(si + 2 * TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);    // same bytes, already in flight
+          else tma_load_3d(si + 2 * TILE_BYTES, &tm_lo, &in_full[st], 0, tau0, b);
+        }
       }
     }
   } else if (warp == 17) {
@@ -339,8 +342,9 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           g0 += p.bias_fg[64 + cg * 16 + 2 * j];
           g1 += p.bias_fg[64 + cg * 16 + 2 * j + 1];
         }
-        const float z0 = valid ? sigmoid_fast(g0) * tanh_fast(f0) : 0.f;
-        const float z1 = valid ? sigmoid_fast(g1) * tanh_fast(f1) : 0.f;
+        float z0 = valid ? sigmoid_fast(g0) * tanh_fast(f0) : 0.f;
+        float z1 = valid ? sigmoid_fast(g1) * tanh_fast(f1) : 0.f;
+        if (p.dbg & 8) { z0 = g0 * f0; z1 = g1 * f1; }
         pz[j] = pack_bf16(z0, z1);
       }
       if (dense && it > 0) mbar_wait(&z_free, (it & 1) ^ 1);      // UMMA #2 of the previous tile has read the z tile
@@ -353,7 +357,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       epi16_bar_sync();
       if (tid == 0) {
         if (dense) mbar_arrive(&z_ready);
-        if (tau0 >= p.tw_al) {
+        if (tau0 >= p.tw_al && !(p.dbg & 1)) {
           tma_store_3d(&tm_z, sm + Fwd2Smem::Z, p.zcol, tau0 - p.tw_al, b);
           tma_store_commit();
         }
@@ -401,7 +405,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (tid == 0) {
         mbar_arrive(&in_empty[st]);
         mbar_arrive(&acc_empty[st]);
-        if (dense) {
+        if (dense && !(p.dbg & 2)) {
           tma_store_3d(&tm_xo, sm + Fwd2Smem::XO, 0, tau0, b);
           tma_store_3d(&tm_loo, sm + Fwd2Smem::LOO, 0, tau0, b);
           tma_store_commit();

@@ -414,6 +414,12 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
     p.has_dense = (i + 1 < N) ? 1 : 0;
     p.bias_fg = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
     p.bias_d = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_d) + i * 64 : nullptr;
+    static int dbg_env = -1;
+    if (dbg_env < 0) {
+      const char* e = getenv("WN_DBG");
+      dbg_env = e ? atoi(e) : 0;
+    }
+    p.dbg = dbg_env;
     static int simple_env = -1;
     if (simple_env < 0) {
       const char* e = getenv("WN_FWD_SIMPLE");

@@ -26,6 +26,7 @@ struct BlockFwdParams {
   int has_dense;            // 0 for the last layer (its dense output is discarded, model.py:121-124)
   const float* bias_fg;     // [128] or null
   const float* bias_d;      // [64] or null
+  int dbg;                  // WN_DBG bit mask (timing experiments only): 1 no Zcat store, 2 no x stores, 4 no lo load, 8 no MUFU
 };
 int launch_block_fwd(const BlockFwdMaps& m, const BlockFwdParams& p, int n_ctas, cudaStream_t s);
 // persistent, warp-specialised variant (one CTA per SM loops over the (batch, tile) items)
