@@ -634,12 +634,19 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 // dW = sum over CTAs of the partial tiles written by block_bwd2 (fixed summation order: deterministic)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, float* __restrict__ g_filt,
                                                            float* __restrict__ g_gate, float* __restrict__ g_dense) {
-  const int e = blockIdx.x * 256 + threadIdx.x;           // element of the [128][192] tile
-  if (e >= 128 * 192) return;
+  // 8 consecutive elements x 32 partial-tile groups per block: thread = (element e0 + tid % 8, tiles tid / 8, +32, ...)
+  const int e = blockIdx.x * 8 + (threadIdx.x & 7);
   const int m = e / 192, c = e % 192;
-  if (c >= 128 && (m >= 64 || g_dense == nullptr)) return;
   float s = 0.f;
-  for (int k = 0; k < n_ctas; ++k) s += partial[(int64_t)k * 128 * 192 + e];
+  for (int k = threadIdx.x >> 3; k < n_ctas; k += 32) s += partial[(int64_t)k * 128 * 192 + e];
+  __shared__ float red[32][8];
+  red[threadIdx.x >> 3][threadIdx.x & 7] = s;
+  __syncthreads();
+  if (threadIdx.x >= 8) return;
+  s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) s += red[k][threadIdx.x];      // fixed order: deterministic
+  if (c >= 128 && (m >= 64 || g_dense == nullptr)) return;
   if (c < 128) {          // column = (tap, r): tap = c / 64, r = c % 64 ; row m = output channel (filter 0..63 | gate 64..127)
     float* base = m < 64 ? g_filt : g_gate;
     base[(int64_t)(m & 63) * 128 + (c & 63) * 2 + (c >> 6)] = s;
@@ -670,15 +677,15 @@ __global__ void __launch_bounds__(256) dlogits_transpose_kernel(const float* __r
 }
 
 // dWc (R=64, Q, 2) += scatter of dx0 rows: shared-memory privatised histogram of 64-vectors
-__global__ void __launch_bounds__(256) causal_scatter_bwd_kernel(const int64_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dx0,
+__global__ void __launch_bounds__(1024) causal_scatter_bwd_kernel(const int64_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dx0,
                                                                  float* __restrict__ dW, int L, int Q, int rows_per_cta) {
   extern __shared__ float acc[];       // [2][Q][64]
   const int b = blockIdx.y;
   const int t_begin = 1 + blockIdx.x * rows_per_cta, t_end = min(L, t_begin + rows_per_cta);
   for (int e = threadIdx.x; e < 2 * Q * 64; e += blockDim.x) acc[e] = 0.f;
   __syncthreads();
-  const int r = threadIdx.x & 63, sub = threadIdx.x >> 6;     // 4 rows in flight
-  for (int tau = t_begin + sub; tau < t_end; tau += 4) {
+  const int r = threadIdx.x & 63, sub = threadIdx.x >> 6, nsub = blockDim.x >> 6;     // 16 rows in flight
+  for (int tau = t_begin + sub; tau < t_end; tau += nsub) {
     const float g = __bfloat162float(dx0[((int64_t)b * L + tau) * 64 + r]);
     const int q0 = (int)idx[(int64_t)b * L + tau - 1], q1 = (int)idx[(int64_t)b * L + tau];
     atomicAdd(&acc[(0 * Q + q0) * 64 + r], g);
@@ -825,7 +832,7 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   }
   {
     WN_PROF("wgrad_reduce", s);
-    wgrad_reduce_kernel<<<(128 * 192) / 256, 256, 0, s>>>(p.partial, n_ctas, p.g_filt, p.g_gate, p.g_dense);
+    wgrad_reduce_kernel<<<(128 * 192) / 8, 256, 0, s>>>(p.partial, n_ctas, p.g_filt, p.g_gate, p.g_dense);
     WN_CHECK_LAUNCH();
   }
   return WN_OK;
@@ -913,21 +920,19 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     }
     WN_DEBUG_SYNC("head bias grads", s);
   }
-  // ---- head weight gradients: dP2 = dLg^T relu(h1), dP1 = dH1^T relu(h0)
+  // ---- head weight gradients: dP2 = dLg^T relu(h1), dP1 = dH1^T relu(h0); both m-tiles of each in one launch
   for (int which = 0; which < 2; ++which) {
-    for (int mt = 0; mt < 2; ++mt) {
-      GemmTnMaps tm{};
-      tm.a = which == 0 ? M.dlg : M.dh1;
-      tm.b[0] = which == 0 ? M.h1 : M.h0; tm.b[1] = tm.b[0];
-      GemmTnParams tp{};
-      tp.n_batches = B; tp.tile0 = 0; tp.tiles_per_batch = skip_tiles;
-      tp.a_col0 = 128 * mt; tp.m_valid = 128;
-      for (int j = 0; j < 4; ++j) { tp.b_map[j] = 0; tp.b_row_off[j] = 0; tp.b_col[j] = 64 * j; tp.blk_off[j] = 64 * j; }
-      float* base = G + (which == 0 ? m.post2.w : m.post1.w) + (int64_t)128 * mt * 256;
-      tp.out0 = base; tp.out1 = base + 64 * 256; tp.s_m = 256; tp.s_n = 1; tp.tag = "gemm_tn_head";
-      WN_PROPAGATE(launch_gemm_tn(4, tm, tp, s));
-      WN_DEBUG_SYNC("gemm_tn head", s);
-    }
+    GemmTnMaps tm{};
+    tm.a = which == 0 ? M.dlg : M.dh1;
+    tm.b[0] = which == 0 ? M.h1 : M.h0; tm.b[1] = tm.b[0];
+    GemmTnParams tp{};
+    tp.n_batches = B; tp.tile0 = 0; tp.tiles_per_batch = skip_tiles; tp.m_valid = 128;
+    float* base = G + (which == 0 ? m.post2.w : m.post1.w);
+    tp.out0 = base; tp.out1 = base + 64 * 256; tp.s_m = 256; tp.s_n = 1;
+    tp.y_layers = 4; tp.y_off0 = 0; tp.y_stride = 64;      // four 64-column blocks of the 256-wide B operand
+    tp.tag = "gemm_tn_head";
+    WN_PROPAGATE(launch_gemm_tn(4, tm, tp, s));
+    WN_DEBUG_SYNC("gemm_tn head", s);
   }
   // ---- dZcat = dSK Wskip_cat (every layer's skip data-gradient at once; dSK is read once)
   {
@@ -1041,7 +1046,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     dim3 grid((unsigned)ceil_div(L - 1, rows_per_cta), (unsigned)B);
     {
       WN_PROF("causal_scatter_bwd", s);
-      causal_scatter_bwd_kernel<<<grid, 256, smem, s>>>(d_idx, dx0, G + m.causal.w, L, m.Q, rows_per_cta);
+      causal_scatter_bwd_kernel<<<grid, 1024, smem, s>>>(d_idx, dx0, G + m.causal.w, L, m.Q, rows_per_cta);
       WN_CHECK_LAUNCH();
     }
     WN_DEBUG_SYNC("causal_scatter", s);
