@@ -212,39 +212,45 @@ int launch_block_fwd(const BlockFwdMaps& m, const BlockFwdParams& p, int n_ctas,
 
 // ====================================================================================== block (persistent)
 // 18 warps: 0-15 epilogue (4 per TMEM lane quarter, 16 columns each), 16 TMA producer, 17 MMA issuer.
-// TMEM: two accumulator buffers {f|g: 128 cols, dense: 64 cols} so UMMA #1 of tile n+1 overlaps the epilogues of tile n.
+// TMEM: two accumulator buffers {f|g: 128 cols, dense: 64 cols}; UMMA #1 of tile n+1/n+2 overlaps the epilogues of tile n.
+// Shared memory: resident weights, THREE input stages {x tap0, x tap1}, two z tiles (A operand of UMMA #2).
+// Outputs (x_{i+1} hi / lo, z) go from registers straight to global memory and `lo` is read from global at the top of
+// the tile, so there is no TMA store to wait for; the MMA issuer polls its two job queues (UMMA #2 of tile j2, UMMA #1
+// of tile j1) and never blocks on one while the other is ready.  History (clock64 instrumentation, profiles/): the first
+// persistent version spent, per 6800-cycle tile, 1250 cycles with all threads waiting for the TMA store to drain and
+// 2000 waiting for UMMA #2 queued behind the next tile's UMMA #1 in the in-order tensor pipe.
 namespace {
 
 struct Fwd2Smem {
   static constexpr uint32_t W0 = 0, W1 = TILE_BYTES, WD = 2 * TILE_BYTES;
-  static constexpr uint32_t IN = 2 * TILE_BYTES + WD_BYTES, IN_STAGE = 3 * TILE_BYTES;     // {x tap0, x tap1, lo}
-  static constexpr uint32_t Z = IN + 2 * IN_STAGE, XO = Z + TILE_BYTES, LOO = XO + TILE_BYTES;
-  static constexpr uint32_t TOTAL = LOO + TILE_BYTES;                                      // 184 KB
+  static constexpr uint32_t IN = 2 * TILE_BYTES + WD_BYTES, IN_STAGE = 2 * TILE_BYTES;     // {x tap0, x tap1}
+  static constexpr int STAGES = 3;
+  static constexpr uint32_t Z = IN + STAGES * IN_STAGE;                                    // 2 z tiles
+  static constexpr uint32_t TOTAL = Z + 2 * TILE_BYTES;                                    // 168 KB
 };
 __device__ __forceinline__ void epi16_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __global__ void __launch_bounds__(576, 1)
-block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_xo,
-                  const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
-                  const __grid_constant__ CUtensorMap tm_wd, const __grid_constant__ CUtensorMap tm_z,
-                  const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_loo, BlockFwdParams p,
-                  int n_batches) {
+block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
+                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_wd, BlockFwdParams p,
+                  BlockFwdPtrs g, int n_batches) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t w_full, in_full[2], in_empty[2], fg_full[2], dense_full[2], acc_empty[2], z_ready, z_free;
+  __shared__ __align__(8) uint64_t w_full, in_full[3], in_empty[3], fg_full[2], dense_full[2], acc_empty[2], z_ready;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     mbar_init(&w_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&in_full[i], 1);
-      mbar_init(&in_empty[i], 2);       // UMMA #1 commit + epilogue (residual / lo tiles read)
+      mbar_init(&in_empty[i], 2);       // UMMA #1 commit + epilogue (residual tile read)
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&fg_full[i], 1);
       mbar_init(&dense_full[i], 1);
       mbar_init(&acc_empty[i], 1);
     }
     mbar_init(&z_ready, 1);
-    mbar_init(&z_free, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
@@ -265,51 +271,45 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (dense) tma_load_2d(sm + Fwd2Smem::WD, &tm_wd, &w_full, 0, 0);
       for (int it = 0; it < n_mine; ++it) {
         const int item = blockIdx.x + it * gridDim.x;
-        const int st = it & 1;
-        const uint32_t ph2 = (it >> 1) & 1;
+        const int st = it % 3;
         const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
-        mbar_wait(&in_empty[st], ph2 ^ 1);
+        mbar_wait(&in_empty[st], ((it / 3) & 1) ^ 1);
         uint8_t* si = sm + Fwd2Smem::IN + st * Fwd2Smem::IN_STAGE;
-        mbar_expect_tx(&in_full[st], (dense ? 3 : 2) * TILE_BYTES);
+        mbar_expect_tx(&in_full[st], 2 * TILE_BYTES);
         tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b);
         tma_load_3d(si + TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);
-        if (dense) {
-          if (p.dbg & 4) tma_load_3d(si + 2 * TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);    // same bytes, already in flight
-          else tma_load_3d(si + 2 * TILE_BYTES, &tm_lo, &in_full[st], 0, tau0, b);
-        }
       }
     }
   } else if (warp == 17) {
     if (lane == 0 && n_mine > 0) {
       constexpr uint32_t id1 = idesc_bf16(128, 128, 0, 0), id2 = idesc_bf16(128, 64, 0, 0);
       mbar_wait(&w_full, 0);
-      auto mma1 = [&](int k) {
-        const int st = k & 1;
-        const uint32_t ph2 = (k >> 1) & 1;
-        const uint32_t si = sbase + Fwd2Smem::IN + st * Fwd2Smem::IN_STAGE, acc = tmem + st * 192;
-        mbar_wait(&in_full[st], ph2);
-        mbar_wait(&acc_empty[st], ph2 ^ 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si, kk), desc_kmajor(sbase + Fwd2Smem::W0, kk), id1, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si + TILE_BYTES, kk), desc_kmajor(sbase + Fwd2Smem::W1, kk), id1, true);
-        umma_commit(&fg_full[st]);
-        umma_commit(&in_empty[st]);
-      };
-      mma1(0);
-      for (int it = 0; it < n_mine; ++it) {
-        if (it + 1 < n_mine) mma1(it + 1);
-        if (dense) {
-          mbar_wait(&z_ready, it & 1);
+      int j1 = 0, j2 = 0;          // next UMMA #1 / UMMA #2 tile
+      while (j1 < n_mine || (dense && j2 < n_mine)) {
+        bool progressed = false;
+        if (dense && j2 < j1 && mbar_try_wait(&z_ready, j2 & 1)) {      // UMMA #2 first: never queue it behind a UMMA #1
           tc_fence_after();
-          const uint32_t acc = tmem + (it & 1) * 192 + 128;
+          const uint32_t acc = tmem + (j2 & 1) * 192 + 128;
+          const uint32_t zt = sbase + Fwd2Smem::Z + (j2 & 1) * TILE_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(acc, desc_kmajor(sbase + Fwd2Smem::Z, kk), desc_kmajor(sbase + Fwd2Smem::WD, kk), id2, kk > 0);
-          umma_commit(&dense_full[it & 1]);
-          umma_commit(&z_free);
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(zt, kk), desc_kmajor(sbase + Fwd2Smem::WD, kk), id2, kk > 0);
+          umma_commit(&dense_full[j2 & 1]);
+          ++j2;
+          progressed = true;
         }
+        if (j1 < n_mine && mbar_try_wait(&in_full[j1 % 3], (j1 / 3) & 1) && mbar_try_wait(&acc_empty[j1 & 1], ((j1 >> 1) & 1) ^ 1)) {
+          tc_fence_after();
+          const uint32_t si = sbase + Fwd2Smem::IN + (j1 % 3) * Fwd2Smem::IN_STAGE, acc = tmem + (j1 & 1) * 192;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si, kk), desc_kmajor(sbase + Fwd2Smem::W0, kk), id1, kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si + TILE_BYTES, kk), desc_kmajor(sbase + Fwd2Smem::W1, kk), id1, true);
+          umma_commit(&fg_full[j1 & 1]);
+          umma_commit(&in_empty[j1 % 3]);
+          ++j1;
+          progressed = true;
+        }
+        if (!progressed) __nanosleep(20);
       }
     }
   } else {
@@ -317,69 +317,82 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int row = q4 * 32 + lane;
     for (int it = 0; it < n_mine; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
-      const int st = it & 1;
+      const int st = it % 3, ab = it & 1;
       const uint32_t ph2 = (it >> 1) & 1;
       const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
       const int tau = tau0 + row;
       const bool valid = (tau >= p.s_out) && (tau < p.L);
-      const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, st * 192);
+      const bool in_range = tau < p.L;
+      const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, ab * 192);
       const uint8_t* si = sm + Fwd2Smem::IN + st * Fwd2Smem::IN_STAGE;
-      // ---- epilogue 1: gate
-      mbar_wait(&fg_full[st], ph2);
+      uint8_t* zt = sm + Fwd2Smem::Z + ab * TILE_BYTES;
+      const int64_t grow = ((int64_t)b * p.L + tau) * 64 + cg * 16;          // this thread's 16 channels of row tau
+      const bool rec = p.ts != nullptr && blockIdx.x == 0 && tid == 0;
+      long long* ts = p.ts + (int64_t)it * 8;
+      if (rec) ts[0] = clock64();
+      // low half of the residual stream: issue the global read now, consume it in epilogue 2
+      uint4 lo0 = make_uint4(0, 0, 0, 0), lo1 = lo0;
+      if (dense && in_range && !(p.dbg & 4)) {
+        lo0 = *reinterpret_cast<const uint4*>(g.lo_in + grow);
+        lo1 = *reinterpret_cast<const uint4*>(g.lo_in + grow + 8);
+      }
+      // ---- epilogue 1: gate -> z tile (smem, A operand of UMMA #2) and Zcat (global).  z tile `ab` was last read by
+      //      UMMA #2 of tile it-2, whose completion (dense_full) every thread waited for in that tile's epilogue 2.
+      mbar_wait(&fg_full[ab], ph2);
       tc_fence_after();
-      uint32_t f[16], g[16];
+      if (rec) ts[1] = clock64();
+      uint32_t f[16], gq[16];
       tmem_ld16(lane_addr + cg * 16, f);
-      tmem_ld16(lane_addr + 64 + cg * 16, g);
+      tmem_ld16(lane_addr + 64 + cg * 16, gq);
       tmem_ld_wait();
       uint32_t pz[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float f0 = __uint_as_float(f[2 * j]), f1 = __uint_as_float(f[2 * j + 1]);
-        float g0 = __uint_as_float(g[2 * j]), g1 = __uint_as_float(g[2 * j + 1]);
+        float g0 = __uint_as_float(gq[2 * j]), g1 = __uint_as_float(gq[2 * j + 1]);
         if (p.bias_fg) {
           f0 += p.bias_fg[cg * 16 + 2 * j];
           f1 += p.bias_fg[cg * 16 + 2 * j + 1];
           g0 += p.bias_fg[64 + cg * 16 + 2 * j];
           g1 += p.bias_fg[64 + cg * 16 + 2 * j + 1];
         }
-        float z0 = valid ? sigmoid_fast(g0) * tanh_fast(f0) : 0.f;
-        float z1 = valid ? sigmoid_fast(g1) * tanh_fast(f1) : 0.f;
+        float z0 = sigmoid_fast(g0) * tanh_fast(f0), z1 = sigmoid_fast(g1) * tanh_fast(f1);
         if (p.dbg & 8) { z0 = g0 * f0; z1 = g1 * f1; }
-        pz[j] = pack_bf16(z0, z1);
+        pz[j] = valid ? pack_bf16(z0, z1) : 0u;
       }
-      if (dense && it > 0) mbar_wait(&z_free, (it & 1) ^ 1);      // UMMA #2 of the previous tile has read the z tile
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-        *reinterpret_cast<uint4*>(sm + Fwd2Smem::Z + sw128_chunk(row, cg * 2 + q)) =
-            make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
+      const uint4 zv0 = make_uint4(pz[0], pz[1], pz[2], pz[3]), zv1 = make_uint4(pz[4], pz[5], pz[6], pz[7]);
+      *reinterpret_cast<uint4*>(zt + sw128_chunk(row, cg * 2)) = zv0;
+      *reinterpret_cast<uint4*>(zt + sw128_chunk(row, cg * 2 + 1)) = zv1;
+      if (rec) ts[2] = clock64();
       fence_proxy_async_smem();
       tc_fence_before();
       epi16_bar_sync();
-      if (tid == 0) {
-        if (dense) mbar_arrive(&z_ready);
-        if (tau0 >= p.tw_al && !(p.dbg & 1)) {
-          tma_store_3d(&tm_z, sm + Fwd2Smem::Z, p.zcol, tau0 - p.tw_al, b);
-          tma_store_commit();
-        }
+      if (rec) ts[3] = clock64();
+      if (tid == 0 && dense) mbar_arrive(&z_ready);
+      if (tau >= p.tw0 && in_range && !(p.dbg & 1)) {      // rows of the last W time steps feed the skip GEMM
+        __nv_bfloat16* zc = g.zcat + ((int64_t)b * p.Wp + (tau - p.tw_al)) * p.zpitch + p.zcol + cg * 16;
+        *reinterpret_cast<uint4*>(zc) = zv0;
+        *reinterpret_cast<uint4*>(zc + 8) = zv1;
       }
-      // ---- epilogue 2: dense + residual (hi + lo)
+      // ---- epilogue 2: x_{i+1} = dense + (hi + lo) in fp32, split again into hi + lo
       if (dense) {
-        mbar_wait(&dense_full[st], ph2);
+        mbar_wait(&dense_full[ab], ph2);
         tc_fence_after();
+        if (rec) ts[4] = clock64();
         uint32_t dv[16];
         tmem_ld16(lane_addr + 128 + cg * 16, dv);
         tmem_ld_wait();
         uint32_t ph[8], pl[8];
+        const uint32_t ll[8] = {lo0.x, lo0.y, lo0.z, lo0.w, lo1.x, lo1.y, lo1.z, lo1.w};
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const uint4 rv = *reinterpret_cast<const uint4*>(si + TILE_BYTES + sw128_chunk(row, cg * 2 + q));
-          const uint4 lv = *reinterpret_cast<const uint4*>(si + 2 * TILE_BYTES + sw128_chunk(row, cg * 2 + q));
-          const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w}, ll[4] = {lv.x, lv.y, lv.z, lv.w};
+          const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = 4 * q + e;
             const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
-            const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[e]);
+            const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[j]);
             float x0 = __uint_as_float(dv[2 * j]) + (__low2float(r2) + __low2float(l2));
             float x1 = __uint_as_float(dv[2 * j + 1]) + (__high2float(r2) + __high2float(l2));
             if (p.bias_d) {
@@ -392,27 +405,22 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             pl[j] = pack_bf16(x0 - __low2float(h2), x1 - __high2float(h2));
           }
         }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const uint32_t o = sw128_chunk(row, cg * 2 + q);
-          *reinterpret_cast<uint4*>(sm + Fwd2Smem::XO + o) = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-          *reinterpret_cast<uint4*>(sm + Fwd2Smem::LOO + o) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+        if (in_range && !(p.dbg & 2)) {
+          *reinterpret_cast<uint4*>(g.x_out + grow) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          *reinterpret_cast<uint4*>(g.x_out + grow + 8) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+          *reinterpret_cast<uint4*>(g.lo_out + grow) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          *reinterpret_cast<uint4*>(g.lo_out + grow + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
         }
-        fence_proxy_async_smem();
       }
+      if (rec) ts[5] = clock64();
       tc_fence_before();
-      epi16_bar_sync();
+      epi16_bar_sync();              // every thread has finished reading this tile's TMEM buffer and residual tile
+      if (rec) ts[6] = clock64();
       if (tid == 0) {
+        mbar_arrive(&acc_empty[ab]);
         mbar_arrive(&in_empty[st]);
-        mbar_arrive(&acc_empty[st]);
-        if (dense && !(p.dbg & 2)) {
-          tma_store_3d(&tm_xo, sm + Fwd2Smem::XO, 0, tau0, b);
-          tma_store_3d(&tm_loo, sm + Fwd2Smem::LOO, 0, tau0, b);
-          tma_store_commit();
-        }
-        tma_store_wait_read();           // z / x_{i+1} staging tiles may be rewritten by the next tile
       }
-      epi16_bar_sync();
+      if (rec) ts[7] = clock64();
     }
   }
   tc_fence_before();
@@ -422,7 +430,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 
 }  // namespace
 
-int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, int n_batches, cudaStream_t s) {
+int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, const BlockFwdPtrs& g, int n_batches, cudaStream_t s) {
   static bool attr_set = false;
   const int smem = Fwd2Smem::TOTAL + 1024;
   if (!attr_set) {
@@ -432,7 +440,7 @@ int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, int n_batc
   const int n_items = n_batches * p.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
   WN_PROF("block_fwd", s);
-  block_fwd2_kernel<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.xo, m.w0, m.w1, m.wd, m.z, m.lo, m.loo, p, n_batches);
+  block_fwd2_kernel<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.w0, m.w1, m.wd, p, g, n_batches);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }

@@ -420,13 +420,22 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
       dbg_env = e ? atoi(e) : 0;
     }
     p.dbg = dbg_env;
+    p.ts = (getenv("WN_TS") && i == N / 2) ? reinterpret_cast<long long*>(Wp + wl.X0f) : nullptr;   // layer N/2, scratch = X0f
     static int simple_env = -1;
     if (simple_env < 0) {
       const char* e = getenv("WN_FWD_SIMPLE");
       simple_env = (e && e[0] == '1') ? 1 : 0;
     }
     if (simple_env) WN_PROPAGATE(launch_block_fwd(fp->block[i], p, B * p.tiles_per_batch, s));     // one tile per CTA
-    else WN_PROPAGATE(launch_block_fwd2(fp->block[i], p, B, s));                                    // persistent
+    else {                                                                                          // persistent
+      p.Wp = skip_wp(m, L); p.zpitch = 64 * N;
+      BlockFwdPtrs g{};
+      g.lo_in = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.XLO + wl.x_stride * (i & 1));
+      g.lo_out = reinterpret_cast<__nv_bfloat16*>(Wp + wl.XLO + wl.x_stride * ((i + 1) & 1));
+      g.x_out = reinterpret_cast<__nv_bfloat16*>(Wp + wl.X + wl.x_stride * (i + 1 < N ? i + 1 : i));
+      g.zcat = reinterpret_cast<__nv_bfloat16*>(Wp + wl.Zcat);
+      WN_PROPAGATE(launch_block_fwd2(fp->block[i], p, g, B, s));
+    }
     WN_DEBUG_SYNC("block_fwd", s);
   }
   SkipHeadParams hp{};

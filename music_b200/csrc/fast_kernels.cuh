@@ -1,6 +1,7 @@
 // fast_kernels.cuh - parameter blocks and launchers of the tcgen05 kernels (fast_fwd.cu, fast_bwd.cu).
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "common.cuh"
 
@@ -23,14 +24,23 @@ struct BlockFwdParams {
   int tw0;                  // L - W: first time index that feeds the skip path
   int tw_al;                // tw0 rounded down to a tile boundary: row 0 of the (padded) skip row space
   int zcol;                 // 64 * layer
+  int Wp, zpitch;           // rows per batch and row pitch (elements) of Zcat
   int has_dense;            // 0 for the last layer (its dense output is discarded, model.py:121-124)
   const float* bias_fg;     // [128] or null
   const float* bias_d;      // [64] or null
+  long long* ts;            // optional timestamp buffer (timing experiments): CTA 0 writes 8 clock64 values per tile
   int dbg;                  // WN_DBG bit mask (timing experiments only): 1 no Zcat store, 2 no x stores, 4 no lo load, 8 no MUFU
 };
 int launch_block_fwd(const BlockFwdMaps& m, const BlockFwdParams& p, int n_ctas, cudaStream_t s);
-// persistent, warp-specialised variant (one CTA per SM loops over the (batch, tile) items)
-int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, int n_batches, cudaStream_t s);
+// persistent, warp-specialised variant (one CTA per SM loops over the (batch, tile) items); outputs are written
+// to global memory straight from the epilogue registers
+struct BlockFwdPtrs {
+  const __nv_bfloat16* lo_in;    // low half of x_i      (B, L, 64)
+  __nv_bfloat16* lo_out;         // low half of x_{i+1}
+  __nv_bfloat16* x_out;          // x_{i+1} (hi)
+  __nv_bfloat16* zcat;           // (B, Wp, zpitch)
+};
+int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, const BlockFwdPtrs& g, int n_batches, cudaStream_t s);
 
 // ---------------------------------------------------------------- forward: skip GEMM + head
 struct SkipHeadMaps {
