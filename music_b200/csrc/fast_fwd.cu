@@ -226,14 +226,16 @@ struct Fwd2Smem {
   static constexpr uint32_t IN = 2 * TILE_BYTES + WD_BYTES, IN_STAGE = 2 * TILE_BYTES;     // {x tap0, x tap1}
   static constexpr int STAGES = 3;
   static constexpr uint32_t Z = IN + STAGES * IN_STAGE;                                    // 2 z tiles
-  static constexpr uint32_t TOTAL = Z + 2 * TILE_BYTES;                                    // 168 KB
+  static constexpr uint32_t XO = Z + 2 * TILE_BYTES, LOO = XO + TILE_BYTES;                // staging of x_{i+1} hi / lo
+  static constexpr uint32_t TOTAL = LOO + TILE_BYTES;                                      // 200 KB
 };
 __device__ __forceinline__ void epi16_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __global__ void __launch_bounds__(576, 1)
 block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
-                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_wd, BlockFwdParams p,
-                  BlockFwdPtrs g, int n_batches) {
+                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_wd,
+                  const __grid_constant__ CUtensorMap tm_xo, const __grid_constant__ CUtensorMap tm_loo,
+                  const __grid_constant__ CUtensorMap tm_z, BlockFwdParams p, BlockFwdPtrs g, int n_batches) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t w_full, in_full[3], in_empty[3], fg_full[2], dense_full[2], acc_empty[2], z_ready;
@@ -366,14 +368,12 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (rec) ts[2] = clock64();
       fence_proxy_async_smem();
       tc_fence_before();
+      // all TMA stores committed so far (tiles <= it-1) have been read: the x_{i+1} staging tiles may be rewritten in
+      // epilogue 2, and z tile 1-ab in the next tile.  They were issued a whole epilogue phase ago: normally no wait.
+      if (tid == 0) tma_store_wait_read();
       epi16_bar_sync();
       if (rec) ts[3] = clock64();
       if (tid == 0 && dense) mbar_arrive(&z_ready);
-      if (tau >= p.tw0 && in_range && !(p.dbg & 1)) {      // rows of the last W time steps feed the skip GEMM
-        __nv_bfloat16* zc = g.zcat + ((int64_t)b * p.Wp + (tau - p.tw_al)) * p.zpitch + p.zcol + cg * 16;
-        *reinterpret_cast<uint4*>(zc) = zv0;
-        *reinterpret_cast<uint4*>(zc + 8) = zv1;
-      }
       // ---- epilogue 2: x_{i+1} = dense + (hi + lo) in fp32, split again into hi + lo
       if (dense) {
         mbar_wait(&dense_full[ab], ph2);
@@ -405,12 +405,13 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             pl[j] = pack_bf16(x0 - __low2float(h2), x1 - __high2float(h2));
           }
         }
-        if (in_range && !(p.dbg & 2)) {
-          *reinterpret_cast<uint4*>(g.x_out + grow) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          *reinterpret_cast<uint4*>(g.x_out + grow + 8) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-          *reinterpret_cast<uint4*>(g.lo_out + grow) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-          *reinterpret_cast<uint4*>(g.lo_out + grow + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t o = sw128_chunk(row, cg * 2 + q);
+          *reinterpret_cast<uint4*>(sm + Fwd2Smem::XO + o) = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+          *reinterpret_cast<uint4*>(sm + Fwd2Smem::LOO + o) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
         }
+        fence_proxy_async_smem();
       }
       if (rec) ts[5] = clock64();
       tc_fence_before();
@@ -419,9 +420,16 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (tid == 0) {
         mbar_arrive(&acc_empty[ab]);
         mbar_arrive(&in_empty[st]);
+        if (tau0 >= p.tw_al && !(p.dbg & 1)) tma_store_3d(&tm_z, zt, p.zcol, tau0 - p.tw_al, b);
+        if (dense && !(p.dbg & 2)) {
+          tma_store_3d(&tm_xo, sm + Fwd2Smem::XO, 0, tau0, b);
+          tma_store_3d(&tm_loo, sm + Fwd2Smem::LOO, 0, tau0, b);
+        }
+        tma_store_commit();          // not waited for here: checked before the staging tiles are rewritten (above)
       }
       if (rec) ts[7] = clock64();
     }
+    if (tid == 0) tma_store_wait_read();
   }
   tc_fence_before();
   __syncthreads();
@@ -440,7 +448,7 @@ int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, const Bloc
   const int n_items = n_batches * p.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
   WN_PROF("block_fwd", s);
-  block_fwd2_kernel<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.w0, m.w1, m.wd, p, g, n_batches);
+  block_fwd2_kernel<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.w0, m.w1, m.wd, m.xo, m.loo, m.z, p, g, n_batches);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
