@@ -289,7 +289,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       int j1 = 0, j2 = 0;          // next UMMA #1 / UMMA #2 tile
       while (j1 < n_mine || (dense && j2 < n_mine)) {
         bool progressed = false;
-        if (dense && j2 < j1 && mbar_try_wait(&z_ready, j2 & 1)) {      // UMMA #2 first: never queue it behind a UMMA #1
+        if (dense && j2 < j1 && mbar_test_wait(&z_ready, j2 & 1)) {      // UMMA #2 first: never queue it behind a UMMA #1
           tc_fence_after();
           const uint32_t acc = tmem + (j2 & 1) * 192 + 128;
           const uint32_t zt = sbase + Fwd2Smem::Z + (j2 & 1) * TILE_BYTES;
@@ -299,7 +299,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           ++j2;
           progressed = true;
         }
-        if (j1 < n_mine && mbar_try_wait(&in_full[j1 % 3], (j1 / 3) & 1) && mbar_try_wait(&acc_empty[j1 & 1], ((j1 >> 1) & 1) ^ 1)) {
+        if (j1 < n_mine && mbar_test_wait(&in_full[j1 % 3], (j1 / 3) & 1) && mbar_test_wait(&acc_empty[j1 & 1], ((j1 >> 1) & 1) ^ 1)) {
           tc_fence_after();
           const uint32_t si = sbase + Fwd2Smem::IN + (j1 % 3) * Fwd2Smem::IN_STAGE, acc = tmem + (j1 & 1) * 192;
 #pragma unroll
@@ -311,7 +311,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           ++j1;
           progressed = true;
         }
-        if (!progressed) __nanosleep(20);
+        (void)progressed;
       }
     }
   } else {
