@@ -280,6 +280,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         mbar_expect_tx(&in_full[st], 2 * TILE_BYTES);
         tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b);
         tma_load_3d(si + TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);
+        if (p.ts && blockIdx.x == 0) p.ts[1024 + it * 4 + 2] = clock64();
       }
     }
   } else if (warp == 17) {
@@ -296,6 +297,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(zt, kk), desc_kmajor(sbase + Fwd2Smem::WD, kk), id2, kk > 0);
           umma_commit(&dense_full[j2 & 1]);
+          if (p.ts && blockIdx.x == 0) p.ts[1024 + j2 * 4 + 1] = clock64();
           ++j2;
           progressed = true;
         }
@@ -308,6 +310,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si + TILE_BYTES, kk), desc_kmajor(sbase + Fwd2Smem::W1, kk), id1, true);
           umma_commit(&fg_full[j1 & 1]);
           umma_commit(&in_empty[j1 % 3]);
+          if (p.ts && blockIdx.x == 0) p.ts[1024 + j1 * 4 + 0] = clock64();
           ++j1;
           progressed = true;
         }
@@ -317,6 +320,20 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   } else {
     const int q4 = warp & 3, cg = warp >> 2;
     const int row = q4 * 32 + lane;
+    // low half of the residual stream: read from global one tile AHEAD into registers (its latency is a full tile)
+    auto load_lo = [&](int it_, uint4& a0, uint4& a1) {
+      a0 = make_uint4(0, 0, 0, 0);
+      a1 = a0;
+      if (!dense || it_ >= n_mine || (p.dbg & 4)) return;
+      const int item_ = blockIdx.x + it_ * gridDim.x;
+      const int b_ = item_ / p.tiles_per_batch, tau_ = (p.tile0 + item_ % p.tiles_per_batch) * 128 + row;
+      if (tau_ >= p.L) return;
+      const __nv_bfloat16* src = g.lo_in + ((int64_t)b_ * p.L + tau_) * 64 + cg * 16;
+      a0 = *reinterpret_cast<const uint4*>(src);
+      a1 = *reinterpret_cast<const uint4*>(src + 8);
+    };
+    uint4 nlo0, nlo1;
+    load_lo(0, nlo0, nlo1);
     for (int it = 0; it < n_mine; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int st = it % 3, ab = it & 1;
@@ -332,12 +349,8 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const bool rec = p.ts != nullptr && blockIdx.x == 0 && tid == 0;
       long long* ts = p.ts + (int64_t)it * 8;
       if (rec) ts[0] = clock64();
-      // low half of the residual stream: issue the global read now, consume it in epilogue 2
-      uint4 lo0 = make_uint4(0, 0, 0, 0), lo1 = lo0;
-      if (dense && in_range && !(p.dbg & 4)) {
-        lo0 = *reinterpret_cast<const uint4*>(g.lo_in + grow);
-        lo1 = *reinterpret_cast<const uint4*>(g.lo_in + grow + 8);
-      }
+      const uint4 lo0 = nlo0, lo1 = nlo1;
+      load_lo(it + 1, nlo0, nlo1);
       // ---- epilogue 1: gate -> z tile (smem, A operand of UMMA #2) and Zcat (global).  z tile `ab` was last read by
       //      UMMA #2 of tile it-2, whose completion (dense_full) every thread waited for in that tile's epilogue 2.
       mbar_wait(&fg_full[ab], ph2);

@@ -21,6 +21,10 @@ N = 30; Wp = Lx - ((net.receptive_field - 1) // 128) * 128
 xs = al(B * Lx * 64 * 2)
 off = xs * N + xs * 2 + al(B * Wp * 64 * N * 2) + 2 * al(B * Wp * 256 * 2)
 ts = ws[off:off + 16 * 8 * 8].view(torch.int64).view(16, 8).cpu()
+mm = ws[off + 1024 * 8: off + 1024 * 8 + 16 * 4 * 8].view(torch.int64).view(16, 4).cpu()
+t0 = int(ts[0][0])
+for t in range(15):
+    print(f"T{t:2d}: load_issued {int(mm[t][2])-t0:7d}  M1_issued {int(mm[t][0])-t0:7d}  epi_start {int(ts[t][0])-t0:7d}  fg_seen {int(ts[t][1])-t0:7d}  z_ready~ {int(ts[t][3])-t0:7d}  M2_issued {int(mm[t][1])-t0:7d}  dense_seen {int(ts[t][4])-t0:7d}  end {int(ts[t][7])-t0:7d}")
 names = ["start", "fg_full", "epi1 math", "bar1", "dense_full", "epi2 math", "bar2", "end"]
 for t in range(15):
     row = ts[t]
