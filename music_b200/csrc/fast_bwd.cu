@@ -417,7 +417,12 @@ block_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
 // ========================================================================================= block_bwd2
 // Persistent CTA per SM, 18 warps: 0-15 epilogue (four warps per TMEM lane quarter, 16 columns each),
-// 16 TMA producer, 17 MMA issuer.  TMEM: [0,128) f|g, [128,192) dz, [192,320) dW_fg (both taps), [320,384) dW_dense.
+// 16 TMA producer, 17 MMA issuer.
+// TMEM (512 cols): f|g buffer 0 [0,128), f|g buffer 1 [128,256), dz [256,320), dW_fg (both taps) [320,448), dW_dense [448,512).
+// The recompute UMMA of tile n+1 runs into the other f|g buffer during the epilogue of tile n; the MMA issuer polls its
+// three job queues (dz of the next tile - on the epilogue's critical path - first, then weight gradients, then f|g) with
+// the non-blocking mbarrier.test_wait.  The dFG tiles are TMA-stored without anyone waiting: thread 0 checks the bulk
+// group one phase later, just before the tiles are rewritten.
 struct Bwd2Smem {
   static constexpr uint32_t W0 = 0, W1 = TILE, WDT = 2 * TILE;                 // resident weights (40 KB)
   static constexpr uint32_t IN = 2 * TILE + 8192, IN_STAGE = 3 * TILE;         // 2 x {x tap0, x tap1, dx_{i+1}}
@@ -433,7 +438,7 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const BlockBwdParams& p = pp.b;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t w_full, in_full[2], in_empty[2], acc_full, acc_empty, out_full, out_empty, wg_done;
+  __shared__ __align__(8) uint64_t w_full, in_full[2], in_empty[2], acc_full[2], fg_empty[2], dz_empty, out_full, out_empty, wg_done;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -441,9 +446,10 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&in_full[i], 1);
       mbar_init(&in_empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&fg_empty[i], 1);
     }
-    mbar_init(&acc_full, 1);
-    mbar_init(&acc_empty, 1);
+    mbar_init(&dz_empty, 1);
     mbar_init(&out_full, 1);
     mbar_init(&out_empty, 1);
     mbar_init(&wg_done, 1);
@@ -457,20 +463,21 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const uint32_t sbase = smem_u32(sm);
   const int n_items = pp.n_batches * p.tiles_per_batch;
   const bool dense = p.has_dense != 0;
+  const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  constexpr uint32_t C_DZ = 256, C_WFG = 320, C_WD = 448;
 
   if (warp == 16) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (lane == 0 && n_mine > 0) {
       mbar_expect_tx(&w_full, 2 * TILE + (dense ? 8192 : 0));
       tma_load_2d(sm + Bwd2Smem::W0, &tm_w0, &w_full, 0, 0);
       tma_load_2d(sm + Bwd2Smem::W1, &tm_w1, &w_full, 0, 0);
       if (dense) tma_load_2d(sm + Bwd2Smem::WDT, &tm_wdT, &w_full, 0, 0);
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      for (int it = 0; it < n_mine; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
         const int st = it & 1;
-        const uint32_t sph = (it >> 1) & 1;
         const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
-        mbar_wait(&in_empty[st], sph ^ 1);
+        mbar_wait(&in_empty[st], ((it >> 1) & 1) ^ 1);
         uint8_t* si = sm + Bwd2Smem::IN + st * Bwd2Smem::IN_STAGE;
         mbar_expect_tx(&in_full[st], (dense ? 3 : 2) * TILE);
         tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b);
@@ -479,43 +486,54 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
     }
   } else if (warp == 17) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && (int)blockIdx.x < n_items) {
+    // ------------------------------------------------------------ MMA issuer (polling)
+    if (lane == 0 && n_mine > 0) {
       constexpr uint32_t id_fg = idesc_bf16(128, 128, 0, 0), id_dz = idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t id_wfg = idesc_bf16(128, 128, 1, 1), id_wd = idesc_bf16(128, 64, 1, 1);
       mbar_wait(&w_full, 0);
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int st = it & 1;
-        const uint32_t sph = (it >> 1) & 1, ph = it & 1;
-        const uint32_t si = sbase + Bwd2Smem::IN + st * Bwd2Smem::IN_STAGE;
-        mbar_wait(&in_full[st], sph);
-        mbar_wait(&acc_empty, ph ^ 1);
-        tc_fence_after();
+      int jf = 0, jd = 0, jw = 0;       // next tile for: f|g recompute, dz (+ acc_full commit), weight gradients
+      while (jw < n_mine) {
+        // (1) dz of tile jd: its f|g MMAs have been issued; the dz accumulator has been drained by the previous epilogue
+        if (jd < jf && mbar_test_wait(&dz_empty, (jd & 1) ^ 1)) {
+          if (dense) {
+            tc_fence_after();
+            const uint32_t si = sbase + Bwd2Smem::IN + (jd & 1) * Bwd2Smem::IN_STAGE;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_kmajor(si, k), desc_kmajor(sbase + Bwd2Smem::W0, k), id_fg, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_kmajor(si + TILE, k), desc_kmajor(sbase + Bwd2Smem::W1, k), id_fg, true);
-        if (dense) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + 128, desc_kmajor(si + 2 * TILE, k), desc_kmajor(sbase + Bwd2Smem::WDT, k), id_dz, k > 0);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem + C_DZ, desc_kmajor(si + 2 * TILE, k), desc_kmajor(sbase + Bwd2Smem::WDT, k), id_dz, k > 0);
+          }
+          umma_commit(&acc_full[jd & 1]);
+          ++jd;
+          continue;
         }
-        umma_commit(&acc_full);
-        // weight gradients of this tile once the epilogue has produced dF | dG and z in shared memory
-        mbar_wait(&out_full, ph);
-        tc_fence_after();
+        // (2) weight gradients of tile jw once its epilogue has produced dF | dG | z in shared memory
+        if (jw < jd && mbar_test_wait(&out_full, jw & 1)) {
+          tc_fence_after();
+          const uint32_t si = sbase + Bwd2Smem::IN + (jw & 1) * Bwd2Smem::IN_STAGE;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
-          umma_bf16(tmem + 192, desc_mnmajor(sbase + Bwd2Smem::DF, k, TILE), desc_mnmajor(si, k, TILE), id_wfg, (it | (uint32_t)k) != 0);
-        if (dense) {
+          for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
+            umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd2Smem::DF, k, TILE), desc_mnmajor(si, k, TILE), id_wfg, (jw | k) != 0);
+          if (dense) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)   // dW_dense[r, d] += sum_t dx_{i+1}[t, r] * z[t, d]   (rows 64..127 of the tile are unused)
-            umma_bf16(tmem + 320, desc_mnmajor(si + 2 * TILE, k, 0), desc_mnmajor(sbase + Bwd2Smem::Z, k, TILE), id_wd,
-                      (it | (uint32_t)k) != 0);
+            for (int k = 0; k < 8; ++k)   // dW_dense[r, d] += sum_t dx_{i+1}[t, r] * z[t, d]   (rows 64..127 unused)
+              umma_bf16(tmem + C_WD, desc_mnmajor(si + 2 * TILE, k, 0), desc_mnmajor(sbase + Bwd2Smem::Z, k, TILE), id_wd, (jw | k) != 0);
+          }
+          umma_commit(&in_empty[jw & 1]);
+          umma_commit(&out_empty);
+          ++jw;
+          continue;
         }
-        umma_commit(&in_empty[st]);
-        umma_commit(&out_empty);
+        // (3) f|g recompute of tile jf into buffer jf & 1
+        if (jf < n_mine && mbar_test_wait(&in_full[jf & 1], (jf >> 1) & 1) && mbar_test_wait(&fg_empty[jf & 1], ((jf >> 1) & 1) ^ 1)) {
+          tc_fence_after();
+          const uint32_t si = sbase + Bwd2Smem::IN + (jf & 1) * Bwd2Smem::IN_STAGE, acc = tmem + (jf & 1) * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(si, k), desc_kmajor(sbase + Bwd2Smem::W0, k), id_fg, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(si + TILE, k), desc_kmajor(sbase + Bwd2Smem::W1, k), id_fg, true);
+          ++jf;
+          continue;
+        }
       }
       umma_commit(&wg_done);
     }
@@ -524,9 +542,9 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int q4 = warp & 3, cg = warp >> 2;          // TMEM lane quarter, 16-column group
     const int row = q4 * 32 + lane;
     const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, 0);
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const uint32_t ph = it & 1;
+    for (int it = 0; it < n_mine; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const uint32_t ph = it & 1, ph2 = (it >> 1) & 1;
       const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
       const int tau = tau0 + row;
       const bool valid = tau >= p.s_out && tau < p.L;
@@ -543,12 +561,12 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 8; ++j) zs[j] = 0u;
       }
-      mbar_wait(&acc_full, ph);
+      mbar_wait(&acc_full[ph], ph2);
       tc_fence_after();
       uint32_t f[16], g[16], dzv[16];
-      tmem_ld16(lane_addr + cg * 16, f);
-      tmem_ld16(lane_addr + 64 + cg * 16, g);
-      if (dense) tmem_ld16(lane_addr + 128 + cg * 16, dzv);
+      tmem_ld16(lane_addr + ph * 128 + cg * 16, f);
+      tmem_ld16(lane_addr + ph * 128 + 64 + cg * 16, g);
+      if (dense) tmem_ld16(lane_addr + C_DZ + cg * 16, dzv);
       tmem_ld_wait();
       uint32_t pz[8], pf[8], pg[8];
 #pragma unroll
@@ -570,15 +588,24 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           }
           const float t = tanh_fast(fv[e]), sg = sigmoid_fast(gv[e]);
           const float zz = t * sg;
-          zo[e] = valid ? zz : 0.f;
-          df[e] = valid ? dz[e] * sg * (1.f - t * t) : 0.f;
-          dg[e] = valid ? dz[e] * zz * (1.f - sg) : 0.f;
+          zo[e] = zz;
+          df[e] = dz[e] * sg * (1.f - t * t);
+          dg[e] = dz[e] * zz * (1.f - sg);
         }
-        pz[j] = pack_bf16(zo[0], zo[1]);
-        pf[j] = pack_bf16(df[0], df[1]);
-        pg[j] = pack_bf16(dg[0], dg[1]);
+        pz[j] = valid ? pack_bf16(zo[0], zo[1]) : 0u;
+        pf[j] = valid ? pack_bf16(df[0], df[1]) : 0u;
+        pg[j] = valid ? pack_bf16(dg[0], dg[1]) : 0u;
       }
-      if (it > 0) mbar_wait(&out_empty, ph ^ 1);     // the previous tile's weight-gradient MMAs have read dF | dG | z
+      // the dF | dG | z tiles may be rewritten once (a) the previous tile's weight-gradient MMAs have read them
+      // (out_empty) and (b) its TMA stores have read them (thread 0 checks the bulk group, the barrier publishes it)
+      if (it > 0) mbar_wait(&out_empty, ph ^ 1);
+      tc_fence_before();
+      if (tid == 0) tma_store_wait_read();
+      epi8_bar_sync();                     // also: every thread has drained this tile's TMEM accumulators
+      if (tid == 0) {
+        mbar_arrive(&fg_empty[ph]);
+        mbar_arrive(&dz_empty);
+      }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const uint32_t o = sw128_chunk(row, cg * 2 + q);
@@ -587,34 +614,31 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         *reinterpret_cast<uint4*>(sm + Bwd2Smem::DG + o) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
       }
       fence_proxy_async_smem();
-      tc_fence_before();
       epi8_bar_sync();
       if (tid == 0) {
-        mbar_arrive(&acc_empty);
         mbar_arrive(&out_full);
         tma_store_3d(&tm_dfg, sm + Bwd2Smem::DF, 0, tau0, b);
         tma_store_3d(&tm_dfg, sm + Bwd2Smem::DG, 64, tau0, b);
-        tma_store_commit();
-        tma_store_wait_read();
+        tma_store_commit();                // checked one phase later (above), nobody waits here
       }
-      epi8_bar_sync();
     }
+    if (tid == 0) tma_store_wait_read();
     // ---- flush the weight-gradient accumulators as a per-CTA partial tile [128][192] (plain 16-byte stores; a
     //      second small kernel sums the tiles: 3 M fp32 atomics per launch saturated the L2 atomic units)
     {
       float* prow = pp.partial + ((int64_t)blockIdx.x * 128 + row) * 192;
-      if ((int)blockIdx.x < n_items) {
+      if (n_mine > 0) {
         mbar_wait(&wg_done, 0);
         tc_fence_after();
         uint32_t v[32];
-        tmem_ld32(lane_addr + 192 + cg * 32, v);           // dW_fg columns [32 cg, 32 cg + 32)
+        tmem_ld32(lane_addr + C_WFG + cg * 32, v);         // dW_fg columns [32 cg, 32 cg + 32)
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<uint4*>(prow + cg * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         uint32_t u[16];
         if (dense) {
-          tmem_ld16(lane_addr + 320 + cg * 16, u);         // dW_dense columns [16 cg, 16 cg + 16)
+          tmem_ld16(lane_addr + C_WD + cg * 16, u);        // dW_dense columns [16 cg, 16 cg + 16)
           tmem_ld_wait();
         } else {
 #pragma unroll
