@@ -427,18 +427,21 @@ struct Bwd2Smem {
   static constexpr uint32_t W0 = 0, W1 = TILE, WDT = 2 * TILE;                 // resident weights (40 KB)
   static constexpr uint32_t IN = 2 * TILE + 8192, IN_STAGE = 3 * TILE;         // 2 x {x tap0, x tap1, dx_{i+1}}
   static constexpr uint32_t DF = IN + 2 * IN_STAGE, DG = DF + TILE, Z = DG + TILE;
-  static constexpr uint32_t TOTAL = Z + TILE;                                  // 184 KB
+  static constexpr uint32_t DZS = Z + TILE;                                    // 2 tiles of the skip-path gradient dzs
+  static constexpr uint32_t TOTAL = DZS + 2 * TILE;                            // 216 KB
 };
 __device__ __forceinline__ void epi8_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __global__ void __launch_bounds__(576, 1)
 block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
                   const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_dx,
-                  const __grid_constant__ CUtensorMap tm_wdT, const __grid_constant__ CUtensorMap tm_dfg, BlockBwd2Params pp) {
+                  const __grid_constant__ CUtensorMap tm_wdT, const __grid_constant__ CUtensorMap tm_dfg,
+                  const __grid_constant__ CUtensorMap tm_dzs, BlockBwd2Params pp) {
   const BlockBwdParams& p = pp.b;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t w_full, in_full[2], in_empty[2], acc_full[2], fg_empty[2], dz_empty, out_full, out_empty, wg_done;
+  __shared__ __align__(8) uint64_t dzs_full[2], dzs_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -448,6 +451,8 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_init(&in_empty[i], 1);
       mbar_init(&acc_full[i], 1);
       mbar_init(&fg_empty[i], 1);
+      mbar_init(&dzs_full[i], 1);
+      mbar_init(&dzs_empty[i], 1);
     }
     mbar_init(&dz_empty, 1);
     mbar_init(&out_full, 1);
@@ -483,6 +488,12 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b);
         tma_load_3d(si + TILE, &tm_x, &in_full[st], 0, tau0, b);
         if (dense) tma_load_3d(si + 2 * TILE, &tm_dx, &in_full[st], 0, tau0, b);
+        // skip-path gradient tile (every tile gets one so that the buffer parity stays in step; tiles before the
+        // last W time steps read rows < 0 of the padded row space -> clamp to an all-zero pad tile instead)
+        mbar_wait(&dzs_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&dzs_full[st], TILE);
+        if (tau0 >= p.tw_al) tma_load_3d(sm + Bwd2Smem::DZS + st * TILE, &tm_dzs, &dzs_full[st], p.dzs_col, tau0 - p.tw_al, b);
+        else tma_load_3d(sm + Bwd2Smem::DZS + st * TILE, &tm_dzs, &dzs_full[st], p.dzs_col, p.Wp, b);   // fully out of bounds: zeros
       }
     }
   } else if (warp == 17) {
@@ -548,19 +559,11 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
       const int tau = tau0 + row;
       const bool valid = tau >= p.s_out && tau < p.L;
-      const bool in_w = valid && tau >= p.tw0;
-      uint32_t zs[8];
-      if (in_w) {       // issue the global read of the skip-path gradient before waiting on the MMA
-        const __nv_bfloat16* dzs_row = p.dzs + ((int64_t)b * p.Wp + (tau - p.tw_al)) * p.dzs_pitch + p.dzs_col + cg * 16;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const uint4 a4 = *reinterpret_cast<const uint4*>(dzs_row + q * 8);
-          zs[4 * q] = a4.x; zs[4 * q + 1] = a4.y; zs[4 * q + 2] = a4.z; zs[4 * q + 3] = a4.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) zs[j] = 0u;
-      }
+      mbar_wait(&dzs_full[ph], ph2);
+      const uint8_t* dzt = sm + Bwd2Smem::DZS + ph * TILE;
+      const uint4 zq0 = *reinterpret_cast<const uint4*>(dzt + sw128_chunk(row, cg * 2));
+      const uint4 zq1 = *reinterpret_cast<const uint4*>(dzt + sw128_chunk(row, cg * 2 + 1));
+      const uint32_t zs[8] = {zq0.x, zq0.y, zq0.z, zq0.w, zq1.x, zq1.y, zq1.z, zq1.w};
       mbar_wait(&acc_full[ph], ph2);
       tc_fence_after();
       uint32_t f[16], g[16], dzv[16];
@@ -605,6 +608,7 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (tid == 0) {
         mbar_arrive(&fg_empty[ph]);
         mbar_arrive(&dz_empty);
+        mbar_arrive(&dzs_empty[ph]);
       }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -851,7 +855,7 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   const int n_ctas = std::min(n_items, g_sm_count);
   {
     WN_PROF("block_bwd2", s);
-    block_bwd2_kernel<<<n_ctas, 576, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p);
+    block_bwd2_kernel<<<n_ctas, 576, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, m.dzs, p);
     WN_CHECK_LAUNCH();
   }
   {
@@ -1001,7 +1005,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     {
       BlockBwdMaps bm{};
       bm.x = M.layer[i].x; bm.w0 = M.layer[i].w0; bm.w1 = M.layer[i].w1; bm.dx = dx_next; bm.wdT = M.layer[i].wdT;
-      bm.dfg = M.dfg; bm.zf = M.zf;
+      bm.dfg = M.dfg; bm.zf = M.zf; bm.dzs = M.dzcat;
       BlockBwdParams bp{};
       bp.L = L; bp.d = d; bp.s_out = s_out; bp.tile0 = tile0; bp.tiles_per_batch = tpb; bp.has_dense = has_dense;
       bp.tw0 = L - W; bp.tw_al = tw_al; bp.Wp = Wpad;

@@ -66,6 +66,7 @@ struct BlockBwdMaps {
   CUtensorMap wdT;    // [64 d][64 r]
   CUtensorMap dfg;    // (128, L, B) store
   CUtensorMap zf;     // (64, L, B) store
+  CUtensorMap dzs;    // dZcat (64 N, Wp, B): this layer's 64 columns of the skip-path gradient (load)
 };
 struct BlockBwdParams {
   int L, d, s_out, tile0, tiles_per_batch, has_dense;

@@ -226,8 +226,9 @@ struct Fwd2Smem {
   static constexpr uint32_t IN = 2 * TILE_BYTES + WD_BYTES, IN_STAGE = 2 * TILE_BYTES;     // {x tap0, x tap1}
   static constexpr int STAGES = 3;
   static constexpr uint32_t Z = IN + STAGES * IN_STAGE;                                    // 2 z tiles
-  static constexpr uint32_t XO = Z + 2 * TILE_BYTES, LOO = XO + TILE_BYTES;                // staging of x_{i+1} hi / lo
-  static constexpr uint32_t TOTAL = LOO + TILE_BYTES;                                      // 200 KB
+  static constexpr uint32_t XO = Z + 2 * TILE_BYTES;                                       // staging of x_{i+1} hi
+  static constexpr uint32_t LO = XO + TILE_BYTES;                                          // 2 lo tiles: TMA-loaded, lo' written in place
+  static constexpr uint32_t TOTAL = LO + 2 * TILE_BYTES;                                   // 216 KB
 };
 __device__ __forceinline__ void epi16_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
@@ -235,10 +236,12 @@ __global__ void __launch_bounds__(576, 1)
 block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
                   const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_wd,
                   const __grid_constant__ CUtensorMap tm_xo, const __grid_constant__ CUtensorMap tm_loo,
-                  const __grid_constant__ CUtensorMap tm_z, BlockFwdParams p, BlockFwdPtrs g, int n_batches) {
+                  const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_lo, BlockFwdParams p,
+                  BlockFwdPtrs g, int n_batches) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t w_full, in_full[3], in_empty[3], fg_full[2], dense_full[2], acc_empty[2], z_ready;
+  __shared__ __align__(8) uint64_t lo_full[2], lo_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -251,6 +254,8 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_init(&fg_full[i], 1);
       mbar_init(&dense_full[i], 1);
       mbar_init(&acc_empty[i], 1);
+      mbar_init(&lo_full[i], 1);
+      mbar_init(&lo_empty[i], 1);
     }
     mbar_init(&z_ready, 1);
     fence_barrier_init();
@@ -281,6 +286,11 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b);
         tma_load_3d(si + TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);
         if (p.ts && blockIdx.x == 0) p.ts[1024 + it * 4 + 2] = clock64();
+        if (dense) {      // low half of the residual stream; its tile is reused for lo' and released after that store
+          mbar_wait(&lo_empty[it & 1], ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&lo_full[it & 1], TILE_BYTES);
+          tma_load_3d(sm + Fwd2Smem::LO + (it & 1) * TILE_BYTES, &tm_lo, &lo_full[it & 1], 0, tau0, b);
+        }
       }
     }
   } else if (warp == 17) {
@@ -320,20 +330,6 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   } else {
     const int q4 = warp & 3, cg = warp >> 2;
     const int row = q4 * 32 + lane;
-    // low half of the residual stream: read from global one tile AHEAD into registers (its latency is a full tile)
-    auto load_lo = [&](int it_, uint4& a0, uint4& a1) {
-      a0 = make_uint4(0, 0, 0, 0);
-      a1 = a0;
-      if (!dense || it_ >= n_mine || (p.dbg & 4)) return;
-      const int item_ = blockIdx.x + it_ * gridDim.x;
-      const int b_ = item_ / p.tiles_per_batch, tau_ = (p.tile0 + item_ % p.tiles_per_batch) * 128 + row;
-      if (tau_ >= p.L) return;
-      const __nv_bfloat16* src = g.lo_in + ((int64_t)b_ * p.L + tau_) * 64 + cg * 16;
-      a0 = *reinterpret_cast<const uint4*>(src);
-      a1 = *reinterpret_cast<const uint4*>(src + 8);
-    };
-    uint4 nlo0, nlo1;
-    load_lo(0, nlo0, nlo1);
     for (int it = 0; it < n_mine; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int st = it % 3, ab = it & 1;
@@ -349,8 +345,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const bool rec = p.ts != nullptr && blockIdx.x == 0 && tid == 0;
       long long* ts = p.ts + (int64_t)it * 8;
       if (rec) ts[0] = clock64();
-      const uint4 lo0 = nlo0, lo1 = nlo1;
-      load_lo(it + 1, nlo0, nlo1);
+      uint8_t* lot = sm + Fwd2Smem::LO + ab * TILE_BYTES;
       // ---- epilogue 1: gate -> z tile (smem, A operand of UMMA #2) and Zcat (global).  z tile `ab` was last read by
       //      UMMA #2 of tile it-2, whose completion (dense_full) every thread waited for in that tile's epilogue 2.
       mbar_wait(&fg_full[ab], ph2);
@@ -383,12 +378,16 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       tc_fence_before();
       // all TMA stores committed so far (tiles <= it-1) have been read: the x_{i+1} staging tiles may be rewritten in
       // epilogue 2, and z tile 1-ab in the next tile.  They were issued a whole epilogue phase ago: normally no wait.
-      if (tid == 0) tma_store_wait_read();
+      if (tid == 0) {
+        tma_store_wait_read();
+        if (dense && it > 0) mbar_arrive(&lo_empty[ab ^ 1]);       // the previous tile's lo' store has been read
+      }
       epi16_bar_sync();
       if (rec) ts[3] = clock64();
       if (tid == 0 && dense) mbar_arrive(&z_ready);
       // ---- epilogue 2: x_{i+1} = dense + (hi + lo) in fp32, split again into hi + lo
       if (dense) {
+        mbar_wait(&lo_full[ab], ph2);
         mbar_wait(&dense_full[ab], ph2);
         tc_fence_after();
         if (rec) ts[4] = clock64();
@@ -396,7 +395,9 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tmem_ld16(lane_addr + 128 + cg * 16, dv);
         tmem_ld_wait();
         uint32_t ph[8], pl[8];
-        const uint32_t ll[8] = {lo0.x, lo0.y, lo0.z, lo0.w, lo1.x, lo1.y, lo1.z, lo1.w};
+        const uint4 lv0 = *reinterpret_cast<const uint4*>(lot + sw128_chunk(row, cg * 2));
+        const uint4 lv1 = *reinterpret_cast<const uint4*>(lot + sw128_chunk(row, cg * 2 + 1));
+        const uint32_t ll[8] = {lv0.x, lv0.y, lv0.z, lv0.w, lv1.x, lv1.y, lv1.z, lv1.w};
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const uint4 rv = *reinterpret_cast<const uint4*>(si + TILE_BYTES + sw128_chunk(row, cg * 2 + q));
@@ -422,7 +423,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int q = 0; q < 2; ++q) {
           const uint32_t o = sw128_chunk(row, cg * 2 + q);
           *reinterpret_cast<uint4*>(sm + Fwd2Smem::XO + o) = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-          *reinterpret_cast<uint4*>(sm + Fwd2Smem::LOO + o) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+          *reinterpret_cast<uint4*>(lot + o) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);   // in place
         }
         fence_proxy_async_smem();
       }
@@ -436,7 +437,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (tau0 >= p.tw_al && !(p.dbg & 1)) tma_store_3d(&tm_z, zt, p.zcol, tau0 - p.tw_al, b);
         if (dense && !(p.dbg & 2)) {
           tma_store_3d(&tm_xo, sm + Fwd2Smem::XO, 0, tau0, b);
-          tma_store_3d(&tm_loo, sm + Fwd2Smem::LOO, 0, tau0, b);
+          tma_store_3d(&tm_loo, lot, 0, tau0, b);
         }
         tma_store_commit();          // not waited for here: checked before the staging tiles are rewritten (above)
       }
@@ -461,7 +462,7 @@ int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, const Bloc
   const int n_items = n_batches * p.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
   WN_PROF("block_fwd", s);
-  block_fwd2_kernel<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.w0, m.w1, m.wd, m.xo, m.loo, m.z, p, g, n_batches);
+  block_fwd2_kernel<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.w0, m.w1, m.wd, m.xo, m.loo, m.z, m.lo, p, g, n_batches);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
