@@ -113,60 +113,110 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int b = rt / p.tiles_per_batch, row0 = (p.tile0 + rt % p.tiles_per_batch) * 128;
       const int row = row0 + tid;
       const bool valid = row >= p.row_lo && row < p.row_hi;
-      mbar_wait(&acc_full[as], aph);
-      tc_fence_after();
       const uint32_t src = tmem_addr(tmem, warp * 32, as * NT);
       const __nv_bfloat16* auxp =
           p.aux ? p.aux + (int64_t)b * p.aux_bstride + (int64_t)row * p.aux_rstride + p.aux_col0 + nt * NT : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < NT / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(src + c * 32, v);
-        tmem_ld_wait();
-        uint32_t packed[16];
-        uint32_t ax[16];
+      if constexpr (NT == 64) {
+        // the whole 128-byte aux row is fetched BEFORE waiting for the accumulator, and the TMA store of the
+        // previous item is only checked right before the staging tile is rewritten: nobody waits for a store
+        uint4 ax4[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ax4[q] = make_uint4(0, 0, 0, 0);
         if (p.epi != EPI_PLAIN && valid) {
 #pragma unroll
+          for (int q = 0; q < 8; ++q) ax4[q] = *reinterpret_cast<const uint4*>(auxp + q * 8);
+        }
+        mbar_wait(&acc_full[as], aph);
+        tc_fence_after();
+        uint32_t packed[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(src + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
+            const uint32_t axw = reinterpret_cast<const uint32_t*>(&ax4[c * 4 + (j >> 2)])[j & 3];
+            const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&axw);
+            if (p.epi == EPI_MASK) {
+              a0 = __low2float(x2) > 0.f ? a0 : 0.f;
+              a1 = __high2float(x2) > 0.f ? a1 : 0.f;
+            } else if (p.epi == EPI_ADD) {
+              a0 += __low2float(x2);
+              a1 += __high2float(x2);
+            }
+            packed[c * 16 + j] = valid ? pack_bf16(a0, a1) : 0u;
+          }
+        }
+        tc_fence_before();
+        if (tid == 0) tma_store_wait_read();
+        epi_bar_sync();
+        if (tid == 0) mbar_arrive(&acc_empty[as]);
+        uint8_t* ot = sm + Cfg::OUT_OFF;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(ot + sw128_chunk(tid, q)) = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (tid == 0) {
+          tma_store_3d(&tmOut, ot, p.out_col0 + nt * NT, row0, b);
+          tma_store_commit();
+        }
+      } else {
+        mbar_wait(&acc_full[as], aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < NT / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(src + c * 32, v);
+          tmem_ld_wait();
+          uint32_t packed[16];
+          uint32_t ax[16];
+          if (p.epi != EPI_PLAIN && valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 a4 = *reinterpret_cast<const uint4*>(auxp + c * 32 + q * 8);
+              ax[4 * q] = a4.x; ax[4 * q + 1] = a4.y; ax[4 * q + 2] = a4.z; ax[4 * q + 3] = a4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ax[j] = 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
+            const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&ax[j]);
+            if (p.epi == EPI_MASK) {
+              a0 = __low2float(x2) > 0.f ? a0 : 0.f;
+              a1 = __high2float(x2) > 0.f ? a1 : 0.f;
+            } else if (p.epi == EPI_ADD) {
+              a0 += __low2float(x2);
+              a1 += __high2float(x2);
+            }
+            packed[j] = valid ? pack_bf16(a0, a1) : 0u;
+          }
+          uint8_t* ot = sm + Cfg::OUT_OFF + (c >> 1) * TILE;
+#pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 a4 = *reinterpret_cast<const uint4*>(auxp + c * 32 + q * 8);
-            ax[4 * q] = a4.x; ax[4 * q + 1] = a4.y; ax[4 * q + 2] = a4.z; ax[4 * q + 3] = a4.w;
+            uint4 val = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            *reinterpret_cast<uint4*>(ot + sw128_chunk(tid, (c & 1) * 4 + q)) = val;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) ax[j] = 0u;
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
-          const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&ax[j]);
-          if (p.epi == EPI_MASK) {
-            a0 = __low2float(x2) > 0.f ? a0 : 0.f;
-            a1 = __high2float(x2) > 0.f ? a1 : 0.f;
-          } else if (p.epi == EPI_ADD) {
-            a0 += __low2float(x2);
-            a1 += __high2float(x2);
-          }
-          packed[j] = valid ? pack_bf16(a0, a1) : 0u;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        epi_bar_sync();
+        if (tid == 0) {
+          mbar_arrive(&acc_empty[as]);
+          for (int j = 0; j < NT / 64; ++j)
+            tma_store_3d(&tmOut, sm + Cfg::OUT_OFF + j * TILE, p.out_col0 + nt * NT + 64 * j, row0, b);
+          tma_store_commit();
+          tma_store_wait_read();
         }
-        uint8_t* ot = sm + Cfg::OUT_OFF + (c >> 1) * TILE;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 val = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-          *reinterpret_cast<uint4*>(ot + sw128_chunk(tid, (c & 1) * 4 + q)) = val;
-        }
+        epi_bar_sync();
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      epi_bar_sync();
-      if (tid == 0) {
-        mbar_arrive(&acc_empty[as]);
-        for (int j = 0; j < NT / 64; ++j)
-          tma_store_3d(&tmOut, sm + Cfg::OUT_OFF + j * TILE, p.out_col0 + nt * NT + 64 * j, row0, b);
-        tma_store_commit();
-        tma_store_wait_read();
-      }
-      epi_bar_sync();
     }
+    if (tid == 0) tma_store_wait_read();
   }
   tc_fence_before();
   __syncthreads();
@@ -660,9 +710,20 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 }
 
 // dW = sum over CTAs of the partial tiles written by block_bwd2 (fixed summation order: deterministic)
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, float* __restrict__ g_filt,
-                                                           float* __restrict__ g_gate, float* __restrict__ g_dense) {
-  // 8 consecutive elements x 32 partial-tile groups per block: thread = (element e0 + tid % 8, tiles tid / 8, +32, ...)
+struct WgradReduceArgs {
+  int64_t filt0, gate0, dense0, layer_stride;     // flat-vector offsets of layer 0's filter / gate / dense weights
+  int n_layers;
+  int n_ctas[64];                                  // partial tiles written per layer
+};
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial_all, int64_t layer_pitch, WgradReduceArgs a,
+                                                           float* __restrict__ G) {
+  // blockIdx.y = layer; 8 consecutive elements x 32 partial-tile groups per block
+  const int layer = blockIdx.y;
+  const float* partial = partial_all + (int64_t)layer * layer_pitch;
+  const int n_ctas = a.n_ctas[layer];
+  float* g_filt = G + a.filt0 + (int64_t)layer * a.layer_stride;
+  float* g_gate = G + a.gate0 + (int64_t)layer * a.layer_stride;
+  float* g_dense = (layer + 1 < a.n_layers) ? G + a.dense0 + (int64_t)layer * a.layer_stride : nullptr;
   const int e = blockIdx.x * 8 + (threadIdx.x & 7);
   const int m = e / 192, c = e % 192;
   float s = 0.f;
@@ -858,11 +919,6 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
     block_bwd2_kernel<<<n_ctas, 576, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, m.dzs, p);
     WN_CHECK_LAUNCH();
   }
-  {
-    WN_PROF("wgrad_reduce", s);
-    wgrad_reduce_kernel<<<(128 * 192) / 8, 256, 0, s>>>(p.partial, n_ctas, p.g_filt, p.g_gate, p.g_dense);
-    WN_CHECK_LAUNCH();
-  }
   return WN_OK;
 }
 
@@ -1015,7 +1071,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
         BlockBwd2Params b2{};
         b2.b = bp; b2.n_batches = B;
         b2.g_filt = G + l.filt.w; b2.g_gate = G + l.gate.w; b2.g_dense = has_dense ? G + l.dense.w : nullptr;
-        b2.partial = reinterpret_cast<float*>(Wp + wl.WGP);
+        b2.partial = reinterpret_cast<float*>(Wp + wl.WGP) + (int64_t)i * WGP_LAYER_FLOATS;
         WN_PROPAGATE(launch_block_bwd2(bm, b2, s));
         WN_DEBUG_SYNC("block_bwd2", s);
       } else {
@@ -1061,6 +1117,17 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       WN_PROPAGATE(launch_gemm_nt(64, gm, gp, s));
       WN_DEBUG_SYNC("gemm_nt dx", s);
     }
+  }
+  if (fused) {   // one reduction of every layer's per-CTA weight-gradient tiles (fixed order: deterministic)
+    WgradReduceArgs ra{};
+    ra.filt0 = m.layers[0].filt.w; ra.gate0 = m.layers[0].gate.w; ra.dense0 = m.layers[0].dense.w;
+    ra.layer_stride = N > 1 ? m.layers[1].filt.w - m.layers[0].filt.w : 0;
+    ra.n_layers = N;
+    for (int i = 0; i < N; ++i) ra.n_ctas[i] = std::min(B * (tiles_total - m.layers[i].start / 128), g_sm_count);
+    WN_PROF("wgrad_reduce", s);
+    dim3 grid((128 * 192) / 8, (unsigned)N);
+    wgrad_reduce_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(Wp + wl.WGP), WGP_LAYER_FLOATS, ra, G);
+    WN_CHECK_LAUNCH();
   }
   // ---- causal layer
   const __nv_bfloat16* dx0 = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DXa);

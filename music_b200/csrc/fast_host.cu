@@ -272,7 +272,7 @@ WsLayout ws_layout(const Model& m, int B, int L) {
   w.DFG = take((size_t)B * L * 128 * 2);
   w.Zf = take((size_t)B * L * 64 * 2);
   w.DX0f = take((size_t)B * L * 64 * 4);
-  w.WGP = take((size_t)160 * 128 * 192 * 4);
+  w.WGP = take((size_t)WGP_LAYER_FLOATS * 4 * N);
   w.total = off;
   return w;
 }

@@ -32,6 +32,7 @@ struct WsLayout {       // byte offsets
   size_t total;
 };
 WsLayout ws_layout(const Model& m, int B, int L);
+constexpr int64_t WGP_LAYER_FLOATS = (int64_t)160 * 128 * 192;     // per-layer region of per-CTA weight-gradient tiles
 // padded skip row space: rows per batch Wp = L - tw_al, tw_al = floor((L-W)/128)*128
 inline int skip_tw_al(const Model& m, int L) { return ((m.rf - 1) / 128) * 128; }
 inline int skip_wp(const Model& m, int L) { return L - skip_tw_al(m, L); }
