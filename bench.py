@@ -61,12 +61,23 @@ def kernel_flops(B):
     f["gemm_nt_dx"] = sum(2.0 * B * l * 2 * R * 2 * D for l in lens)
     f["gemm_tn_dWfg"] = f["gemm_nt_dx"]
     f["gemm_tn_dWd"] = f["block_bwd"]
+    f["block_bwd2"] = f["block_bwd"] + f["gemm_tn_dWfg"] + f["gemm_tn_dWd"]      # dz dgrad + fused weight gradients
     f["gemm_nt_dZcat"] = 2.0 * B * W * N * D * S
     f["gemm_tn_dWs"] = f["gemm_nt_dZcat"]
     f["gemm_nt_dH1"] = 2.0 * B * W * S * Q
     f["gemm_nt_dSK"] = 2.0 * B * W * S * S
     f["gemm_tn_head"] = 2.0 * B * W * (S * Q + S * S)
     return f
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu captures
+    (profiles/r1b_traffic.json; bytes cannot be measured live outside a profiler).  None when not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
+        return t["kernels"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -334,7 +345,7 @@ def main():
             n, c, m = top
             ach = kf[n] * n_prof / (m * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": n, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "traffic": None, "peak_source": peak_src, "launches_per_step": c / n_prof,
+                        "traffic": ncu_traffic(n), "peak_source": peak_src, "launches_per_step": c / n_prof,
                         "avg_launch_ms": m / c,
                         "step_tensor_frac": (value * 3 * flops_per_sample() / world) / (peak * 1e12)}
 

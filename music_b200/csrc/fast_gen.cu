@@ -76,6 +76,27 @@ gen_steps_bf16_kernel(FastGenParams p, char* __restrict__ state, const int64_t* 
   float* part8 = &s_part[0][0][0];                          // viewed as [8][SPC][256]
   float* part32 = &s_part[0][0][0];                         // viewed as [32][SPC][64]
 
+  // per-thread weight slices of one block: [f|g] 8 rows x 8 outputs, dense 2 x 8, skip 8 x 8 (16-byte loads from L2)
+  struct LayerW {
+    uint4 fg[8], d[2], s[8];
+  };
+  const int fg_n0 = (tid & 15) * 8, fg_kg = tid >> 4, fg_k0 = fg_kg * 8;
+  const int d_n0 = (tid & 7) * 8, d_kg = tid >> 3, d_k0 = d_kg * 2;
+  const int s_n0 = (tid & 31) * 8, s_k0 = (tid >> 5) * 8;
+  auto load_layer = [&](int i, LayerW& w) {
+    const __nv_bfloat16* wf = (fg_k0 < 64 ? p.wfgT0 + ((int64_t)i * 64 + fg_k0) * 128 : p.wfgT1 + ((int64_t)i * 64 + (fg_k0 - 64)) * 128) + fg_n0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w.fg[k] = *reinterpret_cast<const uint4*>(wf + (int64_t)k * 128);
+    const __nv_bfloat16* wd = p.wdT + ((int64_t)i * 64 + d_k0) * 64 + d_n0;
+    w.d[0] = *reinterpret_cast<const uint4*>(wd);
+    w.d[1] = *reinterpret_cast<const uint4*>(wd + 64);
+    const __nv_bfloat16* ws = p.wsT + ((int64_t)i * 64 + s_k0) * 256 + s_n0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w.s[k] = *reinterpret_cast<const uint4*>(ws + (int64_t)k * 256);
+  };
+
+  LayerW wa, wb;
+  load_layer(0, wa);
   for (int step = 0; step < p.n_steps; ++step) {
     // ---- prefetch every block's dilated tap (slot t mod d) and run the causal layer (a gather)
     for (int e = tid; e < SPC * p.n_layers * 16; e += 256) {
@@ -99,25 +120,19 @@ gen_steps_bf16_kernel(FastGenParams p, char* __restrict__ state, const int64_t* 
       for (int j = 0; j < 8; ++j) sk[s][j] = 0.f;
     __syncthreads();
 
-    for (int i = 0; i < p.n_layers; ++i) {
+    // one residual block with its weights already in registers (wavenet/fast_generate.py:118-129)
+    auto run_layer = [&](int i, const LayerW& w) {
       // ---- [f|g] = W0 old + W1 x : thread = (8 outputs, 8 inputs)
-      {
-        const int n0 = (tid & 15) * 8, kg = tid >> 4, k0 = kg * 8;       // k in [0,128): tap0 rows then tap1 rows
-        const __nv_bfloat16* wbase = (k0 < 64 ? p.wfgT0 + ((int64_t)i * 64 + k0) * 128 : p.wfgT1 + ((int64_t)i * 64 + (k0 - 64)) * 128) + n0;
-        uint4 w[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) w[k] = *reinterpret_cast<const uint4*>(wbase + (int64_t)k * 128);
+      for (int s = 0; s < SPC; ++s) {
+        float acc[8];
 #pragma unroll
-        for (int s = 0; s < SPC; ++s) {
-          float acc[8];
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const float* in = fg_k0 < 64 ? &s_old[s][i][fg_k0] : &s_x[s][fg_k0 - 64];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-          const float* in = k0 < 64 ? &s_old[s][i][k0] : &s_x[s][k0 - 64];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) fma8(acc, w[k], in[k]);
-          *reinterpret_cast<float4*>(&s_part[kg][s][n0]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-          *reinterpret_cast<float4*>(&s_part[kg][s][n0 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        }
+        for (int k = 0; k < 8; ++k) fma8(acc, w.fg[k], in[k]);
+        *reinterpret_cast<float4*>(&s_part[fg_kg][s][fg_n0]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(&s_part[fg_kg][s][fg_n0 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }
       __syncthreads();
       if (tid < SPC * 64) {        // reduce the 16 partial sums, gate
@@ -132,32 +147,21 @@ gen_steps_bf16_kernel(FastGenParams p, char* __restrict__ state, const int64_t* 
       }
       __syncthreads();
       // ---- dense (64 -> 64) partials and skip (64 -> 256) accumulation in registers
-      {
-        const int n0 = (tid & 7) * 8, kg = tid >> 3, k0 = kg * 2;        // 32 groups of 2 inputs
-        const __nv_bfloat16* wbase = p.wdT + ((int64_t)i * 64 + k0) * 64 + n0;
-        const uint4 w0 = *reinterpret_cast<const uint4*>(wbase), w1 = *reinterpret_cast<const uint4*>(wbase + 64);
 #pragma unroll
-        for (int s = 0; s < SPC; ++s) {
-          float acc[8];
+      for (int s = 0; s < SPC; ++s) {
+        float acc[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-          fma8(acc, w0, s_z[s][k0]);
-          fma8(acc, w1, s_z[s][k0 + 1]);
-          float* dst = part32 + ((int64_t)kg * SPC + s) * 64 + n0;
-          *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-          *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        }
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        fma8(acc, w.d[0], s_z[s][d_k0]);
+        fma8(acc, w.d[1], s_z[s][d_k0 + 1]);
+        float* dst = part32 + ((int64_t)d_kg * SPC + s) * 64 + d_n0;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }
-      {
-        const int n0 = (tid & 31) * 8, k0 = (tid >> 5) * 8;              // 8 groups of 8 inputs
-        const __nv_bfloat16* wbase = p.wsT + ((int64_t)i * 64 + k0) * 256 + n0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint4 w = *reinterpret_cast<const uint4*>(wbase + (int64_t)k * 256);
+      for (int k = 0; k < 8; ++k)
 #pragma unroll
-          for (int s = 0; s < SPC; ++s) fma8(sk[s], w, s_z[s][k0 + k]);
-        }
-      }
+        for (int s = 0; s < SPC; ++s) fma8(sk[s], w.s[k], s_z[s][s_k0 + k]);
       __syncthreads();
       if (tid < SPC * 64) {        // dense reduce + residual, queue push, next block input
         const int s = tid >> 6, r = tid & 63;
@@ -173,7 +177,24 @@ gen_steps_bf16_kernel(FastGenParams p, char* __restrict__ state, const int64_t* 
         s_x[s][r] = y;
       }
       __syncthreads();
+    };
+    // weights of block i+1 are requested from L2 before block i is computed (ping-pong register sets)
+    for (int i = 0; i < p.n_layers; i += 2) {
+      if (i + 1 < p.n_layers) load_layer(i + 1, wb);
+      run_layer(i, wa);
+      if (i + 1 < p.n_layers) {
+        if (i + 2 < p.n_layers) load_layer(i + 2, wa);
+        run_layer(i + 1, wb);
+      }
     }
+    // ---- head weights (two 256 x 256 GEMVs, 8 groups of 32 inputs) are requested a phase ahead as well
+    const int h_n0 = (tid & 31) * 8, h_k0 = (tid >> 5) * 32;
+    uint4 hwa[16], hwb[16];
+    auto load_head = [&](const __nv_bfloat16* Wm, int half, uint4 (&w)[16]) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) w[k] = *reinterpret_cast<const uint4*>(Wm + (int64_t)(h_k0 + half * 16 + k) * 256 + h_n0);
+    };
+    load_head(p.p1T, 0, hwa);
     // ---- skip sum: reduce the 8 input groups, bias, relu
 #pragma unroll
     for (int s = 0; s < SPC; ++s) {
@@ -191,19 +212,25 @@ gen_steps_bf16_kernel(FastGenParams p, char* __restrict__ state, const int64_t* 
     }
     __syncthreads();
     // ---- head: two 256 x 256 GEMVs (8 groups of 32 inputs)
+#pragma unroll
     for (int which = 0; which < 2; ++which) {
-      const __nv_bfloat16* Wm = which == 0 ? p.p1T : p.p2T;
-      const int n0 = (tid & 31) * 8, k0 = (tid >> 5) * 32;
+      const int n0 = h_n0, k0 = h_k0;
       float acc[SPC][8];
 #pragma unroll
       for (int s = 0; s < SPC; ++s)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[s][j] = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < 32; ++k) {
-        const uint4 w = *reinterpret_cast<const uint4*>(Wm + (int64_t)(k0 + k) * 256 + n0);
+      load_head(which == 0 ? p.p1T : p.p2T, 1, hwb);
 #pragma unroll
-        for (int s = 0; s < SPC; ++s) fma8(acc[s], w, s_h[s][k0 + k]);
+      for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int s = 0; s < SPC; ++s) fma8(acc[s], hwa[k], s_h[s][k0 + k]);
+      }
+      if (which == 0) load_head(p.p2T, 0, hwa);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int s = 0; s < SPC; ++s) fma8(acc[s], hwb[k], s_h[s][k0 + 16 + k]);
       }
 #pragma unroll
       for (int s = 0; s < SPC; ++s) {
@@ -211,6 +238,7 @@ gen_steps_bf16_kernel(FastGenParams p, char* __restrict__ state, const int64_t* 
         *reinterpret_cast<float4*>(dst) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]);
       }
+      if (which == 1 && step + 1 < p.n_steps) load_layer(0, wa);
       __syncthreads();
       for (int e = tid; e < SPC * 256; e += 256) {
         const int s = e >> 8, c = e & 255;
