@@ -180,6 +180,17 @@ int32_t wn_ae_receptive_field(const wn_ae* a);
 int wn_ae_workspace_bytes(const wn_ae* a, int32_t B, int32_t L, size_t* bytes);
 int wn_ae_forward(wn_ae* a, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx, const float* d_params,
                   const float* d_cond, void* d_workspace, float* d_logits, float* d_encoding, void* stream);
+/* Training (what autograd does for wavenet_autoencoder/train.py's loss.backward() through model1.py:137-268):
+ * wn_ae_forward_train is wn_ae_forward that keeps every layer's input and pre-activation in the (larger) training
+ * workspace; wn_ae_backward consumes that workspace and d loss / d logits (B,Q,W) and writes d_grads (layout of
+ * d_params) and, if non-NULL, d_cond_grads (layout of d_cond; the reference discards these convs, so this is an
+ * extension for trainable conditioning). */
+int wn_ae_train_workspace_bytes(const wn_ae* a, int32_t B, int32_t L, size_t* bytes);
+int wn_ae_forward_train(wn_ae* a, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx, const float* d_params,
+                        const float* d_cond, void* d_workspace, float* d_logits, float* d_encoding, void* stream);
+int wn_ae_backward(wn_ae* a, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx, const float* d_params,
+                   const float* d_cond, void* d_workspace, const float* d_dlogits, float* d_grads, float* d_cond_grads,
+                   void* stream);
 
 /* ---- instrumentation (bench.py): kernel-launch counter and per-kernel CUDA-event profiler ---------- */
 uint64_t wn_launch_count(void);                 /* kernels launched by this library so far */

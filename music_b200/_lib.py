@@ -75,6 +75,9 @@ SIGNATURES = {
     "wn_ae_receptive_field": (C.c_int32, [_p]),
     "wn_ae_workspace_bytes": (C.c_int, [_p, _i32, _i32, _psz]),
     "wn_ae_forward": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "wn_ae_train_workspace_bytes": (C.c_int, [_p, _i32, _i32, _psz]),
+    "wn_ae_forward_train": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "wn_ae_backward": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "wn_launch_count": (C.c_uint64, []),
     "wn_profile_enable": (C.c_int, [_i32]),
     "wn_profile_report": (C.c_int, [C.c_char_p, _sz]),

@@ -1,4 +1,4 @@
-// ae.cu - wavenet_autoencoder forward (wavenet_autoencoder/model1.py:137-268), fp32 check mode.
+// ae.cu - wavenet_autoencoder forward and backward (wavenet_autoencoder/model1.py:137-268), fp32 check mode.
 //
 //   _encode  (:137-156): en_causal(k=2) -> N x [relu -> dilated conv(k=2) -> relu -> 1x1 -> + residual] -> bottleneck 1x1
 //                        -> AvgPool1d(pool)                         => encoding (B, BW, frames), frames = floor(W / pool)
@@ -69,6 +69,54 @@ __global__ void ae_cond_add_kernel(float* __restrict__ H, const float* __restric
   }
 }
 
+// backward of ae_gate_kernel: dYc[b,t,0:D] = d(gate pre-activation), dYc[b,t,D:2D] = d(filter pre-activation)
+__global__ void ae_gate_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ cond, const float* __restrict__ dZ,
+                                   float* __restrict__ dYc, int L, int D, int t0, int t1, int frames) {
+  const int b = blockIdx.y, len = t1 - t0;
+  const int64_t n = (int64_t)len * D;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tl = (int)(e / D), d = (int)(e % D);
+    const int f = cond_frame(tl, len, frames);
+    const int64_t row = (int64_t)b * L + t0 + tl;
+    const float* y = Y + row * 2 * D;
+    const float* c = cond + ((int64_t)b * frames + f) * 2 * D;
+    const float xg = y[d] + c[d], xf = y[D + d] + c[D + d];
+    const float t = tanhf(xf), sg = 1.f / (1.f + expf(-xg)), dz = dZ[row * D + d];
+    dYc[row * 2 * D + d] = dz * t * sg * (1.f - sg);
+    dYc[row * 2 * D + D + d] = dz * sg * (1.f - t * t);
+  }
+}
+
+// backward of `_conditon` (model1.py:227-247): dcond[b,f,c] = sum over the local rows tl in [0,len) that read frame f.
+// G (B, *, C) rows are addressed as t0 + tl with row pitch `pitch` per batch.
+__global__ void ae_cond_reduce_kernel(const float* __restrict__ G, float* __restrict__ dcond, int64_t pitch, int C, int t0,
+                                      int len, int frames) {
+  const int b = blockIdx.y;
+  const int64_t n = (int64_t)frames * C;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(e / C), c = (int)(e % C);
+    float s = 0.f;
+    if (len % frames == 0) {
+      const int m = len / frames;
+      for (int j = 0; j < m; ++j) s += G[((int64_t)b * pitch + t0 + f * m + j) * C + c];
+    } else {
+      for (int tl = f; tl < len; tl += frames) s += G[((int64_t)b * pitch + t0 + tl) * C + c];
+    }
+    dcond[((int64_t)b * frames + f) * C + c] = s;
+  }
+}
+
+// backward of AvgPool1d: rows t0 + f*pool + j (f < frames) get dENC[b,f,:] / pool, rows past the last full window get 0
+__global__ void avgpool_bwd_kernel(const float* __restrict__ denc, float* __restrict__ dHb, int L, int C, int t0, int pool, int frames) {
+  const int b = blockIdx.y;
+  const int64_t n = (int64_t)(L - t0) * C;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tl = (int)(e / C), c = (int)(e % C);
+    const int f = tl / pool;
+    dHb[((int64_t)b * L + t0 + tl) * C + c] = f < frames ? denc[((int64_t)b * frames + f) * C + c] / (float)pool : 0.f;
+  }
+}
+
 __global__ void onehot_rows_kernel(const int64_t* __restrict__ idx, float* __restrict__ X, int64_t n_rows, int Q) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_rows * Q; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / Q;
@@ -80,11 +128,15 @@ inline int ew_blocks(int64_t n) { return (int)std::min<int64_t>(ceil_div(n, 256)
 
 struct AeWs {
   float *Xin, *S0, *S1, *T, *HB, *ENC, *COND, *Y, *Z, *SK, *H1, *WT;
+  // training only: per-layer saved activations and the gradient buffers of wn_ae_backward
+  float *EX, *ET, *DX, *DY;             // encoder x_i (N+1), encoder conv output (N), decoder x_i (N+1), decoder pre-activation (N)
+  int64_t ex_stride, et_stride, dx_stride, dy_stride;
+  float *gX, *gT, *gZ, *gY, *gSK, *gH1, *gENC, *gCOND, *gHB;
   size_t bytes;
 };
 int64_t conv_elems(const ConvP& c) { return (int64_t)c.out * c.in * c.k; }
 
-AeWs ae_ws(const wn_ae& a, int B, int L, bool need_onehot, void* base) {
+AeWs ae_ws(const wn_ae& a, int B, int L, bool need_onehot, void* base, bool train = false) {
   const int W = L - a.rf + 1, frames = std::max(1, W / a.pool);
   AeWs w{};
   size_t off = 0;
@@ -110,6 +162,23 @@ AeWs ae_ws(const wn_ae& a, int B, int L, bool need_onehot, void* base) {
     for (auto& c : *v) wmax = std::max(wmax, conv_elems(c));
   for (const ConvP* c : {&a.en_causal, &a.bottleneck, &a.de_causal, &a.conn1, &a.conn2}) wmax = std::max(wmax, conv_elems(*c));
   w.WT = take(2 * wmax);      // Wt + Wtt of the conv being applied (repacked per call; check mode)
+  if (train) {
+    w.ex_stride = (int64_t)B * L * a.Re; w.et_stride = (int64_t)B * L * a.De;
+    w.dx_stride = (int64_t)B * L * a.Rd; w.dy_stride = (int64_t)B * L * 2 * a.Dd;
+    w.EX = take(w.ex_stride * (a.N + 1));
+    w.ET = take(w.et_stride * a.N);
+    w.DX = take(w.dx_stride * (a.N + 1));
+    w.DY = take(w.dy_stride * a.N);
+    w.gX = take((int64_t)B * L * std::max(a.Re, a.Rd));
+    w.gT = take((int64_t)B * L * a.De);
+    w.gZ = take((int64_t)B * L * a.Dd);
+    w.gY = take((int64_t)B * L * 2 * a.Dd);
+    w.gSK = take((int64_t)B * W * a.Sd);
+    w.gH1 = take((int64_t)B * W * a.Sd);
+    w.gENC = take((int64_t)B * frames * a.BW);
+    w.gCOND = take((int64_t)B * frames * std::max(2 * a.Dd, a.Sd));
+    w.gHB = take((int64_t)B * L * a.BW);
+  }
   w.bytes = off;
   return w;
 }
@@ -194,8 +263,8 @@ extern "C" int wn_ae_workspace_bytes(const wn_ae* a, int32_t B, int32_t L, size_
   return WN_OK;
 }
 
-extern "C" int wn_ae_forward(wn_ae* a, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx, const float* d_params,
-                             const float* d_cond, void* d_workspace, float* d_logits, float* d_encoding, void* stream) {
+static int ae_forward_impl(wn_ae* a, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx, const float* d_params,
+                           const float* d_cond, void* d_workspace, float* d_logits, float* d_encoding, void* stream, bool train) {
   WN_REQUIRE(g_inited, WN_ERR_UNSUPPORTED, "wn_init() has not succeeded: no sm_100 device, no fallback");
   WN_REQUIRE(a && d_params && d_cond && d_workspace && d_logits, WN_ERR_INVALID, "wn_ae_forward: null argument");
   WN_REQUIRE((d_x != nullptr) != (d_idx != nullptr), WN_ERR_INVALID, "wn_ae_forward: exactly one of d_x / d_idx must be given");
@@ -204,8 +273,13 @@ extern "C" int wn_ae_forward(wn_ae* a, int32_t B, int32_t L, const float* d_x, c
   const int frames = W / a->pool;
   WN_REQUIRE(frames >= 1, WN_ERR_SHAPE, "output width %d shorter than the pooling window %d", W, a->pool);
   cudaStream_t s = (cudaStream_t)stream;
-  AeWs w = ae_ws(*a, B, L, true, d_workspace);
+  AeWs w = ae_ws(*a, B, L, true, d_workspace, train);
   const int N = a->N, Q = a->Q, tw = L - W;
+  // in training every layer writes its own slot (x_i, conv outputs) instead of the ping-pong buffers
+  auto enc_x = [&](int i) { return train ? w.EX + w.ex_stride * i : ((i & 1) ? w.S1 : w.S0); };
+  auto enc_t = [&](int i) { return train ? w.ET + w.et_stride * i : w.T; };
+  auto dec_x = [&](int i) { return train ? w.DX + w.dx_stride * i : ((i & 1) ? w.S1 : w.S0); };
+  auto dec_y = [&](int i) { return train ? w.DY + w.dy_stride * i : w.Y; };
   TensorView Xin;
   if (d_x) {
     Xin = tv(d_x, (int64_t)Q * L, 1, L);                                  // (B,Q,L) as the reference takes it
@@ -217,21 +291,23 @@ extern "C" int wn_ae_forward(wn_ae* a, int32_t B, int32_t L, const float* d_x, c
   auto view = [&](const float* p, int C) { return tv(p, (int64_t)L * C, C, 1); };
   // ------------------------------------------------------------------ encoder (model1.py:137-156)
   {
-    PwArgs p; p.X = Xin; p.x_lo = 0; p.x_hi = L; p.Y = view(w.S0, a->Re); p.B = B; p.t0 = 1; p.t1 = L;
+    PwArgs p; p.X = Xin; p.x_lo = 0; p.x_hi = L; p.Y = view(enc_x(0), a->Re); p.B = B; p.t0 = 1; p.t1 = L;
     WN_PROPAGATE(apply_conv(d_params, a->en_causal, w.WT, p, 1, s));
   }
-  float* cur = w.S0;
-  float* nxt = w.S1;
+  float* cur = enc_x(0);
+  float* nxt = nullptr;
   int s_in = 1;
   for (int i = 0; i < N; ++i) {
     const int d = a->dil[i], s_out = s_in + d;
-    PwArgs p1; p1.X = view(cur, a->Re); p1.x_lo = s_in; p1.x_hi = L; p1.x_relu = 1; p1.Y = view(w.T, a->De);
+    nxt = enc_x(i + 1);
+    float* T = enc_t(i);
+    PwArgs p1; p1.X = view(cur, a->Re); p1.x_lo = s_in; p1.x_hi = L; p1.x_relu = 1; p1.Y = view(T, a->De);
     p1.B = B; p1.t0 = s_out; p1.t1 = L;
     WN_PROPAGATE(apply_conv(d_params, a->en_dil[i], w.WT, p1, d, s));
-    PwArgs p2; p2.X = view(w.T, a->De); p2.x_lo = s_out; p2.x_hi = L; p2.x_relu = 1; p2.Res = view(cur, a->Re);
+    PwArgs p2; p2.X = view(T, a->De); p2.x_lo = s_out; p2.x_hi = L; p2.x_relu = 1; p2.Res = view(cur, a->Re);
     p2.Y = view(nxt, a->Re); p2.B = B; p2.t0 = s_out; p2.t1 = L;
     WN_PROPAGATE(apply_conv(d_params, a->en_dense[i], w.WT, p2, 1, s));
-    std::swap(cur, nxt);
+    cur = nxt;
     s_in = s_out;
   }
   {
@@ -245,21 +321,23 @@ extern "C" int wn_ae_forward(wn_ae* a, int32_t B, int32_t L, const float* d_x, c
   }
   // ------------------------------------------------------------------ decoder (model1.py:158-225)
   {
-    PwArgs p; p.X = Xin; p.x_lo = 0; p.x_hi = L; p.Y = view(w.S0, a->Rd); p.B = B; p.t0 = 1; p.t1 = L;
+    PwArgs p; p.X = Xin; p.x_lo = 0; p.x_hi = L; p.Y = view(dec_x(0), a->Rd); p.B = B; p.t0 = 1; p.t1 = L;
     WN_PROPAGATE(apply_conv(d_params, a->de_causal, w.WT, p, 1, s));
   }
-  cur = w.S0; nxt = w.S1; s_in = 1;
+  cur = dec_x(0); s_in = 1;
   TensorView ENCv = tv(w.ENC, (int64_t)frames * a->BW, a->BW, 1);
   for (int i = 0; i < N; ++i) {
     const int d = a->dil[i], s_out = s_in + d;
     PwArgs pc; pc.X = ENCv; pc.x_lo = 0; pc.x_hi = frames; pc.Y = tv(w.COND, (int64_t)frames * 2 * a->Dd, 2 * a->Dd, 1);
     pc.B = B; pc.t0 = 0; pc.t1 = frames;
     WN_PROPAGATE(apply_conv(d_cond, a->cond[i], w.WT, pc, 1, s));                       // fresh conv on the encoding (:178-179)
-    PwArgs p1; p1.X = view(cur, a->Rd); p1.x_lo = s_in; p1.x_hi = L; p1.Y = view(w.Y, 2 * a->Dd); p1.B = B; p1.t0 = s_out; p1.t1 = L;
+    nxt = dec_x(i + 1);
+    float* Yi = dec_y(i);
+    PwArgs p1; p1.X = view(cur, a->Rd); p1.x_lo = s_in; p1.x_hi = L; p1.Y = view(Yi, 2 * a->Dd); p1.B = B; p1.t0 = s_out; p1.t1 = L;
     WN_PROPAGATE(apply_conv(d_params, a->de_fg[i], w.WT, p1, d, s));                    // filter_gate conv (:175)
     {
       dim3 grid((unsigned)ew_blocks((int64_t)(L - s_out) * a->Dd), (unsigned)B);
-      ae_gate_kernel<<<grid, 256, 0, s>>>(w.Y, w.COND, w.Z, L, a->Dd, s_out, L, frames);   // _conditon + gate (:183-192)
+      ae_gate_kernel<<<grid, 256, 0, s>>>(Yi, w.COND, w.Z, L, a->Dd, s_out, L, frames);   // _conditon + gate (:183-192)
       WN_CHECK_LAUNCH();
     }
     PwArgs p2; p2.X = view(w.Z, a->Dd); p2.x_lo = s_out; p2.x_hi = L; p2.Res = view(cur, a->Rd); p2.Y = view(nxt, a->Rd);
@@ -268,7 +346,7 @@ extern "C" int wn_ae_forward(wn_ae* a, int32_t B, int32_t L, const float* d_x, c
     PwArgs p3; p3.X = view(w.Z, a->Dd); p3.x_lo = tw; p3.x_hi = L; p3.Y = tv(w.SK, (int64_t)W * a->Sd, a->Sd, 1, -tw);
     p3.accumulate = i > 0; p3.B = B; p3.t0 = tw; p3.t1 = L;
     WN_PROPAGATE(apply_conv(d_params, a->de_skip[i], w.WT, p3, 1, s));                  // skip on the last W (:204-208)
-    std::swap(cur, nxt);
+    cur = nxt;
     s_in = s_out;
   }
   TensorView SKv = tv(w.SK, (int64_t)W * a->Sd, a->Sd, 1, -tw), H1v = tv(w.H1, (int64_t)W * a->Sd, a->Sd, 1, -tw);
@@ -285,5 +363,171 @@ extern "C" int wn_ae_forward(wn_ae* a, int32_t B, int32_t L, const float* d_x, c
     p2.B = B; p2.t0 = tw; p2.t1 = L;
     WN_PROPAGATE(apply_conv(d_params, a->conn2, w.WT, p2, 1, s));                       // relu -> connection_2 (:219-221)
   }
+  return WN_OK;
+}
+
+extern "C" int wn_ae_forward(wn_ae* a, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx, const float* d_params,
+                             const float* d_cond, void* d_workspace, float* d_logits, float* d_encoding, void* stream) {
+  return ae_forward_impl(a, B, L, d_x, d_idx, d_params, d_cond, d_workspace, d_logits, d_encoding, stream, false);
+}
+
+extern "C" int wn_ae_train_workspace_bytes(const wn_ae* a, int32_t B, int32_t L, size_t* bytes) {
+  WN_REQUIRE(a && bytes && B > 0, WN_ERR_INVALID, "wn_ae_train_workspace_bytes: bad argument");
+  WN_REQUIRE(L - a->rf + 1 > 0, WN_ERR_SHAPE, "wave sample not long enough");
+  *bytes = ae_ws(*a, B, L, true, nullptr, true).bytes;
+  return WN_OK;
+}
+
+extern "C" int wn_ae_forward_train(wn_ae* a, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx, const float* d_params,
+                                   const float* d_cond, void* d_workspace, float* d_logits, float* d_encoding, void* stream) {
+  return ae_forward_impl(a, B, L, d_x, d_idx, d_params, d_cond, d_workspace, d_logits, d_encoding, stream, true);
+}
+
+// Backward of the whole autoencoder (what autograd does for model1.py:137-268 given d loss / d connection_2 output).
+// The workspace must be the one wn_ae_forward_train filled for the same inputs.  d_grads has the layout of d_params,
+// d_cond_grads (optional) the layout of d_cond.
+extern "C" int wn_ae_backward(wn_ae* a, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx, const float* d_params,
+                              const float* d_cond, void* d_workspace, const float* d_dlogits, float* d_grads, float* d_cond_grads,
+                              void* stream) {
+  WN_REQUIRE(g_inited, WN_ERR_UNSUPPORTED, "wn_init() has not succeeded: no sm_100 device, no fallback");
+  WN_REQUIRE(a && d_params && d_cond && d_workspace && d_dlogits && d_grads, WN_ERR_INVALID, "wn_ae_backward: null argument");
+  WN_REQUIRE((d_x != nullptr) != (d_idx != nullptr), WN_ERR_INVALID, "wn_ae_backward: exactly one of d_x / d_idx must be given");
+  const int W = L - a->rf + 1;
+  WN_REQUIRE(W > 0, WN_ERR_SHAPE, "wave sample not long enough");
+  const int frames = W / a->pool;
+  WN_REQUIRE(frames >= 1, WN_ERR_SHAPE, "output width %d shorter than the pooling window %d", W, a->pool);
+  cudaStream_t s = (cudaStream_t)stream;
+  AeWs w = ae_ws(*a, B, L, true, d_workspace, true);
+  const int N = a->N, Q = a->Q, tw = L - W, Sd = a->Sd, Dd = a->Dd, Rd = a->Rd, Re = a->Re, De = a->De, BW = a->BW;
+  float* G = d_grads;
+  float* Gc = d_cond_grads;
+  WN_CHECK_CUDA(cudaMemsetAsync(G, 0, (size_t)a->n_params * sizeof(float), s));
+  if (Gc) WN_CHECK_CUDA(cudaMemsetAsync(Gc, 0, (size_t)a->n_cond * sizeof(float), s));
+  auto view = [&](const float* p, int C) { return tv(p, (int64_t)L * C, C, 1); };
+  auto wview = [&](const float* p) { return tv(p, (int64_t)W * Sd, Sd, 1, -tw); };
+  TensorView Xin = d_x ? tv(d_x, (int64_t)Q * L, 1, L) : tv(w.Xin, (int64_t)L * Q, Q, 1);     // the one-hot copy is still in the workspace
+  TensorView ENCv = tv(w.ENC, (int64_t)frames * BW, BW, 1), gENCv = tv(w.gENC, (int64_t)frames * BW, BW, 1);
+  // weight gradient of a Conv1d (out,in,k): one reduction per tap; bias = column sums
+  auto conv_wgrad = [&](float* Gbase, const ConvP& c, TensorView X, int x_lo, int x_hi, int x_relu, TensorView dY, int t0, int t1,
+                        int dilation, int nb) -> int {
+    for (int tap = 0; tap < c.k; ++tap) {
+      WgArgs g;
+      g.X = X; g.x_lo = x_lo; g.x_hi = x_hi; g.n_in = c.in; g.x_relu = x_relu; g.off = (c.k == 2 && tap == 0) ? -dilation : 0;
+      g.dY = dY; g.n_out = c.out; g.dW = Gbase + c.w + tap; g.s_out = (int64_t)c.in * c.k; g.s_in = c.k;
+      g.B = nb; g.t0 = t0; g.t1 = t1;
+      WN_PROPAGATE(launch_wgrad(g, s));
+    }
+    if (c.b >= 0) WN_PROPAGATE(launch_colsum(dY, c.out, nb, t0, t1, Gbase + c.b, s));
+    return WN_OK;
+  };
+  // Y (+)= W^T dY : transposed weights [k][out][in] are the second half of the repack scratch
+  auto conv_dgrad = [&](const float* pbase, const ConvP& c, PwArgs p, int dilation) -> int {
+    WN_PROPAGATE(launch_pack_f32(pbase + c.w, w.WT, w.WT + conv_elems(c), c.out, c.in, c.k, s));
+    p.Wt = w.WT + conv_elems(c);
+    p.n_in = c.out; p.n_out = c.in; p.n_taps = c.k;
+    if (c.k == 2) { p.off[0] = dilation; p.off[1] = 0; } else { p.off[0] = 0; }
+    return launch_pw_gemm(p, s);
+  };
+  // conditioning conv i applied to the encoding -> w.COND (needed again by the gate backward)
+  auto cond_fwd = [&](int i, int C) -> int {
+    PwArgs pc; pc.X = ENCv; pc.x_lo = 0; pc.x_hi = frames; pc.Y = tv(w.COND, (int64_t)frames * C, C, 1); pc.B = B; pc.t0 = 0; pc.t1 = frames;
+    return apply_conv(d_cond, a->cond[i], w.WT, pc, 1, s);
+  };
+  // gradient arriving at conditioning conv i's output (already reduced over time into w.gCOND): its weights, and the encoding
+  bool enc_started = false;
+  auto cond_bwd = [&](int i, int C) -> int {
+    TensorView gC = tv(w.gCOND, (int64_t)frames * C, C, 1);
+    if (Gc) WN_PROPAGATE(conv_wgrad(Gc, a->cond[i], ENCv, 0, frames, 0, gC, 0, frames, 1, B));
+    PwArgs p; p.X = gC; p.x_lo = 0; p.x_hi = frames; p.Y = gENCv; p.accumulate = enc_started ? 1 : 0; p.B = B; p.t0 = 0; p.t1 = frames;
+    enc_started = true;
+    return conv_dgrad(d_cond, a->cond[i], p, 1);
+  };
+
+  // ------------------------------------------------------------------ head (model1.py:210-221)
+  TensorView dLg = tv(d_dlogits, (int64_t)Q * W, 1, W, -tw);
+  TensorView SKv = wview(w.SK), H1v = wview(w.H1), gH1v = wview(w.gH1), gSKv = wview(w.gSK);
+  WN_PROPAGATE(conv_wgrad(G, a->conn2, H1v, tw, L, 1, dLg, tw, L, 1, B));
+  {
+    PwArgs p; p.X = dLg; p.x_lo = tw; p.x_hi = L; p.Mask = H1v; p.Y = gH1v; p.B = B; p.t0 = tw; p.t1 = L;
+    WN_PROPAGATE(conv_dgrad(d_params, a->conn2, p, 1));
+  }
+  {
+    dim3 grid((unsigned)ew_blocks((int64_t)frames * Sd), (unsigned)B);
+    ae_cond_reduce_kernel<<<grid, 256, 0, s>>>(w.gH1, w.gCOND, W, Sd, 0, W, frames);
+    WN_CHECK_LAUNCH();
+    WN_PROPAGATE(cond_bwd(N, Sd));
+  }
+  WN_PROPAGATE(conv_wgrad(G, a->conn1, SKv, tw, L, 1, gH1v, tw, L, 1, B));
+  {
+    PwArgs p; p.X = gH1v; p.x_lo = tw; p.x_hi = L; p.Mask = SKv; p.Y = gSKv; p.B = B; p.t0 = tw; p.t1 = L;
+    WN_PROPAGATE(conv_dgrad(d_params, a->conn1, p, 1));
+  }
+  // ------------------------------------------------------------------ decoder blocks in reverse (model1.py:171-208)
+  WN_CHECK_CUDA(cudaMemsetAsync(w.gX, 0, (size_t)B * L * std::max(Re, Rd) * sizeof(float), s));
+  TensorView gXv = view(w.gX, Rd), gZv = view(w.gZ, Dd), gYv = view(w.gY, 2 * Dd), Zv = view(w.Z, Dd);
+  for (int i = N - 1; i >= 0; --i) {
+    const int d = a->dil[i], s_out = a->start[i], s_in = s_out - d;
+    const float* Xi = w.DX + w.dx_stride * i;
+    const float* Yi = w.DY + w.dy_stride * i;
+    WN_PROPAGATE(cond_fwd(i, 2 * Dd));
+    {
+      dim3 grid((unsigned)ew_blocks((int64_t)(L - s_out) * Dd), (unsigned)B);
+      ae_gate_kernel<<<grid, 256, 0, s>>>(Yi, w.COND, w.Z, L, Dd, s_out, L, frames);          // recompute z
+      WN_CHECK_LAUNCH();
+    }
+    // dZ = dense^T dX_{i+1} + skip^T dSkip
+    {
+      PwArgs p; p.X = gXv; p.x_lo = s_out; p.x_hi = L; p.Y = gZv; p.B = B; p.t0 = s_out; p.t1 = L;
+      WN_PROPAGATE(conv_dgrad(d_params, a->de_dense[i], p, 1));
+      PwArgs q; q.X = gSKv; q.x_lo = tw; q.x_hi = L; q.Y = gZv; q.accumulate = 1; q.B = B; q.t0 = tw; q.t1 = L;
+      WN_PROPAGATE(conv_dgrad(d_params, a->de_skip[i], q, 1));
+    }
+    WN_PROPAGATE(conv_wgrad(G, a->de_dense[i], Zv, s_out, L, 0, gXv, s_out, L, 1, B));
+    WN_PROPAGATE(conv_wgrad(G, a->de_skip[i], Zv, tw, L, 0, gSKv, tw, L, 1, B));
+    {
+      dim3 grid((unsigned)ew_blocks((int64_t)(L - s_out) * Dd), (unsigned)B);
+      ae_gate_bwd_kernel<<<grid, 256, 0, s>>>(Yi, w.COND, w.gZ, w.gY, L, Dd, s_out, L, frames);
+      WN_CHECK_LAUNCH();
+      dim3 grid2((unsigned)ew_blocks((int64_t)frames * 2 * Dd), (unsigned)B);
+      ae_cond_reduce_kernel<<<grid2, 256, 0, s>>>(w.gY, w.gCOND, L, 2 * Dd, s_out, L - s_out, frames);
+      WN_CHECK_LAUNCH();
+      WN_PROPAGATE(cond_bwd(i, 2 * Dd));
+    }
+    WN_PROPAGATE(conv_wgrad(G, a->de_fg[i], view(Xi, Rd), s_in, L, 0, gYv, s_out, L, d, B));
+    {   // dX_i[tau] += W1^T dY[tau] + W0^T dY[tau + d]   (the residual pass-through is already in gX)
+      PwArgs p; p.X = gYv; p.x_lo = s_out; p.x_hi = L; p.Y = gXv; p.accumulate = 1; p.B = B; p.t0 = s_in; p.t1 = L;
+      WN_PROPAGATE(conv_dgrad(d_params, a->de_fg[i], p, d));
+    }
+  }
+  WN_PROPAGATE(conv_wgrad(G, a->de_causal, Xin, 0, L, 0, gXv, 1, L, 1, B));
+  // ------------------------------------------------------------------ encoder (model1.py:137-156)
+  {
+    dim3 grid((unsigned)ew_blocks((int64_t)W * BW), (unsigned)B);
+    avgpool_bwd_kernel<<<grid, 256, 0, s>>>(w.gENC, w.gHB, L, BW, tw, a->pool, frames);
+    WN_CHECK_LAUNCH();
+  }
+  TensorView gHBv = view(w.gHB, BW);
+  WN_PROPAGATE(conv_wgrad(G, a->bottleneck, view(w.EX + w.ex_stride * N, Re), tw, L, 0, gHBv, tw, L, 1, B));
+  WN_CHECK_CUDA(cudaMemsetAsync(w.gX, 0, (size_t)B * L * std::max(Re, Rd) * sizeof(float), s));
+  TensorView gXe = view(w.gX, Re), gTv = view(w.gT, De);
+  {
+    PwArgs p; p.X = gHBv; p.x_lo = tw; p.x_hi = L; p.Y = gXe; p.B = B; p.t0 = tw; p.t1 = L;
+    WN_PROPAGATE(conv_dgrad(d_params, a->bottleneck, p, 1));
+  }
+  for (int i = N - 1; i >= 0; --i) {
+    const int d = a->dil[i], s_out = a->start[i], s_in = s_out - d;
+    TensorView Xi = view(w.EX + w.ex_stride * i, Re), Ti = view(w.ET + w.et_stride * i, De);
+    WN_PROPAGATE(conv_wgrad(G, a->en_dense[i], Ti, s_out, L, 1, gXe, s_out, L, 1, B));
+    {   // dT = (dense^T dX_{i+1}) where T > 0
+      PwArgs p; p.X = gXe; p.x_lo = s_out; p.x_hi = L; p.Mask = Ti; p.Y = gTv; p.B = B; p.t0 = s_out; p.t1 = L;
+      WN_PROPAGATE(conv_dgrad(d_params, a->en_dense[i], p, 1));
+    }
+    WN_PROPAGATE(conv_wgrad(G, a->en_dil[i], Xi, s_in, L, 1, gTv, s_out, L, d, B));
+    {   // dX_i[tau] += [x_i > 0] (W1^T dT[tau] + W0^T dT[tau + d])
+      PwArgs p; p.X = gTv; p.x_lo = s_out; p.x_hi = L; p.Mask = Xi; p.Y = gXe; p.accumulate = 1; p.B = B; p.t0 = s_in; p.t1 = L;
+      WN_PROPAGATE(conv_dgrad(d_params, a->en_dil[i], p, d));
+    }
+  }
+  WN_PROPAGATE(conv_wgrad(G, a->en_causal, Xin, 0, L, 0, gXe, 1, L, 1, B));
   return WN_OK;
 }

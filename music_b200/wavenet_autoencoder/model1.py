@@ -1,7 +1,8 @@
 """Drop-in for the reference's `wavenet_autoencoder/model1.py`: NSynth-style WaveNet autoencoder.
 
 Reference: class wavenet_autoencoder, wavenet_autoencoder/model1.py:12-268.  Same constructor, attributes,
-submodule names and state_dict keys; `forward` runs in libwavenet_b200.so (csrc/ae.cu, fp32 check mode).
+submodule names and state_dict keys; `forward` and its backward run in libwavenet_b200.so (csrc/ae.cu, fp32 check
+mode), so `loss.backward()` / `optimizer.step()` of wavenet_autoencoder/train.py:150-160 work unchanged.
 
 The reference draws NEW random conditioning convs (`nn.Conv1d(bottleneck, 2*Dd, 1).cuda()` per layer and one more
 after connection_1, model1.py:178-179 and :216-217) on every forward call and never registers or trains them, so its
@@ -20,6 +21,48 @@ import torch.nn as nn
 
 from .. import _lib as L
 from .._engine import SoftmaxRowsFunction, _require_cuda
+
+
+class _AeFunction(torch.autograd.Function):
+    """logits (B,Q,W) = connection_2 output; backward = wn_ae_backward (per-parameter gradients, and gradients of
+    the conditioning convs when they take part in autograd)."""
+
+    @staticmethod
+    def forward(ctx, net, x, idx, cond, *params):
+        src = x if x is not None else idx
+        dev = src.device
+        lib, h = L.load(), net._plan()
+        B, Lx = src.shape[0], src.shape[-1]
+        W = Lx - net.receptive_field + 1
+        flat = torch.cat([p.detach().reshape(-1).float() for p in params]).contiguous()
+        cond = cond.detach().contiguous()
+        ws = net._workspace(B, Lx, dev, train=True)
+        logits = torch.empty(B, net.quantization_channel, W, dtype=torch.float32, device=dev)
+        L.check(lib.wn_ae_forward_train(h, B, Lx, L.ptr(x), L.ptr(idx), L.ptr(flat), L.ptr(cond), L.ptr(ws), L.ptr(logits),
+                                        None, L.stream_ptr()))
+        net._ws_gen += 1
+        ctx.net, ctx.x, ctx.idx, ctx.flat, ctx.cond, ctx.ws, ctx.gen = net, x, idx, flat, cond, ws, net._ws_gen
+        ctx.shapes = [p.shape for p in params]
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        net = ctx.net
+        if ctx.gen != net._ws_gen:
+            raise L.WavenetB200Error("the activation workspace of this forward was overwritten by a later forward; "
+                                     "call backward() before running the module again")
+        src = ctx.x if ctx.x is not None else ctx.idx
+        B, Lx = src.shape[0], src.shape[-1]
+        g = torch.empty_like(ctx.flat)
+        gc = torch.empty_like(ctx.cond) if ctx.needs_input_grad[3] else None
+        L.check(L.load().wn_ae_backward(net._plan(), B, Lx, L.ptr(ctx.x), L.ptr(ctx.idx), L.ptr(ctx.flat), L.ptr(ctx.cond),
+                                        L.ptr(ctx.ws), L.ptr(dlogits.contiguous().float()), L.ptr(g), L.ptr(gc), L.stream_ptr()))
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = int(np.prod(shp))
+            grads.append(g[off:off + n].view(shp))
+            off += n
+        return (None, None, None, gc, *grads)
 
 
 class wavenet_autoencoder(nn.Module):
@@ -50,6 +93,7 @@ class wavenet_autoencoder(nn.Module):
         object.__setattr__(self, "_cond_layers", self._new_cond_layers())
         self._handle = None
         self._ws = {}
+        self._ws_gen = 0
 
     # ---- identical registration order / names (model1.py:55-134) ------------------------------------------------
     def _init_causal_layer(self):
@@ -85,6 +129,8 @@ class wavenet_autoencoder(nn.Module):
     def _new_cond_layers(self):
         layers = [nn.Conv1d(self.en_bottleneck_width, 2 * self.de_dilation_channel, 1) for _ in self.dilations]
         layers.append(nn.Conv1d(self.en_bottleneck_width, self.de_skip_channel, 1))
+        for c in layers:                 # throw-away in the reference: not trained unless the caller turns this on
+            c.requires_grad_(False)
         return layers
 
     @property
@@ -106,13 +152,26 @@ class wavenet_autoencoder(nn.Module):
             assert lib.wn_ae_param_count(h) == sum(p.numel() for p in self.parameters())
         return self._handle
 
+    def _workspace(self, B, Lx, dev, train):
+        key = (B, Lx, str(dev), train)
+        ws = self._ws.get(key)
+        if ws is None:
+            lib = L.load()
+            nbytes = C.c_size_t()
+            fn = lib.wn_ae_train_workspace_bytes if train else lib.wn_ae_workspace_bytes
+            L.check(fn(self._plan(), B, Lx, C.byref(nbytes)))
+            self._ws.clear()
+            ws = torch.zeros(nbytes.value, dtype=torch.uint8, device=dev)
+            self._ws[key] = ws
+        return ws
+
     def _cond_flat(self, cond_weights, device):
         if cond_weights is None:
             if self.fresh_cond:
                 object.__setattr__(self, "_cond_layers", self._new_cond_layers())
             tensors = []
-            for c in self._cond_layers:
-                tensors += [c.weight.detach(), c.bias.detach()]
+            for c in self._cond_layers:      # kept in the autograd graph: they receive gradients if they require them
+                tensors += [c.weight, c.bias]
         else:
             tensors = list(cond_weights.values()) if isinstance(cond_weights, dict) else list(cond_weights)
         flat = torch.cat([t.reshape(-1).float() for t in tensors]).to(device).contiguous()
@@ -125,8 +184,6 @@ class wavenet_autoencoder(nn.Module):
         """Pre-softmax (B,Q,W) tensor = output of connection_2 (model1.py:221)."""
         src = wave_sample if wave_sample is not None else indices
         _require_cuda(src, "input")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and src.requires_grad:
-            raise L.WavenetB200Error("wavenet_autoencoder: only the forward pass is implemented on the GPU so far")
         dev = src.device
         lib = L.init(dev.index if dev.index is not None else torch.cuda.current_device())
         h = self._plan()
@@ -139,16 +196,18 @@ class wavenet_autoencoder(nn.Module):
             x = wave_sample.detach().float().contiguous()
         else:
             idx = indices.detach().to(torch.int64).contiguous()
-        params = torch.cat([p.detach().reshape(-1).float() for p in self.parameters()]).to(dev).contiguous()
         cond = self._cond_flat(cond_weights, dev)
-        key = (B, Lx, str(dev))
-        ws = self._ws.get(key)
-        if ws is None:
-            nbytes = C.c_size_t()
-            L.check(lib.wn_ae_workspace_bytes(h, B, Lx, C.byref(nbytes)))
-            self._ws.clear()
-            ws = torch.zeros(nbytes.value, dtype=torch.uint8, device=dev)
-            self._ws[key] = ws
+        plist = list(self.parameters())
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in plist) or cond.requires_grad):
+            if return_encoding:
+                raise L.WavenetB200Error("return_encoding is an inference-only option (use torch.no_grad())")
+            for p in plist:
+                _require_cuda(p, "parameter")
+            return _AeFunction.apply(self, x, idx, cond, *plist)
+        params = torch.cat([p.detach().reshape(-1).float() for p in plist]).to(dev).contiguous()
+        cond = cond.detach()
+        ws = self._workspace(B, Lx, dev, train=False)
+        self._ws_gen += 1
         logits = torch.empty(B, self.quantization_channel, W, dtype=torch.float32, device=dev)
         frames = W // self.en_pool_kernel_size
         enc = torch.empty(B, max(frames, 1), self.en_bottleneck_width, dtype=torch.float32, device=dev) if return_encoding else None

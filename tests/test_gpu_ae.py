@@ -58,3 +58,108 @@ def test_broadcast_branch_and_encoding_vs_oracle():
     assert max_rel(lg.cpu().numpy(), ref.numpy()) < 1e-4
     with pytest.raises(ValueError, match="wave sample not long enough"):
         net(torch.zeros(1, 256, rf - 1).cuda())
+
+
+def _ae_case(dil, cfg, bias, B, W, seed):
+    from music_b200.wavenet_autoencoder.model1 import wavenet_autoencoder
+    torch.manual_seed(seed)
+    net = wavenet_autoencoder(2, 256, dil, cfg["Re"], cfg["De"], cfg["BW"], cfg["pool"], cfg["Rd"], cfg["Dd"], cfg["Sd"], bias)
+    with torch.no_grad():
+        for p in net.parameters():       # larger weights than the default init so that every ReLU / gate is exercised
+            p.mul_(2.0)
+    st = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    cond = {}
+    for i, c in enumerate(net.cond_layers):
+        cond[f"cond.{i}.weight"] = c.weight.detach().clone().requires_grad_(True)
+        cond[f"cond.{i}.bias"] = c.bias.detach().clone().requires_grad_(True)
+    rf = O.receptive_field(2, dil)
+    idx = torch.randint(0, 256, (B, rf + W - 1))
+    tgt = torch.randint(0, 256, (B * W,))
+    return net, st, cond, idx, tgt
+
+
+@pytest.mark.parametrize("W,bias,dense", [(96, True, True), (100, False, False), (61, True, False)])
+def test_backward_vs_oracle_autograd(W, bias, dense):
+    """loss.backward() through the module (wavenet_autoencoder/train.py:150-160: CrossEntropyLoss on the softmax output)
+    against torch autograd on the oracle, fp32: every registered parameter and the conditioning convs.
+    W=96: 12 frames, broadcast branch of `_conditon`; W=100 / 61: tiled branch, ragged tail after the last pool window."""
+    dil = [1, 2, 4, 8, 1, 2, 4, 8]
+    cfg = dict(Re=16, De=24, BW=32, pool=8, Rd=16, Dd=16, Sd=48)
+    net, st, cond, idx, tgt = _ae_case(dil, cfg, bias, 2, W, seed=W)
+    x = O.one_hot(idx, 256)
+    if dense:
+        x = x + 0.1 * torch.randn_like(x)
+    probs = O.ae_forward_probs(st, cond, dil, x, cfg["pool"])
+    loss_ref = torch.nn.functional.cross_entropy(probs, tgt)
+    loss_ref.backward()
+
+    net = net.cuda()
+    for c in net.cond_layers:
+        c.requires_grad_(True)
+    if dense:
+        out = net(x.cuda())
+    else:
+        out = net.forward_logits(indices=idx.cuda())
+        from music_b200._engine import SoftmaxRowsFunction
+        from music_b200 import _lib as L
+        out = SoftmaxRowsFunction.apply(out, L.ROWS_REFERENCE)
+    assert max_rel(out.detach().cpu().numpy(), probs.detach().numpy()) < 1e-4
+    loss = torch.nn.functional.cross_entropy(out, tgt.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-5
+    worst = 0.0
+    for name, p in net.named_parameters():
+        g_ref = st[name].grad
+        if g_ref is None:                                   # the last block's dense conv feeds nothing (model1.py:194-202)
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        err = max_rel(p.grad.cpu().numpy(), g_ref.numpy())
+        worst = max(worst, err)
+        assert err < 2e-4, (name, err)
+    for i, c in enumerate(net.cond_layers):
+        for nm, t in (("weight", c.weight), ("bias", c.bias)):
+            err = max_rel(t.grad.cpu().numpy(), cond[f"cond.{i}.{nm}"].grad.numpy())
+            assert err < 2e-4, (i, nm, err)
+
+
+def test_train_steps_reduce_loss(tmp_path):
+    """A few iterations of the reference's AE training loop (wavenet_autoencoder/train.py:117-134) on one batch, through the
+    package's own train module, then a checkpoint round trip with the reference's file naming."""
+    from music_b200.wavenet_autoencoder import train as T
+    dil = [1, 2, 4, 8, 1, 2, 4, 8]
+    cfg = dict(Re=16, De=24, BW=32, pool=8, Rd=16, Dd=16, Sd=48)
+    net, st, cond, idx, tgt = _ae_case(dil, cfg, False, 2, 96, seed=5)
+    net = net.cuda()
+    opt = T.get_optimizer(net, 'Adam', 1e-3)
+    x = O.one_hot(idx, 256).cuda()
+    rf = O.receptive_field(2, dil)
+    target = idx[:, rf - 1:]                                 # predict the input itself: learnable
+    losses = [float(T.train_step(net, opt, x, target)) for _ in range(12)]
+    assert losses[-1] < losses[0] - 1e-3, losses
+    T.save_model(net, 3, str(tmp_path) + "/")
+    from music_b200.wavenet_autoencoder.model1 import wavenet_autoencoder
+    net2 = wavenet_autoencoder(2, 256, dil, cfg["Re"], cfg["De"], cfg["BW"], cfg["pool"], cfg["Rd"], cfg["Dd"], cfg["Sd"], False)
+    assert T.load_model(net2, str(tmp_path) + "/", "missing.model") is None
+    assert T.load_model(net2, str(tmp_path) + "/", "wavenet_autoencoder3.model") is net2
+    for (k, a), (_, b) in zip(net.state_dict().items(), net2.state_dict().items()):
+        assert torch.equal(a.cpu(), b), k
+
+
+def test_slow_generate_matches_oracle_greedy():
+    """wavenet_autoencoder/generate.py:13-19: greedy pick over the last row of the scrambled softmax, sliding window."""
+    from music_b200.wavenet_autoencoder.generate import generate_codes
+    dil = [1, 2, 4, 1, 2, 4]
+    cfg = dict(Re=16, De=16, BW=16, pool=8, Rd=16, Dd=16, Sd=32)
+    net, st, cond, idx, tgt = _ae_case(dil, cfg, True, 1, 16, seed=11)
+    rf = O.receptive_field(2, dil)
+    start = O.one_hot(torch.randint(0, 256, (1, rf + 40)), 256)
+    st = {k: v.detach() for k, v in st.items()}
+    cond = {k: v.detach() for k, v in cond.items()}
+    wav, ref = start.clone(), []
+    for _ in range(5):
+        out = O.ae_forward_probs(st, cond, dil, wav, cfg["pool"]).view(-1, 256)
+        p = int(torch.topk(out[-1], 1)[1])
+        ref.append(p)
+        wav = torch.cat((wav[:, :, -rf - 511:], O.one_hot(torch.tensor([[p]]), 256)), 2)
+    got = generate_codes(net.cuda(), 5, start_piece=start)
+    assert got == ref
