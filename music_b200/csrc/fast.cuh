@@ -17,6 +17,8 @@ int fast_backward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx
 
 int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t* d_first_note, const void* d_packed,
                    void* d_state, const float* d_uniforms, int64_t* d_out, float* d_logits, cudaStream_t s);
+size_t fast_gen_frag_bytes(const Model& m);                         // A-fragment image appended to the packed weights
+int fast_gen_pack(const Model& m, const float* d_params, uint8_t* P, cudaStream_t s);   // builds it (fp16) from the fp32 weights
 int fast_selftest(float* h_maxerr, int n_cases, cudaStream_t s);
 
 }  // namespace wn

@@ -1,20 +1,42 @@
-// fast_gen.cu - bf16-weight incremental generation kernel (fast_generate.predict_next step branch,
+// fast_gen.cu - half-precision incremental generation kernel (fast_generate.predict_next step branch,
 // wavenet/fast_generate.py:66-141), R = D = 64, S = Q = 256.
 //
-// One CTA advances SPC = 2 independent streams through n_steps samples.  Per step and stream the work is
-// 31 small GEMVs (1.27 M MAC); the weights (2.4 MB bf16, [in][out] layout of the packed image) do not fit
-// in shared memory, so they are streamed from L2 with 16-byte loads and every load is used for both
-// streams.  State is the same per-stream ring-buffer block as the fp32 kernel (gen.cu): the dilated tap
-// is slot t mod d, and the new vector overwrites it.  HBM/L2-bound by construction: per step a CTA moves
-// 2.4 MB of weights + 2 x 15 KB of ring vectors; the skip sums stay in registers across the 30 blocks.
+// One CTA advances G = 8 independent streams through n_steps samples; the 8 streams are the N dimension of
+// mma.sync.m16n8k16 tiles whose A operand is the weight matrix ([out][in]) and whose B operand is the activation
+// matrix ([in][stream]).  Weights and MMA operands are fp16 (11-bit significand: tighter than the bf16 of the
+// training kernels), accumulation, the residual stream and the ring-buffer state are fp32.  The weights (2.47 MB)
+// do not fit in one SM's shared memory, so they are streamed from L2 once per step and CTA, pre-arranged in
+// A-FRAGMENT order (gen_frag_pack_kernel): every warp load is one coalesced 512-byte line that lands directly in
+// the registers the MMA reads, requested 1.5 blocks ahead of its use.  Measured on B200 (tools/mma_bench.cu):
+// mma.sync.m16n8k16 issues at 0.5 per clock per SM with 21 cycles latency, which is why operands are single fp16
+// values rather than bf16 hi+lo pairs (half the MMAs) and why every accumulator chain is split in two.
+// State is the same per-stream ring-buffer block as the fp32 kernel (gen.cu): the dilated tap is slot t mod d,
+// and the new vector overwrites it; the taps of the NEXT step are fetched with cp.async while the head runs.
+// Bounds (measured, profiles/): one SM pulls the 72 KB of a block's fragments from L2 in ~1150 cycles (64 B/clk), so a step
+// cannot be shorter than ~20 us while every CTA streams all weights; staging them in shared memory instead (TMA bulk ring, tried)
+// is no faster because the LDS traffic of the fragments then costs 576 cycles per block on the critical path.  The next step is a
+// weights-stationary pipeline: fragments resident in the REGISTERS of 17 CTAs (2 blocks each + 2 head CTAs), streams hopping
+// from CTA to CTA.  Latency-bound by construction (31 dependent stages per sample, 2 block-wide barriers per stage).
+#include <cuda_fp16.h>
+#include <cuda_pipeline.h>
+
 #include "fast.cuh"
 #include "fast_layout.cuh"
+#include "tc05.cuh"
 
 namespace wn {
+using namespace tc;
 namespace {
 
-constexpr int SPC = 2;            // streams per CTA
-constexpr int GEN_MAXL = 40;      // static shared memory budget (prefetched taps: 2 x 40 x 64 floats)
+constexpr int G = 8;              // streams per CTA
+constexpr int GEN_MAXL = 40;
+constexpr int XS = 72;            // padded fp32 row of 64
+constexpr int XH = 72;            // padded fp16 row of 64: 36 words -> the 32 lanes of a fragment load hit 32 banks
+constexpr int HH = 264;           // padded fp16 row of 256 (132 words)
+constexpr int HS = 264;           // padded fp32 row of 256
+// fragment image (uint4 per lane and tile): per block [f|g: 8 m-tiles x 8 k-tiles][dense: 4 x 4][skip: 16 x 4], then the head
+constexpr int FRAG_FG = 0, FRAG_D = 8 * 8 * 32, FRAG_S = FRAG_D + 4 * 4 * 32, FRAG_LAYER = FRAG_S + 16 * 4 * 32;
+constexpr int FRAG_HEAD = 16 * 16 * 32;
 
 struct FastGenParams {
   int n_layers, n_streams, n_steps, push, has_bias;
@@ -28,240 +50,336 @@ struct FastGenParams {
   const float* bias_skip;          // 256 (sum over layers)
   const float* bias_p1;
   const float* bias_p2;
-  const __nv_bfloat16* wfgT0;      // [N][64 r][128 o]
-  const __nv_bfloat16* wfgT1;
-  const __nv_bfloat16* wdT;        // [N][64 d][64 r]
-  const __nv_bfloat16* wsT;        // [N][64 d][256 s]
-  const __nv_bfloat16* p1T;        // [256 in][256 out]
-  const __nv_bfloat16* p2T;
+  const uint4* frag;               // A fragments: [N][FRAG_LAYER] then P1 [FRAG_HEAD], P2 [FRAG_HEAD]
 };
 
-__device__ __forceinline__ void fma8(float (&acc)[8], const uint4& w, float x) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+// ---------------------------------------------------------------- fragment image
+struct FragPackArgs {
+  int n_layers;
+  int64_t filt[GEN_MAXL], gate[GEN_MAXL], dense[GEN_MAXL], skip[GEN_MAXL], post1, post2;     // float offsets of the Conv1d weights
+  const float* params;
+  uint4* frag;
+};
+// element (row, k) of A-fragment register e (0..7) of lane l:  row = l/4 + 8*((e>>1)&1),  k = 2*(l%4) + (e&1) + 8*(e>>2)
+__global__ void __launch_bounds__(256) gen_frag_pack_kernel(FragPackArgs a) {
+  const int64_t total = (int64_t)a.n_layers * FRAG_LAYER + 2 * FRAG_HEAD;
+  const float* P = a.params;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = (int)(e & 31);
+    const int64_t tile = e >> 5;
+    const int64_t layer_tiles = FRAG_LAYER / 32;
+    __half v[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 f = __bfloat1622float2(h[j]);
-    acc[2 * j] = fmaf(f.x, x, acc[2 * j]);
-    acc[2 * j + 1] = fmaf(f.y, x, acc[2 * j + 1]);
+    for (int r = 0; r < 8; ++r) {
+      const int row = (lane >> 2) + 8 * ((r >> 1) & 1), kk = 2 * (lane & 3) + (r & 1) + 8 * (r >> 2);
+      float w;
+      if (tile < (int64_t)a.n_layers * layer_tiles) {
+        const int i = (int)(tile / layer_tiles), t = (int)(tile % layer_tiles);
+        if (t < 64) {               // f|g: m-tile j holds filter channels 8j..8j+7 (rows 0-7) and gate channels 8j..8j+7 (rows 8-15);
+                                    // k < 64: tap 0 (applied to the queue head), k >= 64: tap 1 (applied to the new vector)
+          const int mt = t >> 3, kt = t & 7, k = kt * 16 + kk;
+          const int64_t base = row < 8 ? a.filt[i] : a.gate[i];
+          const int o = 8 * mt + (row & 7), in = k & 63, tap = k >> 6;
+          w = P[base + ((int64_t)o * 64 + in) * 2 + tap];
+        } else if (t < 64 + 16) {   // dense (R out, D in, 1)
+          const int u = t - 64, mt = u >> 2, kt = u & 3;
+          w = P[a.dense[i] + (int64_t)(mt * 16 + row) * 64 + kt * 16 + kk];
+        } else {                    // skip (S out, D in, 1)
+          const int u = t - 80, mt = u >> 2, kt = u & 3;
+          w = P[a.skip[i] + (int64_t)(mt * 16 + row) * 64 + kt * 16 + kk];
+        }
+      } else {
+        const int64_t u = tile - (int64_t)a.n_layers * layer_tiles;
+        const int uu = (int)(u & 255), mt = uu >> 4, kt = uu & 15;
+        w = P[(u < 256 ? a.post1 : a.post2) + (int64_t)(mt * 16 + row) * 256 + kt * 16 + kk];
+      }
+      v[r] = __float2half_rn(w);
+    }
+    a.frag[e] = *reinterpret_cast<const uint4*>(v);
   }
+}
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+// B fragment (k16 x n8) of an fp16 [stream][k] shared matrix: lane (n = lane/4, q = lane%4) holds k = 2q,2q+1 and 2q+8,2q+9
+__device__ __forceinline__ void mma_b(float (&c)[4], const uint4& a, const __half* row_k0, int q) {
+  const uint32_t b0 = *reinterpret_cast<const uint32_t*>(row_k0 + 2 * q), b1 = *reinterpret_cast<const uint32_t*>(row_k0 + 2 * q + 8);
+  mma_f16(c, a, b0, b1);
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gate_z(float f, float g) {       // tanh(f) * sigmoid(g), sigmoid(g) = 0.5 tanh(g/2) + 0.5
+  return tanh_approx(f) * fmaf(0.5f, tanh_approx(0.5f * g), 0.5f);
+}
+
+struct GenSmem {
+  float x[G][XS];                  // residual stream (block input / output), fp32
+  __half xh[G][XH];                // the same, fp16 (MMA operand)
+  __half zh[G][XH];                // gated activations
+  __half hh[2][G][HH];             // head activations (ping-pong)
+  float lg[G][HS];                 // logits
+  int note[G], last[G];
+  int slot[2][GEN_MAXL][G];        // ring slot t mod d of every block and stream, for the current / the next step
+  // dynamic tail: float old[N][G][XS], the dilated taps of this step (cp.async landing zone, read as MMA operands)
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 __global__ void __launch_bounds__(256, 1)
 gen_steps_bf16_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __restrict__ first_note,
                       const float* __restrict__ uniforms, int64_t* __restrict__ out, float* __restrict__ logits_out) {
-  __shared__ __align__(16) float s_x[SPC][64];
-  __shared__ __align__(16) float s_old[SPC][GEN_MAXL][64];
-  __shared__ __align__(16) float s_z[SPC][64];
-  __shared__ __align__(16) float s_y[SPC][64];
-  __shared__ __align__(16) float s_part[16][SPC][128];     // reduction scratch (also [8][SPC][256] and [32][SPC][64])
-  __shared__ __align__(16) float s_h[SPC][256];
-  __shared__ __align__(16) float s_lg[SPC][256];
-  __shared__ int s_note[SPC];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  GenSmem& S = *reinterpret_cast<GenSmem*>(smem_raw);
+  const int N = p.n_layers;
+  float* const old = reinterpret_cast<float*>(smem_raw + ((sizeof(GenSmem) + 15) & ~size_t(15)));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int st0 = blockIdx.x * SPC;
-  int n_act = min(SPC, p.n_streams - st0);
-  char* sp[SPC];
-  float* rings[SPC];
-  int64_t t[SPC];
-  int last[SPC], note[SPC];
-#pragma unroll
-  for (int s = 0; s < SPC; ++s) {
-    const int st = min(st0 + s, p.n_streams - 1);
-    sp[s] = state + (int64_t)st * p.state_stride;
-    rings[s] = reinterpret_cast<float*>(sp[s] + 16);
-    t[s] = reinterpret_cast<const int64_t*>(sp[s])[0];
-    last[s] = (int)reinterpret_cast<const int64_t*>(sp[s])[1];
-    note[s] = (int)first_note[st];
+  const int n8 = lane >> 2, q = lane & 3;          // fragment coordinates: B column / C row = n8, C columns = 2q, 2q+1
+  const int st0 = blockIdx.x * G;
+  const int n_act = min(G, p.n_streams - st0);
+  auto stream_ptr = [&](int s) { return state + (int64_t)min(st0 + s, p.n_streams - 1) * p.state_stride; };
+  if (tid < G) {
+    S.note[tid] = (int)first_note[min(st0 + tid, p.n_streams - 1)];
+    S.last[tid] = (int)reinterpret_cast<const int64_t*>(stream_ptr(tid))[1];
   }
-  float* part8 = &s_part[0][0][0];                          // viewed as [8][SPC][256]
-  float* part32 = &s_part[0][0][0];                         // viewed as [32][SPC][64]
+  for (int e = tid; e < N * G; e += 256) {          // the only 64-bit divisions: afterwards the slots advance by one per step
+    const int i = e / G, s = e % G;
+    S.slot[0][i][s] = (int)(reinterpret_cast<const int64_t*>(stream_ptr(s))[0] % p.dil[i]);
+  }
+  __syncthreads();
+  // rings of the two streams whose results this thread holds in its accumulator fragments (columns 2q, 2q+1)
+  float* const ring0 = reinterpret_cast<float*>(stream_ptr(2 * q) + 16);
+  float* const ring1 = reinterpret_cast<float*>(stream_ptr(2 * q + 1) + 16);
 
-  // per-thread weight slices of one block: [f|g] 8 rows x 8 outputs, dense 2 x 8, skip 8 x 8 (16-byte loads from L2)
-  struct LayerW {
-    uint4 fg[8], d[2], s[8];
-  };
-  const int fg_n0 = (tid & 15) * 8, fg_kg = tid >> 4, fg_k0 = fg_kg * 8;
-  const int d_n0 = (tid & 7) * 8, d_kg = tid >> 3, d_k0 = d_kg * 2;
-  const int s_n0 = (tid & 31) * 8, s_k0 = (tid >> 5) * 8;
-  auto load_layer = [&](int i, LayerW& w) {
-    const __nv_bfloat16* wf = (fg_k0 < 64 ? p.wfgT0 + ((int64_t)i * 64 + fg_k0) * 128 : p.wfgT1 + ((int64_t)i * 64 + (fg_k0 - 64)) * 128) + fg_n0;
+  // ---- A fragments in registers, two parity sets (block i uses set i & 1).  fg: the warp's f|g m-tile (8 k-tiles).  w2: warps 0-3
+  // hold their dense m-tile in [0,4) and skip m-tile `warp` in [4,8); warps 4-7 hold skip m-tiles 4 + 3 (warp - 4) + {0,1,2} in
+  // [0,12).  (Warps 0-3 also run the residual epilogue, so they get one skip tile instead of three.)
+  uint4 fgA[8], fgB[8], w2A[12], w2B[12];
+  const uint4* const fbase = p.frag + lane;
+  auto load_fg = [&](int i, uint4 (&w)[8]) {
+    const uint4* base = fbase + (int64_t)i * FRAG_LAYER + FRAG_FG + warp * 8 * 32;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) w.fg[k] = *reinterpret_cast<const uint4*>(wf + (int64_t)k * 128);
-    const __nv_bfloat16* wd = p.wdT + ((int64_t)i * 64 + d_k0) * 64 + d_n0;
-    w.d[0] = *reinterpret_cast<const uint4*>(wd);
-    w.d[1] = *reinterpret_cast<const uint4*>(wd + 64);
-    const __nv_bfloat16* ws = p.wsT + ((int64_t)i * 64 + s_k0) * 256 + s_n0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) w.s[k] = *reinterpret_cast<const uint4*>(ws + (int64_t)k * 256);
+    for (int k = 0; k < 8; ++k) w[k] = base[k * 32];
   };
+  auto load_w2 = [&](int i, uint4 (&w)[12]) {
+    const uint4* base = fbase + (int64_t)i * FRAG_LAYER;
+    if (warp < 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] = base[FRAG_D + (warp * 4 + k) * 32];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[4 + k] = base[FRAG_S + (warp * 4 + k) * 32];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) w[k] = base[FRAG_S + ((4 + 3 * (warp - 4)) * 4 + k) * 32];
+    }
+  };
+  // ---- asynchronous fetch of every block's dilated tap (slot t mod d of the per-stream queues) of all streams.  advance = 0: the
+  // slots of buffer `cur` as they are; advance = 1: the slots of the NEXT step, which are also written to buffer cur ^ 1.
+  auto prefetch_taps = [&](int cur, int advance) {
+    for (int e = tid; e < G * N * 16; e += 256) {
+      const int c4 = (e & 15) * 4, s = (e >> 4) % G, i = (e >> 4) / G;
+      int slot = S.slot[cur][i][s];
+      if (advance) {
+        slot = slot + 1 == p.dil[i] ? 0 : slot + 1;
+        if (c4 == 0) S.slot[cur ^ 1][i][s] = slot;
+      }
+      const float* src = reinterpret_cast<const float*>(stream_ptr(s) + 16) + ((int64_t)p.ring_off[i] + slot) * 64 + c4;
+      __pipeline_memcpy_async(old + (size_t)(e >> 4) * XS + c4, src, 16);
+    }
+    __pipeline_commit();
+  };
+  load_fg(0, fgA);
+  load_w2(0, w2A);
+  if (N > 1) load_fg(1, fgB);
+  prefetch_taps(0, 0);
 
-  LayerW wa, wb;
-  load_layer(0, wa);
+  const uint4* const headA = fbase + (int64_t)N * FRAG_LAYER;
+
   for (int step = 0; step < p.n_steps; ++step) {
-    // ---- prefetch every block's dilated tap (slot t mod d) and run the causal layer (a gather)
-    for (int e = tid; e < SPC * p.n_layers * 16; e += 256) {
-      const int s = e / (p.n_layers * 16), r = e % (p.n_layers * 16), i = r >> 4, c4 = (r & 15) * 4;
-      const int slot = (int)(t[s] % p.dil[i]);
-      *reinterpret_cast<float4*>(&s_old[s][i][c4]) =
-          *reinterpret_cast<const float4*>(rings[s] + ((int64_t)p.ring_off[i] + slot) * 64 + c4);
-    }
-    if (tid < SPC * 64) {
-      const int s = tid >> 6, r = tid & 63;
-      float v = p.wc_t[(int64_t)last[s] * 64 + r] + p.wc_t[((int64_t)256 + note[s]) * 64 + r];
+    const int cur = step & 1;
+    // ---- causal layer: a gather of two embedding rows (fast_generate.py:111-116)
+    for (int e = tid; e < G * 64; e += 256) {
+      const int s = e >> 6, r = e & 63;
+      float v = p.wc_t[(int64_t)S.last[s] * 64 + r] + p.wc_t[((int64_t)256 + S.note[s]) * 64 + r];
       if (p.has_bias) v += p.bias_c[r];
-      s_x[s][r] = v;
+      S.x[s][r] = v;
+      S.xh[s][r] = __float2half_rn(v);
     }
+    float sk[3][4];
 #pragma unroll
-    for (int s = 0; s < SPC; ++s) last[s] = note[s];
-    float sk[SPC][8];
+    for (int j = 0; j < 3; ++j)
 #pragma unroll
-    for (int s = 0; s < SPC; ++s)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sk[s][j] = 0.f;
+      for (int r = 0; r < 4; ++r) sk[j][r] = 0.f;
+    __pipeline_wait_prior(0);                        // this step's taps
     __syncthreads();
+    if (tid < G) S.last[tid] = S.note[tid];          // next step's tap 0 of the causal layer (read again only after later barriers)
 
-    // one residual block with its weights already in registers (wavenet/fast_generate.py:118-129)
-    auto run_layer = [&](int i, const LayerW& w) {
-      // ---- [f|g] = W0 old + W1 x : thread = (8 outputs, 8 inputs)
-#pragma unroll
-      for (int s = 0; s < SPC; ++s) {
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        const float* in = fg_k0 < 64 ? &s_old[s][i][fg_k0] : &s_x[s][fg_k0 - 64];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) fma8(acc, w.fg[k], in[k]);
-        *reinterpret_cast<float4*>(&s_part[fg_kg][s][fg_n0]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(&s_part[fg_kg][s][fg_n0 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    // one residual block (fast_generate.py:118-129).  While block i runs, the dense + skip fragments of block i+1 and (after its
+    // f|g MMAs) the f|g fragments of block i+2 are requested from L2.
+    auto run_layer = [&](int i, uint4 (&fg)[8], uint4 (&w2)[12], uint4 (&w2_next)[12]) {
+      if (i + 1 < N) load_w2(i + 1, w2_next);
+      // ---- [f|g] = W0 old + W1 x : warp w owns filter and gate channels 8w..8w+7 for all 8 streams
+      const int ch = 8 * warp + n8;
+      float c0[4], c1[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        const float bf = p.has_bias ? p.bias_fg[i * 128 + ch] : 0.f, bg = p.has_bias ? p.bias_fg[i * 128 + 64 + ch] : 0.f;
+        c0[0] = c0[1] = bf;
+        c0[2] = c0[3] = bg;
       }
-      __syncthreads();
-      if (tid < SPC * 64) {        // reduce the 16 partial sums, gate
-        const int s = tid >> 6, c = tid & 63;
-        float f = p.has_bias ? p.bias_fg[i * 128 + c] : 0.f, g = p.has_bias ? p.bias_fg[i * 128 + 64 + c] : 0.f;
+      const float* orow = old + ((size_t)i * G + n8) * XS + 2 * q;
+      const __half* xrow = &S.xh[n8][2 * q];
+      uint32_t bo[4][2], bx[4][2];
 #pragma unroll
-        for (int kg = 0; kg < 16; ++kg) {
-          f += s_part[kg][s][c];
-          g += s_part[kg][s][64 + c];
+      for (int kt = 0; kt < 4; ++kt) {
+        const float2 v0 = *reinterpret_cast<const float2*>(orow + kt * 16), v1 = *reinterpret_cast<const float2*>(orow + kt * 16 + 8);
+        bo[kt][0] = pack_h2(v0.x, v0.y);
+        bo[kt][1] = pack_h2(v1.x, v1.y);
+        bx[kt][0] = *reinterpret_cast<const uint32_t*>(xrow + kt * 16);
+        bx[kt][1] = *reinterpret_cast<const uint32_t*>(xrow + kt * 16 + 8);
+      }
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        mma_f16(c0, fg[kt], bo[kt][0], bo[kt][1]);
+        mma_f16(c1, fg[4 + kt], bx[kt][0], bx[kt][1]);
+      }
+      if (i + 2 < N) load_fg(i + 2, fg);
+      S.zh[2 * q][ch] = __float2half_rn(gate_z(c0[0] + c1[0], c0[2] + c1[2]));
+      S.zh[2 * q + 1][ch] = __float2half_rn(gate_z(c0[1] + c1[1], c0[3] + c1[3]));
+      __syncthreads();
+      // ---- dense (64 -> 64) + residual on warps 0-3 first (it is the critical path), skip (64 -> 256) accumulates in registers
+      uint32_t bz[4][2];
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        const __half* zr = &S.zh[n8][kt * 16 + 2 * q];
+        bz[kt][0] = *reinterpret_cast<const uint32_t*>(zr);
+        bz[kt][1] = *reinterpret_cast<const uint32_t*>(zr + 8);
+      }
+      if (warp < 4) {
+        const int chd = 16 * warp + n8;
+        const int s0 = 2 * q, s1 = 2 * q + 1;
+        float dn[4];
+        dn[0] = S.x[s0][chd]; dn[1] = S.x[s1][chd]; dn[2] = S.x[s0][chd + 8]; dn[3] = S.x[s1][chd + 8];     // residual
+        const float xin[4] = {dn[0], dn[1], dn[2], dn[3]};
+        if (p.has_bias) {
+          const float b0 = p.bias_d[i * 64 + chd], b1 = p.bias_d[i * 64 + chd + 8];
+          dn[0] += b0; dn[1] += b0; dn[2] += b1; dn[3] += b1;
         }
-        s_z[s][c] = (1.f / (1.f + __expf(-g))) * tanhf(f);
-      }
-      __syncthreads();
-      // ---- dense (64 -> 64) partials and skip (64 -> 256) accumulation in registers
+        const int o0 = (p.ring_off[i] + S.slot[cur][i][s0]) * 64 + chd, o1 = (p.ring_off[i] + S.slot[cur][i][s1]) * 64 + chd;
 #pragma unroll
-      for (int s = 0; s < SPC; ++s) {
-        float acc[8];
+        for (int kt = 0; kt < 4; ++kt) mma_f16(dn, w2[kt], bz[kt][0], bz[kt][1]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        fma8(acc, w.d[0], s_z[s][d_k0]);
-        fma8(acc, w.d[1], s_z[s][d_k0 + 1]);
-        float* dst = part32 + ((int64_t)d_kg * SPC + s) * 64 + d_n0;
-        *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-      }
+        for (int kt = 0; kt < 4; ++kt) mma_f16(sk[0], w2[4 + kt], bz[kt][0], bz[kt][1]);
+        S.x[s0][chd] = dn[0]; S.x[s1][chd] = dn[1]; S.x[s0][chd + 8] = dn[2]; S.x[s1][chd + 8] = dn[3];
+        S.xh[s0][chd] = __float2half_rn(dn[0]); S.xh[s1][chd] = __float2half_rn(dn[1]);
+        S.xh[s0][chd + 8] = __float2half_rn(dn[2]); S.xh[s1][chd + 8] = __float2half_rn(dn[3]);
+        const bool out_push = p.push == WN_PUSH_OUTPUT;                                     // fast_generate.py:128-129
+        if (s0 < n_act) { ring0[o0] = out_push ? dn[0] : xin[0]; ring0[o0 + 8] = out_push ? dn[2] : xin[2]; }
+        if (s1 < n_act) { ring1[o1] = out_push ? dn[1] : xin[1]; ring1[o1 + 8] = out_push ? dn[3] : xin[3]; }
+      } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int s = 0; s < SPC; ++s) fma8(sk[s], w.s[k], s_z[s][s_k0 + k]);
-      __syncthreads();
-      if (tid < SPC * 64) {        // dense reduce + residual, queue push, next block input
-        const int s = tid >> 6, r = tid & 63;
-        float y = p.has_bias ? p.bias_d[i * 64 + r] : 0.f;
-#pragma unroll
-        for (int kg = 0; kg < 32; ++kg) y += part32[((int64_t)kg * SPC + s) * 64 + r];
-        const float xin = s_x[s][r];
-        y += xin;
-        if (s < n_act) {
-          const int slot = (int)(t[s] % p.dil[i]);
-          rings[s][((int64_t)p.ring_off[i] + slot) * 64 + r] = (p.push == WN_PUSH_OUTPUT) ? y : xin;   // fast_generate.py:128-129
+        for (int kt = 0; kt < 4; ++kt) {
+          mma_f16(sk[0], w2[kt], bz[kt][0], bz[kt][1]);
+          mma_f16(sk[1], w2[4 + kt], bz[kt][0], bz[kt][1]);
+          mma_f16(sk[2], w2[8 + kt], bz[kt][0], bz[kt][1]);
         }
-        s_x[s][r] = y;
       }
       __syncthreads();
     };
-    // weights of block i+1 are requested from L2 before block i is computed (ping-pong register sets)
-    for (int i = 0; i < p.n_layers; i += 2) {
-      if (i + 1 < p.n_layers) load_layer(i + 1, wb);
-      run_layer(i, wa);
-      if (i + 1 < p.n_layers) {
-        if (i + 2 < p.n_layers) load_layer(i + 2, wa);
-        run_layer(i + 1, wb);
-      }
+    for (int i = 0; i < N; i += 2) {
+      run_layer(i, fgA, w2A, w2B);
+      if (i + 1 < N) run_layer(i + 1, fgB, w2B, w2A);
     }
-    // ---- head weights (two 256 x 256 GEMVs, 8 groups of 32 inputs) are requested a phase ahead as well
-    const int h_n0 = (tid & 31) * 8, h_k0 = (tid >> 5) * 32;
-    uint4 hwa[16], hwb[16];
-    auto load_head = [&](const __nv_bfloat16* Wm, int half, uint4 (&w)[16]) {
+    // the taps of the next step (slot (t+1) mod d; for d = 1 that is the vector pushed just now, visible after the barrier)
+    if (step + 1 < p.n_steps) prefetch_taps(cur, 1);
+
+    // ---- head: relu(sum skips) -> P1 -> relu -> P2 ; warp w owns rows 32w..32w+31 of P1 / P2 outputs
+    uint4 ha[8], hb[8];
+    auto head_load = [&](int which, int part, uint4 (&dst)[8]) {               // both m-tiles, k-tiles [4 part, 4 part + 4)
 #pragma unroll
-      for (int k = 0; k < 16; ++k) w[k] = *reinterpret_cast<const uint4*>(Wm + (int64_t)(h_k0 + half * 16 + k) * 256 + h_n0);
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[j * 4 + k] = headA[(int64_t)which * FRAG_HEAD + ((2 * warp + j) * 16 + part * 4 + k) * 32];
     };
-    load_head(p.p1T, 0, hwa);
-    // ---- skip sum: reduce the 8 input groups, bias, relu
+    head_load(0, 0, ha);
+    head_load(0, 1, hb);
+    {   // skip sums -> relu -> fp16, rows of the skip m-tiles this warp accumulated
+      const int nt = warp < 4 ? 1 : 3, mt0 = warp < 4 ? warp : 4 + 3 * (warp - 4);
 #pragma unroll
-    for (int s = 0; s < SPC; ++s) {
-      float* dst = part8 + ((int64_t)(tid >> 5) * SPC + s) * 256 + (tid & 31) * 8;
-      *reinterpret_cast<float4*>(dst) = make_float4(sk[s][0], sk[s][1], sk[s][2], sk[s][3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(sk[s][4], sk[s][5], sk[s][6], sk[s][7]);
+      for (int j = 0; j < 3; ++j)
+        if (j < nt) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int row = 16 * (mt0 + j) + n8 + 8 * (r >> 1), s = 2 * q + (r & 1);
+            S.hh[0][s][row] = __float2half_rn(fmaxf(sk[j][r] + (p.has_bias ? p.bias_skip[row] : 0.f), 0.f));
+          }
+        }
     }
     __syncthreads();
-    for (int e = tid; e < SPC * 256; e += 256) {
-      const int s = e >> 8, c = e & 255;
-      float v = p.has_bias ? p.bias_skip[c] : 0.f;
-#pragma unroll
-      for (int kg = 0; kg < 8; ++kg) v += part8[((int64_t)kg * SPC + s) * 256 + c];
-      s_h[s][c] = fmaxf(v, 0.f);
-    }
-    __syncthreads();
-    // ---- head: two 256 x 256 GEMVs (8 groups of 32 inputs)
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      const int n0 = h_n0, k0 = h_k0;
-      float acc[SPC][8];
+      float c[2][2][4];               // [m-tile][k parity][fragment]
 #pragma unroll
-      for (int s = 0; s < SPC; ++s)
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[s][j] = 0.f;
-      load_head(which == 0 ? p.p1T : p.p2T, 1, hwb);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-#pragma unroll
-        for (int s = 0; s < SPC; ++s) fma8(acc[s], hwa[k], s_h[s][k0 + k]);
-      }
-      if (which == 0) load_head(p.p2T, 0, hwa);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-#pragma unroll
-        for (int s = 0; s < SPC; ++s) fma8(acc[s], hwb[k], s_h[s][k0 + 16 + k]);
-      }
-#pragma unroll
-      for (int s = 0; s < SPC; ++s) {
-        float* dst = part8 + ((int64_t)(tid >> 5) * SPC + s) * 256 + n0;
-        *reinterpret_cast<float4*>(dst) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]);
-      }
-      if (which == 1 && step + 1 < p.n_steps) load_layer(0, wa);
-      __syncthreads();
-      for (int e = tid; e < SPC * 256; e += 256) {
-        const int s = e >> 8, c = e & 255;
-        const float* bias = which == 0 ? p.bias_p1 : p.bias_p2;
-        float v = p.has_bias ? bias[c] : 0.f;
-#pragma unroll
-        for (int kg = 0; kg < 8; ++kg) v += part8[((int64_t)kg * SPC + s) * 256 + c];
-        if (which == 0) s_h[s][c] = fmaxf(v, 0.f);
-        else {
-          s_lg[s][c] = v;
-          if (logits_out && s < n_act) logits_out[((int64_t)step * p.n_streams + st0 + s) * 256 + c] = v;
+        for (int r = 0; r < 4; ++r) {
+          const int row = 16 * (2 * warp + j) + n8 + 8 * (r >> 1);
+          const float* bias = which == 0 ? p.bias_p1 : p.bias_p2;
+          c[j][0][r] = p.has_bias ? bias[row] : 0.f;
+          c[j][1][r] = 0.f;
         }
+      const __half* hr = &S.hh[which][n8][2 * q];
+#pragma unroll
+      for (int part = 0; part < 4; ++part) {
+        uint4 (&cur_w)[8] = (part & 1) ? hb : ha;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int kt = part * 4 + k;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(hr + kt * 16), b1 = *reinterpret_cast<const uint32_t*>(hr + kt * 16 + 8);
+          mma_f16(c[0][k & 1], cur_w[k], b0, b1);
+          mma_f16(c[1][k & 1], cur_w[4 + k], b0, b1);
+        }
+        // refill the set just consumed: two parts ahead, rolling over into the second matrix
+        if (part + 2 < 4) head_load(which, part + 2, cur_w);
+        else if (which == 0) head_load(1, part - 2, cur_w);
       }
+      if (which == 1 && step + 1 < p.n_steps) {          // the first blocks of the next step
+        load_fg(0, fgA);
+        load_w2(0, w2A);
+        if (N > 1) load_fg(1, fgB);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = 16 * (2 * warp + j) + n8 + 8 * (r >> 1), s = 2 * q + (r & 1);
+          const float v = c[j][0][r] + c[j][1][r];
+          if (which == 0) {
+            S.hh[1][s][row] = __float2half_rn(fmaxf(v, 0.f));
+          } else {
+            S.lg[s][row] = v;
+            if (logits_out && s < n_act) logits_out[((int64_t)step * p.n_streams + st0 + s) * 256 + row] = v;
+          }
+        }
       __syncthreads();
     }
     // ---- pick: greedy topk(1) over the softmax (fast_generate.py:138-140) or inverse CDF (extension); one warp per stream
-    if (warp < SPC) {
+    {
       const int s = warp;
+      const float* lg = S.lg[s];
       float v[8];
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        v[j] = s_lg[s][lane * 8 + j];
+        v[j] = lg[lane * 8 + j];
         mx = fmaxf(mx, v[j]);
       }
 #pragma unroll
@@ -280,38 +398,58 @@ gen_steps_bf16_kernel(FastGenParams p, char* __restrict__ state, const int64_t* 
         pick = 255;
         if (lane == 0) {
           float sum = 0.f;
-          for (int k = 0; k < 256; ++k) sum += expf(s_lg[s][k] - mx);
+          for (int k = 0; k < 256; ++k) sum += expf(lg[k] - mx);
           const float inv = 1.f / sum;
-          float total = 0.f;
-          for (int k = 0; k < 256; ++k) total += expf(s_lg[s][k] - mx) * inv;
-          const float thr = uniforms[(int64_t)step * p.n_streams + min(st0 + s, p.n_streams - 1)] * total;
-          float c = 0.f;
+          float total_p = 0.f;
+          for (int k = 0; k < 256; ++k) total_p += expf(lg[k] - mx) * inv;
+          const float thr = uniforms[(int64_t)step * p.n_streams + min(st0 + s, p.n_streams - 1)] * total_p;
+          float cdf = 0.f;
           for (int k = 0; k < 256; ++k) {
-            c += expf(s_lg[s][k] - mx) * inv;
-            if (c > thr) { pick = k; break; }
+            cdf += expf(lg[k] - mx) * inv;
+            if (cdf > thr) { pick = k; break; }
           }
         }
         pick = __shfl_sync(0xffffffffu, pick, 0);
       }
       if (lane == 0) {
-        s_note[s] = pick;
+        S.note[s] = pick;
         if (s < n_act) out[(int64_t)step * p.n_streams + st0 + s] = pick;
       }
     }
     __syncthreads();
-#pragma unroll
-    for (int s = 0; s < SPC; ++s) {
-      note[s] = s_note[s];
-      t[s] += 1;
-    }
   }
+  __pipeline_wait_prior(0);
   if (tid < n_act) {
-    reinterpret_cast<int64_t*>(sp[tid])[0] = t[tid];
-    reinterpret_cast<int64_t*>(sp[tid])[1] = last[tid];
+    reinterpret_cast<int64_t*>(stream_ptr(tid))[0] += p.n_steps;
+    reinterpret_cast<int64_t*>(stream_ptr(tid))[1] = S.last[tid];
   }
 }
 
+size_t gen_smem_bytes(int n_layers) {
+  return ((sizeof(GenSmem) + 15) & ~size_t(15)) + (size_t)n_layers * G * XS * sizeof(float);
+}
+
 }  // namespace
+
+size_t fast_gen_frag_bytes(const Model& m) { return ((size_t)m.n_layers * FRAG_LAYER + 2 * FRAG_HEAD) * sizeof(uint4); }
+
+// Builds the fp16 A-fragment image behind the regular packed image (called at the end of the weight pack, same stream).
+int fast_gen_pack(const Model& m, const float* d_params, uint8_t* P, cudaStream_t s) {
+  if (m.n_layers > GEN_MAXL) return WN_OK;      // generation refuses such models (fast_gen_steps)
+  const PackLayout pl = pack_layout(m);
+  FragPackArgs a{};
+  a.n_layers = m.n_layers;
+  for (int i = 0; i < m.n_layers; ++i) {
+    a.filt[i] = m.layers[i].filt.w; a.gate[i] = m.layers[i].gate.w;
+    a.dense[i] = m.layers[i].dense.w; a.skip[i] = m.layers[i].skip.w;
+  }
+  a.post1 = m.post1.w; a.post2 = m.post2.w;
+  a.params = d_params;
+  a.frag = reinterpret_cast<uint4*>(P + pl.gen_frag);
+  gen_frag_pack_kernel<<<148, 256, 0, s>>>(a);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
 
 int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t* d_first_note, const void* d_packed, void* d_state,
                    const float* d_uniforms, int64_t* d_out, float* d_logits, cudaStream_t s) {
@@ -335,15 +473,16 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
   p.bias_skip = reinterpret_cast<const float*>(P + pl.bias_skip);
   p.bias_p1 = reinterpret_cast<const float*>(P + pl.bias_p1);
   p.bias_p2 = reinterpret_cast<const float*>(P + pl.bias_p2);
-  p.wfgT0 = reinterpret_cast<const __nv_bfloat16*>(P + pl.wfgT0);
-  p.wfgT1 = reinterpret_cast<const __nv_bfloat16*>(P + pl.wfgT1);
-  p.wdT = reinterpret_cast<const __nv_bfloat16*>(P + pl.wdT);
-  p.wsT = reinterpret_cast<const __nv_bfloat16*>(P + pl.wsT);
-  p.p1T = reinterpret_cast<const __nv_bfloat16*>(P + pl.p1T);
-  p.p2T = reinterpret_cast<const __nv_bfloat16*>(P + pl.p2T);
+  p.frag = reinterpret_cast<const uint4*>(P + pl.gen_frag);
+  const size_t smem = gen_smem_bytes(m.n_layers);
+  static bool once = false;
+  if (!once) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(gen_steps_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem_bytes(GEN_MAXL)));
+    once = true;
+  }
   WN_PROF("gen_steps_bf16", s);
-  gen_steps_bf16_kernel<<<(unsigned)ceil_div(n_streams, SPC), 256, 0, s>>>(p, reinterpret_cast<char*>(d_state), d_first_note,
-                                                                          d_uniforms, d_out, d_logits);
+  gen_steps_bf16_kernel<<<(unsigned)ceil_div(n_streams, G), 256, smem, s>>>(p, reinterpret_cast<char*>(d_state), d_first_note,
+                                                                           d_uniforms, d_out, d_logits);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }

@@ -102,6 +102,7 @@ PackLayout pack_layout(const Model& m) {
   p.wsT = take((size_t)N * 64 * 256 * 2);       // [64 d][256 s]
   p.p1T = take(256 * 256 * 2);
   p.p2T = take(256 * 256 * 2);
+  p.gen_frag = take(fast_gen_frag_bytes(m));
   p.total = off;
   return p;
 }
@@ -242,6 +243,7 @@ int fast_pack(Model& m, const float* d_params, void* d_packed, cudaStream_t s) {
                                            m.n_layers, reinterpret_cast<float*>(P + pl.bias_skip));
     WN_CHECK_LAUNCH();
   }
+  WN_PROPAGATE(fast_gen_pack(m, d_params, P, s));
   return WN_OK;
 }
 

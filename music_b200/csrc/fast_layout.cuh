@@ -20,6 +20,7 @@ struct PackLayout {     // byte offsets
   size_t jobs, wc_t, bias_c, bias_fg, bias_d, bias_skip, bias_p1, bias_p2;
   size_t wfg0, wfg1, wd, wscat, p1, p2;          // K-major [out][in] bf16 (forward B operands)
   size_t wfgT0, wfgT1, wdT, wsT, p1T, p2T;       // [in][out] bf16 (data-gradient B operands)
+  size_t gen_frag;                               // mma.sync A-fragment image of all weights (generation kernel, fast_gen.cu)
   size_t total;
 };
 PackLayout pack_layout(const Model& m);
