@@ -223,6 +223,163 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
+// ============================================================================================ gemm_nt, resident B
+// OUT[rows, 256 nt .. 256 nt + 256) = epi(A[rows, 0..256) W^T) with K = 256: the 128 KB weight block of the CTA's column
+// tile stays in shared memory for the whole launch and only the A row tiles stream through (64 KB per 16.8 MFLOP item).
+// The streaming version above re-reads the weight block per item (192 KB per item, 28 MB per wave of 148 CTAs) and is
+// bound by L2 -> SM bandwidth at a quarter of the tensor rate.  CTA c owns column tile c mod n_ntiles and every
+// (number of CTAs with that tile)-th row tile.  Output goes through a ring of three 64-column staging tiles whose TMA
+// stores are only checked two tiles later.
+struct NtResCfg {
+  static constexpr int A_STAGES = 3, OUT_SLOTS = 3;
+  static constexpr uint32_t B_OFF = 0, B_BYTES = 4 * 256 * 128;            // 4 k-chunks of [256 n][64 k]
+  static constexpr uint32_t A_OFF = B_BYTES, OUT_OFF = A_OFF + A_STAGES * TILE, TOTAL = OUT_OFF + OUT_SLOTS * TILE;
+};
+
+__global__ void __launch_bounds__(192, 1)
+gemm_nt_resb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmOut, GemmNtParams p) {
+  using Cfg = NtResCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t b_full, full[Cfg::A_STAGES], empty[Cfg::A_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&b_full, 1);
+    for (int i = 0; i < Cfg::A_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t sbase = smem_u32(sm);
+  const int T = p.n_ntiles;
+  const int nt = (int)blockIdx.x % T, rank = (int)blockIdx.x / T;
+  const int peers = ((int)gridDim.x - 1 - nt) / T + 1;                    // CTAs that own column tile nt
+  const int n_rows = p.n_batches * p.tiles_per_batch;
+  const int n_mine = rank < n_rows ? (n_rows - 1 - rank) / peers + 1 : 0;
+  const int n_valid = min(256, p.n_total - nt * 256);                      // multiple of 64
+  const int n_otiles = n_valid / 64;
+
+  if (warp == 4) {
+    if (lane == 0 && n_mine > 0) {
+      mbar_expect_tx(&b_full, Cfg::B_BYTES);
+      for (int k = 0; k < 4; ++k) tma_load_2d(sm + Cfg::B_OFF + k * 256 * 128, &tmB, &b_full, p.b_col0[0] + 64 * k, nt * 256);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_mine; ++it) {
+        const int rt = rank + it * peers;
+        const int b = rt / p.tiles_per_batch, row0 = (p.tile0 + rt % p.tiles_per_batch) * 128;
+        for (int k = 0; k < 4; ++k) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], TILE);
+          tma_load_3d(sm + Cfg::A_OFF + stage * TILE, &tmA, &full[stage], p.a_col0[0] + 64 * k, row0 + p.a_row_off[0], b);
+          if (++stage == Cfg::A_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && n_mine > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idn = idesc_bf16(128, n_valid, 0, 0);
+      mbar_wait(&b_full, 0);
+      for (int it = 0; it < n_mine; ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t dst = tmem + as * 256;
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = sbase + Cfg::A_OFF + stage * TILE, sb = sbase + Cfg::B_OFF + kc * 256 * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(dst, desc_kmajor(sa, k), desc_kmajor(sb, k), idn, (kc | k) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::A_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    int slot = 0;
+    for (int it = 0; it < n_mine; ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const int rt = rank + it * peers;
+      const int b = rt / p.tiles_per_batch, row0 = (p.tile0 + rt % p.tiles_per_batch) * 128;
+      const int row = row0 + tid;
+      const bool valid = row >= p.row_lo && row < p.row_hi;
+      const uint32_t src = tmem_addr(tmem, warp * 32, as * 256);
+      const __nv_bfloat16* auxp =
+          p.aux ? p.aux + (int64_t)b * p.aux_bstride + (int64_t)row * p.aux_rstride + p.aux_col0 + nt * 256 : nullptr;
+      for (int j = 0; j < n_otiles; ++j) {
+        uint4 ax4[8];
+        if (p.epi != EPI_PLAIN && valid) {         // the 128-byte aux row of this tile, requested before the accumulator is read
+#pragma unroll
+          for (int q = 0; q < 8; ++q) ax4[q] = *reinterpret_cast<const uint4*>(auxp + j * 64 + q * 8);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) ax4[q] = make_uint4(0, 0, 0, 0);
+        }
+        if (j == 0) {
+          mbar_wait(&acc_full[as], aph);
+          tc_fence_after();
+        }
+        uint32_t packed[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(src + j * 64 + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float a0 = __uint_as_float(v[2 * e]), a1 = __uint_as_float(v[2 * e + 1]);
+            const uint32_t axw = reinterpret_cast<const uint32_t*>(&ax4[c * 4 + (e >> 2)])[e & 3];
+            const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&axw);
+            if (p.epi == EPI_MASK) {
+              a0 = __low2float(x2) > 0.f ? a0 : 0.f;
+              a1 = __high2float(x2) > 0.f ? a1 : 0.f;
+            } else if (p.epi == EPI_ADD) {
+              a0 += __low2float(x2);
+              a1 += __high2float(x2);
+            }
+            packed[c * 16 + e] = valid ? pack_bf16(a0, a1) : 0u;
+          }
+        }
+        // staging slot `slot` was stored three tiles ago; thread 0 checked that store before the previous barrier
+        uint8_t* ot = sm + Cfg::OUT_OFF + slot * TILE;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(ot + sw128_chunk(tid, q)) = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        fence_proxy_async_smem();
+        if (j == n_otiles - 1) tc_fence_before();
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // all but the newest store have left smem
+        epi_bar_sync();
+        if (tid == 0) {
+          if (j == n_otiles - 1) mbar_arrive(&acc_empty[as]);
+          tma_store_3d(&tmOut, ot, p.out_col0 + nt * 256 + 64 * j, row0, b);
+          tma_store_commit();
+        }
+        if (++slot == Cfg::OUT_SLOTS) slot = 0;
+      }
+    }
+    if (tid == 0) tma_store_wait_read();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 // ============================================================================================ gemm_tn
 template <int NB>
 struct TnCfg {
@@ -846,7 +1003,14 @@ int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStrea
   if (n_items <= 0) return WN_OK;
   const int grid = std::min(n_items, g_sm_count * (NT == 64 ? NtCfg<64>::CTAS_PER_SM : 1));
   WN_PROF(p.tag ? p.tag : "gemm_nt", s);
-  if (NT == 256) {
+  if (NT == 256 && p.nk[0] == 4 && p.nk[1] == 0 && p.n_total > 0 && p.n_total % 64 == 0 && !getenv("WN_NT_STREAM")) {
+    // K = 256: weight block resident in shared memory, one column tile per CTA
+    static bool once = false;
+    const int smem = NtResCfg::TOTAL + 1024;
+    if (!once) { WN_PROPAGATE(set_smem(gemm_nt_resb_kernel, smem)); once = true; }
+    const int g2 = std::min(g_sm_count, p.n_batches * p.tiles_per_batch * p.n_ntiles);
+    gemm_nt_resb_kernel<<<g2, 192, smem, s>>>(m.a[0], m.b[0], m.out, p);
+  } else if (NT == 256) {
     static bool once = false;
     const int smem = NtCfg<256>::TOTAL + 1024;
     if (!once) { WN_PROPAGATE(set_smem(gemm_nt_kernel<256>, smem)); once = true; }
@@ -982,7 +1146,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     GemmNtMaps gm{};
     gm.a[0] = M.dlg; gm.a[1] = M.dlg; gm.b[0] = M.p2T; gm.b[1] = M.p2T; gm.out = M.dh1;
     GemmNtParams gp{};
-    gp.n_batches = B; gp.tile0 = 0; gp.tiles_per_batch = skip_tiles; gp.n_ntiles = 1;
+    gp.n_batches = B; gp.tile0 = 0; gp.tiles_per_batch = skip_tiles; gp.n_ntiles = 1; gp.n_total = 256;
     gp.nk[0] = 4; gp.nk[1] = 0;
     gp.epi = EPI_MASK; gp.aux = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.H1);
     gp.aux_bstride = (int64_t)Wpad * 256; gp.aux_rstride = 256; gp.aux_col0 = 0;
@@ -1023,7 +1187,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     GemmNtMaps gm{};
     gm.a[0] = M.dsk; gm.a[1] = M.dsk; gm.b[0] = M.wsTcat; gm.b[1] = M.wsTcat; gm.out = M.dzcat;
     GemmNtParams gp{};
-    gp.n_batches = B; gp.tile0 = 0; gp.tiles_per_batch = skip_tiles; gp.n_ntiles = (int)ceil_div(64 * N, 256);
+    gp.n_batches = B; gp.tile0 = 0; gp.tiles_per_batch = skip_tiles; gp.n_ntiles = (int)ceil_div(64 * N, 256); gp.n_total = 64 * N;
     gp.nk[0] = 4; gp.nk[1] = 0; gp.epi = EPI_PLAIN; gp.row_lo = 0; gp.row_hi = Wpad; gp.tag = "gemm_nt_dZcat";
     WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
     WN_DEBUG_SYNC("gemm_nt dZcat", s);

@@ -20,6 +20,7 @@ struct GemmNtMaps {
 };
 struct GemmNtParams {
   int n_batches, tile0, tiles_per_batch, n_ntiles;
+  int n_total;                  // output columns in total (0: every column tile is full) - resident-B kernel only
   int nk[2], a_row_off[2], a_col0[2], b_col0[2];
   int out_col0;
   int epi;
