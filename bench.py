@@ -214,6 +214,48 @@ def bench_generation(net, n_streams, n_steps, dev):
                                  "(~64 B/clk) and the 31-stage dependency chain; many_streams shows the same kernel on 128 SMs"}}
 
 
+def bench_autoencoder(dev, steps=3):
+    """BASELINE.json configs[4] shape on ONE GPU: wavenet_autoencoder with the shipped parameters (40 layers, 32 channels,
+    512 bottleneck / skip, pool 512), one clip of W = 64000 targets (L = 68093), Adam.  The autoencoder runs in the fp32
+    check mode (SIMT kernels, csrc/ae.cu): this is a correctness-path timing, not a tensor-core number."""
+    import torch
+    from music_b200.wavenet_autoencoder.model1 import wavenet_autoencoder
+    from music_b200.wavenet_autoencoder import train as T
+    dil = [2 ** i for i in range(10)] * 4
+    torch.manual_seed(0)
+    net = wavenet_autoencoder(2, 256, dil, 32, 32, 512, 512, 32, 32, 512, False).to(dev)
+    W = 64000
+    L = net.receptive_field + W - 1
+    g = torch.Generator().manual_seed(1234)
+    idx = torch.randint(0, 256, (1, L), generator=g).to(dev)
+    target = idx[:, net.receptive_field - 1:].contiguous()
+    opt = T.get_optimizer(net, 'Adam', 1e-4)
+
+    def step():
+        opt.zero_grad()
+        logits = net.forward_logits(indices=idx)
+        from music_b200._engine import SoftmaxRowsFunction
+        from music_b200 import _lib as L_
+        probs = SoftmaxRowsFunction.apply(logits, L_.ROWS_REFERENCE)
+        loss = torch.nn.functional.cross_entropy(probs, target.reshape(-1))
+        loss.backward()
+        opt.step()
+        return loss
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": "wavenet_autoencoder 40 layers (1..512 x4), 32 ch, bottleneck/skip 512, pool 512; 1 clip x 64000 targets "
+                        "(L=68093), index input, Adam (torch.optim), fp32 check mode",
+            "samples_per_s": W / (ms * 1e-3), "ms_per_step": ms, "dtype": "f32", "loss": float(loss),
+            "train_flops_per_sample": 8.656e6, "tflops": W * 8.656e6 / (ms * 1e-3) / 1e12}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -243,6 +285,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--gen-steps", type=int, default=2000, help="incremental-generation steps timed per stream (0 = skip)")
     ap.add_argument("--gen-streams", type=int, default=64)
+    ap.add_argument("--no-ae", action="store_true", help="skip the autoencoder (configs[4] shape, fp32 check mode) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -381,6 +424,12 @@ def main():
     gen = None
     if rank == 0 and world == 1 and args.gen_steps > 0:
         gen = bench_generation(net, args.gen_streams, args.gen_steps, dev)
+    ae = None
+    if rank == 0 and world == 1 and not args.no_ae:
+        try:
+            ae = bench_autoencoder(dev)
+        except Exception as exc:        # reported, never fatal for the headline line
+            ae = {"error": repr(exc)}
 
     if rank == 0:
         out = {"metric": "training audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
@@ -395,7 +444,7 @@ def main():
                        "ms_per_step": ms_e2e / K},
                "gpu_launches": int(launches), "loss": last_loss, "clocks": clocks, "roofline": roofline,
                "cpu_baseline": cpu, "train_flops_per_sample": 3 * flops_per_sample(), "generation": gen,
-               "kernels": breakdown}
+               "autoencoder": ae, "kernels": breakdown}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
