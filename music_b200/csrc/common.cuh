@@ -92,6 +92,17 @@ struct Pack32 {
 std::vector<const ConvP*> all_convs(const Model& m);
 Pack32 pack32_of(const Model& m, const ConvP* target, int64_t* total = nullptr);
 
+// L2 eviction-priority hints on the TMA transfers of the bf16 path (WN_L2HINT=0 disables them; timing experiments)
+inline bool l2_hints_on() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("WN_L2HINT");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+constexpr unsigned long long kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
+
 extern int g_device;
 extern int g_sm_count;
 extern bool g_inited;

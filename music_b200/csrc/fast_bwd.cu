@@ -33,7 +33,7 @@ struct NtCfg {
   static constexpr int CTAS_PER_SM = NT == 256 ? 1 : 3;      // NT=64: 65 KB smem, 128 TMEM columns per CTA
 };
 
-template <int NT>
+template <int NT, int EPI>      // EPI is a compile-time constant: a run-time p.epi made the epilogue branch per element
 __global__ void __launch_bounds__(192, NtCfg<NT>::CTAS_PER_SM)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -75,7 +75,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = sm + stage * Cfg::STAGE;
             mbar_expect_tx(&full[stage], Cfg::STAGE);
-            tma_load_3d(sa, seg == 0 ? &tmA0 : &tmA1, &full[stage], p.a_col0[seg] + 64 * k, row0 + p.a_row_off[seg], b);
+            tma_load_3d(sa, seg == 0 ? &tmA0 : &tmA1, &full[stage], p.a_col0[seg] + 64 * k, row0 + p.a_row_off[seg], b, p.pol_a[seg]);
             tma_load_2d(sa + Cfg::A_BYTES, seg == 0 ? &tmB0 : &tmB1, &full[stage], p.b_col0[seg] + 64 * k, nt * NT);
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           }
@@ -122,7 +122,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         uint4 ax4[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) ax4[q] = make_uint4(0, 0, 0, 0);
-        if (p.epi != EPI_PLAIN && valid) {
+        if (EPI != EPI_PLAIN && valid) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) ax4[q] = *reinterpret_cast<const uint4*>(auxp + q * 8);
         }
@@ -139,10 +139,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
             const uint32_t axw = reinterpret_cast<const uint32_t*>(&ax4[c * 4 + (j >> 2)])[j & 3];
             const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&axw);
-            if (p.epi == EPI_MASK) {
+            if (EPI == EPI_MASK) {
               a0 = __low2float(x2) > 0.f ? a0 : 0.f;
               a1 = __high2float(x2) > 0.f ? a1 : 0.f;
-            } else if (p.epi == EPI_ADD) {
+            } else if (EPI == EPI_ADD) {
               a0 += __low2float(x2);
               a1 += __high2float(x2);
             }
@@ -160,7 +160,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         fence_proxy_async_smem();
         epi_bar_sync();
         if (tid == 0) {
-          tma_store_3d(&tmOut, ot, p.out_col0 + nt * NT, row0, b);
+          tma_store_3d(&tmOut, ot, p.out_col0 + nt * NT, row0, b, p.pol_out);
           tma_store_commit();
         }
       } else {
@@ -173,7 +173,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tmem_ld_wait();
           uint32_t packed[16];
           uint32_t ax[16];
-          if (p.epi != EPI_PLAIN && valid) {
+          if (EPI != EPI_PLAIN && valid) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint4 a4 = *reinterpret_cast<const uint4*>(auxp + c * 32 + q * 8);
@@ -187,10 +187,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int j = 0; j < 16; ++j) {
             float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
             const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&ax[j]);
-            if (p.epi == EPI_MASK) {
+            if (EPI == EPI_MASK) {
               a0 = __low2float(x2) > 0.f ? a0 : 0.f;
               a1 = __high2float(x2) > 0.f ? a1 : 0.f;
-            } else if (p.epi == EPI_ADD) {
+            } else if (EPI == EPI_ADD) {
               a0 += __low2float(x2);
               a1 += __high2float(x2);
             }
@@ -236,6 +236,7 @@ struct NtResCfg {
   static constexpr uint32_t A_OFF = B_BYTES, OUT_OFF = A_OFF + A_STAGES * TILE, TOTAL = OUT_OFF + OUT_SLOTS * TILE;
 };
 
+template <int EPI>
 __global__ void __launch_bounds__(192, 1)
 gemm_nt_resb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, GemmNtParams p) {
@@ -324,7 +325,7 @@ gemm_nt_resb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           p.aux ? p.aux + (int64_t)b * p.aux_bstride + (int64_t)row * p.aux_rstride + p.aux_col0 + nt * 256 : nullptr;
       for (int j = 0; j < n_otiles; ++j) {
         uint4 ax4[8];
-        if (p.epi != EPI_PLAIN && valid) {         // the 128-byte aux row of this tile, requested before the accumulator is read
+        if (EPI != EPI_PLAIN && valid) {         // the 128-byte aux row of this tile, requested before the accumulator is read
 #pragma unroll
           for (int q = 0; q < 8; ++q) ax4[q] = *reinterpret_cast<const uint4*>(auxp + j * 64 + q * 8);
         } else {
@@ -346,10 +347,10 @@ gemm_nt_resb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             float a0 = __uint_as_float(v[2 * e]), a1 = __uint_as_float(v[2 * e + 1]);
             const uint32_t axw = reinterpret_cast<const uint32_t*>(&ax4[c * 4 + (e >> 2)])[e & 3];
             const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&axw);
-            if (p.epi == EPI_MASK) {
+            if (EPI == EPI_MASK) {
               a0 = __low2float(x2) > 0.f ? a0 : 0.f;
               a1 = __high2float(x2) > 0.f ? a1 : 0.f;
-            } else if (p.epi == EPI_ADD) {
+            } else if (EPI == EPI_ADD) {
               a0 += __low2float(x2);
               a1 += __high2float(x2);
             }
@@ -692,14 +693,14 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         mbar_wait(&in_empty[st], ((it >> 1) & 1) ^ 1);
         uint8_t* si = sm + Bwd2Smem::IN + st * Bwd2Smem::IN_STAGE;
         mbar_expect_tx(&in_full[st], (dense ? 3 : 2) * TILE);
-        tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b);
+        tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b, p.pol_first);     // the last read of these rows of x_i
         tma_load_3d(si + TILE, &tm_x, &in_full[st], 0, tau0, b);
         if (dense) tma_load_3d(si + 2 * TILE, &tm_dx, &in_full[st], 0, tau0, b);
         // skip-path gradient tile (every tile gets one so that the buffer parity stays in step; tiles before the
         // last W time steps read rows < 0 of the padded row space -> clamp to an all-zero pad tile instead)
         mbar_wait(&dzs_empty[st], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&dzs_full[st], TILE);
-        if (tau0 >= p.tw_al) tma_load_3d(sm + Bwd2Smem::DZS + st * TILE, &tm_dzs, &dzs_full[st], p.dzs_col, tau0 - p.tw_al, b);
+        if (tau0 >= p.tw_al) tma_load_3d(sm + Bwd2Smem::DZS + st * TILE, &tm_dzs, &dzs_full[st], p.dzs_col, tau0 - p.tw_al, b, p.pol_first);
         else tma_load_3d(sm + Bwd2Smem::DZS + st * TILE, &tm_dzs, &dzs_full[st], p.dzs_col, p.Wp, b);   // fully out of bounds: zeros
       }
     }
@@ -828,8 +829,8 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       epi8_bar_sync();
       if (tid == 0) {
         mbar_arrive(&out_full);
-        tma_store_3d(&tm_dfg, sm + Bwd2Smem::DF, 0, tau0, b);
-        tma_store_3d(&tm_dfg, sm + Bwd2Smem::DG, 64, tau0, b);
+        tma_store_3d(&tm_dfg, sm + Bwd2Smem::DF, 0, tau0, b, p.pol_last);          // read by the dx GEMM that follows
+        tma_store_3d(&tm_dfg, sm + Bwd2Smem::DG, 64, tau0, b, p.pol_last);
         tma_store_commit();                // checked one phase later (above), nobody waits here
       }
     }
@@ -974,6 +975,17 @@ int set_smem(K kernel, int bytes) {
   WN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return WN_OK;
 }
+// same, once per kernel (for call sites that pick one of several instantiations at run time)
+template <typename K>
+int set_smem_once(K kernel, int bytes) {
+  static std::vector<const void*> done;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (const void* d : done)
+    if (d == key) return WN_OK;
+  WN_PROPAGATE(set_smem(kernel, bytes));
+  done.push_back(key);
+  return WN_OK;
+}
 
 int launch_colsum_bf16(const void* src, int C, int B, int64_t rows_per_batch, int row_lo, int row_hi, float* out, cudaStream_t s) {
   if (row_hi <= row_lo) return WN_OK;
@@ -1003,23 +1015,26 @@ int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStrea
   if (n_items <= 0) return WN_OK;
   const int grid = std::min(n_items, g_sm_count * (NT == 64 ? NtCfg<64>::CTAS_PER_SM : 1));
   WN_PROF(p.tag ? p.tag : "gemm_nt", s);
+  auto pick = [&](auto kernel_plain, auto kernel_mask, auto kernel_add) {
+    return p.epi == EPI_PLAIN ? kernel_plain : (p.epi == EPI_MASK ? kernel_mask : kernel_add);
+  };
   if (NT == 256 && p.nk[0] == 4 && p.nk[1] == 0 && p.n_total > 0 && p.n_total % 64 == 0 && !getenv("WN_NT_STREAM")) {
     // K = 256: weight block resident in shared memory, one column tile per CTA
-    static bool once = false;
     const int smem = NtResCfg::TOTAL + 1024;
-    if (!once) { WN_PROPAGATE(set_smem(gemm_nt_resb_kernel, smem)); once = true; }
+    auto k = pick(gemm_nt_resb_kernel<EPI_PLAIN>, gemm_nt_resb_kernel<EPI_MASK>, gemm_nt_resb_kernel<EPI_ADD>);
+    WN_PROPAGATE(set_smem_once(k, smem));
     const int g2 = std::min(g_sm_count, p.n_batches * p.tiles_per_batch * p.n_ntiles);
-    gemm_nt_resb_kernel<<<g2, 192, smem, s>>>(m.a[0], m.b[0], m.out, p);
+    k<<<g2, 192, smem, s>>>(m.a[0], m.b[0], m.out, p);
   } else if (NT == 256) {
-    static bool once = false;
     const int smem = NtCfg<256>::TOTAL + 1024;
-    if (!once) { WN_PROPAGATE(set_smem(gemm_nt_kernel<256>, smem)); once = true; }
-    gemm_nt_kernel<256><<<grid, 192, smem, s>>>(m.a[0], m.a[1], m.b[0], m.b[1], m.out, p);
+    auto k = pick(gemm_nt_kernel<256, EPI_PLAIN>, gemm_nt_kernel<256, EPI_MASK>, gemm_nt_kernel<256, EPI_ADD>);
+    WN_PROPAGATE(set_smem_once(k, smem));
+    k<<<grid, 192, smem, s>>>(m.a[0], m.a[1], m.b[0], m.b[1], m.out, p);
   } else if (NT == 64) {
-    static bool once = false;
     const int smem = NtCfg<64>::TOTAL + 1024;
-    if (!once) { WN_PROPAGATE(set_smem(gemm_nt_kernel<64>, smem)); once = true; }
-    gemm_nt_kernel<64><<<grid, 192, smem, s>>>(m.a[0], m.a[1], m.b[0], m.b[1], m.out, p);
+    auto k = pick(gemm_nt_kernel<64, EPI_PLAIN>, gemm_nt_kernel<64, EPI_MASK>, gemm_nt_kernel<64, EPI_ADD>);
+    WN_PROPAGATE(set_smem_once(k, smem));
+    k<<<grid, 192, smem, s>>>(m.a[0], m.a[1], m.b[0], m.b[1], m.out, p);
   } else {
     set_error("launch_gemm_nt: NT=%d", NT);
     return WN_ERR_INVALID;
@@ -1231,6 +1246,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       bp.tw0 = L - W; bp.tw_al = tw_al; bp.Wp = Wpad;
       bp.dzs = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DZcat); bp.dzs_pitch = 64 * N; bp.dzs_col = 64 * i;
       bp.bias_fg = bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
+      if (l2_hints_on()) { bp.pol_first = kL2EvictFirst; bp.pol_last = kL2EvictLast; }
       if (fused) {
         BlockBwd2Params b2{};
         b2.b = bp; b2.n_batches = B;
@@ -1278,6 +1294,8 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       gp.epi = EPI_ADD; gp.aux = reinterpret_cast<const __nv_bfloat16*>(Wp + dx_next_off);
       gp.aux_bstride = (int64_t)L * 64; gp.aux_rstride = 64; gp.aux_col0 = 0;
       gp.row_lo = s_in; gp.row_hi = L; gp.tag = "gemm_nt_dx";
+      // (L2 hints on this GEMM's dFG loads / dx stores were measured to cost 0.1 ms per step: left off)
+      if (getenv("WN_L2HINT_DX")) { gp.pol_a[0] = kL2EvictFirst; gp.pol_out = kL2EvictLast; }
       WN_PROPAGATE(launch_gemm_nt(64, gm, gp, s));
       WN_DEBUG_SYNC("gemm_nt dx", s);
     }

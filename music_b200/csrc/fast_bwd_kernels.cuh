@@ -28,6 +28,8 @@ struct GemmNtParams {
   int64_t aux_bstride, aux_rstride;
   int aux_col0;
   int row_lo, row_hi;           // rows outside are written as zeros
+  unsigned long long pol_a[2];  // L2 eviction hint of the A loads of each segment (0: none)
+  unsigned long long pol_out;   // ... of the output stores
   const char* tag;              // profiler label (host only)
 };
 int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStream_t s);
@@ -75,6 +77,7 @@ struct BlockBwdParams {
   const __nv_bfloat16* dzs;     // [B*Wp][dzs_pitch], this layer's 64 columns start at dzs_col
   int dzs_pitch, dzs_col;
   const float* bias_fg;
+  unsigned long long pol_first, pol_last;   // L2 eviction hints (0: none)
 };
 int launch_block_bwd(const BlockBwdMaps& m, const BlockBwdParams& p, int n_ctas, cudaStream_t s);
 

@@ -283,13 +283,14 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         mbar_wait(&in_empty[st], ((it / 3) & 1) ^ 1);
         uint8_t* si = sm + Fwd2Smem::IN + st * Fwd2Smem::IN_STAGE;
         mbar_expect_tx(&in_full[st], 2 * TILE_BYTES);
-        tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b);
+        // rows of x_i are read as tap 1 by their own tile and, d rows later, as tap 0: that second read is the last one
+        tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b, p.pol_first);
         tma_load_3d(si + TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);
         if (p.ts && blockIdx.x == 0) p.ts[1024 + it * 4 + 2] = clock64();
         if (dense) {      // low half of the residual stream; its tile is reused for lo' and released after that store
           mbar_wait(&lo_empty[it & 1], ((it >> 1) & 1) ^ 1);
           mbar_expect_tx(&lo_full[it & 1], TILE_BYTES);
-          tma_load_3d(sm + Fwd2Smem::LO + (it & 1) * TILE_BYTES, &tm_lo, &lo_full[it & 1], 0, tau0, b);
+          tma_load_3d(sm + Fwd2Smem::LO + (it & 1) * TILE_BYTES, &tm_lo, &lo_full[it & 1], 0, tau0, b, p.pol_first);
         }
       }
     }
@@ -434,10 +435,11 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (tid == 0) {
         mbar_arrive(&acc_empty[ab]);
         mbar_arrive(&in_empty[st]);
-        if (tau0 >= p.tw_al && !(p.dbg & 1)) tma_store_3d(&tm_z, zt, p.zcol, tau0 - p.tw_al, b);
+        // z is read again only by the skip GEMM at the end of the forward; x_{i+1} hi / lo' by the very next launch
+        if (tau0 >= p.tw_al && !(p.dbg & 1)) tma_store_3d(&tm_z, zt, p.zcol, tau0 - p.tw_al, b, p.pol_first);
         if (dense && !(p.dbg & 2)) {
-          tma_store_3d(&tm_xo, sm + Fwd2Smem::XO, 0, tau0, b);
-          tma_store_3d(&tm_loo, lot, 0, tau0, b);
+          tma_store_3d(&tm_xo, sm + Fwd2Smem::XO, 0, tau0, b, p.pol_last);
+          tma_store_3d(&tm_loo, lot, 0, tau0, b, p.pol_last);
         }
         tma_store_commit();          // not waited for here: checked before the staging tiles are rewritten (above)
       }

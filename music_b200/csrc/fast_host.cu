@@ -422,6 +422,7 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
       dbg_env = e ? atoi(e) : 0;
     }
     p.dbg = dbg_env;
+    if (l2_hints_on()) { p.pol_first = kL2EvictFirst; p.pol_last = kL2EvictLast; }
     p.ts = (getenv("WN_TS") && i == N / 2) ? reinterpret_cast<long long*>(Wp + wl.X0f) : nullptr;   // layer N/2, scratch = X0f
     static int simple_env = -1;
     if (simple_env < 0) {
