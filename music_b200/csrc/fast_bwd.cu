@@ -640,6 +640,7 @@ struct Bwd2Smem {
 };
 __device__ __forceinline__ void epi8_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
+template <bool BIAS, bool DENSE>      // compile-time: run-time tests inside the unrolled epilogue loops cost a branch per element
 __global__ void __launch_bounds__(576, 1)
 block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
                   const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_dx,
@@ -675,7 +676,7 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const uint32_t tmem = tmem_base_s;
   const uint32_t sbase = smem_u32(sm);
   const int n_items = pp.n_batches * p.tiles_per_batch;
-  const bool dense = p.has_dense != 0;
+  constexpr bool dense = DENSE;
   const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   constexpr uint32_t C_DZ = 256, C_WFG = 320, C_WD = 448;
 
@@ -793,7 +794,7 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         float zo[2], df[2], dg[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          if (p.bias_fg) {
+          if (BIAS) {
             fv[e] += p.bias_fg[cg * 16 + 2 * j + e];
             gv[e] += p.bias_fg[64 + cg * 16 + 2 * j + e];
           }
@@ -1087,15 +1088,17 @@ int launch_block_bwd(const BlockBwdMaps& m, const BlockBwdParams& p, int n_ctas,
 }
 
 int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStream_t s) {
-  static bool once = false;
   const int smem = Bwd2Smem::TOTAL + 1024;
-  if (!once) { WN_PROPAGATE(set_smem(block_bwd2_kernel, smem)); once = true; }
   const int n_items = p.n_batches * p.b.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
   const int n_ctas = std::min(n_items, g_sm_count);
+  const bool bias = p.b.bias_fg != nullptr, dense = p.b.has_dense != 0;
+  auto k = bias ? (dense ? block_bwd2_kernel<true, true> : block_bwd2_kernel<true, false>)
+                : (dense ? block_bwd2_kernel<false, true> : block_bwd2_kernel<false, false>);
+  WN_PROPAGATE(set_smem_once(k, smem));
   {
     WN_PROF("block_bwd2", s);
-    block_bwd2_kernel<<<n_ctas, 576, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, m.dzs, p);
+    k<<<n_ctas, 576, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, m.dzs, p);
     WN_CHECK_LAUNCH();
   }
   return WN_OK;

@@ -232,6 +232,8 @@ struct Fwd2Smem {
 };
 __device__ __forceinline__ void epi16_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
+// BIAS and TRACE are compile-time: run-time tests inside the unrolled epilogue loops cost a branch per element
+template <bool BIAS, bool TRACE>
 __global__ void __launch_bounds__(576, 1)
 block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
                   const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_wd,
@@ -286,7 +288,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // rows of x_i are read as tap 1 by their own tile and, d rows later, as tap 0: that second read is the last one
         tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b, p.pol_first);
         tma_load_3d(si + TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);
-        if (p.ts && blockIdx.x == 0) p.ts[1024 + it * 4 + 2] = clock64();
+        if (TRACE && p.ts && blockIdx.x == 0) p.ts[1024 + it * 4 + 2] = clock64();
         if (dense) {      // low half of the residual stream; its tile is reused for lo' and released after that store
           mbar_wait(&lo_empty[it & 1], ((it >> 1) & 1) ^ 1);
           mbar_expect_tx(&lo_full[it & 1], TILE_BYTES);
@@ -308,7 +310,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(zt, kk), desc_kmajor(sbase + Fwd2Smem::WD, kk), id2, kk > 0);
           umma_commit(&dense_full[j2 & 1]);
-          if (p.ts && blockIdx.x == 0) p.ts[1024 + j2 * 4 + 1] = clock64();
+          if (TRACE && p.ts && blockIdx.x == 0) p.ts[1024 + j2 * 4 + 1] = clock64();
           ++j2;
           progressed = true;
         }
@@ -321,7 +323,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si + TILE_BYTES, kk), desc_kmajor(sbase + Fwd2Smem::W1, kk), id1, true);
           umma_commit(&fg_full[j1 & 1]);
           umma_commit(&in_empty[j1 % 3]);
-          if (p.ts && blockIdx.x == 0) p.ts[1024 + j1 * 4 + 0] = clock64();
+          if (TRACE && p.ts && blockIdx.x == 0) p.ts[1024 + j1 * 4 + 0] = clock64();
           ++j1;
           progressed = true;
         }
@@ -343,7 +345,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const uint8_t* si = sm + Fwd2Smem::IN + st * Fwd2Smem::IN_STAGE;
       uint8_t* zt = sm + Fwd2Smem::Z + ab * TILE_BYTES;
       const int64_t grow = ((int64_t)b * p.L + tau) * 64 + cg * 16;          // this thread's 16 channels of row tau
-      const bool rec = p.ts != nullptr && blockIdx.x == 0 && tid == 0;
+      const bool rec = TRACE && p.ts != nullptr && blockIdx.x == 0 && tid == 0;
       long long* ts = p.ts + (int64_t)it * 8;
       if (rec) ts[0] = clock64();
       uint8_t* lot = sm + Fwd2Smem::LO + ab * TILE_BYTES;
@@ -361,14 +363,14 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       for (int j = 0; j < 8; ++j) {
         float f0 = __uint_as_float(f[2 * j]), f1 = __uint_as_float(f[2 * j + 1]);
         float g0 = __uint_as_float(gq[2 * j]), g1 = __uint_as_float(gq[2 * j + 1]);
-        if (p.bias_fg) {
+        if (BIAS) {
           f0 += p.bias_fg[cg * 16 + 2 * j];
           f1 += p.bias_fg[cg * 16 + 2 * j + 1];
           g0 += p.bias_fg[64 + cg * 16 + 2 * j];
           g1 += p.bias_fg[64 + cg * 16 + 2 * j + 1];
         }
         float z0 = sigmoid_fast(g0) * tanh_fast(f0), z1 = sigmoid_fast(g1) * tanh_fast(f1);
-        if (p.dbg & 8) { z0 = g0 * f0; z1 = g1 * f1; }
+        if (TRACE && (p.dbg & 8)) { z0 = g0 * f0; z1 = g1 * f1; }
         pz[j] = valid ? pack_bf16(z0, z1) : 0u;
       }
       const uint4 zv0 = make_uint4(pz[0], pz[1], pz[2], pz[3]), zv1 = make_uint4(pz[4], pz[5], pz[6], pz[7]);
@@ -410,7 +412,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[j]);
             float x0 = __uint_as_float(dv[2 * j]) + (__low2float(r2) + __low2float(l2));
             float x1 = __uint_as_float(dv[2 * j + 1]) + (__high2float(r2) + __high2float(l2));
-            if (p.bias_d) {
+            if (BIAS) {
               x0 += p.bias_d[cg * 16 + 2 * j];
               x1 += p.bias_d[cg * 16 + 2 * j + 1];
             }
@@ -436,8 +438,8 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         mbar_arrive(&acc_empty[ab]);
         mbar_arrive(&in_empty[st]);
         // z is read again only by the skip GEMM at the end of the forward; x_{i+1} hi / lo' by the very next launch
-        if (tau0 >= p.tw_al && !(p.dbg & 1)) tma_store_3d(&tm_z, zt, p.zcol, tau0 - p.tw_al, b, p.pol_first);
-        if (dense && !(p.dbg & 2)) {
+        if (tau0 >= p.tw_al && !(TRACE && (p.dbg & 1))) tma_store_3d(&tm_z, zt, p.zcol, tau0 - p.tw_al, b, p.pol_first);
+        if (dense && !(TRACE && (p.dbg & 2))) {
           tma_store_3d(&tm_xo, sm + Fwd2Smem::XO, 0, tau0, b, p.pol_last);
           tma_store_3d(&tm_loo, lot, 0, tau0, b, p.pol_last);
         }
@@ -455,16 +457,20 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 }  // namespace
 
 int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, const BlockFwdPtrs& g, int n_batches, cudaStream_t s) {
-  static bool attr_set = false;
   const int smem = Fwd2Smem::TOTAL + 1024;
-  if (!attr_set) {
-    WN_CHECK_CUDA(cudaFuncSetAttribute(block_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
   const int n_items = n_batches * p.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
+  const bool trace = p.ts != nullptr || p.dbg != 0, bias = p.bias_fg != nullptr;
+  auto k = trace ? (bias ? block_fwd2_kernel<true, true> : block_fwd2_kernel<false, true>)
+                 : (bias ? block_fwd2_kernel<true, false> : block_fwd2_kernel<false, false>);
+  static const void* configured[4] = {};
+  const int slot = (trace ? 2 : 0) + (bias ? 1 : 0);
+  if (configured[slot] == nullptr) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[slot] = reinterpret_cast<const void*>(k);
+  }
   WN_PROF("block_fwd", s);
-  block_fwd2_kernel<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.w0, m.w1, m.wd, m.xo, m.loo, m.z, m.lo, p, g, n_batches);
+  k<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.w0, m.w1, m.wd, m.xo, m.loo, m.z, m.lo, p, g, n_batches);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
