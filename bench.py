@@ -72,9 +72,9 @@ def kernel_flops(B):
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu captures
-    (profiles/r1b_traffic.json; bytes cannot be measured live outside a profiler).  None when not captured."""
+    (profiles/r1c_traffic.json; bytes cannot be measured live outside a profiler).  None when not captured."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
         return t["kernels"][kernel]["dram_bytes_per_launch"]
     except Exception:
         return None

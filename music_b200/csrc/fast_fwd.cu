@@ -488,6 +488,7 @@ constexpr uint32_t SH_TOTAL = SH_H_OFF + 4 * TILE_BYTES;
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+template <bool BIAS>
 __global__ void __launch_bounds__(SH_THREADS, 1)
 skip_head_kernel(const __grid_constant__ CUtensorMap tm_zcat, const __grid_constant__ CUtensorMap tm_wsk,
                  const __grid_constant__ CUtensorMap tm_p1, const __grid_constant__ CUtensorMap tm_p2,
@@ -603,7 +604,7 @@ skip_head_kernel(const __grid_constant__ CUtensorMap tm_zcat, const __grid_const
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
-            if (bias) {
+            if (BIAS) {
               a0 += bias[c * 32 + 2 * j];
               a1 += bias[c * 32 + 2 * j + 1];
             }
@@ -648,7 +649,7 @@ skip_head_kernel(const __grid_constant__ CUtensorMap tm_zcat, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float a = __uint_as_float(v[j]);
-            if (p.bias_p2) a += p.bias_p2[c * 32 + j];
+            if (BIAS) a += p.bias_p2[c * 32 + j];
             out[(int64_t)(c * 32 + j) * p.W] = a;
           }
         }
@@ -666,15 +667,17 @@ skip_head_kernel(const __grid_constant__ CUtensorMap tm_zcat, const __grid_const
 }  // namespace
 
 int launch_skip_head(const SkipHeadMaps& m, const SkipHeadParams& p, cudaStream_t s) {
-  static bool attr_set = false;
   const int smem = SH_TOTAL + 1024;
-  if (!attr_set) {
-    WN_CHECK_CUDA(cudaFuncSetAttribute(skip_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+  const bool bias = p.bias_skip != nullptr;
+  auto k = bias ? skip_head_kernel<true> : skip_head_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[bias]) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[bias] = true;
   }
   int grid = std::min(p.n_tiles, g_sm_count);
   WN_PROF("skip_head", s);
-  skip_head_kernel<<<grid, SH_THREADS, smem, s>>>(m.zcat, m.wsk, m.p1, m.p2, m.h0, m.h1, p);
+  k<<<grid, SH_THREADS, smem, s>>>(m.zcat, m.wsk, m.p1, m.p2, m.h0, m.h1, p);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
