@@ -101,6 +101,28 @@ inline bool l2_hints_on() {
   }
   return on == 1;
 }
+// Launch with programmatic stream serialization (see pdl_wait() in tc05.cuh).  Only for kernels that call pdl_wait() before
+// their first access to memory written by earlier kernels.  WN_PDL=0 turns the attribute off (timing experiments).
+inline bool pdl_on() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("WN_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_on() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr unsigned long long kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
 
 extern int g_device;

@@ -60,6 +60,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_launch_dependents();      // programmatic dependent launch: see tc05.cuh
+  pdl_wait();
   const uint32_t sbase = smem_u32(sm);
   const int n_items = p.n_batches * p.tiles_per_batch * p.n_ntiles;
 
@@ -263,6 +265,8 @@ gemm_nt_resb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_launch_dependents();      // programmatic dependent launch: see tc05.cuh
+  pdl_wait();
   const uint32_t sbase = smem_u32(sm);
   const int T = p.n_ntiles;
   const int nt = (int)blockIdx.x % T, rank = (int)blockIdx.x / T;
@@ -425,6 +429,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_launch_dependents();      // programmatic dependent launch: see tc05.cuh
+  pdl_wait();
   const uint32_t sbase = smem_u32(sm);
   const int n_items = p.n_batches * p.tiles_per_batch;
   const bool have_work = (int)blockIdx.x < n_items;
@@ -674,6 +680,8 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_launch_dependents();      // programmatic dependent launch: see tc05.cuh
+  pdl_wait();
   const uint32_t sbase = smem_u32(sm);
   const int n_items = pp.n_batches * p.tiles_per_batch;
   constexpr bool dense = DENSE;
@@ -1025,17 +1033,17 @@ int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStrea
     auto k = pick(gemm_nt_resb_kernel<EPI_PLAIN>, gemm_nt_resb_kernel<EPI_MASK>, gemm_nt_resb_kernel<EPI_ADD>);
     WN_PROPAGATE(set_smem_once(k, smem));
     const int g2 = std::min(g_sm_count, p.n_batches * p.tiles_per_batch * p.n_ntiles);
-    k<<<g2, 192, smem, s>>>(m.a[0], m.b[0], m.out, p);
+    WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)g2), dim3(192), smem, s, m.a[0], m.b[0], m.out, p));
   } else if (NT == 256) {
     const int smem = NtCfg<256>::TOTAL + 1024;
     auto k = pick(gemm_nt_kernel<256, EPI_PLAIN>, gemm_nt_kernel<256, EPI_MASK>, gemm_nt_kernel<256, EPI_ADD>);
     WN_PROPAGATE(set_smem_once(k, smem));
-    k<<<grid, 192, smem, s>>>(m.a[0], m.a[1], m.b[0], m.b[1], m.out, p);
+    WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)grid), dim3(192), smem, s, m.a[0], m.a[1], m.b[0], m.b[1], m.out, p));
   } else if (NT == 64) {
     const int smem = NtCfg<64>::TOTAL + 1024;
     auto k = pick(gemm_nt_kernel<64, EPI_PLAIN>, gemm_nt_kernel<64, EPI_MASK>, gemm_nt_kernel<64, EPI_ADD>);
     WN_PROPAGATE(set_smem_once(k, smem));
-    k<<<grid, 192, smem, s>>>(m.a[0], m.a[1], m.b[0], m.b[1], m.out, p);
+    WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)grid), dim3(192), smem, s, m.a[0], m.a[1], m.b[0], m.b[1], m.out, p));
   } else {
     set_error("launch_gemm_nt: NT=%d", NT);
     return WN_ERR_INVALID;
@@ -1058,17 +1066,17 @@ int launch_gemm_tn(int NB, const GemmTnMaps& m, const GemmTnParams& p, cudaStrea
     static bool once = false;
     const int smem = TnCfg<4>::TOTAL + 1024;
     if (!once) { WN_PROPAGATE(set_smem(gemm_tn_kernel<4>, smem)); once = true; }
-    gemm_tn_kernel<4><<<grid, 192, smem, s>>>(m.a, m.b[0], m.b[1], p);
+    WN_CHECK_CUDA(launch_pdl(gemm_tn_kernel<4>, grid, dim3(192), smem, s, m.a, m.b[0], m.b[1], p));
   } else if (NB == 2) {
     static bool once = false;
     const int smem = TnCfg<2>::TOTAL + 1024;
     if (!once) { WN_PROPAGATE(set_smem(gemm_tn_kernel<2>, smem)); once = true; }
-    gemm_tn_kernel<2><<<grid, 192, smem, s>>>(m.a, m.b[0], m.b[1], p);
+    WN_CHECK_CUDA(launch_pdl(gemm_tn_kernel<2>, grid, dim3(192), smem, s, m.a, m.b[0], m.b[1], p));
   } else if (NB == 1) {
     static bool once = false;
     const int smem = TnCfg<1>::TOTAL + 1024;
     if (!once) { WN_PROPAGATE(set_smem(gemm_tn_kernel<1>, smem)); once = true; }
-    gemm_tn_kernel<1><<<grid, 192, smem, s>>>(m.a, m.b[0], m.b[1], p);
+    WN_CHECK_CUDA(launch_pdl(gemm_tn_kernel<1>, grid, dim3(192), smem, s, m.a, m.b[0], m.b[1], p));
   } else {
     set_error("launch_gemm_tn: NB=%d", NB);
     return WN_ERR_INVALID;
@@ -1098,7 +1106,7 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   WN_PROPAGATE(set_smem_once(k, smem));
   {
     WN_PROF("block_bwd2", s);
-    k<<<n_ctas, 576, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, m.dzs, p);
+    WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)n_ctas), dim3(576), smem, s, m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, m.dzs, p));
     WN_CHECK_LAUNCH();
   }
   return WN_OK;

@@ -271,6 +271,8 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const int n_items = n_batches * p.tiles_per_batch;
   const bool dense = p.has_dense != 0;
   const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  pdl_launch_dependents();      // the next launch may set itself up on SMs this grid has left ...
+  pdl_wait();                   // ... and this one touches activations only after its predecessor has completed
 
   if (warp == 16) {
     if (lane == 0 && n_mine > 0) {
@@ -470,7 +472,8 @@ int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, const Bloc
     configured[slot] = reinterpret_cast<const void*>(k);
   }
   WN_PROF("block_fwd", s);
-  k<<<std::min(n_items, g_sm_count), 576, smem, s>>>(m.x, m.w0, m.w1, m.wd, m.xo, m.loo, m.z, m.lo, p, g, n_batches);
+  WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)std::min(n_items, g_sm_count)), dim3(576), smem, s, m.x, m.w0, m.w1, m.wd, m.xo, m.loo, m.z, m.lo, p, g,
+                           n_batches));
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -518,6 +521,8 @@ skip_head_kernel(const __grid_constant__ CUtensorMap tm_zcat, const __grid_const
   const uint32_t tmem = tmem_base_s;
   const uint32_t sbase = smem_u32(sm);
   const int kc_skip = p.k_skip / 64;
+  pdl_launch_dependents();      // programmatic dependent launch: see tc05.cuh
+  pdl_wait();
 
   if (warp == 4) {
     // ------------------------------------------------ TMA producer
@@ -677,7 +682,7 @@ int launch_skip_head(const SkipHeadMaps& m, const SkipHeadParams& p, cudaStream_
   }
   int grid = std::min(p.n_tiles, g_sm_count);
   WN_PROF("skip_head", s);
-  k<<<grid, SH_THREADS, smem, s>>>(m.zcat, m.wsk, m.p1, m.p2, m.h0, m.h1, p);
+  WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)grid), dim3(SH_THREADS), smem, s, m.zcat, m.wsk, m.p1, m.p2, m.h0, m.h1, p));
   WN_CHECK_LAUNCH();
   return WN_OK;
 }

@@ -63,6 +63,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with the programmatic-stream-serialization attribute (launch_pdl, common.cuh) may start while its
+// predecessor in the stream is still running: its CTAs take the SMs the predecessor's CTAs have left, set up their barriers
+// and tensor memory, and then block in pdl_wait() until the predecessor grid has completed and its writes are visible.
+// Both instructions are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
