@@ -256,6 +256,15 @@ def bench_autoencoder(dev, steps=3):
             "train_flops_per_sample": 8.656e6, "tflops": W * 8.656e6 / (ms * 1e-3) / 1e12}
 
 
+def workload_config(world, B):
+    """The `config` object both arms print (BASELINE.json configs[1] / configs[2] per GPU)."""
+    return {"workload": "wavenet 30 layers (dilations 1..512 x3), 64 residual/64 dilation/256 skip ch, "
+                        f"batch {B} x 16k-sample windows per GPU (L=19070), Adam, index (true one-hot) input",
+            "global_batch": world * B, "window": WINDOW, "parallelism": f"dp{world}",
+            "l2": "per-step working set ~4.6 GB of activations rewritten every step >> 126 MB L2; "
+                  "4 distinct input batches rotate"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -266,8 +275,9 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "training audio samples/sec", "value": rate, "unit": "samples/s",
            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "wavenet 30 layers (1..512 x3), 64/64/256 ch, batch 16 x 16k-sample windows; "
-                                  "reference arm steps one clip at a time on the host cores"},
+           "config": dict(workload_config(max(1, args.gpus), args.batch),
+                          reference_note="CPU arm: rank 0 steps a bounded sample (one clip per step) on the host cores; "
+                                         "the rate per target sample does not depend on the batch size"),
            "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -435,11 +445,7 @@ def main():
         out = {"metric": "training audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
-               "config": {"workload": "wavenet 30 layers (dilations 1..512 x3), 64 residual/64 dilation/256 skip ch, "
-                                      f"batch {B} x 16k-sample windows per GPU (L=19070), Adam, index (true one-hot) input",
-                          "global_batch": world * B, "window": WINDOW, "parallelism": f"dp{world}",
-                          "l2": "per-step working set ~4.6 GB of activations rewritten every step >> 126 MB L2; "
-                                "4 distinct input batches rotate"},
+               "config": workload_config(world, B),
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": ms_e2e / K},
                "gpu_launches": int(launches), "loss": last_loss, "clocks": clocks, "roofline": roofline,
