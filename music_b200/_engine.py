@@ -202,6 +202,12 @@ class SoftmaxRowsFunction(torch.autograd.Function):
         return dlogits, None
 
 
+def loss_scratch_bytes(B: int, W: int) -> int:
+    nbytes = C.c_size_t()
+    L.check(L.load().wn_loss_scratch_bytes(B, W, C.byref(nbytes)))
+    return int(nbytes.value)
+
+
 def fused_loss(logits: torch.Tensor, target: torch.Tensor, rows: int, want_grad: bool, grad_scale: float = 1.0,
                scratch: Optional[torch.Tensor] = None):
     """(loss[1] device tensor, dlogits or None) via wn_loss_fwd_bwd."""

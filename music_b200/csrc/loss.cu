@@ -212,7 +212,37 @@ __global__ void __launch_bounds__(256, 4) loss_fwd_bwd_q256_kernel(const float* 
   }
 }
 
-// deterministic mean of n floats (single block, fixed order)
+// deterministic mean of n floats in two fixed-order stages: MEAN_BLOCKS partial sums (double), then one block over them
+constexpr int MEAN_BLOCKS = 128;
+__global__ void __launch_bounds__(1024) partial_sum_kernel(const float* __restrict__ v, int64_t n, double* __restrict__ partial) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += (double)v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = sh[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(MEAN_BLOCKS) mean_of_partials_kernel(const double* __restrict__ partial, int64_t n, float* __restrict__ out) {
+  __shared__ double sh[MEAN_BLOCKS / 32];
+  double s = partial[threadIdx.x];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < MEAN_BLOCKS / 32; ++k) t += sh[k];
+    out[0] = (float)(t / (double)n);
+  }
+}
+// single-block variant (kept for small inputs)
 __global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ v, int64_t n, float* __restrict__ out) {
   __shared__ double sh[32];
   double s = 0.0;
@@ -257,7 +287,7 @@ extern "C" int wn_softmax_bwd(const float* d_probs, const float* d_dprobs, int32
 
 extern "C" int wn_loss_scratch_bytes(int32_t B, int32_t W, size_t* bytes) {
   WN_REQUIRE(bytes && B > 0 && W > 0, WN_ERR_INVALID, "wn_loss_scratch_bytes: bad args");
-  *bytes = align_up((size_t)B * W * sizeof(float), 256);
+  *bytes = align_up((size_t)B * W * sizeof(float), 256) + MEAN_BLOCKS * sizeof(double);     // row losses + partial sums
   return WN_OK;
 }
 
@@ -276,7 +306,15 @@ extern "C" int wn_loss_fwd_bwd(const float* d_logits, const int64_t* d_target, i
     loss_fwd_bwd_kernel<<<(unsigned)ceil_div(n_rows, 8), 256, 0, s>>>(d_logits, d_target, m, n_rows, grad_scale,
                                                                       (float*)d_scratch, d_dlogits);
   WN_CHECK_LAUNCH();
-  mean_kernel<<<1, 1024, 0, s>>>((const float*)d_scratch, n_rows, d_loss);
-  WN_CHECK_LAUNCH();
+  if (n_rows < 64 * 1024) {
+    mean_kernel<<<1, 1024, 0, s>>>((const float*)d_scratch, n_rows, d_loss);
+    WN_CHECK_LAUNCH();
+  } else {
+    double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(d_scratch) + align_up((size_t)B * W * sizeof(float), 256));
+    partial_sum_kernel<<<MEAN_BLOCKS, 1024, 0, s>>>((const float*)d_scratch, n_rows, partial);
+    WN_CHECK_LAUNCH();
+    mean_of_partials_kernel<<<1, MEAN_BLOCKS, 0, s>>>(partial, n_rows, d_loss);
+    WN_CHECK_LAUNCH();
+  }
   return WN_OK;
 }

@@ -19,7 +19,7 @@ import torch.nn as nn
 import torch.optim as optim
 
 from .. import _lib as L
-from .._engine import fused_loss
+from .._engine import fused_loss, loss_scratch_bytes
 from .model import wavenet
 
 
@@ -138,7 +138,7 @@ class Trainer:
         src = x if x is not None else idx
         ws = e.workspace(mode, src.shape[0], src.shape[-1])
         logits = e.forward_logits(mode, x, idx, packed, ws)
-        loss, dlogits = fused_loss(logits, target, rows, True, 1.0, e.scratch("loss", 4 * logits.shape[0] * logits.shape[2] + 256))
+        loss, dlogits = fused_loss(logits, target, rows, True, 1.0, e.scratch("loss", loss_scratch_bytes(logits.shape[0], logits.shape[2])))
         e.backward(mode, x, idx, packed, ws, dlogits, e.gflat)
         return loss
 
