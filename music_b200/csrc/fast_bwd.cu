@@ -495,6 +495,134 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
+// ===================================================================================== causal_wgrad
+// dW_causal (R = 64, Q = 256, 2) = scatter of dx0 rows by the input codes, as a tensor-core GEMM with a ONE-HOT A operand that
+// is built in shared memory from the indices (never materialised in HBM):
+//   tap 1:  dW[r, q, 1] = sum_t [idx[t] == q] dx0[t, r]          tap 0:  dW[r, q, 0] = sum_t [idx[t] == q] dx0[t + 1, r]
+// Per 128-row tile: A = OH [K = 128 rows t][M = 256 q] (MN-major, four 64-column blocks), B = [dx0[t+1] | dx0[t]] (MN-major,
+// N = 128), two UMMA groups (q < 128, q >= 128) accumulate in TMEM across all tiles of the CTA.  The one-hot tiles are zeroed
+// once; afterwards every thread only clears the element it set two tiles ago and sets the new one.  Unlike the shared-memory
+// histogram this replaces (39 M shared atomics, 0.2 ms), the cost does not depend on how the codes are distributed.
+struct CwCfg {
+  static constexpr int STAGES = 2;
+  static constexpr uint32_t A_BYTES = 4 * TILE, B_BYTES = 2 * TILE, STAGE = A_BYTES + B_BYTES, TOTAL = STAGES * STAGE;
+};
+__global__ void __launch_bounds__(192, 1)
+causal_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dx0, const int64_t* __restrict__ idx, float* __restrict__ dW, int L,
+                    int n_batches, int tiles_per_batch) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full[CwCfg::STAGES], oh_full[CwCfg::STAGES], empty[CwCfg::STAGES], acc_full;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < CwCfg::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&oh_full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  if (warp < 4) {      // zero both one-hot areas once (128 threads, 16-byte stores)
+    for (int st = 0; st < CwCfg::STAGES; ++st)
+      for (uint32_t o = tid * 16; o < CwCfg::A_BYTES; o += 128 * 16) *reinterpret_cast<uint4*>(sm + st * CwCfg::STAGE + o) = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_launch_dependents();      // programmatic dependent launch: see tc05.cuh
+  pdl_wait();
+  const uint32_t sbase = smem_u32(sm);
+  const int n_items = n_batches * tiles_per_batch;
+  const bool have_work = (int)blockIdx.x < n_items;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = item / tiles_per_batch, row0 = (item % tiles_per_batch) * 128;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sb = sm + stage * CwCfg::STAGE + CwCfg::A_BYTES;
+        mbar_expect_tx(&full[stage], CwCfg::B_BYTES);
+        tma_load_3d(sb, &tm_dx0, &full[stage], 0, row0 + 1, b);          // tap 0 pairs idx[t] with dx0[t + 1]
+        tma_load_3d(sb + TILE, &tm_dx0, &full[stage], 0, row0, b);       // tap 1 pairs idx[t] with dx0[t]
+        if (++stage == CwCfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && have_work) {
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      constexpr uint32_t idn = idesc_bf16(128, 128, 1, 1);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        mbar_wait(&full[stage], phase);
+        mbar_wait(&oh_full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = sbase + stage * CwCfg::STAGE, sb = sa + CwCfg::A_BYTES;
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + mh * 128, desc_mnmajor(sa + mh * 2 * TILE, k, TILE), desc_mnmajor(sb, k, TILE), idn, (it | (uint32_t)k) != 0);
+        umma_commit(&empty[stage]);
+        if (++stage == CwCfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&acc_full);
+    }
+  } else if (have_work) {
+    // ---- one-hot builders: thread i owns row i of every tile
+    int stage = 0;
+    uint32_t phase = 0;
+    int prev[CwCfg::STAGES];
+#pragma unroll
+    for (int st = 0; st < CwCfg::STAGES; ++st) prev[st] = -1;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / tiles_per_batch, row0 = (item % tiles_per_batch) * 128;
+      const int t = row0 + tid;
+      const int q = t < L ? (int)idx[(int64_t)b * L + t] : -1;
+      mbar_wait(&empty[stage], phase ^ 1);        // the MMAs that read this stage's previous tile have completed
+      uint8_t* sa = sm + stage * CwCfg::STAGE;
+      // static indexing of prev[] (two stages)
+      int& pv = stage == 0 ? prev[0] : prev[1];
+      if (pv >= 0) *reinterpret_cast<uint16_t*>(sa + pv) = 0;
+      if (q >= 0) {
+        pv = (q >> 6) * (int)TILE + (int)sw128_offset(tid, q & 63);
+        *reinterpret_cast<uint16_t*>(sa + pv) = 0x3F80;      // bf16 1.0
+      } else {
+        pv = -1;
+      }
+      fence_proxy_async_smem();
+      epi_bar_sync();
+      if (tid == 0) mbar_arrive(&oh_full[stage]);
+      if (++stage == CwCfg::STAGES) { stage = 0; phase ^= 1; }
+    }
+    // ---- flush: TMEM row m of group mh = code q = 128 mh + m; columns [0,64) tap 0, [64,128) tap 1
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const uint32_t src = tmem_addr(tmem, warp * 32, 0);
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t v[32];
+      tmem_ld32(src + c * 32, v);
+      tmem_ld_wait();
+      const int mh = c >> 2, tap = (c >> 1) & 1, r0 = (c & 1) * 32;
+      float* ob = dW + (int64_t)(128 * mh + tid) * 2 + tap;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = __uint_as_float(v[j]);
+        if (x != 0.f) atomicAdd(ob + (int64_t)(r0 + j) * 512, x);      // dW[r][q][tap], Q = 256
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 // ========================================================================================== block_bwd
 struct BwdSmem {
   static constexpr uint32_t A0 = 0, A1 = TILE, W0 = 2 * TILE, W1 = 3 * TILE, DX = 4 * TILE, WDT = 5 * TILE, TOTAL = 5 * TILE + 8192;
@@ -1325,7 +1453,16 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   // ---- causal layer
   const __nv_bfloat16* dx0 = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DXa);
   if (bias) WN_PROPAGATE(launch_colsum_bf16(dx0, 64, B, L, 1, L, G + m.causal.b, s));
-  if (d_idx) {
+  if (d_idx && m.Q == 256 && !getenv("WN_SCATTER_SIMT")) {
+    static bool once = false;
+    const int smem = CwCfg::TOTAL + 1024;
+    if (!once) { WN_PROPAGATE(set_smem(causal_wgrad_kernel, smem)); once = true; }
+    const int tiles = (int)ceil_div(L, 128);
+    WN_PROF("causal_wgrad", s);
+    WN_CHECK_CUDA(launch_pdl(causal_wgrad_kernel, dim3((unsigned)std::min(B * tiles, g_sm_count)), dim3(192), smem, s, M.dxa, d_idx,
+                             G + m.causal.w, L, B, tiles));
+    WN_DEBUG_SYNC("causal_wgrad", s);
+  } else if (d_idx) {
     static bool once = false;
     const int smem = 2 * m.Q * 64 * 4;
     if (!once) { WN_PROPAGATE(set_smem(causal_scatter_bwd_kernel, smem)); once = true; }
