@@ -1009,11 +1009,12 @@ struct WgradReduceArgs {
   int64_t filt0, gate0, dense0, layer_stride;     // flat-vector offsets of layer 0's filter / gate / dense weights
   int n_layers;
   int n_ctas[64];                                  // partial tiles written per layer
+  int layer0;                                      // blockIdx.y = 0 is this layer
 };
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial_all, int64_t layer_pitch, WgradReduceArgs a,
                                                            float* __restrict__ G) {
   // blockIdx.y = layer; 8 consecutive elements x 32 partial-tile groups per block
-  const int layer = blockIdx.y;
+  const int layer = a.layer0 + blockIdx.y;
   const float* partial = partial_all + (int64_t)layer * layer_pitch;
   const int n_ctas = a.n_ctas[layer];
   float* g_filt = G + a.filt0 + (int64_t)layer * a.layer_stride;
@@ -1367,7 +1368,25 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     unfused_env = (e && e[0] == '1') ? 1 : 0;
   }
   const bool fused = unfused_env == 0;   // block_bwd2: weight gradients accumulated inside the block kernel
+  // side stream for the per-layer reductions of the weight-gradient partial tiles (WN_WGRAD_SIDE=0: one reduction at the end)
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  static int side_env = -1;
+  if (side_env < 0) {
+    const char* e = getenv("WN_WGRAD_SIDE");
+    side_env = (e && e[0] == '0') ? 0 : 1;
+    if (side_env) {
+      WN_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+      WN_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      WN_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+  }
+  WgradReduceArgs ra{};
+  ra.filt0 = m.layers[0].filt.w; ra.gate0 = m.layers[0].gate.w; ra.dense0 = m.layers[0].dense.w;
+  ra.layer_stride = N > 1 ? m.layers[1].filt.w - m.layers[0].filt.w : 0;
+  ra.n_layers = N;
   const int tiles_total = (int)ceil_div(L, 128);
+  for (int i = 0; i < N; ++i) ra.n_ctas[i] = std::min(B * (tiles_total - m.layers[i].start / 128), g_sm_count);
   for (int i = N - 1; i >= 0; --i) {
     const LayerP& l = m.layers[i];
     const int d = l.dilation, s_out = l.start, s_in = s_out - d;
@@ -1393,6 +1412,14 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
         b2.partial = reinterpret_cast<float*>(Wp + wl.WGP) + (int64_t)i * WGP_LAYER_FLOATS;
         WN_PROPAGATE(launch_block_bwd2(bm, b2, s));
         WN_DEBUG_SYNC("block_bwd2", s);
+        if (side) {   // sum this layer's per-CTA weight-gradient tiles next to the kernels that follow (its CTAs need ~1 KB of smem)
+          WN_CHECK_CUDA(cudaEventRecord(ev_fork, s));
+          WN_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+          ra.layer0 = i;
+          WN_PROF("wgrad_reduce", side);
+          wgrad_reduce_kernel<<<dim3((128 * 192) / 8, 1), 256, 0, side>>>(reinterpret_cast<const float*>(Wp + wl.WGP), WGP_LAYER_FLOATS, ra, G);
+          WN_CHECK_LAUNCH();
+        }
       } else {
         WN_PROPAGATE(launch_block_bwd(bm, bp, B * tpb, s));
         WN_DEBUG_SYNC("block_bwd", s);
@@ -1439,12 +1466,11 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       WN_DEBUG_SYNC("gemm_nt dx", s);
     }
   }
-  if (fused) {   // one reduction of every layer's per-CTA weight-gradient tiles (fixed order: deterministic)
-    WgradReduceArgs ra{};
-    ra.filt0 = m.layers[0].filt.w; ra.gate0 = m.layers[0].gate.w; ra.dense0 = m.layers[0].dense.w;
-    ra.layer_stride = N > 1 ? m.layers[1].filt.w - m.layers[0].filt.w : 0;
-    ra.n_layers = N;
-    for (int i = 0; i < N; ++i) ra.n_ctas[i] = std::min(B * (tiles_total - m.layers[i].start / 128), g_sm_count);
+  if (fused && side) {        // join: everything after this point on `s` sees the reduced weight gradients
+    WN_CHECK_CUDA(cudaEventRecord(ev_join, side));
+    WN_CHECK_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
+  } else if (fused) {         // one reduction of every layer's per-CTA weight-gradient tiles (fixed order: deterministic)
+    ra.layer0 = 0;
     WN_PROF("wgrad_reduce", s);
     dim3 grid((128 * 192) / 8, (unsigned)N);
     wgrad_reduce_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(Wp + wl.WGP), WGP_LAYER_FLOATS, ra, G);
