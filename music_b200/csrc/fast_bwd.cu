@@ -1416,7 +1416,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
           WN_CHECK_CUDA(cudaEventRecord(ev_fork, s));
           WN_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
           ra.layer0 = i;
-          WN_PROF("wgrad_reduce", side);
+          WN_PROF("wgrad_reduce (side stream, overlapped)", side);
           wgrad_reduce_kernel<<<dim3((128 * 192) / 8, 1), 256, 0, side>>>(reinterpret_cast<const float*>(Wp + wl.WGP), WGP_LAYER_FLOATS, ra, G);
           WN_CHECK_LAUNCH();
         }
