@@ -214,10 +214,12 @@ def bench_generation(net, n_streams, n_steps, dev):
                                  "(~64 B/clk) and the 31-stage dependency chain; many_streams shows the same kernel on 128 SMs"}}
 
 
-def bench_autoencoder(dev, steps=3):
-    """BASELINE.json configs[4] shape on ONE GPU: wavenet_autoencoder with the shipped parameters (40 layers, 32 channels,
-    512 bottleneck / skip, pool 512), one clip of W = 64000 targets (L = 68093), Adam.  The autoencoder runs in the fp32
-    check mode (SIMT kernels, csrc/ae.cu): this is a correctness-path timing, not a tensor-core number."""
+def bench_autoencoder(dev, steps=3, world=1, rank=0):
+    """BASELINE.json configs[4] shape: wavenet_autoencoder with the shipped parameters (40 layers, 32 channels, 512
+    bottleneck / skip, pool 512), one clip of W = 64000 targets (L = 68093) per GPU, Adam; with N > 1 ranks the gradients are
+    averaged with one all-reduce per step (weak scaling) and the rate is the aggregate over all GPUs, timed as the max over
+    ranks.  The autoencoder runs in the fp32 check mode (SIMT kernels, csrc/ae.cu): a correctness-path timing, not a
+    tensor-core number."""
     import torch
     from music_b200.wavenet_autoencoder.model1 import wavenet_autoencoder
     from music_b200.wavenet_autoencoder import train as T
@@ -226,7 +228,7 @@ def bench_autoencoder(dev, steps=3):
     net = wavenet_autoencoder(2, 256, dil, 32, 32, 512, 512, 32, 32, 512, False).to(dev)
     W = 64000
     L = net.receptive_field + W - 1
-    g = torch.Generator().manual_seed(1234)
+    g = torch.Generator().manual_seed(1234 + rank)
     idx = torch.randint(0, 256, (1, L), generator=g).to(dev)
     target = idx[:, net.receptive_field - 1:].contiguous()
     opt = T.get_optimizer(net, 'Adam', 1e-4)
@@ -239,10 +241,15 @@ def bench_autoencoder(dev, steps=3):
         probs = SoftmaxRowsFunction.apply(logits, L_.ROWS_REFERENCE)
         loss = torch.nn.functional.cross_entropy(probs, target.reshape(-1))
         loss.backward()
+        if world > 1:
+            T.all_reduce_grads_(net.parameters())
         opt.step()
         return loss
     step()
     torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -250,10 +257,14 @@ def bench_autoencoder(dev, steps=3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
     return {"workload": "wavenet_autoencoder 40 layers (1..512 x4), 32 ch, bottleneck/skip 512, pool 512; 1 clip x 64000 targets "
-                        "(L=68093), index input, Adam (torch.optim), fp32 check mode",
-            "samples_per_s": W / (ms * 1e-3), "ms_per_step": ms, "dtype": "f32", "loss": float(loss),
-            "train_flops_per_sample": 8.656e6, "tflops": W * 8.656e6 / (ms * 1e-3) / 1e12}
+                        f"(L=68093) per GPU on {world} GPU(s), index input, Adam (torch.optim), fp32 check mode",
+            "samples_per_s": world * W / (ms * 1e-3), "ms_per_step": ms, "dtype": "f32", "loss": float(loss), "n_gpus": world,
+            "train_flops_per_sample": 8.656e6, "tflops": world * W * 8.656e6 / (ms * 1e-3) / 1e12}
 
 
 def workload_config(world, B):
@@ -435,9 +446,9 @@ def main():
     if rank == 0 and world == 1 and args.gen_steps > 0:
         gen = bench_generation(net, args.gen_streams, args.gen_steps, dev)
     ae = None
-    if rank == 0 and world == 1 and not args.no_ae:
+    if not args.no_ae:                  # every rank takes part (one gradient all-reduce per step when world > 1)
         try:
-            ae = bench_autoencoder(dev)
+            ae = bench_autoencoder(dev, world=world, rank=rank)
         except Exception as exc:        # reported, never fatal for the headline line
             ae = {"error": repr(exc)}
 

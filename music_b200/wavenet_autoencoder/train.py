@@ -54,14 +54,36 @@ def load_model(model, path, model_name):
     return model
 
 
-def train_step(net, optimizer, music_piece, target_piece, loss_func=None, cond_weights=None):
+def all_reduce_grads_(params, dist=None, group=None):
+    """Data-parallel gradient exchange for one process per GPU (the reference wraps the net in nn.DataParallel,
+    train.py:93-97): ONE all-reduce of the flattened gradients, averaged over ranks.  Every rank holds the same number of
+    loss rows, so this equals the gradient of the mean loss over the gathered batch.  Works on any backend (NCCL on the
+    GPUs, gloo in the CPU tests)."""
+    if dist is None:
+        import torch.distributed as dist
+    params = [p for p in params if p.grad is not None]
+    if not params or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+
+
+def train_step(net, optimizer, music_piece, target_piece, loss_func=None, cond_weights=None, distributed=False):
     """One iteration of the reference loop (:117-134).  `music_piece` (B,Q,L) float on the GPU, `target_piece` any
     integer tensor with B*W entries.  Returns the loss as a 0-d device tensor (no host sync; the reference's
-    `loss.data[0]` is the caller's choice)."""
+    `loss.data[0]` is the caller's choice).  distributed=True averages the gradients over the process group first."""
     loss_func = loss_func or nn.CrossEntropyLoss()
     optimizer.zero_grad()
     outputs = net(music_piece, cond_weights=cond_weights)
     loss = loss_func(outputs, target_piece.reshape(-1).to(outputs.device, torch.int64))
     loss.backward()
+    if distributed:
+        all_reduce_grads_(net.parameters())
     optimizer.step()
     return loss.detach()

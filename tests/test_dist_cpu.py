@@ -64,3 +64,57 @@ def test_allreduce_is_identity_without_process_group():
     from music_b200.wavenet.train import all_reduce_mean_
     t = torch.arange(5.0)
     assert torch.equal(all_reduce_mean_(t.clone()), t)
+
+
+# ---- autoencoder: all_reduce_grads_ of wavenet_autoencoder/train.py on two gloo ranks ------------------------------
+AE_DIL = [1, 2, 4, 1, 2, 4]
+AE_CFG = dict(Re=8, De=8, BW=8, pool=4, Rd=8, Dd=8, Sd=16)
+
+
+def _ae_case():
+    torch.manual_seed(7)
+    shapes = O.ae_param_shapes(AE_DIL, AE_CFG["Re"], AE_CFG["De"], AE_CFG["BW"], AE_CFG["Rd"], AE_CFG["Dd"], AE_CFG["Sd"],
+                               quantization_channel=256, use_bias=True)
+    st = {k: (0.3 * torch.randn(*s)).requires_grad_(True) for k, s in shapes}
+    cond = {k: 0.3 * torch.randn(*s) for k, s in O.ae_cond_shapes(len(AE_DIL), AE_CFG["BW"], AE_CFG["Dd"], AE_CFG["Sd"])}
+    rf = O.receptive_field(2, AE_DIL)
+    W, B = 24, 4
+    idx = torch.randint(0, 256, (B, rf + W - 1))
+    tgt = torch.randint(0, 256, (B, W))
+    return st, cond, idx, tgt
+
+
+def _ae_grads(st, cond, idx, tgt):
+    for v in st.values():
+        v.grad = None
+    probs = O.ae_forward_probs(st, cond, AE_DIL, O.one_hot(idx, 256), AE_CFG["pool"])
+    loss = torch.nn.functional.cross_entropy(probs, tgt.reshape(-1))
+    loss.backward()
+    return float(loss)
+
+
+def _ae_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from music_b200.wavenet_autoencoder.train import all_reduce_grads_
+    st, cond, idx, tgt = _ae_case()
+    per = idx.shape[0] // world
+    sl = slice(rank * per, (rank + 1) * per)
+    _ae_grads(st, cond, idx[sl], tgt[sl])
+    params = [v for v in st.values()]            # the last block's dense conv has no gradient: must be skipped, not crash
+    all_reduce_grads_(params)
+    if rank == 0:
+        np.save(out, torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None]).numpy())
+    dist.destroy_process_group()
+
+
+def test_autoencoder_two_rank_gloo_gradient_average_equals_full_batch(tmp_path):
+    out = str(tmp_path / "ae.npy")
+    mp.spawn(_ae_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    st, cond, idx, tgt = _ae_case()
+    _ae_grads(st, cond, idx, tgt)
+    ref = torch.cat([p.grad.reshape(-1) for p in st.values() if p.grad is not None]).numpy()
+    np.testing.assert_allclose(got, ref, rtol=2e-4, atol=1e-8)
