@@ -233,6 +233,7 @@ inline int ew_blocks(int64_t n) { return (int)std::min<int64_t>(ceil_div(n, 256)
 int launch_pw_gemm(const PwArgs& a, cudaStream_t s) {
   if (a.t1 <= a.t0 || a.B <= 0) return WN_OK;
   dim3 grid((unsigned)ceil_div(a.t1 - a.t0, TM), (unsigned)ceil_div(a.n_out, TN), (unsigned)a.B);
+  WN_PROF("check_pw_gemm", s);
   pw_gemm_kernel<<<grid, 256, 0, s>>>(a);
   WN_CHECK_LAUNCH();
   return WN_OK;
@@ -241,9 +242,15 @@ int launch_pw_gemm(const PwArgs& a, cudaStream_t s) {
 int launch_wgrad(const WgArgs& a, cudaStream_t s) {
   if (a.t1 <= a.t0 || a.B <= 0) return WN_OK;
   const int rows = a.t1 - a.t0;
-  int rows_per_block = 1024;
-  int chunks = (int)ceil_div(rows, rows_per_block);
+  // split the time axis only as far as needed to fill the GPU (~4 CTAs per SM): every chunk ends in one fp32 atomic per
+  // weight, and with 512-channel convs a fixed 1024-row chunk meant 16 M atomics per call
+  const int tiles = (int)(ceil_div(a.n_in, TM) * ceil_div(a.n_out, TN)) * a.B;
+  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(4 * g_sm_count, tiles), ceil_div(rows, 256)));
+  int rows_per_block = (int)ceil_div(rows, chunks);
+  rows_per_block = (rows_per_block + 15) / 16 * 16;
+  chunks = (int)ceil_div(rows, rows_per_block);
   dim3 grid((unsigned)ceil_div(a.n_in, TM), (unsigned)ceil_div(a.n_out, TN), (unsigned)(a.B * chunks));
+  WN_PROF("check_wgrad", s);
   wgrad_kernel<<<grid, 256, 0, s>>>(a, rows_per_block, chunks);
   WN_CHECK_LAUNCH();
   return WN_OK;
