@@ -155,6 +155,26 @@ int wn_gen_export(const wn_model* m, int32_t mode, int32_t n_streams, const void
 int wn_gen_import(const wn_model* m, int32_t mode, int32_t n_streams, void* d_state,
                   const float* d_queues, const int64_t* d_last_note, void* stream);
 
+/* ---- conditioned generation (extension; SURVEY.md 8f rank 3: incremental generation for the autoencoder's decoder) ----
+ * The decoder of wavenet_autoencoder (model1.py:158-225) is a WaveNet stack whose block pre-activations and head receive an
+ * additive, per-frame conditioning vector (`_conditon`, :227-247).  With a descriptor installed, wn_forward (fp32),
+ * wn_gen_prime and wn_gen_steps (fp32) add  d_fg[stream, frame_i(t), block i, :]  to the [f|g] pre-activations of block i and
+ * d_head[stream, frame(t), :]  to post_process_1's output, where frame follows the reference rule on the TOTAL sequence:
+ * len % frames == 0 ? t_local / (len / frames) : t_local % frames, with len = total_len - (first valid index of that tensor).
+ * gate_first != 0 means channels [0,D) of d_fg belong to the gate and [D,2D) to the filter (the autoencoder's split, :188-192).
+ * Pass NULL to remove the descriptor.  The tables are read at call time; they must outlive the calls. */
+typedef struct {
+  const float* d_fg;      /* (n_streams, frames, n_layers, 2D) fp32 */
+  const float* d_head;    /* (n_streams, frames, S) fp32 */
+  int32_t frames, total_len, gate_first;
+} wn_gen_cond;
+int wn_set_conditioning(wn_model* m, const wn_gen_cond* cond);
+/* Builds those tables from an autoencoder: d_encoding (n_streams, frames, BW) channels-last, d_cond = its conditioning
+ * convs (layout of wn_ae_forward).  d_workspace: wn_ae_workspace_bytes(a, n_streams, L >= rf) bytes. */
+typedef struct wn_ae wn_ae;
+int wn_ae_cond_tables(wn_ae* a, int32_t n_streams, int32_t frames, const float* d_encoding, const float* d_cond,
+                      void* d_workspace, float* d_fg, float* d_head, void* stream);
+
 /* ---- autoencoder : wavenet_autoencoder.forward, wavenet_autoencoder/model1.py:137-268 (fp32 check mode) ----
  * Parameters: one flat fp32 vector in the reference state_dict order (model1.py:55-58: en_dilation_layer_stack.*,
  * en_dense_layer_stack.*, de_dilation_layer_stack.{3i,3i+1,3i+2}, en_causal_layer, bottleneck_layer, de_causal_layer,
@@ -171,7 +191,6 @@ typedef struct {
   int32_t use_bias;
   int32_t filter_width;            /* must be 2 */
 } wn_ae_config;
-typedef struct wn_ae wn_ae;
 int wn_ae_create(const wn_ae_config* cfg, wn_ae** out);
 int wn_ae_destroy(wn_ae* a);
 int64_t wn_ae_param_count(const wn_ae* a);

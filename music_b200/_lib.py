@@ -28,6 +28,11 @@ class wn_config(C.Structure):
                 ("use_bias", C.c_int32), ("filter_width", C.c_int32)]
 
 
+class wn_gen_cond(C.Structure):
+    _fields_ = [("d_fg", C.c_void_p), ("d_head", C.c_void_p), ("frames", C.c_int32), ("total_len", C.c_int32),
+                ("gate_first", C.c_int32)]
+
+
 class wn_ae_config(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("dilations", C.POINTER(C.c_int32)), ("quantization_channel", C.c_int32),
                 ("en_residual_channel", C.c_int32), ("en_dilation_channel", C.c_int32),
@@ -75,6 +80,8 @@ SIGNATURES = {
     "wn_ae_receptive_field": (C.c_int32, [_p]),
     "wn_ae_workspace_bytes": (C.c_int, [_p, _i32, _i32, _psz]),
     "wn_ae_forward": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "wn_set_conditioning": (C.c_int, [_p, _p]),
+    "wn_ae_cond_tables": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "wn_ae_train_workspace_bytes": (C.c_int, [_p, _i32, _i32, _psz]),
     "wn_ae_forward_train": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "wn_ae_backward": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

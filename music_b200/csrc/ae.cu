@@ -371,6 +371,30 @@ extern "C" int wn_ae_forward(wn_ae* a, int32_t B, int32_t L, const float* d_x, c
   return ae_forward_impl(a, B, L, d_x, d_idx, d_params, d_cond, d_workspace, d_logits, d_encoding, stream, false);
 }
 
+// Conditioning tables for incremental generation with the decoder (wn_set_conditioning, include/wavenet_b200.h):
+//   d_fg[n, f, i, :]   = cond_i(encoding)[n, :, f]   (2Dd channels in the conv's own order: gate first, model1.py:188-192)
+//   d_head[n, f, :]    = cond_N(encoding)[n, :, f]
+extern "C" int wn_ae_cond_tables(wn_ae* a, int32_t n_streams, int32_t frames, const float* d_encoding, const float* d_cond,
+                                 void* d_workspace, float* d_fg, float* d_head, void* stream) {
+  WN_REQUIRE(g_inited, WN_ERR_UNSUPPORTED, "wn_init() has not succeeded: no sm_100 device, no fallback");
+  WN_REQUIRE(a && d_encoding && d_cond && d_workspace && d_fg && d_head && n_streams > 0 && frames > 0, WN_ERR_INVALID,
+             "wn_ae_cond_tables: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  AeWs w = ae_ws(*a, n_streams, a->rf, true, d_workspace);       // only the weight-repack scratch is used
+  const int N = a->N, C2 = 2 * a->Dd;
+  TensorView ENCv = tv(d_encoding, (int64_t)frames * a->BW, a->BW, 1);
+  for (int i = 0; i < N; ++i) {
+    PwArgs pc; pc.X = ENCv; pc.x_lo = 0; pc.x_hi = frames;
+    pc.Y = tv(d_fg + (int64_t)i * C2, (int64_t)frames * N * C2, (int64_t)N * C2, 1);
+    pc.B = n_streams; pc.t0 = 0; pc.t1 = frames;
+    WN_PROPAGATE(apply_conv(d_cond, a->cond[i], w.WT, pc, 1, s));
+  }
+  PwArgs ph; ph.X = ENCv; ph.x_lo = 0; ph.x_hi = frames; ph.Y = tv(d_head, (int64_t)frames * a->Sd, a->Sd, 1);
+  ph.B = n_streams; ph.t0 = 0; ph.t1 = frames;
+  WN_PROPAGATE(apply_conv(d_cond, a->cond[N], w.WT, ph, 1, s));
+  return WN_OK;
+}
+
 extern "C" int wn_ae_train_workspace_bytes(const wn_ae* a, int32_t B, int32_t L, size_t* bytes) {
   WN_REQUIRE(a && bytes && B > 0, WN_ERR_INVALID, "wn_ae_train_workspace_bytes: bad argument");
   WN_REQUIRE(L - a->rf + 1 > 0, WN_ERR_SHAPE, "wave sample not long enough");

@@ -142,9 +142,26 @@ static TensorView tv(const float* p, int64_t sb, int64_t st, int64_t sc, int shi
   return v;
 }
 
+// Y[b, row, c] += table[(b * frames + frame(row)) * t_stride + t_off + perm(c)] for rows in [t0, t1): the additive conditioning of
+// wavenet_autoencoder._conditon (model1.py:227-247).  frame(row) uses local index row - s0 and length total_len - s0.
+__global__ void cond_add_kernel(float* __restrict__ Y, int64_t y_bstride, int y_shift, int C, int t0, int t1, const float* __restrict__ table,
+                                int frames, int64_t t_stride, int t_off, int swap_halves, int s0, int total_len) {
+  const int b = blockIdx.y;
+  const int64_t n = (int64_t)(t1 - t0) * C;
+  const int len = total_len - s0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int row = t0 + (int)(e / C), c = (int)(e % C);
+    const int tl = row - s0;
+    const int f = (len % frames == 0) ? tl / (len / frames) : tl % frames;
+    const int cc = swap_halves ? (c + C / 2) % C : c;
+    Y[(int64_t)b * y_bstride + (int64_t)(row + y_shift) * C + c] += table[((int64_t)b * frames + f) * t_stride + t_off + cc];
+  }
+}
+
 static int forward32(const Model& m, int B, int L, const float* d_x, const int64_t* d_idx, const float* P, void* ws, float* logits,
-                     cudaStream_t s) {
+                     cudaStream_t s, const wn_gen_cond* cond = nullptr) {
   const int W = L - m.rf + 1, R = m.R, D = m.D, S = m.S, Q = m.Q, N = m.n_layers;
+  if (cond && cond->d_fg == nullptr) cond = nullptr;
   Ws32 w = ws32_layout(m, B, L, ws);
   auto bias = [&](const ConvP& c) { return c.b >= 0 ? P + pack32_of(m, &c).b : nullptr; };
   auto wt = [&](const ConvP& c) { return P + pack32_of(m, &c).wt; };
@@ -176,6 +193,12 @@ static int forward32(const Model& m, int B, int L, const float* d_x, const int64
       a.B = B; a.t0 = s_out; a.t1 = L;
       WN_PROPAGATE(launch_pw_gemm(a, s));
     }
+    if (cond) {        // conditioned decoder: [f|g] += cond_i[frame]  (model1.py:178-186)
+      dim3 grid((unsigned)std::min<int64_t>(ceil_div((int64_t)(L - s_out) * 2 * D, 256), 148 * 8), (unsigned)B);
+      cond_add_kernel<<<grid, 256, 0, s>>>(FGi, (int64_t)L * 2 * D, 0, 2 * D, s_out, L, cond->d_fg, cond->frames,
+                                           (int64_t)N * 2 * D, i * 2 * D, cond->gate_first, s_out, cond->total_len);
+      WN_CHECK_LAUNCH();
+    }
     WN_PROPAGATE(launch_gate_fwd(FGi, w.Z, B, L, D, s_out, L, s));     // :120
     if (i + 1 < N) {                                                    // dense + residual (:121-124)
       PwArgs a;
@@ -206,6 +229,12 @@ static int forward32(const Model& m, int B, int L, const float* d_x, const int64
     a.Y = tv(w.H1, (int64_t)W * S, S, 1, -(L - W)); a.n_out = S;
     a.B = B; a.t0 = L - W; a.t1 = L;
     WN_PROPAGATE(launch_pw_gemm(a, s));
+  }
+  if (cond) {          // H1 += cond_N[frame] before the ReLU  (model1.py:216-219)
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div((int64_t)W * S, 256), 148 * 8), (unsigned)B);
+    cond_add_kernel<<<grid, 256, 0, s>>>(w.H1, (int64_t)W * S, -(L - W), S, L - W, L, cond->d_head, cond->frames, (int64_t)S, 0, 0,
+                                         m.rf - 1, cond->total_len);
+    WN_CHECK_LAUNCH();
   }
   {   // relu -> post_process_2 (:137-138), written as (B,Q,W)
     PwArgs a;
@@ -500,10 +529,24 @@ extern "C" int wn_forward(wn_model* h, int32_t mode, int32_t B, int32_t L, const
   WN_REQUIRE(h && d_packed && d_workspace && d_logits, WN_ERR_INVALID, "wn_forward: null argument");
   WN_REQUIRE((d_x != nullptr) != (d_idx != nullptr), WN_ERR_INVALID, "wn_forward: exactly one of d_x / d_idx must be given");
   WN_PROPAGATE(check_shape(h->m, B, L));
-  if (mode == WN_MODE_FP32) return forward32(h->m, B, L, d_x, d_idx, (const float*)d_packed, d_workspace, d_logits, (cudaStream_t)stream);
+  if (mode == WN_MODE_FP32)
+    return forward32(h->m, B, L, d_x, d_idx, (const float*)d_packed, d_workspace, d_logits, (cudaStream_t)stream, &h->cond);
+  WN_REQUIRE(h->cond.d_fg == nullptr, WN_ERR_UNSUPPORTED, "conditioning (wn_set_conditioning) is implemented in fp32 mode only");
   if (mode == WN_MODE_BF16) return fast_forward(h->m, B, L, d_x, d_idx, d_packed, d_workspace, d_logits, (cudaStream_t)stream);
   set_error("wn_forward: unknown mode %d", mode);
   return WN_ERR_INVALID;
+}
+
+extern "C" int wn_set_conditioning(wn_model* h, const wn_gen_cond* cond) {
+  WN_REQUIRE(h, WN_ERR_INVALID, "wn_set_conditioning: null model");
+  if (cond == nullptr) {
+    h->cond = wn_gen_cond{};
+    return WN_OK;
+  }
+  WN_REQUIRE(cond->d_fg && cond->d_head && cond->frames > 0 && cond->total_len >= h->m.rf, WN_ERR_INVALID,
+             "wn_set_conditioning: tables, frames > 0 and total_len >= receptive field are required");
+  h->cond = *cond;
+  return WN_OK;
 }
 
 extern "C" int wn_backward(wn_model* h, int32_t mode, int32_t B, int32_t L, const float* d_x, const int64_t* d_idx,
@@ -511,6 +554,7 @@ extern "C" int wn_backward(wn_model* h, int32_t mode, int32_t B, int32_t L, cons
   WN_REQUIRE(g_inited, WN_ERR_UNSUPPORTED, "wn_init() has not succeeded: no sm_100 device, no fallback");
   WN_REQUIRE(h && d_packed && d_workspace && d_dlogits && d_grads, WN_ERR_INVALID, "wn_backward: null argument");
   WN_REQUIRE((d_x != nullptr) != (d_idx != nullptr), WN_ERR_INVALID, "wn_backward: exactly one of d_x / d_idx must be given");
+  WN_REQUIRE(h->cond.d_fg == nullptr, WN_ERR_UNSUPPORTED, "wn_backward: a conditioning descriptor is installed (inference only)");
   WN_PROPAGATE(check_shape(h->m, B, L));
   if (mode == WN_MODE_FP32)
     return backward32(h->m, B, L, d_x, d_idx, (const float*)d_packed, d_workspace, d_dlogits, d_grads, (cudaStream_t)stream);

@@ -133,4 +133,5 @@ extern bool g_inited;
 
 struct wn_model {
   wn::Model m;
+  wn_gen_cond cond{};       // optional conditioning descriptor (wn_set_conditioning); d_fg == nullptr: none
 };

@@ -27,7 +27,15 @@ struct GenParams {
   int64_t layer0, layer_sz;      // layer block base / size
   int64_t f_wt, f_b, g_wt, g_b, d_wt, d_b, s_wt, s_b;   // within a layer block
   int64_t p1_wt, p1_b, p2_wt, p2_b;
+  // optional conditioning (wn_set_conditioning): tables, frame rule parameters, first valid index of every block's output
+  const float* cond_fg;
+  const float* cond_head;
+  int cond_frames, cond_total, cond_gate_first, rf;
+  int s_out[GEN_MAXL];
 };
+__host__ __device__ inline int cond_frame_of(int t_local, int len, int frames) {
+  return (len % frames == 0) ? t_local / (len / frames) : t_local % frames;      // model1.py:233-246
+}
 
 static int64_t gen_state_stride(const Model& m) {
   int64_t sum = 0;
@@ -58,7 +66,15 @@ static int fill_params(const Model& m, GenParams* gp) {
   p.d_wt = d0.wt - f0.wt; p.d_b = d0.b - f0.wt;
   p.s_wt = s0.wt - f0.wt; p.s_b = s0.b - f0.wt;
   p.p1_wt = p1.wt; p.p1_b = p1.b; p.p2_wt = p2.wt; p.p2_b = p2.b;
+  p.cond_fg = nullptr; p.cond_head = nullptr; p.cond_frames = 0; p.cond_total = 0; p.cond_gate_first = 0;
+  p.rf = m.rf;
+  for (int i = 0; i < m.n_layers; ++i) p.s_out[i] = m.layers[i].start;
   return WN_OK;
+}
+static void attach_cond(GenParams* p, const wn_gen_cond& c) {
+  if (c.d_fg == nullptr) return;
+  p->cond_fg = c.d_fg; p->cond_head = c.d_head; p->cond_frames = c.frames; p->cond_total = c.total_len;
+  p->cond_gate_first = c.gate_first;
 }
 
 namespace {
@@ -129,6 +145,12 @@ __global__ void __launch_bounds__(256) gen_steps_f32_kernel(GenParams p, const f
       float* ring = rings + (int64_t)p.ring_off[i] * R;
       const int slot = (int)(t % d);
       const float* L = P + p.layer0 + (int64_t)i * p.layer_sz;
+      const float* cfg = nullptr;        // this block's conditioning vector for the current time step (2D values)
+      if (p.cond_fg) {
+        const int tau = p.rf + (int)t;   // absolute index of the sample being consumed
+        const int f = cond_frame_of(tau - p.s_out[i], p.cond_total - p.s_out[i], p.cond_frames);
+        cfg = p.cond_fg + (((int64_t)st * p.cond_frames + f) * p.n_layers + i) * 2 * D;
+      }
       for (int r = tid; r < R; r += nt) old[r] = ring[(int64_t)slot * R + r];
       __syncthreads();
       // filter / gate: W0 * old + W1 * x   (:118-121 via one_layer_forward :71-95)
@@ -137,6 +159,7 @@ __global__ void __launch_bounds__(256) gen_steps_f32_kernel(GenParams p, const f
         const int oo = is_g ? o - D : o;
         const float* Wt = L + (is_g ? p.g_wt : p.f_wt);      // [tap][R][D]
         float acc = p.has_bias ? L[(is_g ? p.g_b : p.f_b) + oo] : 0.f;
+        if (cfg) acc += cfg[p.cond_gate_first ? (is_g ? oo : D + oo) : o];
         for (int c = 0; c < R; ++c) acc = fmaf(Wt[(int64_t)c * D + oo], old[c], acc);
         const float* Wt1 = Wt + (int64_t)R * D;
         for (int c = 0; c < R; ++c) acc = fmaf(Wt1[(int64_t)c * D + oo], x[c], acc);
@@ -172,6 +195,11 @@ __global__ void __launch_bounds__(256) gen_steps_f32_kernel(GenParams p, const f
     for (int s = tid; s < S; s += nt) {
       const float* Wt = P + p.p1_wt;                          // [S][S]
       float acc = p.has_bias ? P[p.p1_b + s] : 0.f;
+      if (p.cond_head) {
+        const int tau = p.rf + (int)t;
+        const int f = cond_frame_of(tau - (p.rf - 1), p.cond_total - (p.rf - 1), p.cond_frames);
+        acc += p.cond_head[((int64_t)st * p.cond_frames + f) * S + s];
+      }
       for (int c = 0; c < S; ++c) acc = fmaf(Wt[(int64_t)c * S + s], fmaxf(sk[c], 0.f), acc);
       h1[s] = fmaxf(acc, 0.f);
     }
@@ -292,11 +320,14 @@ extern "C" int wn_gen_steps(wn_model* h, int32_t mode, int32_t n_streams, int32_
   if (n_steps == 0) return WN_OK;
   const Model& m = h->m;
   cudaStream_t s = (cudaStream_t)stream;
-  if (mode == WN_MODE_BF16)
+  if (mode == WN_MODE_BF16) {
+    WN_REQUIRE(h->cond.d_fg == nullptr, WN_ERR_UNSUPPORTED, "conditioned generation is implemented in fp32 mode only");
     return fast_gen_steps(h->m, n_streams, n_steps, push, d_first_note, d_packed, d_state, d_uniforms, d_out, d_logits, s);
+  }
   WN_REQUIRE(mode == WN_MODE_FP32, WN_ERR_INVALID, "wn_gen_steps: unknown mode %d", mode);
   GenParams gp;
   WN_PROPAGATE(fill_params(m, &gp));
+  attach_cond(&gp, h->cond);
   size_t smem = (size_t)(3 * m.R + 3 * m.D + 2 * m.S + m.Q) * sizeof(float);
   gen_steps_f32_kernel<<<n_streams, 256, smem, s>>>(gp, (const float*)d_packed, (char*)d_state, n_streams, n_steps, push,
                                                     d_first_note, d_uniforms, d_out, d_logits);

@@ -163,3 +163,33 @@ def test_slow_generate_matches_oracle_greedy():
         wav = torch.cat((wav[:, :, -rf - 511:], O.one_hot(torch.tensor([[p]]), 256)), 2)
     got = generate_codes(net.cuda(), 5, start_piece=start)
     assert got == ref
+
+
+@pytest.mark.parametrize("W,pool,bias", [(24, 4, True), (26, 4, False)])
+def test_incremental_decoder_generation_equals_full_forward(W, pool, bias):
+    """Extension: incremental generation with the conditioned decoder.  Teacher-forced with the samples of a
+    given sequence, step j must reproduce row j of the decoder's full forward over that sequence (`_decode`,
+    model1.py:158-225), including `_conditon`'s per-layer frame rule (:227-247), whose branch differs from layer to layer
+    (W=24: 6 frames; W=26: 6 frames and a ragged tail)."""
+    from music_b200.wavenet_autoencoder.generate import fast_generate_codes
+    dil = [1, 2, 4, 1, 2, 4]
+    cfg = dict(Re=16, De=16, BW=16, pool=pool, Rd=16, Dd=16, Sd=32)
+    net, st, cond, idx, tgt = _ae_case(dil, cfg, bias, 2, W, seed=W)
+    st = {k: v.detach() for k, v in st.items()}
+    cond = {k: v.detach() for k, v in cond.items()}
+    rf = O.receptive_field(2, dil)
+    L = rf + W - 1
+    frames = W // pool
+    enc = torch.randn(2, cfg["BW"], frames)
+    x = O.one_hot(idx, 256)
+    ref = O.ae_decode_logits(st, cond, dil, x, enc, W)                       # (B, Q, W)
+    net = net.cuda()
+    forced = idx[:, rf:].t().contiguous()                                    # sample rf + j feeds step j + 1
+    codes, logits = fast_generate_codes(net, enc, L, W, idx[:, :rf], cond_weights=cond, forced=forced, return_logits=True)
+    got = logits.permute(1, 2, 0).cpu().numpy()                              # (B, Q, W)
+    assert max_rel(got, ref.numpy()) < 1e-4
+    assert codes.t().cpu().tolist() == ref.argmax(dim=1).tolist()
+    # free-running generation (no forcing) is self-consistent: replaying its own picks as forced inputs gives the same codes
+    free = fast_generate_codes(net, enc, L, 8, idx[:, :rf], cond_weights=cond)
+    again = fast_generate_codes(net, enc, L, 8, idx[:, :rf], cond_weights=cond, forced=free[:-1])
+    assert torch.equal(free, again)
