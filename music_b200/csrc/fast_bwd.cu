@@ -26,11 +26,15 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 // ============================================================================================ gemm_nt
 template <int NT>
 struct NtCfg {
-  static constexpr int STAGES = NT == 256 ? 3 : 2;
-  static constexpr uint32_t A_BYTES = TILE, B_BYTES = NT * 128, STAGE = A_BYTES + B_BYTES;
-  static constexpr uint32_t OUT_OFF = STAGES * STAGE, TOTAL = OUT_OFF + (NT / 64) * TILE;
+  // NT = 64 (the dx GEMM): the weight chunks of all K segments (up to 4 x 8 KB) are RESIDENT, only A tiles stream through a
+  // 3-stage ring; re-fetching them per item was 29 % of the kernel's L2 -> SM traffic (8.3 TB/s, at the L2 rate limit).
+  static constexpr bool RES_B = NT == 64;
+  static constexpr int STAGES = 3;
+  static constexpr uint32_t A_BYTES = TILE, B_BYTES = NT * 128, STAGE = RES_B ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr uint32_t BRES_OFF = STAGES * STAGE, BRES_BYTES = RES_B ? 4 * B_BYTES : 0;
+  static constexpr uint32_t OUT_OFF = BRES_OFF + BRES_BYTES, TOTAL = OUT_OFF + (NT / 64) * TILE;
   static constexpr int TMEM_COLS = NT == 256 ? 512 : 128;
-  static constexpr int CTAS_PER_SM = NT == 256 ? 1 : 3;      // NT=64: 65 KB smem, 128 TMEM columns per CTA
+  static constexpr int CTAS_PER_SM = NT == 256 ? 1 : 2;      // NT=64: 97 KB smem, 128 TMEM columns per CTA
 };
 
 template <int NT, int EPI>      // EPI is a compile-time constant: a run-time p.epi made the epilogue branch per element
@@ -41,7 +45,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   using Cfg = NtCfg<NT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full[Cfg::STAGES], empty[Cfg::STAGES], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t full[Cfg::STAGES], empty[Cfg::STAGES], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -53,6 +57,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 1);
     }
+    mbar_init(&b_full, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
@@ -67,6 +72,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 4) {
     if (lane == 0) {
+      if (Cfg::RES_B && (int)blockIdx.x < n_items) {      // n_ntiles == 1: every item uses the same weight chunks
+        mbar_expect_tx(&b_full, (p.nk[0] + p.nk[1]) * Cfg::B_BYTES);
+        int c = 0;
+        for (int seg = 0; seg < 2; ++seg)
+          for (int k = 0; k < p.nk[seg]; ++k, ++c)
+            tma_load_2d(sm + Cfg::BRES_OFF + c * Cfg::B_BYTES, seg == 0 ? &tmB0 : &tmB1, &b_full, p.b_col0[seg] + 64 * k, 0);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -78,7 +90,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             uint8_t* sa = sm + stage * Cfg::STAGE;
             mbar_expect_tx(&full[stage], Cfg::STAGE);
             tma_load_3d(sa, seg == 0 ? &tmA0 : &tmA1, &full[stage], p.a_col0[seg] + 64 * k, row0 + p.a_row_off[seg], b, p.pol_a[seg]);
-            tma_load_2d(sa + Cfg::A_BYTES, seg == 0 ? &tmB0 : &tmB1, &full[stage], p.b_col0[seg] + 64 * k, nt * NT);
+            if (!Cfg::RES_B)
+              tma_load_2d(sa + Cfg::A_BYTES, seg == 0 ? &tmB0 : &tmB1, &full[stage], p.b_col0[seg] + 64 * k, nt * NT);
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -89,6 +102,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0, it = 0;
       constexpr uint32_t idn = idesc_bf16(128, NT, 0, 0);
+      if (Cfg::RES_B && (int)blockIdx.x < n_items) mbar_wait(&b_full, 0);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);
@@ -98,7 +112,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
+          const uint32_t sa = sbase + stage * Cfg::STAGE;
+          const uint32_t sb = Cfg::RES_B ? sbase + Cfg::BRES_OFF + kc * Cfg::B_BYTES : sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(dst, desc_kmajor(sa, k), desc_kmajor(sb, k), idn, (kc | k) != 0);
           umma_commit(&empty[stage]);
