@@ -638,6 +638,159 @@ causal_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dx0, const int64_t* _
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+// ======================================================================================= gemm_tn, CTA pair
+// The y-mode launches of gemm_tn_kernel<4> (dW_skip of all layers, dP1, dP2) run two CTAs per (row slice, layer group), one
+// per 128-row m-tile of A, and BOTH stream the same four B blocks: 96 KB per 8.4 MFLOP k-step, L2 -> SM bound.  Here the two
+// form a CTA pair (cluster 2 x 1, tcgen05 cta_group::2): one M = 256 accumulator spans both SMs' tensor memory, the leader
+// issues the MMAs, and each CTA loads its own m-tile of A plus only HALF of the B blocks (64 KB per k-step, three stages).
+// Hand-off per stage: local TMA barrier -> the peer's relay thread arrives on the leader's peer_full -> MMAs -> one commit
+// multicast to both CTAs' empty barriers.  (Building block verified in isolation by tools/pair_umma_test.cu.)
+struct TnPairCfg {
+  static constexpr int STAGES = 3;
+  static constexpr uint32_t A_BYTES = 2 * TILE, B_BYTES = 2 * TILE, STAGE = A_BYTES + B_BYTES, TOTAL = STAGES * STAGE;
+};
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrives on `bar` of BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                    const __grid_constant__ CUtensorMap tmB1, GemmTnParams p) {
+  using Cfg = TnPairCfg;
+  // grid (2 x row slices, layer groups), cluster 2 x 1: blockIdx.x & 1 = m-tile = rank in the pair
+  const int mt = blockIdx.x & 1, g = blockIdx.y;
+  const int slice = blockIdx.x >> 1, n_slices = gridDim.x >> 1;
+  p.a_col0 = 128 * mt;
+  p.out0 += (int64_t)128 * mt * p.s_m;
+  p.out1 += (int64_t)128 * mt * p.s_m;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int li = 4 * g + j;
+    p.b_col[j] = 64 * li;                                   // past the last layer: outside the tensor -> zero fill
+    p.blk_off[j] = p.y_off0 + (int64_t)min(li, p.y_layers - 1) * p.y_stride;
+  }
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full[Cfg::STAGES], peer_full[Cfg::STAGES], empty[Cfg::STAGES], acc_full;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();                  // == mt
+  if (tid == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&peer_full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // both CTAs' barriers and tensor memory exist
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_launch_dependents();      // programmatic dependent launch: see tc05.cuh
+  pdl_wait();
+  const uint32_t sbase = smem_u32(sm);
+  const int n_items = p.n_batches * p.tiles_per_batch;
+  const bool have_work = slice < n_items;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = slice; item < n_items; item += n_slices) {
+        const int b = item / p.tiles_per_batch, row0 = (p.tile0 + item % p.tiles_per_batch) * 128;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = sm + stage * Cfg::STAGE;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        mbar_expect_tx(&full[stage], Cfg::STAGE);
+        tma_load_3d(sa, &tmA, &full[stage], p.a_col0, row0, b);
+        tma_load_3d(sa + TILE, &tmA, &full[stage], p.a_col0 + 64, row0, b);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {                    // this CTA's half of the B blocks
+          const int j = 2 * mt + jj;
+          tma_load_3d(sb + jj * TILE, p.b_map[j] == 0 ? &tmB0 : &tmB1, &full[stage], p.b_col[j], row0 + p.b_row_off[j], b);
+        }
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && have_work) {
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      if (rank != 0) {
+        // relay: tell the leader when this CTA's operands of a stage have landed
+        for (int item = slice; item < n_items; item += n_slices) {
+          mbar_wait(&full[stage], phase);
+          uint32_t remote;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(&peer_full[stage])));
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      } else {
+        constexpr uint32_t idn = idesc_bf16(256, 256, 1, 1);
+        for (int item = slice; item < n_items; item += n_slices, ++it) {
+          mbar_wait(&full[stage], phase);
+          mbar_wait(&peer_full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16_pair(tmem, desc_mnmajor(sa, k, TILE), desc_mnmajor(sb, k, TILE), idn, (it | (uint32_t)k) != 0);
+          umma_commit_pair(&empty[stage]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&acc_full);
+      }
+    }
+  } else if (have_work) {
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const int m = tid;
+    float* base = (m < 64 ? p.out0 : p.out1) + (int64_t)(m & 63) * p.s_m;
+    const uint32_t src = tmem_addr(tmem, warp * 32, 0);
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t v[32];
+      tmem_ld32(src + c * 32, v);
+      tmem_ld_wait();
+      if (m < p.m_valid) {
+        float* ob = base + p.blk_off[c >> 1] + (int64_t)((c & 1) * 32) * p.s_n;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(ob + (int64_t)j * p.s_n, __uint_as_float(v[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // the peer's tensor memory is still read until here
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
 // ========================================================================================== block_bwd
 struct BwdSmem {
   static constexpr uint32_t A0 = 0, A1 = TILE, W0 = 2 * TILE, W1 = 3 * TILE, DX = 4 * TILE, WDT = 5 * TILE, TOTAL = 5 * TILE + 8192;
@@ -1206,7 +1359,23 @@ int launch_gemm_tn(int NB, const GemmTnMaps& m, const GemmTnParams& p, cudaStrea
   }
   const dim3 grid((unsigned)gx, (unsigned)gy);
   WN_PROF(p.tag ? p.tag : "gemm_tn", s);
-  if (NB == 4) {
+  if (NB == 4 && p.y_layers > 0 && p.m_valid == 128 && getenv("WN_TN_PAIR")) {
+    // CTA pairs (cluster 2 x 1, cta_group::2): see gemm_tn_pair_kernel.  Correct (gradient tests pass with WN_TN_PAIR=1) but measured
+    // 5-7 % slower than two independent CTAs on these shapes (dW_skip 0.33 vs 0.32 ms, head 0.26 vs 0.25 ms), so it is opt-in.
+    static bool once = false;
+    const int smem = TnPairCfg::TOTAL + 1024;
+    if (!once) { WN_PROPAGATE(set_smem(gemm_tn_pair_kernel, smem)); once = true; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (unsigned)gx, (unsigned)gy / 2); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_on() ? 2 : 1;
+    WN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tn_pair_kernel, m.a, m.b[0], m.b[1], p));
+  } else if (NB == 4) {
     static bool once = false;
     const int smem = TnCfg<4>::TOTAL + 1024;
     if (!once) { WN_PROPAGATE(set_smem(gemm_tn_kernel<4>, smem)); once = true; }
