@@ -342,11 +342,9 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
       const int tau = tau0 + row;
       const bool valid = (tau >= p.s_out) && (tau < p.L);
-      const bool in_range = tau < p.L;
       const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, ab * 192);
       const uint8_t* si = sm + Fwd2Smem::IN + st * Fwd2Smem::IN_STAGE;
       uint8_t* zt = sm + Fwd2Smem::Z + ab * TILE_BYTES;
-      const int64_t grow = ((int64_t)b * p.L + tau) * 64 + cg * 16;          // this thread's 16 channels of row tau
       const bool rec = TRACE && p.ts != nullptr && blockIdx.x == 0 && tid == 0;
       long long* ts = p.ts + (int64_t)it * 8;
       if (rec) ts[0] = clock64();

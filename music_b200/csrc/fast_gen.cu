@@ -105,11 +105,6 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const uint4& a, uint32_t 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
-// B fragment (k16 x n8) of an fp16 [stream][k] shared matrix: lane (n = lane/4, q = lane%4) holds k = 2q,2q+1 and 2q+8,2q+9
-__device__ __forceinline__ void mma_b(float (&c)[4], const uint4& a, const __half* row_k0, int q) {
-  const uint32_t b0 = *reinterpret_cast<const uint32_t*>(row_k0 + 2 * q), b1 = *reinterpret_cast<const uint32_t*>(row_k0 + 2 * q + 8);
-  mma_f16(c, a, b0, b1);
-}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
