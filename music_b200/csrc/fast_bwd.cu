@@ -724,7 +724,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       for (int item = slice; item < n_items; item += n_slices) {
         const int b = item / p.tiles_per_batch, row0 = (p.tile0 + item % p.tiles_per_batch) * 128;
-        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_spin_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = sm + stage * Cfg::STAGE;
         uint8_t* sb = sa + Cfg::A_BYTES;
         mbar_expect_tx(&full[stage], Cfg::STAGE);
@@ -745,7 +745,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (rank != 0) {
         // relay: tell the leader when this CTA's operands of a stage have landed
         for (int item = slice; item < n_items; item += n_slices) {
-          mbar_wait(&full[stage], phase);
+          mbar_spin_wait(&full[stage], phase);
           uint32_t remote;
           asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(&peer_full[stage])));
           asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
@@ -754,8 +754,8 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       } else {
         constexpr uint32_t idn = idesc_bf16(256, 256, 1, 1);
         for (int item = slice; item < n_items; item += n_slices, ++it) {
-          mbar_wait(&full[stage], phase);
-          mbar_wait(&peer_full[stage], phase);
+          mbar_spin_wait(&full[stage], phase);
+          mbar_spin_wait(&peer_full[stage], phase);
           tc_fence_after();
           const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
 #pragma unroll

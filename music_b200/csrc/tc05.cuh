@@ -58,6 +58,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// spin on the non-suspending probe: for single threads whose wake-up latency is on the critical path
+__device__ __forceinline__ void mbar_spin_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_test_wait(bar, parity)) {
+  }
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
