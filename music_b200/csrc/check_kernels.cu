@@ -27,10 +27,28 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(PwArgs a) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   const bool chan_contig = (a.X.sc == 1);
+  // 16-byte path: channel-contiguous input whose rows / batches / base are 4-float aligned, channel counts multiples of 4
+  const bool vec4 = chan_contig && (a.n_in & 3) == 0 && (a.n_out & 3) == 0 && (a.X.st & 3) == 0 && (a.X.sb & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.X.p) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.Wt) & 15) == 0;
   for (int tap = 0; tap < a.n_taps; ++tap) {
     const int off = a.off[tap];
     const float* Wtap = a.Wt + (int64_t)tap * a.n_in * a.n_out;
     for (int k0 = 0; k0 < a.n_in; k0 += TK) {
+      if (vec4) {          // channels-last input and 4-aligned channel counts: one 16-byte load per thread and operand
+        const int kk = (tid & 3) * 4, rr = tid >> 2;               // 64 rows x 16 channels
+        const int tau = row0 + rr, k = k0 + kk, tsrc = tau + off;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tau < a.t1 && k < a.n_in && tsrc >= a.x_lo && tsrc < a.x_hi) {
+          v = *reinterpret_cast<const float4*>(a.X.p + (int64_t)b * a.X.sb + (int64_t)(tsrc + a.X.shift) * a.X.st + k);
+          if (a.x_relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+        }
+        Xs[kk][rr] = v.x; Xs[kk + 1][rr] = v.y; Xs[kk + 2][rr] = v.z; Xs[kk + 3][rr] = v.w;
+        const int cc = (tid & 15) * 4, kw = tid >> 4;               // 16 k-rows x 64 output channels
+        const int kg = k0 + kw, c = col0 + cc;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kg < a.n_in && c < a.n_out) w = *reinterpret_cast<const float4*>(Wtap + (int64_t)kg * a.n_out + c);
+        *reinterpret_cast<float4*>(&Ws[kw][cc]) = w;
+      } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int e = tid + j * 256;
@@ -51,6 +69,7 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(PwArgs a) {
         int cc = e % TN, kk = e / TN;
         int k = k0 + kk, c = col0 + cc;
         Ws[kk][cc] = (k < a.n_in && c < a.n_out) ? Wtap[(int64_t)k * a.n_out + c] : 0.f;
+      }
       }
       __syncthreads();
 #pragma unroll
