@@ -100,3 +100,21 @@ def test_mulaw_round_trips_at_full_size():
     back = mu_law_decode(e)
     width = mu_law_decode(torch.clamp(e + 1, max=255)) - mu_law_decode(torch.clamp(e - 1, min=0))
     assert bool(((back - x).abs() <= width + 1e-6).all())
+
+
+@pytest.mark.parametrize("n", [1, 3, 9])
+def test_generation_ragged_stream_counts_match_the_full_group(n):
+    """The half-precision kernel advances 8 streams per CTA; stream counts that do not fill a group (1, 3) or spill into a second
+    one (9) must give exactly the sequences the same streams produce inside a full launch of 16."""
+    from music_b200.wavenet import fast_generate as FG
+    net = _net()
+    rf = net.receptive_field
+    g = torch.Generator().manual_seed(21)
+    prime = torch.randint(0, 256, (16, rf), generator=g).cuda()
+    with torch.no_grad():
+        first, st, _ = FG._prime(net, prime)
+        full, _ = FG._steps(net, st, first, 200)
+        first_n, st_n, _ = FG._prime(net, prime[:n].contiguous())
+        part, _ = FG._steps(net, st_n, first_n, 200)
+    assert torch.equal(first_n, first[:n])
+    assert torch.equal(part, full[:, :n])
