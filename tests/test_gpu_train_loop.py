@@ -1,0 +1,62 @@
+"""The reference training loop (wavenet/train.py:76-222) through the package's `train()`: JSON configs, loss / store logs in
+the format `wavenet/vis/visualize.py:7-14` parses, checkpoint naming and rotation, resume from the newest checkpoint."""
+import glob
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DIL = [1, 2, 4, 8, 1, 2, 4, 8]
+
+
+def _write_params(base, restore_model, epochs):
+    os.makedirs(os.path.join(base, "params"), exist_ok=True)
+    tp = {"restore_model": restore_model, "restore_dir": base + "/restore/", "log_dir": base + "/log/", "optimizer": "adam",
+          "learning_rate": 1e-3, "momentum": 0.9, "num_epochs": epochs, "print_every": 2, "check_point_every": 1, "max_check_points": 2}
+    wp = {"filter_width": 2, "dilations": DIL, "dilation_channels": 16, "residual_channels": 16, "skip_channels": 32,
+          "quantization_channels": 256, "use_bias": False}
+    for name, obj in (("train_params", tp), ("wavenet_params", wp), ("dataset_params", {})):
+        with open(os.path.join(base, "params", name + ".json"), "w") as f:
+            json.dump(obj, f)
+    return base + "/params/"
+
+
+def _loader(n_batches):
+    rf = sum(DIL) + 2                                       # (filter_width - 1) * sum(dilations) + 2
+    g = torch.Generator().manual_seed(0)
+    W = 40
+    out = []
+    for _ in range(n_batches):
+        idx = torch.randint(0, 256, (2, rf + W), generator=g)
+        piece = torch.nn.functional.one_hot(idx[:, :-1], 256).permute(0, 2, 1).float()      # (B, Q, L) as the reference feeds it
+        out.append({"audio_piece": piece, "audio_target": idx[:, rf:rf + W].contiguous()})
+    return out
+
+
+def test_train_loop_logs_checkpoints_and_resume(tmp_path):
+    from music_b200.wavenet.train import train
+    base = str(tmp_path)
+    params = _write_params(base, "", epochs=3)
+    net = train(base=params, dataloader=_loader(4))
+    assert net is not None
+    lines = open(base + "/log/loss_log.log").read().splitlines()
+    assert len(lines) == 6                                    # 3 epochs x 4 batches / print_every 2
+    assert [int(l.split(' ')[2]) for l in lines] == [2, 4, 6, 8, 10, 12]            # the resume parser of train.py:159-165
+    losses = [float(l.split(' ')[-1]) for l in lines]                              # the parser of vis/visualize.py:7-14
+    assert all(5.0 < x < 5.6 for x in losses)
+    assert lines[0].startswith("Trained over 2 pieces,Average loss is ")
+    store = open(base + "/log/store_log.log").read().splitlines()
+    assert store == ["Epoch 1, model saved!", "Epoch 2, model saved!", "Epoch 3, model saved!"]
+    models = sorted(os.path.basename(p) for p in glob.glob(base + "/restore/*.model"))
+    assert models == ["wavenet2.model", "wavenet3.model"]     # max_check_points = 2: the oldest was rotated out
+    # resume: epoch numbering and the piece counter continue
+    params = _write_params(base, "wavenet3.model", epochs=1)
+    train(base=params, dataloader=_loader(4))
+    lines = open(base + "/log/loss_log.log").read().splitlines()
+    assert [int(l.split(' ')[2]) for l in lines][-2:] == [14, 16]
+    assert open(base + "/log/store_log.log").read().splitlines()[-1] == "Epoch 4, model saved!"
+    models = sorted(os.path.basename(p) for p in glob.glob(base + "/restore/*.model"))
+    assert models == ["wavenet3.model", "wavenet4.model"]
