@@ -72,12 +72,15 @@ def kernel_flops(B):
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu captures
-    (profiles/r1c_traffic.json; bytes cannot be measured live outside a profiler).  None when not captured."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
-        return t["kernels"][kernel]["dram_bytes_per_launch"]
-    except Exception:
-        return None
+    (profiles/r1d_traffic.json, made by tools/traffic_json.py; bytes cannot be measured live outside a profiler).
+    None when not captured."""
+    for name in ("r1d_traffic.json", "r1c_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return t["kernels"][kernel]["dram_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:

@@ -379,15 +379,23 @@ gemm_nt_resb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // staging slot `slot` was stored three tiles ago; thread 0 checked that store before the previous barrier
         uint8_t* ot = sm + Cfg::OUT_OFF + slot * TILE;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(ot + sw128_chunk(tid, q)) = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        for (int q = 0; q < 8; ++q) {     // 16-byte chunk q of this thread's row: swizzled tile, or the tiled global layout's image
+          const uint32_t o = p.out_tiled ? (uint32_t)(((((tid >> 5) * 4 + (q >> 1)) * 32 + (tid & 31)) << 5) + ((q & 1) << 4)) : sw128_chunk(tid, q);
+          *reinterpret_cast<uint4*>(ot + o) = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
         fence_proxy_async_smem();
         if (j == n_otiles - 1) tc_fence_before();
         if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // all but the newest store have left smem
         epi_bar_sync();
         if (tid == 0) {
           if (j == n_otiles - 1) mbar_arrive(&acc_empty[as]);
-          tma_store_3d(&tmOut, ot, p.out_col0 + nt * 256 + 64 * j, row0, b);
+          if (p.out_tiled) {              // the in-range 32-row blocks of this tile are one contiguous run
+            const int rb0 = row0 >> 5, nb = min(4, p.out_nblk - rb0);
+            const int64_t lb = (int64_t)((p.out_col0 + nt * 256) / 64 + j) * p.n_batches + b;
+            if (nb > 0) bulk_store(p.out_tiled + ((lb * p.out_nblk + rb0) << 11), ot, (uint32_t)nb << 12);
+          } else {
+            tma_store_3d(&tmOut, ot, p.out_col0 + nt * 256 + 64 * j, row0, b);
+          }
           tma_store_commit();
         }
         if (++slot == Cfg::OUT_SLOTS) slot = 0;
@@ -1172,7 +1180,290 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// dW = sum over CTAs of the partial tiles written by block_bwd2 (fixed summation order: deterministic)
+// ========================================================================================= block_bwd3
+// EXPERIMENT, opt-in with WN_BWD3=1 (profiles/r1_summary.md, "three-stage block backward").  Same work and warp roles as
+// block_bwd2 with the per-stage dependency loop shortened (a two-stage input ring is refilled only after the
+// weight-gradient MMAs of the tile that held it, so load issue -> arrival -> recompute -> epilogue -> weight gradients
+// runs once per TWO tiles):
+//  * x taps in a THREE-stage ring, dx_{i+1} in its own two-stage ring.  That fits the same 216 KB only if the skip-path
+//    gradient does not pass through shared memory: every epilogue thread reads its 32 bytes straight from global memory
+//    (the producer prefetches the tile into L2 two to three tiles earlier);
+//  * f|g and dz complete on separate barriers and the epilogue does the tanh / sigmoid part, which does not depend on
+//    dz, before it waits for dz - a late dx tile costs only the last 48 FMAs of the tile.
+// Measured at cfg 2: 1.45 ms per step WITHOUT the skip-gradient loads (block_bwd2: 1.65 ms), 1.81 ms with them - one
+// lane per 3840-byte-pitched row means 32 sectors in 32 lines per request, queued behind the bulk loads.  It needs the
+// skip gradient in a layout whose per-warp 1 KB is contiguous: the dZcat GEMM writes that layout when this kernel is on.
+struct Bwd3Smem {
+  static constexpr uint32_t W0 = 0, W1 = TILE, WDT = 2 * TILE;                 // resident weights (40 KB)
+  static constexpr uint32_t NXS = 3, XR = 2 * TILE + 8192, X_STAGE = 2 * TILE; // 3 x {x tap0, x tap1}
+  static constexpr uint32_t DXR = XR + NXS * X_STAGE;                          // 2 x dx_{i+1}
+  static constexpr uint32_t DF = DXR + 2 * TILE, DG = DF + TILE, Z = DG + TILE;
+  static constexpr uint32_t TOTAL = Z + TILE;                                  // 216 KB
+};
+// 32 bytes per thread in one request (256-bit LDG), not allocated in L1; `policy` = L2 eviction hint or 0
+__device__ __forceinline__ void ldg_stream32(const void* ptr, uint64_t policy, uint32_t (&v)[8]) {
+  if (policy)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(ptr), "l"(policy));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(ptr));
+}
+
+template <bool BIAS, bool DENSE>
+__global__ void __launch_bounds__(576, 1)
+block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
+                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_dx,
+                  const __grid_constant__ CUtensorMap tm_wdT, const __grid_constant__ CUtensorMap tm_dfg, BlockBwd2Params pp) {
+  const BlockBwdParams& p = pp.b;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t w_full, x_full[3], x_empty[3], dxi_full[2], dxi_empty[2], fg_full[2], fg_empty[2];
+  __shared__ __align__(8) uint64_t dz_full, dz_empty, out_full, out_empty, wg_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&dxi_full[i], 1);
+      mbar_init(&dxi_empty[i], 1);
+      mbar_init(&fg_full[i], 1);
+      mbar_init(&fg_empty[i], 1);
+    }
+    mbar_init(&dz_full, 1);
+    mbar_init(&dz_empty, 1);
+    mbar_init(&out_full, 1);
+    mbar_init(&out_empty, 1);
+    mbar_init(&wg_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_launch_dependents();      // programmatic dependent launch: see tc05.cuh
+  pdl_wait();
+  const uint32_t sbase = smem_u32(sm);
+  const int n_items = pp.n_batches * p.tiles_per_batch;
+  const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  constexpr uint32_t C_DZ = 256, C_WFG = 320, C_WD = 448;      // TMEM columns as in block_bwd2
+
+  if (warp == 16) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0 && n_mine > 0) {
+      mbar_expect_tx(&w_full, 2 * TILE + (DENSE ? 8192 : 0));
+      tma_load_2d(sm + Bwd3Smem::W0, &tm_w0, &w_full, 0, 0);
+      tma_load_2d(sm + Bwd3Smem::W1, &tm_w1, &w_full, 0, 0);
+      if (DENSE) tma_load_2d(sm + Bwd3Smem::WDT, &tm_wdT, &w_full, 0, 0);
+      int sx = 0, xph = 0;
+      for (int it = 0; it < n_mine; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
+        mbar_wait(&x_empty[sx], xph ^ 1);
+        uint8_t* sxp = sm + Bwd3Smem::XR + sx * Bwd3Smem::X_STAGE;
+        mbar_expect_tx(&x_full[sx], 2 * TILE);
+        tma_load_3d(sxp, &tm_x, &x_full[sx], 0, tau0 - p.d, b, p.pol_first);     // the last read of these rows of x_i
+        tma_load_3d(sxp + TILE, &tm_x, &x_full[sx], 0, tau0, b);
+        // the epilogue reads this tile's skip-path gradient straight from global memory two to three tiles from now
+        if (tau0 >= p.tw_al) {
+          const int rb0 = (tau0 - p.tw_al) >> 5, nb = min(4, p.dzs_nblk - rb0);
+          if (nb > 0) bulk_prefetch_l2(p.dzs + (((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + rb0) << 11), (uint32_t)nb << 12);
+        }
+        if (DENSE) {
+          const int sd = it & 1;
+          mbar_wait(&dxi_empty[sd], ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&dxi_full[sd], TILE);
+          tma_load_3d(sm + Bwd3Smem::DXR + sd * TILE, &tm_dx, &dxi_full[sd], 0, tau0, b);
+        }
+        if (++sx == 3) { sx = 0; xph ^= 1; }
+      }
+    }
+  } else if (warp == 17) {
+    // ------------------------------------------------------------ MMA issuer (polling)
+    if (lane == 0 && n_mine > 0) {
+      constexpr uint32_t id_fg = idesc_bf16(128, 128, 0, 0), id_dz = idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t id_wfg = idesc_bf16(128, 128, 1, 1), id_wd = idesc_bf16(128, 64, 1, 1);
+      mbar_wait(&w_full, 0);
+      int jf = 0, jd = 0, jw = 0;       // next tile for: f|g recompute, dz, weight gradients
+      int sf = 0, fph = 0, sw = 0;      // x-ring stage / phase of tile jf, stage of tile jw
+      while (jw < n_mine) {
+        // (1) dz of tile jd (on the epilogue's critical path): its dx tile has landed, the previous epilogue has drained the accumulator
+        if (DENSE && jd < n_mine && mbar_test_wait(&dz_empty, (jd & 1) ^ 1) && mbar_test_wait(&dxi_full[jd & 1], (jd >> 1) & 1)) {
+          tc_fence_after();
+          const uint32_t sd = sbase + Bwd3Smem::DXR + (jd & 1) * TILE;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd, k), desc_kmajor(sbase + Bwd3Smem::WDT, k), id_dz, k > 0);
+          umma_commit(&dz_full);
+          ++jd;
+          continue;
+        }
+        // (2) weight gradients of tile jw once its epilogue has produced dF | dG | z in shared memory
+        if (jw < jf && mbar_test_wait(&out_full, jw & 1)) {
+          tc_fence_after();
+          const uint32_t sxa = sbase + Bwd3Smem::XR + sw * Bwd3Smem::X_STAGE;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
+            umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd3Smem::DF, k, TILE), desc_mnmajor(sxa, k, TILE), id_wfg, (jw | k) != 0);
+          umma_commit(&x_empty[sw]);
+          if (DENSE) {
+            const uint32_t sd = sbase + Bwd3Smem::DXR + (jw & 1) * TILE;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)   // dW_dense[r, d] += sum_t dx_{i+1}[t, r] * z[t, d]   (rows 64..127 unused)
+              umma_bf16(tmem + C_WD, desc_mnmajor(sd, k, 0), desc_mnmajor(sbase + Bwd3Smem::Z, k, TILE), id_wd, (jw | k) != 0);
+            umma_commit(&dxi_empty[jw & 1]);
+          }
+          umma_commit(&out_empty);
+          ++jw;
+          if (++sw == 3) sw = 0;
+          continue;
+        }
+        // (3) f|g recompute of tile jf into accumulator buffer jf & 1
+        if (jf < n_mine && mbar_test_wait(&x_full[sf], fph) && mbar_test_wait(&fg_empty[jf & 1], ((jf >> 1) & 1) ^ 1)) {
+          tc_fence_after();
+          const uint32_t sxa = sbase + Bwd3Smem::XR + sf * Bwd3Smem::X_STAGE, acc = tmem + (jf & 1) * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa, k), desc_kmajor(sbase + Bwd3Smem::W0, k), id_fg, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa + TILE, k), desc_kmajor(sbase + Bwd3Smem::W1, k), id_fg, true);
+          umma_commit(&fg_full[jf & 1]);
+          ++jf;
+          if (++sf == 3) { sf = 0; fph ^= 1; }
+          continue;
+        }
+      }
+      umma_commit(&wg_done);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps 0-15
+    const int q4 = warp & 3, cg = warp >> 2;          // TMEM lane quarter, 16-column group
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, 0);
+    // (batch row, tile) of this CTA's next work item, stepped without a division per tile
+    int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
+    for (int it = 0; it < n_mine; ++it) {
+      const uint32_t ph = it & 1, ph2 = (it >> 1) & 1;
+      const int tau0 = (p.tile0 + tl) * 128;
+      const int tau = tau0 + row;
+      const bool valid = tau >= p.s_out && tau < p.L;
+      // skip-path gradient of this thread's 16 channels (zero before the last W time steps and past the end of the row):
+      // one 32-byte request per thread, in flight during the gate math
+      uint32_t zs[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      if (tau0 >= p.tw_al && tau < p.L)      // tiled layout (GemmNtParams::out_tiled): this warp's 32 rows x 16 channels are 1 KB contiguous
+        ldg_stream32(p.dzs + (((((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + ((tau0 - p.tw_al) >> 5) + q4) * 4 + cg) * 32 + lane) << 4), p.pol_first, zs);
+      mbar_wait(&fg_full[ph], ph2);
+      tc_fence_after();
+      uint32_t f[16], g[16];
+      tmem_ld16(lane_addr + ph * 128 + cg * 16, f);
+      tmem_ld16(lane_addr + ph * 128 + 64 + cg * 16, g);
+      tmem_ld_wait();
+      // the part of the gate backward that does not need dz: z = t sg, dF = dz * [sg (1 - t^2)], dG = dz * [z (1 - sg)]
+      float ca[16], cb[16];
+      uint32_t pz[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float zo[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float fv = __uint_as_float(f[2 * j + e]), gv = __uint_as_float(g[2 * j + e]);
+          if (BIAS) {
+            fv += p.bias_fg[cg * 16 + 2 * j + e];
+            gv += p.bias_fg[64 + cg * 16 + 2 * j + e];
+          }
+          const float t = tanh_fast(fv), sg = sigmoid_fast(gv);
+          zo[e] = t * sg;
+          ca[2 * j + e] = sg * (1.f - t * t);
+          cb[2 * j + e] = zo[e] * (1.f - sg);
+        }
+        pz[j] = valid ? pack_bf16(zo[0], zo[1]) : 0u;
+      }
+      uint32_t dzv[16];
+      if (DENSE) {
+        mbar_wait(&dz_full, ph);
+        tc_fence_after();
+        tmem_ld16(lane_addr + C_DZ + cg * 16, dzv);
+        tmem_ld_wait();
+      }
+      // (opaque to the compiler: without it the bf16 unpack of the loaded words - and with it the wait for the load - is
+      //  hoisted to the top of the tile)
+      asm volatile("" : "+r"(zs[0]), "+r"(zs[1]), "+r"(zs[2]), "+r"(zs[3]), "+r"(zs[4]), "+r"(zs[5]), "+r"(zs[6]), "+r"(zs[7]));
+      uint32_t pf[8], pg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
+        float dz0 = __low2float(s2), dz1 = __high2float(s2);
+        if (DENSE) {
+          dz0 += __uint_as_float(dzv[2 * j]);
+          dz1 += __uint_as_float(dzv[2 * j + 1]);
+        }
+        pf[j] = valid ? pack_bf16(dz0 * ca[2 * j], dz1 * ca[2 * j + 1]) : 0u;
+        pg[j] = valid ? pack_bf16(dz0 * cb[2 * j], dz1 * cb[2 * j + 1]) : 0u;
+      }
+      // the dF | dG | z tiles may be rewritten once (a) the previous tile's weight-gradient MMAs have read them
+      // (out_empty) and (b) its TMA stores have read them (thread 0 checks the bulk group, the barrier publishes it)
+      if (it > 0) mbar_wait(&out_empty, ph ^ 1);
+      tc_fence_before();
+      if (tid == 0) tma_store_wait_read();
+      epi8_bar_sync();                     // also: every thread has drained this tile's TMEM accumulators
+      if (tid == 0) {
+        mbar_arrive(&fg_empty[ph]);
+        mbar_arrive(&dz_empty);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t o = sw128_chunk(row, cg * 2 + q);
+        *reinterpret_cast<uint4*>(sm + Bwd3Smem::Z + o) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DF + o) = make_uint4(pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DG + o) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
+      }
+      fence_proxy_async_smem();
+      epi8_bar_sync();
+      if (tid == 0) {
+        mbar_arrive(&out_full);
+        tma_store_3d(&tm_dfg, sm + Bwd3Smem::DF, 0, tau0, b, p.pol_last);          // read by the dx GEMM that follows
+        tma_store_3d(&tm_dfg, sm + Bwd3Smem::DG, 64, tau0, b, p.pol_last);
+        tma_store_commit();                // checked one phase later (above), nobody waits here
+      }
+      tl += (int)gridDim.x;
+      while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
+    }
+    if (tid == 0) tma_store_wait_read();
+    // ---- flush the weight-gradient accumulators as a per-CTA partial tile [128][192] (see block_bwd2)
+    {
+      float* prow = pp.partial + ((int64_t)blockIdx.x * 128 + row) * 192;
+      if (n_mine > 0) {
+        mbar_wait(&wg_done, 0);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(lane_addr + C_WFG + cg * 32, v);         // dW_fg columns [32 cg, 32 cg + 32)
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(prow + cg * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        uint32_t u[16];
+        if (DENSE) {
+          tmem_ld16(lane_addr + C_WD + cg * 16, u);        // dW_dense columns [16 cg, 16 cg + 16)
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) u[j] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(prow + 128 + cg * 16 + q * 4) = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// dW = sum over CTAs of the partial tiles written by block_bwd2 / block_bwd3 (fixed summation order: deterministic)
 struct WgradReduceArgs {
   int64_t filt0, gate0, dense0, layer_stride;     // flat-vector offsets of layer 0's filter / gate / dense weights
   int n_layers;
@@ -1414,6 +1705,17 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   if (n_items <= 0) return WN_OK;
   const int n_ctas = std::min(n_items, g_sm_count);
   const bool bias = p.b.bias_fg != nullptr, dense = p.b.has_dense != 0;
+  const bool three_stage = p.b.dzs_nblk > 0;      // the caller chose the tiled skip-gradient layout (bwd3_enabled)
+  if (three_stage) {
+    auto k3 = bias ? (dense ? block_bwd3_kernel<true, true> : block_bwd3_kernel<true, false>)
+                   : (dense ? block_bwd3_kernel<false, true> : block_bwd3_kernel<false, false>);
+    const int smem3 = Bwd3Smem::TOTAL + 1024;
+    WN_PROPAGATE(set_smem_once(k3, smem3));
+    WN_PROF("block_bwd2", s);
+    WN_CHECK_CUDA(launch_pdl(k3, dim3((unsigned)n_ctas), dim3(576), smem3, s, m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p));
+    WN_CHECK_LAUNCH();
+    return WN_OK;
+  }
   auto k = bias ? (dense ? block_bwd2_kernel<true, true> : block_bwd2_kernel<true, false>)
                 : (dense ? block_bwd2_kernel<false, true> : block_bwd2_kernel<false, false>);
   WN_PROPAGATE(set_smem_once(k, smem));
@@ -1467,6 +1769,11 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   const uint8_t* P = reinterpret_cast<const uint8_t*>(d_packed);
   uint8_t* Wp = reinterpret_cast<uint8_t*>(d_ws);
   const bool bias = m.use_bias != 0;
+  static const bool unfused_env = [] { const char* e = getenv("WN_BWD_UNFUSED"); return e && e[0] == '1'; }();
+  const bool fused = !unfused_env;       // block_bwd2 / block_bwd3: weight gradients accumulated inside the block kernel
+  // WN_BWD3=0 selects block_bwd2; default: three-stage block backward kernel, which reads the skip-path gradient from the tiled layout (GemmNtParams::out_tiled)
+  static const bool bwd3_env = [] { const char* e = getenv("WN_BWD3"); return !(e && e[0] == '0'); }();
+  const bool dz_tiled = bwd3_env && fused && !getenv("WN_NT_STREAM");
   WN_CHECK_CUDA(cudaMemsetAsync(G, 0, (size_t)m.n_params * sizeof(float), s));
   WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXa, 0, (size_t)B * L * 64 * 2, s));
   WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXb, 0, (size_t)B * L * 64 * 2, s));
@@ -1526,6 +1833,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     GemmNtMaps gm{};
     gm.a[0] = M.dsk; gm.a[1] = M.dsk; gm.b[0] = M.wsTcat; gm.b[1] = M.wsTcat; gm.out = M.dzcat;
     GemmNtParams gp{};
+    if (dz_tiled) { gp.out_tiled = reinterpret_cast<__nv_bfloat16*>(Wp + wl.DZcat); gp.out_nblk = (int)ceil_div(Wpad, 32); }
     gp.n_batches = B; gp.tile0 = 0; gp.tiles_per_batch = skip_tiles; gp.n_ntiles = (int)ceil_div(64 * N, 256); gp.n_total = 64 * N;
     gp.nk[0] = 4; gp.nk[1] = 0; gp.epi = EPI_PLAIN; gp.row_lo = 0; gp.row_hi = Wpad; gp.tag = "gemm_nt_dZcat";
     WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
@@ -1546,12 +1854,6 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     WN_DEBUG_SYNC("gemm_tn dWs", s);
   }
   // ---- residual blocks, last to first
-  static int unfused_env = -1;
-  if (unfused_env < 0) {
-    const char* e = getenv("WN_BWD_UNFUSED");
-    unfused_env = (e && e[0] == '1') ? 1 : 0;
-  }
-  const bool fused = unfused_env == 0;   // block_bwd2: weight gradients accumulated inside the block kernel
   // side stream for the per-layer reductions of the weight-gradient partial tiles (WN_WGRAD_SIDE=0: one reduction at the end)
   static cudaStream_t side = nullptr;
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1587,6 +1889,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       bp.L = L; bp.d = d; bp.s_out = s_out; bp.tile0 = tile0; bp.tiles_per_batch = tpb; bp.has_dense = has_dense;
       bp.tw0 = L - W; bp.tw_al = tw_al; bp.Wp = Wpad;
       bp.dzs = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DZcat); bp.dzs_pitch = 64 * N; bp.dzs_col = 64 * i;
+      if (dz_tiled) { bp.dzs_lb0 = i * B; bp.dzs_nblk = (int)ceil_div(Wpad, 32); }
       bp.bias_fg = bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
       if (l2_hints_on()) { bp.pol_first = kL2EvictFirst; bp.pol_last = kL2EvictLast; }
       if (fused) {

@@ -30,6 +30,10 @@ struct GemmNtParams {
   int row_lo, row_hi;           // rows outside are written as zeros
   unsigned long long pol_a[2];  // L2 eviction hint of the A loads of each segment (0: none)
   unsigned long long pol_out;   // ... of the output stores
+  // resident-B kernel only: write OUT in the tiled skip-gradient layout instead (block_bwd3 reads it):
+  // [column block of 64 * n_batches + b][row / 32][column group of 16][row % 32][16 columns], out_nblk 32-row blocks per batch row
+  __nv_bfloat16* out_tiled;
+  int out_nblk;
   const char* tag;              // profiler label (host only)
 };
 int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStream_t s);
@@ -76,6 +80,7 @@ struct BlockBwdParams {
   int tw0, tw_al, Wp;
   const __nv_bfloat16* dzs;     // [B*Wp][dzs_pitch], this layer's 64 columns start at dzs_col
   int dzs_pitch, dzs_col;
+  int dzs_lb0, dzs_nblk;        // block_bwd3 (tiled dZcat): layer * B, 32-row blocks per batch row
   const float* bias_fg;
   unsigned long long pol_first, pol_last;   // L2 eviction hints (0: none)
 };

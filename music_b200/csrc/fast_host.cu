@@ -28,12 +28,13 @@ int fast_init() {
   return WN_OK;
 }
 
-// bf16 tensor map, rank 2 or 3, innermost box = 64 elements (128 B) with 128B swizzle
+// bf16 tensor map, rank 2..5, 128B swizzle (innermost box = 64 elements = 128 B, or a 128-byte row split over two dims)
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box) {
   WN_REQUIRE(g_encode, WN_ERR_UNSUPPORTED, "fast path not initialised (wn_init)");
-  cuuint64_t gd[3], gs[2];
-  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  WN_REQUIRE(rank >= 2 && rank <= 5, WN_ERR_INVALID, "tensor map rank %d", rank);
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) {
     gd[i] = dims[i];
     bx[i] = box[i];
@@ -268,7 +269,7 @@ WsLayout ws_layout(const Model& m, int B, int L) {
   w.DLG = take((size_t)B * W * 256 * 2);
   w.DH1 = take((size_t)B * W * 256 * 2);
   w.DSK = take((size_t)B * W * 256 * 2);
-  w.DZcat = take((size_t)B * W * 64 * N * 2);
+  w.DZcat = take((size_t)B * align_up((size_t)W, 32) * 64 * N * 2);      // (rows padded to 32 for the tiled layout)
   w.DXa = take((size_t)B * L * 64 * 2);
   w.DXb = take((size_t)B * L * 64 * 2);
   w.DFG = take((size_t)B * L * 128 * 2);
