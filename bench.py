@@ -377,16 +377,21 @@ def main():
     last_loss = float(loss)
 
     # ---------------- end to end through the public API with host buffers (`e2e`)
-    d_piece = torch.empty_like(pieces[0])
-    d_target = torch.empty_like(targets[0])
+    # Every step's batch is copied from pinned host memory inside the timed region (K copies for K steps) and its loss
+    # is read back; the package's BatchStager puts the copy of batch i + 1 on a copy stream under step i.
+    from music_b200.wavenet.train import BatchStager
+    stager = BatchStager(dev)
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
+    stager.put(host_pieces[0], host_targets[0])
     for i in range(K):
-        d_piece.copy_(host_pieces[i % n_batches], non_blocking=True)
-        d_target.copy_(host_targets[i % n_batches], non_blocking=True)
+        d_piece, d_target = stager.get()
+        if i + 1 < K:
+            stager.put(host_pieces[(i + 1) % n_batches], host_targets[(i + 1) % n_batches])
         l = trainer.step(d_piece, d_target)
+        stager.done()
         loss_host.copy_(l, non_blocking=True)
     e3.record()
     barrier()

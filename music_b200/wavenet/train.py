@@ -172,6 +172,58 @@ class Trainer:
         return loss
 
 
+class BatchStager:
+    """Host -> device staging of (audio_piece, audio_target) batches under the running train step: two device slots,
+    copies on their own stream, so the copy of batch i + 1 overlaps step i (what `pin_memory=True` + `.cuda(non_blocking)`
+    in the reference loop, train.py:186-194, is after - there the copy sits in the compute stream and serialises).
+
+        stager.put(piece, target)          # start the copy of the next batch (pinned host tensors copy asynchronously)
+        piece_d, target_d = stager.get()   # the compute stream waits for that copy
+        ... trainer.step(piece_d, target_d) ...
+        stager.done()                      # the step that used the oldest slot has been enqueued: the slot may be refilled
+    """
+
+    def __init__(self, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.slots = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [None, None]
+        self.n_put = self.n_get = self.n_done = 0
+
+    def put(self, piece, target):
+        if self.n_put - self.n_done >= 2:
+            raise L.WavenetB200Error("BatchStager: both slots are in use (call done() after the step that consumed a batch)")
+        i = self.n_put % 2
+        slot = self.slots[i]
+        if slot is None or slot[0].shape != piece.shape or slot[1].shape != target.shape or slot[0].dtype != piece.dtype:
+            slot = self.slots[i] = (torch.empty(piece.shape, dtype=piece.dtype, device=self.device),
+                                    torch.empty(target.shape, dtype=target.dtype, device=self.device))
+            self.free[i] = None
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[i] is not None:
+                self.copy_stream.wait_event(self.free[i])     # the step that read this slot two batches ago
+            slot[0].copy_(piece, non_blocking=True)
+            slot[1].copy_(target, non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+        self.n_put += 1
+
+    def get(self):
+        if self.n_get >= self.n_put:
+            raise L.WavenetB200Error("BatchStager: get() without a staged batch")
+        i = self.n_get % 2
+        torch.cuda.current_stream(self.device).wait_event(self.ready[i])
+        self.n_get += 1
+        return self.slots[i]
+
+    def done(self):
+        i = self.n_done % 2
+        if self.free[i] is None:
+            self.free[i] = torch.cuda.Event()
+        self.free[i].record(torch.cuda.current_stream(self.device))
+        self.n_done += 1
+
+
 def train(base='./params/', dataloader=None, rank=0):
     """The reference loop (train.py:76-222): JSON configs, resume, loss / store logs, checkpoint
     rotation.  One process per GPU; launch under torchrun for data parallelism."""
@@ -202,11 +254,19 @@ def train(base='./params/', dataloader=None, rank=0):
         lines = f.readlines()
         num_trained = int(lines[-1].split(' ')[2]) if len(lines) > 0 else 0
     total_loss = torch.zeros(1, device="cuda")
+    stager = BatchStager()
     for epoch in range(train_params["num_epochs"]):
-        for i_batch, sampled_batch in enumerate(dataloader):
-            piece = sampled_batch["audio_piece"].cuda(non_blocking=True)
-            target = sampled_batch["audio_target"].cuda(non_blocking=True)
+        batches = iter(dataloader)
+        nxt = next(batches, None)
+        if nxt is not None:
+            stager.put(nxt["audio_piece"], nxt["audio_target"])
+        while nxt is not None:
+            piece, target = stager.get()
+            nxt = next(batches, None)
+            if nxt is not None:                                # staged under the step below
+                stager.put(nxt["audio_piece"], nxt["audio_target"])
             total_loss += trainer.step(piece, target)         # accumulated on device: no per-step sync
+            stager.done()
             num_trained += 1
             if num_trained % train_params["print_every"] == 0:
                 avg_loss = float(total_loss) / train_params["print_every"]

@@ -60,3 +60,35 @@ def test_train_loop_logs_checkpoints_and_resume(tmp_path):
     assert open(base + "/log/store_log.log").read().splitlines()[-1] == "Epoch 4, model saved!"
     models = sorted(os.path.basename(p) for p in glob.glob(base + "/restore/*.model"))
     assert models == ["wavenet3.model", "wavenet4.model"]
+
+
+def test_batch_stager_orders_copies_and_slot_reuse():
+    """Host batches staged on the copy stream arrive intact and in order while the compute stream is busy, a slot is
+    refilled only after the step that read it (done()), and misuse is reported."""
+    from music_b200 import _lib as L
+    from music_b200.wavenet.train import BatchStager
+    g = torch.Generator().manual_seed(3)
+    host = [(torch.randint(0, 256, (4, 5000), generator=g).pin_memory(), torch.randint(0, 256, (4, 4000), generator=g).pin_memory())
+            for _ in range(7)]
+    st = BatchStager()
+    with pytest.raises(L.WavenetB200Error):
+        st.get()
+    sums = []
+    busy = torch.randn(2048, 2048, device="cuda")
+    st.put(*host[0])
+    for i in range(len(host)):
+        p, t = st.get()
+        if i + 1 < len(host):
+            st.put(*host[i + 1])
+        for _ in range(3):
+            busy = busy @ busy * 1e-3                # keeps the compute stream behind the copy stream
+        sums.append((p.sum() + (busy[0, 0] * 0).long(), t.sum(), p.clone(), t.clone()))
+        st.done()
+    torch.cuda.synchronize()
+    for (ps, ts, pc, tc_), (hp, ht) in zip(sums, host):
+        assert int(ps) == int(hp.sum()) and int(ts) == int(ht.sum())
+        assert torch.equal(pc.cpu(), hp) and torch.equal(tc_.cpu(), ht)
+    st.put(*host[0])
+    st.put(*host[1])
+    with pytest.raises(L.WavenetB200Error):
+        st.put(*host[2])
