@@ -213,10 +213,11 @@ int launch_block_fwd(const BlockFwdMaps& m, const BlockFwdParams& p, int n_ctas,
 // ====================================================================================== block (persistent)
 // 18 warps: 0-15 epilogue (4 per TMEM lane quarter, 16 columns each), 16 TMA producer, 17 MMA issuer.
 // TMEM: two accumulator buffers {f|g: 128 cols, dense: 64 cols}; UMMA #1 of tile n+1/n+2 overlaps the epilogues of tile n.
-// Shared memory: resident weights, THREE input stages {x tap0, x tap1}, two z tiles (A operand of UMMA #2).
-// Outputs (x_{i+1} hi / lo, z) go from registers straight to global memory and `lo` is read from global at the top of
-// the tile, so there is no TMA store to wait for; the MMA issuer polls its two job queues (UMMA #2 of tile j2, UMMA #1
-// of tile j1) and never blocks on one while the other is ready.  History (clock64 instrumentation, profiles/): the first
+// Shared memory: resident weights, THREE input stages {x tap0, x tap1}, two z tiles (A operand of UMMA #2 and source of
+// the Zcat store), one staging tile for x_{i+1} hi and two lo tiles (TMA-loaded, lo' written in place).  The TMA stores of
+// a tile are checked one epilogue phase later, just before their staging tiles are rewritten, so nobody waits for them;
+// the MMA issuer polls its two job queues (UMMA #2 of tile j2, UMMA #1 of tile j1) and never blocks on one while the
+// other is ready.  History (clock64 instrumentation, profiles/): the first
 // persistent version spent, per 6800-cycle tile, 1250 cycles with all threads waiting for the TMA store to drain and
 // 2000 waiting for UMMA #2 queued behind the next tile's UMMA #1 in the in-order tensor pipe.
 namespace {
