@@ -1181,18 +1181,18 @@ block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 }
 
 // ========================================================================================= block_bwd3
-// EXPERIMENT, opt-in with WN_BWD3=1 (profiles/r1_summary.md, "three-stage block backward").  Same work and warp roles as
-// block_bwd2 with the per-stage dependency loop shortened (a two-stage input ring is refilled only after the
-// weight-gradient MMAs of the tile that held it, so load issue -> arrival -> recompute -> epilogue -> weight gradients
-// runs once per TWO tiles):
-//  * x taps in a THREE-stage ring, dx_{i+1} in its own two-stage ring.  That fits the same 216 KB only if the skip-path
-//    gradient does not pass through shared memory: every epilogue thread reads its 32 bytes straight from global memory
-//    (the producer prefetches the tile into L2 two to three tiles earlier);
+// The default block backward (WN_BWD3=0 selects block_bwd2; history and numbers: profiles/r1_summary.md, "r1d").  Same work
+// and warp roles as block_bwd2 with the per-stage dependency loop shortened - there a two-stage input ring is refilled only
+// after the weight-gradient MMAs of the tile that held it, so load issue -> arrival -> recompute -> epilogue -> weight
+// gradients runs once per TWO tiles:
+//  * x taps in a THREE-stage ring, dx_{i+1} in its own two-stage ring.  That fits the same 216 KB because the skip-path
+//    gradient does not pass through shared memory: the dZcat GEMM writes it in a tiled layout (GemmNtParams::out_tiled)
+//    in which the 32 rows x 16 channels of one epilogue warp are 1 KB contiguous, the producer prefetches the 16 KB tile
+//    into L2 two to three tiles ahead and every epilogue thread reads its 32 bytes with one 256-bit load.  (From the
+//    row-major dZcat the same loads - one lane per 3840-byte-pitched row, 32 lines per request - cost 0.3-0.6 ms per step.)
 //  * f|g and dz complete on separate barriers and the epilogue does the tanh / sigmoid part, which does not depend on
 //    dz, before it waits for dz - a late dx tile costs only the last 48 FMAs of the tile.
-// Measured at cfg 2: 1.45 ms per step WITHOUT the skip-gradient loads (block_bwd2: 1.65 ms), 1.81 ms with them - one
-// lane per 3840-byte-pitched row means 32 sectors in 32 lines per request, queued behind the bulk loads.  It needs the
-// skip gradient in a layout whose per-warp 1 KB is contiguous: the dZcat GEMM writes that layout when this kernel is on.
+// Measured at cfg 2: 1.56-1.60 ms per step (block_bwd2: 1.65-1.72 ms; 1.45 ms without the skip-gradient loads).
 struct Bwd3Smem {
   static constexpr uint32_t W0 = 0, W1 = TILE, WDT = 2 * TILE;                 // resident weights (40 KB)
   static constexpr uint32_t NXS = 3, XR = 2 * TILE + 8192, X_STAGE = 2 * TILE; // 3 x {x tap0, x tap1}
