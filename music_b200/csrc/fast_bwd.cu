@@ -8,6 +8,8 @@
 //                       their partial sum in TMEM and flush it once with fp32 atomics.
 //  block_bwd_kernel   : per residual block: recompute [f|g] (UMMA), dz = dx_{i+1} Wd (UMMA) + dzs,
 //                       gate backward in the epilogue -> dFG and z tiles (TMA stores).
+//  block_bwd2 / block_bwd3_kernel : persistent versions that also accumulate the block's weight gradients in TMEM
+//                       (block_bwd3, three-stage input ring + tiled skip gradient, is the one that runs by default).
 #include <stdlib.h>
 
 #include "check_kernels.cuh"
