@@ -1465,6 +1465,297 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// ========================================================================================= block_bwd4
+// DRAFT for the next round, opt-in with WN_BWD4=1 - written after the GPU budget of round 1 was spent: it compiles, it has
+// NOT run on hardware yet (first run: under `timeout`, tests/test_gpu_fast.py, then tools/ab_bwd3.sh).
+// block_bwd3 with the 16 epilogue warps split into TWO GROUPS of 8 that take alternate tiles, so that the gate math of tile
+// n + 1 (MUFU-bound, ~1000 cycles) runs under the shared-memory hand-over + weight-gradient MMAs of tile n instead of after
+// them (profiles/r1_summary.md, r1d: no single wait dominates block_bwd3; all 16 warps are in the same phase at the same
+// time, ~5300 cycles per tile against a tensor-pipe need of 1624).  What is shared and how it is sequenced:
+//  * f|g TMEM buffer g belongs to group g (tile parity); the single dz accumulator is passed from tile to tile through
+//    dz_full / dz_empty exactly as before - dz(n + 1) is needed about one tile period after dz(n) has been read;
+//  * the dF | dG | z staging tiles stay single: tile n + 1 is written when `stage_free` says that the weight-gradient MMAs
+//    AND the TMA store of tile n have read them (two arrivals: tcgen05.commit and the store thread);
+//  * a bulk group belongs to the thread that committed it, so the stores are issued and checked by one thread of an extra
+//    warp (18) that follows out_full, not by the epilogue leaders (whose successor on the staging tiles is the other group);
+//  * every thread owns 32 rows x 32 columns of a tile as two passes of 16 columns; the packed results of the first pass
+//    (24 registers) are held across the second because the staging tiles are still being read at that time.
+template <bool BIAS, bool DENSE>
+__global__ void __launch_bounds__(608, 1)
+block_bwd4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
+                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_dx,
+                  const __grid_constant__ CUtensorMap tm_wdT, const __grid_constant__ CUtensorMap tm_dfg, BlockBwd2Params pp) {
+  const BlockBwdParams& p = pp.b;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t w_full, x_full[3], x_empty[3], dxi_full[2], dxi_empty[2], fg_full[2], fg_empty[2];
+  __shared__ __align__(8) uint64_t dz_full, dz_empty, out_full, stage_free, wg_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&dxi_full[i], 1);
+      mbar_init(&dxi_empty[i], 1);
+      mbar_init(&fg_full[i], 1);
+      mbar_init(&fg_empty[i], 1);
+    }
+    mbar_init(&dz_full, 1);
+    mbar_init(&dz_empty, 1);
+    mbar_init(&out_full, 1);
+    mbar_init(&stage_free, 2);          // weight-gradient MMAs (tcgen05.commit) + TMA store (store thread)
+    mbar_init(&wg_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t sbase = smem_u32(sm);
+  const int n_items = pp.n_batches * p.tiles_per_batch;
+  const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  constexpr uint32_t C_DZ = 256, C_WFG = 320, C_WD = 448;      // TMEM columns as in block_bwd2
+
+  if (warp == 16) {
+    // ------------------------------------------------------------ TMA producer (as block_bwd3)
+    if (lane == 0 && n_mine > 0) {
+      mbar_expect_tx(&w_full, 2 * TILE + (DENSE ? 8192 : 0));
+      tma_load_2d(sm + Bwd3Smem::W0, &tm_w0, &w_full, 0, 0);
+      tma_load_2d(sm + Bwd3Smem::W1, &tm_w1, &w_full, 0, 0);
+      if (DENSE) tma_load_2d(sm + Bwd3Smem::WDT, &tm_wdT, &w_full, 0, 0);
+      int sx = 0, xph = 0;
+      for (int it = 0; it < n_mine; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
+        mbar_wait(&x_empty[sx], xph ^ 1);
+        uint8_t* sxp = sm + Bwd3Smem::XR + sx * Bwd3Smem::X_STAGE;
+        mbar_expect_tx(&x_full[sx], 2 * TILE);
+        tma_load_3d(sxp, &tm_x, &x_full[sx], 0, tau0 - p.d, b, p.pol_first);
+        tma_load_3d(sxp + TILE, &tm_x, &x_full[sx], 0, tau0, b);
+        if (tau0 >= p.tw_al) {
+          const int rb0 = (tau0 - p.tw_al) >> 5, nb = min(4, p.dzs_nblk - rb0);
+          if (nb > 0) bulk_prefetch_l2(p.dzs + (((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + rb0) << 11), (uint32_t)nb << 12);
+        }
+        if (DENSE) {
+          const int sd = it & 1;
+          mbar_wait(&dxi_empty[sd], ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&dxi_full[sd], TILE);
+          tma_load_3d(sm + Bwd3Smem::DXR + sd * TILE, &tm_dx, &dxi_full[sd], 0, tau0, b);
+        }
+        if (++sx == 3) { sx = 0; xph ^= 1; }
+      }
+    }
+  } else if (warp == 17) {
+    // ------------------------------------------------------------ MMA issuer (as block_bwd3; stage_free instead of out_empty)
+    if (lane == 0 && n_mine > 0) {
+      constexpr uint32_t id_fg = idesc_bf16(128, 128, 0, 0), id_dz = idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t id_wfg = idesc_bf16(128, 128, 1, 1), id_wd = idesc_bf16(128, 64, 1, 1);
+      mbar_wait(&w_full, 0);
+      int jf = 0, jd = 0, jw = 0;
+      int sf = 0, fph = 0, sw = 0;
+      while (jw < n_mine) {
+        if (DENSE && jd < n_mine && mbar_test_wait(&dz_empty, (jd & 1) ^ 1) && mbar_test_wait(&dxi_full[jd & 1], (jd >> 1) & 1)) {
+          tc_fence_after();
+          const uint32_t sd = sbase + Bwd3Smem::DXR + (jd & 1) * TILE;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd, k), desc_kmajor(sbase + Bwd3Smem::WDT, k), id_dz, k > 0);
+          umma_commit(&dz_full);
+          ++jd;
+          continue;
+        }
+        if (jw < jf && mbar_test_wait(&out_full, jw & 1)) {
+          tc_fence_after();
+          const uint32_t sxa = sbase + Bwd3Smem::XR + sw * Bwd3Smem::X_STAGE;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd3Smem::DF, k, TILE), desc_mnmajor(sxa, k, TILE), id_wfg, (jw | k) != 0);
+          umma_commit(&x_empty[sw]);
+          if (DENSE) {
+            const uint32_t sd = sbase + Bwd3Smem::DXR + (jw & 1) * TILE;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem + C_WD, desc_mnmajor(sd, k, 0), desc_mnmajor(sbase + Bwd3Smem::Z, k, TILE), id_wd, (jw | k) != 0);
+            umma_commit(&dxi_empty[jw & 1]);
+          }
+          umma_commit(&stage_free);
+          ++jw;
+          if (++sw == 3) sw = 0;
+          continue;
+        }
+        if (jf < n_mine && mbar_test_wait(&x_full[sf], fph) && mbar_test_wait(&fg_empty[jf & 1], ((jf >> 1) & 1) ^ 1)) {
+          tc_fence_after();
+          const uint32_t sxa = sbase + Bwd3Smem::XR + sf * Bwd3Smem::X_STAGE, acc = tmem + (jf & 1) * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa, k), desc_kmajor(sbase + Bwd3Smem::W0, k), id_fg, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa + TILE, k), desc_kmajor(sbase + Bwd3Smem::W1, k), id_fg, true);
+          umma_commit(&fg_full[jf & 1]);
+          ++jf;
+          if (++sf == 3) { sf = 0; fph ^= 1; }
+          continue;
+        }
+      }
+      umma_commit(&wg_done);
+    }
+  } else if (warp == 18) {
+    // ------------------------------------------------------------ store thread: dFG tiles -> global, then frees the staging tiles
+    if (lane == 0 && n_mine > 0) {
+      int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
+      for (int it = 0; it < n_mine; ++it) {
+        const int tau0 = (p.tile0 + tl) * 128;
+        mbar_wait(&out_full, it & 1);
+        tma_store_3d(&tm_dfg, sm + Bwd3Smem::DF, 0, tau0, b, p.pol_last);
+        tma_store_3d(&tm_dfg, sm + Bwd3Smem::DG, 64, tau0, b, p.pol_last);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&stage_free);
+        tl += (int)gridDim.x;
+        while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: group g = warps 8g .. 8g+7, tiles it = g, g+2, ...
+    const int g = warp >> 3, q4 = warp & 3, h = (warp >> 2) & 1;      // TMEM lane quarter (= warp % 4), 32-column half
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, 0);
+    const bool leader = (tid & 255) == 0;
+    auto group_bar = [&]() {
+      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
+    };
+    int b = 0, tl = (int)blockIdx.x + g * (int)gridDim.x;            // this group's first tile, then every second one of the CTA
+    while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
+    for (int it = g; it < n_mine; it += 2) {
+      const uint32_t ph2 = (it >> 1) & 1;
+      const int tau0 = (p.tile0 + tl) * 128;
+      const int tau = tau0 + row;
+      const bool valid = tau >= p.s_out && tau < p.L;
+      const bool has_zs = tau0 >= p.tw_al && tau < p.L;
+      const __nv_bfloat16* zsp =
+          p.dzs + (((((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + ((tau0 - p.tw_al) >> 5) + q4) * 4 + h * 2) * 32 + lane) << 4);
+      uint32_t keep[24];                       // packed z | dF | dG of the first pass
+      uint32_t pz[8], pf[8], pg[8];
+#pragma unroll
+      for (int ps = 0; ps < 2; ++ps) {
+        const int c0 = h * 32 + ps * 16;       // first of this pass's 16 columns
+        uint32_t zs[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (has_zs) ldg_stream32(zsp + ps * 512, p.pol_first, zs);      // next column group of 16: + 32 rows x 16 channels
+        if (ps == 0) {
+          mbar_wait(&fg_full[g], ph2);
+          tc_fence_after();
+        }
+        uint32_t f[16], gq[16];
+        tmem_ld16(lane_addr + g * 128 + c0, f);
+        tmem_ld16(lane_addr + g * 128 + 64 + c0, gq);
+        tmem_ld_wait();
+        float ca[16], cb[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float zo[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float fv = __uint_as_float(f[2 * j + e]), gv = __uint_as_float(gq[2 * j + e]);
+            if (BIAS) {
+              fv += p.bias_fg[c0 + 2 * j + e];
+              gv += p.bias_fg[64 + c0 + 2 * j + e];
+            }
+            const float t = tanh_fast(fv), sg = sigmoid_fast(gv);
+            zo[e] = t * sg;
+            ca[2 * j + e] = sg * (1.f - t * t);
+            cb[2 * j + e] = zo[e] * (1.f - sg);
+          }
+          pz[j] = valid ? pack_bf16(zo[0], zo[1]) : 0u;
+        }
+        uint32_t dzv[16];
+        if (DENSE) {
+          if (ps == 0) {
+            mbar_wait(&dz_full, it & 1);
+            tc_fence_after();
+          }
+          tmem_ld16(lane_addr + C_DZ + c0, dzv);
+          tmem_ld_wait();
+        }
+        asm volatile("" : "+r"(zs[0]), "+r"(zs[1]), "+r"(zs[2]), "+r"(zs[3]), "+r"(zs[4]), "+r"(zs[5]), "+r"(zs[6]), "+r"(zs[7]));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
+          float dz0 = __low2float(s2), dz1 = __high2float(s2);
+          if (DENSE) {
+            dz0 += __uint_as_float(dzv[2 * j]);
+            dz1 += __uint_as_float(dzv[2 * j + 1]);
+          }
+          pf[j] = valid ? pack_bf16(dz0 * ca[2 * j], dz1 * ca[2 * j + 1]) : 0u;
+          pg[j] = valid ? pack_bf16(dz0 * cb[2 * j], dz1 * cb[2 * j + 1]) : 0u;
+        }
+        if (ps == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { keep[j] = pz[j]; keep[8 + j] = pf[j]; keep[16 + j] = pg[j]; }
+        }
+      }
+      // every thread of the group has drained this tile's accumulators: release them, then wait for the staging tiles
+      tc_fence_before();
+      group_bar();
+      if (leader) {
+        mbar_arrive(&fg_empty[g]);
+        mbar_arrive(&dz_empty);
+      }
+      if (it > 0) mbar_wait(&stage_free, (it - 1) & 1);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t o0 = sw128_chunk(row, h * 4 + q), o1 = sw128_chunk(row, h * 4 + 2 + q);
+        *reinterpret_cast<uint4*>(sm + Bwd3Smem::Z + o0) = make_uint4(keep[4 * q], keep[4 * q + 1], keep[4 * q + 2], keep[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DF + o0) = make_uint4(keep[8 + 4 * q], keep[9 + 4 * q], keep[10 + 4 * q], keep[11 + 4 * q]);
+        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DG + o0) = make_uint4(keep[16 + 4 * q], keep[17 + 4 * q], keep[18 + 4 * q], keep[19 + 4 * q]);
+        *reinterpret_cast<uint4*>(sm + Bwd3Smem::Z + o1) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DF + o1) = make_uint4(pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DG + o1) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
+      }
+      fence_proxy_async_smem();
+      // the group's 8 warps together wrote the whole [128][64] tile of each of z, dF, dG
+      group_bar();
+      if (leader) mbar_arrive(&out_full);
+      tl += 2 * (int)gridDim.x;
+      while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
+    }
+    // ---- flush the weight-gradient accumulators as a per-CTA partial tile [128][192] (see block_bwd2); all 16 warps
+    {
+      const int cg = warp >> 2;
+      float* prow = pp.partial + ((int64_t)blockIdx.x * 128 + row) * 192;
+      if (n_mine > 0) {
+        mbar_wait(&wg_done, 0);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(lane_addr + C_WFG + cg * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(prow + cg * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        uint32_t u[16];
+        if (DENSE) {
+          tmem_ld16(lane_addr + C_WD + cg * 16, u);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) u[j] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(prow + 128 + cg * 16 + q * 4) = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 // dW = sum over CTAs of the partial tiles written by block_bwd2 / block_bwd3 (fixed summation order: deterministic)
 struct WgradReduceArgs {
   int64_t filt0, gate0, dense0, layer_stride;     // flat-vector offsets of layer 0's filter / gate / dense weights
@@ -1708,6 +1999,17 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   const int n_ctas = std::min(n_items, g_sm_count);
   const bool bias = p.b.bias_fg != nullptr, dense = p.b.has_dense != 0;
   const bool three_stage = p.b.dzs_nblk > 0;      // the caller chose the tiled skip-gradient layout (bwd3_enabled)
+  static const bool two_groups = [] { const char* e = getenv("WN_BWD4"); return e && e[0] == '1'; }();   // draft, see block_bwd4_kernel
+  if (three_stage && two_groups) {
+    auto k4 = bias ? (dense ? block_bwd4_kernel<true, true> : block_bwd4_kernel<true, false>)
+                   : (dense ? block_bwd4_kernel<false, true> : block_bwd4_kernel<false, false>);
+    const int smem4 = Bwd3Smem::TOTAL + 1024;
+    WN_PROPAGATE(set_smem_once(k4, smem4));
+    WN_PROF("block_bwd2", s);
+    WN_CHECK_CUDA(launch_pdl(k4, dim3((unsigned)n_ctas), dim3(608), smem4, s, m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p));
+    WN_CHECK_LAUNCH();
+    return WN_OK;
+  }
   if (three_stage) {
     auto k3 = bias ? (dense ? block_bwd3_kernel<true, true> : block_bwd3_kernel<true, false>)
                    : (dense ? block_bwd3_kernel<false, true> : block_bwd3_kernel<false, false>);
