@@ -90,6 +90,10 @@ int wn_model_create(const wn_config* cfg, wn_model** out);
 int wn_model_destroy(wn_model* m);
 int64_t wn_model_param_count(const wn_model* m);
 int32_t wn_model_receptive_field(const wn_model* m);          /* model.py:43-44 */
+/* 1 if this build serves the model's shape with: what = 0 the bf16 tcgen05 training path (residual, dilation <= 64 channels,
+ * zero-padded to 64; skip = quantization = 256), what = 1 the half-precision generation kernel (exactly 64/64/256/256);
+ * 0 otherwise (such shapes run in WN_MODE_FP32).  The Python layer's mode="auto" asks this. */
+int32_t wn_model_supports(const wn_model* m, int32_t what);
 
 /* kernel-side weight images derived from the flat fp32 parameters (refresh after every
  * optimizer step).  fp32 mode: transposed fp32 copies; bf16 mode: bf16 K-major matrices that
@@ -220,6 +224,11 @@ int wn_profile_report(char* buf, size_t cap);   /* sync; "name count total_ms" l
 /* Runs D = A*B^T tiles through TMA -> UMMA -> TMEM -> registers for the operand layouts the
  * kernels rely on; writes max |err| vs. an in-kernel fp32 SIMT product to h_maxerr[case]. */
 int wn_selftest_umma(float* h_maxerr, int32_t n_cases, void* stream);
+/* Test hook for the element-wise gradient parity test at the benchmarked shape: gives the fp32 check-mode workspace of a
+ * forward on the same input (d_ws_fp32) the ReLU masks of the bf16 forward (d_ws_bf16) - model.py:135,137 - by setting the
+ * sign of the stored fp32 pre-activations; magnitudes are untouched.  wn_backward(fp32) then differentiates through the
+ * bf16 run's masks, so that what remains between the two gradients is kernel arithmetic, not mask flips. */
+int wn_test_impose_relu_masks(const wn_model* m, int32_t B, int32_t L, const void* d_ws_bf16, void* d_ws_fp32, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,7 @@ MODE_FP32, MODE_BF16 = 0, 1
 ROWS_REFERENCE, ROWS_CORRECTED = 0, 1
 PUSH_OUTPUT, PUSH_INPUT = 0, 1
 MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16}
+MODE_NAMES = ("auto", "fp32", "bf16")           # "auto": bf16 tensor-core kernels when the shape has them, else fp32 (with a warning)
 ROWS = {"reference": ROWS_REFERENCE, "corrected": ROWS_CORRECTED}
 PUSH = {"output": PUSH_OUTPUT, "input": PUSH_INPUT}
 
@@ -55,6 +56,7 @@ SIGNATURES = {
     "wn_model_destroy": (C.c_int, [_p]),
     "wn_model_param_count": (C.c_int64, [_p]),
     "wn_model_receptive_field": (C.c_int32, [_p]),
+    "wn_model_supports": (C.c_int32, [_p, _i32]),
     "wn_packed_bytes": (C.c_int, [_p, _i32, _psz]),
     "wn_pack_weights": (C.c_int, [_p, _i32, _p, _p, _p]),
     "wn_workspace_bytes": (C.c_int, [_p, _i32, _i32, _i32, _psz]),
@@ -73,6 +75,7 @@ SIGNATURES = {
     "wn_gen_export": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p]),
     "wn_gen_import": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p]),
     "wn_selftest_umma": (C.c_int, [_p, _i32, _p]),
+    "wn_test_impose_relu_masks": (C.c_int, [_p, _i32, _i32, _p, _p, _p]),
     "wn_ae_create": (C.c_int, [_p, C.POINTER(_p)]),
     "wn_ae_destroy": (C.c_int, [_p]),
     "wn_ae_param_count": (C.c_int64, [_p]),

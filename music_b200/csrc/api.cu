@@ -10,6 +10,7 @@
 #include "check_kernels.cuh"
 #include "common.cuh"
 #include "fast.cuh"
+#include "fast_layout.cuh"
 
 namespace wn {
 
@@ -355,6 +356,25 @@ static int backward32(const Model& m, int B, int L, const float* d_x, const int6
   return WN_OK;
 }
 
+
+// ---- test hook: impose the bf16 run's ReLU masks on the fp32 check-mode workspace ----------------------------------
+// The head has two ReLUs (model.py:135,137).  A bf16 forward flips the mask of the few inputs that lie within bf16 error of
+// zero, and each flip is a full-size gradient error whatever the kernels do.  To compare the tcgen05 backward with the
+// oracle-pinned fp32 backward element-wise, the fp32 pre-activations SK / H1 get the SIGN the bf16 run saw (its stored
+// relu outputs H0 / H1 > 0), magnitudes untouched: the fp32 backward then uses exactly the bf16 run's masks.
+__global__ void __launch_bounds__(256) impose_masks_kernel(float* __restrict__ pre32, const __nv_bfloat16* __restrict__ post16, int W, int Wp,
+                                                           int pad, int S) {
+  const int b = blockIdx.y;
+  const int64_t n = (int64_t)W * S;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tw = (int)(e / S), c = (int)(e % S);
+    const bool on = __bfloat162float(post16[((int64_t)b * Wp + pad + tw) * S + c]) > 0.f;
+    float* q = pre32 + (int64_t)b * n + e;
+    const float a = fabsf(*q);
+    *q = on ? fmaxf(a, 1e-30f) : -a;
+  }
+}
+
 }  // namespace wn
 
 using namespace wn;
@@ -472,6 +492,10 @@ extern "C" int wn_model_destroy(wn_model* h) {
 }
 extern "C" int64_t wn_model_param_count(const wn_model* h) { return h ? h->m.n_params : -1; }
 extern "C" int32_t wn_model_receptive_field(const wn_model* h) { return h ? h->m.rf : -1; }
+extern "C" int32_t wn_model_supports(const wn_model* h, int32_t what) {
+  if (!h) return 0;
+  return what == 0 ? (fast_supported(h->m) ? 1 : 0) : (what == 1 ? (fast_gen_supported(h->m) && h->m.n_layers <= 40 ? 1 : 0) : 0);
+}
 
 extern "C" int wn_packed_bytes(const wn_model* h, int32_t mode, size_t* bytes) {
   WN_REQUIRE(h && bytes, WN_ERR_INVALID, "wn_packed_bytes: null argument");
@@ -546,6 +570,23 @@ extern "C" int wn_set_conditioning(wn_model* h, const wn_gen_cond* cond) {
   WN_REQUIRE(cond->d_fg && cond->d_head && cond->frames > 0 && cond->total_len >= h->m.rf, WN_ERR_INVALID,
              "wn_set_conditioning: tables, frames > 0 and total_len >= receptive field are required");
   h->cond = *cond;
+  return WN_OK;
+}
+
+extern "C" int wn_test_impose_relu_masks(const wn_model* h, int32_t B, int32_t L, const void* d_ws_bf16, void* d_ws_fp32, void* stream) {
+  WN_REQUIRE(h && d_ws_bf16 && d_ws_fp32, WN_ERR_INVALID, "wn_test_impose_relu_masks: null argument");
+  const Model& m = h->m;
+  WN_PROPAGATE(check_shape(m, B, L));
+  WN_REQUIRE(fast_supported(m), WN_ERR_UNSUPPORTED, "wn_test_impose_relu_masks: shape has no bf16 path");
+  const int W = L - m.rf + 1, Wp = skip_wp(m, L), pad = (L - W) - skip_tw_al(m, L);
+  const WsLayout wl = ws_layout(m, B, L);
+  Ws32 w = ws32_layout(m, B, L, d_ws_fp32);
+  const uint8_t* ws16 = reinterpret_cast<const uint8_t*>(d_ws_bf16);
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div((int64_t)W * m.S, 256), 148 * 8), (unsigned)B);
+  impose_masks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w.SK, reinterpret_cast<const __nv_bfloat16*>(ws16 + wl.H0), W, Wp, pad, m.S);
+  WN_CHECK_LAUNCH();
+  impose_masks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w.H1, reinterpret_cast<const __nv_bfloat16*>(ws16 + wl.H1), W, Wp, pad, m.S);
+  WN_CHECK_LAUNCH();
   return WN_OK;
 }
 

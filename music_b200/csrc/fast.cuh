@@ -5,7 +5,8 @@
 namespace wn {
 
 int fast_init();                         // resolve cuTensorMapEncodeTiled, set smem attributes
-bool fast_supported(const Model& m);     // shapes the tcgen05 kernels are specialised for
+bool fast_supported(const Model& m);     // shapes the tcgen05 training kernels serve: R, D <= 64 (zero-padded to 64), S = Q = 256
+bool fast_gen_supported(const Model& m); // shapes the half-precision generation kernel serves: exactly 64/64/256/256
 void fast_release(Model& m);
 int fast_packed_bytes(const Model& m, size_t* bytes);
 int fast_pack(Model& m, const float* d_params, void* d_packed, cudaStream_t s);

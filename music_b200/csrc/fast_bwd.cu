@@ -510,8 +510,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmem_ld_wait();
       if (m < p.m_valid) {
         float* ob = base + p.blk_off[c >> 1] + (int64_t)((c & 1) * 32) * p.s_n;
+        const int nv = (p.n_valid > 0 ? p.n_valid : 64) - (c & 1) * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(ob + (int64_t)j * p.s_n, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j)
+          if (j < nv) atomicAdd(ob + (int64_t)j * p.s_n, __uint_as_float(v[j]));
       }
     }
   }
@@ -534,7 +536,7 @@ struct CwCfg {
 };
 __global__ void __launch_bounds__(192, 1)
 causal_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dx0, const int64_t* __restrict__ idx, float* __restrict__ dW, int L,
-                    int n_batches, int tiles_per_batch) {
+                    int n_batches, int tiles_per_batch, int R) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full[CwCfg::STAGES], oh_full[CwCfg::STAGES], empty[CwCfg::STAGES], acc_full;
@@ -639,7 +641,7 @@ causal_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dx0, const int64_t* _
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float x = __uint_as_float(v[j]);
-        if (x != 0.f) atomicAdd(ob + (int64_t)(r0 + j) * 512, x);      // dW[r][q][tap], Q = 256
+        if (x != 0.f && r0 + j < R) atomicAdd(ob + (int64_t)(r0 + j) * 512, x);      // dW[r][q][tap], Q = 256
       }
     }
   }
@@ -648,539 +650,7 @@ causal_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dx0, const int64_t* _
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
-// ======================================================================================= gemm_tn, CTA pair
-// The y-mode launches of gemm_tn_kernel<4> (dW_skip of all layers, dP1, dP2) run two CTAs per (row slice, layer group), one
-// per 128-row m-tile of A, and BOTH stream the same four B blocks: 96 KB per 8.4 MFLOP k-step, L2 -> SM bound.  Here the two
-// form a CTA pair (cluster 2 x 1, tcgen05 cta_group::2): one M = 256 accumulator spans both SMs' tensor memory, the leader
-// issues the MMAs, and each CTA loads its own m-tile of A plus only HALF of the B blocks (64 KB per k-step, three stages).
-// Hand-off per stage: local TMA barrier -> the peer's relay thread arrives on the leader's peer_full -> MMAs -> one commit
-// multicast to both CTAs' empty barriers.  (Building block verified in isolation by tools/pair_umma_test.cu.)
-struct TnPairCfg {
-  static constexpr int STAGES = 3;
-  static constexpr uint32_t A_BYTES = 2 * TILE, B_BYTES = 2 * TILE, STAGE = A_BYTES + B_BYTES, TOTAL = STAGES * STAGE;
-};
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrives on `bar` of BOTH CTAs of the pair
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-
-__global__ void __launch_bounds__(192, 1)
-gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
-                    const __grid_constant__ CUtensorMap tmB1, GemmTnParams p) {
-  using Cfg = TnPairCfg;
-  // grid (2 x row slices, layer groups), cluster 2 x 1: blockIdx.x & 1 = m-tile = rank in the pair
-  const int mt = blockIdx.x & 1, g = blockIdx.y;
-  const int slice = blockIdx.x >> 1, n_slices = gridDim.x >> 1;
-  p.a_col0 = 128 * mt;
-  p.out0 += (int64_t)128 * mt * p.s_m;
-  p.out1 += (int64_t)128 * mt * p.s_m;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int li = 4 * g + j;
-    p.b_col[j] = 64 * li;                                   // past the last layer: outside the tensor -> zero fill
-    p.blk_off[j] = p.y_off0 + (int64_t)min(li, p.y_layers - 1) * p.y_stride;
-  }
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full[Cfg::STAGES], peer_full[Cfg::STAGES], empty[Cfg::STAGES], acc_full;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();                  // == mt
-  if (tid == 0) {
-    for (int i = 0; i < Cfg::STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&peer_full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    mbar_init(&acc_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                                       // both CTAs' barriers and tensor memory exist
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-  pdl_launch_dependents();      // programmatic dependent launch: see tc05.cuh
-  pdl_wait();
-  const uint32_t sbase = smem_u32(sm);
-  const int n_items = p.n_batches * p.tiles_per_batch;
-  const bool have_work = slice < n_items;
-
-  if (warp == 4) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = slice; item < n_items; item += n_slices) {
-        const int b = item / p.tiles_per_batch, row0 = (p.tile0 + item % p.tiles_per_batch) * 128;
-        mbar_spin_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = sm + stage * Cfg::STAGE;
-        uint8_t* sb = sa + Cfg::A_BYTES;
-        mbar_expect_tx(&full[stage], Cfg::STAGE);
-        tma_load_3d(sa, &tmA, &full[stage], p.a_col0, row0, b);
-        tma_load_3d(sa + TILE, &tmA, &full[stage], p.a_col0 + 64, row0, b);
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {                    // this CTA's half of the B blocks
-          const int j = 2 * mt + jj;
-          tma_load_3d(sb + jj * TILE, p.b_map[j] == 0 ? &tmB0 : &tmB1, &full[stage], p.b_col[j], row0 + p.b_row_off[j], b);
-        }
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 5) {
-    if (lane == 0 && have_work) {
-      int stage = 0;
-      uint32_t phase = 0, it = 0;
-      if (rank != 0) {
-        // relay: tell the leader when this CTA's operands of a stage have landed
-        for (int item = slice; item < n_items; item += n_slices) {
-          mbar_spin_wait(&full[stage], phase);
-          uint32_t remote;
-          asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(&peer_full[stage])));
-          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-        }
-      } else {
-        constexpr uint32_t idn = idesc_bf16(256, 256, 1, 1);
-        for (int item = slice; item < n_items; item += n_slices, ++it) {
-          mbar_spin_wait(&full[stage], phase);
-          mbar_spin_wait(&peer_full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16_pair(tmem, desc_mnmajor(sa, k, TILE), desc_mnmajor(sb, k, TILE), idn, (it | (uint32_t)k) != 0);
-          umma_commit_pair(&empty[stage]);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit_pair(&acc_full);
-      }
-    }
-  } else if (have_work) {
-    mbar_wait(&acc_full, 0);
-    tc_fence_after();
-    const int m = tid;
-    float* base = (m < 64 ? p.out0 : p.out1) + (int64_t)(m & 63) * p.s_m;
-    const uint32_t src = tmem_addr(tmem, warp * 32, 0);
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      uint32_t v[32];
-      tmem_ld32(src + c * 32, v);
-      tmem_ld_wait();
-      if (m < p.m_valid) {
-        float* ob = base + p.blk_off[c >> 1] + (int64_t)((c & 1) * 32) * p.s_n;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(ob + (int64_t)j * p.s_n, __uint_as_float(v[j]));
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                                       // the peer's tensor memory is still read until here
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
-}
-
-// ========================================================================================== block_bwd
-struct BwdSmem {
-  static constexpr uint32_t A0 = 0, A1 = TILE, W0 = 2 * TILE, W1 = 3 * TILE, DX = 4 * TILE, WDT = 5 * TILE, TOTAL = 5 * TILE + 8192;
-};
-
-__global__ void __launch_bounds__(128, 2)
-block_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
-                 const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_dx,
-                 const __grid_constant__ CUtensorMap tm_wdT, const __grid_constant__ CUtensorMap tm_dfg,
-                 const __grid_constant__ CUtensorMap tm_zf, BlockBwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t bar_ld, bar_m;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int b = blockIdx.x / p.tiles_per_batch;
-  const int tau0 = (p.tile0 + blockIdx.x % p.tiles_per_batch) * 128;
-  if (tid == 0) {
-    mbar_init(&bar_ld, 1);
-    mbar_init(&bar_m, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t sbase = smem_u32(sm);
-
-  if (tid == 0) {
-    mbar_expect_tx(&bar_ld, 4 * TILE + (p.has_dense ? TILE + 8192 : 0));
-    tma_load_3d(sm + BwdSmem::A0, &tm_x, &bar_ld, 0, tau0 - p.d, b);
-    tma_load_3d(sm + BwdSmem::A1, &tm_x, &bar_ld, 0, tau0, b);
-    tma_load_2d(sm + BwdSmem::W0, &tm_w0, &bar_ld, 0, 0);
-    tma_load_2d(sm + BwdSmem::W1, &tm_w1, &bar_ld, 0, 0);
-    if (p.has_dense) {
-      tma_load_3d(sm + BwdSmem::DX, &tm_dx, &bar_ld, 0, tau0, b);
-      tma_load_2d(sm + BwdSmem::WDT, &tm_wdT, &bar_ld, 0, 0);
-    }
-    mbar_wait(&bar_ld, 0);
-    tc_fence_after();
-    constexpr uint32_t id1 = idesc_bf16(128, 128, 0, 0);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_bf16(tmem, desc_kmajor(sbase + BwdSmem::A0, k), desc_kmajor(sbase + BwdSmem::W0, k), id1, k > 0);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_bf16(tmem, desc_kmajor(sbase + BwdSmem::A1, k), desc_kmajor(sbase + BwdSmem::W1, k), id1, true);
-    if (p.has_dense) {
-      constexpr uint32_t id2 = idesc_bf16(128, 64, 0, 0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem + 128, desc_kmajor(sbase + BwdSmem::DX, k), desc_kmajor(sbase + BwdSmem::WDT, k), id2, k > 0);
-    }
-    umma_commit(&bar_m);
-  }
-  __syncwarp();
-  mbar_wait(&bar_m, 0);
-  tc_fence_after();
-
-  const int row = tid, tau = tau0 + row;
-  const bool valid = tau >= p.s_out && tau < p.L;
-  const bool in_w = valid && tau >= p.tw0;
-  const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
-  const __nv_bfloat16* dzs_row =
-      p.dzs + ((int64_t)b * p.Wp + (tau - p.tw_al)) * p.dzs_pitch + p.dzs_col;     // only dereferenced when in_w
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    uint32_t f[32], g[32], dzv[32];
-    tmem_ld32(lane_addr + c * 32, f);
-    tmem_ld32(lane_addr + 64 + c * 32, g);
-    if (p.has_dense) tmem_ld32(lane_addr + 128 + c * 32, dzv);
-    tmem_ld_wait();
-    uint32_t zs[16];
-    if (in_w) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 a4 = *reinterpret_cast<const uint4*>(dzs_row + c * 32 + q * 8);
-        zs[4 * q] = a4.x; zs[4 * q + 1] = a4.y; zs[4 * q + 2] = a4.z; zs[4 * q + 3] = a4.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) zs[j] = 0u;
-    }
-    uint32_t pz[16], pf[16], pg[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float fv[2] = {__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1])};
-      float gv[2] = {__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1])};
-      const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
-      float dz[2] = {__low2float(s2), __high2float(s2)};
-      if (p.has_dense) {
-        dz[0] += __uint_as_float(dzv[2 * j]);
-        dz[1] += __uint_as_float(dzv[2 * j + 1]);
-      }
-      float zo[2], df[2], dg[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (p.bias_fg) {
-          fv[e] += p.bias_fg[c * 32 + 2 * j + e];
-          gv[e] += p.bias_fg[64 + c * 32 + 2 * j + e];
-        }
-        const float t = tanh_fast(fv[e]), sg = sigmoid_fast(gv[e]);
-        zo[e] = valid ? t * sg : 0.f;
-        df[e] = valid ? dz[e] * sg * (1.f - t * t) : 0.f;
-        dg[e] = valid ? dz[e] * t * sg * (1.f - sg) : 0.f;
-      }
-      pz[j] = pack_bf16(zo[0], zo[1]);
-      pf[j] = pack_bf16(df[0], df[1]);
-      pg[j] = pack_bf16(dg[0], dg[1]);
-    }
-    // staging: z over the dx tile, dF over the tap-0 tile, dG over the tap-1 tile (all MMAs have completed)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t o = sw128_chunk(row, c * 4 + q);
-      *reinterpret_cast<uint4*>(sm + BwdSmem::DX + o) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
-      *reinterpret_cast<uint4*>(sm + BwdSmem::A0 + o) = make_uint4(pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
-      *reinterpret_cast<uint4*>(sm + BwdSmem::A1 + o) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
-    }
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  if (tid == 0) {
-    tma_store_3d(&tm_zf, sm + BwdSmem::DX, 0, tau0, b);
-    tma_store_3d(&tm_dfg, sm + BwdSmem::A0, 0, tau0, b);
-    tma_store_3d(&tm_dfg, sm + BwdSmem::A1, 64, tau0, b);
-    tma_store_commit();
-    tma_store_wait_read();
-  }
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
-}
-
-// ========================================================================================= block_bwd2
-// Persistent CTA per SM, 18 warps: 0-15 epilogue (four warps per TMEM lane quarter, 16 columns each),
-// 16 TMA producer, 17 MMA issuer.
-// TMEM (512 cols): f|g buffer 0 [0,128), f|g buffer 1 [128,256), dz [256,320), dW_fg (both taps) [320,448), dW_dense [448,512).
-// The recompute UMMA of tile n+1 runs into the other f|g buffer during the epilogue of tile n; the MMA issuer polls its
-// three job queues (dz of the next tile - on the epilogue's critical path - first, then weight gradients, then f|g) with
-// the non-blocking mbarrier.test_wait.  The dFG tiles are TMA-stored without anyone waiting: thread 0 checks the bulk
-// group one phase later, just before the tiles are rewritten.
-struct Bwd2Smem {
-  static constexpr uint32_t W0 = 0, W1 = TILE, WDT = 2 * TILE;                 // resident weights (40 KB)
-  static constexpr uint32_t IN = 2 * TILE + 8192, IN_STAGE = 3 * TILE;         // 2 x {x tap0, x tap1, dx_{i+1}}
-  static constexpr uint32_t DF = IN + 2 * IN_STAGE, DG = DF + TILE, Z = DG + TILE;
-  static constexpr uint32_t DZS = Z + TILE;                                    // 2 tiles of the skip-path gradient dzs
-  static constexpr uint32_t TOTAL = DZS + 2 * TILE;                            // 216 KB
-};
 __device__ __forceinline__ void epi8_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-
-template <bool BIAS, bool DENSE>      // compile-time: run-time tests inside the unrolled epilogue loops cost a branch per element
-__global__ void __launch_bounds__(576, 1)
-block_bwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
-                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_dx,
-                  const __grid_constant__ CUtensorMap tm_wdT, const __grid_constant__ CUtensorMap tm_dfg,
-                  const __grid_constant__ CUtensorMap tm_dzs, BlockBwd2Params pp) {
-  const BlockBwdParams& p = pp.b;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t w_full, in_full[2], in_empty[2], acc_full[2], fg_empty[2], dz_empty, out_full, out_empty, wg_done;
-  __shared__ __align__(8) uint64_t dzs_full[2], dzs_empty[2];
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    mbar_init(&w_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&in_full[i], 1);
-      mbar_init(&in_empty[i], 1);
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&fg_empty[i], 1);
-      mbar_init(&dzs_full[i], 1);
-      mbar_init(&dzs_empty[i], 1);
-    }
-    mbar_init(&dz_empty, 1);
-    mbar_init(&out_full, 1);
-    mbar_init(&out_empty, 1);
-    mbar_init(&wg_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-  pdl_launch_dependents();      // programmatic dependent launch: see tc05.cuh
-  pdl_wait();
-  const uint32_t sbase = smem_u32(sm);
-  const int n_items = pp.n_batches * p.tiles_per_batch;
-  constexpr bool dense = DENSE;
-  const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  constexpr uint32_t C_DZ = 256, C_WFG = 320, C_WD = 448;
-
-  if (warp == 16) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0 && n_mine > 0) {
-      mbar_expect_tx(&w_full, 2 * TILE + (dense ? 8192 : 0));
-      tma_load_2d(sm + Bwd2Smem::W0, &tm_w0, &w_full, 0, 0);
-      tma_load_2d(sm + Bwd2Smem::W1, &tm_w1, &w_full, 0, 0);
-      if (dense) tma_load_2d(sm + Bwd2Smem::WDT, &tm_wdT, &w_full, 0, 0);
-      for (int it = 0; it < n_mine; ++it) {
-        const int item = blockIdx.x + it * gridDim.x;
-        const int st = it & 1;
-        const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
-        mbar_wait(&in_empty[st], ((it >> 1) & 1) ^ 1);
-        uint8_t* si = sm + Bwd2Smem::IN + st * Bwd2Smem::IN_STAGE;
-        mbar_expect_tx(&in_full[st], (dense ? 3 : 2) * TILE);
-        tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b, p.pol_first);     // the last read of these rows of x_i
-        tma_load_3d(si + TILE, &tm_x, &in_full[st], 0, tau0, b);
-        if (dense) tma_load_3d(si + 2 * TILE, &tm_dx, &in_full[st], 0, tau0, b);
-        // skip-path gradient tile (every tile gets one so that the buffer parity stays in step; tiles before the
-        // last W time steps read rows < 0 of the padded row space -> clamp to an all-zero pad tile instead)
-        mbar_wait(&dzs_empty[st], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&dzs_full[st], TILE);
-        if (tau0 >= p.tw_al) tma_load_3d(sm + Bwd2Smem::DZS + st * TILE, &tm_dzs, &dzs_full[st], p.dzs_col, tau0 - p.tw_al, b, p.pol_first);
-        else tma_load_3d(sm + Bwd2Smem::DZS + st * TILE, &tm_dzs, &dzs_full[st], p.dzs_col, p.Wp, b);   // fully out of bounds: zeros
-      }
-    }
-  } else if (warp == 17) {
-    // ------------------------------------------------------------ MMA issuer (polling)
-    if (lane == 0 && n_mine > 0) {
-      constexpr uint32_t id_fg = idesc_bf16(128, 128, 0, 0), id_dz = idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t id_wfg = idesc_bf16(128, 128, 1, 1), id_wd = idesc_bf16(128, 64, 1, 1);
-      mbar_wait(&w_full, 0);
-      int jf = 0, jd = 0, jw = 0;       // next tile for: f|g recompute, dz (+ acc_full commit), weight gradients
-      while (jw < n_mine) {
-        // (1) dz of tile jd: its f|g MMAs have been issued; the dz accumulator has been drained by the previous epilogue
-        if (jd < jf && mbar_test_wait(&dz_empty, (jd & 1) ^ 1)) {
-          if (dense) {
-            tc_fence_after();
-            const uint32_t si = sbase + Bwd2Smem::IN + (jd & 1) * Bwd2Smem::IN_STAGE;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem + C_DZ, desc_kmajor(si + 2 * TILE, k), desc_kmajor(sbase + Bwd2Smem::WDT, k), id_dz, k > 0);
-          }
-          umma_commit(&acc_full[jd & 1]);
-          ++jd;
-          continue;
-        }
-        // (2) weight gradients of tile jw once its epilogue has produced dF | dG | z in shared memory
-        if (jw < jd && mbar_test_wait(&out_full, jw & 1)) {
-          tc_fence_after();
-          const uint32_t si = sbase + Bwd2Smem::IN + (jw & 1) * Bwd2Smem::IN_STAGE;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
-            umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd2Smem::DF, k, TILE), desc_mnmajor(si, k, TILE), id_wfg, (jw | k) != 0);
-          if (dense) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)   // dW_dense[r, d] += sum_t dx_{i+1}[t, r] * z[t, d]   (rows 64..127 unused)
-              umma_bf16(tmem + C_WD, desc_mnmajor(si + 2 * TILE, k, 0), desc_mnmajor(sbase + Bwd2Smem::Z, k, TILE), id_wd, (jw | k) != 0);
-          }
-          umma_commit(&in_empty[jw & 1]);
-          umma_commit(&out_empty);
-          ++jw;
-          continue;
-        }
-        // (3) f|g recompute of tile jf into buffer jf & 1
-        if (jf < n_mine && mbar_test_wait(&in_full[jf & 1], (jf >> 1) & 1) && mbar_test_wait(&fg_empty[jf & 1], ((jf >> 1) & 1) ^ 1)) {
-          tc_fence_after();
-          const uint32_t si = sbase + Bwd2Smem::IN + (jf & 1) * Bwd2Smem::IN_STAGE, acc = tmem + (jf & 1) * 128;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(si, k), desc_kmajor(sbase + Bwd2Smem::W0, k), id_fg, k > 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(si + TILE, k), desc_kmajor(sbase + Bwd2Smem::W1, k), id_fg, true);
-          ++jf;
-          continue;
-        }
-      }
-      umma_commit(&wg_done);
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue warps 0-15
-    const int q4 = warp & 3, cg = warp >> 2;          // TMEM lane quarter, 16-column group
-    const int row = q4 * 32 + lane;
-    const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, 0);
-    for (int it = 0; it < n_mine; ++it) {
-      const int item = blockIdx.x + it * gridDim.x;
-      const uint32_t ph = it & 1, ph2 = (it >> 1) & 1;
-      const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
-      const int tau = tau0 + row;
-      const bool valid = tau >= p.s_out && tau < p.L;
-      mbar_wait(&dzs_full[ph], ph2);
-      const uint8_t* dzt = sm + Bwd2Smem::DZS + ph * TILE;
-      const uint4 zq0 = *reinterpret_cast<const uint4*>(dzt + sw128_chunk(row, cg * 2));
-      const uint4 zq1 = *reinterpret_cast<const uint4*>(dzt + sw128_chunk(row, cg * 2 + 1));
-      const uint32_t zs[8] = {zq0.x, zq0.y, zq0.z, zq0.w, zq1.x, zq1.y, zq1.z, zq1.w};
-      mbar_wait(&acc_full[ph], ph2);
-      tc_fence_after();
-      uint32_t f[16], g[16], dzv[16];
-      tmem_ld16(lane_addr + ph * 128 + cg * 16, f);
-      tmem_ld16(lane_addr + ph * 128 + 64 + cg * 16, g);
-      if (dense) tmem_ld16(lane_addr + C_DZ + cg * 16, dzv);
-      tmem_ld_wait();
-      uint32_t pz[8], pf[8], pg[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float fv[2] = {__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1])};
-        float gv[2] = {__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1])};
-        const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
-        float dz[2] = {__low2float(s2), __high2float(s2)};
-        if (dense) {
-          dz[0] += __uint_as_float(dzv[2 * j]);
-          dz[1] += __uint_as_float(dzv[2 * j + 1]);
-        }
-        float zo[2], df[2], dg[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          if (BIAS) {
-            fv[e] += p.bias_fg[cg * 16 + 2 * j + e];
-            gv[e] += p.bias_fg[64 + cg * 16 + 2 * j + e];
-          }
-          const float t = tanh_fast(fv[e]), sg = sigmoid_fast(gv[e]);
-          const float zz = t * sg;
-          zo[e] = zz;
-          df[e] = dz[e] * sg * (1.f - t * t);
-          dg[e] = dz[e] * zz * (1.f - sg);
-        }
-        pz[j] = valid ? pack_bf16(zo[0], zo[1]) : 0u;
-        pf[j] = valid ? pack_bf16(df[0], df[1]) : 0u;
-        pg[j] = valid ? pack_bf16(dg[0], dg[1]) : 0u;
-      }
-      // the dF | dG | z tiles may be rewritten once (a) the previous tile's weight-gradient MMAs have read them
-      // (out_empty) and (b) its TMA stores have read them (thread 0 checks the bulk group, the barrier publishes it)
-      if (it > 0) mbar_wait(&out_empty, ph ^ 1);
-      tc_fence_before();
-      if (tid == 0) tma_store_wait_read();
-      epi8_bar_sync();                     // also: every thread has drained this tile's TMEM accumulators
-      if (tid == 0) {
-        mbar_arrive(&fg_empty[ph]);
-        mbar_arrive(&dz_empty);
-        mbar_arrive(&dzs_empty[ph]);
-      }
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const uint32_t o = sw128_chunk(row, cg * 2 + q);
-        *reinterpret_cast<uint4*>(sm + Bwd2Smem::Z + o) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + Bwd2Smem::DF + o) = make_uint4(pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + Bwd2Smem::DG + o) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
-      }
-      fence_proxy_async_smem();
-      epi8_bar_sync();
-      if (tid == 0) {
-        mbar_arrive(&out_full);
-        tma_store_3d(&tm_dfg, sm + Bwd2Smem::DF, 0, tau0, b, p.pol_last);          // read by the dx GEMM that follows
-        tma_store_3d(&tm_dfg, sm + Bwd2Smem::DG, 64, tau0, b, p.pol_last);
-        tma_store_commit();                // checked one phase later (above), nobody waits here
-      }
-    }
-    if (tid == 0) tma_store_wait_read();
-    // ---- flush the weight-gradient accumulators as a per-CTA partial tile [128][192] (plain 16-byte stores; a
-    //      second small kernel sums the tiles: 3 M fp32 atomics per launch saturated the L2 atomic units)
-    {
-      float* prow = pp.partial + ((int64_t)blockIdx.x * 128 + row) * 192;
-      if (n_mine > 0) {
-        mbar_wait(&wg_done, 0);
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(lane_addr + C_WFG + cg * 32, v);         // dW_fg columns [32 cg, 32 cg + 32)
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(prow + cg * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        uint32_t u[16];
-        if (dense) {
-          tmem_ld16(lane_addr + C_WD + cg * 16, u);        // dW_dense columns [16 cg, 16 cg + 16)
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) u[j] = 0u;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(prow + 128 + cg * 16 + q * 4) = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem);
-}
 
 // ========================================================================================= block_bwd3
 // The default block backward (WN_BWD3=0 selects block_bwd2; history and numbers: profiles/r1_summary.md, "r1d").  Same work
@@ -1759,7 +1229,7 @@ block_bwd4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 // dW = sum over CTAs of the partial tiles written by block_bwd2 / block_bwd3 (fixed summation order: deterministic)
 struct WgradReduceArgs {
   int64_t filt0, gate0, dense0, layer_stride;     // flat-vector offsets of layer 0's filter / gate / dense weights
-  int n_layers;
+  int n_layers, R, D;                              // real (unpadded) residual / dilation channel counts
   int n_ctas[64];                                  // partial tiles written per layer
   int layer0;                                      // blockIdx.y = 0 is this layer
 };
@@ -1786,9 +1256,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   if (c >= 128 && (m >= 64 || g_dense == nullptr)) return;
   if (c < 128) {          // column = (tap, r): tap = c / 64, r = c % 64 ; row m = output channel (filter 0..63 | gate 64..127)
     float* base = m < 64 ? g_filt : g_gate;
-    base[(int64_t)(m & 63) * 128 + (c & 63) * 2 + (c >> 6)] = s;
-  } else {
-    g_dense[(int64_t)m * 64 + (c - 128)] = s;
+    if ((m & 63) < a.D && (c & 63) < a.R) base[(int64_t)(m & 63) * (2 * a.R) + (c & 63) * 2 + (c >> 6)] = s;      // (D, R, 2)
+  } else if (m < a.R && c - 128 < a.D) {
+    g_dense[(int64_t)m * a.D + (c - 128)] = s;                                                                    // (R, D, 1)
   }
 }
 
@@ -1845,12 +1315,13 @@ __global__ void __launch_bounds__(256) bf16_to_f32_kernel(const __nv_bfloat16* _
 
 // out[c] += sum over b, rows in [row_lo,row_hi) of src[b][row][c]   (bias gradients); C in {64,128,256}
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int C, int64_t bstride, int row_lo,
-                                                          int row_hi, float* __restrict__ out, float* __restrict__ out_hi) {
+                                                          int row_hi, float* __restrict__ out, float* __restrict__ out_hi, int n_valid) {
   const int b = blockIdx.y;
   const int col = threadIdx.x % C, rsub = threadIdx.x / C, nsub = 256 / C;
   const int r0 = row_lo + blockIdx.x * 512, r1 = min(row_hi, r0 + 512);
   float acc = 0.f;
   for (int r = r0 + rsub; r < r1; r += nsub) acc += __bfloat162float(src[(int64_t)b * bstride + (int64_t)r * C + col]);
+  if ((col & 63) >= n_valid) return;                               // channel-padded models: only the real channels have a bias
   if (out_hi && col >= 64) atomicAdd(out_hi + col - 64, acc);      // split output: columns [64,128) go to a second vector
   else atomicAdd(out + col, acc);
 }
@@ -1877,28 +1348,49 @@ int set_smem_once(K kernel, int bytes) {
   return WN_OK;
 }
 
-int launch_colsum_bf16(const void* src, int C, int B, int64_t rows_per_batch, int row_lo, int row_hi, float* out, cudaStream_t s) {
+int launch_colsum_bf16(const void* src, int C, int B, int64_t rows_per_batch, int row_lo, int row_hi, float* out, cudaStream_t s,
+                       int n_valid = 64) {
   if (row_hi <= row_lo) return WN_OK;
   dim3 grid((unsigned)ceil_div(row_hi - row_lo, 512), (unsigned)B);
   WN_PROF("colsum_bias", s);
   colsum_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), C, rows_per_batch * C, row_lo, row_hi, out,
-                                          nullptr);
+                                          nullptr, n_valid);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
 // dFG (128 columns): filter-bias gradient from columns [0,64), gate-bias gradient from [64,128)
-int launch_colsum_bf16_split(const void* src, int B, int64_t rows_per_batch, int row_lo, float* out_f, float* out_g, cudaStream_t s) {
+int launch_colsum_bf16_split(const void* src, int B, int64_t rows_per_batch, int row_lo, float* out_f, float* out_g, cudaStream_t s,
+                             int n_valid) {
   const int row_hi = (int)rows_per_batch;
   if (row_hi <= row_lo) return WN_OK;
   dim3 grid((unsigned)ceil_div(row_hi - row_lo, 512), (unsigned)B);
   WN_PROF("colsum_bias", s);
   colsum_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), 128, rows_per_batch * 128, row_lo, row_hi,
-                                          out_f, out_g);
+                                          out_f, out_g, n_valid);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
 
 }  // namespace
+
+// environment switches of the backward (timing experiments; read once)
+struct BwdEnv {
+  bool nt_stream, bwd4, wgrad_side, l2hint_dx, scatter_simt;
+};
+static const BwdEnv& bwd_env() {
+  static const BwdEnv e = [] {
+    auto on = [](const char* name) { const char* v = getenv(name); return v && v[0] == '1'; };
+    auto off = [](const char* name) { const char* v = getenv(name); return v && v[0] == '0'; };
+    BwdEnv r{};
+    r.nt_stream = on("WN_NT_STREAM");
+    r.bwd4 = on("WN_BWD4");
+    r.wgrad_side = !off("WN_WGRAD_SIDE");
+    r.l2hint_dx = on("WN_L2HINT_DX");
+    r.scatter_simt = on("WN_SCATTER_SIMT");
+    return r;
+  }();
+  return e;
+}
 
 int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStream_t s) {
   const int n_items = p.n_batches * p.tiles_per_batch * p.n_ntiles;
@@ -1908,7 +1400,7 @@ int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStrea
   auto pick = [&](auto kernel_plain, auto kernel_mask, auto kernel_add) {
     return p.epi == EPI_PLAIN ? kernel_plain : (p.epi == EPI_MASK ? kernel_mask : kernel_add);
   };
-  if (NT == 256 && p.nk[0] == 4 && p.nk[1] == 0 && p.n_total > 0 && p.n_total % 64 == 0 && !getenv("WN_NT_STREAM")) {
+  if (NT == 256 && p.nk[0] == 4 && p.nk[1] == 0 && p.n_total > 0 && p.n_total % 64 == 0 && !bwd_env().nt_stream) {
     // K = 256: weight block resident in shared memory, one column tile per CTA
     const int smem = NtResCfg::TOTAL + 1024;
     auto k = pick(gemm_nt_resb_kernel<EPI_PLAIN>, gemm_nt_resb_kernel<EPI_MASK>, gemm_nt_resb_kernel<EPI_ADD>);
@@ -1943,91 +1435,34 @@ int launch_gemm_tn(int NB, const GemmTnMaps& m, const GemmTnParams& p, cudaStrea
   }
   const dim3 grid((unsigned)gx, (unsigned)gy);
   WN_PROF(p.tag ? p.tag : "gemm_tn", s);
-  if (NB == 4 && p.y_layers > 0 && p.m_valid == 128 && getenv("WN_TN_PAIR")) {
-    // CTA pairs (cluster 2 x 1, cta_group::2): see gemm_tn_pair_kernel.  Correct (gradient tests pass with WN_TN_PAIR=1) but measured
-    // 5-7 % slower than two independent CTAs on these shapes (dW_skip 0.33 vs 0.32 ms, head 0.26 vs 0.25 ms), so it is opt-in.
-    static bool once = false;
-    const int smem = TnPairCfg::TOTAL + 1024;
-    if (!once) { WN_PROPAGATE(set_smem(gemm_tn_pair_kernel, smem)); once = true; }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * (unsigned)gx, (unsigned)gy / 2); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl_on() ? 2 : 1;
-    WN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tn_pair_kernel, m.a, m.b[0], m.b[1], p));
-  } else if (NB == 4) {
-    static bool once = false;
-    const int smem = TnCfg<4>::TOTAL + 1024;
-    if (!once) { WN_PROPAGATE(set_smem(gemm_tn_kernel<4>, smem)); once = true; }
-    WN_CHECK_CUDA(launch_pdl(gemm_tn_kernel<4>, grid, dim3(192), smem, s, m.a, m.b[0], m.b[1], p));
-  } else if (NB == 2) {
-    static bool once = false;
-    const int smem = TnCfg<2>::TOTAL + 1024;
-    if (!once) { WN_PROPAGATE(set_smem(gemm_tn_kernel<2>, smem)); once = true; }
-    WN_CHECK_CUDA(launch_pdl(gemm_tn_kernel<2>, grid, dim3(192), smem, s, m.a, m.b[0], m.b[1], p));
-  } else if (NB == 1) {
-    static bool once = false;
-    const int smem = TnCfg<1>::TOTAL + 1024;
-    if (!once) { WN_PROPAGATE(set_smem(gemm_tn_kernel<1>, smem)); once = true; }
-    WN_CHECK_CUDA(launch_pdl(gemm_tn_kernel<1>, grid, dim3(192), smem, s, m.a, m.b[0], m.b[1], p));
-  } else {
-    set_error("launch_gemm_tn: NB=%d", NB);
-    return WN_ERR_INVALID;
-  }
+  WN_REQUIRE(NB == 4, WN_ERR_INVALID, "launch_gemm_tn: NB=%d", NB);
+  const int smem = TnCfg<4>::TOTAL + 1024;
+  WN_PROPAGATE(set_smem_once(gemm_tn_kernel<4>, smem));
+  WN_CHECK_CUDA(launch_pdl(gemm_tn_kernel<4>, grid, dim3(192), smem, s, m.a, m.b[0], m.b[1], p));
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
 
-int launch_block_bwd(const BlockBwdMaps& m, const BlockBwdParams& p, int n_ctas, cudaStream_t s) {
-  static bool once = false;
-  const int smem = BwdSmem::TOTAL + 1024;
-  if (!once) { WN_PROPAGATE(set_smem(block_bwd_kernel, smem)); once = true; }
-  WN_PROF("block_bwd", s);
-  block_bwd_kernel<<<n_ctas, 128, smem, s>>>(m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, m.zf, p);
-  WN_CHECK_LAUNCH();
-  return WN_OK;
-}
-
+// block backward with the weight gradients accumulated in TMEM (block_bwd3; WN_BWD4=1: the two-epilogue-group variant)
 int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStream_t s) {
-  const int smem = Bwd2Smem::TOTAL + 1024;
   const int n_items = p.n_batches * p.b.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
   const int n_ctas = std::min(n_items, g_sm_count);
   const bool bias = p.b.bias_fg != nullptr, dense = p.b.has_dense != 0;
-  const bool three_stage = p.b.dzs_nblk > 0;      // the caller chose the tiled skip-gradient layout (bwd3_enabled)
-  static const bool two_groups = [] { const char* e = getenv("WN_BWD4"); return e && e[0] == '1'; }();   // draft, see block_bwd4_kernel
-  if (three_stage && two_groups) {
+  const int smem3 = Bwd3Smem::TOTAL + 1024;
+  WN_PROF("block_bwd3", s);
+  if (bwd_env().bwd4) {
     auto k4 = bias ? (dense ? block_bwd4_kernel<true, true> : block_bwd4_kernel<true, false>)
                    : (dense ? block_bwd4_kernel<false, true> : block_bwd4_kernel<false, false>);
-    const int smem4 = Bwd3Smem::TOTAL + 1024;
-    WN_PROPAGATE(set_smem_once(k4, smem4));
-    WN_PROF("block_bwd2", s);
-    WN_CHECK_CUDA(launch_pdl(k4, dim3((unsigned)n_ctas), dim3(608), smem4, s, m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p));
-    WN_CHECK_LAUNCH();
-    return WN_OK;
-  }
-  if (three_stage) {
+    WN_PROPAGATE(set_smem_once(k4, smem3));
+    WN_CHECK_CUDA(launch_pdl(k4, dim3((unsigned)n_ctas), dim3(608), smem3, s, m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p));
+  } else {
     auto k3 = bias ? (dense ? block_bwd3_kernel<true, true> : block_bwd3_kernel<true, false>)
                    : (dense ? block_bwd3_kernel<false, true> : block_bwd3_kernel<false, false>);
-    const int smem3 = Bwd3Smem::TOTAL + 1024;
     WN_PROPAGATE(set_smem_once(k3, smem3));
-    WN_PROF("block_bwd2", s);
     WN_CHECK_CUDA(launch_pdl(k3, dim3((unsigned)n_ctas), dim3(576), smem3, s, m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p));
-    WN_CHECK_LAUNCH();
-    return WN_OK;
   }
-  auto k = bias ? (dense ? block_bwd2_kernel<true, true> : block_bwd2_kernel<true, false>)
-                : (dense ? block_bwd2_kernel<false, true> : block_bwd2_kernel<false, false>);
-  WN_PROPAGATE(set_smem_once(k, smem));
-  {
-    WN_PROF("block_bwd2", s);
-    WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)n_ctas), dim3(576), smem, s, m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, m.dzs, p));
-    WN_CHECK_LAUNCH();
-  }
+  WN_CHECK_LAUNCH();
   return WN_OK;
 }
 
@@ -2065,6 +1500,26 @@ int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int
   return WN_OK;
 }
 
+// per-device side stream + fork / join events of the backward (one process drives one GPU; a second device gets its own set)
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int side_stream(SideStream** out) {
+  static SideStream tab[64];
+  int dev = 0;
+  WN_CHECK_CUDA(cudaGetDevice(&dev));
+  WN_REQUIRE(dev >= 0 && dev < 64, WN_ERR_UNSUPPORTED, "device index %d", dev);
+  SideStream& t = tab[dev];
+  if (!t.stream) {
+    WN_CHECK_CUDA(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking));
+    WN_CHECK_CUDA(cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming));
+    WN_CHECK_CUDA(cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming));
+  }
+  *out = &t;
+  return WN_OK;
+}
+
 int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_x, const int64_t* d_idx, const void* d_packed,
                        void* d_ws, float* d_dlogits, float* G, cudaStream_t s) {
   const PackLayout pl = pack_layout(m);
@@ -2073,16 +1528,15 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   const uint8_t* P = reinterpret_cast<const uint8_t*>(d_packed);
   uint8_t* Wp = reinterpret_cast<uint8_t*>(d_ws);
   const bool bias = m.use_bias != 0;
-  static const bool unfused_env = [] { const char* e = getenv("WN_BWD_UNFUSED"); return e && e[0] == '1'; }();
-  const bool fused = !unfused_env;       // block_bwd2 / block_bwd3: weight gradients accumulated inside the block kernel
-  // WN_BWD3=0 selects block_bwd2; default: three-stage block backward kernel, which reads the skip-path gradient from the tiled layout (GemmNtParams::out_tiled)
-  static const bool bwd3_env = [] { const char* e = getenv("WN_BWD3"); return !(e && e[0] == '0'); }();
-  const bool dz_tiled = bwd3_env && fused && !getenv("WN_NT_STREAM");
+  const BwdEnv& env = bwd_env();
+  const bool dz_tiled = !env.nt_stream;       // the block backward reads the skip-path gradient from the tiled layout (GemmNtParams::out_tiled)
+  WN_REQUIRE(dz_tiled, WN_ERR_UNSUPPORTED, "WN_NT_STREAM=1 (row-major dZcat) has no block-backward kernel any more");
   WN_CHECK_CUDA(cudaMemsetAsync(G, 0, (size_t)m.n_params * sizeof(float), s));
+  // dx ping-pong buffers: layer i writes tiles >= its own first tile only, so rows below hold the previous step's values of
+  // shallower layers (read by the next layer's tile loads) unless cleared
   WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXa, 0, (size_t)B * L * 64 * 2, s));
   WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXb, 0, (size_t)B * L * 64 * 2, s));
   WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DFG, 0, (size_t)B * L * 128 * 2, s));
-  WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.Zf, 0, (size_t)B * L * 64 * 2, s));
   {
     dim3 grid((unsigned)ceil_div(Wpad, 32), (unsigned)B);
     WN_PROF("dlogits_transpose", s);
@@ -2150,7 +1604,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     tm.a = M.dsk; tm.b[0] = M.zcat; tm.b[1] = M.zcat;
     GemmTnParams tp{};
     tp.n_batches = B; tp.tile0 = 0; tp.tiles_per_batch = skip_tiles; tp.m_valid = 128;
-    tp.out0 = G; tp.out1 = G + 64 * 64; tp.s_m = 64; tp.s_n = 1;
+    tp.out0 = G; tp.out1 = G + 64 * m.D; tp.s_m = m.D; tp.s_n = 1; tp.n_valid = m.D;      // skip weight (S, D, 1)
     tp.y_layers = N; tp.y_off0 = m.layers[0].skip.w;
     tp.y_stride = N > 1 ? m.layers[1].skip.w - m.layers[0].skip.w : 0;
     tp.tag = "gemm_tn_dWs";
@@ -2159,22 +1613,12 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   }
   // ---- residual blocks, last to first
   // side stream for the per-layer reductions of the weight-gradient partial tiles (WN_WGRAD_SIDE=0: one reduction at the end)
-  static cudaStream_t side = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  static int side_env = -1;
-  if (side_env < 0) {
-    const char* e = getenv("WN_WGRAD_SIDE");
-    side_env = (e && e[0] == '0') ? 0 : 1;
-    if (side_env) {
-      WN_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-      WN_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-      WN_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    }
-  }
+  SideStream* side = nullptr;
+  if (env.wgrad_side) WN_PROPAGATE(side_stream(&side));
   WgradReduceArgs ra{};
   ra.filt0 = m.layers[0].filt.w; ra.gate0 = m.layers[0].gate.w; ra.dense0 = m.layers[0].dense.w;
   ra.layer_stride = N > 1 ? m.layers[1].filt.w - m.layers[0].filt.w : 0;
-  ra.n_layers = N;
+  ra.n_layers = N; ra.R = m.R; ra.D = m.D;
   const int tiles_total = (int)ceil_div(L, 128);
   for (int i = 0; i < N; ++i) ra.n_ctas[i] = std::min(B * (tiles_total - m.layers[i].start / 128), g_sm_count);
   for (int i = N - 1; i >= 0; --i) {
@@ -2188,58 +1632,32 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     {
       BlockBwdMaps bm{};
       bm.x = M.layer[i].x; bm.w0 = M.layer[i].w0; bm.w1 = M.layer[i].w1; bm.dx = dx_next; bm.wdT = M.layer[i].wdT;
-      bm.dfg = M.dfg; bm.zf = M.zf; bm.dzs = M.dzcat;
-      BlockBwdParams bp{};
+      bm.dfg = M.dfg;
+      BlockBwd2Params b2{};
+      BlockBwdParams& bp = b2.b;
       bp.L = L; bp.d = d; bp.s_out = s_out; bp.tile0 = tile0; bp.tiles_per_batch = tpb; bp.has_dense = has_dense;
       bp.tw0 = L - W; bp.tw_al = tw_al; bp.Wp = Wpad;
       bp.dzs = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DZcat); bp.dzs_pitch = 64 * N; bp.dzs_col = 64 * i;
-      if (dz_tiled) { bp.dzs_lb0 = i * B; bp.dzs_nblk = (int)ceil_div(Wpad, 32); }
+      bp.dzs_lb0 = i * B; bp.dzs_nblk = (int)ceil_div(Wpad, 32);
       bp.bias_fg = bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
       if (l2_hints_on()) { bp.pol_first = kL2EvictFirst; bp.pol_last = kL2EvictLast; }
-      if (fused) {
-        BlockBwd2Params b2{};
-        b2.b = bp; b2.n_batches = B;
-        b2.g_filt = G + l.filt.w; b2.g_gate = G + l.gate.w; b2.g_dense = has_dense ? G + l.dense.w : nullptr;
-        b2.partial = reinterpret_cast<float*>(Wp + wl.WGP) + (int64_t)i * WGP_LAYER_FLOATS;
-        WN_PROPAGATE(launch_block_bwd2(bm, b2, s));
-        WN_DEBUG_SYNC("block_bwd2", s);
-        if (side) {   // sum this layer's per-CTA weight-gradient tiles next to the kernels that follow (its CTAs need ~1 KB of smem)
-          WN_CHECK_CUDA(cudaEventRecord(ev_fork, s));
-          WN_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-          ra.layer0 = i;
-          WN_PROF("wgrad_reduce (side stream, overlapped)", side);
-          wgrad_reduce_kernel<<<dim3((128 * 192) / 8, 1), 256, 0, side>>>(reinterpret_cast<const float*>(Wp + wl.WGP), WGP_LAYER_FLOATS, ra, G);
-          WN_CHECK_LAUNCH();
-        }
-      } else {
-        WN_PROPAGATE(launch_block_bwd(bm, bp, B * tpb, s));
-        WN_DEBUG_SYNC("block_bwd", s);
+      b2.n_batches = B;
+      b2.partial = reinterpret_cast<float*>(Wp + wl.WGP) + (int64_t)i * WGP_LAYER_FLOATS;
+      WN_PROPAGATE(launch_block_bwd2(bm, b2, s));
+      WN_DEBUG_SYNC("block_bwd3", s);
+      if (side) {   // sum this layer's per-CTA weight-gradient tiles next to the kernels that follow (its CTAs need ~1 KB of smem)
+        WN_CHECK_CUDA(cudaEventRecord(side->fork, s));
+        WN_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        ra.layer0 = i;
+        WN_PROF("wgrad_reduce (side stream, overlapped)", side->stream);
+        wgrad_reduce_kernel<<<dim3((128 * 192) / 8, 1), 256, 0, side->stream>>>(reinterpret_cast<const float*>(Wp + wl.WGP), WGP_LAYER_FLOATS,
+                                                                                 ra, G);
+        WN_CHECK_LAUNCH();
       }
     }
     if (bias) {   // dFG columns [0,64) = filter, [64,128) = gate: two separate bias vectors in the flat layout
-      WN_PROPAGATE(launch_colsum_bf16_split(Wp + wl.DFG, B, L, s_out, G + l.filt.b, G + l.gate.b, s));
-      if (has_dense) WN_PROPAGATE(launch_colsum_bf16(Wp + dx_next_off, 64, B, L, s_out, L, G + l.dense.b, s));
-    }
-    if (!fused) {   // dW_filter / dW_gate, both taps: dFG^T x_i[tau - d], dFG^T x_i[tau]
-      GemmTnMaps tm{};
-      tm.a = M.dfg; tm.b[0] = M.layer[i].x; tm.b[1] = M.layer[i].x;
-      GemmTnParams tp{};
-      tp.n_batches = B; tp.tile0 = tile0; tp.tiles_per_batch = tpb; tp.a_col0 = 0; tp.m_valid = 128;
-      tp.b_map[0] = 0; tp.b_row_off[0] = -d; tp.b_col[0] = 0; tp.blk_off[0] = 0;
-      tp.b_map[1] = 0; tp.b_row_off[1] = 0; tp.b_col[1] = 0; tp.blk_off[1] = 1;
-      tp.out0 = G + l.filt.w; tp.out1 = G + l.gate.w; tp.s_m = 128; tp.s_n = 2; tp.tag = "gemm_tn_dWfg";
-      WN_PROPAGATE(launch_gemm_tn(2, tm, tp, s));
-      WN_DEBUG_SYNC("gemm_tn dWfg", s);
-    }
-    if (has_dense && !fused) {   // dW_dense = dx_{i+1}^T z
-      GemmTnMaps tm{};
-      tm.a = dx_next; tm.b[0] = M.zf; tm.b[1] = M.zf;
-      GemmTnParams tp{};
-      tp.n_batches = B; tp.tile0 = tile0; tp.tiles_per_batch = tpb; tp.a_col0 = 0; tp.m_valid = 64;
-      tp.b_map[0] = 0; tp.b_row_off[0] = 0; tp.b_col[0] = 0; tp.blk_off[0] = 0;
-      tp.out0 = G + l.dense.w; tp.out1 = tp.out0; tp.s_m = 64; tp.s_n = 1; tp.tag = "gemm_tn_dWd";
-      WN_PROPAGATE(launch_gemm_tn(1, tm, tp, s));
-      WN_DEBUG_SYNC("gemm_tn dWd", s);
+      WN_PROPAGATE(launch_colsum_bf16_split(Wp + wl.DFG, B, L, s_out, G + l.filt.b, G + l.gate.b, s, m.D));
+      if (has_dense) WN_PROPAGATE(launch_colsum_bf16(Wp + dx_next_off, 64, B, L, s_out, L, G + l.dense.b, s, m.R));
     }
     {   // dx_i[tau] = dx_{i+1}[tau] + W1^T dFG[tau] + W0^T dFG[tau + d]
       GemmNtMaps gm{};
@@ -2252,15 +1670,15 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       gp.aux_bstride = (int64_t)L * 64; gp.aux_rstride = 64; gp.aux_col0 = 0;
       gp.row_lo = s_in; gp.row_hi = L; gp.tag = "gemm_nt_dx";
       // (L2 hints on this GEMM's dFG loads / dx stores were measured to cost 0.1 ms per step: left off)
-      if (getenv("WN_L2HINT_DX")) { gp.pol_a[0] = kL2EvictFirst; gp.pol_out = kL2EvictLast; }
+      if (env.l2hint_dx) { gp.pol_a[0] = kL2EvictFirst; gp.pol_out = kL2EvictLast; }
       WN_PROPAGATE(launch_gemm_nt(64, gm, gp, s));
       WN_DEBUG_SYNC("gemm_nt dx", s);
     }
   }
-  if (fused && side) {        // join: everything after this point on `s` sees the reduced weight gradients
-    WN_CHECK_CUDA(cudaEventRecord(ev_join, side));
-    WN_CHECK_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
-  } else if (fused) {         // one reduction of every layer's per-CTA weight-gradient tiles (fixed order: deterministic)
+  if (side) {                 // join: everything after this point on `s` sees the reduced weight gradients
+    WN_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+    WN_CHECK_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+  } else {                    // one reduction of every layer's per-CTA weight-gradient tiles (fixed order: deterministic)
     ra.layer0 = 0;
     WN_PROF("wgrad_reduce", s);
     dim3 grid((128 * 192) / 8, (unsigned)N);
@@ -2269,20 +1687,18 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   }
   // ---- causal layer
   const __nv_bfloat16* dx0 = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DXa);
-  if (bias) WN_PROPAGATE(launch_colsum_bf16(dx0, 64, B, L, 1, L, G + m.causal.b, s));
-  if (d_idx && m.Q == 256 && !getenv("WN_SCATTER_SIMT")) {
-    static bool once = false;
+  if (bias) WN_PROPAGATE(launch_colsum_bf16(dx0, 64, B, L, 1, L, G + m.causal.b, s, m.R));
+  if (d_idx && m.Q == 256 && !env.scatter_simt) {
     const int smem = CwCfg::TOTAL + 1024;
-    if (!once) { WN_PROPAGATE(set_smem(causal_wgrad_kernel, smem)); once = true; }
+    WN_PROPAGATE(set_smem_once(causal_wgrad_kernel, smem));
     const int tiles = (int)ceil_div(L, 128);
     WN_PROF("causal_wgrad", s);
     WN_CHECK_CUDA(launch_pdl(causal_wgrad_kernel, dim3((unsigned)std::min(B * tiles, g_sm_count)), dim3(192), smem, s, M.dxa, d_idx,
-                             G + m.causal.w, L, B, tiles));
+                             G + m.causal.w, L, B, tiles, m.R));
     WN_DEBUG_SYNC("causal_wgrad", s);
   } else if (d_idx) {
-    static bool once = false;
     const int smem = 2 * m.Q * 64 * 4;
-    if (!once) { WN_PROPAGATE(set_smem(causal_scatter_bwd_kernel, smem)); once = true; }
+    WN_PROPAGATE(set_smem_once(causal_scatter_bwd_kernel, smem));
     const int per_batch = std::max(1, (g_sm_count + B - 1) / B);
     const int rows_per_cta = (int)ceil_div(L - 1, per_batch);
     dim3 grid((unsigned)ceil_div(L - 1, rows_per_cta), (unsigned)B);
@@ -2302,7 +1718,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       g.X.p = d_x; g.X.sb = (int64_t)m.Q * L; g.X.st = 1; g.X.sc = L;
       g.x_lo = 0; g.x_hi = L; g.n_in = m.Q; g.off = tap == 0 ? -1 : 0;
       g.dY.p = dx0f; g.dY.sb = (int64_t)L * 64; g.dY.st = 64; g.dY.sc = 1;
-      g.n_out = 64; g.dW = G + m.causal.w + tap; g.s_out = (int64_t)m.Q * 2; g.s_in = 2;
+      g.n_out = m.R; g.dW = G + m.causal.w + tap; g.s_out = (int64_t)m.Q * 2; g.s_in = 2;
       g.B = B; g.t0 = 1; g.t1 = L;
       WN_PROPAGATE(launch_wgrad(g, s));
     }

@@ -50,6 +50,7 @@ struct GemmTnMaps {
 struct GemmTnParams {
   int n_batches, tile0, tiles_per_batch;
   int a_col0, m_valid;
+  int n_valid;                  // columns n < n_valid of every 64-column block are flushed (0: all 64) - channel-padded models
   int b_map[4], b_row_off[4], b_col[4];
   float* out0;
   float* out1;
@@ -84,7 +85,6 @@ struct BlockBwdParams {
   const float* bias_fg;
   unsigned long long pol_first, pol_last;   // L2 eviction hints (0: none)
 };
-int launch_block_bwd(const BlockBwdMaps& m, const BlockBwdParams& p, int n_ctas, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // block_bwd2: persistent, warp-specialised version that also accumulates the block's weight gradients

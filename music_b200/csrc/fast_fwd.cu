@@ -1,6 +1,6 @@
 // fast_fwd.cu - bf16 tensor-core forward of the WaveNet stack (R = D = 64, S = Q = 256).
 //
-// block_fwd_kernel  : one residual block (wavenet/model.py:118-129) for a [128 time x 64 ch] tile:
+// block_fwd2_kernel : one residual block (wavenet/model.py:118-129), persistent CTAs over [128 time x 64 ch] tiles:
 //     TMA: x_i[tau-d], x_i[tau] tiles + W_fg (both taps) + W_dense          -> shared memory (SW128)
 //     UMMA #1 (M128 N128 K128): [f|g] = x[tau-d] W0^T + x[tau] W1^T         -> TMEM cols [0,128)
 //     epilogue #1: z = sigmoid(g) * tanh(f) -> bf16 -> shared (A operand of #2) and TMA-stored into
@@ -21,194 +21,9 @@ using namespace tc;
 
 // ======================================================================================= block
 namespace {
-
-constexpr int BF_THREADS = 128;
 constexpr uint32_t TILE_BYTES = 128 * 128;     // [128 rows][64 bf16]
 constexpr uint32_t WD_BYTES = 64 * 128;
-
-struct BlockSmem {
-  // offsets from the 1024-aligned base
-  static constexpr uint32_t A0 = 0, A1 = TILE_BYTES, W0 = 2 * TILE_BYTES, W1 = 3 * TILE_BYTES, WD = 4 * TILE_BYTES,
-                            Z = 4 * TILE_BYTES + WD_BYTES, LO = 5 * TILE_BYTES + WD_BYTES, TOTAL = 6 * TILE_BYTES + WD_BYTES;
-};
-
-__global__ void __launch_bounds__(BF_THREADS, 2)
-block_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_xo,
-                 const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
-                 const __grid_constant__ CUtensorMap tm_wd, const __grid_constant__ CUtensorMap tm_z,
-                 const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_loo, BlockFwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t bar_ld, bar_m1, bar_m2;
-  __shared__ uint32_t tmem_base_s;
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int b = blockIdx.x / p.tiles_per_batch;
-  const int tile = p.tile0 + blockIdx.x % p.tiles_per_batch;
-  const int tau0 = tile * 128;
-
-  if (tid == 0) {
-    mbar_init(&bar_ld, 1);
-    mbar_init(&bar_m1, 1);
-    mbar_init(&bar_m2, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t sbase = smem_u32(sm);
-
-  if (tid == 0) {
-    mbar_expect_tx(&bar_ld, 4 * TILE_BYTES + (p.has_dense ? WD_BYTES + TILE_BYTES : 0));
-    tma_load_3d(sm + BlockSmem::A0, &tm_x, &bar_ld, 0, tau0 - p.d, b);
-    tma_load_3d(sm + BlockSmem::A1, &tm_x, &bar_ld, 0, tau0, b);
-    tma_load_2d(sm + BlockSmem::W0, &tm_w0, &bar_ld, 0, 0);
-    tma_load_2d(sm + BlockSmem::W1, &tm_w1, &bar_ld, 0, 0);
-    if (p.has_dense) {
-      tma_load_2d(sm + BlockSmem::WD, &tm_wd, &bar_ld, 0, 0);
-      tma_load_3d(sm + BlockSmem::LO, &tm_lo, &bar_ld, 0, tau0, b);     // low half of the residual stream
-    }
-    mbar_wait(&bar_ld, 0);
-    tc_fence_after();
-    constexpr uint32_t id1 = idesc_bf16(128, 128, 0, 0);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_bf16(tmem, desc_kmajor(sbase + BlockSmem::A0, k), desc_kmajor(sbase + BlockSmem::W0, k), id1, k > 0);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_bf16(tmem, desc_kmajor(sbase + BlockSmem::A1, k), desc_kmajor(sbase + BlockSmem::W1, k), id1, true);
-    umma_commit(&bar_m1);
-  }
-  __syncwarp();
-
-  // ---- epilogue 1: gate ----
-  mbar_wait(&bar_m1, 0);
-  tc_fence_after();
-  const int row = tid;                       // TMEM lane == tile row
-  const int tau = tau0 + row;
-  const bool valid = (tau >= p.s_out) && (tau < p.L);
-  const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    uint32_t f[32], g[32];
-    tmem_ld32(lane_addr + c * 32, f);
-    tmem_ld32(lane_addr + 64 + c * 32, g);
-    tmem_ld_wait();
-    uint32_t packed[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float f0 = __uint_as_float(f[2 * j]), f1 = __uint_as_float(f[2 * j + 1]);
-      float g0 = __uint_as_float(g[2 * j]), g1 = __uint_as_float(g[2 * j + 1]);
-      if (p.bias_fg) {
-        f0 += p.bias_fg[c * 32 + 2 * j];
-        f1 += p.bias_fg[c * 32 + 2 * j + 1];
-        g0 += p.bias_fg[64 + c * 32 + 2 * j];
-        g1 += p.bias_fg[64 + c * 32 + 2 * j + 1];
-      }
-      float z0 = valid ? sigmoid_fast(g0) * tanh_fast(f0) : 0.f;
-      float z1 = valid ? sigmoid_fast(g1) * tanh_fast(f1) : 0.f;
-      packed[j] = pack_bf16(z0, z1);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 v = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-      *reinterpret_cast<uint4*>(sm + BlockSmem::Z + sw128_chunk(row, c * 4 + q)) = v;
-    }
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-
-  if (tid == 0) {
-    tc_fence_after();
-    if (p.has_dense) {
-      constexpr uint32_t id2 = idesc_bf16(128, 64, 0, 0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem + 128, desc_kmajor(sbase + BlockSmem::Z, k), desc_kmajor(sbase + BlockSmem::WD, k), id2, k > 0);
-      umma_commit(&bar_m2);
-    }
-    if (tau0 >= p.tw_al) {      // tile touches the last W time steps: z feeds the skip GEMM
-      // (TMA stores trap on negative coordinates, hence the tile-aligned row space)
-      tma_store_3d(&tm_z, sm + BlockSmem::Z, p.zcol, tau0 - p.tw_al, b);
-      tma_store_commit();
-    }
-  }
-  __syncwarp();
-
-  // ---- epilogue 2: dense + residual ----
-  if (p.has_dense) {
-    mbar_wait(&bar_m2, 0);
-    tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t dv[32];
-      tmem_ld32(lane_addr + 128 + c * 32, dv);
-      tmem_ld_wait();
-      uint32_t packed[16], packed_lo[16];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 rv = *reinterpret_cast<const uint4*>(sm + BlockSmem::A1 + sw128_chunk(row, c * 4 + q));
-        const uint4 lv = *reinterpret_cast<const uint4*>(sm + BlockSmem::LO + sw128_chunk(row, c * 4 + q));
-        const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-        const uint32_t ll[4] = {lv.x, lv.y, lv.z, lv.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = 4 * q + e;     // pair index inside this 32-col chunk
-          __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
-          __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[e]);
-          // residual stream carried as hi + lo (two bf16): x = dense + (hi + lo), fp32
-          float x0 = __uint_as_float(dv[2 * j]) + (__low2float(r2) + __low2float(l2));
-          float x1 = __uint_as_float(dv[2 * j + 1]) + (__high2float(r2) + __high2float(l2));
-          if (p.bias_d) {
-            x0 += p.bias_d[c * 32 + 2 * j];
-            x1 += p.bias_d[c * 32 + 2 * j + 1];
-          }
-          if (!valid) { x0 = 0.f; x1 = 0.f; }
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-          packed[j] = *reinterpret_cast<const uint32_t*>(&h2);
-          packed_lo[j] = pack_bf16(x0 - __low2float(h2), x1 - __high2float(h2));
-        }
-      }
-      // stage x_{i+1}: hi in the (now free) tap-0 tile, lo in place over the lo tile
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 v = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + BlockSmem::A0 + sw128_chunk(row, c * 4 + q)) = v;
-        uint4 w = make_uint4(packed_lo[4 * q], packed_lo[4 * q + 1], packed_lo[4 * q + 2], packed_lo[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + BlockSmem::LO + sw128_chunk(row, c * 4 + q)) = w;
-      }
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tma_store_3d(&tm_xo, sm + BlockSmem::A0, 0, tau0, b);
-      tma_store_3d(&tm_loo, sm + BlockSmem::LO, 0, tau0, b);
-      tma_store_commit();
-    }
-  }
-  if (tid == 0) tma_store_wait_read();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
-}
-
 }  // namespace
-
-int launch_block_fwd(const BlockFwdMaps& m, const BlockFwdParams& p, int n_ctas, cudaStream_t s) {
-  static bool attr_set = false;
-  const int smem = BlockSmem::TOTAL + 1024;
-  if (!attr_set) {
-    WN_CHECK_CUDA(cudaFuncSetAttribute(block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
-  WN_PROF("block_fwd", s);
-  block_fwd_kernel<<<n_ctas, BF_THREADS, smem, s>>>(m.x, m.xo, m.w0, m.w1, m.wd, m.z, m.lo, m.loo, p);
-  WN_CHECK_LAUNCH();
-  return WN_OK;
-}
 
 // ====================================================================================== block (persistent)
 // 18 warps: 0-15 epilogue (4 per TMEM lane quarter, 16 columns each), 16 TMA producer, 17 MMA issuer.

@@ -448,7 +448,7 @@ int fast_gen_pack(const Model& m, const float* d_params, uint8_t* P, cudaStream_
 
 int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t* d_first_note, const void* d_packed, void* d_state,
                    const float* d_uniforms, int64_t* d_out, float* d_logits, cudaStream_t s) {
-  WN_REQUIRE(fast_supported(m) && m.n_layers <= GEN_MAXL, WN_ERR_UNSUPPORTED,
+  WN_REQUIRE(fast_gen_supported(m) && m.n_layers <= GEN_MAXL, WN_ERR_UNSUPPORTED,
              "bf16 generation is specialised for 64/64/256/256 channels and <= %d layers; use mode fp32", GEN_MAXL);
   const PackLayout pl = pack_layout(m);
   const uint8_t* P = reinterpret_cast<const uint8_t*>(d_packed);

@@ -60,13 +60,17 @@ int tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, ui
   return make_tmap(out, base, 3, dims, strides, box);
 }
 
+// The tcgen05 kernels are written for 64 residual / 64 dilation channels.  Narrower stacks (the reference's default
+// wavenet_params: 32 / 32) run through the same kernels ZERO-PADDED to 64: padded weight rows / columns are zero in the packed
+// image, so padded activations stay exactly zero (tanh(0) sigmoid(0) = 0, dense rows 0) and their gradients are never read.
 bool fast_supported(const Model& m) {
-  return m.R == 64 && m.D == 64 && m.S == 256 && m.Q == 256 && m.n_layers >= 1 && m.n_layers <= 64;
+  return m.R >= 1 && m.R <= 64 && m.D >= 1 && m.D <= 64 && m.S == 256 && m.Q == 256 && m.n_layers >= 1 && m.n_layers <= 64;
 }
+bool fast_gen_supported(const Model& m) { return m.R == 64 && m.D == 64 && m.S == 256 && m.Q == 256 && m.n_layers >= 1; }
 
 static int require_supported(const Model& m) {
   WN_REQUIRE(fast_supported(m), WN_ERR_UNSUPPORTED,
-             "bf16 tensor-core mode is specialised for residual=dilation=64, skip=quantization=256 channels "
+             "bf16 tensor-core mode is specialised for residual, dilation <= 64 and skip = quantization = 256 channels "
              "(got R=%d D=%d S=%d Q=%d); use mode fp32 for other shapes",
              m.R, m.D, m.S, m.Q);
   return WN_OK;
@@ -83,7 +87,7 @@ PackLayout pack_layout(const Model& m) {
   };
   const int N = m.n_layers;
   p.jobs = take(sizeof(PackJob) * (size_t)(16 * N + 32) + sizeof(int64_t) * (size_t)N);
-  p.wc_t = take((size_t)2 * m.Q * m.R * 4);
+  p.wc_t = take((size_t)2 * m.Q * 64 * 4);
   p.bias_c = take(64 * 4);
   p.bias_fg = take((size_t)N * 128 * 4);
   p.bias_d = take((size_t)N * 64 * 4);
@@ -103,7 +107,7 @@ PackLayout pack_layout(const Model& m) {
   p.wsT = take((size_t)N * 64 * 256 * 2);       // [64 d][256 s]
   p.p1T = take(256 * 256 * 2);
   p.p2T = take(256 * 256 * 2);
-  p.gen_frag = take(fast_gen_frag_bytes(m));
+  p.gen_frag = take(fast_gen_supported(m) ? fast_gen_frag_bytes(m) : 0);
   p.total = off;
   return p;
 }
@@ -127,9 +131,9 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(packed + j.dst);
       if (j.kind == PJ_BF16) dst[(int64_t)(j.row0 + o) * j.pitch + j.col0 + i] = __float2bfloat16(v);
       else dst[(int64_t)(j.row0 + i) * j.pitch + j.col0 + o] = __float2bfloat16(v);
-    } else if (j.kind == PJ_F32_T) {       // (out,in,k) -> [tap][in][out] fp32
+    } else if (j.kind == PJ_F32_T) {       // (out,in,k) -> [tap][in][pitch >= out] fp32
       const float v = params[j.src + ((int64_t)o * j.in + i) * j.k + j.tap];
-      reinterpret_cast<float*>(packed + j.dst)[((int64_t)j.tap * j.in + i) * j.out + o] = v;
+      reinterpret_cast<float*>(packed + j.dst)[((int64_t)j.tap * j.in + i) * j.pitch + o] = v;
     } else if (j.kind == PJ_COPY) {        // bias copy: out floats (in == 1)
       reinterpret_cast<float*>(packed + j.dst)[j.col0 + o] = params[j.src + o];
     }
@@ -183,8 +187,8 @@ static void build_jobs(const Model& m, const PackLayout& pl, std::vector<PackJob
     jobs.push_back(j);
   };
   const int N = m.n_layers;
-  add(PJ_F32_T, m.causal, 0, pl.wc_t, 0, 0, 0);
-  add(PJ_F32_T, m.causal, 1, pl.wc_t, 0, 0, 0);
+  add(PJ_F32_T, m.causal, 0, pl.wc_t, 64, 0, 0);
+  add(PJ_F32_T, m.causal, 1, pl.wc_t, 64, 0, 0);
   add_bias(m.causal, pl.bias_c, 0);
   for (int i = 0; i < N; ++i) {
     const LayerP& l = m.layers[i];
@@ -244,7 +248,7 @@ int fast_pack(Model& m, const float* d_params, void* d_packed, cudaStream_t s) {
                                            m.n_layers, reinterpret_cast<float*>(P + pl.bias_skip));
     WN_CHECK_LAUNCH();
   }
-  WN_PROPAGATE(fast_gen_pack(m, d_params, P, s));
+  if (fast_gen_supported(m)) WN_PROPAGATE(fast_gen_pack(m, d_params, P, s));
   return WN_OK;
 }
 
@@ -417,29 +421,18 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
     p.has_dense = (i + 1 < N) ? 1 : 0;
     p.bias_fg = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
     p.bias_d = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_d) + i * 64 : nullptr;
-    static int dbg_env = -1;
-    if (dbg_env < 0) {
-      const char* e = getenv("WN_DBG");
-      dbg_env = e ? atoi(e) : 0;
-    }
+    static const int dbg_env = [] { const char* e = getenv("WN_DBG"); return e ? atoi(e) : 0; }();
+    static const bool ts_env = getenv("WN_TS") != nullptr;
     p.dbg = dbg_env;
     if (l2_hints_on()) { p.pol_first = kL2EvictFirst; p.pol_last = kL2EvictLast; }
-    p.ts = (getenv("WN_TS") && i == N / 2) ? reinterpret_cast<long long*>(Wp + wl.X0f) : nullptr;   // layer N/2, scratch = X0f
-    static int simple_env = -1;
-    if (simple_env < 0) {
-      const char* e = getenv("WN_FWD_SIMPLE");
-      simple_env = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (simple_env) WN_PROPAGATE(launch_block_fwd(fp->block[i], p, B * p.tiles_per_batch, s));     // one tile per CTA
-    else {                                                                                          // persistent
-      p.Wp = skip_wp(m, L); p.zpitch = 64 * N;
-      BlockFwdPtrs g{};
-      g.lo_in = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.XLO + wl.x_stride * (i & 1));
-      g.lo_out = reinterpret_cast<__nv_bfloat16*>(Wp + wl.XLO + wl.x_stride * ((i + 1) & 1));
-      g.x_out = reinterpret_cast<__nv_bfloat16*>(Wp + wl.X + wl.x_stride * (i + 1 < N ? i + 1 : i));
-      g.zcat = reinterpret_cast<__nv_bfloat16*>(Wp + wl.Zcat);
-      WN_PROPAGATE(launch_block_fwd2(fp->block[i], p, g, B, s));
-    }
+    p.ts = (ts_env && i == N / 2) ? reinterpret_cast<long long*>(Wp + wl.X0f) : nullptr;   // layer N/2, scratch = X0f
+    p.Wp = skip_wp(m, L); p.zpitch = 64 * N;
+    BlockFwdPtrs g{};
+    g.lo_in = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.XLO + wl.x_stride * (i & 1));
+    g.lo_out = reinterpret_cast<__nv_bfloat16*>(Wp + wl.XLO + wl.x_stride * ((i + 1) & 1));
+    g.x_out = reinterpret_cast<__nv_bfloat16*>(Wp + wl.X + wl.x_stride * (i + 1 < N ? i + 1 : i));
+    g.zcat = reinterpret_cast<__nv_bfloat16*>(Wp + wl.Zcat);
+    WN_PROPAGATE(launch_block_fwd2(fp->block[i], p, g, B, s));
     WN_DEBUG_SYNC("block_fwd", s);
   }
   SkipHeadParams hp{};

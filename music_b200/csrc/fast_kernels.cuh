@@ -32,7 +32,6 @@ struct BlockFwdParams {
   long long* ts;            // optional timestamp buffer (timing experiments): CTA 0 writes 8 clock64 values per tile
   int dbg;                  // WN_DBG bit mask (timing experiments only): 1 no Zcat store, 2 no x stores, 4 no lo load, 8 no MUFU
 };
-int launch_block_fwd(const BlockFwdMaps& m, const BlockFwdParams& p, int n_ctas, cudaStream_t s);
 // persistent, warp-specialised variant (one CTA per SM loops over the (batch, tile) items); outputs are written
 // to global memory straight from the epilogue registers
 struct BlockFwdPtrs {

@@ -91,7 +91,7 @@ def _codes_of(note: torch.Tensor) -> torch.Tensor:
 
 
 def _gen_mode(net) -> int:
-    return L.MODES[getattr(net, "gen_mode", net.mode)]
+    return L.MODES[net.gen_mode]
 
 
 def _prime(net, codes, uniforms=None, want_logits=False):
@@ -209,7 +209,7 @@ def _write_wav(path, audio, sr):
 
 
 def generate(model_path, model_name, generate_path, generate_name, start_piece=None, sr=16000, duration=10,
-             params_path='./params/wavenet_params.json', queue_push="output", mode="fp32"):
+             params_path='./params/wavenet_params.json', queue_push="output", mode="auto"):
     """Same entry point as the reference (:144-179): load params + checkpoint, prime with
     one-hot(128) x rf unless `start_piece` (1,Q,rf) is given, generate duration*sr samples,
     mu-law decode and write the wav.  Returns the decoded float32 waveform (CPU tensor)."""

@@ -16,14 +16,16 @@ from .._engine import ConvStackFunction, Engine, SoftmaxRowsFunction, _require_c
 class wavenet(nn.Module):
     """Same signature as the reference (wavenet/model.py:8-15).  Two keyword-only extensions:
 
-    mode   : "fp32" (SIMT check mode, 1e-4 parity) or "bf16" (tcgen05 tensor-core path).
+    mode   : "auto" (default) = the bf16 tcgen05 tensor-core path whenever this build has kernels for the shape
+             (residual, dilation <= 64 channels, skip = quantization = 256), otherwise the fp32 path with a warning;
+             "bf16" insists on the tensor-core path (raises for other shapes); "fp32" = SIMT check mode (1e-4 parity).
     parity : "reference" reproduces the reference's output exactly as it is - softmax over flat
              256-chunks of the (B,Q,W) buffer (model.py:142-144); "corrected" gives one softmax per
              time step.
     """
 
     def __init__(self, filter_width, dilations, dilation_channels, residual_channels, skip_channels,
-                 quantization_channels, use_bias, *, mode: str = "fp32", parity: str = "reference"):
+                 quantization_channels, use_bias, *, mode: str = "auto", parity: str = "reference"):
         super(wavenet, self).__init__()
         self.filter_width = filter_width
         self.dilations = dilations
@@ -37,12 +39,67 @@ class wavenet(nn.Module):
         self._init_dliation_layer()
         self._init_post_processing_layer()
         self.softmax = nn.Softmax(dim=1)
-        if mode not in L.MODES:
-            raise ValueError(f"mode must be one of {list(L.MODES)}")
+        if mode not in L.MODE_NAMES:
+            raise ValueError(f"mode must be one of {list(L.MODE_NAMES)}")
         if parity not in L.ROWS:
             raise ValueError(f"parity must be one of {list(L.ROWS)}")
-        self.mode, self.parity = mode, parity
+        self._mode_arg, self.parity = mode, parity
         self._engine = None
+
+    @property
+    def mode(self) -> str:
+        """The arithmetic mode the training / forward kernels run in ("fp32" or "bf16"); "auto" is resolved against the
+        library once (wn_model_supports) and says so loudly when it has to settle for the fp32 SIMT path."""
+        if self._mode_arg != "auto":
+            return self._mode_arg
+        r = getattr(self, "_mode_resolved", None)
+        if r is None:
+            ok = bool(L.load().wn_model_supports(self.engine.handle, 0))
+            r = self._mode_resolved = "bf16" if ok else "fp32"
+            if not ok:
+                import warnings
+                warnings.warn("music_b200: no tcgen05 kernels for residual=%d dilation=%d skip=%d quantization=%d channels; "
+                              "mode='auto' runs this model in the fp32 SIMT mode (~20x slower)" %
+                              (self.residual_channels, self.dilation_channels, self.skip_channels, self.quantization_channels))
+        return r
+
+    @mode.setter
+    def mode(self, value: str):
+        if value not in L.MODE_NAMES:
+            raise ValueError(f"mode must be one of {list(L.MODE_NAMES)}")
+        self._mode_arg = value
+        self._mode_resolved = None
+
+    @property
+    def gen_mode(self) -> str:
+        """Mode of the incremental-generation kernels: the half-precision kernel exists for 64/64/256/256 only."""
+        if self._mode_arg == "fp32":
+            return "fp32"
+        ok = bool(L.load().wn_model_supports(self.engine.handle, 1))
+        if not ok and self._mode_arg == "bf16":
+            return "bf16"          # explicit request: let the library refuse loudly
+        return "bf16" if ok else "fp32"
+
+    def invalidate(self):
+        """Call after writing parameters through `.data` (p.data.copy_(), legacy optimizers, EMA): such writes do not
+        bump the version counters the packed-weight cache is keyed on."""
+        if self._engine is not None:
+            self._engine.invalidate_packed()
+
+    def __deepcopy__(self, memo):
+        """The C plan handle is owned by one Engine: a copy gets its own, built lazily."""
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_engine" else copy.deepcopy(v, memo)
+        return new
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        return st
 
     # -- construction: identical submodules / registration order (model.py:43-84) ---------------
     def calc_receptive_field(self):

@@ -196,9 +196,21 @@ class BatchStager:
             raise L.WavenetB200Error("BatchStager: both slots are in use (call done() after the step that consumed a batch)")
         i = self.n_put % 2
         slot = self.slots[i]
-        if slot is None or slot[0].shape != piece.shape or slot[1].shape != target.shape or slot[0].dtype != piece.dtype:
+        if (slot is None or slot[0].shape != piece.shape or slot[1].shape != target.shape or slot[0].dtype != piece.dtype
+                or slot[1].dtype != target.dtype):
+            # A new slot (first use, or a batch of another shape: the short last batch of an epoch).  The caching allocator
+            # may hand out a block the compute stream has freed on the host while its kernels are still running, so the
+            # copy stream first catches up with everything enqueued on the compute stream; the old slot, if any, may still
+            # be read by the step in flight and is kept alive for it by record_stream.
+            compute = torch.cuda.current_stream(self.device)
+            if slot is not None:
+                for t in slot:
+                    t.record_stream(compute)
             slot = self.slots[i] = (torch.empty(piece.shape, dtype=piece.dtype, device=self.device),
                                     torch.empty(target.shape, dtype=target.dtype, device=self.device))
+            self.copy_stream.wait_stream(compute)
+            for t in slot:
+                t.record_stream(self.copy_stream)
             self.free[i] = None
         with torch.cuda.stream(self.copy_stream):
             if self.free[i] is not None:
@@ -224,13 +236,58 @@ class BatchStager:
         self.n_done += 1
 
 
-def train(base='./params/', dataloader=None, rank=0):
-    """The reference loop (train.py:76-222): JSON configs, resume, loss / store logs, checkpoint
-    rotation.  One process per GPU; launch under torchrun for data parallelism."""
+def _setup_data_parallel(train_params):
+    """One process per GPU (what replaces nn.DataParallel, train.py:117-122).  Under torchrun (WORLD_SIZE > 1) each process
+    takes cuda:LOCAL_RANK and joins the NCCL group; returns (rank, world).  A multi-entry `device_ids` without torchrun cannot
+    be honoured by a single process and is refused instead of being ignored silently."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ids = train_params.get("device_ids") or []
+    if world == 1:
+        if len(ids) > 1:
+            raise L.WavenetB200Error(
+                "train_params['device_ids'] names %d GPUs: music_b200 runs data parallelism as one process per GPU - launch "
+                "`torchrun --nproc-per-node %d` (the batch is then split over the ranks as nn.DataParallel would split it)"
+                % (len(ids), len(ids)))
+        if len(ids) == 1:
+            torch.cuda.set_device(int(ids[0]))
+        return 0, 1
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), dist.get_world_size()
+
+
+class _RankShard:
+    """The slice of every batch this rank trains on: rows [rank * B / world, (rank + 1) * B / world) - the split
+    nn.DataParallel applies to a batch (train.py:117-122 asserts batch_size % num_gpu == 0); batches that do not divide
+    (the short last batch of an epoch) are dropped on every rank alike so that the ranks stay in step."""
+
+    def __init__(self, loader, rank, world):
+        self.loader, self.rank, self.world = loader, rank, world
+
+    def __iter__(self):
+        for b in self.loader:
+            n = b["audio_piece"].shape[0]
+            if n % self.world:
+                continue
+            k = n // self.world
+            sl = slice(self.rank * k, (self.rank + 1) * k)
+            yield {"audio_piece": b["audio_piece"][sl], "audio_target": b["audio_target"][sl]}
+
+
+def train(base='./params/', dataloader=None, rank=None):
+    """The reference loop (train.py:76-222): JSON configs, resume, loss / store logs, checkpoint rotation.
+    One process per GPU: run it directly for one GPU, or under `torchrun --nproc-per-node N` for data parallelism -
+    every rank then trains its slice of each batch, the flat gradient is all-reduced (NCCL avg) inside `Trainer.step`,
+    rank 0 alone writes logs and checkpoints, and all ranks meet at a barrier around the checkpoint rotation."""
     from .faster_audio_data import audio_data_loader
     if not torch.cuda.is_available():
         raise L.WavenetB200Error("music_b200 trains on a B200 only (no CPU fallback)")
     train_params, wavenet_params, dataset_params = get_arguments(base)
+    ddp_rank, world = _setup_data_parallel(train_params)
+    rank = ddp_rank if rank is None else rank
     net = wavenet(**wavenet_params)
     epoch_trained = 0
     if train_params["restore_model"]:
@@ -241,18 +298,32 @@ def train(base='./params/', dataloader=None, rank=0):
             epoch_trained = int(train_params["restore_model"].split('.')[0][7:])
     if dataloader is None:
         dataloader = audio_data_loader(**dataset_params)
+    if world > 1:
+        dataloader = _RankShard(dataloader, rank, world)
     net = net.cuda()
+    if world > 1:                       # identical replicas (restored or freshly initialised on rank 0)
+        import torch.distributed as dist
+        for p in net.parameters():
+            dist.broadcast(p.data, 0)
     print("Start training.")
     print("Writing logging information to ", "{}".format(train_params["log_dir"]))
     print("Models are saved in {}".format(train_params["restore_dir"]))
     trainer = Trainer(net, train_params["optimizer"], train_params["learning_rate"], train_params["momentum"])
-    os.makedirs(train_params["log_dir"], exist_ok=True)
-    os.makedirs(train_params["restore_dir"], exist_ok=True)
-    loss_log_file = open(train_params["log_dir"] + 'loss_log.log', 'a')
-    store_log_file = open(train_params["log_dir"] + 'store_log.log', 'a')
-    with open(train_params["log_dir"] + 'loss_log.log', 'r') as f:
-        lines = f.readlines()
-        num_trained = int(lines[-1].split(' ')[2]) if len(lines) > 0 else 0
+    num_trained = 0
+    loss_log_file = store_log_file = None
+    if rank == 0:
+        os.makedirs(train_params["log_dir"], exist_ok=True)
+        os.makedirs(train_params["restore_dir"], exist_ok=True)
+        loss_log_file = open(train_params["log_dir"] + 'loss_log.log', 'a')
+        store_log_file = open(train_params["log_dir"] + 'store_log.log', 'a')
+        with open(train_params["log_dir"] + 'loss_log.log', 'r') as f:
+            lines = f.readlines()
+            num_trained = int(lines[-1].split(' ')[2]) if len(lines) > 0 else 0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([num_trained], device="cuda")
+        dist.broadcast(t, 0)
+        num_trained = int(t[0])
     total_loss = torch.zeros(1, device="cuda")
     stager = BatchStager()
     for epoch in range(train_params["num_epochs"]):
@@ -275,6 +346,9 @@ def train(base='./params/', dataloader=None, rank=0):
                     loss_log_file.writelines(line)
                     loss_log_file.flush()
                 total_loss.zero_()
+        if (epoch + 1) % train_params["check_point_every"] == 0 and world > 1:
+            import torch.distributed as dist
+            dist.barrier()              # every rank has finished the epoch before rank 0 rotates / writes checkpoints
         if (epoch + 1) % train_params["check_point_every"] == 0 and rank == 0:
             stored_models = glob.glob(train_params["restore_dir"] + "*.model")
             if len(stored_models) == train_params["max_check_points"]:
@@ -287,8 +361,12 @@ def train(base='./params/', dataloader=None, rank=0):
             save_model(net, epoch_trained + epoch + 1, train_params["restore_dir"])
             store_log_file.writelines("Epoch " + str(epoch_trained + epoch + 1) + ", model saved!\n")
             store_log_file.flush()
-    loss_log_file.close()
-    store_log_file.close()
+    if rank == 0:
+        loss_log_file.close()
+        store_log_file.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     return net
 
 

@@ -138,6 +138,24 @@ class wavenet_autoencoder(nn.Module):
         return self._cond_layers
 
     # ---- engine --------------------------------------------------------------------------------------------------
+    def __del__(self):
+        h = self.__dict__.get("_handle")
+        if h is not None:
+            try:
+                L.load().wn_ae_destroy(h)
+            except Exception:
+                pass
+            self.__dict__["_handle"] = None
+
+    def __deepcopy__(self, memo):
+        """The C plan handle has one owner: a copy builds its own lazily."""
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_handle" else ({} if k == "_ws" else copy.deepcopy(v, memo))
+        return new
+
     def _plan(self):
         if self._handle is None:
             lib = L.load()

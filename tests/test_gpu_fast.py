@@ -160,3 +160,57 @@ def test_train_steps_bf16_track_fp32_oracle():
         l_gpu = float(tr.step(idx[:, :-1].cuda(), tgt.cuda()))
         l_cpu = O.train_step(ts, dil, x, tgt)
         assert abs(l_gpu - l_cpu) < 2e-4, (step, l_gpu, l_cpu)
+
+
+# ---------------------------------------------------------------------------------------------- channel-padded models
+def test_cfg1_forward_bf16_vs_reference_golden(golden):
+    """BASELINE.json configs[0] (the reference's default wavenet_params shape: 10 x 3 layers, 32 residual / 32 dilation /
+    256 skip channels, one 16000-sample clip) through the tcgen05 kernels, channels zero-padded to 64: logits and scrambled
+    probabilities against the UNMODIFIED reference's outputs frozen in tests/golden/wn_cfg1.npz; mode='auto' picks bf16."""
+    z = golden("wn_cfg1")
+    dil, st = cfg_state(z)
+    idx = torch.from_numpy(z["idx"].astype(np.int64))[:, :int(z["L"])]
+    net = make_net(z, st, mode="auto")
+    assert net.mode == "bf16" and net.gen_mode == "fp32"      # the half-precision generation kernel is 64/64/256/256 only
+    sub = int(z["rows"][1] - z["rows"][0])
+    lg = net.forward_logits(indices=idx.cuda()).detach().cpu().numpy()
+    e = max_rel(lg[:, :, ::sub], z["logits_cols"])
+    print("cfg-1 bf16 logits max-rel err vs reference golden:", e)
+    assert e < TOL
+    probs = net.forward_indices(idx.cuda()).detach().cpu().numpy()
+    assert max_rel(probs[z["rows"]], z["probs_rows"]) < TOL
+
+
+@pytest.mark.parametrize("R,D,bias,dense", [(32, 32, False, False), (24, 40, True, False), (48, 16, True, True), (64, 32, False, True)])
+def test_padded_channels_forward_backward_vs_oracle(R, D, bias, dense):
+    """Residual / dilation channel counts below 64 run zero-padded through the 64-channel kernels: logits 1e-2, every
+    gradient tensor (noflip recipe) 4e-2, and nothing is written outside a tensor's own slice of the flat gradient."""
+    from music_b200.wavenet.train import Trainer
+    dil = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1, 2]
+    st = O.init_wavenet_state(dil, D, R, 256, 256, bias, seed=15, scale=1.0)
+    if bias:
+        for i in range(len(dil)):
+            st[f"dilation_layer_stack.{4 * i + 3}.bias"] = torch.full((256,), 0.3)
+        st["post_process_1.bias"] = torch.full((256,), 2.0)
+        st["post_process_1.weight"] = st["post_process_1.weight"] * 0.1
+    rf = O.receptive_field(2, dil)
+    B, W = 2, 300
+    L = rf + W - 1
+    g = torch.Generator().manual_seed(15)
+    idx = torch.randint(0, 256, (B, L + 1), generator=g)
+    tgt = idx[:, rf:rf + W].contiguous()
+    x = O.one_hot(idx[:, :L], 256)
+    ref = O.forward_logits(st, dil, x).numpy()
+    loss_ref, g_ref = O.grads(st, dil, x, tgt)
+    net = build_net(dil, R, D, 256, 256, bias, st, mode="bf16")
+    with torch.no_grad():
+        lg = (net.forward_logits(wave_sample=x.cuda()) if dense else net.forward_logits(indices=idx[:, :L].cuda())).cpu().numpy()
+    assert max_rel(lg, ref) < TOL
+    tr = Trainer(net, "adam", distributed=False)
+    piece = x.cuda() if dense else idx[:, :L].cuda()
+    loss = float(tr.forward_backward(piece, tgt.cuda()))
+    assert abs(loss - loss_ref) < 1e-4
+    errs = _grad_errors(net, g_ref)
+    worst = max(errs, key=errs.get)
+    print(f"padded R={R} D={D} bias={bias}: worst grad rel-l2", worst, errs[worst])
+    assert errs[worst] < (4e-2 if bias else 0.12), (worst, errs[worst])

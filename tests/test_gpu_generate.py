@@ -135,3 +135,90 @@ def test_bf16_generation_kernel_teacher_forced_vs_oracle():
                 note = torch.zeros(1, Q, 1)
                 note[:, int(codes[i, s]), :] = 1.0
         assert agree >= 0.9 * 3 * n, agree
+
+
+def _save_reference_checkpoint(tmp_path, dil, R, D, S, Q, bias, st, name="wavenet7.model", dataparallel=False):
+    """params JSON + a checkpoint in the reference's format (train.py:45-50: torch.save of the state_dict; files saved from
+    nn.DataParallel carry a 'module.' prefix, train.py:61-69)."""
+    import json
+    from collections import OrderedDict
+    params = {"filter_width": 2, "dilations": dil, "dilation_channels": D, "residual_channels": R, "skip_channels": S,
+              "quantization_channels": Q, "use_bias": bias}
+    pj = tmp_path / "wavenet_params.json"
+    pj.write_text(json.dumps(params))
+    keys = [k for k, _ in O.wavenet_param_shapes(dil, D, R, S, Q, bias)]
+    sd = OrderedDict((("module." + k) if dataparallel else k, st[k].clone()) for k in keys)
+    (tmp_path / "restore").mkdir(exist_ok=True)
+    torch.save(sd, str(tmp_path / "restore" / name))
+    return str(pj), str(tmp_path / "restore") + "/", name
+
+
+@pytest.mark.parametrize("mode,dataparallel", [("fp32", False), ("auto", True)])
+def test_generate_entry_point_end_to_end(tmp_path, mode, dataparallel):
+    """generate() (fast_generate.py:144-179) as a user calls it: params JSON + checkpoint -> prime with one-hot(128) x rf ->
+    duration * sr steps -> mu-law decode -> wav file.  fp32: the written waveform is the oracle's greedy sequence, decoded,
+    bit for bit.  auto (-> the half-precision kernel for this 64/64/256 model): valid codes, a readable wav of the right
+    length, and the first samples equal the fp32 sequence as long as no near-tie in the logits is broken differently."""
+    from scipy.io import wavfile
+    from music_b200.wavenet.fast_generate import generate
+    dil = [1, 2, 4, 8, 16, 1, 2, 4, 8, 16]
+    R = D = 64
+    S = Q = 256
+    st = O.init_wavenet_state(dil, D, R, S, Q, False, seed=12, scale=1.5)
+    pj, mpath, mname = _save_reference_checkpoint(tmp_path, dil, R, D, S, Q, False, st, dataparallel=dataparallel)
+    sr, duration = 40, 2
+    out_dir = str(tmp_path / "gen") + "/"
+    audio = generate(mpath, mname, out_dir, "a.wav", sr=sr, duration=duration, params_path=pj, mode=mode)
+    assert audio.shape == (sr * duration,) and audio.dtype == torch.float32
+    ref_codes = O.generate(st, dil, sr * duration)
+    ref_audio = O.mu_law_decode(torch.tensor(ref_codes), Q)
+    rate, wav = wavfile.read(out_dir + "a.wav")
+    assert rate == sr and wav.shape == (sr * duration,)
+    assert np.array_equal(wav, audio.numpy())
+    if mode == "fp32":
+        assert (audio.view(torch.int32) - ref_audio.view(torch.int32)).abs().max() <= 1    # decode: 1 ulp (vector/scalar pow loops)
+        from music_b200.wavenet.audio_func import mu_law_encode
+        assert mu_law_encode(audio.cuda(), Q).cpu().tolist() == ref_codes
+    else:
+        assert float(audio.abs().max()) <= 1.0
+        assert torch.equal(audio[:4].view(torch.int32), ref_audio[:4].view(torch.int32))
+    # a user-supplied start piece (one-hot (1,Q,rf), as the reference's signature takes it)
+    rf = O.receptive_field(2, dil)
+    g = torch.Generator().manual_seed(2)
+    piece_idx = torch.randint(0, Q, (1, rf), generator=g)
+    audio2 = generate(mpath, mname, out_dir, "b.wav", start_piece=O.one_hot(piece_idx, Q), sr=sr, duration=1, params_path=pj, mode="fp32")
+    ref2 = O.mu_law_decode(torch.tensor(O.generate(st, dil, sr, start_piece=O.one_hot(piece_idx, Q))), Q)
+    assert (audio2.view(torch.int32) - ref2.view(torch.int32)).abs().max() <= 1
+
+
+def test_generate_missing_checkpoint_raises(tmp_path):
+    from music_b200.wavenet.fast_generate import generate
+    dil = [1, 2]
+    st = O.init_wavenet_state(dil, 16, 16, 32, 256, False, seed=1)
+    pj, mpath, _ = _save_reference_checkpoint(tmp_path, dil, 16, 16, 32, 256, False, st)
+    with pytest.raises(FileNotFoundError):
+        generate(mpath, "wavenet999.model", str(tmp_path / "g") + "/", "x.wav", sr=10, duration=1, params_path=pj)
+
+
+@pytest.mark.parametrize("name", ["wn_tiny_onehot", "wn_bias_dense"])
+def test_slow_predict_next_matches_reference_rule(golden, name):
+    """model.predict_next (wavenet/model.py:148-165): full forward, greedy pick on the LAST ROW of the (scrambled) softmax
+    output.  Checked against the same rule applied to the unmodified reference's golden probabilities, and to the oracle."""
+    from music_b200.wavenet.model import predict_next
+    from tests.util import cfg_state, make_net
+    z = golden(name)
+    dil, st = cfg_state(z)
+    net = make_net(z, st, mode="fp32")
+    Q, L = int(z["Q"]), int(z["L"])
+    if "x" in z.files:
+        x = torch.from_numpy(z["x"]).float()
+    else:
+        x = O.one_hot(torch.from_numpy(z["idx"].astype(np.int64))[:, :L], Q)
+    with torch.no_grad():
+        got = predict_next(net, x.cuda(), Q)
+    probs = O.forward_probs(st, dil, x)
+    want = int(torch.topk(probs.view(-1, Q)[-1], 1)[1])
+    assert got.shape == (1,) and got.dtype == torch.int64
+    assert int(got[0]) == want
+    if "probs" in z.files:                                   # the reference's own output, frozen by oracle/make_golden.py
+        assert int(np.argmax(z["probs"].reshape(-1, Q)[-1])) == want
