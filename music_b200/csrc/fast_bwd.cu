@@ -1226,6 +1226,359 @@ block_bwd4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// ========================================================================================= block_bwd5
+// block_bwd3 + the data-gradient GEMM of the dilated conv fused in, so that dF | dG (256 B per row and layer, written once and
+// read twice by gemm_nt_kernel<64>) never reach HBM.  The obstacle to that fusion is the dilation: row tau of dx_i needs
+// W1^T dFG[tau] AND W0^T dFG[tau + d], i.e. rows of another tile.  Here the two products are kept apart until they are consumed:
+//     A_i[tau] = dx_{i+1}[tau] + dFG_i[tau] W1_i          Q_i[tau] = dFG_i[tau] W0_i              dx_i[tau] = A_i[tau] + Q_i[tau + d_i]
+// and the kernel of layer i - 1 loads the tile A_i[tau0..] and the SHIFTED tile Q_i[tau0 + d_i ..] (TMA, out-of-range rows read as
+// zeros) and uses dx_i only through linear maps: dz = A Wd + Q Wd (two accumulating UMMAs), dW_dense = (A + Q)^T z and the residual
+// pass-through A_{i-1} = (A + Q) + ... (summed once per tile in fp32 in the epilogue).  No atomics, no zero-filled buffers.
+// Per tile:  TMA {x[tau-d], x[tau]} (2 stages), {A', Q'} (2 stages)
+//            UMMA  f|g (recompute)  ->  TMEM fg[n & 1];   dz = A' Wd + Q' Wd  ->  TMEM dz
+//            epilogue 1 (16 warps): gate backward -> z, dF, dG tiles; S = A' + Q' (fp32 in registers, bf16 over the A' tile)
+//            UMMA  dW_dense += S^T z;   P = [dF|dG] [W0|W1] -> TMEM fg[n & 1] (the drained f|g buffer);   dW_fg += dFG^T [x taps]
+//            epilogue 2: A_i = S + P[:, 64:128) over the A' tile, Q_i = P[:, 0:64) over the Q' tile -> TMA stores (store warp)
+// The resident forward weights W0 / W1 ([128 o][64 r], K-major B operands of the recompute) are also the MN-major B operand of
+// the P product (K = o): no transposed weight copies in shared memory.  Tiles start at the previous layer's first tile so that
+// everything layer i - 1 reads has been written in this step (rows below s_out are written as zeros).
+struct Bwd5Smem {
+  static constexpr uint32_t W0 = 0, W1 = TILE, WDT = 2 * TILE;                 // resident weights (40 KB)
+  static constexpr uint32_t XR = 2 * TILE + 8192, X_STAGE = 2 * TILE;          // 2 x {x tap0, x tap1}
+  static constexpr uint32_t DXR = XR + 2 * X_STAGE, DX_STAGE = 2 * TILE;       // 2 x {A' (-> S -> A_i), Q' (-> Q_i)}
+  static constexpr uint32_t DF = DXR + 2 * DX_STAGE, DG = DF + TILE, Z = DG + TILE;
+  static constexpr uint32_t TOTAL = Z + TILE;                                  // 216 KB
+};
+
+template <bool DENSE>
+__global__ void __launch_bounds__(608, 1)
+block_bwd5_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
+                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_a_in,
+                  const __grid_constant__ CUtensorMap tm_q_in, const __grid_constant__ CUtensorMap tm_wdT,
+                  const __grid_constant__ CUtensorMap tm_a_out, const __grid_constant__ CUtensorMap tm_q_out, BlockBwd2Params pp) {
+  const BlockBwdParams& p = pp.b;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t w_full, x_full[2], x_empty[2], dxi_full[2], dxi_empty[2], fg_full[2], fg_empty[2], p_full[2];
+  __shared__ __align__(8) uint64_t dz_full, dz_empty, out_full, out_empty, st_req, wg_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+      mbar_init(&dxi_full[i], 1);
+      mbar_init(&dxi_empty[i], 1);
+      mbar_init(&fg_full[i], 1);
+      mbar_init(&fg_empty[i], 1);
+      mbar_init(&p_full[i], 1);
+    }
+    mbar_init(&dz_full, 1);
+    mbar_init(&dz_empty, 1);
+    mbar_init(&out_full, 1);
+    mbar_init(&out_empty, 1);
+    mbar_init(&st_req, 1);
+    mbar_init(&wg_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t sbase = smem_u32(sm);
+  const int n_items = pp.n_batches * p.tiles_per_batch;
+  const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  constexpr uint32_t C_DZ = 256, C_WFG = 320, C_WD = 448;      // TMEM columns; f|g / P buffers at 0 and 128
+
+  if (warp == 16) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0 && n_mine > 0) {
+      mbar_expect_tx(&w_full, 2 * TILE + (DENSE ? 8192 : 0));
+      tma_load_2d(sm + Bwd5Smem::W0, &tm_w0, &w_full, 0, 0);
+      tma_load_2d(sm + Bwd5Smem::W1, &tm_w1, &w_full, 0, 0);
+      if (DENSE) tma_load_2d(sm + Bwd5Smem::WDT, &tm_wdT, &w_full, 0, 0);
+      for (int it = 0; it < n_mine; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
+        const int st = it & 1;
+        const uint32_t eph = ((it >> 1) & 1) ^ 1;
+        mbar_wait(&x_empty[st], eph);
+        uint8_t* sxp = sm + Bwd5Smem::XR + st * Bwd5Smem::X_STAGE;
+        mbar_expect_tx(&x_full[st], 2 * TILE);
+        tma_load_3d(sxp, &tm_x, &x_full[st], 0, tau0 - p.d, b, p.pol_first);     // the last read of these rows of x_i
+        tma_load_3d(sxp + TILE, &tm_x, &x_full[st], 0, tau0, b);
+        if (tau0 >= p.tw_al) {      // skip-path gradient tile: read by the epilogue straight from global memory, staged in L2 here
+          const int rb0 = (tau0 - p.tw_al) >> 5, nb = min(4, p.dzs_nblk - rb0);
+          if (nb > 0) bulk_prefetch_l2(p.dzs + (((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + rb0) << 11), (uint32_t)nb << 12);
+        }
+        if (DENSE) {
+          // tiles below this layer's own first tile exist only to write zeros for the next kernel: their A' / Q' are not read
+          // from memory (rows there were not written in this step) but from a fully out-of-range box, which reads as zeros
+          const int row_a = tau0 >= p.own_row0 ? tau0 : p.L, row_q = tau0 >= p.own_row0 ? tau0 + p.d_next : p.L;
+          mbar_wait(&dxi_empty[st], eph);
+          uint8_t* sd = sm + Bwd5Smem::DXR + st * Bwd5Smem::DX_STAGE;
+          mbar_expect_tx(&dxi_full[st], 2 * TILE);
+          tma_load_3d(sd, &tm_a_in, &dxi_full[st], 0, row_a, b, p.pol_first);
+          tma_load_3d(sd + TILE, &tm_q_in, &dxi_full[st], 0, row_q, b, p.pol_first);
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // ------------------------------------------------------------ MMA issuer (polling)
+    if (lane == 0 && n_mine > 0) {
+      constexpr uint32_t id_fg = idesc_bf16(128, 128, 0, 0), id_dz = idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t id_wfg = idesc_bf16(128, 128, 1, 1), id_wd = idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t id_p = idesc_bf16(128, 128, 0, 1);      // A = [dF|dG] K-major, B = [W0|W1] MN-major (K = f|g output channel)
+      mbar_wait(&w_full, 0);
+      int jf = 0, jd = 0, jw = 0;       // next tile for: f|g recompute, dz, {dW_dense, P, dW_fg}
+      while (jw < n_mine) {
+        // (1) dz of tile jd (on the epilogue's critical path)
+        if (DENSE && jd < n_mine && mbar_test_wait(&dz_empty, (jd & 1) ^ 1) && mbar_test_wait(&dxi_full[jd & 1], (jd >> 1) & 1)) {
+          tc_fence_after();
+          const uint32_t sd = sbase + Bwd5Smem::DXR + (jd & 1) * Bwd5Smem::DX_STAGE;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd, k), desc_kmajor(sbase + Bwd5Smem::WDT, k), id_dz, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd + TILE, k), desc_kmajor(sbase + Bwd5Smem::WDT, k), id_dz, true);
+          umma_commit(&dz_full);
+          ++jd;
+          continue;
+        }
+        // (2) tile jw after its epilogue 1: dW_dense (frees the S and z tiles), P (needed by epilogue 2), dW_fg
+        if (jw < jf && mbar_test_wait(&out_full, jw & 1)) {
+          tc_fence_after();
+          const uint32_t sxa = sbase + Bwd5Smem::XR + (jw & 1) * Bwd5Smem::X_STAGE;
+          if (DENSE) {
+            const uint32_t ss = sbase + Bwd5Smem::DXR + (jw & 1) * Bwd5Smem::DX_STAGE;      // S = A' + Q' (bf16), written by epilogue 1
+#pragma unroll
+            for (int k = 0; k < 8; ++k)   // dW_dense[r, d] += sum_t S[t, r] * z[t, d]   (rows 64..127 unused)
+              umma_bf16(tmem + C_WD, desc_mnmajor(ss, k, 0), desc_mnmajor(sbase + Bwd5Smem::Z, k, TILE), id_wd, (jw | k) != 0);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)     // P[t, (tap, r)] = sum_o dFG[t, o] * W_tap[o, r]
+            umma_bf16(tmem + (jw & 1) * 128, desc_kmajor(sbase + (k < 4 ? Bwd5Smem::DF : Bwd5Smem::DG), k & 3),
+                      desc_mnmajor(sbase + Bwd5Smem::W0, k, TILE), id_p, k > 0);
+          umma_commit(&p_full[jw & 1]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
+            umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd5Smem::DF, k, TILE), desc_mnmajor(sxa, k, TILE), id_wfg, (jw | k) != 0);
+          umma_commit(&x_empty[jw & 1]);
+          umma_commit(&out_empty);
+          ++jw;
+          continue;
+        }
+        // (3) f|g recompute of tile jf into buffer jf & 1 (free once epilogue 2 of tile jf - 2 has drained P from it)
+        if (jf < n_mine && mbar_test_wait(&x_full[jf & 1], (jf >> 1) & 1) && mbar_test_wait(&fg_empty[jf & 1], ((jf >> 1) & 1) ^ 1)) {
+          tc_fence_after();
+          const uint32_t sxa = sbase + Bwd5Smem::XR + (jf & 1) * Bwd5Smem::X_STAGE, acc = tmem + (jf & 1) * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa, k), desc_kmajor(sbase + Bwd5Smem::W0, k), id_fg, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa + TILE, k), desc_kmajor(sbase + Bwd5Smem::W1, k), id_fg, true);
+          umma_commit(&fg_full[jf & 1]);
+          ++jf;
+          continue;
+        }
+      }
+      umma_commit(&wg_done);
+    }
+  } else if (warp == 18) {
+    // ------------------------------------------------------------ store thread: A_i / Q_i tiles -> global, then frees their stage
+    if (lane == 0 && n_mine > 0) {
+      int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
+      for (int it = 0; it < n_mine; ++it) {
+        const int tau0 = (p.tile0 + tl) * 128;
+        uint8_t* sd = sm + Bwd5Smem::DXR + (it & 1) * Bwd5Smem::DX_STAGE;
+        mbar_wait(&st_req, it & 1);
+        tma_store_3d(&tm_a_out, sd, 0, tau0, b, p.pol_last);               // both read by the next launch
+        tma_store_3d(&tm_q_out, sd + TILE, 0, tau0, b, p.pol_last);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&dxi_empty[it & 1]);
+        tl += (int)gridDim.x;
+        while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps 0-15
+    const int q4 = warp & 3, cg = warp >> 2;          // TMEM lane quarter, 16-column group
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, 0);
+    int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
+    for (int it = 0; it < n_mine; ++it) {
+      const uint32_t ph = it & 1, ph2 = (it >> 1) & 1;
+      const int tau0 = (p.tile0 + tl) * 128;
+      const int tau = tau0 + row;
+      const bool valid = tau >= p.s_out && tau < p.L;
+      uint8_t* sa = sm + Bwd5Smem::DXR + ph * Bwd5Smem::DX_STAGE;      // A' -> S -> A_i ; + TILE: Q' -> Q_i
+      const uint32_t o0 = sw128_chunk(row, cg * 2), o1 = sw128_chunk(row, cg * 2 + 1);
+      // ---------------- epilogue 1: gate backward
+      uint32_t zs[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      if (tau0 >= p.tw_al && tau < p.L)      // tiled layout (GemmNtParams::out_tiled): this warp's 32 rows x 16 channels are 1 KB contiguous
+        ldg_stream32(p.dzs + (((((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + ((tau0 - p.tw_al) >> 5) + q4) * 4 + cg) * 32 + lane) << 4), p.pol_first, zs);
+      mbar_wait(&fg_full[ph], ph2);
+      tc_fence_after();
+      uint32_t f[16], g[16];
+      tmem_ld16(lane_addr + ph * 128 + cg * 16, f);
+      tmem_ld16(lane_addr + ph * 128 + 64 + cg * 16, g);
+      tmem_ld_wait();
+      float ca[16], cb[16];
+      uint32_t pz[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float zo[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float fv = __uint_as_float(f[2 * j + e]), gv = __uint_as_float(g[2 * j + e]);
+          const float t = tanh_fast(fv), sg = sigmoid_fast(gv);
+          zo[e] = t * sg;
+          ca[2 * j + e] = sg * (1.f - t * t);
+          cb[2 * j + e] = zo[e] * (1.f - sg);
+        }
+        pz[j] = valid ? pack_bf16(zo[0], zo[1]) : 0u;
+      }
+      float sum[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sum[j] = 0.f;
+      uint32_t dzv[16];
+      if (DENSE) {
+        mbar_wait(&dz_full, ph);             // dz complete: the MMAs have read A' and Q', and (TMA barrier observed by the issuer
+        mbar_wait(&dxi_full[ph], ph2);       //  and here) both tiles are visible to this thread
+        tc_fence_after();
+        tmem_ld16(lane_addr + C_DZ + cg * 16, dzv);
+        const uint4 a0 = *reinterpret_cast<const uint4*>(sa + o0), a1 = *reinterpret_cast<const uint4*>(sa + o1);
+        const uint4 q0 = *reinterpret_cast<const uint4*>(sa + TILE + o0), q1 = *reinterpret_cast<const uint4*>(sa + TILE + o1);
+        const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
+          const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&qw[j]);
+          sum[2 * j] = __low2float(a2) + __low2float(q2);
+          sum[2 * j + 1] = __high2float(a2) + __high2float(q2);
+        }
+        tmem_ld_wait();
+      }
+      asm volatile("" : "+r"(zs[0]), "+r"(zs[1]), "+r"(zs[2]), "+r"(zs[3]), "+r"(zs[4]), "+r"(zs[5]), "+r"(zs[6]), "+r"(zs[7]));
+      uint32_t pf[8], pg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
+        float dz0 = __low2float(s2), dz1 = __high2float(s2);
+        if (DENSE) {
+          dz0 += __uint_as_float(dzv[2 * j]);
+          dz1 += __uint_as_float(dzv[2 * j + 1]);
+        }
+        pf[j] = valid ? pack_bf16(dz0 * ca[2 * j], dz1 * ca[2 * j + 1]) : 0u;
+        pg[j] = valid ? pack_bf16(dz0 * cb[2 * j], dz1 * cb[2 * j + 1]) : 0u;
+      }
+      // dF | dG | z may be rewritten once the previous tile's MMAs have read them (out_empty: committed after its dW_fg)
+      if (it > 0) mbar_wait(&out_empty, ph ^ 1);
+      if (!DENSE) mbar_wait(&dxi_empty[ph], ph2 ^ 1);      // no producer waits for the staging slots of this stage: do it here
+      tc_fence_before();
+      epi8_bar_sync();                     // every thread has drained dz (and read A' / Q')
+      if (tid == 0) mbar_arrive(&dz_empty);
+      *reinterpret_cast<uint4*>(sm + Bwd5Smem::Z + o0) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
+      *reinterpret_cast<uint4*>(sm + Bwd5Smem::Z + o1) = make_uint4(pz[4], pz[5], pz[6], pz[7]);
+      *reinterpret_cast<uint4*>(sm + Bwd5Smem::DF + o0) = make_uint4(pf[0], pf[1], pf[2], pf[3]);
+      *reinterpret_cast<uint4*>(sm + Bwd5Smem::DF + o1) = make_uint4(pf[4], pf[5], pf[6], pf[7]);
+      *reinterpret_cast<uint4*>(sm + Bwd5Smem::DG + o0) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+      *reinterpret_cast<uint4*>(sm + Bwd5Smem::DG + o1) = make_uint4(pg[4], pg[5], pg[6], pg[7]);
+      if (DENSE) {                         // S = A' + Q' over the A' tile: the A operand of dW_dense
+        uint32_t ps[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ps[j] = pack_bf16(sum[2 * j], sum[2 * j + 1]);
+        *reinterpret_cast<uint4*>(sa + o0) = make_uint4(ps[0], ps[1], ps[2], ps[3]);
+        *reinterpret_cast<uint4*>(sa + o1) = make_uint4(ps[4], ps[5], ps[6], ps[7]);
+      }
+      fence_proxy_async_smem();
+      epi8_bar_sync();
+      if (tid == 0) mbar_arrive(&out_full);
+      // ---------------- epilogue 2: A_i = S + P1, Q_i = P0 (P = [dF|dG][W0|W1] sits in this tile's drained f|g buffer)
+      mbar_wait(&p_full[ph], ph2);         // also: dW_dense has read the S and z tiles
+      tc_fence_after();
+      uint32_t p0[16], p1[16];
+      tmem_ld16(lane_addr + ph * 128 + cg * 16, p0);
+      tmem_ld16(lane_addr + ph * 128 + 64 + cg * 16, p1);
+      tmem_ld_wait();
+      uint32_t pa[8], pq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        pa[j] = valid ? pack_bf16(sum[2 * j] + __uint_as_float(p1[2 * j]), sum[2 * j + 1] + __uint_as_float(p1[2 * j + 1])) : 0u;
+        pq[j] = valid ? pack_bf16(__uint_as_float(p0[2 * j]), __uint_as_float(p0[2 * j + 1])) : 0u;
+      }
+      *reinterpret_cast<uint4*>(sa + o0) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+      *reinterpret_cast<uint4*>(sa + o1) = make_uint4(pa[4], pa[5], pa[6], pa[7]);
+      *reinterpret_cast<uint4*>(sa + TILE + o0) = make_uint4(pq[0], pq[1], pq[2], pq[3]);
+      *reinterpret_cast<uint4*>(sa + TILE + o1) = make_uint4(pq[4], pq[5], pq[6], pq[7]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      epi8_bar_sync();                     // every thread has drained P and written its part of both output tiles
+      if (tid == 0) {
+        mbar_arrive(&fg_empty[ph]);
+        mbar_arrive(&st_req);
+      }
+      tl += (int)gridDim.x;
+      while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
+    }
+    // ---- flush the weight-gradient accumulators as a per-CTA partial tile [128][192] (summed by wgrad_reduce_kernel)
+    {
+      float* prow = pp.partial + ((int64_t)blockIdx.x * 128 + row) * 192;
+      if (n_mine > 0) {
+        mbar_wait(&wg_done, 0);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(lane_addr + C_WFG + cg * 32, v);         // dW_fg columns [32 cg, 32 cg + 32)
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(prow + cg * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        uint32_t u[16];
+        if (DENSE) {
+          tmem_ld16(lane_addr + C_WD + cg * 16, u);        // dW_dense columns [16 cg, 16 cg + 16)
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) u[j] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(prow + 128 + cg * 16 + q * 4) = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// dx_0[tau] = A_0[tau] + Q_0[tau + d_0]: the input gradient of the causal layer's weight-gradient kernel (the only consumer
+// of a data gradient that is not a block_bwd5 launch)
+__global__ void __launch_bounds__(256) combine_dx0_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Qd,
+                                                          __nv_bfloat16* __restrict__ out, int L, int d0) {
+  const int b = blockIdx.y;
+  const int64_t n = (int64_t)L * 8;            // 8 chunks of 8 channels per row
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tau = (int)(e >> 3), c = (int)(e & 7) * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(A + ((int64_t)b * L + tau) * 64 + c);
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (tau + d0 < L) q = *reinterpret_cast<const uint4*>(Qd + ((int64_t)b * L + tau + d0) * 64 + c);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, qw[4] = {q.x, q.y, q.z, q.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
+      const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&qw[j]);
+      o[j] = pack_bf16(__low2float(a2) + __low2float(q2), __high2float(a2) + __high2float(q2));
+    }
+    *reinterpret_cast<uint4*>(out + ((int64_t)b * L + tau) * 64 + c) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // dW = sum over CTAs of the partial tiles written by block_bwd2 / block_bwd3 (fixed summation order: deterministic)
 struct WgradReduceArgs {
   int64_t filt0, gate0, dense0, layer_stride;     // flat-vector offsets of layer 0's filter / gate / dense weights
@@ -1375,7 +1728,7 @@ int launch_colsum_bf16_split(const void* src, int B, int64_t rows_per_batch, int
 
 // environment switches of the backward (timing experiments; read once)
 struct BwdEnv {
-  bool nt_stream, bwd4, wgrad_side, l2hint_dx, scatter_simt;
+  bool nt_stream, bwd4, bwd5, wgrad_side, l2hint_dx, scatter_simt;
 };
 static const BwdEnv& bwd_env() {
   static const BwdEnv e = [] {
@@ -1384,6 +1737,7 @@ static const BwdEnv& bwd_env() {
     BwdEnv r{};
     r.nt_stream = on("WN_NT_STREAM");
     r.bwd4 = on("WN_BWD4");
+    r.bwd5 = on("WN_BWD5");               // block_bwd5: the dx GEMM fused into the block backward (models without bias)
     r.wgrad_side = !off("WN_WGRAD_SIDE");
     r.l2hint_dx = on("WN_L2HINT_DX");
     r.scatter_simt = on("WN_SCATTER_SIMT");
@@ -1466,6 +1820,21 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   return WN_OK;
 }
 
+// block backward with the dilated conv's data-gradient GEMM fused in (block_bwd5)
+int launch_block_bwd5(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStream_t s) {
+  const int n_items = p.n_batches * p.b.tiles_per_batch;
+  if (n_items <= 0) return WN_OK;
+  const int n_ctas = std::min(n_items, g_sm_count);
+  const int smem = Bwd5Smem::TOTAL + 1024;
+  WN_REQUIRE(p.b.bias_fg == nullptr, WN_ERR_INVALID, "block_bwd5 serves models without bias");
+  auto k = p.b.has_dense ? block_bwd5_kernel<true> : block_bwd5_kernel<false>;
+  WN_PROPAGATE(set_smem_once(k, smem));
+  WN_PROF("block_bwd5", s);
+  WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)n_ctas), dim3(608), smem, s, m.x, m.w0, m.w1, m.a_in, m.q_in, m.wdT, m.a_out, m.q_out, p));
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
 // =============================================================================================== host
 int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int B, int L, const uint8_t* P, uint8_t* Wp,
                    const std::vector<CUtensorMap>& xm, BwdMaps* out) {
@@ -1497,6 +1866,10 @@ int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int
   WN_PROPAGATE(tmap_3d(&out->dxb, Wp + wl.DXb, 64, L, B, 64, (uint64_t)L * 64, 128));
   WN_PROPAGATE(tmap_3d(&out->dfg, Wp + wl.DFG, 128, L, B, 128, (uint64_t)L * 128, 128));
   WN_PROPAGATE(tmap_3d(&out->zf, Wp + wl.Zf, 64, L, B, 64, (uint64_t)L * 64, 128));
+  // block_bwd5: the Q halves of the split data gradient live in the two halves of the (then unused) dFG buffer
+  const size_t half = align_up((size_t)B * L * 64 * 2, 1024);
+  WN_PROPAGATE(tmap_3d(&out->dqa, Wp + wl.DFG, 64, L, B, 64, (uint64_t)L * 64, 128));
+  WN_PROPAGATE(tmap_3d(&out->dqb, Wp + wl.DFG + half, 64, L, B, 64, (uint64_t)L * 64, 128));
   return WN_OK;
 }
 
@@ -1531,12 +1904,15 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   const BwdEnv& env = bwd_env();
   const bool dz_tiled = !env.nt_stream;       // the block backward reads the skip-path gradient from the tiled layout (GemmNtParams::out_tiled)
   WN_REQUIRE(dz_tiled, WN_ERR_UNSUPPORTED, "WN_NT_STREAM=1 (row-major dZcat) has no block-backward kernel any more");
+  const bool fuse_dx = env.bwd5 && !bias;     // block_bwd5 (bias gradients need dF|dG in memory: those models keep the dx GEMM)
   WN_CHECK_CUDA(cudaMemsetAsync(G, 0, (size_t)m.n_params * sizeof(float), s));
-  // dx ping-pong buffers: layer i writes tiles >= its own first tile only, so rows below hold the previous step's values of
-  // shallower layers (read by the next layer's tile loads) unless cleared
-  WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXa, 0, (size_t)B * L * 64 * 2, s));
-  WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXb, 0, (size_t)B * L * 64 * 2, s));
-  WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DFG, 0, (size_t)B * L * 128 * 2, s));
+  if (!fuse_dx) {
+    // dx ping-pong buffers: layer i writes tiles >= its own first tile only, so rows below hold the previous step's values of
+    // shallower layers (read by the next layer's tile loads) unless cleared.  (block_bwd5 writes every row that is read.)
+    WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXa, 0, (size_t)B * L * 64 * 2, s));
+    WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXb, 0, (size_t)B * L * 64 * 2, s));
+    WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DFG, 0, (size_t)B * L * 128 * 2, s));
+  }
   {
     dim3 grid((unsigned)ceil_div(Wpad, 32), (unsigned)B);
     WN_PROF("dlogits_transpose", s);
@@ -1620,15 +1996,47 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   ra.layer_stride = N > 1 ? m.layers[1].filt.w - m.layers[0].filt.w : 0;
   ra.n_layers = N; ra.R = m.R; ra.D = m.D;
   const int tiles_total = (int)ceil_div(L, 128);
-  for (int i = 0; i < N; ++i) ra.n_ctas[i] = std::min(B * (tiles_total - m.layers[i].start / 128), g_sm_count);
+  // first tile of layer i: its own first valid one; block_bwd5 starts at the previous layer's, so that every row layer i - 1
+  // reads has been written in this step (rows below s_out as zeros)
+  auto first_tile = [&](int i) { return fuse_dx ? (i > 0 ? m.layers[i - 1].start / 128 : 0) : m.layers[i].start / 128; };
+  for (int i = 0; i < N; ++i) ra.n_ctas[i] = std::min(B * (tiles_total - first_tile(i)), g_sm_count);
   for (int i = N - 1; i >= 0; --i) {
     const LayerP& l = m.layers[i];
     const int d = l.dilation, s_out = l.start, s_in = s_out - d;
     const bool has_dense = i + 1 < N;
-    const CUtensorMap& dx_next = ((i + 1) & 1) ? M.dxb : M.dxa;       // dx_{i+1}
-    const CUtensorMap& dx_cur = (i & 1) ? M.dxb : M.dxa;              // dx_i
+    const CUtensorMap& dx_next = ((i + 1) & 1) ? M.dxb : M.dxa;       // dx_{i+1}  (block_bwd5: A_{i+1})
+    const CUtensorMap& dx_cur = (i & 1) ? M.dxb : M.dxa;              // dx_i      (block_bwd5: A_i)
     const size_t dx_next_off = ((i + 1) & 1) ? wl.DXb : wl.DXa;
-    const int tile0 = s_out / 128, tpb = tiles_total - tile0;
+    const int tile0 = first_tile(i), tpb = tiles_total - tile0;
+    if (fuse_dx) {
+      BlockBwdMaps bm{};
+      bm.x = M.layer[i].x; bm.w0 = M.layer[i].w0; bm.w1 = M.layer[i].w1; bm.wdT = M.layer[i].wdT;
+      bm.a_in = dx_next; bm.q_in = ((i + 1) & 1) ? M.dqb : M.dqa;
+      bm.a_out = dx_cur; bm.q_out = (i & 1) ? M.dqb : M.dqa;
+      BlockBwd2Params b2{};
+      BlockBwdParams& bp = b2.b;
+      bp.L = L; bp.d = d; bp.s_out = s_out; bp.tile0 = tile0; bp.tiles_per_batch = tpb; bp.has_dense = has_dense;
+      bp.tw0 = L - W; bp.tw_al = tw_al; bp.Wp = Wpad;
+      bp.dzs = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DZcat); bp.dzs_pitch = 64 * N; bp.dzs_col = 64 * i;
+      bp.dzs_lb0 = i * B; bp.dzs_nblk = (int)ceil_div(Wpad, 32);
+      bp.d_next = has_dense ? m.layers[i + 1].dilation : 0;
+      bp.own_row0 = (s_out / 128) * 128;
+      if (l2_hints_on()) { bp.pol_first = kL2EvictFirst; bp.pol_last = kL2EvictLast; }
+      b2.n_batches = B;
+      b2.partial = reinterpret_cast<float*>(Wp + wl.WGP) + (int64_t)i * WGP_LAYER_FLOATS;
+      WN_PROPAGATE(launch_block_bwd5(bm, b2, s));
+      WN_DEBUG_SYNC("block_bwd5", s);
+      if (side) {
+        WN_CHECK_CUDA(cudaEventRecord(side->fork, s));
+        WN_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        ra.layer0 = i;
+        WN_PROF("wgrad_reduce (side stream, overlapped)", side->stream);
+        wgrad_reduce_kernel<<<dim3((128 * 192) / 8, 1), 256, 0, side->stream>>>(reinterpret_cast<const float*>(Wp + wl.WGP), WGP_LAYER_FLOATS,
+                                                                                 ra, G);
+        WN_CHECK_LAUNCH();
+      }
+      continue;
+    }
     {
       BlockBwdMaps bm{};
       bm.x = M.layer[i].x; bm.w0 = M.layer[i].w0; bm.w1 = M.layer[i].w1; bm.dx = dx_next; bm.wdT = M.layer[i].wdT;
@@ -1686,14 +2094,21 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     WN_CHECK_LAUNCH();
   }
   // ---- causal layer
-  const __nv_bfloat16* dx0 = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DXa);
+  if (fuse_dx) {      // dx_0[tau] = A_0[tau] + Q_0[tau + d_0]  ->  the buffer behind M.zf
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div((int64_t)L * 8, 256), 2048), (unsigned)B);
+    WN_PROF("combine_dx0", s);
+    combine_dx0_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DXa), reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DFG),
+                                            reinterpret_cast<__nv_bfloat16*>(Wp + wl.Zf), L, m.layers[0].dilation);
+    WN_CHECK_LAUNCH();
+  }
+  const __nv_bfloat16* dx0 = reinterpret_cast<const __nv_bfloat16*>(Wp + (fuse_dx ? wl.Zf : wl.DXa));
   if (bias) WN_PROPAGATE(launch_colsum_bf16(dx0, 64, B, L, 1, L, G + m.causal.b, s, m.R));
   if (d_idx && m.Q == 256 && !env.scatter_simt) {
     const int smem = CwCfg::TOTAL + 1024;
     WN_PROPAGATE(set_smem_once(causal_wgrad_kernel, smem));
     const int tiles = (int)ceil_div(L, 128);
     WN_PROF("causal_wgrad", s);
-    WN_CHECK_CUDA(launch_pdl(causal_wgrad_kernel, dim3((unsigned)std::min(B * tiles, g_sm_count)), dim3(192), smem, s, M.dxa, d_idx,
+    WN_CHECK_CUDA(launch_pdl(causal_wgrad_kernel, dim3((unsigned)std::min(B * tiles, g_sm_count)), dim3(192), smem, s, fuse_dx ? M.zf : M.dxa, d_idx,
                              G + m.causal.w, L, B, tiles, m.R));
     WN_DEBUG_SYNC("causal_wgrad", s);
   } else if (d_idx) {

@@ -68,6 +68,7 @@ int launch_gemm_tn(int NB, const GemmTnMaps& m, const GemmTnParams& p, cudaStrea
 // block_bwd: recompute [f|g] of block i, dz = dx_{i+1} Wd + dzs, gate backward -> dFG, z  (one tile / CTA)
 // ---------------------------------------------------------------------------------------------
 struct BlockBwdMaps {
+  CUtensorMap a_in, q_in, a_out, q_out;   // block_bwd5: A / Q of layer i + 1 (loads) and of layer i (stores), each (64, L, B)
   CUtensorMap x;      // x_i (64, L, B)
   CUtensorMap w0, w1; // W_fg taps [128][64]
   CUtensorMap dx;     // dx_{i+1} (64, L, B)
@@ -82,6 +83,7 @@ struct BlockBwdParams {
   const __nv_bfloat16* dzs;     // [B*Wp][dzs_pitch], this layer's 64 columns start at dzs_col
   int dzs_pitch, dzs_col;
   int dzs_lb0, dzs_nblk;        // block_bwd3 (tiled dZcat): layer * B, 32-row blocks per batch row
+  int d_next, own_row0;         // block_bwd5: dilation of layer i + 1 (row shift of its Q tile); first row of this layer's own first tile
   const float* bias_fg;
   unsigned long long pol_first, pol_last;   // L2 eviction hints (0: none)
 };

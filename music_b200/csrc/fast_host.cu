@@ -276,7 +276,7 @@ WsLayout ws_layout(const Model& m, int B, int L) {
   w.DZcat = take((size_t)B * align_up((size_t)W, 32) * 64 * N * 2);      // (rows padded to 32 for the tiled layout)
   w.DXa = take((size_t)B * L * 64 * 2);
   w.DXb = take((size_t)B * L * 64 * 2);
-  w.DFG = take((size_t)B * L * 128 * 2);
+  w.DFG = take(2 * align_up((size_t)B * L * 64 * 2, 1024));      // dF|dG (B, L, 128), or block_bwd5's two Q buffers (B, L, 64)
   w.Zf = take((size_t)B * L * 64 * 2);
   w.DX0f = take((size_t)B * L * 64 * 4);
   w.WGP = take((size_t)WGP_LAYER_FLOATS * 4 * N);

@@ -55,6 +55,7 @@ struct BwdMaps {
   CUtensorMap p1T, p2T;                  // [256][256] box {64,256}
   CUtensorMap wsTcat;                    // [64 N rows (layer, d)][256 s] box {64,256}
   CUtensorMap dxa, dxb, dfg, zf;         // (64|128, L, B)
+  CUtensorMap dqa, dqb;                  // block_bwd5: Q_i ping-pong buffers (64, L, B) inside the dFG region
 };
 int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int B, int L, const uint8_t* P, uint8_t* Wp,
                    const std::vector<CUtensorMap>& xm, BwdMaps* out);
