@@ -115,7 +115,7 @@ class ClockSampler:
                 self.samples.append((sm, pw, rs))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def stop(self):
         if not self.ok:
@@ -161,12 +161,35 @@ def cpu_reference_rate(steps, warmup, n_threads=None):
     return WINDOW / dt, n_threads, dt
 
 
+def measure_l2_read_peak(dev, n_ctas):
+    """Measured L2 -> SM read bandwidth (GB/s) with `n_ctas` CTAs each streaming one L2-resident 2.5 MB buffer - the access
+    pattern of the generation kernel's CTAs on their shared weight image (csrc/bench_kernels.cu)."""
+    import torch
+    from music_b200 import _lib as L
+    lib = L.load()
+    nbytes = 2_621_440
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    sink = torch.zeros(4, dtype=torch.int32, device=dev)
+    iters = 200
+    L.check(lib.wn_bench_l2_read(L.ptr(buf), nbytes, n_ctas, 5, L.ptr(sink), L.stream_ptr()))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.check(lib.wn_bench_l2_read(L.ptr(buf), nbytes, n_ctas, iters, L.ptr(sink), L.stream_ptr()))
+    e1.record()
+    torch.cuda.synchronize()
+    return nbytes * n_ctas * iters / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 def bench_generation(net, n_streams, n_steps, dev):
-    """BASELINE.json configs[3]: fast_generate incremental sampling, 30-layer model, 64 parallel streams.
-    Prime every stream with one-hot(128) x rf (fast_generate.py:158-161), then time n_steps greedy steps per stream
-    on the device (CUDA events).  Bytes: per step a CTA streams the 2.47 MB fp16 weight-fragment image once for its 8
-    streams and each stream reads + writes one 64-float vector per block.  Also timed: a throughput configuration with
-    8 streams on every SM-sized slice of the GPU (1024 streams), same kernel."""
+    """BASELINE.json configs[3]: fast_generate incremental sampling, 30-layer model, 64 parallel streams x 160 000 samples.
+    Prime every stream with one-hot(128) x rf (fast_generate.py:158-161; timed separately), then time n_steps greedy steps
+    per stream on the device (CUDA events).
+    `roofline` follows SURVEY.md 8(d): ALGORITHMIC bytes per step = streams x 15 368 B (ring read + write of 30 x 64 fp32 per
+    stream-step + 8 B of I/O) + the 2.54 MB weight set once, over the step time, against the measured HBM copy peak.
+    The kernel's actual L2 -> SM traffic (every CTA of 8 streams streams the weight-fragment image each step) is reported
+    separately in `l2` against an L2 read peak measured in this run with the same number of CTAs.
+    Also timed: a throughput configuration with 8 streams on every SM-sized slice of the GPU (1024 streams), same kernel."""
     import torch
     from music_b200.wavenet import fast_generate as FG
     peaks = {}
@@ -174,49 +197,187 @@ def bench_generation(net, n_streams, n_steps, dev):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.no_grad():
-        first, state, _ = FG._prime(net, torch.full((n_streams, net.receptive_field), Q // 2, dtype=torch.int64, device=dev))
+        prime = torch.full((n_streams, net.receptive_field), Q // 2, dtype=torch.int64, device=dev)
+        FG._prime(net, prime)                                  # warm-up (workspace allocation, packing)
+        torch.cuda.synchronize()
+        e0.record()
+        first, state, _ = FG._prime(net, prime)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_prime = e0.elapsed_time(e1)
         FG._steps(net, state, first, 50)                       # warm-up
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         codes, _ = FG._steps(net, state, first, n_steps)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        del codes
         # throughput configuration: 128 CTAs x 8 streams
         big = 1024
         first_b, state_b, _ = FG._prime(net, torch.full((big, net.receptive_field), Q // 2, dtype=torch.int64, device=dev))
         FG._steps(net, state_b, first_b, 20)
         torch.cuda.synchronize()
-        nb = max(50, n_steps // 10)
+        nb = max(50, min(2000, n_steps // 10))
         e0.record()
         FG._steps(net, state_b, first_b, nb)
         e1.record()
         torch.cuda.synchronize()
         ms_big = e0.elapsed_time(e1)
     n_layers = len(DIL)
-    w_bytes = 2 * (n_layers * (2 * 64 * 128 + 64 * 64 + 64 * 256) + 2 * 256 * 256) + 4 * 2 * Q * R
-    ring_bytes = n_layers * 64 * 4 * 2
+    w_bytes = 2 * (n_layers * (2 * 64 * 128 + 64 * 64 + 64 * 256) + 2 * 256 * 256) + 4 * 2 * Q * R      # what a CTA streams per step
+    w_algo = 2 * 1_269_760                                    # the parameter set in half precision, once per step
+    ring_algo = n_layers * 64 * 4 * 2 + 8                     # per stream-step: one fp32 vector read + written per block, + I/O
+
+    def algo_rate(streams, steps, t_ms):
+        return steps * (streams * ring_algo + w_algo) / (t_ms * 1e-3) / 1e9
 
     def l2_rate(streams, steps, t_ms):
-        n_ctas = (streams + 7) // 8
-        return steps * (n_ctas * w_bytes + streams * ring_bytes) / (t_ms * 1e-3) / 1e9
-    gbs = l2_rate(n_streams, n_steps, ms)
+        return steps * (((streams + 7) // 8) * w_bytes + streams * (ring_algo - 8)) / (t_ms * 1e-3) / 1e9
     peak = peaks.get("hbm_gbs", 6650.0)
+    n_ctas = (n_streams + 7) // 8
+    l2_peak, l2_peak_big = measure_l2_read_peak(dev, n_ctas), measure_l2_read_peak(dev, big // 8)
+    gbs = algo_rate(n_streams, n_steps, ms)
     many = {"streams": big, "steps": nb, "us_per_step": ms_big * 1e3 / nb, "samples_per_s_per_stream": nb / (ms_big * 1e-3),
-            "samples_per_s_total": big * nb / (ms_big * 1e-3), "l2_to_sm_gbs": l2_rate(big, nb, ms_big),
-            "frac_of_hbm_peak": l2_rate(big, nb, ms_big) / peak}
+            "samples_per_s_total": big * nb / (ms_big * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": algo_rate(big, nb, ms_big), "peak": peak, "unit": "GB/s",
+                         "frac": algo_rate(big, nb, ms_big) / peak},
+            "l2": {"achieved_gbs": l2_rate(big, nb, ms_big), "measured_peak_gbs": l2_peak_big,
+                   "frac": l2_rate(big, nb, ms_big) / l2_peak_big, "ctas": big // 8}}
     return {"workload": f"fast_generate incremental sampling, 30-layer 64/64/256 model, {n_streams} streams x {n_steps} steps "
                         "(greedy, queue_push=output as the reference)",
             "samples_per_s_per_stream": n_steps / (ms * 1e-3), "samples_per_s_total": n_streams * n_steps / (ms * 1e-3),
-            "us_per_step": ms * 1e3 / n_steps, "dtype": "f16 weights and MMA operands, f32 accumulate / state",
+            "us_per_step": ms * 1e3 / n_steps, "prime_ms": ms_prime,
+            "dtype": "f16 weights and MMA operands, f32 accumulate / ring state",
             "many_streams": many,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
-                         "note": "achieved = bytes the kernel requests from L2 (weight-fragment image per CTA of 8 streams per step "
-                                 "+ ring vectors); the image is L2-resident, so this is an L2->SM figure quoted against the HBM "
-                                 "copy peak.  At 64 streams only 8 CTAs run and each is bound by one SM's L2 read rate "
-                                 "(~64 B/clk) and the 31-stage dependency chain; many_streams shows the same kernel on 128 SMs"}}
+                         "bytes_per_step": n_streams * ring_algo + w_algo,
+                         "note": "SURVEY.md 8(d) accounting: algorithmic bytes per step over the step time.  The recurrence is "
+                                 "a 31-stage dependency chain per stream (latency-bound at 64 streams): this fraction measures "
+                                 "how far the kernel is from streaming its state and weights once, not its L2 efficiency"},
+            "l2": {"achieved_gbs": l2_rate(n_streams, n_steps, ms), "measured_peak_gbs": l2_peak, "frac": l2_rate(n_streams, n_steps, ms) / l2_peak,
+                   "ctas": n_ctas, "note": "bytes the kernel requests from L2 (weight-fragment image per CTA of 8 streams per step + "
+                                           "ring vectors) against the L2 read rate the same number of CTAs reach in wn_bench_l2_read"}}
+
+
+def bench_gpu_incumbent(dev, B, steps=3):
+    """What a user of the reference gets on this GPU without this library: the same model built from torch.nn.Conv1d modules
+    (cuDNN / cuBLAS kernels, torch eager autograd, torch.optim.Adam), dense one-hot input generated on the device, the
+    reference's forward + scrambled softmax + CrossEntropyLoss(probabilities) step (wavenet/model.py:86-145,
+    train.py:171-182) - in fp32 and under bf16 autocast.  Same shape as the headline (B x 16000 targets), CUDA-event timed."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    class EagerWaveNet(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.causal = nn.Conv1d(Q, R, 2, bias=False)
+            self.filt = nn.ModuleList(nn.Conv1d(R, D, 2, dilation=d, bias=False) for d in DIL)
+            self.gate = nn.ModuleList(nn.Conv1d(R, D, 2, dilation=d, bias=False) for d in DIL)
+            self.dense = nn.ModuleList(nn.Conv1d(D, R, 1, bias=False) for _ in DIL)
+            self.skip = nn.ModuleList(nn.Conv1d(D, S, 1, bias=False) for _ in DIL)
+            self.p1 = nn.Conv1d(S, S, 1, bias=False)
+            self.p2 = nn.Conv1d(S, Q, 1, bias=False)
+
+        def forward(self, x):
+            W = x.shape[2] - (sum(DIL) + 2) + 1
+            cur = self.causal(x)
+            total = None
+            for i in range(len(DIL)):
+                z = torch.sigmoid(self.gate[i](cur)) * torch.tanh(self.filt[i](cur))
+                dense = self.dense[i](z)
+                cur = dense + cur[:, :, -dense.shape[2]:]
+                sk = self.skip[i](z[:, :, -W:])
+                total = sk if total is None else total + sk
+            out = self.p2(F.relu(self.p1(F.relu(total))))
+            return torch.softmax(out.contiguous().view(-1, Q).float(), dim=1)
+
+    rf = sum(DIL) + 2
+    Lx = rf + WINDOW - 1
+    g = torch.Generator(device=dev).manual_seed(7)
+    idx = torch.randint(0, Q, (B, Lx + 1), generator=g, device=dev)
+    x = F.one_hot(idx[:, :Lx], Q).permute(0, 2, 1).float().contiguous()
+    tgt = idx[:, rf:rf + WINDOW].reshape(-1)
+    out = {}
+    for name, autocast in (("fp32", False), ("bf16_autocast", True)):
+        torch.manual_seed(0)
+        net = EagerWaveNet().to(dev)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                probs = net(x)
+            loss = F.cross_entropy(probs, tgt)
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"ms_per_step": ms, "samples_per_s": B * WINDOW / (ms * 1e-3), "loss": float(loss)}
+        del net, opt
+        torch.cuda.empty_cache()
+    out["workload"] = (f"torch eager (nn.Conv1d -> cuDNN/cuBLAS, autograd, torch.optim.Adam) on the same B200, same model and "
+                       f"shape (batch {B} x 16000 targets, dense one-hot input resident on the device), {steps} steps")
+    out["tf32"] = bool(torch.backends.cudnn.allow_tf32)
+    return out
+
+
+def bench_cfg1(dev, cpu_seconds=6.0):
+    """BASELINE.json configs[0]: the reference's default shape (10 x 3 layers, 32 residual / 32 dilation / 256 skip channels)
+    on one 16000-sample clip (W = 12930 targets), batch 1, Adam - on the GPU through the package (mode='auto': the tcgen05
+    kernels with channels zero-padded to 64) and on the host cores with the oracle port, same shape."""
+    import torch
+    from music_b200.wavenet.model import wavenet
+    from music_b200.wavenet.train import Trainer
+    from oracle import wavenet_oracle as O
+    torch.manual_seed(0)
+    net = wavenet(2, DIL, 32, 32, 256, Q, False).to(dev)
+    rf = net.receptive_field
+    Lc = 16000
+    W = Lc - rf + 1
+    codes = O.mu_law_encode(O.synthetic_audio(1, Lc + 1, seed=99), Q)
+    piece, tgt = codes[:, :Lc].contiguous().to(dev), codes[:, rf:rf + W].contiguous().to(dev)
+    tr = Trainer(net, "adam", learning_rate=1e-4, distributed=False)
+    for _ in range(3):
+        tr.step(piece, tgt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    for _ in range(n):
+        loss = tr.step(piece, tgt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    # CPU, same shape
+    torch.set_num_threads(os.cpu_count())
+    st = O.init_wavenet_state(DIL, 32, 32, 256, Q, False, seed=0)
+    x = O.one_hot(codes[:, :Lc], Q)
+    ts = O.TrainState(st, "adam", lr=1e-4)
+    O.train_step(ts, DIL, x, codes[:, rf:rf + W].contiguous())
+    t0 = time.perf_counter()
+    k = 0
+    while k < 2 or time.perf_counter() - t0 < cpu_seconds:
+        O.train_step(ts, DIL, x, codes[:, rf:rf + W].contiguous())
+        k += 1
+    dt = (time.perf_counter() - t0) / k
+    return {"workload": "wavenet/train.py default shape: 30 layers (1..512 x3), 32 residual / 32 dilation / 256 skip ch, 1 clip of "
+                        f"16000 samples (W = {W} targets), Adam",
+            "gpu": {"samples_per_s": W / (ms * 1e-3), "ms_per_step": ms, "mode": net.mode, "loss": float(loss),
+                    "note": "tcgen05 kernels, channels zero-padded 32 -> 64; 1 clip = 126 tiles per layer < 148 SMs"},
+            "cpu": {"samples_per_s": W / dt, "s_per_step": dt, "cores": os.cpu_count(), "kind": "port", "steps": k}}
 
 
 def bench_autoencoder(dev, steps=3, world=1, rank=0):
@@ -309,7 +470,11 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--gen-steps", type=int, default=2000, help="incremental-generation steps timed per stream (0 = skip)")
+    ap.add_argument("--gen-steps", type=int, default=160000,
+                    help="incremental-generation steps timed per stream (configs[3]: 160000 = 10 s of audio; 0 = skip)")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip the torch-eager GPU incumbent leg")
+    ap.add_argument("--no-cfg1", action="store_true", help="skip the configs[0] (32/32/256, one clip) leg")
+    ap.add_argument("--no-dense-e2e", action="store_true", help="skip the end-to-end variant fed with the reference loader's dense (B,256,L) batch")
     ap.add_argument("--gen-streams", type=int, default=64)
     ap.add_argument("--no-ae", action="store_true", help="skip the autoencoder (configs[4] shape, fp32 check mode) leg")
     args = ap.parse_args()
@@ -382,24 +547,48 @@ def main():
     # Every step's batch is copied from pinned host memory inside the timed region (K copies for K steps) and its loss
     # is read back; the package's BatchStager puts the copy of batch i + 1 on a copy stream under step i.
     from music_b200.wavenet.train import BatchStager
-    stager = BatchStager(dev)
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    stager.put(host_pieces[0], host_targets[0])
-    for i in range(K):
-        d_piece, d_target = stager.get()
-        if i + 1 < K:
-            stager.put(host_pieces[(i + 1) % n_batches], host_targets[(i + 1) % n_batches])
-        l = trainer.step(d_piece, d_target)
-        stager.done()
-        loss_host.copy_(l, non_blocking=True)
-    e3.record()
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
-    h2d = d_piece.numel() * 8 + d_target.numel() * 8
+
+    def run_e2e(h_pieces, h_targets, n_steps):
+        """n_steps steps fed from pinned host memory through BatchStager; the stager's device slots are allocated and
+        the pipeline is primed by two untimed warm-up steps, so the timed region holds exactly one H2D copy per step."""
+        stager = BatchStager(dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = n_steps + 2
+        stager.put(h_pieces[0], h_targets[0])
+        for i in range(total):
+            if i == 2:
+                barrier()
+                ev0.record()
+            d_piece, d_target = stager.get()
+            if i + 1 < total:
+                stager.put(h_pieces[(i + 1) % len(h_pieces)], h_targets[(i + 1) % len(h_pieces)])
+            l = trainer.step(d_piece, d_target)
+            stager.done()
+            loss_host.copy_(l, non_blocking=True)
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1), d_piece.numel() * d_piece.element_size() + d_target.numel() * d_target.element_size()
+
+    ms_e2e, h2d = run_e2e(host_pieces, host_targets, K)
     d2h = 4
+    # the same through the reference loader's own batch format: dense (B,256,L) float "one-hot" pieces (faster_audio_data.py:62-83)
+    dense_e2e = None
+    if not args.no_dense_e2e:
+        try:
+            nd = 2
+            h_dense = [torch.nn.functional.one_hot(host_pieces[i], Q).permute(0, 2, 1).float().contiguous().pin_memory() for i in range(nd)]
+            kd = max(3, K // 2)
+            ms_d, h2d_d = run_e2e(h_dense, host_targets[:nd], kd)
+            td = torch.tensor([ms_d], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            dense_e2e = {"value": world * B * WINDOW * kd / (float(td[0]) * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_d,
+                         "d2h_bytes_per_step": 4, "ms_per_step": float(td[0]) / kd,
+                         "input": "dense float32 (B,256,L) one-hot pieces as the reference's audio_data_loader yields them"}
+            del h_dense
+        except Exception as exc:
+            dense_e2e = {"error": repr(exc)}
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -452,9 +641,46 @@ def main():
                "sample": f"oracle port of wavenet/model.py + train.py:171-182 step, torch CPU fp32, cfg-2 model, "
                          f"1 clip x {WINDOW} targets per step, {n} steps ({dt:.2f} s/step)"}
 
+    # strong-scaling reading of configs[2]: global batch 128 at 2 / 4 GPUs (64 / 32 clips per GPU); 8 GPUs x 16 is the headline itself
+    strong = None
+    if world in (2, 4):
+        try:
+            Bs = 128 // world
+            audio_s = O.synthetic_audio(Bs, Lx + 1, seed=4321 + rank)
+            codes_s = mu_law_encode(audio_s.to(dev), Q)
+            p_s, t_s = codes_s[:, :Lx].contiguous(), codes_s[:, rf:rf + WINDOW].contiguous()
+            for _ in range(2):
+                trainer.step(p_s, t_s)
+            barrier()
+            es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ks = max(3, K // 2)
+            es0.record()
+            for _ in range(ks):
+                trainer.step(p_s, t_s)
+            es1.record()
+            barrier()
+            ts_ = torch.tensor([es0.elapsed_time(es1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+            strong = {"global_batch": 128, "per_gpu_batch": Bs, "ms_per_step": float(ts_[0]) / ks,
+                      "value": 128 * WINDOW * ks / (float(ts_[0]) * 1e-3), "unit": "samples/s", "scaling": "strong"}
+            del p_s, t_s, codes_s
+        except Exception as exc:
+            strong = {"error": repr(exc)}
+
     gen = None
     if rank == 0 and world == 1 and args.gen_steps > 0:
         gen = bench_generation(net, args.gen_streams, args.gen_steps, dev)
+    incumbent = cfg1 = None
+    if rank == 0 and world == 1 and not args.no_incumbent:
+        try:
+            incumbent = bench_gpu_incumbent(dev, B)
+        except Exception as exc:
+            incumbent = {"error": repr(exc)}
+    if rank == 0 and world == 1 and not args.no_cfg1:
+        try:
+            cfg1 = bench_cfg1(dev)
+        except Exception as exc:
+            cfg1 = {"error": repr(exc)}
     ae = None
     if not args.no_ae:                  # every rank takes part (one gradient all-reduce per step when world > 1)
         try:
@@ -468,10 +694,11 @@ def main():
                "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
                "config": workload_config(world, B),
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "ms_per_step": ms_e2e / K},
+                       "ms_per_step": ms_e2e / K, "input": "int64 mu-law codes (B,L) + targets (B,W), pinned host memory",
+                       "dense_input": dense_e2e},
                "gpu_launches": int(launches), "loss": last_loss, "clocks": clocks, "roofline": roofline,
                "cpu_baseline": cpu, "train_flops_per_sample": 3 * flops_per_sample(), "generation": gen,
-               "autoencoder": ae, "kernels": breakdown}
+               "autoencoder": ae, "gpu_incumbent": incumbent, "cfg1": cfg1, "strong_scaling": strong, "kernels": breakdown}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -85,6 +85,11 @@ int wn_mulaw_encode(const float* d_audio, int64_t n, int32_t q, const float* d_t
 int wn_mulaw_decode(const int64_t* d_codes, int64_t n, int32_t q, const float* d_values,
                     float* d_audio, void* stream);
 
+/* ---- loader one-hot : one_hot_encode, wavenet/faster_audio_data.py:62-83, on the device ------------------------------
+ * d_codes (B,T) int64 -> d_out (B,Q,T) fp32.  transpose = 0 reproduces the reference bit for bit: it builds a (T,Q) one-hot
+ * and RESHAPES it to (Q,T) (:77-81), which is not a one-hot; transpose = 1 gives the true one-hot.  Only the codes cross PCIe. */
+int wn_onehot_encode(const int64_t* d_codes, int32_t B, int32_t T, int32_t q, int32_t transpose, float* d_out, void* stream);
+
 /* ---- model plan : wavenet.__init__ / calc_receptive_field, wavenet/model.py:8-84 ------ */
 int wn_model_create(const wn_config* cfg, wn_model** out);
 int wn_model_destroy(wn_model* m);
@@ -219,6 +224,10 @@ int wn_ae_backward(wn_ae* a, int32_t B, int32_t L, const float* d_x, const int64
 uint64_t wn_launch_count(void);                 /* kernels launched by this library so far */
 int wn_profile_enable(int32_t on);              /* bracket every launch with CUDA events on its stream */
 int wn_profile_report(char* buf, size_t cap);   /* sync; "name count total_ms" lines, longest first; clears */
+
+/* L2 -> SM read-bandwidth probe (bench.py): n_ctas CTAs each stream the L2-resident buffer `iters` times with 128-bit loads,
+ * like the generation kernel's CTAs stream the shared weight image.  bytes * n_ctas * iters / time = achieved L2 read rate. */
+int wn_bench_l2_read(const void* d_buf, int64_t bytes, int32_t n_ctas, int32_t iters, void* d_sink, void* stream);
 
 /* ---- self tests of the tcgen05 / TMA building blocks (used by tests/, not by the product) -- */
 /* Runs D = A*B^T tiles through TMA -> UMMA -> TMEM -> registers for the operand layouts the

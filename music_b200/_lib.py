@@ -52,6 +52,7 @@ SIGNATURES = {
     "wn_init": (C.c_int, [C.c_int]),
     "wn_mulaw_encode": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "wn_mulaw_decode": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "wn_onehot_encode": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "wn_model_create": (C.c_int, [C.POINTER(wn_config), C.POINTER(_p)]),
     "wn_model_destroy": (C.c_int, [_p]),
     "wn_model_param_count": (C.c_int64, [_p]),
@@ -91,6 +92,7 @@ SIGNATURES = {
     "wn_launch_count": (C.c_uint64, []),
     "wn_profile_enable": (C.c_int, [_i32]),
     "wn_profile_report": (C.c_int, [C.c_char_p, _sz]),
+    "wn_bench_l2_read": (C.c_int, [_p, _i64, _i32, _i32, _p, _p]),
 }
 
 _lib = None

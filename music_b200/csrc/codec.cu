@@ -38,10 +38,35 @@ __global__ void __launch_bounds__(256) mulaw_decode_kernel(const int64_t* __rest
   }
 }
 
+// one_hot_encode of wavenet/faster_audio_data.py:62-83 on the device.  The reference builds a (T, Q) one-hot and RESHAPES it
+// to (Q, T) (:77-81), so the 1 of sample t sits at flat offset t * Q + code[t] of the (Q, T) plane; the true one-hot
+// (transpose) has it at code[t] * T + t.  The plane is cleared by a memset; this kernel writes the T ones.
+__global__ void __launch_bounds__(256) onehot_scatter_kernel(const int64_t* __restrict__ codes, int T, int q, int transpose,
+                                                             float* __restrict__ out) {
+  const int b = blockIdx.y;
+  float* plane = out + (int64_t)b * q * T;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    int64_t c = codes[(int64_t)b * T + t];
+    c = c < 0 ? 0 : (c >= q ? q - 1 : c);
+    plane[transpose ? c * T + t : (int64_t)t * q + c] = 1.0f;
+  }
+}
+
 }  // namespace
 }  // namespace wn
 
 using namespace wn;
+
+extern "C" int wn_onehot_encode(const int64_t* d_codes, int32_t B, int32_t T, int32_t q, int32_t transpose, float* d_out, void* stream) {
+  WN_REQUIRE(g_inited, WN_ERR_UNSUPPORTED, "wn_init() has not succeeded: no sm_100 device, no fallback");
+  WN_REQUIRE(d_codes && d_out && B > 0 && T > 0 && q >= 2, WN_ERR_INVALID, "wn_onehot_encode: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  WN_CHECK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)B * q * T * sizeof(float), s));
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(T, 256), 64), (unsigned)B);
+  onehot_scatter_kernel<<<grid, 256, 0, s>>>(d_codes, T, q, transpose, d_out);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
 
 extern "C" int wn_mulaw_encode(const float* d_audio, int64_t n, int32_t q, const float* d_thresholds, int64_t* d_codes, void* stream) {
   WN_REQUIRE(g_inited, WN_ERR_UNSUPPORTED, "wn_init() has not succeeded: no sm_100 device, no fallback");

@@ -432,7 +432,9 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
     g.lo_out = reinterpret_cast<__nv_bfloat16*>(Wp + wl.XLO + wl.x_stride * ((i + 1) & 1));
     g.x_out = reinterpret_cast<__nv_bfloat16*>(Wp + wl.X + wl.x_stride * (i + 1 < N ? i + 1 : i));
     g.zcat = reinterpret_cast<__nv_bfloat16*>(Wp + wl.Zcat);
-    WN_PROPAGATE(launch_block_fwd2(fp->block[i], p, g, B, s));
+    static const bool fwd3_env = [] { const char* e = getenv("WN_FWD3"); return e && e[0] == '1'; }();
+    if (fwd3_env && p.ts == nullptr && p.dbg == 0) WN_PROPAGATE(launch_block_fwd3(fp->block[i], p, B, s));
+    else WN_PROPAGATE(launch_block_fwd2(fp->block[i], p, g, B, s));
     WN_DEBUG_SYNC("block_fwd", s);
   }
   SkipHeadParams hp{};

@@ -282,7 +282,7 @@ def train(base='./params/', dataloader=None, rank=None):
     One process per GPU: run it directly for one GPU, or under `torchrun --nproc-per-node N` for data parallelism -
     every rank then trains its slice of each batch, the flat gradient is all-reduced (NCCL avg) inside `Trainer.step`,
     rank 0 alone writes logs and checkpoints, and all ranks meet at a barrier around the checkpoint rotation."""
-    from .faster_audio_data import audio_data_loader
+    from .faster_audio_data import audio_data_loader, one_hot_encode_device
     if not torch.cuda.is_available():
         raise L.WavenetB200Error("music_b200 trains on a B200 only (no CPU fallback)")
     train_params, wavenet_params, dataset_params = get_arguments(base)
@@ -297,7 +297,12 @@ def train(base='./params/', dataloader=None, rank=None):
         else:
             epoch_trained = int(train_params["restore_model"].split('.')[0][7:])
     if dataloader is None:
+        # the dataset hands out integer codes; the reference's (Q, T) "one-hot" (reshape quirk and all) is built on the
+        # device from them (one_hot_encode_device), so 8 bytes per sample cross PCIe instead of 1 KB
+        dataset_params = dict(dataset_params)
+        dataset_params.setdefault("encoding", "codes")
         dataloader = audio_data_loader(**dataset_params)
+    device_encoding = getattr(getattr(dataloader, "dataset", None), "encoding", None) == "codes"
     if world > 1:
         dataloader = _RankShard(dataloader, rank, world)
     net = net.cuda()
@@ -336,6 +341,8 @@ def train(base='./params/', dataloader=None, rank=None):
             nxt = next(batches, None)
             if nxt is not None:                                # staged under the step below
                 stager.put(nxt["audio_piece"], nxt["audio_target"])
+            if device_encoding:
+                piece = one_hot_encode_device(piece, net.quantization_channels)
             total_loss += trainer.step(piece, target)         # accumulated on device: no per-step sync
             stager.done()
             num_trained += 1

@@ -42,3 +42,24 @@ def test_other_q():
     for q in (16, 64):
         assert torch.equal(mu_law_encode(x.cuda(), q).cpu(), O.mu_law_encode(x, q))
         assert torch.equal(mu_law_decode(torch.arange(q).cuda(), q).cpu(), O.mu_law_decode(torch.arange(q), q))
+
+
+def test_device_one_hot_encode_matches_reference_loader(golden):
+    """one_hot_encode (wavenet/faster_audio_data.py:62-83) on the device, against the UNMODIFIED reference's own output
+    (tests/golden/loader.npz) and against the host mirror on a full-size batch: the reshape quirk bit for bit, and the true
+    one-hot; only the integer codes cross PCIe."""
+    from music_b200.wavenet.faster_audio_data import one_hot_encode, one_hot_encode_device
+    z = golden("loader")
+    codes = torch.from_numpy(z["onehot_in"].astype(np.int64))
+    got = one_hot_encode_device(codes.cuda(), 256).cpu().numpy()
+    assert got.shape == z["onehot_out"].shape and np.array_equal(got, z["onehot_out"])
+    g = torch.Generator().manual_seed(3)
+    batch = torch.randint(0, 256, (3, 19070), generator=g)
+    dev = one_hot_encode_device(batch.cuda(), 256)
+    dev_t = one_hot_encode_device(batch.cuda(), 256, transpose=True)
+    for b in range(3):
+        ref = one_hot_encode({"audio_piece": batch[b], "audio_target": torch.zeros(1)})["audio_piece"]
+        assert torch.equal(dev[b].cpu(), ref)
+    assert torch.equal(dev_t.argmax(dim=1).cpu(), batch) and float(dev_t.sum()) == batch.numel()
+    with pytest.raises(Exception):
+        one_hot_encode_device(batch, 256)          # host tensor: refused, no CPU fallback

@@ -25,3 +25,5 @@ def test_windowing_and_reshape_onehot_match_reference(golden, tmp_path):
     ds_idx = audio_dataset(str(path), int(z["rf"]), int(z["window"]), encoding="index")
     s = ds_idx[0]
     assert s["audio_piece"].dtype == torch.int64 and s["audio_piece"].shape[0] == int(z["rf"]) + int(z["window"]) - 1
+    ds_codes = audio_dataset(str(path), int(z["rf"]), int(z["window"]), encoding="codes")
+    assert torch.equal(ds_codes[3]["audio_piece"], ds_idx[3]["audio_piece"])
