@@ -14,6 +14,7 @@
 
 #include "check_kernels.cuh"
 #include "fast_bwd_kernels.cuh"
+#include "fast_kernels.cuh"
 #include "fast_layout.cuh"
 #include "tc05.cuh"
 
@@ -182,6 +183,30 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tma_store_3d(&tmOut, ot, p.out_col0 + nt * NT, row0, b, p.pol_out);
           tma_store_commit();
         }
+      } else if constexpr (EPI == EPI_LOGITS || EPI == EPI_LOGITS_BIAS) {
+        // head output: fp32 logits written straight into the (B, Q, W) tensor (lanes = consecutive time steps: coalesced per column)
+        mbar_wait(&acc_full[as], aph);
+        tc_fence_after();
+        const int tw = row - p.lg_pad;
+        const bool ok = valid && tw >= 0 && tw < p.lg_W;
+        float* out = p.logits + ((int64_t)b * p.lg_Q + nt * NT) * p.lg_W + tw;
+#pragma unroll 1
+        for (int c = 0; c < NT / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(src + c * 32, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float a = __uint_as_float(v[j]);
+              if (EPI == EPI_LOGITS_BIAS) a += p.bias[nt * NT + c * 32 + j];
+              if (nt * NT + c * 32 + j < p.lg_Q) out[(int64_t)(c * 32 + j) * p.lg_W] = a;
+            }
+          }
+        }
+        tc_fence_before();
+        epi_bar_sync();
+        if (tid == 0) mbar_arrive(&acc_empty[as]);
       } else {
         mbar_wait(&acc_full[as], aph);
         tc_fence_after();
@@ -192,7 +217,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tmem_ld_wait();
           uint32_t packed[16];
           uint32_t ax[16];
-          if (EPI != EPI_PLAIN && valid) {
+          if ((EPI == EPI_MASK || EPI == EPI_ADD) && valid) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint4 a4 = *reinterpret_cast<const uint4*>(auxp + c * 32 + q * 8);
@@ -212,6 +237,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             } else if (EPI == EPI_ADD) {
               a0 += __low2float(x2);
               a1 += __high2float(x2);
+            } else if (EPI == EPI_RELU || EPI == EPI_RELU_BIAS) {
+              if (EPI == EPI_RELU_BIAS) {
+                a0 += p.bias[nt * NT + c * 32 + 2 * j];
+                a1 += p.bias[nt * NT + c * 32 + 2 * j + 1];
+              }
+              a0 = fmaxf(a0, 0.f);
+              a1 = fmaxf(a1, 0.f);
             }
             packed[j] = valid ? pack_bf16(a0, a1) : 0u;
           }
@@ -219,7 +251,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 val = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-            *reinterpret_cast<uint4*>(ot + sw128_chunk(tid, (c & 1) * 4 + q)) = val;
+            const int qq = (c & 1) * 4 + q;      // 16-byte chunk of this thread's row inside the 64-column staging tile
+            const uint32_t o = p.out_tiled ? (uint32_t)(((((tid >> 5) * 4 + (qq >> 1)) * 32 + (tid & 31)) << 5) + ((qq & 1) << 4)) : sw128_chunk(tid, qq);
+            *reinterpret_cast<uint4*>(ot + o) = val;
           }
         }
         fence_proxy_async_smem();
@@ -227,8 +261,16 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         epi_bar_sync();
         if (tid == 0) {
           mbar_arrive(&acc_empty[as]);
-          for (int j = 0; j < NT / 64; ++j)
-            tma_store_3d(&tmOut, sm + Cfg::OUT_OFF + j * TILE, p.out_col0 + nt * NT + 64 * j, row0, b);
+          for (int j = 0; j < NT / 64; ++j) {
+            if (p.n_total > 0 && nt * NT + 64 * j >= p.n_total) break;      // partial last column tile
+            if (p.out_tiled) {      // tiled skip-gradient layout (see gemm_nt_resb_kernel): the in-range 32-row blocks are one contiguous run
+              const int rb0 = row0 >> 5, nb = min(4, p.out_nblk - rb0);
+              const int64_t lb = (int64_t)((p.out_col0 + nt * NT) / 64 + j) * p.n_batches + b;
+              if (nb > 0) bulk_store(p.out_tiled + ((lb * p.out_nblk + rb0) << 11), sm + Cfg::OUT_OFF + j * TILE, (uint32_t)nb << 12);
+            } else {
+              tma_store_3d(&tmOut, sm + Cfg::OUT_OFF + j * TILE, p.out_col0 + nt * NT + 64 * j, row0, b);
+            }
+          }
           tma_store_commit();
           tma_store_wait_read();
         }
@@ -425,7 +467,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmB1, GemmTnParams p) {
   using Cfg = TnCfg<NB>;
   if (p.y_layers > 0) {      // derive this y-slice's operands (uniform over the CTA)
-    const int mt = blockIdx.y & 1, g = blockIdx.y >> 1;
+    const int n_mt = p.n_mtiles > 0 ? p.n_mtiles : 2;
+    const int mt = blockIdx.y % n_mt, g = blockIdx.y / n_mt;
     p.a_col0 = 128 * mt;
     p.out0 += (int64_t)128 * mt * p.s_m;
     p.out1 += (int64_t)128 * mt * p.s_m;
@@ -682,7 +725,7 @@ __device__ __forceinline__ void ldg_stream32(const void* ptr, uint64_t policy, u
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(ptr));
 }
 
-template <bool BIAS, bool DENSE>
+template <bool BIAS, bool DENSE, bool COND>
 __global__ void __launch_bounds__(576, 1)
 block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
                   const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_dx,
@@ -827,6 +870,10 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       uint32_t zs[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
       if (tau0 >= p.tw_al && tau < p.L)      // tiled layout (GemmNtParams::out_tiled): this warp's 32 rows x 16 channels are 1 KB contiguous
         ldg_stream32(p.dzs + (((((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + ((tau0 - p.tw_al) >> 5) + q4) * 4 + cg) * 32 + lane) << 4), p.pol_first, zs);
+      const float* condp = nullptr;
+      if (COND)      // this row's conditioning vector (rows outside the valid range read frame 0: their results are masked)
+        condp = p.cond + (((int64_t)b * p.cond_frames + (valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0)) * p.cond_layers +
+                          p.cond_layer) * 128 + cg * 16;
       mbar_wait(&fg_full[ph], ph2);
       tc_fence_after();
       uint32_t f[16], g[16];
@@ -845,6 +892,10 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           if (BIAS) {
             fv += p.bias_fg[cg * 16 + 2 * j + e];
             gv += p.bias_fg[64 + cg * 16 + 2 * j + e];
+          }
+          if (COND) {
+            fv += __ldg(condp + 2 * j + e);
+            gv += __ldg(condp + 64 + 2 * j + e);
           }
           const float t = tanh_fast(fv), sg = sigmoid_fast(gv);
           zo[e] = t * sg;
@@ -1272,7 +1323,9 @@ block_bwd5_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 // per-tile resources belong to the tile's parity = its group (TMEM f|g / P buffer, x stage, {A', Q'} stage), so group 1 runs
 // the gate math of tile n + 1 while group 0 waits for the MMAs of tile n and writes its outputs.  What stays shared is
 // sequenced by barriers that complete once per tile, in tile order: the dz accumulator (dz_full / dz_empty) and the
-// dF | dG | z staging tiles (out_full / out_empty).  Differences to block_bwd5 inside a tile: every thread owns 32 rows x 32
+// dF | dG | z staging tiles (out_full / out_empty).  A barrier whose completions are consumed ALTERNATELY by the two groups
+// (dz_full, out_empty) is split per tile parity: an mbarrier wait only names the phase parity, and a group that arrives
+// early at "completion #1" of a barrier still in phase 0 would pass immediately.  Differences to block_bwd5 inside a tile: every thread owns 32 rows x 32
 // columns as two passes of 16 (packed results of the first pass are held in registers), and dW_dense is accumulated from
 // A' and Q' separately (two MMA groups, no S tile), so that epilogue 2 re-reads both in bf16 and sums them in fp32.
 template <bool DENSE>
@@ -1285,7 +1338,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t w_full, x_full[2], x_empty[2], dxi_full[2], dxi_empty[2], fg_full[2], fg_empty[2], p_full[2], st_req[2];
-  __shared__ __align__(8) uint64_t dz_full, dz_empty, out_full, out_empty, wg_done;
+  __shared__ __align__(8) uint64_t dz_full[2], dz_empty, out_full, out_empty[2], wg_done;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -1299,11 +1352,11 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_init(&fg_empty[i], 1);
       mbar_init(&p_full[i], 1);
       mbar_init(&st_req[i], 1);
+      mbar_init(&dz_full[i], 1);
+      mbar_init(&out_empty[i], 1);
     }
-    mbar_init(&dz_full, 1);
     mbar_init(&dz_empty, 1);
     mbar_init(&out_full, 1);
-    mbar_init(&out_empty, 1);
     mbar_init(&wg_done, 1);
     fence_barrier_init();
   }
@@ -1366,7 +1419,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd, k), desc_kmajor(sbase + Bwd5Smem::WDT, k), id_dz, k > 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd + TILE, k), desc_kmajor(sbase + Bwd5Smem::WDT, k), id_dz, true);
-          umma_commit(&dz_full);
+          umma_commit(&dz_full[jd & 1]);
           ++jd;
           continue;
         }
@@ -1391,7 +1444,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
             umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd5Smem::DF, k, TILE), desc_mnmajor(sxa, k, TILE), id_wfg, (jw | k) != 0);
           umma_commit(&x_empty[jw & 1]);
-          umma_commit(&out_empty);
+          umma_commit(&out_empty[jw & 1]);
           ++jw;
           continue;
         }
@@ -1480,7 +1533,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         uint32_t dzv[16];
         if (DENSE) {
           if (ps == 0) {
-            mbar_wait(&dz_full, it & 1);
+            mbar_wait(&dz_full[g], ph2);
             tc_fence_after();
           }
           tmem_ld16(lane_addr + C_DZ + c0, dzv);
@@ -1508,7 +1561,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       group_bar();
       if (leader) mbar_arrive(&dz_empty);
       // the dF | dG | z tiles are free once the MMAs of tile it - 1 (the other group's) have read them
-      if (it > 0) mbar_wait(&out_empty, (it - 1) & 1);
+      if (it > 0) mbar_wait(&out_empty[g ^ 1], ((it - 1) >> 1) & 1);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const uint32_t o0 = sw128_chunk(row, h * 4 + q), o1 = sw128_chunk(row, h * 4 + 2 + q);
@@ -1710,12 +1763,13 @@ __global__ void __launch_bounds__(256) bf16_to_f32_kernel(const __nv_bfloat16* _
 
 // out[c] += sum over b, rows in [row_lo,row_hi) of src[b][row][c]   (bias gradients); C in {64,128,256}
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int C, int64_t bstride, int row_lo,
-                                                          int row_hi, float* __restrict__ out, float* __restrict__ out_hi, int n_valid) {
+                                                          int row_hi, float* __restrict__ out, float* __restrict__ out_hi, int n_valid,
+                                                          int pitch) {
   const int b = blockIdx.y;
   const int col = threadIdx.x % C, rsub = threadIdx.x / C, nsub = 256 / C;
   const int r0 = row_lo + blockIdx.x * 512, r1 = min(row_hi, r0 + 512);
   float acc = 0.f;
-  for (int r = r0 + rsub; r < r1; r += nsub) acc += __bfloat162float(src[(int64_t)b * bstride + (int64_t)r * C + col]);
+  for (int r = r0 + rsub; r < r1; r += nsub) acc += __bfloat162float(src[(int64_t)b * bstride + (int64_t)r * pitch + col]);
   if ((col & 63) >= n_valid) return;                               // channel-padded models: only the real channels have a bias
   if (out_hi && col >= 64) atomicAdd(out_hi + col - 64, acc);      // split output: columns [64,128) go to a second vector
   else atomicAdd(out + col, acc);
@@ -1744,12 +1798,13 @@ int set_smem_once(K kernel, int bytes) {
 }
 
 int launch_colsum_bf16(const void* src, int C, int B, int64_t rows_per_batch, int row_lo, int row_hi, float* out, cudaStream_t s,
-                       int n_valid = 64) {
+                       int n_valid = 64, int pitch = 0) {
   if (row_hi <= row_lo) return WN_OK;
+  if (pitch == 0) pitch = C;
   dim3 grid((unsigned)ceil_div(row_hi - row_lo, 512), (unsigned)B);
   WN_PROF("colsum_bias", s);
-  colsum_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), C, rows_per_batch * C, row_lo, row_hi, out,
-                                          nullptr, n_valid);
+  colsum_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), C, rows_per_batch * pitch, row_lo, row_hi, out,
+                                          nullptr, n_valid, pitch);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -1761,7 +1816,7 @@ int launch_colsum_bf16_split(const void* src, int B, int64_t rows_per_batch, int
   dim3 grid((unsigned)ceil_div(row_hi - row_lo, 512), (unsigned)B);
   WN_PROF("colsum_bias", s);
   colsum_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), 128, rows_per_batch * 128, row_lo, row_hi,
-                                          out_f, out_g, n_valid);
+                                          out_f, out_g, n_valid, 128);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -1796,7 +1851,7 @@ int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStrea
   auto pick = [&](auto kernel_plain, auto kernel_mask, auto kernel_add) {
     return p.epi == EPI_PLAIN ? kernel_plain : (p.epi == EPI_MASK ? kernel_mask : kernel_add);
   };
-  if (NT == 256 && p.nk[0] == 4 && p.nk[1] == 0 && p.n_total > 0 && p.n_total % 64 == 0 && !bwd_env().nt_stream) {
+  if (NT == 256 && p.epi <= EPI_ADD && p.nk[0] == 4 && p.nk[1] == 0 && p.n_total > 0 && p.n_total % 64 == 0 && !bwd_env().nt_stream) {
     // K = 256: weight block resident in shared memory, one column tile per CTA
     const int smem = NtResCfg::TOTAL + 1024;
     auto k = pick(gemm_nt_resb_kernel<EPI_PLAIN>, gemm_nt_resb_kernel<EPI_MASK>, gemm_nt_resb_kernel<EPI_ADD>);
@@ -1806,6 +1861,10 @@ int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStrea
   } else if (NT == 256) {
     const int smem = NtCfg<256>::TOTAL + 1024;
     auto k = pick(gemm_nt_kernel<256, EPI_PLAIN>, gemm_nt_kernel<256, EPI_MASK>, gemm_nt_kernel<256, EPI_ADD>);
+    if (p.epi == EPI_RELU) k = gemm_nt_kernel<256, EPI_RELU>;
+    else if (p.epi == EPI_RELU_BIAS) k = gemm_nt_kernel<256, EPI_RELU_BIAS>;
+    else if (p.epi == EPI_LOGITS) k = gemm_nt_kernel<256, EPI_LOGITS>;
+    else if (p.epi == EPI_LOGITS_BIAS) k = gemm_nt_kernel<256, EPI_LOGITS_BIAS>;
     WN_PROPAGATE(set_smem_once(k, smem));
     WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)grid), dim3(192), smem, s, m.a[0], m.a[1], m.b[0], m.b[1], m.out, p));
   } else if (NT == 64) {
@@ -1826,7 +1885,7 @@ int launch_gemm_tn(int NB, const GemmTnMaps& m, const GemmTnParams& p, cudaStrea
   if (n_items <= 0) return WN_OK;
   int gx = std::min(n_items, g_sm_count), gy = 1;
   if (p.y_layers > 0) {
-    gy = 2 * (int)ceil_div(p.y_layers, 4);
+    gy = (p.n_mtiles > 0 ? p.n_mtiles : 2) * (int)ceil_div(p.y_layers, 4);
     gx = std::max(1, std::min(n_items, g_sm_count / gy));
   }
   const dim3 grid((unsigned)gx, (unsigned)gy);
@@ -1847,8 +1906,12 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   const bool bias = p.b.bias_fg != nullptr, dense = p.b.has_dense != 0;
   const int smem3 = Bwd3Smem::TOTAL + 1024;
   WN_PROF("block_bwd3", s);
-  auto k3 = bias ? (dense ? block_bwd3_kernel<true, true> : block_bwd3_kernel<true, false>)
-                 : (dense ? block_bwd3_kernel<false, true> : block_bwd3_kernel<false, false>);
+  auto k3 = bias ? (dense ? block_bwd3_kernel<true, true, false> : block_bwd3_kernel<true, false, false>)
+                 : (dense ? block_bwd3_kernel<false, true, false> : block_bwd3_kernel<false, false, false>);
+  if (p.b.cond) {      // conditioned decoder of the autoencoder (its conv biases are folded into the conditioning table)
+    WN_REQUIRE(!bias, WN_ERR_INVALID, "conditioned block backward: fold the bias into the conditioning table");
+    k3 = dense ? block_bwd3_kernel<false, true, true> : block_bwd3_kernel<false, false, true>;
+  }
   WN_PROPAGATE(set_smem_once(k3, smem3));
   WN_CHECK_CUDA(launch_pdl(k3, dim3((unsigned)n_ctas), dim3(576), smem3, s, m.x, m.w0, m.w1, m.dx, m.wdT, m.dfg, p));
   WN_CHECK_LAUNCH();
@@ -1871,6 +1934,37 @@ int launch_block_bwd5(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   return WN_OK;
 }
 
+// skip sum + head for skip widths other than 256 (the fused skip_head_kernel keeps its [128 x 256] accumulators in TMEM and is
+// written for S = 256): three GEMMs of the streaming kernel with fused epilogues, intermediates h0 / h1 in HBM (they are
+// saved for the backward anyway):  h0 = relu(Zcat Wskip_cat^T + b) ; h1 = relu(h0 P1^T + b1) ; logits = h1 P2^T + b2   (model.py:134-138)
+int head_forward_generic(const Model& m, const BwdMaps& M, const SkipHeadMaps& H, const SkipHeadParams& hp, int B, int L, cudaStream_t s) {
+  const int Wpad = skip_wp(m, L), N = m.n_layers, S = m.S;
+  const bool bias = hp.bias_skip != nullptr;
+  GemmNtMaps gm{};
+  GemmNtParams gp{};
+  gp.n_batches = B; gp.tile0 = 0; gp.tiles_per_batch = (int)ceil_div(Wpad, 128);
+  gp.row_lo = 0; gp.row_hi = Wpad; gp.nk[1] = 0;
+  // h0
+  gm.a[0] = M.zcat; gm.a[1] = M.zcat; gm.b[0] = H.wsk; gm.b[1] = H.wsk; gm.out = M.h0;
+  gp.n_ntiles = S / 256; gp.n_total = S; gp.nk[0] = N;
+  gp.epi = bias ? EPI_RELU_BIAS : EPI_RELU; gp.bias = hp.bias_skip; gp.tag = "head_skip_gemm";
+  WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
+  WN_DEBUG_SYNC("head skip gemm", s);
+  // h1
+  gm.a[0] = M.h0; gm.a[1] = M.h0; gm.b[0] = H.p1; gm.b[1] = H.p1; gm.out = M.h1;
+  gp.nk[0] = S / 64; gp.bias = hp.bias_p1; gp.tag = "head_p1_gemm";
+  WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
+  WN_DEBUG_SYNC("head p1 gemm", s);
+  // logits
+  gm.a[0] = M.h1; gm.a[1] = M.h1; gm.b[0] = H.p2; gm.b[1] = H.p2; gm.out = M.h1;      // (out map unused)
+  gp.n_ntiles = 1; gp.n_total = 256; gp.nk[0] = S / 64;
+  gp.epi = bias ? EPI_LOGITS_BIAS : EPI_LOGITS; gp.bias = hp.bias_p2;
+  gp.logits = hp.logits; gp.lg_W = hp.W; gp.lg_Q = hp.Q; gp.lg_pad = hp.pad; gp.tag = "head_p2_gemm";
+  WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
+  WN_DEBUG_SYNC("head p2 gemm", s);
+  return WN_OK;
+}
+
 // =============================================================================================== host
 int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int B, int L, const uint8_t* P, uint8_t* Wp,
                    const std::vector<CUtensorMap>& xm, BwdMaps* out) {
@@ -1889,15 +1983,15 @@ int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int
     return tmap_3d(t, Wp + off, cols, Wpad, B, cols, (uint64_t)Wpad * cols, 128);
   };
   WN_PROPAGATE(skip3(&out->dlg, wl.DLG, 256));
-  WN_PROPAGATE(skip3(&out->h0, wl.H0, 256));
-  WN_PROPAGATE(skip3(&out->h1, wl.H1, 256));
-  WN_PROPAGATE(skip3(&out->dh1, wl.DH1, 256));
-  WN_PROPAGATE(skip3(&out->dsk, wl.DSK, 256));
+  WN_PROPAGATE(skip3(&out->h0, wl.H0, m.S));
+  WN_PROPAGATE(skip3(&out->h1, wl.H1, m.S));
+  WN_PROPAGATE(skip3(&out->dh1, wl.DH1, m.S));
+  WN_PROPAGATE(skip3(&out->dsk, wl.DSK, m.S));
   WN_PROPAGATE(skip3(&out->zcat, wl.Zcat, 64 * N));
   WN_PROPAGATE(skip3(&out->dzcat, wl.DZcat, 64 * N));
-  WN_PROPAGATE(tmap_2d(&out->p1T, P + pl.p1T, 256, 256, 256, 256));
-  WN_PROPAGATE(tmap_2d(&out->p2T, P + pl.p2T, 256, 256, 256, 256));
-  WN_PROPAGATE(tmap_2d(&out->wsTcat, P + pl.wsT, 256, (uint64_t)64 * N, 256, 256));
+  WN_PROPAGATE(tmap_2d(&out->p1T, P + pl.p1T, m.S, m.S, m.S, 256));                    // [S in][S out]: B of dSK = dH1 P1
+  WN_PROPAGATE(tmap_2d(&out->p2T, P + pl.p2T, 256, m.S, 256, 256));                    // [S][Q]:        B of dH1 = dLg P2
+  WN_PROPAGATE(tmap_2d(&out->wsTcat, P + pl.wsT, m.S, (uint64_t)64 * N, m.S, 256));    // [64 N][S]:     B of dZcat = dSK Ws
   WN_PROPAGATE(tmap_3d(&out->dxa, Wp + wl.DXa, 64, L, B, 64, (uint64_t)L * 64, 128));
   WN_PROPAGATE(tmap_3d(&out->dxb, Wp + wl.DXb, 64, L, B, 64, (uint64_t)L * 64, 128));
   WN_PROPAGATE(tmap_3d(&out->dfg, Wp + wl.DFG, 128, L, B, 128, (uint64_t)L * 128, 128));
@@ -1962,24 +2056,28 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     GemmNtMaps gm{};
     gm.a[0] = M.dlg; gm.a[1] = M.dlg; gm.b[0] = M.p2T; gm.b[1] = M.p2T; gm.out = M.dh1;
     GemmNtParams gp{};
-    gp.n_batches = B; gp.tile0 = 0; gp.tiles_per_batch = skip_tiles; gp.n_ntiles = 1; gp.n_total = 256;
-    gp.nk[0] = 4; gp.nk[1] = 0;
+    const int S = m.S;
+    gp.n_batches = B; gp.tile0 = 0; gp.tiles_per_batch = skip_tiles; gp.n_ntiles = S / 256; gp.n_total = S;
+    gp.nk[0] = 4; gp.nk[1] = 0;                                  // K = Q = 256
     gp.epi = EPI_MASK; gp.aux = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.H1);
-    gp.aux_bstride = (int64_t)Wpad * 256; gp.aux_rstride = 256; gp.aux_col0 = 0;
+    gp.aux_bstride = (int64_t)Wpad * S; gp.aux_rstride = S; gp.aux_col0 = 0;
     gp.row_lo = 0; gp.row_hi = Wpad; gp.tag = "gemm_nt_dH1";
     WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
     WN_DEBUG_SYNC("gemm_nt dH1", s);
     gm.a[0] = M.dh1; gm.a[1] = M.dh1; gm.b[0] = M.p1T; gm.b[1] = M.p1T; gm.out = M.dsk;
+    gp.nk[0] = S / 64;                                           // K = S (S = 512: the streaming kernel)
     gp.aux = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.H0); gp.tag = "gemm_nt_dSK";
     WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
     WN_DEBUG_SYNC("gemm_nt dSK", s);
   }
   if (bias) {   // bias gradients = column sums of the matching output gradients (pad rows are zero)
     WN_PROPAGATE(launch_colsum_bf16(Wp + wl.DLG, 256, B, Wpad, 0, Wpad, G + m.post2.b, s));
-    WN_PROPAGATE(launch_colsum_bf16(Wp + wl.DH1, 256, B, Wpad, 0, Wpad, G + m.post1.b, s));
-    WN_PROPAGATE(launch_colsum_bf16(Wp + wl.DSK, 256, B, Wpad, 0, Wpad, G + m.layers[0].skip.b, s));
+    for (int c0 = 0; c0 < m.S; c0 += 256) {      // 256 columns per launch of the (B, Wpad, S) tensors
+      WN_PROPAGATE(launch_colsum_bf16(Wp + wl.DH1 + (size_t)c0 * 2, 256, B, Wpad, 0, Wpad, G + m.post1.b + c0, s, 64, m.S));
+      WN_PROPAGATE(launch_colsum_bf16(Wp + wl.DSK + (size_t)c0 * 2, 256, B, Wpad, 0, Wpad, G + m.layers[0].skip.b + c0, s, 64, m.S));
+    }
     if (N > 1) {   // offsets of the skip biases were uploaded behind the pack-job table by fast_pack
-      replicate_kernel<<<N - 1, 256, 0, s>>>(G, reinterpret_cast<const int64_t*>(P + pl.jobs + skip_bias_offs_pos(m)), N, 256);
+      replicate_kernel<<<N - 1, m.S, 0, s>>>(G, reinterpret_cast<const int64_t*>(P + pl.jobs + skip_bias_offs_pos(m)), N, m.S);
       WN_CHECK_LAUNCH();
     }
     WN_DEBUG_SYNC("head bias grads", s);
@@ -1992,8 +2090,9 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     GemmTnParams tp{};
     tp.n_batches = B; tp.tile0 = 0; tp.tiles_per_batch = skip_tiles; tp.m_valid = 128;
     float* base = G + (which == 0 ? m.post2.w : m.post1.w);
-    tp.out0 = base; tp.out1 = base + 64 * 256; tp.s_m = 256; tp.s_n = 1;
-    tp.y_layers = 4; tp.y_off0 = 0; tp.y_stride = 64;      // four 64-column blocks of the 256-wide B operand
+    tp.out0 = base; tp.out1 = base + 64 * m.S; tp.s_m = m.S; tp.s_n = 1;      // (Q, S) / (S, S): rows = A columns, row pitch S
+    tp.n_mtiles = (which == 0 ? m.Q : m.S) / 128;
+    tp.y_layers = m.S / 64; tp.y_off0 = 0; tp.y_stride = 64;                    // 64-column blocks of the S-wide B operand
     tp.tag = "gemm_tn_head";
     WN_PROPAGATE(launch_gemm_tn(4, tm, tp, s));
     WN_DEBUG_SYNC("gemm_tn head", s);
@@ -2005,7 +2104,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     GemmNtParams gp{};
     if (dz_tiled) { gp.out_tiled = reinterpret_cast<__nv_bfloat16*>(Wp + wl.DZcat); gp.out_nblk = (int)ceil_div(Wpad, 32); }
     gp.n_batches = B; gp.tile0 = 0; gp.tiles_per_batch = skip_tiles; gp.n_ntiles = (int)ceil_div(64 * N, 256); gp.n_total = 64 * N;
-    gp.nk[0] = 4; gp.nk[1] = 0; gp.epi = EPI_PLAIN; gp.row_lo = 0; gp.row_hi = Wpad; gp.tag = "gemm_nt_dZcat";
+    gp.nk[0] = m.S / 64; gp.nk[1] = 0; gp.epi = EPI_PLAIN; gp.row_lo = 0; gp.row_hi = Wpad; gp.tag = "gemm_nt_dZcat";
     WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
     WN_DEBUG_SYNC("gemm_nt dZcat", s);
   }
@@ -2017,6 +2116,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     GemmTnParams tp{};
     tp.n_batches = B; tp.tile0 = 0; tp.tiles_per_batch = skip_tiles; tp.m_valid = 128;
     tp.out0 = G; tp.out1 = G + 64 * m.D; tp.s_m = m.D; tp.s_n = 1; tp.n_valid = m.D;      // skip weight (S, D, 1)
+    tp.n_mtiles = m.S / 128;
     tp.y_layers = N; tp.y_off0 = m.layers[0].skip.w;
     tp.y_stride = N > 1 ? m.layers[1].skip.w - m.layers[0].skip.w : 0;
     tp.tag = "gemm_tn_dWs";

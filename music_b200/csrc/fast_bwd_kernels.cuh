@@ -12,7 +12,8 @@ namespace wn {
 //                                               B_seg[n0 + n, b_col0[seg] + k] )            (bf16 out)
 // rows are tiled by 128 inside each batch of a 3-D tensor (cols, rows, batches); n0 = NT * n-tile.
 // ---------------------------------------------------------------------------------------------
-enum { EPI_PLAIN = 0, EPI_MASK = 1, EPI_ADD = 2 };
+// streaming NT = 256 kernel only: EPI_RELU (out = relu(acc [+ bias]) in bf16) and EPI_LOGITS (fp32 (B,Q,W) output of the head)
+enum { EPI_PLAIN = 0, EPI_MASK = 1, EPI_ADD = 2, EPI_RELU = 3, EPI_RELU_BIAS = 4, EPI_LOGITS = 5, EPI_LOGITS_BIAS = 6 };
 struct GemmNtMaps {
   CUtensorMap a[2];   // 3-D (cols, rows, batches) box {64,128,1}
   CUtensorMap b[2];   // 2-D [N rows][K cols]       box {64, NT}
@@ -34,6 +35,9 @@ struct GemmNtParams {
   // [column block of 64 * n_batches + b][row / 32][column group of 16][row % 32][16 columns], out_nblk 32-row blocks per batch row
   __nv_bfloat16* out_tiled;
   int out_nblk;
+  const float* bias;            // EPI_RELU_BIAS / EPI_LOGITS_BIAS: [n_total] added to the accumulator
+  float* logits;                // EPI_LOGITS*: (B, lg_Q, lg_W) fp32; row j of a batch is time step j - lg_pad (rows with j < lg_pad are skipped)
+  int lg_W, lg_Q, lg_pad;
   const char* tag;              // profiler label (host only)
 };
 int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStream_t s);
@@ -50,6 +54,7 @@ struct GemmTnMaps {
 struct GemmTnParams {
   int n_batches, tile0, tiles_per_batch;
   int a_col0, m_valid;
+  int n_mtiles;                 // "all layers" mode: 128-row m-tiles of A (0: the historical 2)
   int n_valid;                  // columns n < n_valid of every 64-column block are flushed (0: all 64) - channel-padded models
   int b_map[4], b_row_off[4], b_col[4];
   float* out0;
@@ -86,6 +91,11 @@ struct BlockBwdParams {
   int d_next, own_row0;         // block_bwd5: dilation of layer i + 1 (row shift of its Q tile); first row of this layer's own first tile
   const float* bias_fg;
   unsigned long long pol_first, pol_last;   // L2 eviction hints (0: none)
+  // additive per-frame conditioning of the [f|g] pre-activations (wavenet_autoencoder `_conditon`, model1.py:227-247): row tau of
+  // batch b adds cond[((b * cond_frames + frame) * cond_layers + layer) * 128 + column], frame = the reference's rule on the local
+  // index tau - s_out and length L - s_out.  null: none.
+  const float* cond;
+  int cond_frames, cond_layers, cond_layer;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -49,7 +49,7 @@ struct Fwd2Smem {
 __device__ __forceinline__ void epi16_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // BIAS and TRACE are compile-time: run-time tests inside the unrolled epilogue loops cost a branch per element
-template <bool BIAS, bool TRACE>
+template <bool BIAS, bool TRACE, bool COND>
 __global__ void __launch_bounds__(576, 1)
 block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
                   const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_wd,
@@ -167,6 +167,10 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       uint8_t* lot = sm + Fwd2Smem::LO + ab * TILE_BYTES;
       // ---- epilogue 1: gate -> z tile (smem, A operand of UMMA #2) and Zcat (global).  z tile `ab` was last read by
       //      UMMA #2 of tile it-2, whose completion (dense_full) every thread waited for in that tile's epilogue 2.
+      const float* condp = nullptr;
+      if (COND)      // this row's conditioning vector (autoencoder decoder; rows outside the valid range are masked anyway)
+        condp = p.cond + (((int64_t)b * p.cond_frames + (valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0)) * p.cond_layers +
+                          p.cond_layer) * 128 + cg * 16;
       mbar_wait(&fg_full[ab], ph2);
       tc_fence_after();
       if (rec) ts[1] = clock64();
@@ -184,6 +188,12 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           f1 += p.bias_fg[cg * 16 + 2 * j + 1];
           g0 += p.bias_fg[64 + cg * 16 + 2 * j];
           g1 += p.bias_fg[64 + cg * 16 + 2 * j + 1];
+        }
+        if (COND) {
+          f0 += __ldg(condp + 2 * j);
+          f1 += __ldg(condp + 2 * j + 1);
+          g0 += __ldg(condp + 64 + 2 * j);
+          g1 += __ldg(condp + 64 + 2 * j + 1);
         }
         float z0 = sigmoid_fast(g0) * tanh_fast(f0), z1 = sigmoid_fast(g1) * tanh_fast(f1);
         if (TRACE && (p.dbg & 8)) { z0 = g0 * f0; z1 = g1 * f1; }
@@ -289,7 +299,7 @@ struct Fwd3Smem {
   static constexpr uint32_t TOTAL = LO + 2 * TILE_BYTES;                                   // 200 KB
 };
 
-template <bool BIAS>
+template <bool BIAS, bool COND>
 __global__ void __launch_bounds__(608, 1)
 block_fwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
                   const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_wd,
@@ -419,6 +429,10 @@ block_fwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int tau = tau0 + row;
       const bool valid = (tau >= p.s_out) && (tau < p.L);
       uint8_t* xt = sm + Fwd3Smem::IN + st * Fwd3Smem::IN_STAGE + TILE_BYTES;      // x_i[tau] (residual) -> x_{i+1} hi
+      const float* condp = nullptr;
+      if (COND)      // this row's conditioning vector (autoencoder decoder; rows outside the valid range are masked anyway)
+        condp = p.cond + (((int64_t)b * p.cond_frames + (valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0)) * p.cond_layers +
+                          p.cond_layer) * 128;
       // ---- epilogue 1: gate -> z tile (A operand of UMMA #2, source of the Zcat store)
       mbar_wait(&fg_full[g], ph2);
       tc_fence_after();
@@ -439,6 +453,12 @@ block_fwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             f1 += p.bias_fg[c0 + 2 * j + 1];
             g0 += p.bias_fg[64 + c0 + 2 * j];
             g1 += p.bias_fg[64 + c0 + 2 * j + 1];
+          }
+          if (COND) {
+            f0 += __ldg(condp + c0 + 2 * j);
+            f1 += __ldg(condp + c0 + 2 * j + 1);
+            g0 += __ldg(condp + 64 + c0 + 2 * j);
+            g1 += __ldg(condp + 64 + c0 + 2 * j + 1);
           }
           const float z0 = sigmoid_fast(g0) * tanh_fast(f0), z1 = sigmoid_fast(g1) * tanh_fast(f1);
           pz[ps * 8 + j] = valid ? pack_bf16(z0, z1) : 0u;
@@ -525,13 +545,16 @@ int launch_block_fwd3(const BlockFwdMaps& m, const BlockFwdParams& p, int n_batc
   const int n_items = n_batches * p.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
   const bool bias = p.bias_fg != nullptr;
-  auto k = bias ? block_fwd3_kernel<true> : block_fwd3_kernel<false>;
-  static const void* configured[2] = {};
-  if (configured[bias] == nullptr) {
+  const bool cond = p.cond != nullptr;
+  auto k = cond ? (bias ? block_fwd3_kernel<true, true> : block_fwd3_kernel<false, true>)
+                : (bias ? block_fwd3_kernel<true, false> : block_fwd3_kernel<false, false>);
+  static const void* configured[4] = {};
+  const int slot = (cond ? 2 : 0) + (bias ? 1 : 0);
+  if (configured[slot] == nullptr) {
     WN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[bias] = reinterpret_cast<const void*>(k);
+    configured[slot] = reinterpret_cast<const void*>(k);
   }
-  WN_PROF("block_fwd", s);
+  WN_PROF("block_fwd3", s);
   WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)std::min(n_items, g_sm_count)), dim3(608), smem, s, m.x, m.w0, m.w1, m.wd, m.xo, m.loo, m.z, m.lo, p,
                            n_batches));
   WN_CHECK_LAUNCH();
@@ -543,10 +566,14 @@ int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, const Bloc
   const int n_items = n_batches * p.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
   const bool trace = p.ts != nullptr || p.dbg != 0, bias = p.bias_fg != nullptr;
-  auto k = trace ? (bias ? block_fwd2_kernel<true, true> : block_fwd2_kernel<false, true>)
-                 : (bias ? block_fwd2_kernel<true, false> : block_fwd2_kernel<false, false>);
-  static const void* configured[4] = {};
-  const int slot = (trace ? 2 : 0) + (bias ? 1 : 0);
+  auto k = trace ? (bias ? block_fwd2_kernel<true, true, false> : block_fwd2_kernel<false, true, false>)
+                 : (bias ? block_fwd2_kernel<true, false, false> : block_fwd2_kernel<false, false, false>);
+  static const void* configured[6] = {};
+  int slot = (trace ? 2 : 0) + (bias ? 1 : 0);
+  if (p.cond) {      // conditioned decoder of the autoencoder
+    k = bias ? block_fwd2_kernel<true, false, true> : block_fwd2_kernel<false, false, true>;
+    slot = 4 + (bias ? 1 : 0);
+  }
   if (configured[slot] == nullptr) {
     WN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[slot] = reinterpret_cast<const void*>(k);

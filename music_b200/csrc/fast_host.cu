@@ -64,13 +64,13 @@ int tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, ui
 // wavenet_params: 32 / 32) run through the same kernels ZERO-PADDED to 64: padded weight rows / columns are zero in the packed
 // image, so padded activations stay exactly zero (tanh(0) sigmoid(0) = 0, dense rows 0) and their gradients are never read.
 bool fast_supported(const Model& m) {
-  return m.R >= 1 && m.R <= 64 && m.D >= 1 && m.D <= 64 && m.S == 256 && m.Q == 256 && m.n_layers >= 1 && m.n_layers <= 64;
+  return m.R >= 1 && m.R <= 64 && m.D >= 1 && m.D <= 64 && (m.S == 256 || m.S == 512) && m.Q == 256 && m.n_layers >= 1 && m.n_layers <= 64;
 }
 bool fast_gen_supported(const Model& m) { return m.R == 64 && m.D == 64 && m.S == 256 && m.Q == 256 && m.n_layers >= 1; }
 
 static int require_supported(const Model& m) {
   WN_REQUIRE(fast_supported(m), WN_ERR_UNSUPPORTED,
-             "bf16 tensor-core mode is specialised for residual, dilation <= 64 and skip = quantization = 256 channels "
+             "bf16 tensor-core mode is specialised for residual, dilation <= 64, skip 256 or 512 and quantization 256 channels "
              "(got R=%d D=%d S=%d Q=%d); use mode fp32 for other shapes",
              m.R, m.D, m.S, m.Q);
   return WN_OK;
@@ -91,22 +91,23 @@ PackLayout pack_layout(const Model& m) {
   p.bias_c = take(64 * 4);
   p.bias_fg = take((size_t)N * 128 * 4);
   p.bias_d = take((size_t)N * 64 * 4);
-  p.bias_skip = take(256 * 4);
-  p.bias_p1 = take(256 * 4);
+  const size_t S = (size_t)m.S;
+  p.bias_skip = take(S * 4);
+  p.bias_p1 = take(S * 4);
   p.bias_p2 = take(256 * 4);
   p.wfg0 = take((size_t)N * 128 * 64 * 2);
   p.wfg1 = take((size_t)N * 128 * 64 * 2);
   p.wd = take((size_t)N * 64 * 64 * 2);
-  p.wscat = take((size_t)256 * 64 * N * 2);
-  p.p1 = take(256 * 256 * 2);
-  p.p2 = take(256 * 256 * 2);
+  p.wscat = take(S * 64 * N * 2);               // [S][64 N]
+  p.p1 = take(S * S * 2);                        // [S out][S in]
+  p.p2 = take(256 * S * 2);                      // [Q][S]
   // transposed images for the data-gradient GEMMs
   p.wfgT0 = take((size_t)N * 64 * 128 * 2);     // [64 r][128 o]
   p.wfgT1 = take((size_t)N * 64 * 128 * 2);
   p.wdT = take((size_t)N * 64 * 64 * 2);        // [64 d][64 r]
-  p.wsT = take((size_t)N * 64 * 256 * 2);       // [64 d][256 s]
-  p.p1T = take(256 * 256 * 2);
-  p.p2T = take(256 * 256 * 2);
+  p.wsT = take((size_t)N * 64 * S * 2);         // [64 d][S]
+  p.p1T = take(S * S * 2);                       // [S in][S out]
+  p.p2T = take(S * 256 * 2);                     // [S][Q]
   p.gen_frag = take(fast_gen_supported(m) ? fast_gen_frag_bytes(m) : 0);
   p.total = off;
   return p;
@@ -206,14 +207,14 @@ static void build_jobs(const Model& m, const PackLayout& pl, std::vector<PackJob
     add(PJ_BF16_T, l.filt, 1, t1, 128, 0, 0);
     add(PJ_BF16_T, l.gate, 1, t1, 128, 0, 64);
     add(PJ_BF16_T, l.dense, 0, pl.wdT + (size_t)i * 64 * 64 * 2, 64, 0, 0);
-    add(PJ_BF16_T, l.skip, 0, pl.wsT + (size_t)i * 64 * 256 * 2, 256, 0, 0);
+    add(PJ_BF16_T, l.skip, 0, pl.wsT + (size_t)i * 64 * m.S * 2, m.S, 0, 0);
     add_bias(l.filt, pl.bias_fg, i * 128);
     add_bias(l.gate, pl.bias_fg, i * 128 + 64);
     add_bias(l.dense, pl.bias_d, i * 64);
   }
-  add(PJ_BF16, m.post1, 0, pl.p1, 256, 0, 0);
-  add(PJ_BF16, m.post2, 0, pl.p2, 256, 0, 0);
-  add(PJ_BF16_T, m.post1, 0, pl.p1T, 256, 0, 0);
+  add(PJ_BF16, m.post1, 0, pl.p1, m.S, 0, 0);
+  add(PJ_BF16, m.post2, 0, pl.p2, m.S, 0, 0);
+  add(PJ_BF16_T, m.post1, 0, pl.p1T, m.S, 0, 0);
   add(PJ_BF16_T, m.post2, 0, pl.p2T, 256, 0, 0);
   add_bias(m.post1, pl.bias_p1, 0);
   add_bias(m.post2, pl.bias_p2, 0);
@@ -244,7 +245,7 @@ int fast_pack(Model& m, const float* d_params, void* d_packed, cudaStream_t s) {
   WN_CHECK_LAUNCH();
   WN_DEBUG_SYNC("pack_jobs", s);
   if (m.use_bias) {
-    bias_skip_sum_kernel<<<1, 256, 0, s>>>(d_params, reinterpret_cast<const int64_t*>(P + pl.jobs + skip_bias_offs_pos(m)),
+    bias_skip_sum_kernel<<<1, m.S, 0, s>>>(d_params, reinterpret_cast<const int64_t*>(P + pl.jobs + skip_bias_offs_pos(m)),
                                            m.n_layers, reinterpret_cast<float*>(P + pl.bias_skip));
     WN_CHECK_LAUNCH();
   }
@@ -266,13 +267,13 @@ WsLayout ws_layout(const Model& m, int B, int L) {
   w.X = take(w.x_stride * N);
   w.XLO = take(w.x_stride * 2);
   w.Zcat = take((size_t)B * W * 64 * N * 2);
-  w.H0 = take((size_t)B * W * 256 * 2);
-  w.H1 = take((size_t)B * W * 256 * 2);
+  w.H0 = take((size_t)B * W * m.S * 2);
+  w.H1 = take((size_t)B * W * m.S * 2);
   w.X0f = take((size_t)B * L * 64 * 4);         // fp32 causal output (dense-input path only)
   // backward
   w.DLG = take((size_t)B * W * 256 * 2);
-  w.DH1 = take((size_t)B * W * 256 * 2);
-  w.DSK = take((size_t)B * W * 256 * 2);
+  w.DH1 = take((size_t)B * W * m.S * 2);
+  w.DSK = take((size_t)B * W * m.S * 2);
   w.DZcat = take((size_t)B * align_up((size_t)W, 32) * 64 * N * 2);      // (rows padded to 32 for the tiled layout)
   w.DXa = take((size_t)B * L * 64 * 2);
   w.DXb = take((size_t)B * L * 64 * 2);
@@ -318,11 +319,11 @@ static int build_maps(Model& m, FastPlan* fp, int B, int L, const void* d_packed
   }
   SkipHeadMaps& h = fp->head;
   WN_PROPAGATE(tmap_2d(&h.zcat, Wp + wl.Zcat, 64 * N, (uint64_t)B * W, 64 * N, 128));
-  WN_PROPAGATE(tmap_2d(&h.wsk, P + pl.wscat, 64 * N, 256, 64 * N, 256));
-  WN_PROPAGATE(tmap_2d(&h.p1, P + pl.p1, 256, 256, 256, 256));
-  WN_PROPAGATE(tmap_2d(&h.p2, P + pl.p2, 256, 256, 256, 256));
-  WN_PROPAGATE(tmap_2d(&h.h0, Wp + wl.H0, 256, (uint64_t)B * W, 256, 128));
-  WN_PROPAGATE(tmap_2d(&h.h1, Wp + wl.H1, 256, (uint64_t)B * W, 256, 128));
+  WN_PROPAGATE(tmap_2d(&h.wsk, P + pl.wscat, 64 * N, m.S, 64 * N, 256));
+  WN_PROPAGATE(tmap_2d(&h.p1, P + pl.p1, m.S, m.S, m.S, 256));
+  WN_PROPAGATE(tmap_2d(&h.p2, P + pl.p2, m.S, 256, m.S, 256));
+  WN_PROPAGATE(tmap_2d(&h.h0, Wp + wl.H0, m.S, (uint64_t)B * W, m.S, 128));
+  WN_PROPAGATE(tmap_2d(&h.h1, Wp + wl.H1, m.S, (uint64_t)B * W, m.S, 128));
   WN_PROPAGATE(build_bwd_maps(m, pl, wl, B, L, P, Wp, xm, &fp->bwd));
   fp->key_ws = d_ws;
   fp->key_packed = d_packed;
@@ -447,8 +448,12 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
   hp.bias_skip = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_skip) : nullptr;
   hp.bias_p1 = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_p1) : nullptr;
   hp.bias_p2 = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_p2) : nullptr;
-  WN_PROPAGATE(launch_skip_head(fp->head, hp, s));
-  WN_DEBUG_SYNC("skip_head", s);
+  if (m.S == 256) {
+    WN_PROPAGATE(launch_skip_head(fp->head, hp, s));
+    WN_DEBUG_SYNC("skip_head", s);
+  } else {
+    WN_PROPAGATE(head_forward_generic(m, fp->bwd, fp->head, hp, B, L, s));
+  }
   return WN_OK;
 }
 

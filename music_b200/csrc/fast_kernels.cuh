@@ -28,6 +28,8 @@ struct BlockFwdParams {
   int has_dense;            // 0 for the last layer (its dense output is discarded, model.py:121-124)
   const float* bias_fg;     // [128] or null
   const float* bias_d;      // [64] or null
+  const float* cond;        // per-frame conditioning of [f|g] (see BlockBwdParams::cond) or null
+  int cond_frames, cond_layers, cond_layer;
   unsigned long long pol_first, pol_last;   // L2 eviction hints for tiles read for the last time / read by the next kernel (0: none)
   long long* ts;            // optional timestamp buffer (timing experiments): CTA 0 writes 8 clock64 values per tile
   int dbg;                  // WN_DBG bit mask (timing experiments only): 1 no Zcat store, 2 no x stores, 4 no lo load, 8 no MUFU

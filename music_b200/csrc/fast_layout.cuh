@@ -59,6 +59,9 @@ struct BwdMaps {
 };
 int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int B, int L, const uint8_t* P, uint8_t* Wp,
                    const std::vector<CUtensorMap>& xm, BwdMaps* out);
+struct SkipHeadMaps;
+struct SkipHeadParams;
+int head_forward_generic(const Model& m, const BwdMaps& M, const SkipHeadMaps& H, const SkipHeadParams& hp, int B, int L, cudaStream_t s);
 int fast_backward_impl(Model& m, const BwdMaps& maps, int B, int L, const float* d_x, const int64_t* d_idx, const void* d_packed,
                        void* d_ws, float* d_dlogits, float* d_grads, cudaStream_t s);
 

@@ -220,6 +220,10 @@ __device__ __forceinline__ uint32_t sw128_chunk(int row, int chunk) {
   return (uint32_t)row * 128u + ((((uint32_t)chunk) ^ ((uint32_t)row & 7u)) << 4);
 }
 
+// frame of the encoding that conditions local time step tl of a tensor of `len` steps (wavenet_autoencoder/model1.py:233-246):
+// every frame is held for len / frames steps when that divides, otherwise the encoding is tiled along time
+__device__ __forceinline__ int cond_frame(int tl, int len, int frames) { return (len % frames == 0) ? tl / (len / frames) : tl % frames; }
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -214,3 +214,41 @@ def test_padded_channels_forward_backward_vs_oracle(R, D, bias, dense):
     worst = max(errs, key=errs.get)
     print(f"padded R={R} D={D} bias={bias}: worst grad rel-l2", worst, errs[worst])
     assert errs[worst] < (4e-2 if bias else 0.12), (worst, errs[worst])
+
+
+@pytest.mark.parametrize("R,D,bias", [(32, 32, False), (64, 64, True)])
+def test_skip_512_forward_backward_vs_oracle(R, D, bias):
+    """512 skip channels - the reference's shipped wavenet/params/wavenet_params.json (32 residual / 32 dilation / 512 skip) -
+    run the head as three streaming tcgen05 GEMMs with fused bias / ReLU / logits epilogues instead of the fused S = 256
+    kernel: logits 1e-2, gradients as in test_backward_gradients_vs_oracle."""
+    from music_b200.wavenet.train import Trainer
+    dil = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1, 2, 4]
+    st = O.init_wavenet_state(dil, D, R, 512, 256, bias, seed=21, scale=1.0)
+    if bias:
+        for i in range(len(dil)):
+            st[f"dilation_layer_stack.{4 * i + 3}.bias"] = torch.full((512,), 0.3)
+        st["post_process_1.bias"] = torch.full((512,), 2.0)
+        st["post_process_1.weight"] = st["post_process_1.weight"] * 0.1
+    rf = O.receptive_field(2, dil)
+    B, W = 2, 333
+    L = rf + W - 1
+    g = torch.Generator().manual_seed(21)
+    idx = torch.randint(0, 256, (B, L + 1), generator=g)
+    tgt = idx[:, rf:rf + W].contiguous()
+    x = O.one_hot(idx[:, :L], 256)
+    ref = O.forward_logits(st, dil, x).numpy()
+    loss_ref, g_ref = O.grads(st, dil, x, tgt)
+    net = build_net(dil, R, D, 512, 256, bias, st, mode="auto")
+    assert net.mode == "bf16"
+    with torch.no_grad():
+        lg = net.forward_logits(indices=idx[:, :L].cuda()).cpu().numpy()
+    e = max_rel(lg, ref)
+    print(f"S=512 R={R}: logits max-rel", e)
+    assert e < TOL
+    tr = Trainer(net, "adam", distributed=False)
+    loss = float(tr.forward_backward(idx[:, :L].cuda(), tgt.cuda()))
+    assert abs(loss - loss_ref) < 1e-4
+    errs = _grad_errors(net, g_ref)
+    worst = max(errs, key=errs.get)
+    print(f"S=512 R={R} bias={bias}: worst grad rel-l2", worst, errs[worst])
+    assert errs[worst] < (4e-2 if bias else 0.12), (worst, errs[worst])
