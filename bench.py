@@ -63,7 +63,7 @@ def kernel_flops(B):
     f["gemm_tn_dWd"] = f["block_bwd"]
     f["block_bwd2"] = f["block_bwd"] + f["gemm_tn_dWfg"] + f["gemm_tn_dWd"]      # dz dgrad + fused weight gradients
     f["block_bwd3"] = f["block_bwd2"]
-    f["block_bwd5"] = f["block_bwd2"] + f["gemm_nt_dx"]                          # + the fused data-gradient GEMM of the dilated conv
+    f["block_bwd6"] = f["block_bwd2"] + f["gemm_nt_dx"]                          # + the fused data-gradient GEMM of the dilated conv
     f["gemm_nt_dZcat"] = 2.0 * B * W * N * D * S
     f["gemm_tn_dWs"] = f["gemm_nt_dZcat"]
     f["gemm_nt_dH1"] = 2.0 * B * W * S * Q

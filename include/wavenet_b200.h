@@ -225,6 +225,9 @@ uint64_t wn_launch_count(void);                 /* kernels launched by this libr
 int wn_profile_enable(int32_t on);              /* bracket every launch with CUDA events on its stream */
 int wn_profile_report(char* buf, size_t cap);   /* sync; "name count total_ms" lines, longest first; clears */
 
+/* timing experiments (WN_TS=1 in the environment): 16 clock64 stamps per tile of CTA 0 of the fused block backward */
+int wn_debug_ts(long long* h_buf, int32_t n);
+
 /* L2 -> SM read-bandwidth probe (bench.py): n_ctas CTAs each stream the L2-resident buffer `iters` times with 128-bit loads,
  * like the generation kernel's CTAs stream the shared weight image.  bytes * n_ctas * iters / time = achieved L2 read rate. */
 int wn_bench_l2_read(const void* d_buf, int64_t bytes, int32_t n_ctas, int32_t iters, void* d_sink, void* stream);

@@ -93,6 +93,7 @@ SIGNATURES = {
     "wn_profile_enable": (C.c_int, [_i32]),
     "wn_profile_report": (C.c_int, [C.c_char_p, _sz]),
     "wn_bench_l2_read": (C.c_int, [_p, _i64, _i32, _i32, _p, _p]),
+    "wn_debug_ts": (C.c_int, [_p, _i32]),
 }
 
 _lib = None

@@ -83,6 +83,13 @@ struct Model {
   int rf = 0;
   bool fast_ok = false;   // shapes supported by the tcgen05 kernels
   void* tmaps = nullptr;  // FastPlan cache (fast_plan.cu)
+  // optional additive per-frame conditioning in the bf16 path (the decoder of wavenet_autoencoder, model1.py:158-247); the tables
+  // are in the kernels' padded layout and must outlive the calls.  Conv biases of the conditioned layers are folded into them.
+  const float* cond_fg = nullptr;     // (B, frames, n_layers, 128) fp32, [filter 64 | gate 64]: added to the [f|g] pre-activations
+  const float* cond_head = nullptr;   // (B, frames, S) fp32: added to post_process_1's output before its ReLU
+  float* cond_fg_grad = nullptr;      // backward: sums of d[f|g] / d(head pre-activation) over the rows of each frame, same shapes
+  float* cond_head_grad = nullptr;    //           (must be zero-filled by the caller)
+  int cond_frames = 0;
 };
 
 // fp32 packed image: per conv Wt[k][in][out], Wtt[k][out][in], bias copy (offsets in floats)

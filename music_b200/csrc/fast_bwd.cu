@@ -217,6 +217,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tmem_ld_wait();
           uint32_t packed[16];
           uint32_t ax[16];
+          const float* condp = nullptr;
+          if (EPI == EPI_RELU_COND) {
+            const int tw = min(max(row - p.lg_pad, 0), p.lg_W - 1);      // pad rows: any frame (their gradients are zero)
+            condp = p.cond + ((int64_t)b * p.cond_frames + cond_frame(tw, p.lg_W, p.cond_frames)) * p.n_total + nt * NT + c * 32;
+          }
           if ((EPI == EPI_MASK || EPI == EPI_ADD) && valid) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -237,10 +242,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             } else if (EPI == EPI_ADD) {
               a0 += __low2float(x2);
               a1 += __high2float(x2);
-            } else if (EPI == EPI_RELU || EPI == EPI_RELU_BIAS) {
+            } else if (EPI == EPI_RELU || EPI == EPI_RELU_BIAS || EPI == EPI_RELU_COND) {
               if (EPI == EPI_RELU_BIAS) {
                 a0 += p.bias[nt * NT + c * 32 + 2 * j];
                 a1 += p.bias[nt * NT + c * 32 + 2 * j + 1];
+              }
+              if (EPI == EPI_RELU_COND) {
+                a0 += __ldg(condp + 2 * j);
+                a1 += __ldg(condp + 2 * j + 1);
               }
               a0 = fmaxf(a0, 0.f);
               a1 = fmaxf(a1, 0.f);
@@ -986,7 +995,7 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// ========================================================================================= block_bwd5
+// ========================================================================================= block_bwd6 (1/2: the idea)
 // block_bwd3 + the data-gradient GEMM of the dilated conv fused in, so that dF | dG (256 B per row and layer, written once and
 // read twice by gemm_nt_kernel<64>) never reach HBM.  The obstacle to that fusion is the dilation: row tau of dx_i needs
 // W1^T dFG[tau] AND W0^T dFG[tau + d], i.e. rows of another tile.  Here the two products are kept apart until they are consumed:
@@ -996,31 +1005,54 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 // pass-through A_{i-1} = (A + Q) + ... (summed once per tile in fp32 in the epilogue).  No atomics, no zero-filled buffers.
 // Per tile:  TMA {x[tau-d], x[tau]} (2 stages), {A', Q'} (2 stages)
 //            UMMA  f|g (recompute)  ->  TMEM fg[n & 1];   dz = A' Wd + Q' Wd  ->  TMEM dz
-//            epilogue 1 (16 warps): gate backward -> z, dF, dG tiles; S = A' + Q' (fp32 in registers, bf16 over the A' tile)
-//            UMMA  dW_dense += S^T z;   P = [dF|dG] [W0|W1] -> TMEM fg[n & 1] (the drained f|g buffer);   dW_fg += dFG^T [x taps]
-//            epilogue 2: A_i = S + P[:, 64:128) over the A' tile, Q_i = P[:, 0:64) over the Q' tile -> TMA stores (store warp)
+//            epilogue 1: gate backward -> z, dF, dG tiles
+//            UMMA  P = [dF|dG] [W0|W1] -> TMEM fg[n & 1] (the drained f|g buffer);  dW_dense += (A' + Q')^T z;  dW_fg += dFG^T [x taps]
+//            epilogue 2: A_i = (A' + Q') + P[:, 64:128) over the A' tile, Q_i = P[:, 0:64) over the Q' tile -> TMA stores (store warp)
 // The resident forward weights W0 / W1 ([128 o][64 r], K-major B operands of the recompute) are also the MN-major B operand of
 // the P product (K = o): no transposed weight copies in shared memory.  Tiles start at the previous layer's first tile so that
 // everything layer i - 1 reads has been written in this step (rows below s_out are written as zeros).
+// timing experiments (WN_TS=1): clock64 stamps of CTA 0, 16 per tile (tools/ts_bwd.py reads them through wn_debug_ts)
+__device__ long long g_ts[16 * 64];
+#define WN_TS_MARK(it, k)                                                        \
+  do {                                                                           \
+    if (p.trace && blockIdx.x == 0 && (it) < 64) g_ts[(it) * 16 + (k)] = clock64(); \
+  } while (0)
+
 struct Bwd5Smem {
   static constexpr uint32_t W0 = 0, W1 = TILE, WDT = 2 * TILE;                 // resident weights (40 KB)
   static constexpr uint32_t XR = 2 * TILE + 8192, X_STAGE = 2 * TILE;          // 2 x {x tap0, x tap1}
-  static constexpr uint32_t DXR = XR + 2 * X_STAGE, DX_STAGE = 2 * TILE;       // 2 x {A' (-> S -> A_i), Q' (-> Q_i)}
+  static constexpr uint32_t DXR = XR + 2 * X_STAGE, DX_STAGE = 2 * TILE;       // 2 x {A' (-> A_i), Q' (-> Q_i)}
   static constexpr uint32_t DF = DXR + 2 * DX_STAGE, DG = DF + TILE, Z = DG + TILE;
   static constexpr uint32_t TOTAL = Z + TILE;                                  // 216 KB
 };
 
+// ========================================================================================= block_bwd6 (2/2: the kernel)
+// 19 warps: 0-15 epilogue in TWO GROUPS of 8 that take alternate tiles, 16 TMA producer, 17 MMA issuer, 18 store thread.
+// The per-tile resources belong to the tile's parity = its group (TMEM f|g / P buffer, x stage, {A', Q'} stage), so group 1
+// runs the gate math of tile n + 1 while group 0 waits for the MMAs of tile n and writes its outputs.  What stays shared is
+// sequenced by barriers that complete once per tile, in tile order: the dz accumulator (dz_full / dz_empty) and the
+// dF | dG | z staging tiles (out_full / out_empty).  A barrier whose completions are consumed ALTERNATELY by the two groups
+// (dz_full, out_empty) is split per tile parity: an mbarrier wait only names the phase parity, and a group that arrives
+// early at "completion #1" of a barrier still in phase 0 would pass immediately (the first version of this kernel hung on
+// exactly that as soon as a CTA had more than two tiles).  Every thread owns 32 rows x 32 columns as two passes of 16
+// (packed results of the first pass are held in registers); dW_dense is accumulated from A' and Q' separately (two MMA
+// groups) so that epilogue 2 re-reads both in bf16 and sums them in fp32, exactly as the unfused path adds its bf16 dx.
+// Measured (cfg 2, profiles/r2_summary.md): 2.41 ms per step for the 30 launches, against 1.57 (block_bwd3) + 1.06 (dx GEMM)
+// of the unfused pair, and 3.3 GB less HBM traffic.  The clock64 timeline (tools/ts_bwd.py) shows what bounds it: with the
+// 216 KB of shared memory two {x, A'/Q'} stages are all that fits, each {A', Q'} stage doubles as the output staging area and
+// is refilled only after its TMA store has been read, so per parity the loop  load (2-4 k cycles) -> dz -> epilogue 1 (3.2 k)
+// -> P (1.5 k) -> epilogue 2 (2.1 k) -> store (1.4 k)  is serial: ~12 k cycles per two tiles.
 template <bool DENSE>
 __global__ void __launch_bounds__(608, 1)
-block_bwd5_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
+block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
                   const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_a_in,
                   const __grid_constant__ CUtensorMap tm_q_in, const __grid_constant__ CUtensorMap tm_wdT,
                   const __grid_constant__ CUtensorMap tm_a_out, const __grid_constant__ CUtensorMap tm_q_out, BlockBwd2Params pp) {
   const BlockBwdParams& p = pp.b;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t w_full, x_full[2], x_empty[2], dxi_full[2], dxi_empty[2], fg_full[2], fg_empty[2], p_full[2];
-  __shared__ __align__(8) uint64_t dz_full, dz_empty, out_full, out_empty, st_req, wg_done;
+  __shared__ __align__(8) uint64_t w_full, x_full[2], x_empty[2], dxi_full[2], dxi_empty[2], fg_full[2], fg_empty[2], p_full[2], st_req[2], wd_done[2];
+  __shared__ __align__(8) uint64_t dz_full[2], dz_empty, out_full, out_empty[2], wg_done;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -1033,12 +1065,13 @@ block_bwd5_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_init(&fg_full[i], 1);
       mbar_init(&fg_empty[i], 1);
       mbar_init(&p_full[i], 1);
+      mbar_init(&st_req[i], 1);
+      mbar_init(&wd_done[i], 1);
+      mbar_init(&dz_full[i], 1);
+      mbar_init(&out_empty[i], 1);
     }
-    mbar_init(&dz_full, 1);
     mbar_init(&dz_empty, 1);
     mbar_init(&out_full, 1);
-    mbar_init(&out_empty, 1);
-    mbar_init(&st_req, 1);
     mbar_init(&wg_done, 1);
     fence_barrier_init();
   }
@@ -1066,329 +1099,22 @@ block_bwd5_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
         const int st = it & 1;
         const uint32_t eph = ((it >> 1) & 1) ^ 1;
-        mbar_wait(&x_empty[st], eph);
-        uint8_t* sxp = sm + Bwd5Smem::XR + st * Bwd5Smem::X_STAGE;
-        mbar_expect_tx(&x_full[st], 2 * TILE);
-        tma_load_3d(sxp, &tm_x, &x_full[st], 0, tau0 - p.d, b, p.pol_first);     // the last read of these rows of x_i
-        tma_load_3d(sxp + TILE, &tm_x, &x_full[st], 0, tau0, b);
-        if (tau0 >= p.tw_al) {      // skip-path gradient tile: read by the epilogue straight from global memory, staged in L2 here
-          const int rb0 = (tau0 - p.tw_al) >> 5, nb = min(4, p.dzs_nblk - rb0);
-          if (nb > 0) bulk_prefetch_l2(p.dzs + (((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + rb0) << 11), (uint32_t)nb << 12);
-        }
-        if (DENSE) {
-          // tiles below this layer's own first tile exist only to write zeros for the next kernel: their A' / Q' are not read
-          // from memory (rows there were not written in this step) but from a fully out-of-range box, which reads as zeros
-          const int row_a = tau0 >= p.own_row0 ? tau0 : p.L, row_q = tau0 >= p.own_row0 ? tau0 + p.d_next : p.L;
-          mbar_wait(&dxi_empty[st], eph);
-          uint8_t* sd = sm + Bwd5Smem::DXR + st * Bwd5Smem::DX_STAGE;
-          mbar_expect_tx(&dxi_full[st], 2 * TILE);
-          tma_load_3d(sd, &tm_a_in, &dxi_full[st], 0, row_a, b, p.pol_first);
-          tma_load_3d(sd + TILE, &tm_q_in, &dxi_full[st], 0, row_q, b, p.pol_first);
-        }
-      }
-    }
-  } else if (warp == 17) {
-    // ------------------------------------------------------------ MMA issuer (polling)
-    if (lane == 0 && n_mine > 0) {
-      constexpr uint32_t id_fg = idesc_bf16(128, 128, 0, 0), id_dz = idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t id_wfg = idesc_bf16(128, 128, 1, 1), id_wd = idesc_bf16(128, 64, 1, 1);
-      constexpr uint32_t id_p = idesc_bf16(128, 128, 0, 1);      // A = [dF|dG] K-major, B = [W0|W1] MN-major (K = f|g output channel)
-      mbar_wait(&w_full, 0);
-      int jf = 0, jd = 0, jw = 0;       // next tile for: f|g recompute, dz, {dW_dense, P, dW_fg}
-      while (jw < n_mine) {
-        // (1) dz of tile jd (on the epilogue's critical path)
-        if (DENSE && jd < n_mine && mbar_test_wait(&dz_empty, (jd & 1) ^ 1) && mbar_test_wait(&dxi_full[jd & 1], (jd >> 1) & 1)) {
-          tc_fence_after();
-          const uint32_t sd = sbase + Bwd5Smem::DXR + (jd & 1) * Bwd5Smem::DX_STAGE;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd, k), desc_kmajor(sbase + Bwd5Smem::WDT, k), id_dz, k > 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd + TILE, k), desc_kmajor(sbase + Bwd5Smem::WDT, k), id_dz, true);
-          umma_commit(&dz_full);
-          ++jd;
-          continue;
-        }
-        // (2) tile jw after its epilogue 1: dW_dense (frees the S and z tiles), P (needed by epilogue 2), dW_fg
-        if (jw < jf && mbar_test_wait(&out_full, jw & 1)) {
-          tc_fence_after();
-          const uint32_t sxa = sbase + Bwd5Smem::XR + (jw & 1) * Bwd5Smem::X_STAGE;
-          if (DENSE) {
-            const uint32_t ss = sbase + Bwd5Smem::DXR + (jw & 1) * Bwd5Smem::DX_STAGE;      // S = A' + Q' (bf16), written by epilogue 1
-#pragma unroll
-            for (int k = 0; k < 8; ++k)   // dW_dense[r, d] += sum_t S[t, r] * z[t, d]   (rows 64..127 unused)
-              umma_bf16(tmem + C_WD, desc_mnmajor(ss, k, 0), desc_mnmajor(sbase + Bwd5Smem::Z, k, TILE), id_wd, (jw | k) != 0);
+        if (it + 2 < n_mine) {      // the tile that will use these stages next: pull its boxes into L2 now (a whole stage period ahead),
+          const int item2 = item + 2 * (int)gridDim.x;      // so that the loads issued when the stages free up do not pay DRAM latency
+          const int b2 = item2 / p.tiles_per_batch, tau2 = (p.tile0 + item2 % p.tiles_per_batch) * 128;
+          tma_prefetch_3d(&tm_x, 0, tau2 - p.d, b2);
+          tma_prefetch_3d(&tm_x, 0, tau2, b2);
+          if (DENSE && tau2 >= p.own_row0) {
+            tma_prefetch_3d(&tm_a_in, 0, tau2, b2);
+            tma_prefetch_3d(&tm_q_in, 0, tau2 + p.d_next, b2);
           }
-#pragma unroll
-          for (int k = 0; k < 8; ++k)     // P[t, (tap, r)] = sum_o dFG[t, o] * W_tap[o, r]
-            umma_bf16(tmem + (jw & 1) * 128, desc_kmajor(sbase + (k < 4 ? Bwd5Smem::DF : Bwd5Smem::DG), k & 3),
-                      desc_mnmajor(sbase + Bwd5Smem::W0, k, TILE), id_p, k > 0);
-          umma_commit(&p_full[jw & 1]);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
-            umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd5Smem::DF, k, TILE), desc_mnmajor(sxa, k, TILE), id_wfg, (jw | k) != 0);
-          umma_commit(&x_empty[jw & 1]);
-          umma_commit(&out_empty);
-          ++jw;
-          continue;
         }
-        // (3) f|g recompute of tile jf into buffer jf & 1 (free once epilogue 2 of tile jf - 2 has drained P from it)
-        if (jf < n_mine && mbar_test_wait(&x_full[jf & 1], (jf >> 1) & 1) && mbar_test_wait(&fg_empty[jf & 1], ((jf >> 1) & 1) ^ 1)) {
-          tc_fence_after();
-          const uint32_t sxa = sbase + Bwd5Smem::XR + (jf & 1) * Bwd5Smem::X_STAGE, acc = tmem + (jf & 1) * 128;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa, k), desc_kmajor(sbase + Bwd5Smem::W0, k), id_fg, k > 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa + TILE, k), desc_kmajor(sbase + Bwd5Smem::W1, k), id_fg, true);
-          umma_commit(&fg_full[jf & 1]);
-          ++jf;
-          continue;
-        }
-      }
-      umma_commit(&wg_done);
-    }
-  } else if (warp == 18) {
-    // ------------------------------------------------------------ store thread: A_i / Q_i tiles -> global, then frees their stage
-    if (lane == 0 && n_mine > 0) {
-      int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
-      for (int it = 0; it < n_mine; ++it) {
-        const int tau0 = (p.tile0 + tl) * 128;
-        uint8_t* sd = sm + Bwd5Smem::DXR + (it & 1) * Bwd5Smem::DX_STAGE;
-        mbar_wait(&st_req, it & 1);
-        tma_store_3d(&tm_a_out, sd, 0, tau0, b, p.pol_last);               // both read by the next launch
-        tma_store_3d(&tm_q_out, sd + TILE, 0, tau0, b, p.pol_last);
-        tma_store_commit();
-        tma_store_wait_read();
-        mbar_arrive(&dxi_empty[it & 1]);
-        tl += (int)gridDim.x;
-        while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue warps 0-15
-    const int q4 = warp & 3, cg = warp >> 2;          // TMEM lane quarter, 16-column group
-    const int row = q4 * 32 + lane;
-    const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, 0);
-    int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
-    for (int it = 0; it < n_mine; ++it) {
-      const uint32_t ph = it & 1, ph2 = (it >> 1) & 1;
-      const int tau0 = (p.tile0 + tl) * 128;
-      const int tau = tau0 + row;
-      const bool valid = tau >= p.s_out && tau < p.L;
-      uint8_t* sa = sm + Bwd5Smem::DXR + ph * Bwd5Smem::DX_STAGE;      // A' -> S -> A_i ; + TILE: Q' -> Q_i
-      const uint32_t o0 = sw128_chunk(row, cg * 2), o1 = sw128_chunk(row, cg * 2 + 1);
-      // ---------------- epilogue 1: gate backward
-      uint32_t zs[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-      if (tau0 >= p.tw_al && tau < p.L)      // tiled layout (GemmNtParams::out_tiled): this warp's 32 rows x 16 channels are 1 KB contiguous
-        ldg_stream32(p.dzs + (((((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + ((tau0 - p.tw_al) >> 5) + q4) * 4 + cg) * 32 + lane) << 4), p.pol_first, zs);
-      mbar_wait(&fg_full[ph], ph2);
-      tc_fence_after();
-      uint32_t f[16], g[16];
-      tmem_ld16(lane_addr + ph * 128 + cg * 16, f);
-      tmem_ld16(lane_addr + ph * 128 + 64 + cg * 16, g);
-      tmem_ld_wait();
-      float ca[16], cb[16];
-      uint32_t pz[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float zo[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float fv = __uint_as_float(f[2 * j + e]), gv = __uint_as_float(g[2 * j + e]);
-          const float t = tanh_fast(fv), sg = sigmoid_fast(gv);
-          zo[e] = t * sg;
-          ca[2 * j + e] = sg * (1.f - t * t);
-          cb[2 * j + e] = zo[e] * (1.f - sg);
-        }
-        pz[j] = valid ? pack_bf16(zo[0], zo[1]) : 0u;
-      }
-      float sum[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) sum[j] = 0.f;
-      uint32_t dzv[16];
-      if (DENSE) {
-        mbar_wait(&dz_full, ph);             // dz complete: the MMAs have read A' and Q', and (TMA barrier observed by the issuer
-        mbar_wait(&dxi_full[ph], ph2);       //  and here) both tiles are visible to this thread
-        tc_fence_after();
-        tmem_ld16(lane_addr + C_DZ + cg * 16, dzv);
-        const uint4 a0 = *reinterpret_cast<const uint4*>(sa + o0), a1 = *reinterpret_cast<const uint4*>(sa + o1);
-        const uint4 q0 = *reinterpret_cast<const uint4*>(sa + TILE + o0), q1 = *reinterpret_cast<const uint4*>(sa + TILE + o1);
-        const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
-          const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&qw[j]);
-          sum[2 * j] = __low2float(a2) + __low2float(q2);
-          sum[2 * j + 1] = __high2float(a2) + __high2float(q2);
-        }
-        tmem_ld_wait();
-      }
-      asm volatile("" : "+r"(zs[0]), "+r"(zs[1]), "+r"(zs[2]), "+r"(zs[3]), "+r"(zs[4]), "+r"(zs[5]), "+r"(zs[6]), "+r"(zs[7]));
-      uint32_t pf[8], pg[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
-        float dz0 = __low2float(s2), dz1 = __high2float(s2);
-        if (DENSE) {
-          dz0 += __uint_as_float(dzv[2 * j]);
-          dz1 += __uint_as_float(dzv[2 * j + 1]);
-        }
-        pf[j] = valid ? pack_bf16(dz0 * ca[2 * j], dz1 * ca[2 * j + 1]) : 0u;
-        pg[j] = valid ? pack_bf16(dz0 * cb[2 * j], dz1 * cb[2 * j + 1]) : 0u;
-      }
-      // dF | dG | z may be rewritten once the previous tile's MMAs have read them (out_empty: committed after its dW_fg)
-      if (it > 0) mbar_wait(&out_empty, ph ^ 1);
-      if (!DENSE) mbar_wait(&dxi_empty[ph], ph2 ^ 1);      // no producer waits for the staging slots of this stage: do it here
-      tc_fence_before();
-      epi8_bar_sync();                     // every thread has drained dz (and read A' / Q')
-      if (tid == 0) mbar_arrive(&dz_empty);
-      *reinterpret_cast<uint4*>(sm + Bwd5Smem::Z + o0) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
-      *reinterpret_cast<uint4*>(sm + Bwd5Smem::Z + o1) = make_uint4(pz[4], pz[5], pz[6], pz[7]);
-      *reinterpret_cast<uint4*>(sm + Bwd5Smem::DF + o0) = make_uint4(pf[0], pf[1], pf[2], pf[3]);
-      *reinterpret_cast<uint4*>(sm + Bwd5Smem::DF + o1) = make_uint4(pf[4], pf[5], pf[6], pf[7]);
-      *reinterpret_cast<uint4*>(sm + Bwd5Smem::DG + o0) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
-      *reinterpret_cast<uint4*>(sm + Bwd5Smem::DG + o1) = make_uint4(pg[4], pg[5], pg[6], pg[7]);
-      if (DENSE) {                         // S = A' + Q' over the A' tile: the A operand of dW_dense
-        uint32_t ps[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ps[j] = pack_bf16(sum[2 * j], sum[2 * j + 1]);
-        *reinterpret_cast<uint4*>(sa + o0) = make_uint4(ps[0], ps[1], ps[2], ps[3]);
-        *reinterpret_cast<uint4*>(sa + o1) = make_uint4(ps[4], ps[5], ps[6], ps[7]);
-      }
-      fence_proxy_async_smem();
-      epi8_bar_sync();
-      if (tid == 0) mbar_arrive(&out_full);
-      // ---------------- epilogue 2: A_i = S + P1, Q_i = P0 (P = [dF|dG][W0|W1] sits in this tile's drained f|g buffer)
-      mbar_wait(&p_full[ph], ph2);         // also: dW_dense has read the S and z tiles
-      tc_fence_after();
-      uint32_t p0[16], p1[16];
-      tmem_ld16(lane_addr + ph * 128 + cg * 16, p0);
-      tmem_ld16(lane_addr + ph * 128 + 64 + cg * 16, p1);
-      tmem_ld_wait();
-      uint32_t pa[8], pq[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        pa[j] = valid ? pack_bf16(sum[2 * j] + __uint_as_float(p1[2 * j]), sum[2 * j + 1] + __uint_as_float(p1[2 * j + 1])) : 0u;
-        pq[j] = valid ? pack_bf16(__uint_as_float(p0[2 * j]), __uint_as_float(p0[2 * j + 1])) : 0u;
-      }
-      *reinterpret_cast<uint4*>(sa + o0) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
-      *reinterpret_cast<uint4*>(sa + o1) = make_uint4(pa[4], pa[5], pa[6], pa[7]);
-      *reinterpret_cast<uint4*>(sa + TILE + o0) = make_uint4(pq[0], pq[1], pq[2], pq[3]);
-      *reinterpret_cast<uint4*>(sa + TILE + o1) = make_uint4(pq[4], pq[5], pq[6], pq[7]);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      epi8_bar_sync();                     // every thread has drained P and written its part of both output tiles
-      if (tid == 0) {
-        mbar_arrive(&fg_empty[ph]);
-        mbar_arrive(&st_req);
-      }
-      tl += (int)gridDim.x;
-      while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
-    }
-    // ---- flush the weight-gradient accumulators as a per-CTA partial tile [128][192] (summed by wgrad_reduce_kernel)
-    {
-      float* prow = pp.partial + ((int64_t)blockIdx.x * 128 + row) * 192;
-      if (n_mine > 0) {
-        mbar_wait(&wg_done, 0);
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(lane_addr + C_WFG + cg * 32, v);         // dW_fg columns [32 cg, 32 cg + 32)
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(prow + cg * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        uint32_t u[16];
-        if (DENSE) {
-          tmem_ld16(lane_addr + C_WD + cg * 16, u);        // dW_dense columns [16 cg, 16 cg + 16)
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) u[j] = 0u;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(prow + 128 + cg * 16 + q * 4) = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem);
-}
-
-// ========================================================================================= block_bwd6
-// block_bwd5 with the 16 epilogue warps split into TWO GROUPS of 8 that take alternate tiles.  In block_bwd5 every tile is a
-// serial chain - gate backward (epilogue 1) -> wait for dW_dense + P on the tensor pipe -> epilogue 2 - that all 16 warps walk
-// through in lock step: 9800 cycles per tile against a tensor-pipe need of 2700 and an issue-slot need of ~2400.  Here the
-// per-tile resources belong to the tile's parity = its group (TMEM f|g / P buffer, x stage, {A', Q'} stage), so group 1 runs
-// the gate math of tile n + 1 while group 0 waits for the MMAs of tile n and writes its outputs.  What stays shared is
-// sequenced by barriers that complete once per tile, in tile order: the dz accumulator (dz_full / dz_empty) and the
-// dF | dG | z staging tiles (out_full / out_empty).  A barrier whose completions are consumed ALTERNATELY by the two groups
-// (dz_full, out_empty) is split per tile parity: an mbarrier wait only names the phase parity, and a group that arrives
-// early at "completion #1" of a barrier still in phase 0 would pass immediately.  Differences to block_bwd5 inside a tile: every thread owns 32 rows x 32
-// columns as two passes of 16 (packed results of the first pass are held in registers), and dW_dense is accumulated from
-// A' and Q' separately (two MMA groups, no S tile), so that epilogue 2 re-reads both in bf16 and sums them in fp32.
-template <bool DENSE>
-__global__ void __launch_bounds__(608, 1)
-block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
-                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_a_in,
-                  const __grid_constant__ CUtensorMap tm_q_in, const __grid_constant__ CUtensorMap tm_wdT,
-                  const __grid_constant__ CUtensorMap tm_a_out, const __grid_constant__ CUtensorMap tm_q_out, BlockBwd2Params pp) {
-  const BlockBwdParams& p = pp.b;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t w_full, x_full[2], x_empty[2], dxi_full[2], dxi_empty[2], fg_full[2], fg_empty[2], p_full[2], st_req[2];
-  __shared__ __align__(8) uint64_t dz_full[2], dz_empty, out_full, out_empty[2], wg_done;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    mbar_init(&w_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&x_full[i], 1);
-      mbar_init(&x_empty[i], 1);
-      mbar_init(&dxi_full[i], 1);
-      mbar_init(&dxi_empty[i], 1);
-      mbar_init(&fg_full[i], 1);
-      mbar_init(&fg_empty[i], 1);
-      mbar_init(&p_full[i], 1);
-      mbar_init(&st_req[i], 1);
-      mbar_init(&dz_full[i], 1);
-      mbar_init(&out_empty[i], 1);
-    }
-    mbar_init(&dz_empty, 1);
-    mbar_init(&out_full, 1);
-    mbar_init(&wg_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-  pdl_launch_dependents();
-  pdl_wait();
-  const uint32_t sbase = smem_u32(sm);
-  const int n_items = pp.n_batches * p.tiles_per_batch;
-  const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  constexpr uint32_t C_DZ = 256, C_WFG = 320, C_WD = 448;      // TMEM columns; f|g / P buffers at 0 and 128
-
-  if (warp == 16) {
-    // ------------------------------------------------------------ TMA producer (as block_bwd5)
-    if (lane == 0 && n_mine > 0) {
-      mbar_expect_tx(&w_full, 2 * TILE + (DENSE ? 8192 : 0));
-      tma_load_2d(sm + Bwd5Smem::W0, &tm_w0, &w_full, 0, 0);
-      tma_load_2d(sm + Bwd5Smem::W1, &tm_w1, &w_full, 0, 0);
-      if (DENSE) tma_load_2d(sm + Bwd5Smem::WDT, &tm_wdT, &w_full, 0, 0);
-      for (int it = 0; it < n_mine; ++it) {
-        const int item = blockIdx.x + it * gridDim.x;
-        const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
-        const int st = it & 1;
-        const uint32_t eph = ((it >> 1) & 1) ^ 1;
         mbar_wait(&x_empty[st], eph);
         uint8_t* sxp = sm + Bwd5Smem::XR + st * Bwd5Smem::X_STAGE;
         mbar_expect_tx(&x_full[st], 2 * TILE);
         tma_load_3d(sxp, &tm_x, &x_full[st], 0, tau0 - p.d, b, p.pol_first);
         tma_load_3d(sxp + TILE, &tm_x, &x_full[st], 0, tau0, b);
+        WN_TS_MARK(it, 0);
         if (tau0 >= p.tw_al) {
           const int rb0 = (tau0 - p.tw_al) >> 5, nb = min(4, p.dzs_nblk - rb0);
           if (nb > 0) bulk_prefetch_l2(p.dzs + (((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + rb0) << 11), (uint32_t)nb << 12);
@@ -1400,6 +1126,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           mbar_expect_tx(&dxi_full[st], 2 * TILE);
           tma_load_3d(sd, &tm_a_in, &dxi_full[st], 0, row_a, b, p.pol_first);
           tma_load_3d(sd + TILE, &tm_q_in, &dxi_full[st], 0, row_q, b, p.pol_first);
+          WN_TS_MARK(it, 1);
         }
       }
     }
@@ -1420,12 +1147,18 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DZ, desc_kmajor(sd + TILE, k), desc_kmajor(sbase + Bwd5Smem::WDT, k), id_dz, true);
           umma_commit(&dz_full[jd & 1]);
+          WN_TS_MARK(jd, 2);
           ++jd;
           continue;
         }
         if (jw < jf && mbar_test_wait(&out_full, jw & 1)) {
           tc_fence_after();
           const uint32_t sxa = sbase + Bwd5Smem::XR + (jw & 1) * Bwd5Smem::X_STAGE;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)     // P[t, (tap, r)] = sum_o dFG[t, o] * W_tap[o, r]   (first: epilogue 2 waits for it)
+            umma_bf16(tmem + (jw & 1) * 128, desc_kmajor(sbase + (k < 4 ? Bwd5Smem::DF : Bwd5Smem::DG), k & 3),
+                      desc_mnmajor(sbase + Bwd5Smem::W0, k, TILE), id_p, k > 0);
+          umma_commit(&p_full[jw & 1]);
           if (DENSE) {      // dW_dense[r, d] += sum_t (A'[t, r] + Q'[t, r]) * z[t, d]   (rows 64..127 unused)
             const uint32_t sd = sbase + Bwd5Smem::DXR + (jw & 1) * Bwd5Smem::DX_STAGE;
 #pragma unroll
@@ -1435,16 +1168,13 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             for (int k = 0; k < 8; ++k)
               umma_bf16(tmem + C_WD, desc_mnmajor(sd + TILE, k, 0), desc_mnmajor(sbase + Bwd5Smem::Z, k, TILE), id_wd, true);
           }
-#pragma unroll
-          for (int k = 0; k < 8; ++k)     // P[t, (tap, r)] = sum_o dFG[t, o] * W_tap[o, r]
-            umma_bf16(tmem + (jw & 1) * 128, desc_kmajor(sbase + (k < 4 ? Bwd5Smem::DF : Bwd5Smem::DG), k & 3),
-                      desc_mnmajor(sbase + Bwd5Smem::W0, k, TILE), id_p, k > 0);
-          umma_commit(&p_full[jw & 1]);      // also: dW_dense has read A' and Q' (epilogue 2 overwrites them in place)
+          umma_commit(&wd_done[jw & 1]);     // dW_dense has read A' and Q': epilogue 2 may overwrite them in place
 #pragma unroll
           for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
             umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd5Smem::DF, k, TILE), desc_mnmajor(sxa, k, TILE), id_wfg, (jw | k) != 0);
           umma_commit(&x_empty[jw & 1]);
           umma_commit(&out_empty[jw & 1]);
+          WN_TS_MARK(jw, 3);
           ++jw;
           continue;
         }
@@ -1456,6 +1186,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(acc, desc_kmajor(sxa + TILE, k), desc_kmajor(sbase + Bwd5Smem::W1, k), id_fg, true);
           umma_commit(&fg_full[jf & 1]);
+          WN_TS_MARK(jf, 4);
           ++jf;
           continue;
         }
@@ -1469,11 +1200,12 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       for (int it = 0; it < n_mine; ++it) {
         const int tau0 = (p.tile0 + tl) * 128;
         uint8_t* sd = sm + Bwd5Smem::DXR + (it & 1) * Bwd5Smem::DX_STAGE;
-        mbar_wait(&st_req[it & 1], (it >> 1) & 1);
+        mbar_spin_wait(&st_req[it & 1], (it >> 1) & 1);
         tma_store_3d(&tm_a_out, sd, 0, tau0, b, p.pol_last);
         tma_store_3d(&tm_q_out, sd + TILE, 0, tau0, b, p.pol_last);
         tma_store_commit();
         tma_store_wait_read();
+        WN_TS_MARK(it, 5);
         mbar_arrive(&dxi_empty[it & 1]);
         tl += (int)gridDim.x;
         while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
@@ -1501,45 +1233,24 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const __nv_bfloat16* zsp =
           p.dzs + (((((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + ((tau0 - p.tw_al) >> 5) + q4) * 4 + h * 2) * 32 + lane) << 4);
       // ---------------- epilogue 1: gate backward, two passes of 16 columns
-      uint32_t keep[24];                       // packed z | dF | dG of the first pass
-      uint32_t pz[8], pf[8], pg[8];
+      // The single dz accumulator is what the two groups share inside a tile period: it is drained FIRST - dz + skip-path
+      // gradient of both passes, held as packed bf16 (16 registers) - and handed to the other group's tile before any of the
+      // gate math, so that dz(n + 1) is computed under the math of tile n.
+      uint32_t dzp[16];
+      if (leader) WN_TS_MARK(it, 6);
 #pragma unroll
       for (int ps = 0; ps < 2; ++ps) {
-        const int c0 = h * 32 + ps * 16;
         uint32_t zs[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        if (has_zs) ldg_stream32(zsp + ps * 512, p.pol_first, zs);
-        if (ps == 0) {
-          mbar_wait(&fg_full[g], ph2);
-          tc_fence_after();
-        }
-        uint32_t f[16], gq[16];
-        tmem_ld16(lane_addr + g * 128 + c0, f);
-        tmem_ld16(lane_addr + g * 128 + 64 + c0, gq);
-        tmem_ld_wait();
-        float ca[16], cb[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float zo[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float fv = __uint_as_float(f[2 * j + e]), gv = __uint_as_float(gq[2 * j + e]);
-            const float t = tanh_fast(fv), sg = sigmoid_fast(gv);
-            zo[e] = t * sg;
-            ca[2 * j + e] = sg * (1.f - t * t);
-            cb[2 * j + e] = zo[e] * (1.f - sg);
-          }
-          pz[j] = valid ? pack_bf16(zo[0], zo[1]) : 0u;
-        }
+        if (has_zs) ldg_stream32(zsp + ps * 512, p.pol_first, zs);      // next column group of 16: + 32 rows x 16 channels
         uint32_t dzv[16];
         if (DENSE) {
           if (ps == 0) {
             mbar_wait(&dz_full[g], ph2);
             tc_fence_after();
           }
-          tmem_ld16(lane_addr + C_DZ + c0, dzv);
+          tmem_ld16(lane_addr + C_DZ + h * 32 + ps * 16, dzv);
           tmem_ld_wait();
         }
-        asm volatile("" : "+r"(zs[0]), "+r"(zs[1]), "+r"(zs[2]), "+r"(zs[3]), "+r"(zs[4]), "+r"(zs[5]), "+r"(zs[6]), "+r"(zs[7]));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
@@ -1548,19 +1259,56 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             dz0 += __uint_as_float(dzv[2 * j]);
             dz1 += __uint_as_float(dzv[2 * j + 1]);
           }
-          pf[j] = valid ? pack_bf16(dz0 * ca[2 * j], dz1 * ca[2 * j + 1]) : 0u;
-          pg[j] = valid ? pack_bf16(dz0 * cb[2 * j], dz1 * cb[2 * j + 1]) : 0u;
+          dzp[ps * 8 + j] = pack_bf16(dz0, dz1);
+        }
+      }
+      if (DENSE) {
+        tc_fence_before();
+        group_bar();
+        if (leader) mbar_arrive(&dz_empty);
+      }
+      uint32_t keep[24];                       // packed z | dF | dG of the first pass
+      uint32_t pz[8], pf[8], pg[8];
+      if (leader) WN_TS_MARK(it, 7);
+      mbar_wait(&fg_full[g], ph2);
+      tc_fence_after();
+      if (leader) WN_TS_MARK(it, 8);
+#pragma unroll
+      for (int ps = 0; ps < 2; ++ps) {
+        const int c0 = h * 32 + ps * 16;
+        uint32_t f[16], gq[16];
+        tmem_ld16(lane_addr + g * 128 + c0, f);
+        tmem_ld16(lane_addr + g * 128 + 64 + c0, gq);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&dzp[ps * 8 + j]);
+          const float dz[2] = {__low2float(d2), __high2float(d2)};
+          float zo[2], df[2], dg[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float fv = __uint_as_float(f[2 * j + e]), gv = __uint_as_float(gq[2 * j + e]);
+            const float t = tanh_fast(fv), sg = sigmoid_fast(gv);
+            zo[e] = t * sg;
+            df[e] = dz[e] * (sg * (1.f - t * t));
+            dg[e] = dz[e] * (zo[e] * (1.f - sg));
+          }
+          pz[j] = valid ? pack_bf16(zo[0], zo[1]) : 0u;
+          pf[j] = valid ? pack_bf16(df[0], df[1]) : 0u;
+          pg[j] = valid ? pack_bf16(dg[0], dg[1]) : 0u;
         }
         if (ps == 0) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { keep[j] = pz[j]; keep[8 + j] = pf[j]; keep[16 + j] = pg[j]; }
         }
       }
-      // every thread of the group has drained dz: hand the accumulator to the next tile (the other group's)
-      tc_fence_before();
-      group_bar();
-      if (leader) mbar_arrive(&dz_empty);
+      if (!DENSE) {      // (dz_empty still completes once per tile: the issuer's job order does not depend on DENSE)
+        tc_fence_before();
+        group_bar();
+        if (leader) mbar_arrive(&dz_empty);
+      }
       // the dF | dG | z tiles are free once the MMAs of tile it - 1 (the other group's) have read them
+      if (leader) WN_TS_MARK(it, 9);
       if (it > 0) mbar_wait(&out_empty[g ^ 1], ((it - 1) >> 1) & 1);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -1574,12 +1322,17 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       fence_proxy_async_smem();
       group_bar();                           // the group's 8 warps together wrote the whole [128][64] tile of each of z, dF, dG
-      if (leader) mbar_arrive(&out_full);
+      if (leader) {
+        mbar_arrive(&out_full);
+        WN_TS_MARK(it, 10);
+      }
       // ---------------- epilogue 2: A_i = (A' + Q') + P1, Q_i = P0, in place over A' / Q'
       mbar_wait(&p_full[g], ph2);            // P complete; dW_dense has read A' and Q'
       if (DENSE) mbar_wait(&dxi_full[g], ph2);                  // (TMA data of this stage observed by this thread as well)
       else mbar_wait(&dxi_empty[g], ph2 ^ 1);                   // no producer waits for the staging slots: the store of tile it - 2
       tc_fence_after();
+      if (leader) WN_TS_MARK(it, 11);
+      uint32_t pa[16], pq[16];               // packed A_i / Q_i of both passes: written once dW_dense has read A' and Q'
 #pragma unroll
       for (int ps = 0; ps < 2; ++ps) {
         const int c0 = h * 32 + ps * 16;
@@ -1595,19 +1348,21 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           qw[0] = q0.x; qw[1] = q0.y; qw[2] = q0.z; qw[3] = q0.w; qw[4] = q1.x; qw[5] = q1.y; qw[6] = q1.z; qw[7] = q1.w;
         }
         tmem_ld_wait();
-        uint32_t pa[8], pq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
           const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&qw[j]);
           const float s0 = __low2float(a2) + __low2float(q2), s1 = __high2float(a2) + __high2float(q2);
-          pa[j] = valid ? pack_bf16(s0 + __uint_as_float(p1[2 * j]), s1 + __uint_as_float(p1[2 * j + 1])) : 0u;
-          pq[j] = valid ? pack_bf16(__uint_as_float(p0[2 * j]), __uint_as_float(p0[2 * j + 1])) : 0u;
+          pa[ps * 8 + j] = valid ? pack_bf16(s0 + __uint_as_float(p1[2 * j]), s1 + __uint_as_float(p1[2 * j + 1])) : 0u;
+          pq[ps * 8 + j] = valid ? pack_bf16(__uint_as_float(p0[2 * j]), __uint_as_float(p0[2 * j + 1])) : 0u;
         }
-        *reinterpret_cast<uint4*>(sa + o0) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
-        *reinterpret_cast<uint4*>(sa + o1) = make_uint4(pa[4], pa[5], pa[6], pa[7]);
-        *reinterpret_cast<uint4*>(sa + TILE + o0) = make_uint4(pq[0], pq[1], pq[2], pq[3]);
-        *reinterpret_cast<uint4*>(sa + TILE + o1) = make_uint4(pq[4], pq[5], pq[6], pq[7]);
+      }
+      if (DENSE) mbar_wait(&wd_done[g], ph2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t o = sw128_chunk(row, h * 4 + q);
+        *reinterpret_cast<uint4*>(sa + o) = make_uint4(pa[4 * q], pa[4 * q + 1], pa[4 * q + 2], pa[4 * q + 3]);
+        *reinterpret_cast<uint4*>(sa + TILE + o) = make_uint4(pq[4 * q], pq[4 * q + 1], pq[4 * q + 2], pq[4 * q + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -1615,6 +1370,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (leader) {
         mbar_arrive(&fg_empty[g]);
         mbar_arrive(&st_req[g]);
+        WN_TS_MARK(it, 12);
       }
       tl += 2 * (int)gridDim.x;
       while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
@@ -1652,7 +1408,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 }
 
 // dx_0[tau] = A_0[tau] + Q_0[tau + d_0]: the input gradient of the causal layer's weight-gradient kernel (the only consumer
-// of a data gradient that is not a block_bwd5 launch)
+// of a data gradient that is not a block_bwd6 launch)
 __global__ void __launch_bounds__(256) combine_dx0_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Qd,
                                                           __nv_bfloat16* __restrict__ out, int L, int d0) {
   const int b = blockIdx.y;
@@ -1780,6 +1536,60 @@ __global__ void replicate_kernel(float* __restrict__ G, const int64_t* __restric
   if (i < n && c < C) G[offs[i] + c] = G[offs[0] + c];
 }
 
+// out[b][frame][col_map(c)] += sum over the rows tl of a (B, rows, pitch) bf16 tensor that belong to `frame` (the transpose of the
+// conditioning broadcast, model1.py:227-247).  Rows t0 + tl, tl in [0, len); 128 columns starting at c0 per launch slab.  Each
+// CTA accumulates its chunk of rows in a shared [frames][128] tile (both frame rules: consecutive rows share a frame, or walk
+// through all frames) and flushes it with atomics.  dd > 0: columns are the kernels' padded [filter 64 | gate 64] order and go
+// to the autoencoder's raw (2 dd) order, gate first; dd == 0: identity.
+__global__ void __launch_bounds__(256) frame_sum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int64_t bstride, int pitch, int c0,
+                                                             int t0, int len, int frames, int rows_per_cta, float* __restrict__ out,
+                                                             int out_pitch, int dd) {
+  extern __shared__ float acc[];      // [frames][128]
+  const int b = blockIdx.y;
+  for (int e = threadIdx.x; e < frames * 128; e += 256) acc[e] = 0.f;
+  __syncthreads();
+  const int col = threadIdx.x & 127, rsub = threadIdx.x >> 7;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(len, r0 + rows_per_cta);
+  for (int tl = r0 + rsub; tl < r1; tl += 2) {
+    const float v = __bfloat162float(src[(int64_t)b * bstride + (int64_t)(t0 + tl) * pitch + c0 + col]);
+    atomicAdd(&acc[cond_frame(tl, len, frames) * 128 + col], v);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < frames * 128; e += 256) {
+    const float v = acc[e];
+    if (v == 0.f) continue;
+    const int f = e >> 7, c = e & 127;
+    int oc = c0 + c;
+    if (dd > 0) {
+      const int ch = c & 63;
+      if (ch >= dd) continue;
+      oc = c < 64 ? dd + ch : ch;      // filter -> second half, gate -> first half
+    }
+    atomicAdd(out + ((int64_t)b * frames + f) * out_pitch + oc, v);
+  }
+}
+
+// raw conditioning conv output (B * frames, 2 dd), gate first (model1.py:188-192) [+ the conv bias (2 dd) of the conditioned layer]
+// -> the kernels' table slot: out[row * out_stride + c], c < 64: filter channel c, c >= 64: gate channel c - 64, zero padded
+__global__ void cond_table_kernel(const float* __restrict__ raw, const float* __restrict__ bias, int64_t n_rows, int dd,
+                                  float* __restrict__ out, int64_t out_stride) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_rows * 128; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e >> 7;
+    const int c = (int)(e & 127), ch = c & 63;
+    float v = 0.f;
+    if (ch < dd) {
+      const int rc = c < 64 ? dd + ch : ch;
+      v = raw[row * 2 * dd + rc] + (bias ? bias[rc] : 0.f);
+    }
+    out[row * out_stride + c] = v;
+  }
+}
+// out[row][c] = raw[row][c] + bias[c]   (head conditioning + connection_1 bias)
+__global__ void add_bias_rows_kernel(const float* __restrict__ raw, const float* __restrict__ bias, int64_t n_rows, int C, float* __restrict__ out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_rows * C; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = raw[e] + (bias ? bias[e % C] : 0.f);
+}
+
 template <typename K>
 int set_smem(K kernel, int bytes) {
   WN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -1825,7 +1635,7 @@ int launch_colsum_bf16_split(const void* src, int B, int64_t rows_per_batch, int
 
 // environment switches of the backward (timing experiments; read once)
 struct BwdEnv {
-  bool nt_stream, bwd5, bwd6, wgrad_side, l2hint_dx, scatter_simt;
+  bool nt_stream, bwd6, wgrad_side, l2hint_dx, scatter_simt;
 };
 static const BwdEnv& bwd_env() {
   static const BwdEnv e = [] {
@@ -1833,8 +1643,7 @@ static const BwdEnv& bwd_env() {
     auto off = [](const char* name) { const char* v = getenv(name); return v && v[0] == '0'; };
     BwdEnv r{};
     r.nt_stream = on("WN_NT_STREAM");
-    r.bwd5 = on("WN_BWD5");               // block_bwd5: the dx GEMM fused into the block backward (models without bias)
-    r.bwd6 = on("WN_BWD6");               // block_bwd6: block_bwd5 with two epilogue groups on alternate tiles
+    r.bwd6 = !off("WN_BWD6");             // block_bwd6 (default): the dx GEMM fused into the block backward; WN_BWD6=0: block_bwd3 + dx GEMM
     r.wgrad_side = !off("WN_WGRAD_SIDE");
     r.l2hint_dx = on("WN_L2HINT_DX");
     r.scatter_simt = on("WN_SCATTER_SIMT");
@@ -1865,6 +1674,7 @@ int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStrea
     else if (p.epi == EPI_RELU_BIAS) k = gemm_nt_kernel<256, EPI_RELU_BIAS>;
     else if (p.epi == EPI_LOGITS) k = gemm_nt_kernel<256, EPI_LOGITS>;
     else if (p.epi == EPI_LOGITS_BIAS) k = gemm_nt_kernel<256, EPI_LOGITS_BIAS>;
+    else if (p.epi == EPI_RELU_COND) k = gemm_nt_kernel<256, EPI_RELU_COND>;
     WN_PROPAGATE(set_smem_once(k, smem));
     WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)grid), dim3(192), smem, s, m.a[0], m.a[1], m.b[0], m.b[1], m.out, p));
   } else if (NT == 64) {
@@ -1918,18 +1728,43 @@ int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   return WN_OK;
 }
 
-// block backward with the dilated conv's data-gradient GEMM fused in (block_bwd5)
-int launch_block_bwd5(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStream_t s) {
+// block backward with the dilated conv's data-gradient GEMM fused in (block_bwd6)
+int launch_block_bwd6(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStream_t s) {
   const int n_items = p.n_batches * p.b.tiles_per_batch;
   if (n_items <= 0) return WN_OK;
   const int n_ctas = std::min(n_items, g_sm_count);
   const int smem = Bwd5Smem::TOTAL + 1024;
-  WN_REQUIRE(p.b.bias_fg == nullptr, WN_ERR_INVALID, "block_bwd5 serves models without bias");
-  auto k = bwd_env().bwd6 ? (p.b.has_dense ? block_bwd6_kernel<true> : block_bwd6_kernel<false>)
-                          : (p.b.has_dense ? block_bwd5_kernel<true> : block_bwd5_kernel<false>);
+  WN_REQUIRE(p.b.bias_fg == nullptr, WN_ERR_INVALID, "block_bwd6 serves models without bias");
+  auto k = p.b.has_dense ? block_bwd6_kernel<true> : block_bwd6_kernel<false>;
   WN_PROPAGATE(set_smem_once(k, smem));
-  WN_PROF("block_bwd5", s);
+  WN_PROF("block_bwd6", s);
   WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)n_ctas), dim3(608), smem, s, m.x, m.w0, m.w1, m.a_in, m.q_in, m.wdT, m.a_out, m.q_out, p));
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+int launch_frame_sum_bf16(const void* src, int64_t rows_per_batch, int pitch, int c0, int B, int t0, int len, int frames, float* out,
+                          int out_pitch, int dd, cudaStream_t s) {
+  if (len <= 0) return WN_OK;
+  const int smem = frames * 128 * 4;
+  WN_REQUIRE(smem <= 200 * 1024, WN_ERR_UNSUPPORTED, "conditioning with %d frames does not fit the frame-sum kernel", frames);
+  WN_PROPAGATE(set_smem_once(frame_sum_bf16_kernel, smem));
+  const int per_batch = std::max(1, (2 * g_sm_count) / std::max(B, 1));
+  const int rows_per_cta = (int)ceil_div(len, per_batch);
+  dim3 grid((unsigned)ceil_div(len, rows_per_cta), (unsigned)B);
+  WN_PROF("frame_sum", s);
+  frame_sum_bf16_kernel<<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows_per_batch * pitch, pitch, c0, t0, len, frames,
+                                                rows_per_cta, out, out_pitch, dd);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+int launch_cond_table(const float* raw, const float* bias, int64_t n_rows, int dd, float* out, int64_t out_stride, cudaStream_t s) {
+  cond_table_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_rows * 128, 256), 1184), 256, 0, s>>>(raw, bias, n_rows, dd, out, out_stride);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+int launch_add_bias_rows(const float* raw, const float* bias, int64_t n_rows, int C, float* out, cudaStream_t s) {
+  add_bias_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_rows * C, 256), 1184), 256, 0, s>>>(raw, bias, n_rows, C, out);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -1953,17 +1788,29 @@ int head_forward_generic(const Model& m, const BwdMaps& M, const SkipHeadMaps& H
   // h1
   gm.a[0] = M.h0; gm.a[1] = M.h0; gm.b[0] = H.p1; gm.b[1] = H.p1; gm.out = M.h1;
   gp.nk[0] = S / 64; gp.bias = hp.bias_p1; gp.tag = "head_p1_gemm";
+  if (m.cond_head) {      // autoencoder decoder: + cond_N[frame] before the ReLU (model1.py:216-219); connection_1's bias is folded in
+    gp.epi = EPI_RELU_COND; gp.cond = m.cond_head; gp.cond_frames = m.cond_frames;
+    gp.lg_W = hp.W; gp.lg_pad = hp.pad;
+  }
   WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
   WN_DEBUG_SYNC("head p1 gemm", s);
   // logits
   gm.a[0] = M.h1; gm.a[1] = M.h1; gm.b[0] = H.p2; gm.b[1] = H.p2; gm.out = M.h1;      // (out map unused)
-  gp.n_ntiles = 1; gp.n_total = 256; gp.nk[0] = S / 64;
+  gp.n_ntiles = 1; gp.n_total = 256; gp.nk[0] = S / 64; gp.cond = nullptr;
   gp.epi = bias ? EPI_LOGITS_BIAS : EPI_LOGITS; gp.bias = hp.bias_p2;
   gp.logits = hp.logits; gp.lg_W = hp.W; gp.lg_Q = hp.Q; gp.lg_pad = hp.pad; gp.tag = "head_p2_gemm";
   WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
   WN_DEBUG_SYNC("head p2 gemm", s);
   return WN_OK;
 }
+
+}  // namespace wn
+extern "C" int wn_debug_ts(long long* h_buf, int32_t n) {      // timing experiments: the clock64 stamps of block_bwd6's CTA 0
+  if (!h_buf || n <= 0 || n > 16 * 64) return WN_ERR_INVALID;
+  cudaError_t e = cudaMemcpyFromSymbol(h_buf, wn::g_ts, (size_t)n * sizeof(long long));
+  return e == cudaSuccess ? WN_OK : WN_ERR_CUDA;
+}
+namespace wn {
 
 // =============================================================================================== host
 int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int B, int L, const uint8_t* P, uint8_t* Wp,
@@ -1996,7 +1843,7 @@ int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int
   WN_PROPAGATE(tmap_3d(&out->dxb, Wp + wl.DXb, 64, L, B, 64, (uint64_t)L * 64, 128));
   WN_PROPAGATE(tmap_3d(&out->dfg, Wp + wl.DFG, 128, L, B, 128, (uint64_t)L * 128, 128));
   WN_PROPAGATE(tmap_3d(&out->zf, Wp + wl.Zf, 64, L, B, 64, (uint64_t)L * 64, 128));
-  // block_bwd5: the Q halves of the split data gradient live in the two halves of the (then unused) dFG buffer
+  // block_bwd6: the Q halves of the split data gradient live in the two halves of the (then unused) dFG buffer
   const size_t half = align_up((size_t)B * L * 64 * 2, 1024);
   WN_PROPAGATE(tmap_3d(&out->dqa, Wp + wl.DFG, 64, L, B, 64, (uint64_t)L * 64, 128));
   WN_PROPAGATE(tmap_3d(&out->dqb, Wp + wl.DFG + half, 64, L, B, 64, (uint64_t)L * 64, 128));
@@ -2034,11 +1881,11 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   const BwdEnv& env = bwd_env();
   const bool dz_tiled = !env.nt_stream;       // the block backward reads the skip-path gradient from the tiled layout (GemmNtParams::out_tiled)
   WN_REQUIRE(dz_tiled, WN_ERR_UNSUPPORTED, "WN_NT_STREAM=1 (row-major dZcat) has no block-backward kernel any more");
-  const bool fuse_dx = (env.bwd5 || env.bwd6) && !bias;     // block_bwd5 (bias gradients need dF|dG in memory: those models keep the dx GEMM)
+  const bool fuse_dx = env.bwd6 && !bias && m.cond_fg == nullptr;      // (conditioning gradients need dF|dG in memory too)     // block_bwd6 (bias gradients need dF|dG in memory: those models keep block_bwd3 + the dx GEMM)
   WN_CHECK_CUDA(cudaMemsetAsync(G, 0, (size_t)m.n_params * sizeof(float), s));
   if (!fuse_dx) {
     // dx ping-pong buffers: layer i writes tiles >= its own first tile only, so rows below hold the previous step's values of
-    // shallower layers (read by the next layer's tile loads) unless cleared.  (block_bwd5 writes every row that is read.)
+    // shallower layers (read by the next layer's tile loads) unless cleared.  (block_bwd6 writes every row that is read.)
     WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXa, 0, (size_t)B * L * 64 * 2, s));
     WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXb, 0, (size_t)B * L * 64 * 2, s));
     WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DFG, 0, (size_t)B * L * 128 * 2, s));
@@ -2064,6 +1911,9 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     gp.row_lo = 0; gp.row_hi = Wpad; gp.tag = "gemm_nt_dH1";
     WN_PROPAGATE(launch_gemm_nt(256, gm, gp, s));
     WN_DEBUG_SYNC("gemm_nt dH1", s);
+    if (m.cond_head_grad)      // d loss / d cond_N[frame] = sum of dH1 (gradient at the head's pre-activation) over the frame's time steps
+      for (int c0 = 0; c0 < S; c0 += 128)
+        WN_PROPAGATE(launch_frame_sum_bf16(Wp + wl.DH1, Wpad, S, c0, B, pad, W, m.cond_frames, m.cond_head_grad, S, 0, s));
     gm.a[0] = M.dh1; gm.a[1] = M.dh1; gm.b[0] = M.p1T; gm.b[1] = M.p1T; gm.out = M.dsk;
     gp.nk[0] = S / 64;                                           // K = S (S = 512: the streaming kernel)
     gp.aux = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.H0); gp.tag = "gemm_nt_dSK";
@@ -2132,7 +1982,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   ra.layer_stride = N > 1 ? m.layers[1].filt.w - m.layers[0].filt.w : 0;
   ra.n_layers = N; ra.R = m.R; ra.D = m.D;
   const int tiles_total = (int)ceil_div(L, 128);
-  // first tile of layer i: its own first valid one; block_bwd5 starts at the previous layer's, so that every row layer i - 1
+  // first tile of layer i: its own first valid one; block_bwd6 starts at the previous layer's, so that every row layer i - 1
   // reads has been written in this step (rows below s_out as zeros)
   auto first_tile = [&](int i) { return fuse_dx ? (i > 0 ? m.layers[i - 1].start / 128 : 0) : m.layers[i].start / 128; };
   for (int i = 0; i < N; ++i) ra.n_ctas[i] = std::min(B * (tiles_total - first_tile(i)), g_sm_count);
@@ -2140,8 +1990,8 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     const LayerP& l = m.layers[i];
     const int d = l.dilation, s_out = l.start, s_in = s_out - d;
     const bool has_dense = i + 1 < N;
-    const CUtensorMap& dx_next = ((i + 1) & 1) ? M.dxb : M.dxa;       // dx_{i+1}  (block_bwd5: A_{i+1})
-    const CUtensorMap& dx_cur = (i & 1) ? M.dxb : M.dxa;              // dx_i      (block_bwd5: A_i)
+    const CUtensorMap& dx_next = ((i + 1) & 1) ? M.dxb : M.dxa;       // dx_{i+1}  (block_bwd6: A_{i+1})
+    const CUtensorMap& dx_cur = (i & 1) ? M.dxb : M.dxa;              // dx_i      (block_bwd6: A_i)
     const size_t dx_next_off = ((i + 1) & 1) ? wl.DXb : wl.DXa;
     const int tile0 = first_tile(i), tpb = tiles_total - tile0;
     if (fuse_dx) {
@@ -2155,13 +2005,15 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       bp.tw0 = L - W; bp.tw_al = tw_al; bp.Wp = Wpad;
       bp.dzs = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DZcat); bp.dzs_pitch = 64 * N; bp.dzs_col = 64 * i;
       bp.dzs_lb0 = i * B; bp.dzs_nblk = (int)ceil_div(Wpad, 32);
+      static const bool ts_env = getenv("WN_TS") != nullptr;
+      bp.trace = (ts_env && i == N / 2) ? 1 : 0;
       bp.d_next = has_dense ? m.layers[i + 1].dilation : 0;
       bp.own_row0 = (s_out / 128) * 128;
       if (l2_hints_on()) { bp.pol_first = kL2EvictFirst; bp.pol_last = kL2EvictLast; }
       b2.n_batches = B;
       b2.partial = reinterpret_cast<float*>(Wp + wl.WGP) + (int64_t)i * WGP_LAYER_FLOATS;
-      WN_PROPAGATE(launch_block_bwd5(bm, b2, s));
-      WN_DEBUG_SYNC("block_bwd5", s);
+      WN_PROPAGATE(launch_block_bwd6(bm, b2, s));
+      WN_DEBUG_SYNC("block_bwd6", s);
       if (side) {
         WN_CHECK_CUDA(cudaEventRecord(side->fork, s));
         WN_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
@@ -2184,11 +2036,18 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       bp.dzs = reinterpret_cast<const __nv_bfloat16*>(Wp + wl.DZcat); bp.dzs_pitch = 64 * N; bp.dzs_col = 64 * i;
       bp.dzs_lb0 = i * B; bp.dzs_nblk = (int)ceil_div(Wpad, 32);
       bp.bias_fg = bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
+      if (m.cond_fg) {      // conditioned decoder: recompute with the same table (the conv bias is part of it)
+        bp.cond = m.cond_fg; bp.cond_frames = m.cond_frames; bp.cond_layers = N; bp.cond_layer = i;
+        bp.bias_fg = nullptr;
+      }
       if (l2_hints_on()) { bp.pol_first = kL2EvictFirst; bp.pol_last = kL2EvictLast; }
       b2.n_batches = B;
       b2.partial = reinterpret_cast<float*>(Wp + wl.WGP) + (int64_t)i * WGP_LAYER_FLOATS;
       WN_PROPAGATE(launch_block_bwd2(bm, b2, s));
       WN_DEBUG_SYNC("block_bwd3", s);
+      if (m.cond_fg_grad)   // d loss / d cond_i[frame] in the autoencoder's raw (gate | filter) order: (B, frames, N, 2 D)
+        WN_PROPAGATE(launch_frame_sum_bf16(Wp + wl.DFG, L, 128, 0, B, s_out, L - s_out, m.cond_frames,
+                                           m.cond_fg_grad + (int64_t)i * 2 * m.D, N * 2 * m.D, m.D, s));
       if (side) {   // sum this layer's per-CTA weight-gradient tiles next to the kernels that follow (its CTAs need ~1 KB of smem)
         WN_CHECK_CUDA(cudaEventRecord(side->fork, s));
         WN_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));

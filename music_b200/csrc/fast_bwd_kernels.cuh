@@ -13,7 +13,8 @@ namespace wn {
 // rows are tiled by 128 inside each batch of a 3-D tensor (cols, rows, batches); n0 = NT * n-tile.
 // ---------------------------------------------------------------------------------------------
 // streaming NT = 256 kernel only: EPI_RELU (out = relu(acc [+ bias]) in bf16) and EPI_LOGITS (fp32 (B,Q,W) output of the head)
-enum { EPI_PLAIN = 0, EPI_MASK = 1, EPI_ADD = 2, EPI_RELU = 3, EPI_RELU_BIAS = 4, EPI_LOGITS = 5, EPI_LOGITS_BIAS = 6 };
+// EPI_RELU_COND: out = relu(acc + cond[(b * cond_frames + frame(row)) * n_total + column]) (per-frame conditioning of the head)
+enum { EPI_PLAIN = 0, EPI_MASK = 1, EPI_ADD = 2, EPI_RELU = 3, EPI_RELU_BIAS = 4, EPI_LOGITS = 5, EPI_LOGITS_BIAS = 6, EPI_RELU_COND = 7 };
 struct GemmNtMaps {
   CUtensorMap a[2];   // 3-D (cols, rows, batches) box {64,128,1}
   CUtensorMap b[2];   // 2-D [N rows][K cols]       box {64, NT}
@@ -38,6 +39,8 @@ struct GemmNtParams {
   const float* bias;            // EPI_RELU_BIAS / EPI_LOGITS_BIAS: [n_total] added to the accumulator
   float* logits;                // EPI_LOGITS*: (B, lg_Q, lg_W) fp32; row j of a batch is time step j - lg_pad (rows with j < lg_pad are skipped)
   int lg_W, lg_Q, lg_pad;
+  const float* cond;            // EPI_RELU_COND: (B, cond_frames, n_total) fp32; the frame follows the time step row - lg_pad of lg_W
+  int cond_frames;
   const char* tag;              // profiler label (host only)
 };
 int launch_gemm_nt(int NT, const GemmNtMaps& m, const GemmNtParams& p, cudaStream_t s);
@@ -73,7 +76,7 @@ int launch_gemm_tn(int NB, const GemmTnMaps& m, const GemmTnParams& p, cudaStrea
 // block_bwd: recompute [f|g] of block i, dz = dx_{i+1} Wd + dzs, gate backward -> dFG, z  (one tile / CTA)
 // ---------------------------------------------------------------------------------------------
 struct BlockBwdMaps {
-  CUtensorMap a_in, q_in, a_out, q_out;   // block_bwd5: A / Q of layer i + 1 (loads) and of layer i (stores), each (64, L, B)
+  CUtensorMap a_in, q_in, a_out, q_out;   // block_bwd6: A / Q of layer i + 1 (loads) and of layer i (stores), each (64, L, B)
   CUtensorMap x;      // x_i (64, L, B)
   CUtensorMap w0, w1; // W_fg taps [128][64]
   CUtensorMap dx;     // dx_{i+1} (64, L, B)
@@ -88,7 +91,7 @@ struct BlockBwdParams {
   const __nv_bfloat16* dzs;     // [B*Wp][dzs_pitch], this layer's 64 columns start at dzs_col
   int dzs_pitch, dzs_col;
   int dzs_lb0, dzs_nblk;        // block_bwd3 (tiled dZcat): layer * B, 32-row blocks per batch row
-  int d_next, own_row0;         // block_bwd5: dilation of layer i + 1 (row shift of its Q tile); first row of this layer's own first tile
+  int d_next, own_row0;         // block_bwd6: dilation of layer i + 1 (row shift of its Q tile); first row of this layer's own first tile
   const float* bias_fg;
   unsigned long long pol_first, pol_last;   // L2 eviction hints (0: none)
   // additive per-frame conditioning of the [f|g] pre-activations (wavenet_autoencoder `_conditon`, model1.py:227-247): row tau of
@@ -96,6 +99,7 @@ struct BlockBwdParams {
   // index tau - s_out and length L - s_out.  null: none.
   const float* cond;
   int cond_frames, cond_layers, cond_layer;
+  int trace;                    // WN_TS=1 (timing experiments): CTA 0 of block_bwd6 writes clock64 stamps per tile (wn_debug_ts)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -280,286 +280,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// ====================================================================================== block (two epilogue groups)
-// block_fwd2 with the 16 epilogue warps split into TWO GROUPS of 8 that take alternate tiles.  In block_fwd2 all 16 warps walk
-// through the same phases at the same time (TMEM load -> MUFU -> shared-memory hand-over -> wait for UMMA #2 -> residual ->
-// hand-over): ~4300 cycles per tile against a tensor-pipe need of 712 and a MUFU floor of 1024, issue slots 45 % used.  Here
-// group g owns tile parity g - its TMEM buffer {f|g, dense}, z tile and lo tile were per parity already - so the gate math of
-// tile n + 1 runs while tile n waits for UMMA #2 and stages its outputs.  What was shared is made private or handed to a
-// store thread:
-//  * x_{i+1} (hi) is staged IN PLACE over the tap-1 tile of the tile's own input stage (each thread overwrites exactly the
-//    chunks it has just read as the residual; UMMA #1 has long completed), lo' in place over the lo tile as before; warp 18
-//    issues their TMA stores, waits for the reads and only then releases the input stage and the lo tile;
-//  * the Zcat store is issued by each group's leader right after epilogue 1 and checked one phase later.
-struct Fwd3Smem {
-  static constexpr uint32_t W0 = 0, W1 = TILE_BYTES, WD = 2 * TILE_BYTES;
-  static constexpr uint32_t IN = 2 * TILE_BYTES + WD_BYTES, IN_STAGE = 2 * TILE_BYTES;     // 3 x {x tap0, x tap1 (-> x_{i+1} hi)}
-  static constexpr uint32_t Z = IN + 3 * IN_STAGE;                                         // 2 z tiles (one per group)
-  static constexpr uint32_t LO = Z + 2 * TILE_BYTES;                                       // 2 lo tiles (one per group)
-  static constexpr uint32_t TOTAL = LO + 2 * TILE_BYTES;                                   // 200 KB
-};
-
-template <bool BIAS, bool COND>
-__global__ void __launch_bounds__(608, 1)
-block_fwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
-                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_wd,
-                  const __grid_constant__ CUtensorMap tm_xo, const __grid_constant__ CUtensorMap tm_loo,
-                  const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_lo, BlockFwdParams p, int n_batches) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t w_full, in_full[3], in_empty[3], fg_full[2], dense_full[2], acc_empty[2], z_ready[2];
-  __shared__ __align__(8) uint64_t lo_full[2], lo_empty[2], st_req[2];
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    mbar_init(&w_full, 1);
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(&in_full[i], 1);
-      mbar_init(&in_empty[i], 2);       // UMMA #1 commit + (store thread after the x_{i+1} store | group leader when there is no dense conv)
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&fg_full[i], 1);
-      mbar_init(&dense_full[i], 1);
-      mbar_init(&acc_empty[i], 1);
-      mbar_init(&z_ready[i], 1);
-      mbar_init(&lo_full[i], 1);
-      mbar_init(&lo_empty[i], 1);
-      mbar_init(&st_req[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t sbase = smem_u32(sm);
-  const int n_items = n_batches * p.tiles_per_batch;
-  const bool dense = p.has_dense != 0;
-  const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp == 16) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0 && n_mine > 0) {
-      mbar_expect_tx(&w_full, 2 * TILE_BYTES + (dense ? WD_BYTES : 0));
-      tma_load_2d(sm + Fwd3Smem::W0, &tm_w0, &w_full, 0, 0);
-      tma_load_2d(sm + Fwd3Smem::W1, &tm_w1, &w_full, 0, 0);
-      if (dense) tma_load_2d(sm + Fwd3Smem::WD, &tm_wd, &w_full, 0, 0);
-      for (int it = 0; it < n_mine; ++it) {
-        const int item = blockIdx.x + it * gridDim.x;
-        const int st = it % 3;
-        const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
-        mbar_wait(&in_empty[st], ((it / 3) & 1) ^ 1);
-        uint8_t* si = sm + Fwd3Smem::IN + st * Fwd3Smem::IN_STAGE;
-        mbar_expect_tx(&in_full[st], 2 * TILE_BYTES);
-        tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b, p.pol_first);     // tap 0: the last read of these rows of x_i
-        tma_load_3d(si + TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);
-        if (dense) {      // low half of the residual stream
-          mbar_wait(&lo_empty[it & 1], ((it >> 1) & 1) ^ 1);
-          mbar_expect_tx(&lo_full[it & 1], TILE_BYTES);
-          tma_load_3d(sm + Fwd3Smem::LO + (it & 1) * TILE_BYTES, &tm_lo, &lo_full[it & 1], 0, tau0, b, p.pol_first);
-        }
-      }
-    }
-  } else if (warp == 17) {
-    // ------------------------------------------------------------ MMA issuer (polling)
-    if (lane == 0 && n_mine > 0) {
-      constexpr uint32_t id1 = idesc_bf16(128, 128, 0, 0), id2 = idesc_bf16(128, 64, 0, 0);
-      mbar_wait(&w_full, 0);
-      int j1 = 0, j2 = 0;          // next UMMA #1 / UMMA #2 tile
-      while (j1 < n_mine || (dense && j2 < n_mine)) {
-        if (dense && j2 < j1 && mbar_test_wait(&z_ready[j2 & 1], (j2 >> 1) & 1)) {      // UMMA #2 first: never queue it behind a UMMA #1
-          tc_fence_after();
-          const uint32_t acc = tmem + (j2 & 1) * 192 + 128;
-          const uint32_t zt = sbase + Fwd3Smem::Z + (j2 & 1) * TILE_BYTES;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(zt, kk), desc_kmajor(sbase + Fwd3Smem::WD, kk), id2, kk > 0);
-          umma_commit(&dense_full[j2 & 1]);
-          ++j2;
-        }
-        if (j1 < n_mine && mbar_test_wait(&in_full[j1 % 3], (j1 / 3) & 1) && mbar_test_wait(&acc_empty[j1 & 1], ((j1 >> 1) & 1) ^ 1)) {
-          tc_fence_after();
-          const uint32_t si = sbase + Fwd3Smem::IN + (j1 % 3) * Fwd3Smem::IN_STAGE, acc = tmem + (j1 & 1) * 192;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si, kk), desc_kmajor(sbase + Fwd3Smem::W0, kk), id1, kk > 0);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si + TILE_BYTES, kk), desc_kmajor(sbase + Fwd3Smem::W1, kk), id1, true);
-          umma_commit(&fg_full[j1 & 1]);
-          umma_commit(&in_empty[j1 % 3]);
-          ++j1;
-        }
-      }
-    }
-  } else if (warp == 18) {
-    // ------------------------------------------------------------ store thread: x_{i+1} hi / lo' -> global, then frees their tiles
-    if (lane == 0 && dense) {
-      for (int it = 0; it < n_mine; ++it) {
-        const int item = blockIdx.x + it * gridDim.x;
-        const int st = it % 3, g = it & 1;
-        const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
-        mbar_wait(&st_req[g], (it >> 1) & 1);
-        // x_{i+1} hi / lo' are read by the very next launch
-        tma_store_3d(&tm_xo, sm + Fwd3Smem::IN + st * Fwd3Smem::IN_STAGE + TILE_BYTES, 0, tau0, b, p.pol_last);
-        tma_store_3d(&tm_loo, sm + Fwd3Smem::LO + g * TILE_BYTES, 0, tau0, b, p.pol_last);
-        tma_store_commit();
-        tma_store_wait_read();
-        mbar_arrive(&in_empty[st]);
-        mbar_arrive(&lo_empty[g]);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue: group g = warps 8g .. 8g+7, tiles it = g, g+2, ...
-    const int g = warp >> 3, q4 = warp & 3, h = (warp >> 2) & 1;      // TMEM lane quarter (= warp % 4), 32-column half
-    const int row = q4 * 32 + lane;
-    const bool leader = (tid & 255) == 0;
-    auto group_bar = [&]() {
-      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-      else asm volatile("bar.sync 2, 256;" ::: "memory");
-    };
-    const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, g * 192);
-    uint8_t* zt = sm + Fwd3Smem::Z + g * TILE_BYTES;
-    uint8_t* lot = sm + Fwd3Smem::LO + g * TILE_BYTES;
-    for (int it = g; it < n_mine; it += 2) {
-      const int item = blockIdx.x + it * gridDim.x;
-      const int st = it % 3;
-      const uint32_t ph2 = (it >> 1) & 1;
-      const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
-      const int tau = tau0 + row;
-      const bool valid = (tau >= p.s_out) && (tau < p.L);
-      uint8_t* xt = sm + Fwd3Smem::IN + st * Fwd3Smem::IN_STAGE + TILE_BYTES;      // x_i[tau] (residual) -> x_{i+1} hi
-      const float* condp = nullptr;
-      if (COND)      // this row's conditioning vector (autoencoder decoder; rows outside the valid range are masked anyway)
-        condp = p.cond + (((int64_t)b * p.cond_frames + (valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0)) * p.cond_layers +
-                          p.cond_layer) * 128;
-      // ---- epilogue 1: gate -> z tile (A operand of UMMA #2, source of the Zcat store)
-      mbar_wait(&fg_full[g], ph2);
-      tc_fence_after();
-      uint32_t pz[16];
-#pragma unroll
-      for (int ps = 0; ps < 2; ++ps) {
-        const int c0 = h * 32 + ps * 16;
-        uint32_t f[16], gq[16];
-        tmem_ld16(lane_addr + c0, f);
-        tmem_ld16(lane_addr + 64 + c0, gq);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float f0 = __uint_as_float(f[2 * j]), f1 = __uint_as_float(f[2 * j + 1]);
-          float g0 = __uint_as_float(gq[2 * j]), g1 = __uint_as_float(gq[2 * j + 1]);
-          if (BIAS) {
-            f0 += p.bias_fg[c0 + 2 * j];
-            f1 += p.bias_fg[c0 + 2 * j + 1];
-            g0 += p.bias_fg[64 + c0 + 2 * j];
-            g1 += p.bias_fg[64 + c0 + 2 * j + 1];
-          }
-          if (COND) {
-            f0 += __ldg(condp + c0 + 2 * j);
-            f1 += __ldg(condp + c0 + 2 * j + 1);
-            g0 += __ldg(condp + 64 + c0 + 2 * j);
-            g1 += __ldg(condp + 64 + c0 + 2 * j + 1);
-          }
-          const float z0 = sigmoid_fast(g0) * tanh_fast(f0), z1 = sigmoid_fast(g1) * tanh_fast(f1);
-          pz[ps * 8 + j] = valid ? pack_bf16(z0, z1) : 0u;
-        }
-      }
-      if (!dense) {      // no epilogue 2: the previous Zcat store of this group (tile it - 2) is checked here instead
-        if (leader) tma_store_wait_read();
-        group_bar();
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(zt + sw128_chunk(row, h * 4 + q)) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      group_bar();
-      if (leader) {
-        if (dense) mbar_arrive(&z_ready[g]);
-        else {
-          mbar_arrive(&acc_empty[g]);
-          mbar_arrive(&in_empty[st]);
-        }
-        if (tau0 >= p.tw_al) {      // z is read again only by the skip GEMM at the end of the forward
-          tma_store_3d(&tm_z, zt, p.zcol, tau0 - p.tw_al, b, p.pol_first);
-          tma_store_commit();      // checked before this group's next write of the z tile
-        }
-      }
-      if (!dense) continue;
-      // ---- epilogue 2: x_{i+1} = dense + (hi + lo) in fp32, split again into hi + lo
-      mbar_wait(&lo_full[g], ph2);
-      mbar_wait(&dense_full[g], ph2);
-      tc_fence_after();
-#pragma unroll
-      for (int ps = 0; ps < 2; ++ps) {
-        const int c0 = h * 32 + ps * 16;
-        uint32_t dv[16];
-        tmem_ld16(lane_addr + 128 + c0, dv);
-        const uint32_t o0 = sw128_chunk(row, h * 4 + ps * 2), o1 = sw128_chunk(row, h * 4 + ps * 2 + 1);
-        const uint4 rv0 = *reinterpret_cast<const uint4*>(xt + o0), rv1 = *reinterpret_cast<const uint4*>(xt + o1);
-        const uint4 lv0 = *reinterpret_cast<const uint4*>(lot + o0), lv1 = *reinterpret_cast<const uint4*>(lot + o1);
-        const uint32_t rr[8] = {rv0.x, rv0.y, rv0.z, rv0.w, rv1.x, rv1.y, rv1.z, rv1.w};
-        const uint32_t ll[8] = {lv0.x, lv0.y, lv0.z, lv0.w, lv1.x, lv1.y, lv1.z, lv1.w};
-        tmem_ld_wait();
-        uint32_t phh[8], pll[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
-          const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[j]);
-          float x0 = __uint_as_float(dv[2 * j]) + (__low2float(r2) + __low2float(l2));
-          float x1 = __uint_as_float(dv[2 * j + 1]) + (__high2float(r2) + __high2float(l2));
-          if (BIAS) {
-            x0 += p.bias_d[c0 + 2 * j];
-            x1 += p.bias_d[c0 + 2 * j + 1];
-          }
-          if (!valid) { x0 = 0.f; x1 = 0.f; }
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-          phh[j] = *reinterpret_cast<const uint32_t*>(&h2);
-          pll[j] = pack_bf16(x0 - __low2float(h2), x1 - __high2float(h2));
-        }
-        *reinterpret_cast<uint4*>(xt + o0) = make_uint4(phh[0], phh[1], phh[2], phh[3]);      // in place: these chunks are this thread's own
-        *reinterpret_cast<uint4*>(xt + o1) = make_uint4(phh[4], phh[5], phh[6], phh[7]);
-        *reinterpret_cast<uint4*>(lot + o0) = make_uint4(pll[0], pll[1], pll[2], pll[3]);
-        *reinterpret_cast<uint4*>(lot + o1) = make_uint4(pll[4], pll[5], pll[6], pll[7]);
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      if (leader) tma_store_wait_read();      // this tile's Zcat store, issued a whole epilogue ago: the z tile may be rewritten
-      group_bar();                            // every thread of the group has drained the TMEM buffer and staged its outputs
-      if (leader) {
-        mbar_arrive(&acc_empty[g]);
-        mbar_arrive(&st_req[g]);
-      }
-    }
-    if (leader) tma_store_wait_read();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem);
-}
-
 }  // namespace
-
-int launch_block_fwd3(const BlockFwdMaps& m, const BlockFwdParams& p, int n_batches, cudaStream_t s) {
-  const int smem = Fwd3Smem::TOTAL + 1024;
-  const int n_items = n_batches * p.tiles_per_batch;
-  if (n_items <= 0) return WN_OK;
-  const bool bias = p.bias_fg != nullptr;
-  const bool cond = p.cond != nullptr;
-  auto k = cond ? (bias ? block_fwd3_kernel<true, true> : block_fwd3_kernel<false, true>)
-                : (bias ? block_fwd3_kernel<true, false> : block_fwd3_kernel<false, false>);
-  static const void* configured[4] = {};
-  const int slot = (cond ? 2 : 0) + (bias ? 1 : 0);
-  if (configured[slot] == nullptr) {
-    WN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[slot] = reinterpret_cast<const void*>(k);
-  }
-  WN_PROF("block_fwd3", s);
-  WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)std::min(n_items, g_sm_count)), dim3(608), smem, s, m.x, m.w0, m.w1, m.wd, m.xo, m.loo, m.z, m.lo, p,
-                           n_batches));
-  WN_CHECK_LAUNCH();
-  return WN_OK;
-}
 
 int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, const BlockFwdPtrs& g, int n_batches, cudaStream_t s) {
   const int smem = Fwd2Smem::TOTAL + 1024;

@@ -277,7 +277,7 @@ WsLayout ws_layout(const Model& m, int B, int L) {
   w.DZcat = take((size_t)B * align_up((size_t)W, 32) * 64 * N * 2);      // (rows padded to 32 for the tiled layout)
   w.DXa = take((size_t)B * L * 64 * 2);
   w.DXb = take((size_t)B * L * 64 * 2);
-  w.DFG = take(2 * align_up((size_t)B * L * 64 * 2, 1024));      // dF|dG (B, L, 128), or block_bwd5's two Q buffers (B, L, 64)
+  w.DFG = take(2 * align_up((size_t)B * L * 64 * 2, 1024));      // dF|dG (B, L, 128), or block_bwd6's two Q buffers (B, L, 64)
   w.Zf = take((size_t)B * L * 64 * 2);
   w.DX0f = take((size_t)B * L * 64 * 4);
   w.WGP = take((size_t)WGP_LAYER_FLOATS * 4 * N);
@@ -422,6 +422,10 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
     p.has_dense = (i + 1 < N) ? 1 : 0;
     p.bias_fg = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
     p.bias_d = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_d) + i * 64 : nullptr;
+    if (m.cond_fg) {      // conditioned decoder: the conv bias is part of the table
+      p.cond = m.cond_fg; p.cond_frames = m.cond_frames; p.cond_layers = N; p.cond_layer = i;
+      p.bias_fg = nullptr;
+    }
     static const int dbg_env = [] { const char* e = getenv("WN_DBG"); return e ? atoi(e) : 0; }();
     static const bool ts_env = getenv("WN_TS") != nullptr;
     p.dbg = dbg_env;
@@ -433,9 +437,7 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
     g.lo_out = reinterpret_cast<__nv_bfloat16*>(Wp + wl.XLO + wl.x_stride * ((i + 1) & 1));
     g.x_out = reinterpret_cast<__nv_bfloat16*>(Wp + wl.X + wl.x_stride * (i + 1 < N ? i + 1 : i));
     g.zcat = reinterpret_cast<__nv_bfloat16*>(Wp + wl.Zcat);
-    static const bool fwd3_env = [] { const char* e = getenv("WN_FWD3"); return e && e[0] == '1'; }();
-    if (fwd3_env && p.ts == nullptr && p.dbg == 0) WN_PROPAGATE(launch_block_fwd3(fp->block[i], p, B, s));
-    else WN_PROPAGATE(launch_block_fwd2(fp->block[i], p, g, B, s));
+    WN_PROPAGATE(launch_block_fwd2(fp->block[i], p, g, B, s));
     WN_DEBUG_SYNC("block_fwd", s);
   }
   SkipHeadParams hp{};
@@ -448,7 +450,7 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
   hp.bias_skip = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_skip) : nullptr;
   hp.bias_p1 = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_p1) : nullptr;
   hp.bias_p2 = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_p2) : nullptr;
-  if (m.S == 256) {
+  if (m.S == 256 && m.cond_head == nullptr) {
     WN_PROPAGATE(launch_skip_head(fp->head, hp, s));
     WN_DEBUG_SYNC("skip_head", s);
   } else {

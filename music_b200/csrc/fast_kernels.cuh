@@ -43,8 +43,7 @@ struct BlockFwdPtrs {
   __nv_bfloat16* zcat;           // (B, Wp, zpitch)
 };
 int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, const BlockFwdPtrs& g, int n_batches, cudaStream_t s);
-// two epilogue groups on alternate tiles, outputs staged in place, dedicated store thread (WN_FWD3=1)
-int launch_block_fwd3(const BlockFwdMaps& m, const BlockFwdParams& p, int n_batches, cudaStream_t s);
+
 
 // ---------------------------------------------------------------- forward: skip GEMM + head
 struct SkipHeadMaps {

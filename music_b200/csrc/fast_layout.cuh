@@ -55,10 +55,15 @@ struct BwdMaps {
   CUtensorMap p1T, p2T;                  // [256][256] box {64,256}
   CUtensorMap wsTcat;                    // [64 N rows (layer, d)][256 s] box {64,256}
   CUtensorMap dxa, dxb, dfg, zf;         // (64|128, L, B)
-  CUtensorMap dqa, dqb;                  // block_bwd5: Q_i ping-pong buffers (64, L, B) inside the dFG region
+  CUtensorMap dqa, dqb;                  // block_bwd6: Q_i ping-pong buffers (64, L, B) inside the dFG region
 };
 int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int B, int L, const uint8_t* P, uint8_t* Wp,
                    const std::vector<CUtensorMap>& xm, BwdMaps* out);
+// conditioning helpers of the autoencoder's bf16 decoder (fast_bwd.cu)
+int launch_frame_sum_bf16(const void* src, int64_t rows_per_batch, int pitch, int c0, int B, int t0, int len, int frames, float* out,
+                          int out_pitch, int dd, cudaStream_t s);
+int launch_cond_table(const float* raw, const float* bias, int64_t n_rows, int dd, float* out, int64_t out_stride, cudaStream_t s);
+int launch_add_bias_rows(const float* raw, const float* bias, int64_t n_rows, int C, float* out, cudaStream_t s);
 struct SkipHeadMaps;
 struct SkipHeadParams;
 int head_forward_generic(const Model& m, const BwdMaps& M, const SkipHeadMaps& H, const SkipHeadParams& hp, int B, int L, cudaStream_t s);
