@@ -199,6 +199,9 @@ typedef struct {
   int32_t de_residual_channel, de_dilation_channel, de_skip_channel;
   int32_t use_bias;
   int32_t filter_width;            /* must be 2 */
+  int32_t mode;                    /* 0: fp32 check mode everywhere; 1: the conditioned decoder (model1.py:158-247, 89 % of the FLOPs)
+                                      on the bf16 tcgen05 WaveNet kernels, encoder in fp32.  Mode 1 needs decoder residual, dilation <= 64,
+                                      skip 256 or 512, quantization 256 channels, use_bias = 0 (the shipped model_params.json qualifies). */
 } wn_ae_config;
 int wn_ae_create(const wn_ae_config* cfg, wn_ae** out);
 int wn_ae_destroy(wn_ae* a);

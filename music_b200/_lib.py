@@ -39,7 +39,7 @@ class wn_ae_config(C.Structure):
                 ("en_residual_channel", C.c_int32), ("en_dilation_channel", C.c_int32),
                 ("en_bottleneck_width", C.c_int32), ("en_pool_kernel_size", C.c_int32),
                 ("de_residual_channel", C.c_int32), ("de_dilation_channel", C.c_int32), ("de_skip_channel", C.c_int32),
-                ("use_bias", C.c_int32), ("filter_width", C.c_int32)]
+                ("use_bias", C.c_int32), ("filter_width", C.c_int32), ("mode", C.c_int32)]
 
 
 _p, _i32, _i64, _f, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t

@@ -14,6 +14,8 @@
 // the generic tap-GEMM of check_kernels.cu plus three element-wise kernels below.
 #include "check_kernels.cuh"
 #include "common.cuh"
+#include "fast.cuh"
+#include "fast_layout.cuh"
 
 struct wn_ae {
   int N = 0, Q = 0, Re = 0, De = 0, BW = 0, pool = 0, Rd = 0, Dd = 0, Sd = 0, use_bias = 0, rf = 0;
@@ -23,6 +25,12 @@ struct wn_ae {
   wn::ConvP en_causal, bottleneck, de_causal, conn1, conn2;
   std::vector<wn::ConvP> cond;                 // offsets into the conditioning vector (always biased)
   int64_t n_params = 0, n_cond = 0;
+  // mode 1: the conditioned decoder (89 % of the FLOPs) runs through the bf16 tcgen05 WaveNet kernels.  `dec` is a WaveNet plan
+  // whose parameter offsets point INTO the autoencoder's flat vector (filter = second half of filter_gate, gate = first half,
+  // post_process_1/2 = connection_1/2), so packing reads and the backward writes the autoencoder's own parameters / gradients.
+  int mode = 0;
+  wn::Model dec;
+  ~wn_ae() { wn::fast_release(dec); }
 };
 
 namespace wn {
@@ -183,6 +191,33 @@ AeWs ae_ws(const wn_ae& a, int B, int L, bool need_onehot, void* base, bool trai
   return w;
 }
 
+// mode 1: what follows the fp32 workspace - packed bf16 weight image, bf16 activation workspace of the decoder, conditioning
+// tables in the kernels' layout and their gradients (frame sums) in the autoencoder's raw layout
+struct AeFast {
+  size_t packed, ws, ctab_fg, ctab_head, cgrad_fg, cgrad_head, total;
+};
+AeFast ae_fast_layout(wn_ae& a, int B, int L, size_t base) {
+  AeFast f{};
+  const int W = L - a.rf + 1, frames = std::max(1, W / a.pool);
+  size_t off = align_up(base, 1024);
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 1024);
+    return o;
+  };
+  size_t pb = 0, wb = 0;
+  fast_packed_bytes(a.dec, &pb);
+  fast_workspace_bytes(a.dec, B, L, &wb);
+  f.packed = take(pb);
+  f.ws = take(wb);
+  f.ctab_fg = take((size_t)B * frames * a.N * 128 * 4);
+  f.ctab_head = take((size_t)B * frames * a.Sd * 4);
+  f.cgrad_fg = take((size_t)B * frames * a.N * 2 * a.Dd * 4);
+  f.cgrad_head = take((size_t)B * frames * a.Sd * 4);
+  f.total = off;
+  return f;
+}
+
 TensorView tv(const float* p, int64_t sb, int64_t st, int64_t sc, int shift = 0) {
   TensorView v;
   v.p = p; v.sb = sb; v.st = st; v.sc = sc; v.shift = shift;
@@ -248,6 +283,32 @@ extern "C" int wn_ae_create(const wn_ae_config* cfg, wn_ae** out) {
   add(a->cond[a->N], a->Sd, a->BW, 1, true, coff);
   a->n_cond = coff;
   a->rf = sum + 2;
+  a->mode = cfg->mode;
+  if (a->mode != 0) {
+    WN_REQUIRE(a->mode == 1, WN_ERR_INVALID, "wn_ae_create: unknown mode %d", a->mode);
+    Model& d = a->dec;
+    d.n_layers = a->N; d.R = a->Rd; d.D = a->Dd; d.S = a->Sd; d.Q = a->Q; d.use_bias = a->use_bias; d.fw = 2;
+    d.dil = a->dil; d.rf = a->rf; d.n_params = a->n_params;
+    d.layers.resize(a->N);
+    for (int i = 0; i < a->N; ++i) {
+      LayerP& l = d.layers[i];
+      const ConvP& fg = a->de_fg[i];
+      l.dilation = a->dil[i]; l.start = a->start[i];
+      l.gate = fg; l.gate.out = a->Dd;                                           // first half of filter_gate's outputs (model1.py:188)
+      l.filt = fg; l.filt.out = a->Dd; l.filt.w = fg.w + (int64_t)a->Dd * a->Rd * 2;      // second half (:190)
+      if (fg.b >= 0) l.filt.b = fg.b + a->Dd;
+      l.dense = a->de_dense[i];
+      l.skip = a->de_skip[i];
+    }
+    d.causal = a->de_causal; d.post1 = a->conn1; d.post2 = a->conn2;
+    d.fast_ok = fast_supported(d);
+    if (!d.fast_ok || a->use_bias) {
+      set_error("wn_ae_create: mode 1 (bf16 tensor-core decoder) needs decoder residual, dilation <= 64, skip 256 or 512, quantization 256 "
+                "channels and use_bias = 0 (got %d / %d / %d / %d, bias %d); use mode 0 (fp32)", a->Rd, a->Dd, a->Sd, a->Q, a->use_bias);
+      delete a;
+      return WN_ERR_UNSUPPORTED;
+    }
+  }
   *out = a;
   return WN_OK;
 }
@@ -260,6 +321,7 @@ extern "C" int wn_ae_workspace_bytes(const wn_ae* a, int32_t B, int32_t L, size_
   WN_REQUIRE(a && bytes && B > 0, WN_ERR_INVALID, "wn_ae_workspace_bytes: bad argument");
   WN_REQUIRE(L - a->rf + 1 > 0, WN_ERR_SHAPE, "wave sample not long enough");
   *bytes = ae_ws(*a, B, L, true, nullptr).bytes;
+  if (a->mode == 1) *bytes = ae_fast_layout(*const_cast<wn_ae*>(a), B, L, *bytes).total;
   return WN_OK;
 }
 
@@ -320,6 +382,32 @@ static int ae_forward_impl(wn_ae* a, int32_t B, int32_t L, const float* d_x, con
       WN_CHECK_CUDA(cudaMemcpyAsync(d_encoding, w.ENC, (size_t)B * frames * a->BW * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
   // ------------------------------------------------------------------ decoder (model1.py:158-225)
+  if (a->mode == 1) {
+    // bf16 tensor-core decoder: the N + 1 conditioning convs are applied to the (B, frames, BW) encoding in fp32 (tiny), their
+    // outputs become per-frame tables that the WaveNet block kernels add to the [f|g] pre-activations (and the head GEMM to
+    // connection_1's output); everything else is the conditioned WaveNet forward of fast_host.cu on the shared parameters.
+    uint8_t* base = reinterpret_cast<uint8_t*>(d_workspace);
+    const AeFast fl = ae_fast_layout(*a, B, L, w.bytes);
+    float* ctab_fg = reinterpret_cast<float*>(base + fl.ctab_fg);
+    float* ctab_head = reinterpret_cast<float*>(base + fl.ctab_head);
+    TensorView ENCf = tv(w.ENC, (int64_t)frames * a->BW, a->BW, 1);
+    for (int i = 0; i < N; ++i) {
+      PwArgs pc; pc.X = ENCf; pc.x_lo = 0; pc.x_hi = frames; pc.Y = tv(w.COND, (int64_t)frames * 2 * a->Dd, 2 * a->Dd, 1);
+      pc.B = B; pc.t0 = 0; pc.t1 = frames;
+      WN_PROPAGATE(apply_conv(d_cond, a->cond[i], w.WT, pc, 1, s));                       // (:178-179)
+      WN_PROPAGATE(launch_cond_table(w.COND, nullptr, (int64_t)B * frames, a->Dd, ctab_fg + (int64_t)i * 128, (int64_t)N * 128, s));
+    }
+    {
+      PwArgs pc; pc.X = ENCf; pc.x_lo = 0; pc.x_hi = frames; pc.Y = tv(ctab_head, (int64_t)frames * a->Sd, a->Sd, 1);
+      pc.B = B; pc.t0 = 0; pc.t1 = frames;
+      WN_PROPAGATE(apply_conv(d_cond, a->cond[N], w.WT, pc, 1, s));                       // (:216-217)
+    }
+    Model& d = a->dec;
+    d.cond_fg = ctab_fg; d.cond_head = ctab_head; d.cond_frames = frames;
+    d.cond_fg_grad = nullptr; d.cond_head_grad = nullptr;
+    WN_PROPAGATE(fast_pack(d, d_params, base + fl.packed, s));
+    return fast_forward(d, B, L, d_x, d_idx, base + fl.packed, base + fl.ws, d_logits, s);
+  }
   {
     PwArgs p; p.X = Xin; p.x_lo = 0; p.x_hi = L; p.Y = view(dec_x(0), a->Rd); p.B = B; p.t0 = 1; p.t1 = L;
     WN_PROPAGATE(apply_conv(d_params, a->de_causal, w.WT, p, 1, s));
@@ -399,6 +487,7 @@ extern "C" int wn_ae_train_workspace_bytes(const wn_ae* a, int32_t B, int32_t L,
   WN_REQUIRE(a && bytes && B > 0, WN_ERR_INVALID, "wn_ae_train_workspace_bytes: bad argument");
   WN_REQUIRE(L - a->rf + 1 > 0, WN_ERR_SHAPE, "wave sample not long enough");
   *bytes = ae_ws(*a, B, L, true, nullptr, true).bytes;
+  if (a->mode == 1) *bytes = ae_fast_layout(*const_cast<wn_ae*>(a), B, L, *bytes).total;
   return WN_OK;
 }
 
@@ -467,6 +556,32 @@ extern "C" int wn_ae_backward(wn_ae* a, int32_t B, int32_t L, const float* d_x, 
     return conv_dgrad(d_cond, a->cond[i], p, 1);
   };
 
+  if (a->mode == 1) {
+    // decoder backward on the tensor cores: writes every decoder gradient straight into G (shared offsets; it zero-fills G
+    // first) and leaves, per conditioning conv, the sum of the gradient at its output over the rows of each frame
+    uint8_t* base = reinterpret_cast<uint8_t*>(d_workspace);
+    const AeFast fl = ae_fast_layout(*a, B, L, w.bytes);
+    float* cg_fg = reinterpret_cast<float*>(base + fl.cgrad_fg);
+    float* cg_head = reinterpret_cast<float*>(base + fl.cgrad_head);
+    WN_CHECK_CUDA(cudaMemsetAsync(cg_fg, 0, (size_t)B * frames * N * 2 * Dd * sizeof(float), s));
+    WN_CHECK_CUDA(cudaMemsetAsync(cg_head, 0, (size_t)B * frames * Sd * sizeof(float), s));
+    Model& d = a->dec;
+    d.cond_fg = reinterpret_cast<const float*>(base + fl.ctab_fg); d.cond_head = reinterpret_cast<const float*>(base + fl.ctab_head);
+    d.cond_frames = frames; d.cond_fg_grad = cg_fg; d.cond_head_grad = cg_head;
+    WN_PROPAGATE(fast_backward(d, B, L, d_x, d_idx, base + fl.packed, base + fl.ws, const_cast<float*>(d_dlogits), G, s));
+    // conditioning convs: their weights (optional) and the encoding, head first as in the fp32 path
+    auto cond_bwd_from = [&](int i, const float* gsrc, int64_t g_bstride, int64_t g_rstride, int C) -> int {
+      TensorView gC = tv(gsrc, g_bstride, g_rstride, 1);
+      if (Gc) WN_PROPAGATE(conv_wgrad(Gc, a->cond[i], ENCv, 0, frames, 0, gC, 0, frames, 1, B));
+      PwArgs p; p.X = gC; p.x_lo = 0; p.x_hi = frames; p.Y = gENCv; p.accumulate = enc_started ? 1 : 0; p.B = B; p.t0 = 0; p.t1 = frames;
+      enc_started = true;
+      (void)C;
+      return conv_dgrad(d_cond, a->cond[i], p, 1);
+    };
+    WN_PROPAGATE(cond_bwd_from(N, cg_head, (int64_t)frames * Sd, Sd, Sd));
+    for (int i = N - 1; i >= 0; --i)
+      WN_PROPAGATE(cond_bwd_from(i, cg_fg + (int64_t)i * 2 * Dd, (int64_t)frames * N * 2 * Dd, (int64_t)N * 2 * Dd, 2 * Dd));
+  } else {
   // ------------------------------------------------------------------ head (model1.py:210-221)
   TensorView dLg = tv(d_dlogits, (int64_t)Q * W, 1, W, -tw);
   TensorView SKv = wview(w.SK), H1v = wview(w.H1), gH1v = wview(w.gH1), gSKv = wview(w.gSK);
@@ -524,6 +639,7 @@ extern "C" int wn_ae_backward(wn_ae* a, int32_t B, int32_t L, const float* d_x, 
     }
   }
   WN_PROPAGATE(conv_wgrad(G, a->de_causal, Xin, 0, L, 0, gXv, 1, L, 1, B));
+  }      // mode 0
   // ------------------------------------------------------------------ encoder (model1.py:137-156)
   {
     dim3 grid((unsigned)ew_blocks((int64_t)W * BW), (unsigned)B);

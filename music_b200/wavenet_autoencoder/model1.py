@@ -69,7 +69,7 @@ class wavenet_autoencoder(nn.Module):
 
     def __init__(self, filter_width, quantization_channel, dilations, en_residual_channel, en_dilation_channel,
                  en_bottleneck_width, en_pool_kernel_size, de_residual_channel, de_dilation_channel, de_skip_channel,
-                 use_bias, *, fresh_cond: bool = False):
+                 use_bias, *, fresh_cond: bool = False, mode: str = "auto"):
         super(wavenet_autoencoder, self).__init__()
         self.filter_width = filter_width
         self.quantization_channel = quantization_channel
@@ -89,6 +89,18 @@ class wavenet_autoencoder(nn.Module):
         self._init_causal_layer()
         self._init_connection()
         self.fresh_cond = fresh_cond
+        if mode not in L.MODE_NAMES:
+            raise ValueError(f"mode must be one of {list(L.MODE_NAMES)}")
+        # "bf16": the conditioned decoder (89 % of the FLOPs at the shipped parameters) runs on the tcgen05 WaveNet kernels, the
+        # encoder in fp32; "auto" picks that whenever the decoder's shape has kernels; "fp32": the SIMT check mode (1e-4 parity)
+        fast_ok = (de_residual_channel <= 64 and de_dilation_channel <= 64 and de_skip_channel in (256, 512)
+                   and quantization_channel == 256 and not use_bias)
+        if mode == "auto" and not fast_ok:
+            import warnings
+            warnings.warn("music_b200: no tcgen05 kernels for this decoder shape (residual %d, dilation %d, skip %d, quantization %d, "
+                          "bias %s); mode='auto' runs the autoencoder in the fp32 SIMT mode" %
+                          (de_residual_channel, de_dilation_channel, de_skip_channel, quantization_channel, bool(use_bias)))
+        self.mode = "fp32" if (mode == "fp32" or (mode == "auto" and not fast_ok)) else "bf16"
         # not registered in the reference (they are throw-away there): kept out of state_dict() on purpose
         object.__setattr__(self, "_cond_layers", self._new_cond_layers())
         self._handle = None
@@ -163,7 +175,7 @@ class wavenet_autoencoder(nn.Module):
             cfg = L.wn_ae_config(len(self.dilations), arr, self.quantization_channel, self.en_residual_channel,
                                  self.en_dilation_channel, self.en_bottleneck_width, self.en_pool_kernel_size,
                                  self.de_residual_channel, self.de_dilation_channel, self.de_skip_channel,
-                                 int(bool(self.use_bias)), self.filter_width)
+                                 int(bool(self.use_bias)), self.filter_width, 1 if self.mode == "bf16" else 0)
             h = C.c_void_p()
             L.check(lib.wn_ae_create(C.byref(cfg), C.byref(h)))
             self._handle = h

@@ -193,3 +193,97 @@ def test_incremental_decoder_generation_equals_full_forward(W, pool, bias):
     free = fast_generate_codes(net, enc, L, 8, idx[:, :rf], cond_weights=cond)
     again = fast_generate_codes(net, enc, L, 8, idx[:, :rf], cond_weights=cond, forced=free[:-1])
     assert torch.equal(free, again)
+
+
+# ------------------------------------------------------------------------------------------ bf16 tensor-core decoder
+@pytest.mark.parametrize("W,Sd,dense", [(96, 512, False), (100, 256, False), (61, 512, True)])
+def test_bf16_decoder_forward_backward_vs_oracle(W, Sd, dense):
+    """mode="bf16": the conditioned decoder (model1.py:158-247) on the tcgen05 WaveNet kernels - 32-channel stacks zero-padded to
+    64, per-frame conditioning added in the block kernels' epilogues (both `_conditon` branches: W = 96 divides into 12 frames,
+    100 / 61 tile the encoding), the S = 512 head as streaming GEMMs - and the encoder in fp32.  Logits 1e-2 relative (north
+    star's bf16 bar); gradients against torch autograd on the oracle: the decoder's tensors within the bf16 bound of
+    tests/test_gpu_fast.py (ordinary weights: ReLU mask flips included), the encoder's - which receive their gradient through
+    the bf16 decoder's conditioning sums - likewise; cosine of the whole gradient > 0.99."""
+    dil = [1, 2, 4, 8, 16, 1, 2, 4, 8, 16]
+    cfg = dict(Re=32, De=32, BW=64, pool=8, Rd=32, Dd=32, Sd=Sd)
+    from music_b200.wavenet_autoencoder.model1 import wavenet_autoencoder
+    torch.manual_seed(W)
+    net = wavenet_autoencoder(2, 256, dil, cfg["Re"], cfg["De"], cfg["BW"], cfg["pool"], cfg["Rd"], cfg["Dd"], cfg["Sd"], False, mode="auto")
+    assert net.mode == "bf16"
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.5)
+    st = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    cond = {}
+    for i, c in enumerate(net.cond_layers):
+        cond[f"cond.{i}.weight"] = c.weight.detach().clone().requires_grad_(True)
+        cond[f"cond.{i}.bias"] = c.bias.detach().clone().requires_grad_(True)
+    rf = O.receptive_field(2, dil)
+    B = 2
+    idx = torch.randint(0, 256, (B, rf + W - 1))
+    tgt = torch.randint(0, 256, (B * W,))
+    x = O.one_hot(idx, 256)
+    if dense:
+        x = x + 0.1 * torch.randn_like(x)
+    logits_ref = O.ae_forward_logits(st, cond, dil, x, cfg["pool"])
+    probs_ref = O.scrambled_softmax(logits_ref)
+    loss_ref = torch.nn.functional.cross_entropy(probs_ref, tgt)
+    loss_ref.backward()
+
+    net = net.cuda()
+    for c in net.cond_layers:
+        c.requires_grad_(True)
+    lg = net.forward_logits(wave_sample=x.cuda()) if dense else net.forward_logits(indices=idx.cuda())
+    e = max_rel(lg.detach().cpu().numpy(), logits_ref.detach().numpy())
+    print(f"AE bf16 decoder W={W} Sd={Sd}: logits max-rel {e:.3e}")
+    assert e < 1e-2
+    from music_b200._engine import SoftmaxRowsFunction
+    from music_b200 import _lib as L
+    out = SoftmaxRowsFunction.apply(lg, L.ROWS_REFERENCE)
+    loss = torch.nn.functional.cross_entropy(out, tgt.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-4
+    ga, gb, worst = [], [], (0.0, "")
+    for name, p in net.named_parameters():
+        g_ref = st[name].grad
+        if g_ref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        a, b = p.grad.detach().cpu().double().reshape(-1), g_ref.double().reshape(-1)
+        err = float((a - b).norm() / (b.norm() + 1e-30))
+        worst = max(worst, (err, name))
+        ga.append(a)
+        gb.append(b)
+    for i, c in enumerate(net.cond_layers):
+        for nm, t in (("weight", c.weight), ("bias", c.bias)):
+            a, b = t.grad.detach().cpu().double().reshape(-1), cond[f"cond.{i}.{nm}"].grad.double().reshape(-1)
+            err = float((a - b).norm() / (b.norm() + 1e-30))
+            worst = max(worst, (err, f"cond.{i}.{nm}"))
+    ga, gb = torch.cat(ga), torch.cat(gb)
+    cos = float((ga @ gb) / (ga.norm() * gb.norm()))
+    print(f"AE bf16 decoder W={W} Sd={Sd}: worst grad rel-l2 {worst}, cosine {cos:.5f}")
+    assert worst[0] < 0.15, worst
+    assert cos > 0.99
+
+
+def test_bf16_decoder_at_shipped_shape_tracks_fp32_mode():
+    """The shipped model_params.json shape (40 layers, 32 channels, bottleneck / skip 512, pool 512) on one clip of 8192 targets:
+    the bf16-decoder mode against the library's own fp32 check mode (oracle-pinned above) - logits 1e-2, loss 1e-4."""
+    from music_b200.wavenet_autoencoder.model1 import wavenet_autoencoder
+    dil = [2 ** i for i in range(10)] * 4
+    torch.manual_seed(0)
+    net16 = wavenet_autoencoder(2, 256, dil, 32, 32, 512, 512, 32, 32, 512, False, mode="bf16").cuda()
+    net32 = wavenet_autoencoder(2, 256, dil, 32, 32, 512, 512, 32, 32, 512, False, mode="fp32").cuda()
+    net32.load_state_dict(net16.state_dict())
+    cond = {}
+    for i, c in enumerate(net16.cond_layers):
+        cond[f"cond.{i}.weight"] = c.weight.detach().clone()
+        cond[f"cond.{i}.bias"] = c.bias.detach().clone()
+    W = 8192
+    idx = torch.randint(0, 256, (1, net16.receptive_field + W - 1)).cuda()
+    with torch.no_grad():
+        a = net16.forward_logits(indices=idx, cond_weights=cond)
+        b = net32.forward_logits(indices=idx, cond_weights=cond)
+    e = max_rel(a.cpu().numpy(), b.cpu().numpy())
+    print("AE shipped shape bf16 decoder vs fp32 mode: logits max-rel", e)
+    assert e < 1e-2
