@@ -734,6 +734,16 @@ __device__ __forceinline__ void ldg_stream32(const void* ptr, uint64_t policy, u
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(ptr));
 }
 
+// 32 bytes per thread in one request (256-bit STG): a full sector per lane; `policy` = L2 eviction hint or 0
+__device__ __forceinline__ void stg32(void* ptr, uint64_t policy, const uint32_t* v) {
+  if (policy)
+    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "l"(policy) : "memory");
+  else
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
 template <bool BIAS, bool DENSE, bool COND>
 __global__ void __launch_bounds__(576, 1)
 block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
@@ -1042,7 +1052,7 @@ struct Bwd5Smem {
 // 216 KB of shared memory two {x, A'/Q'} stages are all that fits, each {A', Q'} stage doubles as the output staging area and
 // is refilled only after its TMA store has been read, so per parity the loop  load (2-4 k cycles) -> dz -> epilogue 1 (3.2 k)
 // -> P (1.5 k) -> epilogue 2 (2.1 k) -> store (1.4 k)  is serial: ~12 k cycles per two tiles.
-template <bool DENSE>
+template <bool DENSE, bool DIRECT>
 __global__ void __launch_bounds__(608, 1)
 block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
                   const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_a_in,
@@ -1061,7 +1071,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_init(&x_full[i], 1);
       mbar_init(&x_empty[i], 1);
       mbar_init(&dxi_full[i], 1);
-      mbar_init(&dxi_empty[i], 1);
+      mbar_init(&dxi_empty[i], DIRECT ? 9 : 1);      // DIRECT: the group's 8 warps (after their reads) + the dW_dense commit
       mbar_init(&fg_full[i], 1);
       mbar_init(&fg_empty[i], 1);
       mbar_init(&p_full[i], 1);
@@ -1154,25 +1164,44 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (jw < jf && mbar_test_wait(&out_full, jw & 1)) {
           tc_fence_after();
           const uint32_t sxa = sbase + Bwd5Smem::XR + (jw & 1) * Bwd5Smem::X_STAGE;
+          auto job_p = [&]() {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)     // P[t, (tap, r)] = sum_o dFG[t, o] * W_tap[o, r]   (first: epilogue 2 waits for it)
-            umma_bf16(tmem + (jw & 1) * 128, desc_kmajor(sbase + (k < 4 ? Bwd5Smem::DF : Bwd5Smem::DG), k & 3),
-                      desc_mnmajor(sbase + Bwd5Smem::W0, k, TILE), id_p, k > 0);
-          umma_commit(&p_full[jw & 1]);
-          if (DENSE) {      // dW_dense[r, d] += sum_t (A'[t, r] + Q'[t, r]) * z[t, d]   (rows 64..127 unused)
-            const uint32_t sd = sbase + Bwd5Smem::DXR + (jw & 1) * Bwd5Smem::DX_STAGE;
+            for (int k = 0; k < 8; ++k)     // P[t, (tap, r)] = sum_o dFG[t, o] * W_tap[o, r]
+              umma_bf16(tmem + (jw & 1) * 128, desc_kmajor(sbase + (k < 4 ? Bwd5Smem::DF : Bwd5Smem::DG), k & 3),
+                        desc_mnmajor(sbase + Bwd5Smem::W0, k, TILE), id_p, k > 0);
+            umma_commit(&p_full[jw & 1]);
+          };
+          auto job_wd = [&]() {
+            if (DENSE) {      // dW_dense[r, d] += sum_t (A'[t, r] + Q'[t, r]) * z[t, d]   (rows 64..127 unused)
+              const uint32_t sd = sbase + Bwd5Smem::DXR + (jw & 1) * Bwd5Smem::DX_STAGE;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              umma_bf16(tmem + C_WD, desc_mnmajor(sd, k, 0), desc_mnmajor(sbase + Bwd5Smem::Z, k, TILE), id_wd, (jw | k) != 0);
+              for (int k = 0; k < 8; ++k)
+                umma_bf16(tmem + C_WD, desc_mnmajor(sd, k, 0), desc_mnmajor(sbase + Bwd5Smem::Z, k, TILE), id_wd, (jw | k) != 0);
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              umma_bf16(tmem + C_WD, desc_mnmajor(sd + TILE, k, 0), desc_mnmajor(sbase + Bwd5Smem::Z, k, TILE), id_wd, true);
+              for (int k = 0; k < 8; ++k)
+                umma_bf16(tmem + C_WD, desc_mnmajor(sd + TILE, k, 0), desc_mnmajor(sbase + Bwd5Smem::Z, k, TILE), id_wd, true);
+            }
+            if (DIRECT) {
+              if (DENSE) umma_commit(&dxi_empty[jw & 1]);     // dW_dense has read A' and Q' (the stage's other 8 arrivals: the group's warps)
+            } else {
+              umma_commit(&wd_done[jw & 1]);     // dW_dense has read A' and Q': epilogue 2 may overwrite them in place
+            }
+          };
+          auto job_wfg = [&]() {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
+              umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd5Smem::DF, k, TILE), desc_mnmajor(sxa, k, TILE), id_wfg, (jw | k) != 0);
+            umma_commit(&x_empty[jw & 1]);
+          };
+          if (pp.w_order == 1) {      // stages first: the {x} and {A', Q'} stages are what the tile loop waits for
+            job_wfg();
+            job_wd();
+            job_p();
+          } else {                    // P first: epilogue 2 starts earliest
+            job_p();
+            job_wd();
+            job_wfg();
           }
-          umma_commit(&wd_done[jw & 1]);     // dW_dense has read A' and Q': epilogue 2 may overwrite them in place
-#pragma unroll
-          for (int k = 0; k < 8; ++k)     // dW_fg[o, (tap, r)] += sum_t dFG[t, o] * x[t - (1 - tap) d, r]
-            umma_bf16(tmem + C_WFG, desc_mnmajor(sbase + Bwd5Smem::DF, k, TILE), desc_mnmajor(sxa, k, TILE), id_wfg, (jw | k) != 0);
-          umma_commit(&x_empty[jw & 1]);
           umma_commit(&out_empty[jw & 1]);
           WN_TS_MARK(jw, 3);
           ++jw;
@@ -1195,7 +1224,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     }
   } else if (warp == 18) {
     // ------------------------------------------------------------ store thread: tiles in order, alternating between the groups
-    if (lane == 0 && n_mine > 0) {
+    if (!DIRECT && lane == 0 && n_mine > 0) {
       int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
       for (int it = 0; it < n_mine; ++it) {
         const int tau0 = (p.tile0 + tl) * 128;
@@ -1326,6 +1355,63 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         mbar_arrive(&out_full);
         WN_TS_MARK(it, 10);
       }
+      if (DIRECT) {
+        // ---------------- epilogue 2, direct: the residual pass-through A' + Q' is read (fp32 sums held in registers) BEFORE the
+        // wait for P, so the {A', Q'} stage goes back to the producer as soon as dW_dense has read it too - the refill of the
+        // stage no longer waits for P, epilogue 2 and a TMA store out of the same shared memory; A_i / Q_i go from registers
+        // to global memory, one full 32-byte sector per thread and request (each thread owns 64 contiguous bytes of a row)
+        float sum[32];
+        if (DENSE) {
+          mbar_wait(&dxi_full[g], ph2);                            // (TMA data of this stage observed by this thread as well)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t o = sw128_chunk(row, h * 4 + q);
+            const uint4 a4 = *reinterpret_cast<const uint4*>(sa + o), q4v = *reinterpret_cast<const uint4*>(sa + TILE + o);
+            const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, qw[4] = {q4v.x, q4v.y, q4v.z, q4v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
+              const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&qw[j]);
+              sum[q * 8 + 2 * j] = __low2float(a2) + __low2float(q2);
+              sum[q * 8 + 2 * j + 1] = __high2float(a2) + __high2float(q2);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dxi_empty[g]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+        }
+        mbar_wait(&p_full[g], ph2);
+        tc_fence_after();
+        if (leader) WN_TS_MARK(it, 11);
+        const bool in_range = tau < p.L;
+        __nv_bfloat16* arow = pp.a_out_p + ((int64_t)b * p.L + tau) * 64 + h * 32;
+        __nv_bfloat16* qrow = pp.q_out_p + ((int64_t)b * p.L + tau) * 64 + h * 32;
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const int c0 = h * 32 + ps * 16;
+          uint32_t p0[16], p1[16], pa[8], pq[8];
+          tmem_ld16(lane_addr + g * 128 + c0, p0);
+          tmem_ld16(lane_addr + g * 128 + 64 + c0, p1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            pa[j] = valid ? pack_bf16(sum[ps * 16 + 2 * j] + __uint_as_float(p1[2 * j]), sum[ps * 16 + 2 * j + 1] + __uint_as_float(p1[2 * j + 1])) : 0u;
+            pq[j] = valid ? pack_bf16(__uint_as_float(p0[2 * j]), __uint_as_float(p0[2 * j + 1])) : 0u;
+          }
+          if (in_range) {
+            stg32(arow + ps * 16, p.pol_last, pa);
+            stg32(qrow + ps * 16, p.pol_last, pq);
+          }
+        }
+        tc_fence_before();
+        group_bar();                           // every thread of the group has drained P
+        if (leader) {
+          mbar_arrive(&fg_empty[g]);
+          WN_TS_MARK(it, 12);
+        }
+      } else {
       // ---------------- epilogue 2: A_i = (A' + Q') + P1, Q_i = P0, in place over A' / Q'
       mbar_wait(&p_full[g], ph2);            // P complete; dW_dense has read A' and Q'
       if (DENSE) mbar_wait(&dxi_full[g], ph2);                  // (TMA data of this stage observed by this thread as well)
@@ -1371,6 +1457,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         mbar_arrive(&fg_empty[g]);
         mbar_arrive(&st_req[g]);
         WN_TS_MARK(it, 12);
+      }
       }
       tl += 2 * (int)gridDim.x;
       while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
@@ -1635,7 +1722,8 @@ int launch_colsum_bf16_split(const void* src, int B, int64_t rows_per_batch, int
 
 // environment switches of the backward (timing experiments; read once)
 struct BwdEnv {
-  bool nt_stream, bwd6, wgrad_side, l2hint_dx, scatter_simt;
+  bool nt_stream, bwd6, bwd6_tma, wgrad_side, l2hint_dx, scatter_simt;
+  int bwd6_worder;
 };
 static const BwdEnv& bwd_env() {
   static const BwdEnv e = [] {
@@ -1644,6 +1732,8 @@ static const BwdEnv& bwd_env() {
     BwdEnv r{};
     r.nt_stream = on("WN_NT_STREAM");
     r.bwd6 = !off("WN_BWD6");             // block_bwd6 (default): the dx GEMM fused into the block backward; WN_BWD6=0: block_bwd3 + dx GEMM
+    r.bwd6_tma = on("WN_BWD6_TMA");       // A_i / Q_i staged in shared memory and written by TMA (the first version of block_bwd6)
+    r.bwd6_worder = off("WN_BWD6_WORDER") ? 0 : 1;      // 1 (default): dW_fg, dW_dense, P - the stage releases first (2.33 vs 2.39 ms per step)
     r.wgrad_side = !off("WN_WGRAD_SIDE");
     r.l2hint_dx = on("WN_L2HINT_DX");
     r.scatter_simt = on("WN_SCATTER_SIMT");
@@ -1735,7 +1825,9 @@ int launch_block_bwd6(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
   const int n_ctas = std::min(n_items, g_sm_count);
   const int smem = Bwd5Smem::TOTAL + 1024;
   WN_REQUIRE(p.b.bias_fg == nullptr, WN_ERR_INVALID, "block_bwd6 serves models without bias");
-  auto k = p.b.has_dense ? block_bwd6_kernel<true> : block_bwd6_kernel<false>;
+  const bool direct = !bwd_env().bwd6_tma;
+  auto k = p.b.has_dense ? (direct ? block_bwd6_kernel<true, true> : block_bwd6_kernel<true, false>)
+                         : (direct ? block_bwd6_kernel<false, true> : block_bwd6_kernel<false, false>);
   WN_PROPAGATE(set_smem_once(k, smem));
   WN_PROF("block_bwd6", s);
   WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)n_ctas), dim3(608), smem, s, m.x, m.w0, m.w1, m.a_in, m.q_in, m.wdT, m.a_out, m.q_out, p));
@@ -2012,6 +2104,9 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       if (l2_hints_on()) { bp.pol_first = kL2EvictFirst; bp.pol_last = kL2EvictLast; }
       b2.n_batches = B;
       b2.partial = reinterpret_cast<float*>(Wp + wl.WGP) + (int64_t)i * WGP_LAYER_FLOATS;
+      b2.w_order = env.bwd6_worder;
+      b2.a_out_p = reinterpret_cast<__nv_bfloat16*>(Wp + ((i & 1) ? wl.DXb : wl.DXa));
+      b2.q_out_p = reinterpret_cast<__nv_bfloat16*>(Wp + wl.DFG + ((i & 1) ? align_up((size_t)B * L * 64 * 2, 1024) : 0));
       WN_PROPAGATE(launch_block_bwd6(bm, b2, s));
       WN_DEBUG_SYNC("block_bwd6", s);
       if (side) {

@@ -113,6 +113,9 @@ struct BlockBwd2Params {
   float* g_gate;      // dW gate
   float* g_dense;     // dW dense (R,D,1) or null
   float* partial;     // [n_ctas][128][192] fp32 per-CTA weight-gradient tiles (reduced by wgrad_reduce_kernel)
+  __nv_bfloat16* a_out_p;     // block_bwd6 (direct stores): A_i and Q_i (B, L, 64), the arrays behind BlockBwdMaps::a_out / q_out
+  __nv_bfloat16* q_out_p;
+  int w_order;                // block_bwd6: 0 = P, dW_dense, dW_fg; 1 = dW_fg, dW_dense, P (stage releases first)
 };
 int launch_block_bwd2(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStream_t s);
 

@@ -107,7 +107,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b, p.pol_first);
         tma_load_3d(si + TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);
         if (TRACE && p.ts && blockIdx.x == 0) p.ts[1024 + it * 4 + 2] = clock64();
-        if (dense) {      // low half of the residual stream; its tile is reused for lo' and released after that store
+        if (dense && !(TRACE && (p.dbg & 4))) {      // low half of the residual stream; its tile is reused for lo' and released after that store
           mbar_wait(&lo_empty[it & 1], ((it >> 1) & 1) ^ 1);
           mbar_expect_tx(&lo_full[it & 1], TILE_BYTES);
           tma_load_3d(sm + Fwd2Smem::LO + (it & 1) * TILE_BYTES, &tm_lo, &lo_full[it & 1], 0, tau0, b, p.pol_first);
@@ -216,7 +216,7 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (tid == 0 && dense) mbar_arrive(&z_ready);
       // ---- epilogue 2: x_{i+1} = dense + (hi + lo) in fp32, split again into hi + lo
       if (dense) {
-        mbar_wait(&lo_full[ab], ph2);
+        if (!(TRACE && (p.dbg & 4))) mbar_wait(&lo_full[ab], ph2);
         mbar_wait(&dense_full[ab], ph2);
         tc_fence_after();
         if (rec) ts[4] = clock64();
