@@ -380,38 +380,26 @@ def bench_cfg1(dev, cpu_seconds=6.0):
             "cpu": {"samples_per_s": W / dt, "s_per_step": dt, "cores": os.cpu_count(), "kind": "port", "steps": k}}
 
 
-def bench_autoencoder(dev, steps=3, world=1, rank=0):
+def bench_autoencoder(dev, steps=10, world=1, rank=0):
     """BASELINE.json configs[4] shape: wavenet_autoencoder with the shipped parameters (40 layers, 32 channels, 512
     bottleneck / skip, pool 512), one clip of W = 64000 targets (L = 68093) per GPU, Adam; with N > 1 ranks the gradients are
     averaged with one all-reduce per step (weak scaling) and the rate is the aggregate over all GPUs, timed as the max over
-    ranks.  The autoencoder runs in the fp32 check mode (SIMT kernels, csrc/ae.cu): a correctness-path timing, not a
-    tensor-core number."""
+    ranks.  mode "auto" = bf16: conditioned decoder on the tcgen05 WaveNet kernels, encoder / conditioning convs on the
+    mma.sync kernels of csrc/ae_fast.cu; the step is the fused AeTrainer.step (music_b200/wavenet_autoencoder/train.py)."""
     import torch
     from music_b200.wavenet_autoencoder.model1 import wavenet_autoencoder
     from music_b200.wavenet_autoencoder import train as T
     dil = [2 ** i for i in range(10)] * 4
     torch.manual_seed(0)
-    net = wavenet_autoencoder(2, 256, dil, 32, 32, 512, 512, 32, 32, 512, False).to(dev)
+    net = wavenet_autoencoder(2, 256, dil, 32, 32, 512, 512, 32, 32, 512, False, mode="auto").to(dev)
     W = 64000
     L = net.receptive_field + W - 1
     g = torch.Generator().manual_seed(1234 + rank)
     idx = torch.randint(0, 256, (1, L), generator=g).to(dev)
     target = idx[:, net.receptive_field - 1:].contiguous()
-    opt = T.get_optimizer(net, 'Adam', 1e-4)
-
-    def step():
-        opt.zero_grad()
-        logits = net.forward_logits(indices=idx)
-        from music_b200._engine import SoftmaxRowsFunction
-        from music_b200 import _lib as L_
-        probs = SoftmaxRowsFunction.apply(logits, L_.ROWS_REFERENCE)
-        loss = torch.nn.functional.cross_entropy(probs, target.reshape(-1))
-        loss.backward()
-        if world > 1:
-            T.all_reduce_grads_(net.parameters())
-        opt.step()
-        return loss
-    step()
+    tr = T.AeTrainer(net, 'Adam', 1e-4, distributed=world > 1)
+    for _ in range(3):
+        tr.step(idx, target)
     torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
@@ -419,7 +407,7 @@ def bench_autoencoder(dev, steps=3, world=1, rank=0):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        loss = step()
+        loss = tr.step(idx, target)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -428,8 +416,9 @@ def bench_autoencoder(dev, steps=3, world=1, rank=0):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     return {"workload": "wavenet_autoencoder 40 layers (1..512 x4), 32 ch, bottleneck/skip 512, pool 512; 1 clip x 64000 targets "
-                        f"(L=68093) per GPU on {world} GPU(s), index input, Adam (torch.optim), fp32 check mode",
-            "samples_per_s": world * W / (ms * 1e-3), "ms_per_step": ms, "dtype": "f32", "loss": float(loss), "n_gpus": world,
+                        f"(L=68093) per GPU on {world} GPU(s), index input, fused Adam step (AeTrainer), mode {net.mode}",
+            "samples_per_s": world * W / (ms * 1e-3), "ms_per_step": ms, "dtype": "bf16" if net.mode == "bf16" else "f32",
+            "loss": float(loss), "n_gpus": world, "steps": steps,
             "train_flops_per_sample": 8.656e6, "tflops": world * W * 8.656e6 / (ms * 1e-3) / 1e12}
 
 
@@ -476,7 +465,7 @@ def main():
     ap.add_argument("--no-cfg1", action="store_true", help="skip the configs[0] (32/32/256, one clip) leg")
     ap.add_argument("--no-dense-e2e", action="store_true", help="skip the end-to-end variant fed with the reference loader's dense (B,256,L) batch")
     ap.add_argument("--gen-streams", type=int, default=64)
-    ap.add_argument("--no-ae", action="store_true", help="skip the autoencoder (configs[4] shape, fp32 check mode) leg")
+    ap.add_argument("--no-ae", action="store_true", help="skip the autoencoder (configs[4] shape) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -12,6 +12,7 @@
 //
 // Activations are (B, L, C) fp32 in absolute time coordinates like the WaveNet check mode; everything is composed from
 // the generic tap-GEMM of check_kernels.cu plus three element-wise kernels below.
+#include "ae_fast.cuh"
 #include "check_kernels.cuh"
 #include "common.cuh"
 #include "fast.cuh"
@@ -29,6 +30,7 @@ struct wn_ae {
   // whose parameter offsets point INTO the autoencoder's flat vector (filter = second half of filter_gate, gate = first half,
   // post_process_1/2 = connection_1/2), so packing reads and the backward writes the autoencoder's own parameters / gradients.
   int mode = 0;
+  bool enc_fast = false;      // mode 1 and 32-channel encoder stacks: the kernels of ae_fast.cu (else the fp32 SIMT encoder)
   wn::Model dec;
   ~wn_ae() { wn::fast_release(dec); }
 };
@@ -195,8 +197,9 @@ AeWs ae_ws(const wn_ae& a, int B, int L, bool need_onehot, void* base, bool trai
 // tables in the kernels' layout and their gradients (frame sums) in the autoencoder's raw layout
 struct AeFast {
   size_t packed, ws, ctab_fg, ctab_head, cgrad_fg, cgrad_head, total;
+  size_t xbar, vbar, gx_all, dt_all;      // fast encoder: pooled x_N, its gradient, per-layer gX (N + 1 slots) and dT (N slots)
 };
-AeFast ae_fast_layout(wn_ae& a, int B, int L, size_t base) {
+AeFast ae_fast_layout(wn_ae& a, int B, int L, size_t base, bool train = true) {
   AeFast f{};
   const int W = L - a.rf + 1, frames = std::max(1, W / a.pool);
   size_t off = align_up(base, 1024);
@@ -214,6 +217,14 @@ AeFast ae_fast_layout(wn_ae& a, int B, int L, size_t base) {
   f.ctab_head = take((size_t)B * frames * a.Sd * 4);
   f.cgrad_fg = take((size_t)B * frames * a.N * 2 * a.Dd * 4);
   f.cgrad_head = take((size_t)B * frames * a.Sd * 4);
+  if (a.enc_fast) {
+    f.xbar = take((size_t)B * frames * a.Re * 4);
+    f.vbar = take((size_t)B * frames * a.Re * 4);
+    if (train) {
+      f.gx_all = take((size_t)B * L * a.Re * 4 * (a.N + 1));
+      f.dt_all = take((size_t)B * L * a.De * 4 * a.N);
+    }
+  }
   f.total = off;
   return f;
 }
@@ -308,6 +319,9 @@ extern "C" int wn_ae_create(const wn_ae_config* cfg, wn_ae** out) {
       delete a;
       return WN_ERR_UNSUPPORTED;
     }
+    a->enc_fast = a->Re == kEncC && a->De == kEncC && a->BW % 64 == 0 && a->N <= 64 && 2 * a->Dd <= 128 &&
+                  2 * a->N + a->Sd / 64 <= kCondBlocksMax;
+    if (getenv("WN_AE_ENC_SIMT")) a->enc_fast = false;      // timing experiments: the fp32 SIMT encoder under the bf16 decoder
   }
   *out = a;
   return WN_OK;
@@ -321,7 +335,7 @@ extern "C" int wn_ae_workspace_bytes(const wn_ae* a, int32_t B, int32_t L, size_
   WN_REQUIRE(a && bytes && B > 0, WN_ERR_INVALID, "wn_ae_workspace_bytes: bad argument");
   WN_REQUIRE(L - a->rf + 1 > 0, WN_ERR_SHAPE, "wave sample not long enough");
   *bytes = ae_ws(*a, B, L, true, nullptr).bytes;
-  if (a->mode == 1) *bytes = ae_fast_layout(*const_cast<wn_ae*>(a), B, L, *bytes).total;
+  if (a->mode == 1) *bytes = ae_fast_layout(*const_cast<wn_ae*>(a), B, L, *bytes, false).total;
   return WN_OK;
 }
 
@@ -343,22 +357,44 @@ static int ae_forward_impl(wn_ae* a, int32_t B, int32_t L, const float* d_x, con
   auto dec_x = [&](int i) { return train ? w.DX + w.dx_stride * i : ((i & 1) ? w.S1 : w.S0); };
   auto dec_y = [&](int i) { return train ? w.DY + w.dy_stride * i : w.Y; };
   TensorView Xin;
+  const bool enc_fast = a->mode == 1 && a->enc_fast;
   if (d_x) {
     Xin = tv(d_x, (int64_t)Q * L, 1, L);                                  // (B,Q,L) as the reference takes it
-  } else {
+  } else if (!enc_fast) {
     onehot_rows_kernel<<<ew_blocks((int64_t)B * L * Q), 256, 0, s>>>(d_idx, w.Xin, (int64_t)B * L, Q);
     WN_CHECK_LAUNCH();
     Xin = tv(w.Xin, (int64_t)L * Q, Q, 1);
   }
   auto view = [&](const float* p, int C) { return tv(p, (int64_t)L * C, C, 1); };
+  float* cur = nullptr;
+  float* nxt = nullptr;
+  int s_in = 1;
+  if (enc_fast) {
+    // ---------------------------------------------------------------- encoder on the tensor cores (ae_fast.cu; model1.py:137-156)
+    const AeFast fl = ae_fast_layout(*a, B, L, w.bytes, train);
+    uint8_t* base = reinterpret_cast<uint8_t*>(d_workspace);
+    if (d_idx) {      // causal conv of a one-hot input = two table rows per time step
+      WN_PROPAGATE(launch_pack_f32(d_params + a->en_causal.w, w.WT, w.WT + conv_elems(a->en_causal), a->en_causal.out, a->en_causal.in, 2, s));
+      WN_PROPAGATE(launch_causal_idx_fwd(d_idx, w.WT, nullptr, enc_x(0), B, L, a->Re, Q, s));
+    } else {
+      PwArgs p; p.X = Xin; p.x_lo = 0; p.x_hi = L; p.Y = view(enc_x(0), a->Re); p.B = B; p.t0 = 1; p.t1 = L;
+      WN_PROPAGATE(apply_conv(d_params, a->en_causal, w.WT, p, 1, s));
+    }
+    for (int i = 0; i < N; ++i)
+      WN_PROPAGATE(launch_enc_fwd_layer(enc_x(i), enc_t(i), enc_x(i + 1), d_params + a->en_dil[i].w, d_params + a->en_dense[i].w, B, L,
+                                        a->dil[i], a->start[i], s));
+    // AvgPool1d and the 1x1 bottleneck are both linear: pool the 32 channels first, then one 32 -> BW product per frame
+    WN_PROPAGATE(launch_enc_pool_bottleneck(enc_x(N), d_params + a->bottleneck.w, nullptr, reinterpret_cast<float*>(base + fl.xbar), w.ENC, B, L,
+                                            tw, a->pool, frames, a->BW, s));
+    if (d_encoding)
+      WN_CHECK_CUDA(cudaMemcpyAsync(d_encoding, w.ENC, (size_t)B * frames * a->BW * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
   // ------------------------------------------------------------------ encoder (model1.py:137-156)
   {
     PwArgs p; p.X = Xin; p.x_lo = 0; p.x_hi = L; p.Y = view(enc_x(0), a->Re); p.B = B; p.t0 = 1; p.t1 = L;
     WN_PROPAGATE(apply_conv(d_params, a->en_causal, w.WT, p, 1, s));
   }
-  float* cur = enc_x(0);
-  float* nxt = nullptr;
-  int s_in = 1;
+  cur = enc_x(0);
   for (int i = 0; i < N; ++i) {
     const int d = a->dil[i], s_out = s_in + d;
     nxt = enc_x(i + 1);
@@ -381,16 +417,34 @@ static int ae_forward_impl(wn_ae* a, int32_t B, int32_t L, const float* d_x, con
     if (d_encoding)        // channels-last copy (B, frames, BW); `_encode` returns its transpose (B, BW, frames)
       WN_CHECK_CUDA(cudaMemcpyAsync(d_encoding, w.ENC, (size_t)B * frames * a->BW * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
+  }
   // ------------------------------------------------------------------ decoder (model1.py:158-225)
   if (a->mode == 1) {
     // bf16 tensor-core decoder: the N + 1 conditioning convs are applied to the (B, frames, BW) encoding in fp32 (tiny), their
     // outputs become per-frame tables that the WaveNet block kernels add to the [f|g] pre-activations (and the head GEMM to
     // connection_1's output); everything else is the conditioned WaveNet forward of fast_host.cu on the shared parameters.
     uint8_t* base = reinterpret_cast<uint8_t*>(d_workspace);
-    const AeFast fl = ae_fast_layout(*a, B, L, w.bytes);
+    const AeFast fl = ae_fast_layout(*a, B, L, w.bytes, train);
     float* ctab_fg = reinterpret_cast<float*>(base + fl.ctab_fg);
     float* ctab_head = reinterpret_cast<float*>(base + fl.ctab_head);
     TensorView ENCf = tv(w.ENC, (int64_t)frames * a->BW, a->BW, 1);
+    if (a->enc_fast) {
+      // all N + 1 conditioning convs as ONE grouped GEMM that writes the kernels' table layout directly: per layer the gate rows
+      // [0, Dd) of the conv go to table columns [64, 64 + Dd), the filter rows [Dd, 2 Dd) to [0, Dd) (padding columns stay zero)
+      CondBlocks cb{};
+      for (int i = 0; i < N; ++i)
+        for (int half = 0; half < 2; ++half) {      // 0: gate, 1: filter
+          CondBlock& k = cb.blk[cb.n++];
+          k.w_off = a->cond[i].w + (int64_t)half * a->Dd * a->BW; k.b_off = a->cond[i].b + half * a->Dd;
+          k.out = ctab_fg + (int64_t)i * 128 + (half == 0 ? 64 : 0); k.out_stride = N * 128; k.ncols = a->Dd;
+        }
+      for (int c0 = 0; c0 < a->Sd; c0 += 64) {
+        CondBlock& k = cb.blk[cb.n++];
+        k.w_off = a->cond[N].w + (int64_t)c0 * a->BW; k.b_off = a->cond[N].b + c0;
+        k.out = ctab_head + c0; k.out_stride = a->Sd; k.ncols = std::min(64, a->Sd - c0);
+      }
+      WN_PROPAGATE(launch_cond_tables(w.ENC, d_cond, cb, B * frames, a->BW, s));
+    } else {
     for (int i = 0; i < N; ++i) {
       PwArgs pc; pc.X = ENCf; pc.x_lo = 0; pc.x_hi = frames; pc.Y = tv(w.COND, (int64_t)frames * 2 * a->Dd, 2 * a->Dd, 1);
       pc.B = B; pc.t0 = 0; pc.t1 = frames;
@@ -401,6 +455,7 @@ static int ae_forward_impl(wn_ae* a, int32_t B, int32_t L, const float* d_x, con
       PwArgs pc; pc.X = ENCf; pc.x_lo = 0; pc.x_hi = frames; pc.Y = tv(ctab_head, (int64_t)frames * a->Sd, a->Sd, 1);
       pc.B = B; pc.t0 = 0; pc.t1 = frames;
       WN_PROPAGATE(apply_conv(d_cond, a->cond[N], w.WT, pc, 1, s));                       // (:216-217)
+    }
     }
     Model& d = a->dec;
     d.cond_fg = ctab_fg; d.cond_head = ctab_head; d.cond_frames = frames;
@@ -487,7 +542,7 @@ extern "C" int wn_ae_train_workspace_bytes(const wn_ae* a, int32_t B, int32_t L,
   WN_REQUIRE(a && bytes && B > 0, WN_ERR_INVALID, "wn_ae_train_workspace_bytes: bad argument");
   WN_REQUIRE(L - a->rf + 1 > 0, WN_ERR_SHAPE, "wave sample not long enough");
   *bytes = ae_ws(*a, B, L, true, nullptr, true).bytes;
-  if (a->mode == 1) *bytes = ae_fast_layout(*const_cast<wn_ae*>(a), B, L, *bytes).total;
+  if (a->mode == 1) *bytes = ae_fast_layout(*const_cast<wn_ae*>(a), B, L, *bytes, true).total;
   return WN_OK;
 }
 
@@ -570,17 +625,33 @@ extern "C" int wn_ae_backward(wn_ae* a, int32_t B, int32_t L, const float* d_x, 
     d.cond_frames = frames; d.cond_fg_grad = cg_fg; d.cond_head_grad = cg_head;
     WN_PROPAGATE(fast_backward(d, B, L, d_x, d_idx, base + fl.packed, base + fl.ws, const_cast<float*>(d_dlogits), G, s));
     // conditioning convs: their weights (optional) and the encoding, head first as in the fp32 path
-    auto cond_bwd_from = [&](int i, const float* gsrc, int64_t g_bstride, int64_t g_rstride, int C) -> int {
+    auto cond_bwd_from = [&](int i, const float* gsrc, int64_t g_bstride, int64_t g_rstride, int C, bool dgrad) -> int {
       TensorView gC = tv(gsrc, g_bstride, g_rstride, 1);
       if (Gc) WN_PROPAGATE(conv_wgrad(Gc, a->cond[i], ENCv, 0, frames, 0, gC, 0, frames, 1, B));
+      if (!dgrad) return WN_OK;
       PwArgs p; p.X = gC; p.x_lo = 0; p.x_hi = frames; p.Y = gENCv; p.accumulate = enc_started ? 1 : 0; p.B = B; p.t0 = 0; p.t1 = frames;
       enc_started = true;
       (void)C;
       return conv_dgrad(d_cond, a->cond[i], p, 1);
     };
-    WN_PROPAGATE(cond_bwd_from(N, cg_head, (int64_t)frames * Sd, Sd, Sd));
-    for (int i = N - 1; i >= 0; --i)
-      WN_PROPAGATE(cond_bwd_from(i, cg_fg + (int64_t)i * 2 * Dd, (int64_t)frames * N * 2 * Dd, (int64_t)N * 2 * Dd, 2 * Dd));
+    const bool grouped = a->enc_fast;      // d loss / d encoding of all N + 1 convs in one grouped GEMM (ae_fast.cu)
+    if (Gc || !grouped) {
+      WN_PROPAGATE(cond_bwd_from(N, cg_head, (int64_t)frames * Sd, Sd, Sd, !grouped));
+      for (int i = N - 1; i >= 0; --i)
+        WN_PROPAGATE(cond_bwd_from(i, cg_fg + (int64_t)i * 2 * Dd, (int64_t)frames * N * 2 * Dd, (int64_t)N * 2 * Dd, 2 * Dd, !grouped));
+    }
+    if (grouped) {
+      CondBlocks cb{};
+      for (int i = 0; i < N; ++i) {
+        CondBlock& k = cb.blk[cb.n++];
+        k.w_off = a->cond[i].w; k.cg = cg_fg + (int64_t)i * 2 * Dd; k.cg_stride = N * 2 * Dd; k.ncols = 2 * Dd;
+      }
+      {
+        CondBlock& k = cb.blk[cb.n++];
+        k.w_off = a->cond[N].w; k.cg = cg_head; k.cg_stride = Sd; k.ncols = Sd;
+      }
+      WN_PROPAGATE(launch_cond_bwd(d_cond, cb, w.gENC, B * frames, BW, s));
+    }
   } else {
   // ------------------------------------------------------------------ head (model1.py:210-221)
   TensorView dLg = tv(d_dlogits, (int64_t)Q * W, 1, W, -tw);
@@ -640,6 +711,36 @@ extern "C" int wn_ae_backward(wn_ae* a, int32_t B, int32_t L, const float* d_x, 
   }
   WN_PROPAGATE(conv_wgrad(G, a->de_causal, Xin, 0, L, 0, gXv, 1, L, 1, B));
   }      // mode 0
+  if (a->mode == 1 && a->enc_fast) {
+    // ---------------------------------------------------------------- encoder backward on the tensor cores (ae_fast.cu)
+    uint8_t* base = reinterpret_cast<uint8_t*>(d_workspace);
+    const AeFast fl = ae_fast_layout(*a, B, L, w.bytes, true);
+    float* gx_all = reinterpret_cast<float*>(base + fl.gx_all);
+    float* dt_all = reinterpret_cast<float*>(base + fl.dt_all);
+    const int64_t slot = (int64_t)B * L * Re;
+    WN_PROPAGATE(launch_enc_pool_bottleneck_bwd(w.gENC, reinterpret_cast<const float*>(base + fl.xbar), d_params + a->bottleneck.w,
+                                                gx_all + slot * N, reinterpret_cast<float*>(base + fl.vbar), G + a->bottleneck.w, nullptr, B,
+                                                L, tw, a->pool, frames, BW, s));
+    for (int i = N - 1; i >= 0; --i)
+      WN_PROPAGATE(launch_enc_bwd_layer(gx_all + slot * (i + 1), w.ET + w.et_stride * i, w.EX + w.ex_stride * i, gx_all + slot * i,
+                                        dt_all + slot * i, d_params + a->en_dil[i].w, d_params + a->en_dense[i].w, B, L, a->dil[i],
+                                        a->start[i], s));
+    EncWgradArgs wa{};
+    wa.x = w.EX; wa.T = w.ET; wa.dT = dt_all; wa.gx = gx_all;
+    wa.x_stride = w.ex_stride; wa.t_stride = w.et_stride; wa.dt_stride = slot; wa.gx_stride = slot;
+    wa.N = N; wa.B = B; wa.L = L;
+    for (int i = 0; i < N; ++i) {
+      wa.dil[i] = a->dil[i]; wa.s_out[i] = a->start[i];
+      wa.w_dil[i] = a->en_dil[i].w; wa.w_dense[i] = a->en_dense[i].w;
+    }
+    WN_PROPAGATE(launch_enc_wgrad(wa, G, s));
+    if (d_idx) {
+      WN_PROPAGATE(launch_causal_idx_bwd(d_idx, gx_all, G + a->en_causal.w, B, L, Re, Q, s));
+    } else {
+      WN_PROPAGATE(conv_wgrad(G, a->en_causal, Xin, 0, L, 0, view(gx_all, Re), 1, L, 1, B));
+    }
+    return WN_OK;
+  }
   // ------------------------------------------------------------------ encoder (model1.py:137-156)
   {
     dim3 grid((unsigned)ew_blocks((int64_t)W * BW), (unsigned)B);

@@ -222,6 +222,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int tw = min(max(row - p.lg_pad, 0), p.lg_W - 1);      // pad rows: any frame (their gradients are zero)
             condp = p.cond + ((int64_t)b * p.cond_frames + cond_frame(tw, p.lg_W, p.cond_frames)) * p.n_total + nt * NT + c * 32;
           }
+          float4 cv[8];      // (16-byte loads: n_total and the column offsets are multiples of 32 floats)
+          if (EPI == EPI_RELU_COND) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cv[q] = __ldg(reinterpret_cast<const float4*>(condp) + q);
+          }
           if ((EPI == EPI_MASK || EPI == EPI_ADD) && valid) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -248,8 +253,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 a1 += p.bias[nt * NT + c * 32 + 2 * j + 1];
               }
               if (EPI == EPI_RELU_COND) {
-                a0 += __ldg(condp + 2 * j);
-                a1 += __ldg(condp + 2 * j + 1);
+                const float4 c4 = cv[j >> 1];
+                a0 += (j & 1) ? c4.z : c4.x;
+                a1 += (j & 1) ? c4.w : c4.y;
               }
               a0 = fmaxf(a0, 0.f);
               a1 = fmaxf(a1, 0.f);
@@ -893,6 +899,14 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (COND)      // this row's conditioning vector (rows outside the valid range read frame 0: their results are masked)
         condp = p.cond + (((int64_t)b * p.cond_frames + (valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0)) * p.cond_layers +
                           p.cond_layer) * 128 + cg * 16;
+      float4 cf[4], cgt[4];      // this thread's 2 x 16 conditioning values: eight 16-byte loads in flight during the wait
+      if (COND) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          cf[q] = __ldg(reinterpret_cast<const float4*>(condp) + q);
+          cgt[q] = __ldg(reinterpret_cast<const float4*>(condp + 64) + q);
+        }
+      }
       mbar_wait(&fg_full[ph], ph2);
       tc_fence_after();
       uint32_t f[16], g[16];
@@ -913,8 +927,9 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             gv += p.bias_fg[64 + cg * 16 + 2 * j + e];
           }
           if (COND) {
-            fv += __ldg(condp + 2 * j + e);
-            gv += __ldg(condp + 64 + 2 * j + e);
+            const float4 a = cf[j >> 1], c = cgt[j >> 1];
+            fv += (j & 1) ? (e ? a.w : a.z) : (e ? a.y : a.x);
+            gv += (j & 1) ? (e ? c.w : c.z) : (e ? c.y : c.x);
           }
           const float t = tanh_fast(fv), sg = sigmoid_fast(gv);
           zo[e] = t * sg;
@@ -1624,35 +1639,51 @@ __global__ void replicate_kernel(float* __restrict__ G, const int64_t* __restric
 }
 
 // out[b][frame][col_map(c)] += sum over the rows tl of a (B, rows, pitch) bf16 tensor that belong to `frame` (the transpose of the
-// conditioning broadcast, model1.py:227-247).  Rows t0 + tl, tl in [0, len); 128 columns starting at c0 per launch slab.  Each
-// CTA accumulates its chunk of rows in a shared [frames][128] tile (both frame rules: consecutive rows share a frame, or walk
-// through all frames) and flushes it with atomics.  dd > 0: columns are the kernels' padded [filter 64 | gate 64] order and go
-// to the autoencoder's raw (2 dd) order, gate first; dd == 0: identity.
-__global__ void __launch_bounds__(256) frame_sum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int64_t bstride, int pitch, int c0,
-                                                             int t0, int len, int frames, int rows_per_cta, float* __restrict__ out,
-                                                             int out_pitch, int dd) {
-  extern __shared__ float acc[];      // [frames][128]
-  const int b = blockIdx.y;
-  for (int e = threadIdx.x; e < frames * 128; e += 256) acc[e] = 0.f;
-  __syncthreads();
-  const int col = threadIdx.x & 127, rsub = threadIdx.x >> 7;
-  const int r0 = blockIdx.x * rows_per_cta, r1 = min(len, r0 + rows_per_cta);
-  for (int tl = r0 + rsub; tl < r1; tl += 2) {
-    const float v = __bfloat162float(src[(int64_t)b * bstride + (int64_t)(t0 + tl) * pitch + c0 + col]);
-    atomicAdd(&acc[cond_frame(tl, len, frames) * 128 + col], v);
+// conditioning broadcast, model1.py:227-247).  Rows t0 + tl, tl in [0, len); 128 columns starting at c0 per launch slab.
+// grid (frames, segments, B), 64 threads = 64 column pairs: a CTA walks ONE frame's rows - tl = f + j frames when the encoding is
+// tiled along time, tl = f (len / frames) + j when every frame is held for len / frames steps - so each thread keeps its two sums
+// in registers (no shared-memory atomics: the first version spent 47 us per layer in them), every row is one 256-byte request and
+// a segment ends in 2 atomics per thread.  dd > 0: columns are the kernels' padded [filter 64 | gate 64] order and go to the
+// autoencoder's raw (2 dd) order, gate first; dd == 0: identity.
+__global__ void __launch_bounds__(64) frame_sum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int64_t bstride, int pitch, int c0,
+                                                            int t0, int len, int frames, float* __restrict__ out, int out_pitch, int dd) {
+  const int f = blockIdx.x, seg = blockIdx.y, nseg = gridDim.y, b = blockIdx.z;
+  const bool held = len % frames == 0;
+  const int m = held ? len / frames : (len - f + frames - 1) / frames;      // rows of this frame
+  const int64_t first = held ? (int64_t)f * m : f, step = held ? 1 : frames;
+  const int per = (m + nseg - 1) / nseg, j0 = seg * per, j1 = min(m, j0 + per);
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(src + (int64_t)b * bstride + (int64_t)t0 * pitch + c0) + threadIdx.x;
+  const int64_t pitch2 = pitch / 2;
+  float a0 = 0.f, a1 = 0.f;
+  int j = j0;
+  for (; j + 4 <= j1; j += 4) {
+    uint32_t v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(base + (first + (int64_t)(j + u) * step) * pitch2);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+      a0 += __low2float(h);
+      a1 += __high2float(h);
+    }
   }
-  __syncthreads();
-  for (int e = threadIdx.x; e < frames * 128; e += 256) {
-    const float v = acc[e];
-    if (v == 0.f) continue;
-    const int f = e >> 7, c = e & 127;
+  for (; j < j1; ++j) {
+    const uint32_t v = __ldg(base + (first + (int64_t)j * step) * pitch2);
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&v);
+    a0 += __low2float(h);
+    a1 += __high2float(h);
+  }
+  if (j1 <= j0) return;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int c = 2 * threadIdx.x + e;
     int oc = c0 + c;
     if (dd > 0) {
       const int ch = c & 63;
       if (ch >= dd) continue;
       oc = c < 64 ? dd + ch : ch;      // filter -> second half, gate -> first half
     }
-    atomicAdd(out + ((int64_t)b * frames + f) * out_pitch + oc, v);
+    atomicAdd(out + ((int64_t)b * frames + f) * out_pitch + oc, e ? a1 : a0);
   }
 }
 
@@ -1838,18 +1869,16 @@ int launch_block_bwd6(const BlockBwdMaps& m, const BlockBwd2Params& p, cudaStrea
 int launch_frame_sum_bf16(const void* src, int64_t rows_per_batch, int pitch, int c0, int B, int t0, int len, int frames, float* out,
                           int out_pitch, int dd, cudaStream_t s) {
   if (len <= 0) return WN_OK;
-  const int smem = frames * 128 * 4;
-  WN_REQUIRE(smem <= 200 * 1024, WN_ERR_UNSUPPORTED, "conditioning with %d frames does not fit the frame-sum kernel", frames);
-  WN_PROPAGATE(set_smem_once(frame_sum_bf16_kernel, smem));
-  const int per_batch = std::max(1, (2 * g_sm_count) / std::max(B, 1));
-  const int rows_per_cta = (int)ceil_div(len, per_batch);
-  dim3 grid((unsigned)ceil_div(len, rows_per_cta), (unsigned)B);
+  WN_REQUIRE(pitch % 2 == 0 && c0 % 2 == 0, WN_ERR_INVALID, "frame sum: odd pitch / column offset");
+  const int rows_per_frame = (int)ceil_div(len, frames);
+  const int nseg = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows_per_frame, 32), ceil_div(16 * g_sm_count, (int64_t)frames * B)));
   WN_PROF("frame_sum", s);
-  frame_sum_bf16_kernel<<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows_per_batch * pitch, pitch, c0, t0, len, frames,
-                                                rows_per_cta, out, out_pitch, dd);
+  frame_sum_bf16_kernel<<<dim3((unsigned)frames, (unsigned)nseg, (unsigned)B), 64, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), rows_per_batch * pitch, pitch, c0, t0, len, frames, out, out_pitch, dd);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
+
 int launch_cond_table(const float* raw, const float* bias, int64_t n_rows, int dd, float* out, int64_t out_stride, cudaStream_t s) {
   cond_table_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_rows * 128, 256), 1184), 256, 0, s>>>(raw, bias, n_rows, dd, out, out_stride);
   WN_CHECK_LAUNCH();

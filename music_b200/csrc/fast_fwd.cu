@@ -171,6 +171,16 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (COND)      // this row's conditioning vector (autoencoder decoder; rows outside the valid range are masked anyway)
         condp = p.cond + (((int64_t)b * p.cond_frames + (valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0)) * p.cond_layers +
                           p.cond_layer) * 128 + cg * 16;
+      // the 2 x 16 conditioning values of this thread as eight 16-byte loads issued BEFORE the wait for the accumulator (the table
+      // rows are 512-byte aligned; scalar loads here - 64 requests of 32 different lines each - cost ~8 us per tile)
+      float4 cf[4], cgt[4];
+      if (COND) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          cf[q] = __ldg(reinterpret_cast<const float4*>(condp) + q);
+          cgt[q] = __ldg(reinterpret_cast<const float4*>(condp + 64) + q);
+        }
+      }
       mbar_wait(&fg_full[ab], ph2);
       tc_fence_after();
       if (rec) ts[1] = clock64();
@@ -190,10 +200,11 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           g1 += p.bias_fg[64 + cg * 16 + 2 * j + 1];
         }
         if (COND) {
-          f0 += __ldg(condp + 2 * j);
-          f1 += __ldg(condp + 2 * j + 1);
-          g0 += __ldg(condp + 64 + 2 * j);
-          g1 += __ldg(condp + 64 + 2 * j + 1);
+          const float4 a = cf[j >> 1], c = cgt[j >> 1];
+          f0 += (j & 1) ? a.z : a.x;
+          f1 += (j & 1) ? a.w : a.y;
+          g0 += (j & 1) ? c.z : c.x;
+          g1 += (j & 1) ? c.w : c.y;
         }
         float z0 = sigmoid_fast(g0) * tanh_fast(f0), z1 = sigmoid_fast(g1) * tanh_fast(f1);
         if (TRACE && (p.dbg & 8)) { z0 = g0 * f0; z1 = g1 * f1; }

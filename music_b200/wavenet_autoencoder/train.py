@@ -3,8 +3,9 @@
 Reference: get_optimizer :26-34, save_model :36-41, load_model :44-64, hot loop :117-134
 (zero_grad -> net(music_piece) -> CrossEntropyLoss(outputs, target.view(-1)) -> backward -> step).  The loss is
 applied to the module's softmax OUTPUT (a second softmax inside CrossEntropyLoss), exactly as in wavenet/train.py.
-Forward and backward of the module run in libwavenet_b200.so (csrc/ae.cu); the optimizers are torch.optim objects
-on the module's parameters, as in the reference.
+Forward and backward of the module run in libwavenet_b200.so (csrc/ae.cu, ae_fast.cu); `train_step` keeps the reference's
+shape (torch.optim objects on the module's parameters, autograd in between), `AeTrainer` is the fused step without an autograd
+graph: flat parameters, loss + dlogits in one kernel, fused optimizer, one all-reduce.
 """
 from __future__ import annotations
 
@@ -15,6 +16,9 @@ import torch
 import torch.nn as nn
 import torch.optim as optim
 
+from .. import _lib as L
+from .._engine import fused_loss, loss_scratch_bytes, _require_cuda
+from ..wavenet.train import all_reduce_mean_
 from .model1 import wavenet_autoencoder  # noqa: F401  (re-exported like the reference's `from model1 import ...`)
 
 
@@ -87,3 +91,133 @@ def train_step(net, optimizer, music_piece, target_piece, loss_func=None, cond_w
         all_reduce_grads_(net.parameters())
     optimizer.step()
     return loss.detach()
+
+
+class AeTrainer:
+    """Fused train step of the autoencoder: zero_grad -> net(piece) -> CrossEntropyLoss(probabilities, target) -> backward ->
+    [all-reduce] -> optimizer step (wavenet_autoencoder/train.py:117-134) as four C-ABI calls on flat vectors: wn_ae_forward_train,
+    wn_loss_fwd_bwd (flat-chunk softmax rows + double-softmax cross entropy + dlogits, as the reference's objective), wn_ae_backward
+    and wn_adam_step / wn_sgd_step / wn_rmsprop_step.  The module's parameters become views into one fp32 vector (state_dict and
+    checkpoints are unchanged); after step() every `p.grad` is a view into the flat gradient.
+
+    step(piece, target): `piece` is the dense (B,Q,L) float tensor the reference feeds or a (B,L) integer tensor of mu-law codes;
+    `target` any integer tensor with B*W entries.  Returns the loss as a 1-element device tensor (no host sync).
+    """
+
+    def __init__(self, net, optimizer_type: str = "Adam", learning_rate: float = 1e-4, momentum: float = 0.9, process_group=None,
+                 distributed=None):
+        kind = optimizer_type.lower()
+        if kind not in ("adam", "sgd", "rmsprop"):
+            raise ValueError(optimizer_type)
+        self.net, self.kind, self.lr, self.momentum = net, kind, learning_rate, momentum
+        self.step_count = 0
+        self.flat = self.gflat = None
+        self.state = {}
+        self._cond_key = self._cond = None
+        import torch.distributed as dist
+        self.dist = dist if (distributed if distributed is not None else (dist.is_available() and dist.is_initialized())) else None
+        self.group = process_group
+
+    def _ensure_flat(self):
+        params = list(self.net.parameters())
+        _require_cuda(params[0], "module parameters")
+        dev = params[0].device
+        ok = self.flat is not None and self.flat.device == dev
+        if ok:
+            off, base = 0, self.flat.data_ptr()
+            for p in params:
+                if p.data_ptr() != base + 4 * off or p.dtype != torch.float32 or not p.is_contiguous():
+                    ok = False
+                    break
+                off += p.numel()
+        if not ok:
+            total = sum(p.numel() for p in params)
+            flat = torch.empty(total, dtype=torch.float32, device=dev)
+            off = 0
+            with torch.no_grad():
+                for p in params:
+                    n = p.numel()
+                    flat[off:off + n].copy_(p.detach().reshape(-1).float())
+                    p.data = flat[off:off + n].view(p.shape)
+                    off += n
+            self.flat, self.gflat = flat, torch.zeros(total, dtype=torch.float32, device=dev)
+            self.state.clear()
+        return params
+
+    def _cond_vector(self, cond_weights, dev):
+        net = self.net
+        if cond_weights is not None or net.fresh_cond:
+            return net._cond_flat(cond_weights, dev).detach()
+        key = tuple((c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version) for c in net.cond_layers)
+        if key != self._cond_key or self._cond.device != dev:      # the N + 1 fixed conditioning convs: concatenated once
+            self._cond, self._cond_key = net._cond_flat(None, dev).detach(), key
+        return self._cond
+
+    def _buf(self, name):
+        t = self.state.get(name)
+        if t is None or t.device != self.flat.device or t.numel() != self.flat.numel():
+            t = torch.zeros_like(self.flat)
+            self.state[name] = t
+        return t
+
+    def forward_backward(self, piece, target, cond_weights=None):
+        import ctypes as C
+        net, lib = self.net, L.load()
+        self._ensure_flat()
+        _require_cuda(piece, "input")
+        dev = piece.device
+        L.init(dev.index if dev.index is not None else torch.cuda.current_device())
+        x = idx = None
+        if piece.dtype.is_floating_point:
+            x = piece.detach().float().contiguous()
+        else:
+            idx = piece.detach().to(torch.int64).contiguous()
+        src = x if x is not None else idx
+        B, Lx = src.shape[0], src.shape[-1]
+        W = Lx - net.receptive_field + 1
+        if W <= 0:
+            raise ValueError("wave sample not long enough")
+        h = net._plan()
+        cond = self._cond_vector(cond_weights, dev)
+        ws = net._workspace(B, Lx, dev, train=True)
+        logits = torch.empty(B, net.quantization_channel, W, dtype=torch.float32, device=dev)
+        s = L.stream_ptr()
+        L.check(lib.wn_ae_forward_train(h, B, Lx, L.ptr(x), L.ptr(idx), L.ptr(self.flat), L.ptr(cond), L.ptr(ws), L.ptr(logits), None, s))
+        net._ws_gen += 1
+        nb = loss_scratch_bytes(B, W)
+        sc = self.state.get("loss_scratch")
+        if sc is None or sc.numel() < nb or sc.device != dev:
+            sc = self.state["loss_scratch"] = torch.empty(nb, dtype=torch.uint8, device=dev)
+        loss, dlogits = fused_loss(logits, target, L.ROWS_REFERENCE, True, 1.0, sc)
+        L.check(lib.wn_ae_backward(h, B, Lx, L.ptr(x), L.ptr(idx), L.ptr(self.flat), L.ptr(cond), L.ptr(ws), L.ptr(dlogits),
+                                   L.ptr(self.gflat), None, s))
+        return loss
+
+    def all_reduce(self):
+        if self.dist is not None:
+            all_reduce_mean_(self.gflat, self.dist, self.group)
+
+    def apply(self):
+        lib = L.load()
+        self.step_count += 1
+        n, s = self.flat.numel(), L.stream_ptr()
+        if self.kind == "adam":
+            L.check(lib.wn_adam_step(L.ptr(self.flat), L.ptr(self.gflat), L.ptr(self._buf("m")), L.ptr(self._buf("v")), n,
+                                     self.lr, 0.9, 0.999, 1e-8, self.step_count, s))
+        elif self.kind == "sgd":
+            L.check(lib.wn_sgd_step(L.ptr(self.flat), L.ptr(self.gflat), L.ptr(self._buf("buf")), n, self.lr, self.momentum,
+                                    int(self.step_count == 1), s))
+        else:
+            L.check(lib.wn_rmsprop_step(L.ptr(self.flat), L.ptr(self.gflat), L.ptr(self._buf("sq")), L.ptr(self._buf("buf")), n,
+                                        self.lr, 0.99, 1e-8, self.momentum, s))
+
+    def step(self, piece, target, cond_weights=None):
+        loss = self.forward_backward(piece, target, cond_weights)
+        self.all_reduce()
+        self.apply()
+        off = 0
+        for p in self.net.parameters():
+            n = p.numel()
+            p.grad = self.gflat[off:off + n].view(p.shape)
+            off += n
+        return loss
