@@ -196,7 +196,7 @@ AeWs ae_ws(const wn_ae& a, int B, int L, bool need_onehot, void* base, bool trai
 // mode 1: what follows the fp32 workspace - packed bf16 weight image, bf16 activation workspace of the decoder, conditioning
 // tables in the kernels' layout and their gradients (frame sums) in the autoencoder's raw layout
 struct AeFast {
-  size_t packed, ws, ctab_fg, ctab_head, cgrad_fg, cgrad_head, total;
+  size_t packed, ws, ctab_fg, ctab_fg16, ctab_head, cgrad_fg, cgrad_head, total;
   size_t xbar, vbar, gx_all, dt_all;      // fast encoder: pooled x_N, its gradient, per-layer gX (N + 1 slots) and dT (N slots)
 };
 AeFast ae_fast_layout(wn_ae& a, int B, int L, size_t base, bool train = true) {
@@ -214,6 +214,7 @@ AeFast ae_fast_layout(wn_ae& a, int B, int L, size_t base, bool train = true) {
   f.packed = take(pb);
   f.ws = take(wb);
   f.ctab_fg = take((size_t)B * frames * a.N * 128 * 4);
+  f.ctab_fg16 = take((size_t)B * frames * a.N * 128 * 4);
   f.ctab_head = take((size_t)B * frames * a.Sd * 4);
   f.cgrad_fg = take((size_t)B * frames * a.N * 2 * a.Dd * 4);
   f.cgrad_head = take((size_t)B * frames * a.Sd * 4);
@@ -457,8 +458,9 @@ static int ae_forward_impl(wn_ae* a, int32_t B, int32_t L, const float* d_x, con
       WN_PROPAGATE(apply_conv(d_cond, a->cond[N], w.WT, pc, 1, s));                       // (:216-217)
     }
     }
+    WN_PROPAGATE(launch_cond_pack16(ctab_fg, base + fl.ctab_fg16, (int64_t)B * frames * N, s));
     Model& d = a->dec;
-    d.cond_fg = ctab_fg; d.cond_head = ctab_head; d.cond_frames = frames;
+    d.cond_fg = ctab_fg; d.cond_fg16 = base + fl.ctab_fg16; d.cond_head = ctab_head; d.cond_frames = frames;
     d.cond_fg_grad = nullptr; d.cond_head_grad = nullptr;
     WN_PROPAGATE(fast_pack(d, d_params, base + fl.packed, s));
     return fast_forward(d, B, L, d_x, d_idx, base + fl.packed, base + fl.ws, d_logits, s);
@@ -621,7 +623,8 @@ extern "C" int wn_ae_backward(wn_ae* a, int32_t B, int32_t L, const float* d_x, 
     WN_CHECK_CUDA(cudaMemsetAsync(cg_fg, 0, (size_t)B * frames * N * 2 * Dd * sizeof(float), s));
     WN_CHECK_CUDA(cudaMemsetAsync(cg_head, 0, (size_t)B * frames * Sd * sizeof(float), s));
     Model& d = a->dec;
-    d.cond_fg = reinterpret_cast<const float*>(base + fl.ctab_fg); d.cond_head = reinterpret_cast<const float*>(base + fl.ctab_head);
+    d.cond_fg = reinterpret_cast<const float*>(base + fl.ctab_fg); d.cond_fg16 = base + fl.ctab_fg16;
+    d.cond_head = reinterpret_cast<const float*>(base + fl.ctab_head);
     d.cond_frames = frames; d.cond_fg_grad = cg_fg; d.cond_head_grad = cg_head;
     WN_PROPAGATE(fast_backward(d, B, L, d_x, d_idx, base + fl.packed, base + fl.ws, const_cast<float*>(d_dlogits), G, s));
     // conditioning convs: their weights (optional) and the encoding, head first as in the fp32 path

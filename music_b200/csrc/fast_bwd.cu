@@ -895,16 +895,16 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       uint32_t zs[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
       if (tau0 >= p.tw_al && tau < p.L)      // tiled layout (GemmNtParams::out_tiled): this warp's 32 rows x 16 channels are 1 KB contiguous
         ldg_stream32(p.dzs + (((((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + ((tau0 - p.tw_al) >> 5) + q4) * 4 + cg) * 32 + lane) << 4), p.pol_first, zs);
-      const float* condp = nullptr;
-      if (COND)      // this row's conditioning vector (rows outside the valid range read frame 0: their results are masked)
-        condp = p.cond + (((int64_t)b * p.cond_frames + (valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0)) * p.cond_layers +
-                          p.cond_layer) * 128 + cg * 16;
-      float4 cf[4], cgt[4];      // this thread's 2 x 16 conditioning values: eight 16-byte loads in flight during the wait
+      uint32_t cw[32];      // this row's 16 filter + 16 gate conditioning values (fp32, one 128-byte line): four 256-bit loads in flight during the wait
       if (COND) {
+        const uint4* cp16 = p.cond16 + ((((int64_t)b * p.cond_frames + (valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0)) *
+                                         p.cond_layers + p.cond_layer) * 4 + cg) * 8;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          cf[q] = __ldg(reinterpret_cast<const float4*>(condp) + q);
-          cgt[q] = __ldg(reinterpret_cast<const float4*>(condp + 64) + q);
+          uint32_t t8[8];
+          ldg_stream32(cp16 + 2 * q, 0, t8);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) cw[8 * q + k] = t8[k];
         }
       }
       mbar_wait(&fg_full[ph], ph2);
@@ -927,9 +927,8 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             gv += p.bias_fg[64 + cg * 16 + 2 * j + e];
           }
           if (COND) {
-            const float4 a = cf[j >> 1], c = cgt[j >> 1];
-            fv += (j & 1) ? (e ? a.w : a.z) : (e ? a.y : a.x);
-            gv += (j & 1) ? (e ? c.w : c.z) : (e ? c.y : c.x);
+            fv += __uint_as_float(cw[2 * j + e]);
+            gv += __uint_as_float(cw[16 + 2 * j + e]);
           }
           const float t = tanh_fast(fv), sg = sigmoid_fast(gv);
           zo[e] = t * sg;
@@ -1702,6 +1701,14 @@ __global__ void cond_table_kernel(const float* __restrict__ raw, const float* __
     out[row * out_stride + c] = v;
   }
 }
+// table rows [128] = [filter 64 | gate 64]  ->  rows in the block kernels' per-thread order [column group 4][f16 | g16] (fp32)
+__global__ void cond_pack16_kernel(const float* __restrict__ tab, float* __restrict__ out, int64_t n_rows) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_rows * 128; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e >> 7;
+    const int o = (int)(e & 127), cg = o >> 5, w = o & 31;
+    out[e] = tab[row * 128 + (w < 16 ? cg * 16 + w : 64 + cg * 16 + (w - 16))];
+  }
+}
 // out[row][c] = raw[row][c] + bias[c]   (head conditioning + connection_1 bias)
 __global__ void add_bias_rows_kernel(const float* __restrict__ raw, const float* __restrict__ bias, int64_t n_rows, int C, float* __restrict__ out) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_rows * C; e += (int64_t)gridDim.x * blockDim.x)
@@ -1884,6 +1891,11 @@ int launch_cond_table(const float* raw, const float* bias, int64_t n_rows, int d
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
+int launch_cond_pack16(const float* tab, void* out, int64_t n_rows, cudaStream_t s) {
+  cond_pack16_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_rows * 128, 256), 1184), 256, 0, s>>>(tab, reinterpret_cast<float*>(out), n_rows);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
 int launch_add_bias_rows(const float* raw, const float* bias, int64_t n_rows, int C, float* out, cudaStream_t s) {
   add_bias_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_rows * C, 256), 1184), 256, 0, s>>>(raw, bias, n_rows, C, out);
   WN_CHECK_LAUNCH();
@@ -1963,6 +1975,7 @@ int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int
   WN_PROPAGATE(tmap_3d(&out->dxa, Wp + wl.DXa, 64, L, B, 64, (uint64_t)L * 64, 128));
   WN_PROPAGATE(tmap_3d(&out->dxb, Wp + wl.DXb, 64, L, B, 64, (uint64_t)L * 64, 128));
   WN_PROPAGATE(tmap_3d(&out->dfg, Wp + wl.DFG, 128, L, B, 128, (uint64_t)L * 128, 128));
+  WN_PROPAGATE(tmap_3d(&out->dfg2, Wp + wl.DFG2, 128, L, B, 128, (uint64_t)L * 128, 128));
   WN_PROPAGATE(tmap_3d(&out->zf, Wp + wl.Zf, 64, L, B, 64, (uint64_t)L * 64, 128));
   // block_bwd6: the Q halves of the split data gradient live in the two halves of the (then unused) dFG buffer
   const size_t half = align_up((size_t)B * L * 64 * 2, 1024);
@@ -1975,6 +1988,7 @@ int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t dfg_free[2] = {nullptr, nullptr};      // conditioned models: the frame sums over dF|dG buffer k have been taken
 };
 static int side_stream(SideStream** out) {
   static SideStream tab[64];
@@ -1986,6 +2000,8 @@ static int side_stream(SideStream** out) {
     WN_CHECK_CUDA(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking));
     WN_CHECK_CUDA(cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming));
     WN_CHECK_CUDA(cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming));
+    WN_CHECK_CUDA(cudaEventCreateWithFlags(&t.dfg_free[0], cudaEventDisableTiming));
+    WN_CHECK_CUDA(cudaEventCreateWithFlags(&t.dfg_free[1], cudaEventDisableTiming));
   }
   *out = &t;
   return WN_OK;
@@ -2010,6 +2026,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXa, 0, (size_t)B * L * 64 * 2, s));
     WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DXb, 0, (size_t)B * L * 64 * 2, s));
     WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DFG, 0, (size_t)B * L * 128 * 2, s));
+    if (m.cond_fg_grad) WN_CHECK_CUDA(cudaMemsetAsync(Wp + wl.DFG2, 0, (size_t)B * L * 128 * 2, s));
   }
   {
     dim3 grid((unsigned)ceil_div(Wpad, 32), (unsigned)B);
@@ -2115,6 +2132,9 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     const CUtensorMap& dx_cur = (i & 1) ? M.dxb : M.dxa;              // dx_i      (block_bwd6: A_i)
     const size_t dx_next_off = ((i + 1) & 1) ? wl.DXb : wl.DXa;
     const int tile0 = first_tile(i), tpb = tiles_total - tile0;
+    const bool fs_side = side != nullptr && m.cond_fg_grad != nullptr;
+    const int dfg_alt = fs_side ? (i & 1) : 0;
+    const size_t dfg_off = dfg_alt ? wl.DFG2 : wl.DFG;
     if (fuse_dx) {
       BlockBwdMaps bm{};
       bm.x = M.layer[i].x; bm.w0 = M.layer[i].w0; bm.w1 = M.layer[i].w1; bm.wdT = M.layer[i].wdT;
@@ -2152,7 +2172,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
     {
       BlockBwdMaps bm{};
       bm.x = M.layer[i].x; bm.w0 = M.layer[i].w0; bm.w1 = M.layer[i].w1; bm.dx = dx_next; bm.wdT = M.layer[i].wdT;
-      bm.dfg = M.dfg;
+      bm.dfg = dfg_alt ? M.dfg2 : M.dfg;
       BlockBwd2Params b2{};
       BlockBwdParams& bp = b2.b;
       bp.L = L; bp.d = d; bp.s_out = s_out; bp.tile0 = tile0; bp.tiles_per_batch = tpb; bp.has_dense = has_dense;
@@ -2161,20 +2181,27 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       bp.dzs_lb0 = i * B; bp.dzs_nblk = (int)ceil_div(Wpad, 32);
       bp.bias_fg = bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
       if (m.cond_fg) {      // conditioned decoder: recompute with the same table (the conv bias is part of it)
-        bp.cond = m.cond_fg; bp.cond_frames = m.cond_frames; bp.cond_layers = N; bp.cond_layer = i;
+        WN_REQUIRE(m.cond_fg16, WN_ERR_INVALID, "conditioned backward: the bf16 conditioning table is missing (launch_cond_pack16)");
+        bp.cond = m.cond_fg; bp.cond16 = reinterpret_cast<const uint4*>(m.cond_fg16); bp.cond_frames = m.cond_frames; bp.cond_layers = N; bp.cond_layer = i;
         bp.bias_fg = nullptr;
       }
       if (l2_hints_on()) { bp.pol_first = kL2EvictFirst; bp.pol_last = kL2EvictLast; }
       b2.n_batches = B;
       b2.partial = reinterpret_cast<float*>(Wp + wl.WGP) + (int64_t)i * WGP_LAYER_FLOATS;
+      if (fs_side && i + 2 < N) WN_CHECK_CUDA(cudaStreamWaitEvent(s, side->dfg_free[dfg_alt], 0));      // layer i + 2's frame sums have read this buffer
       WN_PROPAGATE(launch_block_bwd2(bm, b2, s));
       WN_DEBUG_SYNC("block_bwd3", s);
-      if (m.cond_fg_grad)   // d loss / d cond_i[frame] in the autoencoder's raw (gate | filter) order: (B, frames, N, 2 D)
-        WN_PROPAGATE(launch_frame_sum_bf16(Wp + wl.DFG, L, 128, 0, B, s_out, L - s_out, m.cond_frames,
+      if (m.cond_fg_grad && !fs_side)   // d loss / d cond_i[frame] in the autoencoder's raw (gate | filter) order: (B, frames, N, 2 D)
+        WN_PROPAGATE(launch_frame_sum_bf16(Wp + dfg_off, L, 128, 0, B, s_out, L - s_out, m.cond_frames,
                                            m.cond_fg_grad + (int64_t)i * 2 * m.D, N * 2 * m.D, m.D, s));
       if (side) {   // sum this layer's per-CTA weight-gradient tiles next to the kernels that follow (its CTAs need ~1 KB of smem)
         WN_CHECK_CUDA(cudaEventRecord(side->fork, s));
         WN_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        if (fs_side) {      // the frame sums too: dF|dG alternates between two buffers, so the next layer's kernels do not wait for them
+          WN_PROPAGATE(launch_frame_sum_bf16(Wp + dfg_off, L, 128, 0, B, s_out, L - s_out, m.cond_frames,
+                                             m.cond_fg_grad + (int64_t)i * 2 * m.D, N * 2 * m.D, m.D, side->stream));
+          WN_CHECK_CUDA(cudaEventRecord(side->dfg_free[dfg_alt], side->stream));
+        }
         ra.layer0 = i;
         WN_PROF("wgrad_reduce (side stream, overlapped)", side->stream);
         wgrad_reduce_kernel<<<dim3((128 * 192) / 8, 1), 256, 0, side->stream>>>(reinterpret_cast<const float*>(Wp + wl.WGP), WGP_LAYER_FLOATS,
@@ -2183,12 +2210,12 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       }
     }
     if (bias) {   // dFG columns [0,64) = filter, [64,128) = gate: two separate bias vectors in the flat layout
-      WN_PROPAGATE(launch_colsum_bf16_split(Wp + wl.DFG, B, L, s_out, G + l.filt.b, G + l.gate.b, s, m.D));
+      WN_PROPAGATE(launch_colsum_bf16_split(Wp + dfg_off, B, L, s_out, G + l.filt.b, G + l.gate.b, s, m.D));
       if (has_dense) WN_PROPAGATE(launch_colsum_bf16(Wp + dx_next_off, 64, B, L, s_out, L, G + l.dense.b, s, m.R));
     }
     {   // dx_i[tau] = dx_{i+1}[tau] + W1^T dFG[tau] + W0^T dFG[tau + d]
       GemmNtMaps gm{};
-      gm.a[0] = M.dfg; gm.a[1] = M.dfg; gm.b[0] = M.layer[i].wfgT1; gm.b[1] = M.layer[i].wfgT0; gm.out = dx_cur;
+      gm.a[0] = dfg_alt ? M.dfg2 : M.dfg; gm.a[1] = gm.a[0]; gm.b[0] = M.layer[i].wfgT1; gm.b[1] = M.layer[i].wfgT0; gm.out = dx_cur;
       GemmNtParams gp{};
       const int t0 = s_in / 128;
       gp.n_batches = B; gp.tile0 = t0; gp.tiles_per_batch = tiles_total - t0; gp.n_ntiles = 1;

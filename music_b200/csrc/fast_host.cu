@@ -278,6 +278,7 @@ WsLayout ws_layout(const Model& m, int B, int L) {
   w.DXa = take((size_t)B * L * 64 * 2);
   w.DXb = take((size_t)B * L * 64 * 2);
   w.DFG = take(2 * align_up((size_t)B * L * 64 * 2, 1024));      // dF|dG (B, L, 128), or block_bwd6's two Q buffers (B, L, 64)
+  w.DFG2 = take((size_t)B * L * 128 * 2);                        // second dF|dG buffer: conditioned models sum it per frame on the side stream
   w.Zf = take((size_t)B * L * 64 * 2);
   w.DX0f = take((size_t)B * L * 64 * 4);
   w.WGP = take((size_t)WGP_LAYER_FLOATS * 4 * N);
@@ -423,7 +424,8 @@ int fast_forward(Model& m, int B, int L, const float* d_x, const int64_t* d_idx,
     p.bias_fg = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_fg) + i * 128 : nullptr;
     p.bias_d = m.use_bias ? reinterpret_cast<const float*>(P + pl.bias_d) + i * 64 : nullptr;
     if (m.cond_fg) {      // conditioned decoder: the conv bias is part of the table
-      p.cond = m.cond_fg; p.cond_frames = m.cond_frames; p.cond_layers = N; p.cond_layer = i;
+      WN_REQUIRE(m.cond_fg16, WN_ERR_INVALID, "conditioned forward: the bf16 conditioning table is missing (launch_cond_pack16)");
+      p.cond = m.cond_fg; p.cond16 = reinterpret_cast<const uint4*>(m.cond_fg16); p.cond_frames = m.cond_frames; p.cond_layers = N; p.cond_layer = i;
       p.bias_fg = nullptr;
     }
     static const int dbg_env = [] { const char* e = getenv("WN_DBG"); return e ? atoi(e) : 0; }();

@@ -29,7 +29,7 @@ inline size_t skip_bias_offs_pos(const Model& m) { return sizeof(PackJob) * (siz
 
 struct WsLayout {       // byte offsets
   size_t X, x_stride, XLO, Zcat, H0, H1, X0f;     // XLO: 2 ping-pong buffers of x_stride bytes
-  size_t DLG, DH1, DSK, DZcat, DXa, DXb, DFG, Zf, DX0f, WGP;   // WGP: per-CTA weight-gradient partial tiles
+  size_t DLG, DH1, DSK, DZcat, DXa, DXb, DFG, DFG2, Zf, DX0f, WGP;   // WGP: per-CTA weight-gradient partial tiles
   size_t total;
 };
 WsLayout ws_layout(const Model& m, int B, int L);
@@ -54,7 +54,7 @@ struct BwdMaps {
   CUtensorMap zcat, dzcat;               // (64 N, Wp, B)
   CUtensorMap p1T, p2T;                  // [256][256] box {64,256}
   CUtensorMap wsTcat;                    // [64 N rows (layer, d)][256 s] box {64,256}
-  CUtensorMap dxa, dxb, dfg, zf;         // (64|128, L, B)
+  CUtensorMap dxa, dxb, dfg, dfg2, zf;   // (64|128, L, B); dfg2: second dF|dG buffer of conditioned models
   CUtensorMap dqa, dqb;                  // block_bwd6: Q_i ping-pong buffers (64, L, B) inside the dFG region
 };
 int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int B, int L, const uint8_t* P, uint8_t* Wp,
@@ -63,6 +63,8 @@ int build_bwd_maps(const Model& m, const PackLayout& pl, const WsLayout& wl, int
 int launch_frame_sum_bf16(const void* src, int64_t rows_per_batch, int pitch, int c0, int B, int t0, int len, int frames, float* out,
                           int out_pitch, int dd, cudaStream_t s);
 int launch_cond_table(const float* raw, const float* bias, int64_t n_rows, int dd, float* out, int64_t out_stride, cudaStream_t s);
+// fp32 table rows of 128 ([filter 64 | gate 64]) -> rows in the block kernels' per-thread order (Model::cond_fg16)
+int launch_cond_pack16(const float* tab, void* out, int64_t n_rows, cudaStream_t s);
 int launch_add_bias_rows(const float* raw, const float* bias, int64_t n_rows, int C, float* out, cudaStream_t s);
 struct SkipHeadMaps;
 struct SkipHeadParams;
