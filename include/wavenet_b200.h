@@ -228,7 +228,8 @@ uint64_t wn_launch_count(void);                 /* kernels launched by this libr
 int wn_profile_enable(int32_t on);              /* bracket every launch with CUDA events on its stream */
 int wn_profile_report(char* buf, size_t cap);   /* sync; "name count total_ms" lines, longest first; clears */
 
-/* timing experiments (WN_TS=1 in the environment): 16 clock64 stamps per tile of CTA 0 of the fused block backward */
+/* timing experiments (WN_TS=1 in the environment): 16 clock64 stamps per tile of CTA 0 of the fused block backward;
+ * n < 0: -n stamps of the pipelined generation kernel (16 per step of CTA 1, group 0) */
 int wn_debug_ts(long long* h_buf, int32_t n);
 
 /* L2 -> SM read-bandwidth probe (bench.py): n_ctas CTAs each stream the L2-resident buffer `iters` times with 128-bit loads,

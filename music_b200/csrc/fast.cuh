@@ -20,6 +20,7 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
                    void* d_state, const float* d_uniforms, int64_t* d_out, float* d_logits, cudaStream_t s);
 size_t fast_gen_frag_bytes(const Model& m);                         // A-fragment image appended to the packed weights
 int fast_gen_pack(const Model& m, const float* d_params, uint8_t* P, cudaStream_t s);   // builds it (fp16) from the fp32 weights
+int fast_gen_debug_ts(long long* h_buf, int n);                     // WN_TS=1: clock64 stamps of gen_pipe_kernel (timing experiments)
 int fast_selftest(float* h_maxerr, int n_cases, cudaStream_t s);
 
 }  // namespace wn
