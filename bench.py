@@ -74,9 +74,9 @@ def kernel_flops(B):
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu captures
-    (profiles/r1d_traffic.json, made by tools/traffic_json.py; bytes cannot be measured live outside a profiler).
+    (profiles/r2_traffic.json, made by tools/traffic_json.py; bytes cannot be measured live outside a profiler).
     None when not captured."""
-    for name in ("r1d_traffic.json", "r1c_traffic.json"):
+    for name in ("r2_traffic.json", "r1d_traffic.json", "r1c_traffic.json"):
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", name)))
             return t["kernels"][kernel]["dram_bytes_per_launch"]
@@ -187,10 +187,13 @@ def bench_generation(net, n_streams, n_steps, dev):
     per stream on the device (CUDA events).
     `roofline` follows SURVEY.md 8(d): ALGORITHMIC bytes per step = streams x 15 368 B (ring read + write of 30 x 64 fp32 per
     stream-step + 8 B of I/O) + the 2.54 MB weight set once, over the step time, against the measured HBM copy peak.
-    The kernel's actual L2 -> SM traffic (every CTA of 8 streams streams the weight-fragment image each step) is reported
-    separately in `l2` against an L2 read peak measured in this run with the same number of CTAs.
-    Also timed: a throughput configuration with 8 streams on every SM-sized slice of the GPU (1024 streams), same kernel."""
+    Up to 64 streams per resident cluster run on the weights-stationary cluster pipeline (gen_pipe_kernel: `kernel` says which
+    kernel served the run); its only per-step L2 traffic is the ring state.  Larger stream counts run on the one-CTA-per-8-streams
+    kernel, whose L2 -> SM traffic (every CTA streams the weight-fragment image each step) is reported in `l2` against an L2 read
+    peak measured in this run with the same number of CTAs.
+    Also timed: a throughput configuration with 8 streams on every SM-sized slice of the GPU (1024 streams)."""
     import torch
+    from music_b200 import _lib as L_
     from music_b200.wavenet import fast_generate as FG
     peaks = {}
     try:
@@ -226,6 +229,17 @@ def bench_generation(net, n_streams, n_steps, dev):
         e1.record()
         torch.cuda.synchronize()
         ms_big = e0.elapsed_time(e1)
+    def kernel_used(state_, first_):      # which generation kernel serves this stream count (profiler label of a short call)
+        lib_ = L_.load()
+        lib_.wn_profile_enable(1)
+        FG._steps(net, state_, first_, 4)
+        torch.cuda.synchronize()
+        rep = L_.profile_report()
+        lib_.wn_profile_enable(0)
+        names = [n for n, c, m in rep if n.startswith("gen_")]
+        return names[0] if names else "?"
+    with torch.no_grad():
+        k_small, k_big = kernel_used(state, first), kernel_used(state_b, first_b)
     n_layers = len(DIL)
     w_bytes = 2 * (n_layers * (2 * 64 * 128 + 64 * 64 + 64 * 256) + 2 * 256 * 256) + 4 * 2 * Q * R      # what a CTA streams per step
     w_algo = 2 * 1_269_760                                    # the parameter set in half precision, once per step
@@ -240,7 +254,7 @@ def bench_generation(net, n_streams, n_steps, dev):
     n_ctas = (n_streams + 7) // 8
     l2_peak, l2_peak_big = measure_l2_read_peak(dev, n_ctas), measure_l2_read_peak(dev, big // 8)
     gbs = algo_rate(n_streams, n_steps, ms)
-    many = {"streams": big, "steps": nb, "us_per_step": ms_big * 1e3 / nb, "samples_per_s_per_stream": nb / (ms_big * 1e-3),
+    many = {"streams": big, "steps": nb, "kernel": k_big, "us_per_step": ms_big * 1e3 / nb, "samples_per_s_per_stream": nb / (ms_big * 1e-3),
             "samples_per_s_total": big * nb / (ms_big * 1e-3),
             "roofline": {"bound": "hbm", "achieved": algo_rate(big, nb, ms_big), "peak": peak, "unit": "GB/s",
                          "frac": algo_rate(big, nb, ms_big) / peak},
@@ -257,9 +271,17 @@ def bench_generation(net, n_streams, n_steps, dev):
                          "note": "SURVEY.md 8(d) accounting: algorithmic bytes per step over the step time.  The recurrence is "
                                  "a 31-stage dependency chain per stream (latency-bound at 64 streams): this fraction measures "
                                  "how far the kernel is from streaming its state and weights once, not its L2 efficiency"},
-            "l2": {"achieved_gbs": l2_rate(n_streams, n_steps, ms), "measured_peak_gbs": l2_peak, "frac": l2_rate(n_streams, n_steps, ms) / l2_peak,
-                   "ctas": n_ctas, "note": "bytes the kernel requests from L2 (weight-fragment image per CTA of 8 streams per step + "
-                                           "ring vectors) against the L2 read rate the same number of CTAs reach in wn_bench_l2_read"}}
+            "kernel": k_small,
+            "l2": ({"achieved_gbs": l2_rate(n_streams, n_steps, ms), "measured_peak_gbs": l2_peak, "frac": l2_rate(n_streams, n_steps, ms) / l2_peak,
+                    "ctas": n_ctas, "note": "bytes the kernel requests from L2 (weight-fragment image per CTA of 8 streams per step + "
+                                            "ring vectors) against the L2 read rate the same number of CTAs reach in wn_bench_l2_read"}
+                   if k_small != "gen_pipe" else
+                   {"achieved_gbs": n_steps * n_streams * (ring_algo - 8) / (ms * 1e-3) / 1e9, "measured_peak_gbs": None, "frac": None,
+                    "ctas": n_layers // 2 + 1,
+                    "note": "gen_pipe: the weights are resident in the registers of a 16-CTA cluster, so the only per-step L2 traffic is the "
+                            "ring vectors (one fp32 vector read and written per block and stream) = the algorithmic state bytes; tokens "
+                            "move CTA to CTA through distributed shared memory (12 KB per hop and group).  The step is the ring latency "
+                            "(30 blocks of ~1200 cycles + 15 hops + head), not a bandwidth"})}
 
 
 def bench_gpu_incumbent(dev, B, steps=3):
@@ -398,28 +420,37 @@ def bench_autoencoder(dev, steps=10, world=1, rank=0):
     idx = torch.randint(0, 256, (1, L), generator=g).to(dev)
     target = idx[:, net.receptive_field - 1:].contiguous()
     tr = T.AeTrainer(net, 'Adam', 1e-4, distributed=world > 1)
-    for _ in range(3):
-        tr.step(idx, target)
-    torch.cuda.synchronize()
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss = tr.step(idx, target)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
+
+    def timed(idx_, target_, n):
+        for _ in range(3):
+            tr.step(idx_, target_)
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loss_ = tr.step(idx_, target_)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms_], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t[0])
+        return ms_, float(loss_)
+    ms, loss = timed(idx, target, steps)
+    # the same step with 4 clips per GPU (the per-GPU batch is not fixed by configs[4]; one clip is 532 tiles per layer = 3.6 per SM)
+    idx4 = torch.randint(0, 256, (4, L), generator=g).to(dev)
+    ms4, _ = timed(idx4, idx4[:, net.receptive_field - 1:].contiguous(), max(3, steps // 2))
     return {"workload": "wavenet_autoencoder 40 layers (1..512 x4), 32 ch, bottleneck/skip 512, pool 512; 1 clip x 64000 targets "
                         f"(L=68093) per GPU on {world} GPU(s), index input, fused Adam step (AeTrainer), mode {net.mode}",
             "samples_per_s": world * W / (ms * 1e-3), "ms_per_step": ms, "dtype": "bf16" if net.mode == "bf16" else "f32",
-            "loss": float(loss), "n_gpus": world, "steps": steps,
-            "train_flops_per_sample": 8.656e6, "tflops": world * W * 8.656e6 / (ms * 1e-3) / 1e12}
+            "loss": loss, "n_gpus": world, "steps": steps,
+            "train_flops_per_sample": 8.656e6, "tflops": world * W * 8.656e6 / (ms * 1e-3) / 1e12,
+            "clips_per_gpu_4": {"ms_per_step": ms4, "samples_per_s": world * 4 * W / (ms4 * 1e-3),
+                                "tflops": world * 4 * W * 8.656e6 / (ms4 * 1e-3) / 1e12}}
 
 
 def workload_config(world, B):

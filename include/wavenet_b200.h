@@ -94,6 +94,14 @@ int wn_onehot_encode(const int64_t* d_codes, int32_t B, int32_t T, int32_t q, in
 int wn_model_create(const wn_config* cfg, wn_model** out);
 int wn_model_destroy(wn_model* m);
 int64_t wn_model_param_count(const wn_model* m);
+/* Offset (in floats) of residual block `layer`'s first parameter in the flat vector: [offset, param_count) holds blocks
+ * layer .. N-1 and the two post-processing convs (layer == N: only those). */
+int64_t wn_model_layer_offset(const wn_model* m, int32_t layer);
+/* Overlapped data-parallel gradient exchange (replaces what nn.DataParallel's reducer does, wavenet/train.py:121): when set, the
+ * bf16 wn_backward records `cuda_event` (a cudaEvent_t) as soon as the gradients in [wn_model_layer_offset(layer), param_count)
+ * are final - the blocks below `layer` are still running - so the caller can start reducing that bucket on another stream.
+ * layer < 0 or a NULL event: off.  Models with bias and the fp32 mode ignore it (the event is then recorded at the end). */
+int wn_backward_set_split(wn_model* m, int32_t layer, void* cuda_event);
 int32_t wn_model_receptive_field(const wn_model* m);          /* model.py:43-44 */
 /* 1 if this build serves the model's shape with: what = 0 the bf16 tcgen05 training path (residual, dilation <= 64 channels,
  * zero-padded to 64; skip = quantization = 256), what = 1 the half-precision generation kernel (exactly 64/64/256/256);

@@ -57,6 +57,8 @@ SIGNATURES = {
     "wn_model_destroy": (C.c_int, [_p]),
     "wn_model_param_count": (C.c_int64, [_p]),
     "wn_model_receptive_field": (C.c_int32, [_p]),
+    "wn_model_layer_offset": (C.c_int64, [_p, _i32]),
+    "wn_backward_set_split": (C.c_int, [_p, _i32, _p]),
     "wn_model_supports": (C.c_int32, [_p, _i32]),
     "wn_packed_bytes": (C.c_int, [_p, _i32, _psz]),
     "wn_pack_weights": (C.c_int, [_p, _i32, _p, _p, _p]),

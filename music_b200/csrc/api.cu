@@ -492,6 +492,17 @@ extern "C" int wn_model_destroy(wn_model* h) {
 }
 extern "C" int64_t wn_model_param_count(const wn_model* h) { return h ? h->m.n_params : -1; }
 extern "C" int32_t wn_model_receptive_field(const wn_model* h) { return h ? h->m.rf : -1; }
+extern "C" int64_t wn_model_layer_offset(const wn_model* h, int32_t layer) {
+  if (!h || layer < 0 || layer > h->m.n_layers) return -1;
+  return layer == h->m.n_layers ? h->m.post1.w : h->m.layers[layer].filt.w;
+}
+extern "C" int wn_backward_set_split(wn_model* h, int32_t layer, void* cuda_event) {
+  WN_REQUIRE(h, WN_ERR_INVALID, "wn_backward_set_split: null model");
+  WN_REQUIRE(layer < h->m.n_layers, WN_ERR_INVALID, "wn_backward_set_split: layer %d of %d", layer, h->m.n_layers);
+  h->m.split_layer = (layer >= 0 && cuda_event) ? layer : -1;
+  h->m.split_event = h->m.split_layer >= 0 ? cuda_event : nullptr;
+  return WN_OK;
+}
 extern "C" int32_t wn_model_supports(const wn_model* h, int32_t what) {
   if (!h) return 0;
   return what == 0 ? (fast_supported(h->m) ? 1 : 0) : (what == 1 ? (fast_gen_supported(h->m) && h->m.n_layers <= 40 ? 1 : 0) : 0);
@@ -597,8 +608,12 @@ extern "C" int wn_backward(wn_model* h, int32_t mode, int32_t B, int32_t L, cons
   WN_REQUIRE((d_x != nullptr) != (d_idx != nullptr), WN_ERR_INVALID, "wn_backward: exactly one of d_x / d_idx must be given");
   WN_REQUIRE(h->cond.d_fg == nullptr, WN_ERR_UNSUPPORTED, "wn_backward: a conditioning descriptor is installed (inference only)");
   WN_PROPAGATE(check_shape(h->m, B, L));
-  if (mode == WN_MODE_FP32)
-    return backward32(h->m, B, L, d_x, d_idx, (const float*)d_packed, d_workspace, d_dlogits, d_grads, (cudaStream_t)stream);
+  if (mode == WN_MODE_FP32) {
+    WN_PROPAGATE(backward32(h->m, B, L, d_x, d_idx, (const float*)d_packed, d_workspace, d_dlogits, d_grads, (cudaStream_t)stream));
+    if (h->m.split_event && h->m.split_layer >= 0)      // (no early bucket in the check mode: the event fires at the end)
+      WN_CHECK_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(h->m.split_event), (cudaStream_t)stream));
+    return WN_OK;
+  }
   if (mode == WN_MODE_BF16)
     return fast_backward(h->m, B, L, d_x, d_idx, d_packed, d_workspace, d_dlogits, d_grads, (cudaStream_t)stream);
   set_error("wn_backward: unknown mode %d", mode);

@@ -92,6 +92,9 @@ struct Model {
   float* cond_fg_grad = nullptr;      // backward: sums of d[f|g] / d(head pre-activation) over the rows of each frame, same shapes
   float* cond_head_grad = nullptr;    //           (must be zero-filled by the caller)
   int cond_frames = 0;
+  // overlapped gradient exchange (wn_backward_set_split): record split_event once the gradients of blocks >= split_layer are final
+  int split_layer = -1;
+  void* split_event = nullptr;
 };
 
 // fp32 packed image: per conv Wt[k][in][out], Wtt[k][out][in], bias copy (offsets in floats)

@@ -2126,6 +2126,8 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   // reads has been written in this step (rows below s_out as zeros)
   auto first_tile = [&](int i) { return fuse_dx ? (i > 0 ? m.layers[i - 1].start / 128 : 0) : m.layers[i].start / 128; };
   for (int i = 0; i < N; ++i) ra.n_ctas[i] = std::min(B * (tiles_total - first_tile(i)), g_sm_count);
+  const bool split_ok = fuse_dx && side != nullptr && m.split_event != nullptr && m.split_layer >= 0;
+  bool split_done = false;
   for (int i = N - 1; i >= 0; --i) {
     const LayerP& l = m.layers[i];
     const int d = l.dilation, s_out = l.start, s_in = s_out - d;
@@ -2168,6 +2170,10 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
         wgrad_reduce_kernel<<<dim3((128 * 192) / 8, 1), 256, 0, side->stream>>>(reinterpret_cast<const float*>(Wp + wl.WGP), WGP_LAYER_FLOATS,
                                                                                  ra, G);
         WN_CHECK_LAUNCH();
+        if (split_ok && i == m.split_layer) {      // blocks >= i, the skip weights and the head are final: that bucket may be exchanged
+          WN_CHECK_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(m.split_event), side->stream));
+          split_done = true;
+        }
       }
       continue;
     }
@@ -2230,6 +2236,13 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
       WN_PROPAGATE(launch_gemm_nt(64, gm, gp, s));
       WN_DEBUG_SYNC("gemm_nt dx", s);
     }
+  }
+  if (m.split_event && m.split_layer >= 0 && !split_done) {      // configurations without the early record: the event still fires
+    if (side) {
+      WN_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+      WN_CHECK_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+    }
+    WN_CHECK_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(m.split_event), s));
   }
   if (side) {                 // join: everything after this point on `s` sees the reduced weight gradients
     WN_CHECK_CUDA(cudaEventRecord(side->join, side->stream));

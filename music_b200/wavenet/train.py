@@ -14,6 +14,8 @@ import os
 from collections import OrderedDict
 from functools import cmp_to_key
 
+import ctypes as C
+
 import torch
 import torch.nn as nn
 import torch.optim as optim
@@ -142,10 +144,38 @@ class Trainer:
         e.backward(mode, x, idx, packed, ws, dlogits, e.gflat)
         return loss
 
+    # ---- overlapped gradient exchange -------------------------------------------------------------------------------------
+    # The backward produces the gradients top-down: head and skip weights first, then blocks N-1 .. 0.  With two buckets split at
+    # block K = N / 2 the upper bucket [offset(K), n_params) is final when the backward is half way through; the library records an
+    # event at that point (wn_backward_set_split) and its all-reduce runs on a second stream under the lower blocks' kernels.  Only
+    # the lower bucket's exchange (and the slowest rank's skew) is left exposed after the last backward kernel.
+    def _overlap_setup(self):
+        if self.dist is None or self.dist.get_world_size(self.group) == 1 or os.environ.get("WN_AR_OVERLAP", "1") == "0":
+            return False
+        if self._comm_stream is None:
+            e, lib = self.net.engine, L.load()
+            n_layers = len(self.net.dilations)
+            self._split_layer = n_layers // 2
+            self._split_off = int(lib.wn_model_layer_offset(e.handle, self._split_layer))
+            self._comm_stream = torch.cuda.Stream(e.flat.device)
+            self._split_event = torch.cuda.Event()
+            self._split_event.record()          # (creates the underlying cudaEvent_t)
+            L.check(lib.wn_backward_set_split(e.handle, self._split_layer, C.c_void_p(self._split_event.cuda_event)))
+        return self._split_off > 0
+
     def all_reduce(self):
         if self.dist is None:
             return
-        all_reduce_mean_(self.net.engine.gflat, self.dist, self.group)
+        g = self.net.engine.gflat
+        if not self._overlap_setup():
+            all_reduce_mean_(g, self.dist, self.group)
+            return
+        main = torch.cuda.current_stream(g.device)
+        self._comm_stream.wait_event(self._split_event)            # recorded inside the backward that was enqueued just now
+        with torch.cuda.stream(self._comm_stream):
+            all_reduce_mean_(g[self._split_off:], self.dist, self.group)
+        all_reduce_mean_(g[:self._split_off], self.dist, self.group)
+        main.wait_stream(self._comm_stream)
 
     def apply(self):
         e, lib = self.net.engine, L.load()

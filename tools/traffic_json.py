@@ -10,6 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LABELS = {                      # bench.py kernel label -> substring of the demangled kernel name
+    "block_bwd6": ("block_bwd6_kernel<1, 1>", "block_bwd6_kernel<true, true>", "block_bwd6_kernel"),
     "block_bwd2": ("block_bwd3_kernel<0, 1>", "block_bwd2_kernel<0, 1>"),
     "block_fwd": ("block_fwd2_kernel",),
     "skip_head": ("skip_head_kernel",),
