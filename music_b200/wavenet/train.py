@@ -201,6 +201,95 @@ class Trainer:
             p.grad = g
         return loss
 
+    # ---- optimizer state (the reference checkpoints the model only, train.py:44-50; resuming Adam from zero moments costs a
+    #      few hundred steps of re-warm-up, so the fused optimizer's state can be saved next to the `.model` file) ---------------
+    def state_dict(self):
+        """{'kind', 'step', 'lr', 'momentum', buffers...}: the flat moment vectors on the CPU (parameter order = state_dict order)."""
+        out = {"kind": self.kind, "step": self.step_count, "lr": self.lr, "momentum": self.momentum}
+        for k, v in self.state.items():
+            out["buf." + k] = v.detach().cpu().clone()
+        return out
+
+    def load_state_dict(self, sd):
+        if sd["kind"] != self.kind:
+            raise ValueError(f"optimizer state is for '{sd['kind']}', this trainer runs '{self.kind}'")
+        e = self.net.engine
+        e.ensure_flat(self.net._params())
+        self.step_count = int(sd["step"])
+        for k, v in sd.items():
+            if k.startswith("buf."):
+                if v.numel() != e.n_params:
+                    raise ValueError(f"optimizer buffer '{k[4:]}' has {v.numel()} values, the model {e.n_params} parameters")
+                self._buf(k[4:]).copy_(v.to(e.flat.device))
+
+
+def save_optimizer(trainer, num_iter, path):
+    """`wavenet<N>.optim` next to `wavenet<N>.model` (same numbering as save_model)."""
+    torch.save(trainer.state_dict(), path + "wavenet" + str(num_iter) + ".optim")
+
+
+def load_optimizer(trainer, path, model_name):
+    """Restore the optimizer state saved with the checkpoint `model_name` (`wavenet<N>.model`); False when there is none."""
+    f = path + model_name.rsplit(".", 1)[0] + ".optim"
+    if not os.path.exists(f):
+        return False
+    trainer.load_state_dict(torch.load(f, map_location="cpu"))
+    return True
+
+
+# ---- time-axis sharding (SURVEY.md 8(f) row 4) ----------------------------------------------------------------------------------
+def exchange_time_halo(codes, rf, dist=None, group=None):
+    """One long clip split along TIME over the ranks: rank r holds the contiguous slice `codes` (B, T_r) of mu-law codes.  The
+    network is causal with receptive field rf: the prediction of a slice's first sample needs the rf samples before it (rf - 1 of
+    context plus the sample the first window ends on), so each rank sends the last rf codes of its slice to rank r + 1 and receives
+    its left neighbour's - one send / recv pair per boundary; rank 0 has no left context, its first rf samples are context only,
+    exactly as at the start of an unsharded clip.  Returns the (B, rf + T_r) piece this rank trains on (rank 0: its slice unchanged);
+    together the ranks then cover every target of the clip exactly once.  No activation crosses ranks: the halo is INPUT, recomputed
+    through the stack.  Works on any backend (NCCL on GPUs, gloo in the CPU test)."""
+    if dist is None:
+        import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return codes
+    h = rf
+    if codes.shape[-1] < h:
+        raise ValueError(f"a time slice of {codes.shape[-1]} samples is shorter than the halo ({h})")
+    ops, halo = [], None
+    if rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, codes[..., -h:].contiguous(), rank + 1, group))
+    if rank > 0:
+        halo = torch.empty(codes.shape[:-1] + (h,), dtype=codes.dtype, device=codes.device)
+        ops.append(dist.P2POp(dist.irecv, halo, rank - 1, group))
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    return codes if halo is None else torch.cat([halo, codes], dim=-1)
+
+
+def time_sharded_step(trainer, codes, rf=None):
+    """One training step on a clip that spans the ranks along time (exchange_time_halo + the data-parallel step): every rank's
+    targets are its own slice (rank 0: its slice minus the first rf samples); each rank's gradient of its mean loss is weighted by
+    its share of the clip's targets before the flat gradient is averaged, so the result is the gradient of the mean loss over ALL
+    targets of the clip, whatever the slice lengths.  Needs the per-time-step objective (`parity="corrected"`): the reference's
+    flat-chunk softmax rows mix time steps of the whole (B, Q, W) tensor and have no time-local definition.  Returns this rank's loss."""
+    net = trainer.net
+    if net.parity != "corrected":
+        raise L.WavenetB200Error("time-axis sharding needs parity='corrected' (the reference objective's softmax rows are not local in time)")
+    rf = net.receptive_field if rf is None else rf
+    piece = exchange_time_halo(codes, rf, trainer.dist, trainer.group) if trainer.dist is not None else codes
+    W = piece.shape[-1] - rf                      # targets: sample t + 1 for every window ending at t (as audio_data_loader pairs them)
+    loss = trainer.forward_backward(piece[..., :-1].contiguous(), piece[..., rf:rf + W].contiguous())
+    if trainer.dist is not None and trainer.dist.get_world_size(trainer.group) > 1:
+        key = (int(W), tuple(codes.shape))
+        cache = trainer.__dict__.setdefault("_time_shard_weight", {})
+        if key not in cache:                      # this rank's share of the targets x world (one scalar all-reduce per new shape)
+            n = torch.tensor([float(W)], device=codes.device)
+            trainer.dist.all_reduce(n, group=trainer.group)
+            cache[key] = float(W) * trainer.dist.get_world_size(trainer.group) / float(n[0])
+        trainer.net.engine.gflat.mul_(cache[key])
+    trainer.all_reduce()
+    trainer.apply()
+    return loss
+
 
 class BatchStager:
     """Host -> device staging of (audio_piece, audio_target) batches under the running train step: two device slots,

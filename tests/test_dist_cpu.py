@@ -118,3 +118,65 @@ def test_autoencoder_two_rank_gloo_gradient_average_equals_full_batch(tmp_path):
     _ae_grads(st, cond, idx, tgt)
     ref = torch.cat([p.grad.reshape(-1) for p in st.values() if p.grad is not None]).numpy()
     np.testing.assert_allclose(got, ref, rtol=2e-4, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------ time-axis sharding
+def _time_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from music_b200.wavenet.train import all_reduce_mean_, exchange_time_halo
+    st, clip, bounds = _time_case(world)
+    rf = O.receptive_field(2, DIL)
+    mine = clip[:, bounds[rank]:bounds[rank + 1]].contiguous()
+    piece = exchange_time_halo(mine, rf)
+    # this rank's targets under the per-time-step objective: one cross entropy per time step over the Q logits (parity="corrected")
+    W = piece.shape[1] - rf
+    x = O.one_hot(piece[:, :-1], 256)
+    tgt = piece[:, rf:rf + W]
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in st.items()}
+    logits = O.forward_logits(leaves, DIL, x)                                   # (B, Q, W)
+    loss_sum = torch.nn.functional.cross_entropy(logits, tgt, reduction="sum")
+    loss_sum.backward()
+    flat = torch.cat([(torch.zeros_like(leaves[k]) if leaves[k].grad is None else leaves[k].grad).reshape(-1) for k in st])
+    n = torch.tensor([float(tgt.numel())])
+    dist.all_reduce(flat)                                                       # sums of per-target gradients ...
+    dist.all_reduce(n)                                                          # ... over all targets of the clip
+    ok = torch.tensor([1.0 if torch.equal(piece, clip[:, max(bounds[rank] - rf, 0):bounds[rank + 1]]) else 0.0])
+    dist.all_reduce(ok)
+    if rank == 0:
+        np.save(out, np.concatenate([[float(ok[0]), float(n[0])], (flat / n).numpy()]))
+    dist.destroy_process_group()
+
+
+def _time_case(world):
+    st = O.init_wavenet_state(DIL, 8, 8, 16, 256, True, seed=5, scale=2.0)
+    rf = O.receptive_field(2, DIL)
+    T = rf + 90
+    g = torch.Generator().manual_seed(9)
+    clip = torch.randint(0, 256, (2, T), generator=g)
+    first = rf + 29                       # rank 0's slice contains the clip's first rf context samples
+    rest = (T - first) // (world - 1)
+    bounds = [0, first] + [first + rest * (i + 1) for i in range(world - 1)]
+    bounds[-1] = T
+    return st, clip, bounds
+
+
+def test_time_axis_sharding_halo_exchange_equals_whole_clip(tmp_path):
+    """A clip split along time over 3 ranks: after exchange_time_halo every rank holds its slice plus the rf samples before it,
+    and the target-weighted sum of the per-rank gradients equals the gradient of the whole clip (per-time-step objective)."""
+    world = 3
+    out = str(tmp_path / "t.npy")
+    mp.spawn(_time_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got = np.load(out)
+    st, clip, bounds = _time_case(world)
+    rf = O.receptive_field(2, DIL)
+    assert got[0] == world                                   # every rank's piece is the right window of the clip
+    W = clip.shape[1] - rf
+    assert got[1] == 2 * W                                   # together the ranks cover every target exactly once
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in st.items()}
+    logits = O.forward_logits(leaves, DIL, O.one_hot(clip[:, :-1], 256))
+    torch.nn.functional.cross_entropy(logits, clip[:, rf:rf + W], reduction="mean").backward()
+    ref = torch.cat([(torch.zeros_like(leaves[k]) if leaves[k].grad is None else leaves[k].grad).reshape(-1) for k in st]).numpy()
+    np.testing.assert_allclose(got[2:], ref, rtol=2e-4, atol=1e-8)      # (the last block's dense conv is unused: zero gradient)
