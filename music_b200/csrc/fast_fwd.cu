@@ -32,7 +32,10 @@ constexpr uint32_t WD_BYTES = 64 * 128;
 // the Zcat store), one staging tile for x_{i+1} hi and two lo tiles (TMA-loaded, lo' written in place).  The TMA stores of
 // a tile are checked one epilogue phase later, just before their staging tiles are rewritten, so nobody waits for them;
 // the MMA issuer polls its two job queues (UMMA #2 of tile j2, UMMA #1 of tile j1) and never blocks on one while the
-// other is ready.  History (clock64 instrumentation, profiles/): the first
+// other is ready.  Round 2 (profiles/r2_summary.md): a store warp, epilogue 2 software-pipelined behind the next tile's epilogue 1 and
+// outputs written straight from registers were all built and verified - 1.34 to 1.61 ms per step against 1.32 for this kernel:
+// at 7470 warp-instructions per tile (1870 issue slots per scheduler, issue active 45 %) the tile period is set by the epilogue's
+// instruction stream, not by any wait those variants remove.  History (clock64 instrumentation, profiles/): the first
 // persistent version spent, per 6800-cycle tile, 1250 cycles with all threads waiting for the TMA store to drain and
 // 2000 waiting for UMMA #2 queued behind the next tile's UMMA #1 in the in-order tensor pipe.
 namespace {
@@ -47,15 +50,6 @@ struct Fwd2Smem {
   static constexpr uint32_t TOTAL = LO + 2 * TILE_BYTES;                                   // 216 KB
 };
 __device__ __forceinline__ void epi16_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-// 32 bytes per thread in one request (256-bit STG): a full sector per lane; `policy` = L2 eviction hint or 0
-__device__ __forceinline__ void stg32(void* ptr, uint64_t policy, const uint32_t* v) {
-  if (policy)
-    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
-                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "l"(policy) : "memory");
-  else
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
-                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-}
 // 32 bytes per thread in one request (256-bit LDG through the read-only path)
 __device__ __forceinline__ void ldg_nc32(const void* ptr, uint32_t* v) {
   asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -303,294 +297,6 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 
 }  // namespace
 
-// ====================================================================================== block (persistent, pipelined epilogues)
-// block_fwd3_kernel: block_fwd2 with the two things its clock64 timeline (tools/ts_fwd.py: 4000 cycles per tile = epilogue 1 900 +
-// UMMA #2 round trip 750 + epilogue 2 1170 + single-thread store issue and loop top 880) shows on the critical path taken off it:
-//   * epilogue 2 of tile n - 1 runs AFTER epilogue 1 of tile n, so the z -> UMMA #2 -> dense_full round trip of tile n is covered by
-//     work instead of being waited for by all 16 epilogue warps;
-//   * a store warp (warp 18) issues the three TMA stores of a tile, waits for their shared-memory reads and releases the staging tiles
-//     (out_free, lo_empty); no epilogue thread issues a store or waits for one, so thread 0 is no longer ~550 cycles late at the
-//     next barrier.
-// The accumulator release is split accordingly: UMMA #1 of tile n + 2 needs the f|g columns of its TMEM buffer (drained by epilogue 1
-// of tile n), UMMA #2 the dense columns (drained by epilogue 2 of tile n, one iteration later).
-namespace {
-
-// DIRECT: every output (z -> Zcat, x_{i+1} hi, lo') goes from the epilogue registers to global memory as one full 32-byte sector per
-// thread and array; nothing is staged for a TMA store, so no staging tile has to be waited for and the store warp is idle.
-template <bool BIAS, bool COND, bool PIPE, bool DIRECT>
-__global__ void __launch_bounds__(608, 1)
-block_fwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w0,
-                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_wd,
-                  const __grid_constant__ CUtensorMap tm_xo, const __grid_constant__ CUtensorMap tm_loo,
-                  const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_lo, BlockFwdParams p,
-                  BlockFwdPtrs g, int n_batches) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t w_full, in_full[3], in_empty[3], fg_full[2], fg_empty[2], dense_full[2], dense_empty[2], z_ready;
-  __shared__ __align__(8) uint64_t lo_full[2], lo_empty[2], out_ready, out_free;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    mbar_init(&w_full, 1);
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(&in_full[i], 1);
-      mbar_init(&in_empty[i], 2);       // UMMA #1 commit + epilogue 2 (residual tile read)
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&fg_full[i], 1);
-      mbar_init(&fg_empty[i], 1);
-      mbar_init(&dense_full[i], 1);
-      mbar_init(&dense_empty[i], 1);
-      mbar_init(&lo_full[i], 1);
-      mbar_init(&lo_empty[i], 1);
-    }
-    mbar_init(&z_ready, 1);
-    mbar_init(&out_ready, 1);
-    mbar_init(&out_free, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t sbase = smem_u32(sm);
-  const int n_items = n_batches * p.tiles_per_batch;
-  const bool dense = p.has_dense != 0;
-  const int n_mine = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp == 16) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0 && n_mine > 0) {
-      mbar_expect_tx(&w_full, 2 * TILE_BYTES + (dense ? WD_BYTES : 0));
-      tma_load_2d(sm + Fwd2Smem::W0, &tm_w0, &w_full, 0, 0);
-      tma_load_2d(sm + Fwd2Smem::W1, &tm_w1, &w_full, 0, 0);
-      if (dense) tma_load_2d(sm + Fwd2Smem::WD, &tm_wd, &w_full, 0, 0);
-      int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
-      for (int it = 0; it < n_mine; ++it) {
-        const int st = it % 3, tau0 = (p.tile0 + tl) * 128;
-        mbar_wait(&in_empty[st], ((it / 3) & 1) ^ 1);
-        uint8_t* si = sm + Fwd2Smem::IN + st * Fwd2Smem::IN_STAGE;
-        mbar_expect_tx(&in_full[st], 2 * TILE_BYTES);
-        tma_load_3d(si, &tm_x, &in_full[st], 0, tau0 - p.d, b, p.pol_first);
-        tma_load_3d(si + TILE_BYTES, &tm_x, &in_full[st], 0, tau0, b);
-        if (dense) {
-          mbar_wait(&lo_empty[it & 1], ((it >> 1) & 1) ^ 1);
-          mbar_expect_tx(&lo_full[it & 1], TILE_BYTES);
-          tma_load_3d(sm + Fwd2Smem::LO + (it & 1) * TILE_BYTES, &tm_lo, &lo_full[it & 1], 0, tau0, b, p.pol_first);
-        }
-        tl += (int)gridDim.x;
-        while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
-      }
-    }
-  } else if (warp == 17) {
-    // ------------------------------------------------------------ MMA issuer (polling)
-    if (lane == 0 && n_mine > 0) {
-      constexpr uint32_t id1 = idesc_bf16(128, 128, 0, 0), id2 = idesc_bf16(128, 64, 0, 0);
-      mbar_wait(&w_full, 0);
-      int j1 = 0, j2 = 0;
-      while (j1 < n_mine || (dense && j2 < n_mine)) {
-        if (dense && j2 < j1 && mbar_test_wait(&z_ready, j2 & 1) && mbar_test_wait(&dense_empty[j2 & 1], ((j2 >> 1) & 1) ^ 1)) {
-          tc_fence_after();
-          const uint32_t acc = tmem + (j2 & 1) * 192 + 128;
-          const uint32_t zt = sbase + Fwd2Smem::Z + (j2 & 1) * TILE_BYTES;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(zt, kk), desc_kmajor(sbase + Fwd2Smem::WD, kk), id2, kk > 0);
-          umma_commit(&dense_full[j2 & 1]);
-          ++j2;
-        }
-        if (j1 < n_mine && mbar_test_wait(&in_full[j1 % 3], (j1 / 3) & 1) && mbar_test_wait(&fg_empty[j1 & 1], ((j1 >> 1) & 1) ^ 1)) {
-          tc_fence_after();
-          const uint32_t si = sbase + Fwd2Smem::IN + (j1 % 3) * Fwd2Smem::IN_STAGE, acc = tmem + (j1 & 1) * 192;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si, kk), desc_kmajor(sbase + Fwd2Smem::W0, kk), id1, kk > 0);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_bf16(acc, desc_kmajor(si + TILE_BYTES, kk), desc_kmajor(sbase + Fwd2Smem::W1, kk), id1, true);
-          umma_commit(&fg_full[j1 & 1]);
-          umma_commit(&in_empty[j1 % 3]);
-          ++j1;
-        }
-      }
-    }
-  } else if (warp == 18) {
-    // ------------------------------------------------------------ store warp: tiles in order
-    if (!DIRECT && lane == 0 && n_mine > 0) {
-      int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
-      for (int it = 0; it < n_mine; ++it) {
-        const int tau0 = (p.tile0 + tl) * 128;
-        mbar_spin_wait(&out_ready, it & 1);
-        // z is read again only by the skip GEMM at the end of the forward; x_{i+1} hi / lo' by the very next launch
-        if (tau0 >= p.tw_al) tma_store_3d(&tm_z, sm + Fwd2Smem::Z + (it & 1) * TILE_BYTES, p.zcol, tau0 - p.tw_al, b, p.pol_first);
-        if (dense) {
-          tma_store_3d(&tm_xo, sm + Fwd2Smem::XO, 0, tau0, b, p.pol_last);
-          tma_store_3d(&tm_loo, sm + Fwd2Smem::LO + (it & 1) * TILE_BYTES, 0, tau0, b, p.pol_last);
-        }
-        tma_store_commit();
-        tma_store_wait_read();
-        mbar_arrive(&out_free);
-        if (dense) mbar_arrive(&lo_empty[it & 1]);
-        tl += (int)gridDim.x;
-        while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue: E1(it) then E2(it - 1)
-    const int q4 = warp & 3, cg = warp >> 2;
-    const int row = q4 * 32 + lane;
-    int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch;
-    bool valid_prev = false;
-    int st_prev = 0, tau_prev = 0, b_prev = 0, tau_cur = 0, b_cur = 0;
-    for (int it = 0; it < n_mine + (PIPE ? 1 : 0); ++it) {
-      const int ab = it & 1;
-      const uint32_t ph2 = (it >> 1) & 1;
-      bool valid = false;
-      // PIPE: the staging tiles epilogue 1 (z tile `ab`) and epilogue 2 (x_{i+1}, lo') are about to rewrite were stored for tile
-      // it - 2: waited for every iteration, so the phase parity is unambiguous
-      if (!DIRECT && PIPE && it >= 2) mbar_wait(&out_free, it & 1);
-      if (it < n_mine) {
-        const int tau0 = (p.tile0 + tl) * 128;
-        const int tau = tau0 + row;
-        valid = (tau >= p.s_out) && (tau < p.L);
-        const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, ab * 192);
-        uint8_t* zt = sm + Fwd2Smem::Z + ab * TILE_BYTES;
-        uint32_t cw[32];
-        if (COND) {
-          const uint4* cp16 = p.cond16 + ((((int64_t)b * p.cond_frames + (valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0)) *
-                                           p.cond_layers + p.cond_layer) * 4 + cg) * 8;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) ldg_nc32(cp16 + 2 * q, cw + 8 * q);
-        }
-        mbar_wait(&fg_full[ab], ph2);
-        tc_fence_after();
-        uint32_t f[16], gq[16];
-        tmem_ld16(lane_addr + cg * 16, f);
-        tmem_ld16(lane_addr + 64 + cg * 16, gq);
-        tmem_ld_wait();
-        uint32_t pz[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float f0 = __uint_as_float(f[2 * j]), f1 = __uint_as_float(f[2 * j + 1]);
-          float g0 = __uint_as_float(gq[2 * j]), g1 = __uint_as_float(gq[2 * j + 1]);
-          if (BIAS) {
-            f0 += p.bias_fg[cg * 16 + 2 * j];
-            f1 += p.bias_fg[cg * 16 + 2 * j + 1];
-            g0 += p.bias_fg[64 + cg * 16 + 2 * j];
-            g1 += p.bias_fg[64 + cg * 16 + 2 * j + 1];
-          }
-          if (COND) {
-            f0 += __uint_as_float(cw[2 * j]);
-            f1 += __uint_as_float(cw[2 * j + 1]);
-            g0 += __uint_as_float(cw[16 + 2 * j]);
-            g1 += __uint_as_float(cw[16 + 2 * j + 1]);
-          }
-          const float z0 = sigmoid_fast(g0) * tanh_fast(f0), z1 = sigmoid_fast(g1) * tanh_fast(f1);
-          pz[j] = valid ? pack_bf16(z0, z1) : 0u;
-        }
-        *reinterpret_cast<uint4*>(zt + sw128_chunk(row, cg * 2)) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
-        *reinterpret_cast<uint4*>(zt + sw128_chunk(row, cg * 2 + 1)) = make_uint4(pz[4], pz[5], pz[6], pz[7]);
-        fence_proxy_async_smem();
-        tc_fence_before();
-        epi16_bar_sync();
-        if (tid == 0) {
-          mbar_arrive(&fg_empty[ab]);
-          if (dense) mbar_arrive(&z_ready);
-        }
-        if (DIRECT && tau0 >= p.tw_al && tau < p.L)      // z -> Zcat (read again only by the skip GEMM at the end of the forward)
-          stg32(g.zcat + ((int64_t)b * p.Wp + (tau - p.tw_al)) * p.zpitch + p.zcol + cg * 16, p.pol_first, pz);
-        tau_cur = tau;
-        b_cur = b;
-      }
-      if (!PIPE) {      // in order: epilogue 2 of the SAME tile; its staging tiles were stored for tile it - 1 (one epilogue 1 ago)
-        valid_prev = valid;
-        tau_prev = tau_cur;
-        b_prev = b_cur;
-        st_prev = it % 3;
-        if (!DIRECT && it >= 1) mbar_wait(&out_free, (it - 1) & 1);
-      }
-      if (!PIPE || it >= 1) {
-        // ---- epilogue 2 (PIPE: of tile it - 1): x_{i+1} = dense + (hi + lo) in fp32, split again into hi + lo
-        const int pb = PIPE ? (ab ^ 1) : ab;
-        const uint32_t php = PIPE ? (((it - 1) >> 1) & 1) : ph2;
-        if (dense) {
-          const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, pb * 192);
-          const uint8_t* si = sm + Fwd2Smem::IN + st_prev * Fwd2Smem::IN_STAGE;
-          uint8_t* lot = sm + Fwd2Smem::LO + pb * TILE_BYTES;
-          mbar_wait(&lo_full[pb], php);
-          mbar_wait(&dense_full[pb], php);
-          tc_fence_after();
-          uint32_t dv[16];
-          tmem_ld16(lane_addr + 128 + cg * 16, dv);
-          tmem_ld_wait();
-          uint32_t ph[8], pl[8];
-          const uint4 lv0 = *reinterpret_cast<const uint4*>(lot + sw128_chunk(row, cg * 2));
-          const uint4 lv1 = *reinterpret_cast<const uint4*>(lot + sw128_chunk(row, cg * 2 + 1));
-          const uint32_t ll[8] = {lv0.x, lv0.y, lv0.z, lv0.w, lv1.x, lv1.y, lv1.z, lv1.w};
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(si + TILE_BYTES + sw128_chunk(row, cg * 2 + q));
-            const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = 4 * q + e;
-              const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
-              const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[j]);
-              float x0 = __uint_as_float(dv[2 * j]) + (__low2float(r2) + __low2float(l2));
-              float x1 = __uint_as_float(dv[2 * j + 1]) + (__high2float(r2) + __high2float(l2));
-              if (BIAS) {
-                x0 += p.bias_d[cg * 16 + 2 * j];
-                x1 += p.bias_d[cg * 16 + 2 * j + 1];
-              }
-              if (!valid_prev) { x0 = 0.f; x1 = 0.f; }
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-              ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
-              pl[j] = pack_bf16(x0 - __low2float(h2), x1 - __high2float(h2));
-            }
-          }
-          if (DIRECT) {
-            if (tau_prev < p.L) {      // x_{i+1} hi / lo': read by the very next launch
-              const int64_t e = ((int64_t)b_prev * p.L + tau_prev) * 64 + cg * 16;
-              stg32(g.x_out + e, p.pol_last, ph);
-              stg32(g.lo_out + e, p.pol_last, pl);
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const uint32_t o = sw128_chunk(row, cg * 2 + q);
-              *reinterpret_cast<uint4*>(sm + Fwd2Smem::XO + o) = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-              *reinterpret_cast<uint4*>(lot + o) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);   // in place
-            }
-            fence_proxy_async_smem();
-          }
-        }
-        tc_fence_before();
-        epi16_bar_sync();              // every thread has finished reading tile it - 1's dense accumulator and residual tile
-        if (tid == 0) {
-          if (dense) mbar_arrive(&dense_empty[pb]);
-          mbar_arrive(&in_empty[st_prev]);
-          if (DIRECT) {
-            if (dense) mbar_arrive(&lo_empty[pb]);
-          } else {
-            mbar_arrive(&out_ready);
-          }
-        }
-      }
-      valid_prev = valid;
-      tau_prev = tau_cur;
-      b_prev = b_cur;
-      st_prev = it % 3;
-      tl += (int)gridDim.x;
-      while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem);
-}
-
-}  // namespace
-
 int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, const BlockFwdPtrs& g, int n_batches, cudaStream_t s) {
   const int smem = Fwd2Smem::TOTAL + 1024;
   const int n_items = n_batches * p.tiles_per_batch;
@@ -607,32 +313,6 @@ int launch_block_fwd2(const BlockFwdMaps& m, const BlockFwdParams& p, const Bloc
   if (configured[slot] == nullptr) {
     WN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[slot] = reinterpret_cast<const void*>(k);
-  }
-  static const bool fwd2_env = [] { const char* e = getenv("WN_FWD2"); return e && e[0] == '1'; }();
-  if (!trace && !fwd2_env) {      // default: pipelined epilogues + store warp
-    // variant: 0 = in order + TMA stores by the store warp, 1 = pipelined epilogues + TMA stores, 2 = pipelined + direct stores (default),
-    //          3 = in order + direct stores
-    static const int variant = [] { const char* e = getenv("WN_FWD3"); return e ? atoi(e) : 2; }();
-    auto pick = [&](auto kff, auto kft, auto ktf, auto ktt) { return p.cond ? (bias ? ktt : kft) : (bias ? ktf : kff); };
-    auto k3 = variant == 0   ? pick(block_fwd3_kernel<false, false, false, false>, block_fwd3_kernel<false, true, false, false>,
-                                    block_fwd3_kernel<true, false, false, false>, block_fwd3_kernel<true, true, false, false>)
-              : variant == 1 ? pick(block_fwd3_kernel<false, false, true, false>, block_fwd3_kernel<false, true, true, false>,
-                                    block_fwd3_kernel<true, false, true, false>, block_fwd3_kernel<true, true, true, false>)
-              : variant == 3 ? pick(block_fwd3_kernel<false, false, false, true>, block_fwd3_kernel<false, true, false, true>,
-                                    block_fwd3_kernel<true, false, false, true>, block_fwd3_kernel<true, true, false, true>)
-                             : pick(block_fwd3_kernel<false, false, true, true>, block_fwd3_kernel<false, true, true, true>,
-                                    block_fwd3_kernel<true, false, true, true>, block_fwd3_kernel<true, true, true, true>);
-    static const void* configured3[4] = {};
-    const int slot3 = (p.cond ? 2 : 0) + (bias ? 1 : 0);
-    if (configured3[slot3] == nullptr) {
-      WN_CHECK_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      configured3[slot3] = reinterpret_cast<const void*>(k3);
-    }
-    WN_PROF("block_fwd", s);
-    WN_CHECK_CUDA(launch_pdl(k3, dim3((unsigned)std::min(n_items, g_sm_count)), dim3(608), smem, s, m.x, m.w0, m.w1, m.wd, m.xo, m.loo, m.z, m.lo, p,
-                             g, n_batches));
-    WN_CHECK_LAUNCH();
-    return WN_OK;
   }
   WN_PROF("block_fwd", s);
   WN_CHECK_CUDA(launch_pdl(k, dim3((unsigned)std::min(n_items, g_sm_count)), dim3(576), smem, s, m.x, m.w0, m.w1, m.wd, m.xo, m.loo, m.z, m.lo, p, g,
