@@ -4,8 +4,11 @@
 // against 384 bytes of fp32 activations - the kernels are bound by HBM and launch latency, not by the tensor pipe, and the
 // register-chained form needs no shared-memory round trip between the two products of a layer.
 #include "ae_fast.cuh"
+#include "tc05.cuh"
 
 namespace wn {
+using tc::pdl_launch_dependents;
+using tc::pdl_wait;
 namespace {
 
 constexpr int C = kEncC;
@@ -83,6 +86,8 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) enc_fwd_layer_kernel(const flo
     }
     wfrag[slot][ln] = v;
   }
+  pdl_launch_dependents();      // (programmatic dependent launch: the weight gather above overlaps the previous layer's tail ...
+  pdl_wait();                   //  ... activations are touched only after the previous kernel has completed)
   __syncthreads();
   uint32_t wT[4][4][2], wD[2][4][2];
 #pragma unroll
@@ -169,6 +174,8 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) enc_bwd_layer_kernel(const flo
     }
     wfrag[slot][ln] = v;
   }
+  pdl_launch_dependents();
+  pdl_wait();
   __syncthreads();
   uint32_t wA[2][4][2], wB[4][4][2];
 #pragma unroll
@@ -512,7 +519,8 @@ int launch_enc_fwd_layer(const float* x, float* T, float* x_out, const float* w_
   const int n_chunks = (int)ceil_div(L - s_out, 16);
   if (n_chunks <= 0) return WN_OK;
   WN_PROF("enc_fwd_layer", s);
-  enc_fwd_layer_kernel<<<dim3((unsigned)chunk_grid(n_chunks, B), (unsigned)B), 32 * ENC_WARPS, 0, s>>>(x, T, x_out, w_dil, w_dense, L, d, s_out, n_chunks);
+  WN_CHECK_CUDA(launch_pdl(enc_fwd_layer_kernel, dim3((unsigned)chunk_grid(n_chunks, B), (unsigned)B), dim3(32 * ENC_WARPS), 0, s, x, T, x_out, w_dil,
+                           w_dense, L, d, s_out, n_chunks));
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -521,8 +529,8 @@ int launch_enc_bwd_layer(const float* gx_next, const float* T, const float* x, f
   const int n_chunks = (int)ceil_div(L - (s_out - d), 16);
   if (n_chunks <= 0) return WN_OK;
   WN_PROF("enc_bwd_layer", s);
-  enc_bwd_layer_kernel<<<dim3((unsigned)chunk_grid(n_chunks, B), (unsigned)B), 32 * ENC_WARPS, 0, s>>>(gx_next, T, x, gx, dT, w_dil, w_dense, L, d, s_out,
-                                                                                          n_chunks);
+  WN_CHECK_CUDA(launch_pdl(enc_bwd_layer_kernel, dim3((unsigned)chunk_grid(n_chunks, B), (unsigned)B), dim3(32 * ENC_WARPS), 0, s, gx_next, T, x, gx, dT,
+                           w_dil, w_dense, L, d, s_out, n_chunks));
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
