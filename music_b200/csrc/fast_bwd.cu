@@ -972,9 +972,9 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const uint32_t o = sw128_chunk(row, cg * 2 + q);
-        *reinterpret_cast<uint4*>(sm + Bwd3Smem::Z + o) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DF + o) = make_uint4(pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + Bwd3Smem::DG + o) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
+        sts128(smem_u32(sm + Bwd3Smem::Z) + o, pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
+        sts128(smem_u32(sm + Bwd3Smem::DF) + o, pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
+        sts128(smem_u32(sm + Bwd3Smem::DG) + o, pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
       }
       fence_proxy_async_smem();
       epi8_bar_sync();
@@ -1356,12 +1356,12 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const uint32_t o0 = sw128_chunk(row, h * 4 + q), o1 = sw128_chunk(row, h * 4 + 2 + q);
-        *reinterpret_cast<uint4*>(sm + Bwd5Smem::Z + o0) = make_uint4(keep[4 * q], keep[4 * q + 1], keep[4 * q + 2], keep[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + Bwd5Smem::DF + o0) = make_uint4(keep[8 + 4 * q], keep[9 + 4 * q], keep[10 + 4 * q], keep[11 + 4 * q]);
-        *reinterpret_cast<uint4*>(sm + Bwd5Smem::DG + o0) = make_uint4(keep[16 + 4 * q], keep[17 + 4 * q], keep[18 + 4 * q], keep[19 + 4 * q]);
-        *reinterpret_cast<uint4*>(sm + Bwd5Smem::Z + o1) = make_uint4(pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + Bwd5Smem::DF + o1) = make_uint4(pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sm + Bwd5Smem::DG + o1) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
+        sts128(smem_u32(sm + Bwd5Smem::Z) + o0, keep[4 * q], keep[4 * q + 1], keep[4 * q + 2], keep[4 * q + 3]);
+        sts128(smem_u32(sm + Bwd5Smem::DF) + o0, keep[8 + 4 * q], keep[9 + 4 * q], keep[10 + 4 * q], keep[11 + 4 * q]);
+        sts128(smem_u32(sm + Bwd5Smem::DG) + o0, keep[16 + 4 * q], keep[17 + 4 * q], keep[18 + 4 * q], keep[19 + 4 * q]);
+        sts128(smem_u32(sm + Bwd5Smem::Z) + o1, pz[4 * q], pz[4 * q + 1], pz[4 * q + 2], pz[4 * q + 3]);
+        sts128(smem_u32(sm + Bwd5Smem::DF) + o1, pf[4 * q], pf[4 * q + 1], pf[4 * q + 2], pf[4 * q + 3]);
+        sts128(smem_u32(sm + Bwd5Smem::DG) + o1, pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
       }
       fence_proxy_async_smem();
       group_bar();                           // the group's 8 warps together wrote the whole [128][64] tile of each of z, dF, dG
@@ -1380,7 +1380,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t o = sw128_chunk(row, h * 4 + q);
-            const uint4 a4 = *reinterpret_cast<const uint4*>(sa + o), q4v = *reinterpret_cast<const uint4*>(sa + TILE + o);
+            const uint4 a4 = lds128(smem_u32(sa) + o), q4v = lds128(smem_u32(sa + TILE) + o);
             const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, qw[4] = {q4v.x, q4v.y, q4v.z, q4v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -1442,8 +1442,8 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const uint32_t o0 = sw128_chunk(row, h * 4 + ps * 2), o1 = sw128_chunk(row, h * 4 + ps * 2 + 1);
         uint32_t aw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, qw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
         if (DENSE) {
-          const uint4 a0 = *reinterpret_cast<const uint4*>(sa + o0), a1 = *reinterpret_cast<const uint4*>(sa + o1);
-          const uint4 q0 = *reinterpret_cast<const uint4*>(sa + TILE + o0), q1 = *reinterpret_cast<const uint4*>(sa + TILE + o1);
+          const uint4 a0 = lds128(smem_u32(sa) + o0), a1 = lds128(smem_u32(sa) + o1);
+          const uint4 q0 = lds128(smem_u32(sa + TILE) + o0), q1 = lds128(smem_u32(sa + TILE) + o1);
           aw[0] = a0.x; aw[1] = a0.y; aw[2] = a0.z; aw[3] = a0.w; aw[4] = a1.x; aw[5] = a1.y; aw[6] = a1.z; aw[7] = a1.w;
           qw[0] = q0.x; qw[1] = q0.y; qw[2] = q0.z; qw[3] = q0.w; qw[4] = q1.x; qw[5] = q1.y; qw[6] = q1.z; qw[7] = q1.w;
         }
@@ -1461,8 +1461,8 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t o = sw128_chunk(row, h * 4 + q);
-        *reinterpret_cast<uint4*>(sa + o) = make_uint4(pa[4 * q], pa[4 * q + 1], pa[4 * q + 2], pa[4 * q + 3]);
-        *reinterpret_cast<uint4*>(sa + TILE + o) = make_uint4(pq[4 * q], pq[4 * q + 1], pq[4 * q + 2], pq[4 * q + 3]);
+        sts128(smem_u32(sa) + o, pa[4 * q], pa[4 * q + 1], pa[4 * q + 2], pa[4 * q + 3]);
+        sts128(smem_u32(sa + TILE) + o, pq[4 * q], pq[4 * q + 1], pq[4 * q + 2], pq[4 * q + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();

@@ -159,11 +159,12 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   } else {
     const int q4 = warp & 3, cg = warp >> 2;
     const int row = q4 * 32 + lane;
+    // (batch row, tile) of this CTA's next work item, stepped without a division per tile
+    int b = (int)blockIdx.x / p.tiles_per_batch, tl = (int)blockIdx.x % p.tiles_per_batch, st = 0;
     for (int it = 0; it < n_mine; ++it) {
-      const int item = blockIdx.x + it * gridDim.x;
-      const int st = it % 3, ab = it & 1;
+      const int ab = it & 1;
       const uint32_t ph2 = (it >> 1) & 1;
-      const int b = item / p.tiles_per_batch, tau0 = (p.tile0 + item % p.tiles_per_batch) * 128;
+      const int tau0 = (p.tile0 + tl) * 128;
       const int tau = tau0 + row;
       const bool valid = (tau >= p.s_out) && (tau < p.L);
       const uint32_t lane_addr = tmem_addr(tmem, q4 * 32, ab * 192);
@@ -215,8 +216,8 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         pz[j] = valid ? pack_bf16(z0, z1) : 0u;
       }
       const uint4 zv0 = make_uint4(pz[0], pz[1], pz[2], pz[3]), zv1 = make_uint4(pz[4], pz[5], pz[6], pz[7]);
-      *reinterpret_cast<uint4*>(zt + sw128_chunk(row, cg * 2)) = zv0;
-      *reinterpret_cast<uint4*>(zt + sw128_chunk(row, cg * 2 + 1)) = zv1;
+      sts128(smem_u32(zt) + sw128_chunk(row, cg * 2), zv0.x, zv0.y, zv0.z, zv0.w);
+      sts128(smem_u32(zt) + sw128_chunk(row, cg * 2 + 1), zv1.x, zv1.y, zv1.z, zv1.w);
       if (rec) ts[2] = clock64();
       fence_proxy_async_smem();
       tc_fence_before();
@@ -239,12 +240,12 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tmem_ld16(lane_addr + 128 + cg * 16, dv);
         tmem_ld_wait();
         uint32_t ph[8], pl[8];
-        const uint4 lv0 = *reinterpret_cast<const uint4*>(lot + sw128_chunk(row, cg * 2));
-        const uint4 lv1 = *reinterpret_cast<const uint4*>(lot + sw128_chunk(row, cg * 2 + 1));
+        const uint4 lv0 = lds128(smem_u32(lot) + sw128_chunk(row, cg * 2));
+        const uint4 lv1 = lds128(smem_u32(lot) + sw128_chunk(row, cg * 2 + 1));
         const uint32_t ll[8] = {lv0.x, lv0.y, lv0.z, lv0.w, lv1.x, lv1.y, lv1.z, lv1.w};
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const uint4 rv = *reinterpret_cast<const uint4*>(si + TILE_BYTES + sw128_chunk(row, cg * 2 + q));
+          const uint4 rv = lds128(smem_u32(si) + TILE_BYTES + sw128_chunk(row, cg * 2 + q));
           const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -266,8 +267,8 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const uint32_t o = sw128_chunk(row, cg * 2 + q);
-          *reinterpret_cast<uint4*>(sm + Fwd2Smem::XO + o) = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-          *reinterpret_cast<uint4*>(lot + o) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);   // in place
+          sts128(sbase + Fwd2Smem::XO + o, ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+          sts128(smem_u32(lot) + o, pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);   // in place
         }
         fence_proxy_async_smem();
       }
@@ -287,6 +288,9 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tma_store_commit();          // not waited for here: checked before the staging tiles are rewritten (above)
       }
       if (rec) ts[7] = clock64();
+      st = st == 2 ? 0 : st + 1;
+      tl += (int)gridDim.x;
+      while (tl >= p.tiles_per_batch) { tl -= p.tiles_per_batch; ++b; }
     }
     if (tid == 0) tma_store_wait_read();
   }

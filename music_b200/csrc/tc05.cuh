@@ -221,6 +221,16 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col) {
   return (uint32_t)row * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)row & 7u)) << 4) + (((uint32_t)col & 7u) << 1);
 }
 // byte offset of 16-byte chunk `chunk` (8 bf16) of row `row`
+// 16-byte shared-memory accesses by 32-bit shared-space address.  (Through a generic pointer derived from the dynamic shared-memory
+// base the compiler emits ST.E / LD.E with 64-bit address arithmetic, and a MEMBAR.ALL.CTA in front of every proxy fence.)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t sw128_chunk(int row, int chunk) {
   return (uint32_t)row * 128u + ((((uint32_t)chunk) ^ ((uint32_t)row & 7u)) << 4);
 }
