@@ -160,11 +160,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t axw = reinterpret_cast<const uint32_t*>(&ax4[c * 4 + (j >> 2)])[j & 3];
             const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&axw);
             if (EPI == EPI_MASK) {
-              a0 = __low2float(x2) > 0.f ? a0 : 0.f;
-              a1 = __high2float(x2) > 0.f ? a1 : 0.f;
+              a0 = bf16lo(x2) > 0.f ? a0 : 0.f;
+              a1 = bf16hi(x2) > 0.f ? a1 : 0.f;
             } else if (EPI == EPI_ADD) {
-              a0 += __low2float(x2);
-              a1 += __high2float(x2);
+              a0 += bf16lo(x2);
+              a1 += bf16hi(x2);
             }
             packed[c * 16 + j] = valid ? pack_bf16(a0, a1) : 0u;
           }
@@ -242,11 +242,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
             const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&ax[j]);
             if (EPI == EPI_MASK) {
-              a0 = __low2float(x2) > 0.f ? a0 : 0.f;
-              a1 = __high2float(x2) > 0.f ? a1 : 0.f;
+              a0 = bf16lo(x2) > 0.f ? a0 : 0.f;
+              a1 = bf16hi(x2) > 0.f ? a1 : 0.f;
             } else if (EPI == EPI_ADD) {
-              a0 += __low2float(x2);
-              a1 += __high2float(x2);
+              a0 += bf16lo(x2);
+              a1 += bf16hi(x2);
             } else if (EPI == EPI_RELU || EPI == EPI_RELU_BIAS || EPI == EPI_RELU_COND) {
               if (EPI == EPI_RELU_BIAS) {
                 a0 += p.bias[nt * NT + c * 32 + 2 * j];
@@ -426,11 +426,11 @@ gemm_nt_resb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t axw = reinterpret_cast<const uint32_t*>(&ax4[c * 4 + (e >> 2)])[e & 3];
             const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&axw);
             if (EPI == EPI_MASK) {
-              a0 = __low2float(x2) > 0.f ? a0 : 0.f;
-              a1 = __high2float(x2) > 0.f ? a1 : 0.f;
+              a0 = bf16lo(x2) > 0.f ? a0 : 0.f;
+              a1 = bf16hi(x2) > 0.f ? a1 : 0.f;
             } else if (EPI == EPI_ADD) {
-              a0 += __low2float(x2);
-              a1 += __high2float(x2);
+              a0 += bf16lo(x2);
+              a1 += bf16hi(x2);
             }
             packed[c * 16 + e] = valid ? pack_bf16(a0, a1) : 0u;
           }
@@ -951,7 +951,7 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
-        float dz0 = __low2float(s2), dz1 = __high2float(s2);
+        float dz0 = bf16lo(s2), dz1 = bf16hi(s2);
         if (DENSE) {
           dz0 += __uint_as_float(dzv[2 * j]);
           dz1 += __uint_as_float(dzv[2 * j + 1]);
@@ -1297,7 +1297,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&zs[j]);
-          float dz0 = __low2float(s2), dz1 = __high2float(s2);
+          float dz0 = bf16lo(s2), dz1 = bf16hi(s2);
           if (DENSE) {
             dz0 += __uint_as_float(dzv[2 * j]);
             dz1 += __uint_as_float(dzv[2 * j + 1]);
@@ -1326,7 +1326,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&dzp[ps * 8 + j]);
-          const float dz[2] = {__low2float(d2), __high2float(d2)};
+          const float dz[2] = {bf16lo(d2), bf16hi(d2)};
           float zo[2], df[2], dg[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -1386,8 +1386,8 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             for (int j = 0; j < 4; ++j) {
               const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
               const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&qw[j]);
-              sum[q * 8 + 2 * j] = __low2float(a2) + __low2float(q2);
-              sum[q * 8 + 2 * j + 1] = __high2float(a2) + __high2float(q2);
+              sum[q * 8 + 2 * j] = bf16lo(a2) + bf16lo(q2);
+              sum[q * 8 + 2 * j + 1] = bf16hi(a2) + bf16hi(q2);
             }
           }
           __syncwarp();
@@ -1452,7 +1452,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int j = 0; j < 8; ++j) {
           const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
           const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&qw[j]);
-          const float s0 = __low2float(a2) + __low2float(q2), s1 = __high2float(a2) + __high2float(q2);
+          const float s0 = bf16lo(a2) + bf16lo(q2), s1 = bf16hi(a2) + bf16hi(q2);
           pa[ps * 8 + j] = valid ? pack_bf16(s0 + __uint_as_float(p1[2 * j]), s1 + __uint_as_float(p1[2 * j + 1])) : 0u;
           pq[ps * 8 + j] = valid ? pack_bf16(__uint_as_float(p0[2 * j]), __uint_as_float(p0[2 * j + 1])) : 0u;
         }
@@ -1525,7 +1525,7 @@ __global__ void __launch_bounds__(256) combine_dx0_kernel(const __nv_bfloat16* _
     for (int j = 0; j < 4; ++j) {
       const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
       const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&qw[j]);
-      o[j] = pack_bf16(__low2float(a2) + __low2float(q2), __high2float(a2) + __high2float(q2));
+      o[j] = pack_bf16(bf16lo(a2) + bf16lo(q2), bf16hi(a2) + bf16hi(q2));
     }
     *reinterpret_cast<uint4*>(out + ((int64_t)b * L + tau) * 64 + c) = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -1662,15 +1662,15 @@ __global__ void __launch_bounds__(64) frame_sum_bf16_kernel(const __nv_bfloat16*
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&v[u]);
-      a0 += __low2float(h);
-      a1 += __high2float(h);
+      a0 += bf16lo(h);
+      a1 += bf16hi(h);
     }
   }
   for (; j < j1; ++j) {
     const uint32_t v = __ldg(base + (first + (int64_t)j * step) * pitch2);
     const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&v);
-    a0 += __low2float(h);
-    a1 += __high2float(h);
+    a0 += bf16lo(h);
+    a1 += bf16hi(h);
   }
   if (j1 <= j0) return;
 #pragma unroll

@@ -250,18 +250,21 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = 4 * q + e;
-            const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
-            const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[j]);
-            float x0 = __uint_as_float(dv[2 * j]) + (__low2float(r2) + __low2float(l2));
-            float x1 = __uint_as_float(dv[2 * j + 1]) + (__high2float(r2) + __high2float(l2));
+            float x0 = __uint_as_float(dv[2 * j]) + (bf16lo(rr[e]) + bf16lo(ll[j]));
+            float x1 = __uint_as_float(dv[2 * j + 1]) + (bf16hi(rr[e]) + bf16hi(ll[j]));
             if (BIAS) {
               x0 += p.bias_d[cg * 16 + 2 * j];
               x1 += p.bias_d[cg * 16 + 2 * j + 1];
             }
-            if (!valid) { x0 = 0.f; x1 = 0.f; }
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-            ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
-            pl[j] = pack_bf16(x0 - __low2float(h2), x1 - __high2float(h2));
+            const uint32_t h = pack_bf16(x0, x1);
+            ph[j] = h;
+            pl[j] = pack_bf16(x0 - bf16lo(h), x1 - bf16hi(h));
+          }
+        }
+        if (__any_sync(0xffffffffu, !valid)) {      // rows below the layer's valid start are stored as zeros (first tiles only)
+          if (!valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ph[j] = 0u; pl[j] = 0u; }
           }
         }
 #pragma unroll

@@ -239,6 +239,11 @@ __device__ __forceinline__ uint32_t sw128_chunk(int row, int chunk) {
 // every frame is held for len / frames steps when that divides, otherwise the encoding is tiled along time
 __device__ __forceinline__ int cond_frame(int tl, int len, int frames) { return (len % frames == 0) ? tl / (len / frames) : tl % frames; }
 
+// the two bf16 halves of a packed word as fp32, one integer instruction each (__high2float compiles to PRMT + shift)
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ float bf16lo(const __nv_bfloat162& v) { return bf16lo(*reinterpret_cast<const uint32_t*>(&v)); }
+__device__ __forceinline__ float bf16hi(const __nv_bfloat162& v) { return bf16hi(*reinterpret_cast<const uint32_t*>(&v)); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
