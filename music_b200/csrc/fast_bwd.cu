@@ -176,7 +176,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         uint8_t* ot = sm + Cfg::OUT_OFF;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(ot + sw128_chunk(tid, q)) = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+          sts128(smem_u32(ot) + sw128_chunk(tid, q), packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
         fence_proxy_async_smem();
         epi_bar_sync();
         if (tid == 0) {
@@ -268,7 +268,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             uint4 val = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
             const int qq = (c & 1) * 4 + q;      // 16-byte chunk of this thread's row inside the 64-column staging tile
             const uint32_t o = p.out_tiled ? (uint32_t)(((((tid >> 5) * 4 + (qq >> 1)) * 32 + (tid & 31)) << 5) + ((qq & 1) << 4)) : sw128_chunk(tid, qq);
-            *reinterpret_cast<uint4*>(ot + o) = val;
+            sts128(smem_u32(ot) + o, val.x, val.y, val.z, val.w);
           }
         }
         fence_proxy_async_smem();
@@ -440,7 +440,7 @@ gemm_nt_resb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int q = 0; q < 8; ++q) {     // 16-byte chunk q of this thread's row: swizzled tile, or the tiled global layout's image
           const uint32_t o = p.out_tiled ? (uint32_t)(((((tid >> 5) * 4 + (q >> 1)) * 32 + (tid & 31)) << 5) + ((q & 1) << 4)) : sw128_chunk(tid, q);
-          *reinterpret_cast<uint4*>(ot + o) = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+          sts128(smem_u32(ot) + o, packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
         }
         fence_proxy_async_smem();
         if (j == n_otiles - 1) tc_fence_before();
@@ -1272,6 +1272,7 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int tau0 = (p.tile0 + tl) * 128;
       const int tau = tau0 + row;
       const bool valid = tau >= p.s_out && tau < p.L;
+      const bool any_invalid = __any_sync(0xffffffffu, !valid);
       const bool has_zs = tau0 >= p.tw_al && tau < p.L;
       const __nv_bfloat16* zsp =
           p.dzs + (((((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + ((tau0 - p.tw_al) >> 5) + q4) * 4 + h * 2) * 32 + lane) << 4);
@@ -1336,9 +1337,13 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             df[e] = dz[e] * (sg * (1.f - t * t));
             dg[e] = dz[e] * (zo[e] * (1.f - sg));
           }
-          pz[j] = valid ? pack_bf16(zo[0], zo[1]) : 0u;
-          pf[j] = valid ? pack_bf16(df[0], df[1]) : 0u;
-          pg[j] = valid ? pack_bf16(dg[0], dg[1]) : 0u;
+          pz[j] = pack_bf16(zo[0], zo[1]);
+          pf[j] = pack_bf16(df[0], df[1]);
+          pg[j] = pack_bf16(dg[0], dg[1]);
+        }
+        if (any_invalid && !valid) {      // rows outside the layer's valid range are stored as zeros (boundary tiles only)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { pz[j] = 0u; pf[j] = 0u; pg[j] = 0u; }
         }
         if (ps == 0) {
 #pragma unroll
@@ -1411,8 +1416,12 @@ block_bwd6_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            pa[j] = valid ? pack_bf16(sum[ps * 16 + 2 * j] + __uint_as_float(p1[2 * j]), sum[ps * 16 + 2 * j + 1] + __uint_as_float(p1[2 * j + 1])) : 0u;
-            pq[j] = valid ? pack_bf16(__uint_as_float(p0[2 * j]), __uint_as_float(p0[2 * j + 1])) : 0u;
+            pa[j] = pack_bf16(sum[ps * 16 + 2 * j] + __uint_as_float(p1[2 * j]), sum[ps * 16 + 2 * j + 1] + __uint_as_float(p1[2 * j + 1]));
+            pq[j] = pack_bf16(__uint_as_float(p0[2 * j]), __uint_as_float(p0[2 * j + 1]));
+          }
+          if (any_invalid && !valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { pa[j] = 0u; pq[j] = 0u; }
           }
           if (in_range) {
             stg32(arow + ps * 16, p.pol_last, pa);

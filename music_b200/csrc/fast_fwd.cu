@@ -469,7 +469,7 @@ skip_head_kernel(const __grid_constant__ CUtensorMap tm_zcat, const __grid_const
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 val = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-            *reinterpret_cast<uint4*>(ht + sw128_chunk(row, (c & 1) * 4 + q)) = val;
+            sts128(smem_u32(ht) + sw128_chunk(row, (c & 1) * 4 + q), val.x, val.y, val.z, val.w);
           }
         }
         fence_proxy_async_smem();

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_fast.py tests/test_gpu_benchshape.py tests/test_gpu_ae.py -m gpu -q --timeout 400 -x 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_gpu_fast.py tests/test_gpu_benchshape.py tests/test_gpu_ae.py tests/test_gpu_fullsize.py -m gpu -q --timeout 400 -x 2>&1 | tail -1
 B="--steps 20 --warmup 3 --no-cpu-baseline --gen-steps 0 --no-ae --no-incumbent --no-cfg1 --no-dense-e2e"
 timeout 200 python bench.py $B > gpurun_out/r2c27.json 2> gpurun_out/r2c27.err
 python - <<'PY'
