@@ -87,7 +87,7 @@ struct Model {
   // are in the kernels' padded layout and must outlive the calls.  Conv biases of the conditioned layers are folded into them.
   const float* cond_fg = nullptr;     // (B, frames, n_layers, 128) fp32, [filter 64 | gate 64]: added to the [f|g] pre-activations
   const void* cond_fg16 = nullptr;    // the same table in the block kernels' per-thread order (launch_cond_pack16): per (b, frame, layer)
-                                      // 4 column groups x {16 filter | 16 gate} fp32 values = 512 bytes, one 128-byte line per epilogue thread
+                                      // [b][layer][column group 4][chunk 4][frame][8 floats] (cond_pack16_kernel): a warp's loads are sector-contiguous
   const float* cond_head = nullptr;   // (B, frames, S) fp32: added to post_process_1's output before its ReLU
   float* cond_fg_grad = nullptr;      // backward: sums of d[f|g] / d(head pre-activation) over the rows of each frame, same shapes
   float* cond_head_grad = nullptr;    //           (must be zero-filled by the caller)

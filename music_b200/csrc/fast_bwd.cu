@@ -897,12 +897,12 @@ block_bwd3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         ldg_stream32(p.dzs + (((((int64_t)(p.dzs_lb0 + b) * p.dzs_nblk + ((tau0 - p.tw_al) >> 5) + q4) * 4 + cg) * 32 + lane) << 4), p.pol_first, zs);
       uint32_t cw[32];      // this row's 16 filter + 16 gate conditioning values (fp32, one 128-byte line): four 256-bit loads in flight during the wait
       if (COND) {
-        const uint4* cp16 = p.cond16 + ((((int64_t)b * p.cond_frames + (valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0)) *
-                                         p.cond_layers + p.cond_layer) * 4 + cg) * 8;
+        const int fr = valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0;
+        const uint4* cp16 = p.cond16 + (((((int64_t)b * p.cond_layers + p.cond_layer) * 4 + cg) * 4) * p.cond_frames + fr) * 2;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t t8[8];
-          ldg_stream32(cp16 + 2 * q, 0, t8);
+          ldg_stream32(cp16 + (int64_t)q * p.cond_frames * 2, 0, t8);
 #pragma unroll
           for (int k = 0; k < 8; ++k) cw[8 * q + k] = t8[k];
         }
@@ -1710,12 +1710,21 @@ __global__ void cond_table_kernel(const float* __restrict__ raw, const float* __
     out[row * out_stride + c] = v;
   }
 }
-// table rows [128] = [filter 64 | gate 64]  ->  rows in the block kernels' per-thread order [column group 4][f16 | g16] (fp32)
-__global__ void cond_pack16_kernel(const float* __restrict__ tab, float* __restrict__ out, int64_t n_rows) {
+// table rows [128] = [filter 64 | gate 64] per (b, frame, layer)  ->  the block kernels' load order
+//   out[b][layer][column group 4][chunk 4][frame][8 floats],   chunk q = floats [8q, 8q + 8) of a thread's {16 filter | 16 gate} values
+// A warp of the epilogue holds 32 consecutive rows = (mostly) consecutive frames of ONE (layer, column group): with this order its
+// 256-bit load of chunk q touches 32 consecutive 32-byte sectors = 8 lines.  (Frame-major rows - one 128-byte line per thread -
+// cost 32 lines per request and ~10 us per launch at the autoencoder's shape.)
+__global__ void cond_pack16_kernel(const float* __restrict__ tab, float* __restrict__ out, int64_t n_rows, int frames, int layers) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_rows * 128; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = e >> 7;
-    const int o = (int)(e & 127), cg = o >> 5, w = o & 31;
-    out[e] = tab[row * 128 + (w < 16 ? cg * 16 + w : 64 + cg * 16 + (w - 16))];
+    const int64_t row = e >> 7;                                  // (b * frames + f) * layers + layer
+    const int o = (int)(e & 127), cg = o >> 5, w = o & 31, q = w >> 3, k = w & 7;
+    const int layer = (int)(row % layers);
+    const int64_t bf = row / layers;
+    const int f = (int)(bf % frames);
+    const int64_t b = bf / frames;
+    const float v = tab[row * 128 + (w < 16 ? cg * 16 + w : 64 + cg * 16 + (w - 16))];
+    out[(((((b * layers + layer) * 4 + cg) * 4 + q) * frames) + f) * 8 + k] = v;
   }
 }
 // out[row][c] = raw[row][c] + bias[c]   (head conditioning + connection_1 bias)
@@ -1900,8 +1909,9 @@ int launch_cond_table(const float* raw, const float* bias, int64_t n_rows, int d
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
-int launch_cond_pack16(const float* tab, void* out, int64_t n_rows, cudaStream_t s) {
-  cond_pack16_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_rows * 128, 256), 1184), 256, 0, s>>>(tab, reinterpret_cast<float*>(out), n_rows);
+int launch_cond_pack16(const float* tab, void* out, int64_t n_rows, int frames, int layers, cudaStream_t s) {
+  cond_pack16_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_rows * 128, 256), 1184), 256, 0, s>>>(tab, reinterpret_cast<float*>(out), n_rows, frames,
+                                                                                                      layers);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }

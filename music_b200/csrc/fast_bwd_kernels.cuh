@@ -98,7 +98,7 @@ struct BlockBwdParams {
   // batch b adds cond[((b * cond_frames + frame) * cond_layers + layer) * 128 + column], frame = the reference's rule on the local
   // index tau - s_out and length L - s_out.  null: none.
   const float* cond;
-  const uint4* cond16;      // copy in per-thread order: [(b frames + frame) layers + layer][column group 4][f16 | g16] fp32
+  const uint4* cond16;      // copy in load order: [b][layer][column group 4][chunk 4][frame][8 floats] (cond_pack16_kernel)
   int cond_frames, cond_layers, cond_layer;
   int trace;                    // WN_TS=1 (timing experiments): CTA 0 of block_bwd6 writes clock64 stamps per tile (wn_debug_ts)
 };

@@ -177,15 +177,16 @@ block_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       // ---- epilogue 1: gate -> z tile (smem, A operand of UMMA #2) and Zcat (global).  z tile `ab` was last read by
       //      UMMA #2 of tile it-2, whose completion (dense_full) every thread waited for in that tile's epilogue 2.
       // this row's conditioning values (autoencoder decoder; rows outside the valid range are masked anyway): 16 filter + 16 gate
-      // fp32 values, ONE 128-byte line per thread = four 256-bit loads issued BEFORE the wait for the accumulator.  (The row-major
+      // fp32 values as four 256-bit loads issued BEFORE the wait for the accumulator; the table is ordered so that a warp's 32 rows
+      // read 32 consecutive sectors per load (cond_pack16_kernel).  (The row-major
       // table read with scalar loads - 64 requests of 32 different lines each - cost ~8 us per tile, with 16-byte loads ~2.  A
       // bf16 table halves the requests again but adds its rounding to the pre-activations: gradient noise 0.14 -> 0.151.)
       uint32_t cw[32];
       if (COND) {
-        const uint4* cp16 = p.cond16 + ((((int64_t)b * p.cond_frames + (valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0)) *
-                                         p.cond_layers + p.cond_layer) * 4 + cg) * 8;
+        const int fr = valid ? cond_frame(tau - p.s_out, p.L - p.s_out, p.cond_frames) : 0;
+        const uint4* cp16 = p.cond16 + (((((int64_t)b * p.cond_layers + p.cond_layer) * 4 + cg) * 4) * p.cond_frames + fr) * 2;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) ldg_nc32(cp16 + 2 * q, cw + 8 * q);
+        for (int q = 0; q < 4; ++q) ldg_nc32(cp16 + (int64_t)q * p.cond_frames * 2, cw + 8 * q);
       }
       mbar_wait(&fg_full[ab], ph2);
       tc_fence_after();

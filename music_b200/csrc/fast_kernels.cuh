@@ -29,7 +29,7 @@ struct BlockFwdParams {
   const float* bias_fg;     // [128] or null
   const float* bias_d;      // [64] or null
   const float* cond;        // per-frame conditioning of [f|g] (see BlockBwdParams::cond) or null
-  const uint4* cond16;      // copy in per-thread order: [(b frames + frame) layers + layer][column group 4][f16 | g16] fp32
+  const uint4* cond16;      // copy in load order: [b][layer][column group 4][chunk 4][frame][8 floats] (cond_pack16_kernel)
   int cond_frames, cond_layers, cond_layer;
   unsigned long long pol_first, pol_last;   // L2 eviction hints for tiles read for the last time / read by the next kernel (0: none)
   long long* ts;            // optional timestamp buffer (timing experiments): CTA 0 writes 8 clock64 values per tile

@@ -64,7 +64,7 @@ int launch_frame_sum_bf16(const void* src, int64_t rows_per_batch, int pitch, in
                           int out_pitch, int dd, cudaStream_t s);
 int launch_cond_table(const float* raw, const float* bias, int64_t n_rows, int dd, float* out, int64_t out_stride, cudaStream_t s);
 // fp32 table rows of 128 ([filter 64 | gate 64]) -> rows in the block kernels' per-thread order (Model::cond_fg16)
-int launch_cond_pack16(const float* tab, void* out, int64_t n_rows, cudaStream_t s);
+int launch_cond_pack16(const float* tab, void* out, int64_t n_rows, int frames, int layers, cudaStream_t s);
 int launch_add_bias_rows(const float* raw, const float* bias, int64_t n_rows, int C, float* out, cudaStream_t s);
 struct SkipHeadMaps;
 struct SkipHeadParams;
