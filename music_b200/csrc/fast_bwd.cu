@@ -1778,8 +1778,8 @@ int launch_colsum_bf16_split(const void* src, int B, int64_t rows_per_batch, int
 
 // environment switches of the backward (timing experiments; read once)
 struct BwdEnv {
-  bool nt_stream, bwd6, bwd6_tma, wgrad_side, l2hint_dx, scatter_simt;
-  int bwd6_worder;
+  bool nt_stream, bwd6, bwd6_tma, l2hint_dx, scatter_simt;
+  int bwd6_worder, wgrad_side;      // wgrad_side: 1 on, 0 off, -1 auto
 };
 static const BwdEnv& bwd_env() {
   static const BwdEnv e = [] {
@@ -1790,7 +1790,10 @@ static const BwdEnv& bwd_env() {
     r.bwd6 = !off("WN_BWD6");             // block_bwd6 (default): the dx GEMM fused into the block backward; WN_BWD6=0: block_bwd3 + dx GEMM
     r.bwd6_tma = on("WN_BWD6_TMA");       // A_i / Q_i staged in shared memory and written by TMA (the first version of block_bwd6)
     r.bwd6_worder = off("WN_BWD6_WORDER") ? 0 : 1;      // 1 (default): dW_fg, dW_dense, P - the stage releases first (2.33 vs 2.39 ms per step)
-    r.wgrad_side = !off("WN_WGRAD_SIDE");
+    // per-layer weight-gradient reductions on a side stream: on for conditioned models (their frame sums run there too); for the
+    // plain model ONE reduction after the last block kernel is ~1 % faster (same box: 5.25-5.28 vs 5.30-5.34 ms per step) - the
+    // reduction CTAs cannot co-reside with the 608-thread persistent block kernel and only delay the next launch
+    r.wgrad_side = on("WN_WGRAD_SIDE") ? 1 : (off("WN_WGRAD_SIDE") ? 0 : -1);
     r.l2hint_dx = on("WN_L2HINT_DX");
     r.scatter_simt = on("WN_SCATTER_SIMT");
     return r;
@@ -2135,7 +2138,7 @@ int fast_backward_impl(Model& m, const BwdMaps& M, int B, int L, const float* d_
   // ---- residual blocks, last to first
   // side stream for the per-layer reductions of the weight-gradient partial tiles (WN_WGRAD_SIDE=0: one reduction at the end)
   SideStream* side = nullptr;
-  if (env.wgrad_side) WN_PROPAGATE(side_stream(&side));
+  if (env.wgrad_side == 1 || (env.wgrad_side == -1 && m.cond_fg_grad != nullptr)) WN_PROPAGATE(side_stream(&side));
   WgradReduceArgs ra{};
   ra.filt0 = m.layers[0].filt.w; ra.gate0 = m.layers[0].gate.w; ra.dense0 = m.layers[0].dense.w;
   ra.layer_stride = N > 1 ? m.layers[1].filt.w - m.layers[0].filt.w : 0;

@@ -150,8 +150,12 @@ class Trainer:
     # event at that point (wn_backward_set_split) and its all-reduce runs on a second stream under the lower blocks' kernels.  Only
     # the lower bucket's exchange (and the slowest rank's skew) is left exposed after the last backward kernel.
     def _overlap_setup(self):
-        if self.dist is None or self.dist.get_world_size(self.group) == 1 or os.environ.get("WN_AR_OVERLAP", "1") == "0":
+        # opt-in (WN_AR_OVERLAP=1, set before the first backward): measured on 2 and 8 GPUs the two-bucket exchange is no faster than
+        # one all-reduce (the persistent block kernels leave NCCL no SM before they drain), and the per-layer reductions it needs
+        # on the side stream cost the single-GPU step ~1 %
+        if self.dist is None or self.dist.get_world_size(self.group) == 1 or os.environ.get("WN_AR_OVERLAP", "0") != "1":
             return False
+        os.environ.setdefault("WN_WGRAD_SIDE", "1")
         if self._comm_stream is None:
             e, lib = self.net.engine, L.load()
             n_layers = len(self.net.dilations)

@@ -13,6 +13,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 dil = [2 ** i for i in range(10)] * 3
 res = {}
+os.environ["WN_WGRAD_SIDE"] = "1"      # (read once by the library: the overlapped variant needs the per-layer reductions)
 for overlap in ("0", "1"):
     os.environ["WN_AR_OVERLAP"] = overlap
     torch.manual_seed(0)
