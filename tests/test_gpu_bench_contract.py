@@ -30,7 +30,7 @@ def test_bench_line_has_the_contract_keys():
     assert d["value"] > 1e6 and abs(d["value"] - 16 * 16000 / (d["ms_per_step"] * 1e-3)) < 1e-3 * d["value"]
     e = d["e2e"]
     assert e["unit"] == d["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
-    assert d["gpu_launches"] >= 100 * d["steps"]
+    assert d["gpu_launches"] >= 70 * d["steps"]      # (80 launches of this library per training step since the fused block backward)
     r = d["roofline"]
     assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["traffic"] is None or r["traffic"] > 0
