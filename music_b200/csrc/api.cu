@@ -426,6 +426,10 @@ extern "C" int wn_init(int device) {
   WN_CHECK_CUDA(cudaGetDeviceProperties(&p, device));
   WN_REQUIRE(p.major == 10, WN_ERR_UNSUPPORTED, "wn_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
              p.major, p.minor);
+  // one process drives one GPU (torchrun: one process per GPU): kernel attributes, side streams and tensor-map caches are set up once
+  // per process, so a second device in the same process is refused instead of failing later with an invalid-resource error
+  WN_REQUIRE(!g_inited || g_device == device, WN_ERR_UNSUPPORTED,
+             "wn_init: this process already drives cuda:%d; libwavenet_b200 serves one GPU per process (launch one process per GPU)", g_device);
   WN_CHECK_CUDA(cudaSetDevice(device));
   g_device = device;
   g_sm_count = p.multiProcessorCount;
