@@ -441,6 +441,12 @@ def bench_autoencoder(dev, steps=10, world=1, rank=0):
             ms_ = float(t[0])
         return ms_, float(loss_)
     ms, loss = timed(idx, target, steps)
+    # the same step replayed from one CUDA graph (AeTrainer.capture): ~300 launches = 4.1 ms of host time per eager step
+    graphed = None
+    if world == 1 and tr.capture(idx, target):
+        ms_g, loss_g = timed(idx, target, steps)
+        graphed = {"ms_per_step": ms_g, "samples_per_s": W / (ms_g * 1e-3), "tflops": W * 8.656e6 / (ms_g * 1e-3) / 1e12, "loss": loss_g}
+        tr.__dict__.pop("_graph", None)
     # the same step with 4 clips per GPU (the per-GPU batch is not fixed by configs[4]; one clip is 532 tiles per layer = 3.6 per SM)
     idx4 = torch.randint(0, 256, (4, L), generator=g).to(dev)
     ms4, _ = timed(idx4, idx4[:, net.receptive_field - 1:].contiguous(), max(3, steps // 2))
@@ -449,6 +455,7 @@ def bench_autoencoder(dev, steps=10, world=1, rank=0):
             "samples_per_s": world * W / (ms * 1e-3), "ms_per_step": ms, "dtype": "bf16" if net.mode == "bf16" else "f32",
             "loss": loss, "n_gpus": world, "steps": steps,
             "train_flops_per_sample": 8.656e6, "tflops": world * W * 8.656e6 / (ms * 1e-3) / 1e12,
+            "cuda_graph": graphed,
             "clips_per_gpu_4": {"ms_per_step": ms4, "samples_per_s": world * 4 * W / (ms4 * 1e-3),
                                 "tflops": world * 4 * W * 8.656e6 / (ms4 * 1e-3) / 1e12}}
 

@@ -143,6 +143,10 @@ int wn_loss_fwd_bwd(const float* d_logits, const int64_t* d_target /* (B,W) */, 
 /* ---- optimizers : get_optimizer, wavenet/train.py:28-42 (torch.optim defaults) --------- */
 int wn_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n, float lr,
                  float beta1, float beta2, float eps, int32_t step, void* stream);
+/* wn_adam_step with the step count kept in device memory: *d_step is incremented, then used for the bias corrections.  For steps replayed
+ * from a CUDA graph (a captured launch cannot carry a new host scalar); same arithmetic as wn_adam_step. */
+int wn_adam_step_dev(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n, float lr,
+                     float beta1, float beta2, float eps, int32_t* d_step, void* stream);
 int wn_sgd_step(float* d_params, const float* d_grads, float* d_momentum_buf, int64_t n, float lr,
                 float momentum, int32_t first_step, void* stream);
 int wn_rmsprop_step(float* d_params, const float* d_grads, float* d_square_avg, float* d_momentum_buf,

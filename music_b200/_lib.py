@@ -70,6 +70,7 @@ SIGNATURES = {
     "wn_loss_scratch_bytes": (C.c_int, [_i32, _i32, _psz]),
     "wn_loss_fwd_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _f, _p, _p, _p, _p]),
     "wn_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i32, _p]),
+    "wn_adam_step_dev": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _p, _p]),
     "wn_sgd_step": (C.c_int, [_p, _p, _p, _i64, _f, _f, _i32, _p]),
     "wn_rmsprop_step": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _p]),
     "wn_gen_state_bytes": (C.c_int, [_p, _i32, _i32, _psz]),

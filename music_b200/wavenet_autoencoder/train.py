@@ -197,11 +197,15 @@ class AeTrainer:
         if self.dist is not None:
             all_reduce_mean_(self.gflat, self.dist, self.group)
 
-    def apply(self):
+    def apply(self, device_step=None):
+        """Optimizer step on the flat vectors.  device_step: int32 device tensor holding the step count (CUDA-graph replay; Adam only)."""
         lib = L.load()
         self.step_count += 1
         n, s = self.flat.numel(), L.stream_ptr()
-        if self.kind == "adam":
+        if self.kind == "adam" and device_step is not None:
+            L.check(lib.wn_adam_step_dev(L.ptr(self.flat), L.ptr(self.gflat), L.ptr(self._buf("m")), L.ptr(self._buf("v")), n,
+                                         self.lr, 0.9, 0.999, 1e-8, L.ptr(device_step), s))
+        elif self.kind == "adam":
             L.check(lib.wn_adam_step(L.ptr(self.flat), L.ptr(self.gflat), L.ptr(self._buf("m")), L.ptr(self._buf("v")), n,
                                      self.lr, 0.9, 0.999, 1e-8, self.step_count, s))
         elif self.kind == "sgd":
@@ -212,6 +216,14 @@ class AeTrainer:
                                         self.lr, 0.99, 1e-8, self.momentum, s))
 
     def step(self, piece, target, cond_weights=None):
+        g = self.__dict__.get("_graph")
+        if g is not None and cond_weights is None and piece.shape == g["piece"].shape and piece.dtype == g["piece"].dtype \
+                and target.numel() == g["target"].numel():
+            g["piece"].copy_(piece, non_blocking=True)
+            g["target"].copy_(target.reshape(g["target"].shape), non_blocking=True)
+            g["graph"].replay()
+            self.step_count += 1
+            return g["loss"]
         loss = self.forward_backward(piece, target, cond_weights)
         self.all_reduce()
         self.apply()
@@ -221,3 +233,57 @@ class AeTrainer:
             p.grad = self.gflat[off:off + n].view(p.shape)
             off += n
         return loss
+
+    def capture(self, piece, target, warmup=2):
+        """Capture the whole step (forward, loss, backward, [all-reduce], optimizer) for batches of this shape into ONE CUDA graph; later
+        step() calls with the same shapes copy the batch into the graph's static buffers and replay it.  At one 64000-target clip per
+        GPU the eager step is ~300 launches = 4.1 ms of host time under a 5.2 ms device step; the replay takes the host out of the loop.
+        The optimizer state is left exactly as it was (the warm-up steps run on a snapshot that is restored); returns True, or False - with
+        the eager path untouched - when the capture is refused (e.g. by the collective library)."""
+        self._ensure_flat()
+        piece, target = piece.detach(), target.detach()
+        snap = {"flat": self.flat.clone(), "count": self.step_count,
+                "state": {k: v.clone() for k, v in self.state.items() if torch.is_tensor(v)}}
+        d_step = torch.tensor([self.step_count], dtype=torch.int32, device=self.flat.device)
+        st = {"piece": piece.clone(), "target": target.clone()}
+
+        def one():
+            loss = self.forward_backward(st["piece"], st["target"])
+            self.all_reduce()
+            self.apply(device_step=d_step if self.kind == "adam" else None)
+            return loss
+
+        def restore():
+            self.flat.copy_(snap["flat"])
+            for k, v in snap["state"].items():
+                self.state[k].copy_(v)
+            for k in list(self.state):
+                if torch.is_tensor(self.state[k]) and k not in snap["state"] and k != "loss_scratch":
+                    self.state[k].zero_()
+            self.step_count = snap["count"]
+            d_step.fill_(snap["count"])
+        try:
+            side = torch.cuda.Stream(self.flat.device)
+            side.wait_stream(torch.cuda.current_stream(self.flat.device))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    one()
+            torch.cuda.current_stream(self.flat.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["loss"] = one()
+            st["graph"] = graph
+        except Exception as e:          # capture refused: stay eager
+            import warnings
+            warnings.warn(f"music_b200: CUDA-graph capture of the training step failed ({e}); the step stays eager")
+            torch.cuda.synchronize()
+            restore()
+            return False
+        restore()
+        self.__dict__["_graph"] = st
+        off = 0
+        for p in self.net.parameters():
+            n = p.numel()
+            p.grad = self.gflat[off:off + n].view(p.shape)
+            off += n
+        return True

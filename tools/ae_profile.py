@@ -27,6 +27,17 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 print(f"mode {net.mode} B {B}: {ms:.3f} ms/step = {B * W / ms * 1e3:.3e} samples/s = {B * W * 8.656e6 / ms / 1e9:.1f} TFLOP/s, loss {float(loss):.5f}")
+if os.environ.get("GRAPH") == "1":
+    ok = tr.capture(idx, tgt)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        loss = tr.step(idx, tgt)
+    e1.record()
+    torch.cuda.synchronize()
+    msg = e0.elapsed_time(e1) / 20
+    print(f"captured={ok}: {msg:.3f} ms/step = {B * W * 8.656e6 / msg / 1e9:.1f} TFLOP/s, loss {float(loss):.5f}")
+    sys.exit(0)
 lib = L.load()
 lib.wn_profile_enable(1)
 tr.step(idx, tgt)
