@@ -280,6 +280,7 @@ class AeTrainer:
             restore()
             return False
         restore()
+        st["d_step"] = d_step               # the captured optimizer launch reads this tensor on every replay: it must outlive this call
         self.__dict__["_graph"] = st
         off = 0
         for p in self.net.parameters():

@@ -130,3 +130,34 @@ def test_optimizer_state_checkpoint_resumes_exactly(tmp_path):
     # (a trainer restarted WITHOUT its moments moves every weight by ~lr = 1e-3 on its first step; fp32 atomics in the causal layer's
     #  gradient leave run-to-run noise far below that)
     assert worst < 2e-5, worst
+
+
+def test_captured_step_equals_eager_step():
+    """Trainer.capture: the step replayed from one CUDA graph (weight pack, forward, loss, backward, Adam with a device-side step count)
+    reproduces the eager step on the deterministic bf16 path: same losses and parameters over 3 steps on two copies of a model, and the
+    capture's warm-up leaves parameters, moments and the step count as they were."""
+    import copy
+    from music_b200.wavenet.model import wavenet
+    from music_b200.wavenet import train as T
+    dil = [1, 2, 4, 8, 16, 32]
+    torch.manual_seed(4)
+    net_a = wavenet(2, dil, 64, 64, 256, 256, False, mode="bf16", parity="corrected").cuda()
+    net_b = copy.deepcopy(net_a)
+    rf = net_a.receptive_field
+    x1 = torch.randint(0, 256, (2, rf + 300)).cuda()
+    x2 = torch.randint(0, 256, (2, rf + 300)).cuda()
+    tr_a = T.Trainer(net_a, "adam", 1e-3, distributed=False)
+    tr_b = T.Trainer(net_b, "adam", 1e-3, distributed=False)
+    for tr in (tr_a, tr_b):
+        tr.step(x1[:, :-1].contiguous(), x1[:, rf:].contiguous())
+    before = {k: v.detach().clone() for k, v in net_b.state_dict().items()}
+    assert tr_b.capture(x1[:, :-1].contiguous(), x1[:, rf:].contiguous()) is True
+    assert tr_b.step_count == 1
+    for k, v in net_b.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    for x in (x2, x1, x2):
+        la = tr_a.step(x[:, :-1].contiguous(), x[:, rf:].contiguous())
+        lb = tr_b.step(x[:, :-1].contiguous(), x[:, rf:].contiguous())
+        assert abs(float(la) - float(lb)) < 1e-5, (float(la), float(lb))
+    worst = max(float((a - b).abs().max()) for (_, a), (_, b) in zip(net_a.state_dict().items(), net_b.state_dict().items()))
+    assert worst < 2e-5, worst
