@@ -383,6 +383,19 @@ def bench_cfg1(dev, cpu_seconds=6.0):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
+    # the same step replayed from one CUDA graph (Trainer.capture): one clip is 126 tiles per layer, the eager step is bound by the
+    # host's ~80 launches
+    ms_graph = None
+    if tr.capture(piece, tgt):
+        for _ in range(3):
+            tr.step(piece, tgt)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            loss_g = tr.step(piece, tgt)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_graph = e0.elapsed_time(e1) / n
     # CPU, same shape
     torch.set_num_threads(os.cpu_count())
     st = O.init_wavenet_state(DIL, 32, 32, 256, Q, False, seed=0)
@@ -398,7 +411,8 @@ def bench_cfg1(dev, cpu_seconds=6.0):
     return {"workload": "wavenet/train.py default shape: 30 layers (1..512 x3), 32 residual / 32 dilation / 256 skip ch, 1 clip of "
                         f"16000 samples (W = {W} targets), Adam",
             "gpu": {"samples_per_s": W / (ms * 1e-3), "ms_per_step": ms, "mode": net.mode, "loss": float(loss),
-                    "note": "tcgen05 kernels, channels zero-padded 32 -> 64; 1 clip = 126 tiles per layer < 148 SMs"},
+                    "note": "tcgen05 kernels, channels zero-padded 32 -> 64; 1 clip = 126 tiles per layer < 148 SMs",
+                    "cuda_graph": None if ms_graph is None else {"ms_per_step": ms_graph, "samples_per_s": W / (ms_graph * 1e-3)}},
             "cpu": {"samples_per_s": W / dt, "s_per_step": dt, "cores": os.cpu_count(), "kind": "port", "steps": k}}
 
 
