@@ -522,6 +522,9 @@ __device__ __forceinline__ void cp_wait_dyn(int n) {      // all but the newest 
 }
 }  // namespace pipe
 
+// HAS_BIAS / PUSH_OUT are compile-time: every block of the ring is a chain of ~400 dependent-latency instructions per warp, and the
+// run-time tests (and the predicated bias loads behind them) were a measurable part of it
+template <bool HAS_BIAS, bool PUSH_OUT>
 __global__ void __launch_bounds__(256, 1)
 gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __restrict__ first_note, const float* __restrict__ uniforms,
                 int64_t* __restrict__ out, float* __restrict__ logits_out) {
@@ -646,7 +649,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
           for (int e = tid; e < G * 64; e += 256) {      // causal layer: two embedding rows (fast_generate.py:111-116)
             const int s = e >> 6, r = e & 63;
             float v = wc[last[g][s] * 64 + r] + wc[(256 + note[g][s]) * 64 + r];
-            if (p.has_bias) v += p.bias_c[r];
+            if (HAS_BIAS) v += p.bias_c[r];
             xs[s][r] = v;
             xhs[s][r] = __float2half_rn(v);
           }
@@ -679,7 +682,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             const int ch = 8 * warp + n8;
             float c0[4], c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f}, c3[4] = {0.f, 0.f, 0.f, 0.f};
             {
-              const float bf = p.has_bias ? p.bias_fg[i * 128 + ch] : 0.f, bg = p.has_bias ? p.bias_fg[i * 128 + 64 + ch] : 0.f;
+              const float bf = HAS_BIAS ? p.bias_fg[i * 128 + ch] : 0.f, bg = HAS_BIAS ? p.bias_fg[i * 128 + 64 + ch] : 0.f;
               c0[0] = c0[1] = bf;
               c0[2] = c0[3] = bg;
             }
@@ -720,7 +723,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               float dn[4], dm[4] = {0.f, 0.f, 0.f, 0.f};
               dn[0] = xs[s0][chd]; dn[1] = xs[s1][chd]; dn[2] = xs[s0][chd + 8]; dn[3] = xs[s1][chd + 8];     // residual
               const float xi[4] = {dn[0], dn[1], dn[2], dn[3]};
-              if (p.has_bias) {
+              if (HAS_BIAS) {
                 const float b0 = p.bias_d[i * 64 + chd], b1 = p.bias_d[i * 64 + chd + 8];
                 dn[0] += b0; dn[1] += b0; dn[2] += b1; dn[3] += b1;
               }
@@ -752,7 +755,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               }
 #pragma unroll
               for (int kt = 0; kt < 4; ++kt) mma_f16(sk[0], w2w[li][4 + kt], bz[kt][0], bz[kt][1]);
-              const bool out_push = p.push == WN_PUSH_OUTPUT;                                     // fast_generate.py:128-129
+              constexpr bool out_push = PUSH_OUT;                                     // fast_generate.py:128-129
               if (s0 < n_act) { ring0[o0] = out_push ? dn[0] : xi[0]; ring0[o0 + 8] = out_push ? dn[2] : xi[2]; }
               if (s1 < n_act) { ring1[o1] = out_push ? dn[1] : xi[1]; ring1[o1 + 8] = out_push ? dn[3] : xi[3]; }
               GEN_TS(6 + 5 * li);
@@ -829,7 +832,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
         if (tid == 0 && step + 1 < p.n_steps) mbar_expect_tx(&skfull[g], SK_BYTES);
         for (int e = tid; e < G * 256; e += 256) {
           const int s = e >> 8, row = e & 255;
-          hh[0][s][row] = __float2half_rn(fmaxf(skin[g][s][row] + (p.has_bias ? p.bias_skip[row] : 0.f), 0.f));
+          hh[0][s][row] = __float2half_rn(fmaxf(skin[g][s][row] + (HAS_BIAS ? p.bias_skip[row] : 0.f), 0.f));
         }
         __syncthreads();
 #pragma unroll
@@ -841,7 +844,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             for (int r = 0; r < 4; ++r) {
               const int row = 16 * (2 * warp + j) + n8 + 8 * (r >> 1);
               const float* bias = which == 0 ? p.bias_p1 : p.bias_p2;
-              c[j][0][r] = p.has_bias ? bias[row] : 0.f;
+              c[j][0][r] = HAS_BIAS ? bias[row] : 0.f;
               c[j][1][r] = c[j][2][r] = c[j][3][r] = 0.f;
             }
           const __half* hr = &hh[which][n8][2 * q];
@@ -986,11 +989,15 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
     p.trace = ts_env ? 1 : 0;
     const int cs = (m.n_layers + p.lpc - 1) / p.lpc + 1;
     const int groups = (int)ceil_div(n_streams, G), n_clusters = (int)ceil_div(groups, NG);
-    static bool pipe_once = false;
-    if (!pipe_once) {
-      WN_CHECK_CUDA(cudaFuncSetAttribute(gen_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe::TOTAL));
-      WN_CHECK_CUDA(cudaFuncSetAttribute(gen_pipe_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      pipe_once = true;
+    const bool out_push = push == WN_PUSH_OUTPUT;
+    auto kp = m.use_bias ? (out_push ? gen_pipe_kernel<true, true> : gen_pipe_kernel<true, false>)
+                         : (out_push ? gen_pipe_kernel<false, true> : gen_pipe_kernel<false, false>);
+    static bool pipe_once[4] = {false, false, false, false};
+    const int ki = (m.use_bias ? 2 : 0) + (out_push ? 1 : 0);
+    if (!pipe_once[ki]) {
+      WN_CHECK_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe::TOTAL));
+      WN_CHECK_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      pipe_once[ki] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(cs * n_clusters)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = pipe::TOTAL; cfg.stream = s;
@@ -1004,13 +1011,13 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
     static int max_clusters[32] = {};
     if (max_clusters[cs] == 0) {
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, gen_pipe_kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = -1; }
+      if (cudaOccupancyMaxActiveClusters(&n, kp, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = -1; }
       max_clusters[cs] = n > 0 ? n : -1;
     }
     static const bool pipe_force = [] { const char* e = getenv("WN_GEN_PIPE"); return e && e[0] == '1'; }();
     if (pipe_force || n_clusters <= max_clusters[cs]) {
       WN_PROF("gen_pipe", s);
-      WN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gen_pipe_kernel, p, reinterpret_cast<char*>(d_state), d_first_note, d_uniforms, d_out, d_logits));
+      WN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kp, p, reinterpret_cast<char*>(d_state), d_first_note, d_uniforms, d_out, d_logits));
       WN_CHECK_LAUNCH();
       return WN_OK;
     }
