@@ -444,7 +444,7 @@ constexpr int NG = 8;
 __device__ long long g_gen_ts[16 * 64];
 #define GEN_TS(k)                                                                                   \
   do {                                                                                              \
-    if (p.trace && rank == 1 && cid == 0 && g == 0 && tid == 0 && step < 64) g_gen_ts[step * 16 + (k)] = clock64(); \
+    if (TRACE && rank == 1 && cid == 0 && g == 0 && tid == 0 && step < 64) g_gen_ts[step * 16 + (k)] = clock64(); \
   } while (0)
 namespace pipe {
 constexpr uint32_t X_BYTES = G * XS * 4, XH_BYTES = G * XH * 2, SK_BYTES = G * HS * 4;      // one group's x (fp32), x (fp16), skip sums
@@ -524,7 +524,7 @@ __device__ __forceinline__ void cp_wait_dyn(int n) {      // all but the newest 
 
 // HAS_BIAS / PUSH_OUT are compile-time: every block of the ring is a chain of ~400 dependent-latency instructions per warp, and the
 // run-time tests (and the predicated bias loads behind them) were a measurable part of it
-template <bool HAS_BIAS, bool PUSH_OUT>
+template <bool HAS_BIAS, bool PUSH_OUT, bool TRACE>
 __global__ void __launch_bounds__(256, 1)
 gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __restrict__ first_note, const float* __restrict__ uniforms,
                 int64_t* __restrict__ out, float* __restrict__ logits_out) {
@@ -625,6 +625,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
       __pipeline_commit();
     };
     for (int g = 0; g < ng; ++g) prefetch_taps(g, 0);
+    for (int g = ng; g < NG; ++g) __pipeline_commit();      // always NG commit groups per ring period: the wait below is a constant
     // remote addresses of the next CTA's slots (same offsets there)
     const uint32_t r_xin = map_to(sm_base + OFF_XIN, rank + 1), r_xhin = map_to(sm_base + OFF_XHIN, rank + 1);
     const uint32_t r_skin = map_to(sm_base + OFF_SKIN, rank + 1);
@@ -662,7 +663,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
           xhs = reinterpret_cast<__half (*)[G][XH]>(sm + OFF_XHIN)[g];
           sko = skin[g];
         }
-        cp_wait_dyn(ng - 1);                   // this group's taps (requested one ring period ago)
+        cp_wait<NG - 1>();                     // this group's taps (requested one ring period = NG commit groups ago)
         __syncthreads();
         GEN_TS(2);
         if (first && tid < G) last[g][tid] = note[g][tid];
@@ -798,8 +799,9 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
         else __pipeline_commit();               // (keeps the group accounting of cp_wait_dyn uniform)
         GEN_TS(14);
       }
+      for (int g = ng; g < NG; ++g) __pipeline_commit();
     }
-    cp_wait_dyn(0);
+    cp_wait<0>();
     if (tid == 0) bulk_wait_read_0();
     if (first) {
       __syncthreads();
@@ -985,13 +987,15 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
     // weights-stationary cluster pipeline: ceil(N / 2) block CTAs + the head CTA per cluster, 8 groups of 8 streams per cluster
     static const int lpc_env = [] { const char* e = getenv("WN_GEN_LPC"); return e && e[0] == '1' ? 1 : 2; }();
     p.lpc = (lpc_env == 1 && m.n_layers <= 15) ? 1 : 2;
-    static const bool ts_env = getenv("WN_TS") != nullptr;
-    p.trace = ts_env ? 1 : 0;
+    p.trace = 0;
     const int cs = (m.n_layers + p.lpc - 1) / p.lpc + 1;
     const int groups = (int)ceil_div(n_streams, G), n_clusters = (int)ceil_div(groups, NG);
     const bool out_push = push == WN_PUSH_OUTPUT;
-    auto kp = m.use_bias ? (out_push ? gen_pipe_kernel<true, true> : gen_pipe_kernel<true, false>)
-                         : (out_push ? gen_pipe_kernel<false, true> : gen_pipe_kernel<false, false>);
+    static const bool ts_env = getenv("WN_TS") != nullptr;
+    auto kp = ts_env ? (m.use_bias ? (out_push ? gen_pipe_kernel<true, true, true> : gen_pipe_kernel<true, false, true>)
+                                   : (out_push ? gen_pipe_kernel<false, true, true> : gen_pipe_kernel<false, false, true>))
+                     : (m.use_bias ? (out_push ? gen_pipe_kernel<true, true, false> : gen_pipe_kernel<true, false, false>)
+                                   : (out_push ? gen_pipe_kernel<false, true, false> : gen_pipe_kernel<false, false, false>));
     static bool pipe_once[4] = {false, false, false, false};
     const int ki = (m.use_bias ? 2 : 0) + (out_push ? 1 : 0);
     if (!pipe_once[ki]) {
