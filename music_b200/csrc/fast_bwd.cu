@@ -1962,7 +1962,7 @@ int head_forward_generic(const Model& m, const BwdMaps& M, const SkipHeadMaps& H
 }  // namespace wn
 namespace wn { int fast_gen_debug_ts(long long* h_buf, int n); }
 extern "C" int wn_debug_ts(long long* h_buf, int32_t n) {      // timing experiments: the clock64 stamps of block_bwd6's CTA 0
-  if (h_buf && n < 0 && n >= -16 * 64) return wn::fast_gen_debug_ts(h_buf, -n);      // n < 0: the stamps of gen_pipe_kernel (fast_gen.cu)
+  if (h_buf && n < 0 && n >= -3 * 16 * 64) return wn::fast_gen_debug_ts(h_buf, -n);      // n < 0: the stamps of gen_pipe_kernel (fast_gen.cu)
   if (!h_buf || n <= 0 || n > 16 * 64) return WN_ERR_INVALID;
   cudaError_t e = cudaMemcpyFromSymbol(h_buf, wn::g_ts, (size_t)n * sizeof(long long));
   return e == cudaSuccess ? WN_OK : WN_ERR_CUDA;

@@ -20,6 +20,8 @@
 #include <cuda_fp16.h>
 #include <cuda_pipeline.h>
 
+#include <type_traits>
+
 #include "fast.cuh"
 #include "fast_layout.cuh"
 #include "tc05.cuh"
@@ -41,6 +43,7 @@ constexpr int FRAG_HEAD = 16 * 16 * 32;
 struct FastGenParams {
   int n_layers, n_streams, n_steps, push, has_bias;
   int lpc;                         // gen_pipe_kernel: blocks per CTA (2; 1 in timing experiments)
+  int gpc;                         // gen_pipe_kernel: groups of 8 streams per cluster (1..NG)
   int trace;                       // WN_TS=1: clock64 stamps (GEN_TS)
   int dil[GEN_MAXL];
   int ring_off[GEN_MAXL];
@@ -441,35 +444,44 @@ gen_steps_bf16_kernel(FastGenParams p, char* __restrict__ state, const int64_t* 
 // (30 blocks + 15 hops + head), the same for 8 and for 64 streams per cluster; independent clusters serve more streams.
 constexpr int NG = 8;
 // timing experiments (WN_TS=1): clock64 stamps of CTA 1 of cluster 0, group 0, 16 per step (wn_debug_ts with n < 0 reads them)
-__device__ long long g_gen_ts[16 * 64];
+__device__ long long g_gen_ts[3 * 16 * 64];      // [0,1024): clock64 stamps of CTA 1; [1024,2048): globaltimer at token arrival, per rank; [2048,3072): clock64 stamps of the head
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define HEAD_TS(k)                                                                                  \
+  do {                                                                                              \
+    if (TRACE && cid == 0 && g == 0 && tid == 0 && step < 64) g_gen_ts[2048 + step * 16 + (k)] = clock64(); \
+  } while (0)
 #define GEN_TS(k)                                                                                   \
   do {                                                                                              \
     if (TRACE && rank == 1 && cid == 0 && g == 0 && tid == 0 && step < 64) g_gen_ts[step * 16 + (k)] = clock64(); \
   } while (0)
 namespace pipe {
-constexpr uint32_t X_BYTES = G * XS * 4, XH_BYTES = G * XH * 2, SK_BYTES = G * HS * 4;      // one group's x (fp32), x (fp16), skip sums
-constexpr uint32_t OFF_BAR = 0;                                   // xfull[NG], skfull[NG], notefull[NG]
+constexpr uint32_t XR_BYTES = 128 * 16, XF_BYTES = 4 * 32 * 8;      // one group's x: fp32 residual (the dense warps' accumulator fragments),
+                                                                      // fp16 B fragments [k-tile 4][lane 32] of every warp's MMAs
+constexpr uint32_t X_BYTES = G * XS * 4, SK_BYTES = G * HS * 4;      // a group's taps of one block (fp32 rows), its skip sums
+constexpr uint32_t OFF_BAR = 0;                                   // xhfull[NG], xrfull[NG], skfull[NG], notefull[NG]
 constexpr uint32_t OFF_NOTE = 256;                                // int note[NG][G], last[NG][G]
 constexpr uint32_t OFF_SLOT = OFF_NOTE + 2 * NG * G * 4;          // int slot[NG][2][G]
-constexpr uint32_t OFF_ZH = OFF_SLOT + NG * 2 * G * 4;            // __half zh[G][XH]
-constexpr uint32_t OFF_SKIN = (OFF_ZH + XH_BYTES + 127) & ~127u;  // float skin[NG][G][HS]  (same offset in every role but CTA 0)
-constexpr uint32_t OFF_XIN = OFF_SKIN + NG * SK_BYTES;            // block CTAs: float xin[NG][G][XS]   (same offset in all of them)
-constexpr uint32_t OFF_XHIN = OFF_XIN + NG * X_BYTES;             //             __half xhin[NG][G][XH]
-constexpr uint32_t OFF_TAPS = OFF_XHIN + NG * XH_BYTES;           //             float taps[NG][2][G][XS]
+constexpr uint32_t OFF_ZF = OFF_SLOT + NG * 2 * G * 4;            // uint32 zf[2][4][2][32]: gated activations of the two blocks, B fragments
+constexpr uint32_t OFF_XL = OFF_ZF + 2 * XF_BYTES;                // uint2 xl[4][32]: block 0's output (CTA 0: also the embedding), B fragments
+constexpr uint32_t OFF_SKIN = (OFF_XL + XF_BYTES + 127) & ~127u;  // float skin[NG][G][HS]  (same offset in every role but CTA 0)
+constexpr uint32_t OFF_XIN = OFF_SKIN + NG * SK_BYTES;            // block CTAs: float4 xr[NG][128]   (same offset in all of them)
+constexpr uint32_t OFF_XHIN = OFF_XIN + NG * XR_BYTES;            //             uint2 xf[NG][4][32]
+constexpr uint32_t OFF_TAPS = OFF_XHIN + NG * XF_BYTES;           //             float taps[NG][2][G][XS]
 constexpr uint32_t BLOCK_BYTES = OFF_TAPS + NG * 2 * X_BYTES;
 constexpr uint32_t OFF_WC = OFF_SKIN;                             // CTA 0 (nothing arrives but notes): float wc[2][256][64]
 constexpr uint32_t OFF_TAPS0 = OFF_WC + 2 * 256 * 64 * 4;         //        its taps
-constexpr uint32_t OFF_STG0 = OFF_TAPS0 + NG * 2 * X_BYTES;       //        two staging sets {x fp32, x fp16, skip sums} (outgoing tokens)
-constexpr uint32_t STG_BYTES = X_BYTES + XH_BYTES + SK_BYTES;
+constexpr uint32_t OFF_STG0 = OFF_TAPS0 + NG * 2 * X_BYTES;       //        two staging sets of outgoing skip sums
+constexpr uint32_t STG_BYTES = SK_BYTES;
 constexpr uint32_t CTA0_BYTES = OFF_STG0 + 2 * STG_BYTES;
-constexpr uint32_t OFF_P2 = OFF_SKIN + NG * SK_BYTES;             // head: uint4 p2[FRAG_HEAD]
+constexpr uint32_t HF_BYTES = 16 * 32 * 8;                            // a group's relu(skip sums), fp16 B fragments [k-tile 16][lane 32]
+constexpr uint32_t OFF_HF = OFF_SKIN;                             // head: uint2 hf[NG][16][32] (what the last block CTA sends)
+constexpr uint32_t OFF_P2 = OFF_HF + NG * HF_BYTES;               //       uint4 p2[FRAG_HEAD]
 constexpr uint32_t OFF_HH = OFF_P2 + FRAG_HEAD * 16;              //       __half hh[2][G][HH]
 constexpr uint32_t OFF_LG = OFF_HH + 2 * G * HH * 2;              //       float lg[G][HS]
 constexpr uint32_t HEAD_BYTES = OFF_LG + G * HS * 4;
 constexpr uint32_t TOTAL = HEAD_BYTES > CTA0_BYTES ? (HEAD_BYTES > BLOCK_BYTES ? HEAD_BYTES : BLOCK_BYTES) : (CTA0_BYTES > BLOCK_BYTES ? CTA0_BYTES : BLOCK_BYTES);
 static_assert(TOTAL <= 227 * 1024, "pipeline generation kernel: shared memory");
-static_assert(X_BYTES % 16 == 0 && XH_BYTES % 16 == 0 && SK_BYTES % 16 == 0 && OFF_XIN % 16 == 0 && OFF_XHIN % 16 == 0 && OFF_STG0 % 16 == 0,
-              "bulk copies move 16-byte units");
+static_assert(SK_BYTES % 16 == 0 && OFF_SKIN % 16 == 0 && OFF_STG0 % 16 == 0 && OFF_XIN % 16 == 0 && OFF_XHIN % 16 == 0, "16-byte units");
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
@@ -491,20 +503,54 @@ __device__ __forceinline__ void bulk_to_peer(uint32_t dst_cluster, uint32_t src_
                "r"(bytes), "r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// one thread's 16 / 8 bytes -> another CTA's shared memory; the bytes complete on THAT CTA's mbarrier (data and signal travel together:
+// measured 310 cycles per hand-off of 1 KB against 530 for st.shared + fence.proxy.async + barrier + cp.async.bulk of the 3 KB token)
+__device__ __forceinline__ void st_async_f4(uint32_t dst_cluster, const float (&v)[4], uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(dst_cluster), "f"(v[0]),
+               "f"(v[1]), "f"(v[2]), "f"(v[3]), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void st_async_u1(uint32_t dst_cluster, uint32_t a, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster), "r"(a), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void st_async_u2(uint32_t dst_cluster, uint32_t a, uint32_t b, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1,%2}, [%3];" ::"r"(dst_cluster), "r"(a), "r"(b),
+               "r"(bar_cluster) : "memory");
+}
+// 8x8 fp16 transpose inside a warp: an accumulator fragment (row = channel, two streams per thread) becomes a B fragment (row = stream's
+// column, two channels per thread)
+__device__ __forceinline__ uint32_t movm_t(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
 __device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// wait for completion `parity` of a local mbarrier whose arrivals / bytes come from another CTA of the cluster.  Bounded: a token that
-// never arrives (a bug) traps after ~2 s instead of hanging the GPU.
+// wait for completion `parity` of a local mbarrier whose bytes come from another CTA of the cluster (st.async / bulk copies into THIS
+// CTA's shared memory: the transaction count orders them before the phase flips, so the default CTA-scope acquire is enough - a
+// cluster-scope acquire compiles to CCTL.IVALL, an L1 invalidation on every token).  Bounded: a token that never arrives (a bug) traps
+// after ~2 s instead of hanging the GPU.
 __device__ __forceinline__ void wait_token(uint64_t* bar, uint32_t parity) {
+#ifdef WN_GEN_WAIT_LANE0
+  if ((threadIdx.x & 31) != 0) { __syncwarp(); return; }
+#endif
   const uint32_t a = smem_u32(bar);
   const long long t0 = clock64();
   for (;;) {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    if (ok) return;
+    if (ok) break;
     if (clock64() - t0 > 4000000000ll) __trap();
   }
+#ifdef WN_GEN_WAIT_LANE0
+  __syncwarp();
+#endif
+}
+__device__ __forceinline__ uint32_t try_wait_once(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok;
 }
 template <int N_>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
@@ -535,11 +581,12 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
   const int n8 = lane >> 2, q = lane & 3;
   const int CS = (int)cluster_size(), rank = (int)cluster_rank(), cid = (int)blockIdx.x / CS;
   const int groups_total = (p.n_streams + G - 1) / G;
-  const int g0 = cid * NG, ng = min(NG, groups_total - g0);
+  const int g0 = cid * p.gpc, ng = min(p.gpc, groups_total - g0);
   const bool is_head = rank == CS - 1;
-  uint64_t* xfull = reinterpret_cast<uint64_t*>(sm + OFF_BAR);     // a group's x (fp32 + fp16) has arrived: tx bytes
-  uint64_t* skfull = xfull + NG;                                    // its running skip sums have arrived (a second, larger copy: waited for later)
-  uint64_t* notefull = xfull + 2 * NG;                              // CTA 0: the head's picks of a group
+  uint64_t* xhfull = reinterpret_cast<uint64_t*>(sm + OFF_BAR);    // a group's x has arrived, fp16 fragments (what the first MMAs need): tx bytes
+  uint64_t* xrfull = xhfull + NG;                                   // its fp32 residual (needed one exchange phase later)
+  uint64_t* skfull = xhfull + 2 * NG;                               // its running skip sums (a bulk copy, behind the token)
+  uint64_t* notefull = xhfull + 3 * NG;                             // CTA 0: the head's picks of a group
   int (*note)[G] = reinterpret_cast<int (*)[G]>(sm + OFF_NOTE);
   int (*last)[G] = reinterpret_cast<int (*)[G]>(sm + OFF_NOTE + NG * G * 4);
   int (*slot)[2][G] = reinterpret_cast<int (*)[2][G]>(sm + OFF_SLOT);
@@ -547,15 +594,21 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
   const uint32_t sm_base = smem_u32(sm);
   if (tid == 0) {
     for (int g = 0; g < NG; ++g) {
-      mbar_init(&xfull[g], 1);        // the consumer's own arming arrival; the data arrive as tx bytes
+      mbar_init(&xhfull[g], 1);       // the consumer's own arming arrival; the data arrive as tx bytes
+      mbar_init(&xrfull[g], 1);
       mbar_init(&skfull[g], 1);
-      mbar_init(&notefull[g], 8);     // the 8 pick warps of the head
+      mbar_init(&notefull[g], 1);     // CTA 0: the 8 picks of the head arrive as 32 tx bytes
     }
     fence_barrier_init();
+    if (rank == 0)
+      for (int g = 0; g < NG; ++g) mbar_expect_tx(&notefull[g], G * 4);
     if (rank > 0)
       for (int g = 0; g < NG; ++g) {      // armed for step 0
-        if (!is_head) mbar_expect_tx(&xfull[g], X_BYTES + XH_BYTES);
-        mbar_expect_tx(&skfull[g], SK_BYTES);
+        if (!is_head) {
+          mbar_expect_tx(&xhfull[g], XF_BYTES);
+          mbar_expect_tx(&xrfull[g], XR_BYTES);
+        }
+        mbar_expect_tx(&skfull[g], is_head ? HF_BYTES : SK_BYTES);
       }
   }
   auto stream_of = [&](int g, int s) { return min((g0 + g) * G + s, p.n_streams - 1); };
@@ -569,9 +622,13 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
 
   if (!is_head) {
     // ============================================================ block CTA: blocks l0, l0 + 1
+    // The CTA's role (first: gathers the embedding, nothing arrives but notes; to_head: its skip sums go to the head) is a compile-time
+    // constant of the body: the role tests sat on the token's critical path as taken branches.
+    auto block_cta = [&](auto first_c, auto to_head_c) {
+    constexpr bool first = decltype(first_c)::value, to_head = decltype(to_head_c)::value;
     const int l0 = p.lpc * rank, nl = min(p.lpc, N - l0);
-    const bool first = rank == 0, to_head = rank == CS - 2;
-    __half (*zh)[XH] = reinterpret_cast<__half (*)[XH]>(sm + OFF_ZH);
+    uint32_t (*zf)[4][2][32] = reinterpret_cast<uint32_t (*)[4][2][32]>(sm + OFF_ZF);      // [block][k-tile][fragment half][lane]
+    uint2 (*xl)[32] = reinterpret_cast<uint2 (*)[32]>(sm + OFF_XL);                          // [k-tile][lane]
     float* taps = reinterpret_cast<float*>(sm + (first ? OFF_TAPS0 : OFF_TAPS));      // [NG][2][G][XS]
     float* wc = reinterpret_cast<float*>(sm + OFF_WC);                                 // CTA 0
     // ---- resident A fragments (same per-warp ownership as gen_steps_bf16_kernel)
@@ -584,17 +641,10 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
         const uint4* base = fbase + (int64_t)i * FRAG_LAYER;
 #pragma unroll
         for (int k = 0; k < 8; ++k) fgw[li][k] = base[FRAG_FG + (warp * 8 + k) * 32];
-        if (warp < 4) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) w2w[li][k] = base[FRAG_D + (warp * 4 + k) * 32];
+        for (int k = 0; k < 4; ++k) w2w[li][k] = warp < 4 ? base[FRAG_D + (warp * 4 + k) * 32] : make_uint4(0u, 0u, 0u, 0u);      // dense: warps 0-3
 #pragma unroll
-          for (int k = 0; k < 4; ++k) w2w[li][4 + k] = base[FRAG_S + (warp * 4 + k) * 32];
-#pragma unroll
-          for (int k = 8; k < 12; ++k) w2w[li][k] = make_uint4(0u, 0u, 0u, 0u);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 12; ++k) w2w[li][k] = base[FRAG_S + ((4 + 3 * (warp - 4)) * 4 + k) * 32];
-        }
+        for (int k = 0; k < 8; ++k) w2w[li][4 + k] = base[FRAG_S + (2 * warp * 4 + k) * 32];      // skip: m-tiles 2w, 2w+1
       }
     }
     for (int e = tid; e < ng * nl * G; e += 256) {
@@ -627,183 +677,241 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     for (int g = 0; g < ng; ++g) prefetch_taps(g, 0);
     for (int g = ng; g < NG; ++g) __pipeline_commit();      // always NG commit groups per ring period: the wait below is a constant
     // remote addresses of the next CTA's slots (same offsets there)
-    const uint32_t r_xin = map_to(sm_base + OFF_XIN, rank + 1), r_xhin = map_to(sm_base + OFF_XHIN, rank + 1);
+    const uint32_t r_xr = map_to(sm_base + OFF_XIN, rank + 1), r_xf = map_to(sm_base + OFF_XHIN, rank + 1);
     const uint32_t r_skin = map_to(sm_base + OFF_SKIN, rank + 1);
-    const uint32_t r_xfull = map_to(smem_u32(xfull), rank + 1), r_skfull = map_to(smem_u32(skfull), rank + 1);
+    const uint32_t r_xhfull = map_to(smem_u32(xhfull), rank + 1), r_xrfull = map_to(smem_u32(xrfull), rank + 1);
+    const uint32_t r_skfull = map_to(smem_u32(skfull), rank + 1);
+    const uint32_t r_hf = map_to(sm_base + OFF_HF, rank + 1);      // (the last block CTA: the head's fragment slots)
+    // skip MMAs of this CTA's blocks: warp w owns skip channels 32w..32w+31 (m-tiles 2w, 2w+1)
+    auto skip_mmas = [&](float (&sk)[2][4]) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sk[j][r] = 0.f;
+#pragma unroll
+      for (int li = 0; li < 2; ++li)
+        if (li < nl) {
+#pragma unroll
+          for (int kt = 0; kt < 4; ++kt) {
+            const uint32_t b0 = zf[li][kt][0][lane], b1 = zf[li][kt][1][lane];
+            mma_f16(sk[0], w2w[li][4 + kt], b0, b1);
+            mma_f16(sk[1], w2w[li][8 + kt], b0, b1);
+          }
+        }
+    };
+
+    // W0 . old of both blocks of group gg (the taps are known one ring period ahead): computed while the group's token is still
+    // on its way, so that the token's critical path is four independent MMAs per block instead of four chains of two
+    float pre[2][4];
+    auto compute_pre = [&](int gg) {
+#pragma unroll
+      for (int li = 0; li < 2; ++li) {
+        if (li < nl) {
+          const int ch = 8 * warp + n8;
+          const float bf = HAS_BIAS ? p.bias_fg[(l0 + li) * 128 + ch] : 0.f, bg = HAS_BIAS ? p.bias_fg[(l0 + li) * 128 + 64 + ch] : 0.f;
+          float c[4] = {bf, bf, bg, bg}, e[4] = {0.f, 0.f, 0.f, 0.f};
+          const float* orow = taps + ((size_t)(gg * 2 + li) * G + n8) * XS + 2 * q;
+          uint32_t bo[4][2];
+#pragma unroll
+          for (int kt = 0; kt < 4; ++kt) {
+            const float2 v0 = *reinterpret_cast<const float2*>(orow + kt * 16), v1 = *reinterpret_cast<const float2*>(orow + kt * 16 + 8);
+            bo[kt][0] = pack_h2(v0.x, v0.y);
+            bo[kt][1] = pack_h2(v1.x, v1.y);
+          }
+          mma_f16(c, fgw[li][0], bo[0][0], bo[0][1]);
+          mma_f16(e, fgw[li][1], bo[1][0], bo[1][1]);
+          mma_f16(c, fgw[li][2], bo[2][0], bo[2][1]);
+          mma_f16(e, fgw[li][3], bo[3][0], bo[3][1]);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) pre[li][r] = c[r] + e[r];
+        }
+      }
+    };
+    cp_wait<NG - 1>();      // group 0's taps
+    __syncthreads();
+    compute_pre(0);
 
     for (int step = 0; step < p.n_steps; ++step) {
       for (int g = 0; g < ng; ++g) {
         const int n_act = n_act_of(g);
-        float (*xs)[XS];
-        __half (*xhs)[XH];
+        const int chd = 16 * (warp & 3) + n8, s0 = 2 * q, s1 = 2 * q + 1;      // dense warps: accumulator fragment = channels chd, chd + 8
+        const uint2* xfrag;     // this block's input, B fragments [k-tile][lane]
         float (*sko)[HS];       // where this CTA's outgoing skip sums are staged
+        float dn[4] = {0.f, 0.f, 0.f, 0.f};      // dense warps: the residual stream, fp32, in accumulator-fragment layout
         if (first) {
-          // CTA 0: the gathered input and the outgoing token live in one of two staging sets; a set is rewritten two groups later,
-          // when its bulk copies have long been read
-          uint8_t* stg = sm + OFF_STG0 + ((step * ng + g) & 1) * STG_BYTES;
-          xs = reinterpret_cast<float (*)[XS]>(stg);
-          xhs = reinterpret_cast<__half (*)[XH]>(stg + X_BYTES);
-          sko = reinterpret_cast<float (*)[HS]>(stg + X_BYTES + XH_BYTES);
-          if (tid == 0) bulk_wait_read_2();      // the two bulk groups of the iteration that used this staging set have been read
-          if (step > 0) wait_token(&notefull[g], (step - 1) & 1);
-          __syncthreads();      // (tid 0's wait on the staging set before anybody writes it)
-          for (int e = tid; e < G * 64; e += 256) {      // causal layer: two embedding rows (fast_generate.py:111-116)
-            const int s = e >> 6, r = e & 63;
-            float v = wc[last[g][s] * 64 + r] + wc[(256 + note[g][s]) * 64 + r];
-            if (HAS_BIAS) v += p.bias_c[r];
-            xs[s][r] = v;
-            xhs[s][r] = __float2half_rn(v);
+          // CTA 0: the causal layer is two embedding rows (fast_generate.py:111-116), gathered by the dense warps straight into their
+          // fragments.  Outgoing skip sums alternate between two staging sets; a set is rewritten two groups later.
+          sko = reinterpret_cast<float (*)[HS]>(sm + OFF_STG0 + ((step * ng + g) & 1) * STG_BYTES);
+          if (tid == 0) bulk_wait_read_1();      // the bulk copy of the iteration that used this staging set has been read
+          if (step > 0) {
+            wait_token(&notefull[g], (step - 1) & 1);
           }
+          if (warp < 4) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const int s_ = 2 * q + (r & 1), c_ = chd + 8 * (r >> 1);
+              dn[r] = wc[last[g][s_] * 64 + c_] + wc[(256 + note[g][s_]) * 64 + c_] + (HAS_BIAS ? p.bias_c[c_] : 0.f);
+            }
+            xl[warp][lane] = make_uint2(movm_t(pack_h2(dn[0], dn[1])), movm_t(pack_h2(dn[2], dn[3])));
+          }
+          __syncthreads();      // (also tid 0's wait on the staging set before anybody writes it)
+          if (tid < G) last[g][tid] = note[g][tid];
+          xfrag = &xl[0][0];
         } else {
           GEN_TS(0);
-          wait_token(&xfull[g], step & 1);
+          wait_token(&xhfull[g], step & 1);      // every thread waits for itself: no barrier between the token and its first use
           GEN_TS(1);
-          if (tid == 0 && step + 1 < p.n_steps) mbar_expect_tx(&xfull[g], X_BYTES + XH_BYTES);      // armed for the group's next token
-          xs = reinterpret_cast<float (*)[G][XS]>(sm + OFF_XIN)[g];
-          xhs = reinterpret_cast<__half (*)[G][XH]>(sm + OFF_XHIN)[g];
+          if (TRACE && g == 0 && tid == 0 && step < 64 && cid == 0) g_gen_ts[1024 + step * 16 + rank] = (long long)global_ns();
+          xfrag = reinterpret_cast<const uint2*>(sm + OFF_XHIN) + g * 128;
           sko = skin[g];
         }
-        cp_wait<NG - 1>();                     // this group's taps (requested one ring period = NG commit groups ago)
-        __syncthreads();
-        GEN_TS(2);
-        if (first && tid < G) last[g][tid] = note[g][tid];
-        float sk[3][4];
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-          for (int r = 0; r < 4; ++r) sk[j][r] = 0.f;
-        float* const ring0 = reinterpret_cast<float*>(sptr(g, 2 * q) + 16);
-        float* const ring1 = reinterpret_cast<float*>(sptr(g, 2 * q + 1) + 16);
+        float pv[2][4];      // what the two blocks push into their queues (dense warps)
 #pragma unroll
         for (int li = 0; li < 2; ++li) {
           if (li < nl) {
             const int i = l0 + li;
             const bool last_block = li == nl - 1;
-            // ---- [f|g] = W0 old + W1 x : warp w owns filter and gate channels 8w..8w+7 for all 8 streams.  Four chains of two MMAs
-            const int ch = 8 * warp + n8;
-            float c0[4], c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f}, c3[4] = {0.f, 0.f, 0.f, 0.f};
+            // ---- [f|g] = (W0 old, precomputed) + W1 x : warp w owns filter and gate channels 8w..8w+7 for all 8 streams
+            uint2 bx[4];
+#pragma unroll
+            for (int kt = 0; kt < 4; ++kt) bx[kt] = xfrag[kt * 32 + lane];
+            float c0[4] = {pre[li][0], pre[li][1], pre[li][2], pre[li][3]}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f},
+                  c3[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_f16(c0, fgw[li][4], bx[0].x, bx[0].y);
+            mma_f16(c1, fgw[li][5], bx[1].x, bx[1].y);
+            mma_f16(c2, fgw[li][6], bx[2].x, bx[2].y);
+            mma_f16(c3, fgw[li][7], bx[3].x, bx[3].y);
+            uint32_t res_ok = 1;
+            if (li == 0 && !first && warp < 4) res_ok = try_wait_once(&xrfull[g], step & 1);      // (the answer is read behind the barrier below)
+            GEN_TS(2 + 4 * li);
             {
-              const float bf = HAS_BIAS ? p.bias_fg[i * 128 + ch] : 0.f, bg = HAS_BIAS ? p.bias_fg[i * 128 + 64 + ch] : 0.f;
-              c0[0] = c0[1] = bf;
-              c0[2] = c0[3] = bg;
+              const float z0 = gate_z((c0[0] + c1[0]) + (c2[0] + c3[0]), (c0[2] + c1[2]) + (c2[2] + c3[2]));
+              const float z1 = gate_z((c0[1] + c1[1]) + (c2[1] + c3[1]), (c0[3] + c1[3]) + (c2[3] + c3[3]));
+              zf[li][warp >> 1][warp & 1][lane] = movm_t(pack_h2(z0, z1));      // channels 8w..8w+7 = half a k-tile
             }
-            const float* orow = taps + ((size_t)(g * 2 + li) * G + n8) * XS + 2 * q;
-            const __half* xrow = &xhs[n8][2 * q];
-            uint32_t bo[4][2], bx[4][2];
-#pragma unroll
-            for (int kt = 0; kt < 4; ++kt) {
-              const float2 v0 = *reinterpret_cast<const float2*>(orow + kt * 16), v1 = *reinterpret_cast<const float2*>(orow + kt * 16 + 8);
-              bo[kt][0] = pack_h2(v0.x, v0.y);
-              bo[kt][1] = pack_h2(v1.x, v1.y);
-              bx[kt][0] = *reinterpret_cast<const uint32_t*>(xrow + kt * 16);
-              bx[kt][1] = *reinterpret_cast<const uint32_t*>(xrow + kt * 16 + 8);
-            }
-            mma_f16(c1, fgw[li][4], bx[0][0], bx[0][1]);
-            mma_f16(c3, fgw[li][6], bx[2][0], bx[2][1]);
-            mma_f16(c0, fgw[li][0], bo[0][0], bo[0][1]);
-            mma_f16(c2, fgw[li][2], bo[2][0], bo[2][1]);
-            mma_f16(c1, fgw[li][5], bx[1][0], bx[1][1]);
-            mma_f16(c3, fgw[li][7], bx[3][0], bx[3][1]);
-            mma_f16(c0, fgw[li][1], bo[1][0], bo[1][1]);
-            mma_f16(c2, fgw[li][3], bo[3][0], bo[3][1]);
-            GEN_TS(3 + 5 * li);
-            zh[2 * q][ch] = __float2half_rn(gate_z((c0[0] + c1[0]) + (c2[0] + c3[0]), (c0[2] + c1[2]) + (c2[2] + c3[2])));
-            zh[2 * q + 1][ch] = __float2half_rn(gate_z((c0[1] + c1[1]) + (c2[1] + c3[1]), (c0[3] + c1[3]) + (c2[3] + c3[3])));
             __syncthreads();
-            GEN_TS(4 + 5 * li);
-            uint32_t bz[4][2];
+            GEN_TS(3 + 4 * li);
+            if (last_block && to_head) {
+              // the last block CTA: what the head waits for is the skip sum, so it goes first - relu and the fp16 conversion applied
+              // here, sent as the B fragments of post_process_1's MMAs straight from the accumulators
+              float sk[2][4];
+              skip_mmas(sk);
+              if (!first) wait_token(&skfull[g], step & 1);
 #pragma unroll
-            for (int kt = 0; kt < 4; ++kt) {
-              const __half* zr = &zh[n8][kt * 16 + 2 * q];
-              bz[kt][0] = *reinterpret_cast<const uint32_t*>(zr);
-              bz[kt][1] = *reinterpret_cast<const uint32_t*>(zr + 8);
+              for (int j = 0; j < 2; ++j) {
+                float v[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const int row = 16 * (2 * warp + j) + n8 + 8 * (r >> 1), s_ = 2 * q + (r & 1);
+                  v[r] = fmaxf(sk[j][r] + (first ? 0.f : skin[g][s_][row]) + (HAS_BIAS ? p.bias_skip[row] : 0.f), 0.f);
+                }
+                st_async_u2(r_hf + (uint32_t)((g * 16 + 2 * warp + j) * 32 + lane) * 8, movm_t(pack_h2(v[0], v[1])), movm_t(pack_h2(v[2], v[3])),
+                            r_skfull + g * 8);
+              }
             }
             if (warp < 4) {
-              const int chd = 16 * warp + n8;
-              const int s0 = 2 * q, s1 = 2 * q + 1;
-              float dn[4], dm[4] = {0.f, 0.f, 0.f, 0.f};
-              dn[0] = xs[s0][chd]; dn[1] = xs[s1][chd]; dn[2] = xs[s0][chd + 8]; dn[3] = xs[s1][chd + 8];     // residual
-              const float xi[4] = {dn[0], dn[1], dn[2], dn[3]};
-              if (HAS_BIAS) {
-                const float b0 = p.bias_d[i * 64 + chd], b1 = p.bias_d[i * 64 + chd + 8];
-                dn[0] += b0; dn[1] += b0; dn[2] += b1; dn[3] += b1;
-              }
-              const int o0 = (p.ring_off[i] + slot[g][li][s0]) * 64 + chd, o1 = (p.ring_off[i] + slot[g][li][s1]) * 64 + chd;
-              mma_f16(dn, w2w[li][0], bz[0][0], bz[0][1]);
-              mma_f16(dm, w2w[li][2], bz[2][0], bz[2][1]);
-              mma_f16(dn, w2w[li][1], bz[1][0], bz[1][1]);
-              mma_f16(dm, w2w[li][3], bz[3][0], bz[3][1]);
-#pragma unroll
-              for (int r = 0; r < 4; ++r) dn[r] += dm[r];
-              GEN_TS(5 + 5 * li);
-              if (!(last_block && to_head)) {      // in place: the next block's input, or the token's payload
-                xs[s0][chd] = dn[0]; xs[s1][chd] = dn[1]; xs[s0][chd + 8] = dn[2]; xs[s1][chd + 8] = dn[3];
-                xhs[s0][chd] = __float2half_rn(dn[0]); xhs[s1][chd] = __float2half_rn(dn[1]);
-                xhs[s0][chd + 8] = __float2half_rn(dn[2]); xhs[s1][chd + 8] = __float2half_rn(dn[3]);
-                if (last_block) {
-                  // the token leaves as soon as the four dense warps have written it: the skip MMAs, the ring pushes and the skip
-                  // sums below are off the ring's critical path
-                  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                  asm volatile("bar.sync 1, 128;" ::: "memory");
-                  if (tid == 0) {
-                    bulk_to_peer(r_xin + g * X_BYTES, smem_u32(xs), X_BYTES, r_xfull + g * 8);
-                    bulk_to_peer(r_xhin + g * XH_BYTES, smem_u32(xhs), XH_BYTES, r_xfull + g * 8);
-                    bulk_commit();
-                  }
-                }
-              } else if (tid == 0) {
-                bulk_commit();      // (two bulk groups per iteration in every CTA: see bulk_wait_read_2)
-              }
-#pragma unroll
-              for (int kt = 0; kt < 4; ++kt) mma_f16(sk[0], w2w[li][4 + kt], bz[kt][0], bz[kt][1]);
-              constexpr bool out_push = PUSH_OUT;                                     // fast_generate.py:128-129
-              if (s0 < n_act) { ring0[o0] = out_push ? dn[0] : xi[0]; ring0[o0 + 8] = out_push ? dn[2] : xi[2]; }
-              if (s1 < n_act) { ring1[o1] = out_push ? dn[1] : xi[1]; ring1[o1 + 8] = out_push ? dn[3] : xi[3]; }
-              GEN_TS(6 + 5 * li);
-            } else {
+              uint32_t bz[4][2];
 #pragma unroll
               for (int kt = 0; kt < 4; ++kt) {
-                mma_f16(sk[0], w2w[li][kt], bz[kt][0], bz[kt][1]);
-                mma_f16(sk[1], w2w[li][4 + kt], bz[kt][0], bz[kt][1]);
-                mma_f16(sk[2], w2w[li][8 + kt], bz[kt][0], bz[kt][1]);
+                bz[kt][0] = zf[li][kt][0][lane];
+                bz[kt][1] = zf[li][kt][1][lane];
+              }
+              float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f}, d3[4] = {0.f, 0.f, 0.f, 0.f};
+              if (HAS_BIAS) {
+                const float b0 = p.bias_d[i * 64 + chd], b1 = p.bias_d[i * 64 + chd + 8];
+                d0[0] = b0; d0[1] = b0; d0[2] = b1; d0[3] = b1;
+              }
+              mma_f16(d0, w2w[li][0], bz[0][0], bz[0][1]);
+              mma_f16(d1, w2w[li][1], bz[1][0], bz[1][1]);
+              mma_f16(d2, w2w[li][2], bz[2][0], bz[2][1]);
+              mma_f16(d3, w2w[li][3], bz[3][0], bz[3][1]);
+              if (li == 0 && !first) {      // the fp32 residual travels behind the fragments, on its own barrier; fetched behind the MMAs
+                if (!res_ok) wait_token(&xrfull[g], step & 1);
+                const uint4 rv = lds128(sm_base + OFF_XIN + (uint32_t)(g * 128 + tid) * 16);
+                dn[0] = __uint_as_float(rv.x); dn[1] = __uint_as_float(rv.y); dn[2] = __uint_as_float(rv.z); dn[3] = __uint_as_float(rv.w);
+              }
+              const float xi[4] = {dn[0], dn[1], dn[2], dn[3]};
+#pragma unroll
+              for (int r = 0; r < 4; ++r) dn[r] = ((d0[r] + d1[r]) + (d2[r] + d3[r])) + dn[r];
+              GEN_TS(4 + 4 * li);
+#pragma unroll
+              for (int r = 0; r < 4; ++r) pv[li][r] = PUSH_OUT ? dn[r] : xi[r];      // fast_generate.py:128-129
+              if (!last_block) {
+                xl[warp][lane] = make_uint2(movm_t(pack_h2(dn[0], dn[1])), movm_t(pack_h2(dn[2], dn[3])));      // the next block's input
+              } else if (!to_head) {
+                // the token leaves straight from the dense warps' registers: first the fragments the next CTA's MMAs wait for, then the
+                // residual.  The skip MMAs, the queue pushes and the skip sums below are off the ring's critical path.
+                st_async_u2(r_xf + (uint32_t)(g * 128 + tid) * 8, movm_t(pack_h2(dn[0], dn[1])), movm_t(pack_h2(dn[2], dn[3])), r_xhfull + g * 8);
+                st_async_f4(r_xr + (uint32_t)(g * 128 + tid) * 16, dn, r_xrfull + g * 8);
               }
             }
-            if (last_block) {
-              // running skip sums: what arrived behind the token + this CTA's two blocks, in place
-              if (!first) {
-                wait_token(&skfull[g], step & 1);
-                if (tid == 0 && step + 1 < p.n_steps) mbar_expect_tx(&skfull[g], SK_BYTES);
-              }
-              const int nt = warp < 4 ? 1 : 3, mt0 = warp < 4 ? warp : 4 + 3 * (warp - 4);
-#pragma unroll
-              for (int j = 0; j < 3; ++j)
-                if (j < nt) {
-#pragma unroll
-                  for (int r = 0; r < 4; ++r) {
-                    const int row = 16 * (mt0 + j) + n8 + 8 * (r >> 1), s = 2 * q + (r & 1);
-                    sko[s][row] = sk[j][r] + (first ? 0.f : skin[g][s][row]);
-                  }
-                }
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the bulk copies below read these generic-proxy writes
+            if (!last_block) {
+              __syncthreads();      // block li + 1 reads what the dense warps wrote
+              xfrag = &xl[0][0];
             }
-            __syncthreads();
-            GEN_TS(7 + 5 * li);
+            GEN_TS(5 + 4 * li);
           }
         }
-        if (tid == 0) {      // behind the token: the running skip sums -> the next CTA's slot of this group
-          bulk_to_peer(r_skin + g * SK_BYTES, smem_u32(sko), SK_BYTES, r_skfull + g * 8);
-          bulk_commit();
+        // ================= behind the token: queue pushes, skip MMAs of both blocks, running skip sums, next taps, next W0 . old
+        if (warp < 4) {
+          float* const ring0 = reinterpret_cast<float*>(sptr(g, s0) + 16);
+          float* const ring1 = reinterpret_cast<float*>(sptr(g, s1) + 16);
+#pragma unroll
+          for (int li = 0; li < 2; ++li)
+            if (li < nl) {
+              const int i = l0 + li;
+              const int o0 = (p.ring_off[i] + slot[g][li][s0]) * 64 + chd, o1 = (p.ring_off[i] + slot[g][li][s1]) * 64 + chd;
+              if (s0 < n_act) { ring0[o0] = pv[li][0]; ring0[o0 + 8] = pv[li][2]; }
+              if (s1 < n_act) { ring1[o1] = pv[li][1]; ring1[o1 + 8] = pv[li][3]; }
+            }
         }
-        GEN_TS(13);
+        if (!to_head) {
+          float sk[2][4];
+          skip_mmas(sk);
+          GEN_TS(10);
+          if (!first) wait_token(&skfull[g], step & 1);
+          GEN_TS(11);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const int row = 16 * (2 * warp + j) + n8 + 8 * (r >> 1), s = 2 * q + (r & 1);
+              sko[s][row] = sk[j][r] + (first ? 0.f : skin[g][s][row]);      // (in place behind CTA 0)
+            }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the bulk copy below reads these generic-proxy writes
+        }
+        __syncthreads();      // (also: the queue pushes above happen before the tap requests below)
+        GEN_TS(12);
+        if (tid == 0) {
+          if (!to_head) {      // the running skip sums -> the next CTA's slot of this group
+            bulk_to_peer(r_skin + g * SK_BYTES, smem_u32(sko), SK_BYTES, r_skfull + g * 8);
+            bulk_commit();
+          }
+          // this group's barriers, armed for its next token (here, not behind the waits: nothing of it on the ring's critical path)
+          if (first && step > 0) mbar_expect_tx(&notefull[g], G * 4);      // (the last step's picks are awaited before the kernel ends)
+          if (!first && step + 1 < p.n_steps) {
+            mbar_expect_tx(&xhfull[g], XF_BYTES);
+            mbar_expect_tx(&xrfull[g], XR_BYTES);
+            mbar_expect_tx(&skfull[g], SK_BYTES);
+          }
+        }
         if (step + 1 < p.n_steps) prefetch_taps(g, 1);
-        else __pipeline_commit();               // (keeps the group accounting of cp_wait_dyn uniform)
+        else __pipeline_commit();               // (keeps the commit-group accounting uniform)
+        if (g == ng - 1)
+          for (int k = ng; k < NG; ++k) __pipeline_commit();
+        GEN_TS(13);
+        if (g + 1 < ng || step + 1 < p.n_steps) {
+          cp_wait<NG - 1>();      // the next group's taps were requested NG commit groups ago
+          __syncthreads();
+          compute_pre(g + 1 < ng ? g + 1 : 0);
+        }
         GEN_TS(14);
       }
-      for (int g = ng; g < NG; ++g) __pipeline_commit();
     }
     cp_wait<0>();
     if (tid == 0) bulk_wait_read_0();
     if (first) {
+      for (int g = 0; g < ng; ++g) wait_token(&notefull[g], (p.n_steps - 1) & 1);      // nothing is in flight towards this CTA at exit
       __syncthreads();
       for (int e = tid; e < ng * G; e += 256) {
         const int g = e / G, s = e % G;
@@ -812,6 +920,15 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
           reinterpret_cast<int64_t*>(sptr(g, s))[1] = last[g][s];
         }
       }
+    }
+    };
+    if (rank == 0) {
+      if (CS == 2) block_cta(std::true_type{}, std::true_type{});
+      else block_cta(std::true_type{}, std::false_type{});
+    } else if (rank == CS - 2) {
+      block_cta(std::false_type{}, std::true_type{});
+    } else {
+      block_cta(std::false_type{}, std::false_type{});
     }
   } else {
     // ============================================================ head CTA: relu(sum skips) -> P1 -> relu -> P2 -> pick
@@ -827,19 +944,19 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     for (int e = tid; e < FRAG_HEAD; e += 256) p2s[e] = headA[FRAG_HEAD + e];
     __syncthreads();
     const uint32_t r_note = map_to(sm_base + OFF_NOTE, 0), r_notefull = map_to(smem_u32(notefull), 0);
+    const uint2* const hf = reinterpret_cast<const uint2*>(sm + OFF_HF);      // [group][k-tile 16][lane]: relu(skip sums), B fragments
+    uint2* const h1f = reinterpret_cast<uint2*>(sm + OFF_HH);                  // [k-tile 16][lane]: relu(post_process_1), B fragments
+    float2* const cand = reinterpret_cast<float2*>(sm + OFF_HH + 16 * 32 * 8);  // [warp 8][stream 8]: greedy candidates (value, row)
     for (int step = 0; step < p.n_steps; ++step) {
       for (int g = 0; g < ng; ++g) {
         const int n_act = n_act_of(g);
+        HEAD_TS(0);
         wait_token(&skfull[g], step & 1);
-        if (tid == 0 && step + 1 < p.n_steps) mbar_expect_tx(&skfull[g], SK_BYTES);
-        for (int e = tid; e < G * 256; e += 256) {
-          const int s = e >> 8, row = e & 255;
-          hh[0][s][row] = __float2half_rn(fmaxf(skin[g][s][row] + (HAS_BIAS ? p.bias_skip[row] : 0.f), 0.f));
-        }
-        __syncthreads();
+        HEAD_TS(1);
+        if (TRACE && g == 0 && tid == 0 && step < 64 && cid == 0) g_gen_ts[1024 + step * 16 + rank] = (long long)global_ns();
+        float c[2][4][4];      // [m-tile][chain][fragment]: four chains of four MMAs per m-tile
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
-          float c[2][4][4];      // [m-tile][chain][fragment]: four chains of four MMAs per m-tile
 #pragma unroll
           for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -849,80 +966,122 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               c[j][0][r] = HAS_BIAS ? bias[row] : 0.f;
               c[j][1][r] = c[j][2][r] = c[j][3][r] = 0.f;
             }
-          const __half* hr = &hh[which][n8][2 * q];
+          const uint2* bsrc = (which == 0 ? hf + g * 16 * 32 : h1f) + lane;
 #pragma unroll
           for (int kt = 0; kt < 16; ++kt) {
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(hr + kt * 16), b1 = *reinterpret_cast<const uint32_t*>(hr + kt * 16 + 8);
+            const uint2 b = bsrc[kt * 32];
             if (which == 0) {
-              mma_f16(c[0][kt & 3], p1w[0][kt], b0, b1);
-              mma_f16(c[1][kt & 3], p1w[1][kt], b0, b1);
+              mma_f16(c[0][kt & 3], p1w[0][kt], b.x, b.y);
+              mma_f16(c[1][kt & 3], p1w[1][kt], b.x, b.y);
             } else {
               const uint4 a0 = p2s[((2 * warp) * 16 + kt) * 32 + lane], a1 = p2s[((2 * warp + 1) * 16 + kt) * 32 + lane];
-              mma_f16(c[0][kt & 3], a0, b0, b1);
-              mma_f16(c[1][kt & 3], a1, b0, b1);
+              mma_f16(c[0][kt & 3], a0, b.x, b.y);
+              mma_f16(c[1][kt & 3], a1, b.x, b.y);
             }
           }
+          HEAD_TS(3 + 2 * which);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) c[j][0][r] = (c[j][0][r] + c[j][1][r]) + (c[j][2][r] + c[j][3][r]);
+          if (which == 0) {
+            // relu, fp16, and the accumulator fragment transposed into the B fragment of k-tile 2w + j of post_process_2
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              h1f[(2 * warp + j) * 32 + lane] = make_uint2(movm_t(pack_h2(fmaxf(c[j][0][0], 0.f), fmaxf(c[j][0][1], 0.f))),
+                                                           movm_t(pack_h2(fmaxf(c[j][0][2], 0.f), fmaxf(c[j][0][3], 0.f))));
+            __syncthreads();
+            HEAD_TS(4);
+          }
+        }
+        // ---- logits of rows 32w..32w+31 are in c[.][0][.]: thread (n8, q) has rows 16(2w+j) + n8 + 8h of streams 2q, 2q+1
+        if (logits_out) {
 #pragma unroll
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               const int row = 16 * (2 * warp + j) + n8 + 8 * (r >> 1), s = 2 * q + (r & 1);
-              const float v = (c[j][0][r] + c[j][1][r]) + (c[j][2][r] + c[j][3][r]);
-              if (which == 0) {
-                hh[1][s][row] = __float2half_rn(fmaxf(v, 0.f));
-              } else {
-                lg[s][row] = v;
-                if (logits_out && s < n_act) logits_out[((int64_t)step * p.n_streams + (g0 + g) * G + s) * 256 + row] = v;
-              }
+              if (s < n_act) logits_out[((int64_t)step * p.n_streams + (g0 + g) * G + s) * 256 + row] = c[j][0][r];
             }
-          __syncthreads();
         }
-        // ---- pick: greedy topk(1) over the softmax (fast_generate.py:138-140) or inverse CDF; one warp per stream
-        {
+        if (uniforms == nullptr) {
+          // greedy topk(1) over the softmax (fast_generate.py:138-140) = the first maximum of the logits; found in registers:
+          // per thread over its four rows, over the 8 row lanes by shuffles, over the 8 warps through 512 bytes of shared memory
+          float bv[2];
+          int bi[2];
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            bv[b] = c[0][0][b];
+            bi[b] = 32 * warp + n8;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {      // rows in increasing order: (j, h) = (0,1), (1,0), (1,1)
+              const float v = c[k >> 1][0][2 * (k & 1) + b];
+              if (v > bv[b]) { bv[b] = v; bi[b] = 32 * warp + 16 * (k >> 1) + 8 * (k & 1) + n8; }
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, bv[b], o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi[b], o);
+              if (ov > bv[b] || (ov == bv[b] && oi < bi[b])) { bv[b] = ov; bi[b] = oi; }
+            }
+          }
+          if (n8 == 0) {
+            cand[warp * G + 2 * q] = make_float2(bv[0], __int_as_float(bi[0]));
+            cand[warp * G + 2 * q + 1] = make_float2(bv[1], __int_as_float(bi[1]));
+          }
+          __syncthreads();
+          HEAD_TS(6);
+          {
+            const int s = warp;      // one warp per stream; lanes 0..7 hold the 8 warps' candidates (rows increase with the warp)
+            const float2 cv = cand[(lane & 7) * G + s];
+            float v = cv.x;
+            int idx = __float_as_int(cv.y);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+              if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+            }
+            if (lane == 0) {
+              st_async_u1(r_note + (uint32_t)(g * G + s) * 4, (uint32_t)idx, r_notefull + g * 8);      // CTA 0's note[g][s]
+              if (s < n_act) out[(int64_t)step * p.n_streams + (g0 + g) * G + s] = idx;
+            }
+          }
+        } else {
+          // inverse CDF of the softmax; one warp per stream, the logits through shared memory
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) lg[2 * q + (r & 1)][16 * (2 * warp + j) + n8 + 8 * (r >> 1)] = c[j][0][r];
+          __syncthreads();
+          HEAD_TS(6);
           const int s = warp;
           const float* lgs = lg[s];
-          float v[8];
           float mx = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[j] = lgs[lane * 8 + j];
-            mx = fmaxf(mx, v[j]);
-          }
+          for (int j = 0; j < 8; ++j) mx = fmaxf(mx, lgs[j * 32 + lane]);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          int pick;
-          if (uniforms == nullptr) {
-            int best = 1 << 30;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (v[j] == mx) best = min(best, lane * 8 + j);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-            pick = best;
-          } else {
-            pick = 255;
-            if (lane == 0) {
-              float sum = 0.f;
-              for (int k = 0; k < 256; ++k) sum += expf(lgs[k] - mx);
-              const float inv = 1.f / sum;
-              float total_p = 0.f;
-              for (int k = 0; k < 256; ++k) total_p += expf(lgs[k] - mx) * inv;
-              const float thr = uniforms[(int64_t)step * p.n_streams + stream_of(g, s)] * total_p;
-              float cdf = 0.f;
-              for (int k = 0; k < 256; ++k) {
-                cdf += expf(lgs[k] - mx) * inv;
-                if (cdf > thr) { pick = k; break; }
-              }
-            }
-            pick = __shfl_sync(0xffffffffu, pick, 0);
-          }
           if (lane == 0) {
+            int pick = 255;
+            float sum = 0.f;
+            for (int k = 0; k < 256; ++k) sum += expf(lgs[k] - mx);
+            const float inv = 1.f / sum;
+            float total_p = 0.f;
+            for (int k = 0; k < 256; ++k) total_p += expf(lgs[k] - mx) * inv;
+            const float thr = uniforms[(int64_t)step * p.n_streams + stream_of(g, s)] * total_p;
+            float cdf = 0.f;
+            for (int k = 0; k < 256; ++k) {
+              cdf += expf(lgs[k] - mx) * inv;
+              if (cdf > thr) { pick = k; break; }
+            }
+            st_async_u1(r_note + (uint32_t)(g * G + s) * 4, (uint32_t)pick, r_notefull + g * 8);
             if (s < n_act) out[(int64_t)step * p.n_streams + (g0 + g) * G + s] = pick;
-            st_remote_u32(r_note + (uint32_t)(g * G + s) * 4, (uint32_t)pick);      // CTA 0's note[g][s]
-            arrive_remote(r_notefull + g * 8);
           }
         }
-        // (no barrier here: the next group's first barrier comes after every warp has finished this pick)
+        HEAD_TS(7);
+        if (tid == 0 && step + 1 < p.n_steps) mbar_expect_tx(&skfull[g], HF_BYTES);      // armed for the group's next sums
+        // (the next group's / step's writes of h1f, cand and lg come behind its barriers; every warp has read them by then)
       }
     }
   }
@@ -989,7 +1148,7 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
     p.lpc = (lpc_env == 1 && m.n_layers <= 15) ? 1 : 2;
     p.trace = 0;
     const int cs = (m.n_layers + p.lpc - 1) / p.lpc + 1;
-    const int groups = (int)ceil_div(n_streams, G), n_clusters = (int)ceil_div(groups, NG);
+    const int groups = (int)ceil_div(n_streams, G);
     const bool out_push = push == WN_PUSH_OUTPUT;
     static const bool ts_env = getenv("WN_TS") != nullptr;
     auto kp = ts_env ? (m.use_bias ? (out_push ? gen_pipe_kernel<true, true, true> : gen_pipe_kernel<true, false, true>)
@@ -1004,14 +1163,15 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
       pipe_once[ki] = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(cs * n_clusters)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = pipe::TOTAL; cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)cs); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = pipe::TOTAL; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    // The pipeline is the lower-latency kernel (26 vs 32 us per step) as long as every cluster is resident at once; with more stream
-    // groups than that its clusters would run in waves, and the one-CTA-per-8-streams kernel below (same step time for any number of
-    // streams up to 8 x 148) has the higher throughput.
+    // The step is the ring's latency (one group's token through every CTA and back), so the groups are spread over as many clusters
+    // as fit on the GPU at once (9 of 16 CTAs): a cluster serving one group never makes a token wait for another group's tail work.
+    // With more groups than NG per resident cluster the clusters would run in waves, and the one-CTA-per-8-streams kernel below
+    // (same step time for any number of streams up to 8 x 148) has the higher throughput.
     static int max_clusters[32] = {};
     if (max_clusters[cs] == 0) {
       int n = 0;
@@ -1019,7 +1179,13 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
       max_clusters[cs] = n > 0 ? n : -1;
     }
     static const bool pipe_force = [] { const char* e = getenv("WN_GEN_PIPE"); return e && e[0] == '1'; }();
-    if (pipe_force || n_clusters <= max_clusters[cs]) {
+    static const int gpc_env = [] { const char* e = getenv("WN_GEN_GPC"); return e ? atoi(e) : 0; }();      // (timing experiments)
+    int gpc = max_clusters[cs] > 0 ? (int)ceil_div(groups, max_clusters[cs]) : NG + 1;
+    if (gpc_env >= 1 && gpc_env <= NG && gpc_env >= gpc) gpc = gpc_env;
+    if (pipe_force && gpc > NG) gpc = NG;
+    if (gpc <= NG) {
+      p.gpc = gpc;
+      cfg.gridDim = dim3((unsigned)(cs * (int)ceil_div(groups, gpc)));
       WN_PROF("gen_pipe", s);
       WN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kp, p, reinterpret_cast<char*>(d_state), d_first_note, d_uniforms, d_out, d_logits));
       WN_CHECK_LAUNCH();

@@ -13,13 +13,21 @@ prime = torch.full((n, net.receptive_field), 128, dtype=torch.int64, device="cud
 first, st, _ = fg._prime(net, prime)
 out, _ = fg._steps(net, st, first, 40)
 torch.cuda.synchronize()
-N = 16 * 40
+N = 3 * 16 * 64
 buf = (C.c_longlong * N)()
 L.check(L.load().wn_debug_ts(buf, -N))
-names = ["wait start", "token", "top barrier", "b0 fg mma", "b0 bar1", "b0 dense mma", "b0 stores", "b0 bar2", "b1 fg mma", "b1 bar1", "b1 dense mma",
-         "b1 stores", "b1 bar2", "prefetch", "skip token", "skip sent"]
-print("step " + " ".join(f"{i:>6d}" for i in range(16)))
+names = ["wait start", "token", "b0 fg mma", "b0 bar1", "b0 dense", "b0 bar2", "b1 fg mma", "b1 bar1", "b1 dense", "x sent", "pushes+skip mma",
+         "skip token", "skip barrier", "prefetch", "next pre", "-"]
+print("step " + " ".join(f"{i:>6d}" for i in range(15)))
 for it in range(20, 30):
     t0 = buf[it * 16 + 1]
-    print(f"{it:4d} " + " ".join(f"{buf[it * 16 + k] - t0:6d}" for k in range(16)), " period", buf[it * 16 + 1] - buf[(it - 1) * 16 + 1])
+    print(f"{it:4d} " + " ".join(f"{buf[it * 16 + k] - t0:6d}" for k in range(15)), " period", buf[it * 16 + 1] - buf[(it - 1) * 16 + 1])
 print("columns:", ", ".join(f"{i}={s}" for i, s in enumerate(names)))
+print("globaltimer at token arrival, ns after rank 1 (ranks 1..15; rank 15 is the head's skip token)")
+for it in range(20, 26):
+    g0 = buf[1024 + it * 16 + 1]
+    print(f"{it:4d} " + " ".join(f"{buf[1024 + it * 16 + r] - g0:6d}" for r in range(1, 16)), " period ns", g0 - buf[1024 + (it - 1) * 16 + 1])
+print("head (clock64 after its skip token): 0=wait start 1=token 2=relu/convert barrier 3=P1 mmas issued 4=P1 barrier 5=P2 mmas issued 6=P2 barrier 7=pick sent")
+for it in range(20, 26):
+    t0 = buf[2048 + it * 16 + 1]
+    print(f"{it:4d} " + " ".join(f"{buf[2048 + it * 16 + k] - t0:6d}" for k in range(8)))
