@@ -452,7 +452,7 @@ __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t
   } while (0)
 #define GEN_TS(k)                                                                                   \
   do {                                                                                              \
-    if (TRACE && rank == 1 && cid == 0 && g == 0 && tid == 0 && step < 64) g_gen_ts[step * 16 + (k)] = clock64(); \
+    if (TRACE && rank == p.trace && cid == 0 && g == 0 && tid == 0 && step < 64) g_gen_ts[step * 16 + (k)] = clock64(); \
   } while (0)
 namespace pipe {
 constexpr uint32_t XR_BYTES = 128 * 16, XF_BYTES = 4 * 32 * 8;      // one group's x: fp32 residual (the dense warps' accumulator fragments),
@@ -461,9 +461,10 @@ constexpr uint32_t X_BYTES = G * XS * 4, SK_BYTES = G * HS * 4;      // a group'
 constexpr uint32_t OFF_BAR = 0;                                   // xhfull[NG], xrfull[NG], skfull[NG], notefull[NG]
 constexpr uint32_t OFF_NOTE = 256;                                // int note[NG][G], last[NG][G]
 constexpr uint32_t OFF_SLOT = OFF_NOTE + 2 * NG * G * 4;          // int slot[NG][2][G]
-constexpr uint32_t OFF_ZF = OFF_SLOT + NG * 2 * G * 4;            // uint32 zf[2][4][2][32]: gated activations of the two blocks, B fragments
-constexpr uint32_t OFF_XL = OFF_ZF + 2 * XF_BYTES;                // uint2 xl[4][32]: block 0's output (CTA 0: also the embedding), B fragments
-constexpr uint32_t OFF_SKIN = (OFF_XL + XF_BYTES + 127) & ~127u;  // float skin[NG][G][HS]  (same offset in every role but CTA 0)
+constexpr uint32_t XH_BYTES = G * XH * 2;                         // 8 streams x 64 channels of fp16, rows padded to 72 (conflict-free fragment loads)
+constexpr uint32_t OFF_ZF = OFF_SLOT + NG * 2 * G * 4;            // __half zh[2][G][XH]: gated activations of the two blocks
+constexpr uint32_t OFF_XL = OFF_ZF + 2 * XH_BYTES;                // __half xl[G][XH]: block 0's output (CTA 0: also the embedding)
+constexpr uint32_t OFF_SKIN = (OFF_XL + XH_BYTES + 127) & ~127u;  // float skin[NG][G][HS]  (same offset in every role but CTA 0)
 constexpr uint32_t OFF_XIN = OFF_SKIN + NG * SK_BYTES;            // block CTAs: float4 xr[NG][128]   (same offset in all of them)
 constexpr uint32_t OFF_XHIN = OFF_XIN + NG * XR_BYTES;            //             uint2 xf[NG][4][32]
 constexpr uint32_t OFF_TAPS = OFF_XHIN + NG * XF_BYTES;           //             float taps[NG][2][G][XS]
@@ -546,6 +547,11 @@ __device__ __forceinline__ void wait_token(uint64_t* bar, uint32_t parity) {
   __syncwarp();
 #endif
 }
+// float -> unsigned key with the same order (-0 < +0; NaNs sort to the ends)
+__device__ __forceinline__ uint32_t ordered_key(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 __device__ __forceinline__ uint32_t try_wait_once(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -627,8 +633,10 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     auto block_cta = [&](auto first_c, auto to_head_c) {
     constexpr bool first = decltype(first_c)::value, to_head = decltype(to_head_c)::value;
     const int l0 = p.lpc * rank, nl = min(p.lpc, N - l0);
-    uint32_t (*zf)[4][2][32] = reinterpret_cast<uint32_t (*)[4][2][32]>(sm + OFF_ZF);      // [block][k-tile][fragment half][lane]
-    uint2 (*xl)[32] = reinterpret_cast<uint2 (*)[32]>(sm + OFF_XL);                          // [k-tile][lane]
+    // exchanges inside the CTA go through [stream][channel] rows of fp16: the producers scatter halves, the consumers read B fragments
+    // as 32-bit words (the transposing movmatrix costs 25 cycles of latency: only the token that leaves the CTA pays it)
+    __half (*zh)[G][XH] = reinterpret_cast<__half (*)[G][XH]>(sm + OFF_ZF);      // [block][stream][channel]
+    __half (*xl)[XH] = reinterpret_cast<__half (*)[XH]>(sm + OFF_XL);            // [stream][channel]
     float* taps = reinterpret_cast<float*>(sm + (first ? OFF_TAPS0 : OFF_TAPS));      // [NG][2][G][XS]
     float* wc = reinterpret_cast<float*>(sm + OFF_WC);                                 // CTA 0
     // ---- resident A fragments (same per-warp ownership as gen_steps_bf16_kernel)
@@ -693,7 +701,8 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
         if (li < nl) {
 #pragma unroll
           for (int kt = 0; kt < 4; ++kt) {
-            const uint32_t b0 = zf[li][kt][0][lane], b1 = zf[li][kt][1][lane];
+            const __half* zr = &zh[li][n8][kt * 16 + 2 * q];
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(zr), b1 = *reinterpret_cast<const uint32_t*>(zr + 8);
             mma_f16(sk[0], w2w[li][4 + kt], b0, b1);
             mma_f16(sk[1], w2w[li][8 + kt], b0, b1);
           }
@@ -735,7 +744,6 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
       for (int g = 0; g < ng; ++g) {
         const int n_act = n_act_of(g);
         const int chd = 16 * (warp & 3) + n8, s0 = 2 * q, s1 = 2 * q + 1;      // dense warps: accumulator fragment = channels chd, chd + 8
-        const uint2* xfrag;     // this block's input, B fragments [k-tile][lane]
         float (*sko)[HS];       // where this CTA's outgoing skip sums are staged
         float dn[4] = {0.f, 0.f, 0.f, 0.f};      // dense warps: the residual stream, fp32, in accumulator-fragment layout
         if (first) {
@@ -752,17 +760,16 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               const int s_ = 2 * q + (r & 1), c_ = chd + 8 * (r >> 1);
               dn[r] = wc[last[g][s_] * 64 + c_] + wc[(256 + note[g][s_]) * 64 + c_] + (HAS_BIAS ? p.bias_c[c_] : 0.f);
             }
-            xl[warp][lane] = make_uint2(movm_t(pack_h2(dn[0], dn[1])), movm_t(pack_h2(dn[2], dn[3])));
+            xl[s0][chd] = __float2half_rn(dn[0]); xl[s1][chd] = __float2half_rn(dn[1]);
+            xl[s0][chd + 8] = __float2half_rn(dn[2]); xl[s1][chd + 8] = __float2half_rn(dn[3]);
           }
           __syncthreads();      // (also tid 0's wait on the staging set before anybody writes it)
           if (tid < G) last[g][tid] = note[g][tid];
-          xfrag = &xl[0][0];
         } else {
           GEN_TS(0);
           wait_token(&xhfull[g], step & 1);      // every thread waits for itself: no barrier between the token and its first use
           GEN_TS(1);
           if (TRACE && g == 0 && tid == 0 && step < 64 && cid == 0) g_gen_ts[1024 + step * 16 + rank] = (long long)global_ns();
-          xfrag = reinterpret_cast<const uint2*>(sm + OFF_XHIN) + g * 128;
           sko = skin[g];
         }
         float pv[2][4];      // what the two blocks push into their queues (dense warps)
@@ -772,9 +779,16 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             const int i = l0 + li;
             const bool last_block = li == nl - 1;
             // ---- [f|g] = (W0 old, precomputed) + W1 x : warp w owns filter and gate channels 8w..8w+7 for all 8 streams
-            uint2 bx[4];
+            uint2 bx[4];      // this block's input as B fragments: the token's own layout, or rows of the local exchange buffer
+            if (li == 0 && !first) {
 #pragma unroll
-            for (int kt = 0; kt < 4; ++kt) bx[kt] = xfrag[kt * 32 + lane];
+              for (int kt = 0; kt < 4; ++kt) bx[kt] = reinterpret_cast<const uint2*>(sm + OFF_XHIN)[(g * 4 + kt) * 32 + lane];
+            } else {
+              const __half* xrow = &xl[n8][2 * q];
+#pragma unroll
+              for (int kt = 0; kt < 4; ++kt)
+                bx[kt] = make_uint2(*reinterpret_cast<const uint32_t*>(xrow + kt * 16), *reinterpret_cast<const uint32_t*>(xrow + kt * 16 + 8));
+            }
             float c0[4] = {pre[li][0], pre[li][1], pre[li][2], pre[li][3]}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f},
                   c3[4] = {0.f, 0.f, 0.f, 0.f};
             mma_f16(c0, fgw[li][4], bx[0].x, bx[0].y);
@@ -787,7 +801,8 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             {
               const float z0 = gate_z((c0[0] + c1[0]) + (c2[0] + c3[0]), (c0[2] + c1[2]) + (c2[2] + c3[2]));
               const float z1 = gate_z((c0[1] + c1[1]) + (c2[1] + c3[1]), (c0[3] + c1[3]) + (c2[3] + c3[3]));
-              zf[li][warp >> 1][warp & 1][lane] = movm_t(pack_h2(z0, z1));      // channels 8w..8w+7 = half a k-tile
+              zh[li][2 * q][8 * warp + n8] = __float2half_rn(z0);      // warp w: channels 8w..8w+7 of streams 2q, 2q+1
+              zh[li][2 * q + 1][8 * warp + n8] = __float2half_rn(z1);
             }
             __syncthreads();
             GEN_TS(3 + 4 * li);
@@ -796,7 +811,9 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               // here, sent as the B fragments of post_process_1's MMAs straight from the accumulators
               float sk[2][4];
               skip_mmas(sk);
+              GEN_TS(10);
               if (!first) wait_token(&skfull[g], step & 1);
+              GEN_TS(11);
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 float v[4];
@@ -808,13 +825,15 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
                 st_async_u2(r_hf + (uint32_t)((g * 16 + 2 * warp + j) * 32 + lane) * 8, movm_t(pack_h2(v[0], v[1])), movm_t(pack_h2(v[2], v[3])),
                             r_skfull + g * 8);
               }
+              GEN_TS(12);
             }
             if (warp < 4) {
               uint32_t bz[4][2];
 #pragma unroll
               for (int kt = 0; kt < 4; ++kt) {
-                bz[kt][0] = zf[li][kt][0][lane];
-                bz[kt][1] = zf[li][kt][1][lane];
+                const __half* zr = &zh[li][n8][kt * 16 + 2 * q];
+                bz[kt][0] = *reinterpret_cast<const uint32_t*>(zr);
+                bz[kt][1] = *reinterpret_cast<const uint32_t*>(zr + 8);
               }
               float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f}, d3[4] = {0.f, 0.f, 0.f, 0.f};
               if (HAS_BIAS) {
@@ -837,7 +856,8 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
 #pragma unroll
               for (int r = 0; r < 4; ++r) pv[li][r] = PUSH_OUT ? dn[r] : xi[r];      // fast_generate.py:128-129
               if (!last_block) {
-                xl[warp][lane] = make_uint2(movm_t(pack_h2(dn[0], dn[1])), movm_t(pack_h2(dn[2], dn[3])));      // the next block's input
+                xl[s0][chd] = __float2half_rn(dn[0]); xl[s1][chd] = __float2half_rn(dn[1]);      // the next block's input
+                xl[s0][chd + 8] = __float2half_rn(dn[2]); xl[s1][chd + 8] = __float2half_rn(dn[3]);
               } else if (!to_head) {
                 // the token leaves straight from the dense warps' registers: first the fragments the next CTA's MMAs wait for, then the
                 // residual.  The skip MMAs, the queue pushes and the skip sums below are off the ring's critical path.
@@ -847,24 +867,11 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             }
             if (!last_block) {
               __syncthreads();      // block li + 1 reads what the dense warps wrote
-              xfrag = &xl[0][0];
             }
             GEN_TS(5 + 4 * li);
           }
         }
-        // ================= behind the token: queue pushes, skip MMAs of both blocks, running skip sums, next taps, next W0 . old
-        if (warp < 4) {
-          float* const ring0 = reinterpret_cast<float*>(sptr(g, s0) + 16);
-          float* const ring1 = reinterpret_cast<float*>(sptr(g, s1) + 16);
-#pragma unroll
-          for (int li = 0; li < 2; ++li)
-            if (li < nl) {
-              const int i = l0 + li;
-              const int o0 = (p.ring_off[i] + slot[g][li][s0]) * 64 + chd, o1 = (p.ring_off[i] + slot[g][li][s1]) * 64 + chd;
-              if (s0 < n_act) { ring0[o0] = pv[li][0]; ring0[o0 + 8] = pv[li][2]; }
-              if (s1 < n_act) { ring1[o1] = pv[li][1]; ring1[o1 + 8] = pv[li][3]; }
-            }
-        }
+        // ================= behind the token: skip MMAs of both blocks, running skip sums, queue pushes, next taps, next W0 . old
         if (!to_head) {
           float sk[2][4];
           skip_mmas(sk);
@@ -880,7 +887,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the bulk copy below reads these generic-proxy writes
         }
-        __syncthreads();      // (also: the queue pushes above happen before the tap requests below)
+        __syncthreads();
         GEN_TS(12);
         if (tid == 0) {
           if (!to_head) {      // the running skip sums -> the next CTA's slot of this group
@@ -895,6 +902,19 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             mbar_expect_tx(&skfull[g], SK_BYTES);
           }
         }
+        if (warp < 4) {
+          float* const ring0 = reinterpret_cast<float*>(sptr(g, s0) + 16);
+          float* const ring1 = reinterpret_cast<float*>(sptr(g, s1) + 16);
+#pragma unroll
+          for (int li = 0; li < 2; ++li)
+            if (li < nl) {
+              const int i = l0 + li;
+              const int o0 = (p.ring_off[i] + slot[g][li][s0]) * 64 + chd, o1 = (p.ring_off[i] + slot[g][li][s1]) * 64 + chd;
+              if (s0 < n_act) { ring0[o0] = pv[li][0]; ring0[o0 + 8] = pv[li][2]; }
+              if (s1 < n_act) { ring1[o1] = pv[li][1]; ring1[o1 + 8] = pv[li][3]; }
+            }
+        }
+        __syncthreads();      // the queue pushes above happen before the tap requests below (a queue of dilation 1 is read back at once)
         if (step + 1 < p.n_steps) prefetch_taps(g, 1);
         else __pipeline_commit();               // (keeps the commit-group accounting uniform)
         if (g == ng - 1)
@@ -941,6 +961,11 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int k = 0; k < 16; ++k) p1w[j][k] = headA[((2 * warp + j) * 16 + k) * 32 + lane];
+    uint4 p2w[2][6];       // post_process_2: k-tiles 0..5 of the two m-tiles resident too; k-tiles 6..15 come from shared memory
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) p2w[j][k] = headA[FRAG_HEAD + ((2 * warp + j) * 16 + k) * 32 + lane];
     for (int e = tid; e < FRAG_HEAD; e += 256) p2s[e] = headA[FRAG_HEAD + e];
     __syncthreads();
     const uint32_t r_note = map_to(sm_base + OFF_NOTE, 0), r_notefull = map_to(smem_u32(notefull), 0);
@@ -973,6 +998,9 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             if (which == 0) {
               mma_f16(c[0][kt & 3], p1w[0][kt], b.x, b.y);
               mma_f16(c[1][kt & 3], p1w[1][kt], b.x, b.y);
+            } else if (kt < 6) {
+              mma_f16(c[0][kt & 3], p2w[0][kt], b.x, b.y);
+              mma_f16(c[1][kt & 3], p2w[1][kt], b.x, b.y);
             } else {
               const uint4 a0 = p2s[((2 * warp) * 16 + kt) * 32 + lane], a1 = p2s[((2 * warp + 1) * 16 + kt) * 32 + lane];
               mma_f16(c[0][kt & 3], a0, b.x, b.y);
@@ -1018,12 +1046,15 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               const float v = c[k >> 1][0][2 * (k & 1) + b];
               if (v > bv[b]) { bv[b] = v; bi[b] = 32 * warp + 16 * (k >> 1) + 8 * (k & 1) + n8; }
             }
+            // over the 8 row lanes by shuffles (a partial-mask redux.sync measured 5x slower); floats compared as ordered unsigned keys
+            uint32_t key = ordered_key(bv[b]);
 #pragma unroll
             for (int o = 4; o < 32; o <<= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, bv[b], o);
+              const uint32_t ok = __shfl_xor_sync(0xffffffffu, key, o);
               const int oi = __shfl_xor_sync(0xffffffffu, bi[b], o);
-              if (ov > bv[b] || (ov == bv[b] && oi < bi[b])) { bv[b] = ov; bi[b] = oi; }
+              if (ok > key || (ok == key && oi < bi[b])) { key = ok; bi[b] = oi; }
             }
+            bv[b] = __uint_as_float(key);      // (the key; compared as a key below)
           }
           if (n8 == 0) {
             cand[warp * G + 2 * q] = make_float2(bv[0], __int_as_float(bi[0]));
@@ -1034,14 +1065,9 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
           {
             const int s = warp;      // one warp per stream; lanes 0..7 hold the 8 warps' candidates (rows increase with the warp)
             const float2 cv = cand[(lane & 7) * G + s];
-            float v = cv.x;
-            int idx = __float_as_int(cv.y);
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-              const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-              if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-            }
+            const uint32_t key = __float_as_uint(cv.x);
+            const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+            const int idx = (int)__reduce_min_sync(0xffffffffu, key == kmax ? __float_as_uint(cv.y) : 0xffffu);
             if (lane == 0) {
               st_async_u1(r_note + (uint32_t)(g * G + s) * 4, (uint32_t)idx, r_notefull + g * 8);      // CTA 0's note[g][s]
               if (s < n_act) out[(int64_t)step * p.n_streams + (g0 + g) * G + s] = idx;
@@ -1146,7 +1172,7 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
     // weights-stationary cluster pipeline: ceil(N / 2) block CTAs + the head CTA per cluster, 8 groups of 8 streams per cluster
     static const int lpc_env = [] { const char* e = getenv("WN_GEN_LPC"); return e && e[0] == '1' ? 1 : 2; }();
     p.lpc = (lpc_env == 1 && m.n_layers <= 15) ? 1 : 2;
-    p.trace = 0;
+    p.trace = [] { const char* e = getenv("WN_TS_RANK"); return e ? atoi(e) : 1; }();      // (the CTA whose timeline WN_TS=1 records)
     const int cs = (m.n_layers + p.lpc - 1) / p.lpc + 1;
     const int groups = (int)ceil_div(n_streams, G);
     const bool out_push = push == WN_PUSH_OUTPUT;
