@@ -691,6 +691,15 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     const uint32_t r_skfull = map_to(smem_u32(skfull), rank + 1);
     const uint32_t r_hf = map_to(sm_base + OFF_HF, rank + 1);      // (the last block CTA: the head's fragment slots)
     // skip MMAs of this CTA's blocks: warp w owns skip channels 32w..32w+31 (m-tiles 2w, 2w+1)
+    auto skip_block = [&](float (&sk)[2][4], int li) {
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        const __half* zr = &zh[li][n8][kt * 16 + 2 * q];
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(zr), b1 = *reinterpret_cast<const uint32_t*>(zr + 8);
+        mma_f16(sk[0], w2w[li][4 + kt], b0, b1);
+        mma_f16(sk[1], w2w[li][8 + kt], b0, b1);
+      }
+    };
     auto skip_mmas = [&](float (&sk)[2][4]) {
 #pragma unroll
       for (int j = 0; j < 2; ++j)
@@ -698,15 +707,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
         for (int r = 0; r < 4; ++r) sk[j][r] = 0.f;
 #pragma unroll
       for (int li = 0; li < 2; ++li)
-        if (li < nl) {
-#pragma unroll
-          for (int kt = 0; kt < 4; ++kt) {
-            const __half* zr = &zh[li][n8][kt * 16 + 2 * q];
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(zr), b1 = *reinterpret_cast<const uint32_t*>(zr + 8);
-            mma_f16(sk[0], w2w[li][4 + kt], b0, b1);
-            mma_f16(sk[1], w2w[li][8 + kt], b0, b1);
-          }
-        }
+        if (li < nl) skip_block(sk, li);
     };
 
     // W0 . old of both blocks of group gg (the taps are known one ring period ahead): computed while the group's token is still
@@ -797,6 +798,17 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             mma_f16(c3, fgw[li][7], bx[3].x, bx[3].y);
             uint32_t res_ok = 1;
             if (li == 0 && !first && warp < 4) res_ok = try_wait_once(&xrfull[g], step & 1);      // (the answer is read behind the barrier below)
+            float sk[2][4];
+            uint32_t sk_ok = 1;
+            if (last_block && to_head) {
+              // the last block CTA: the earlier block's skip MMAs run in the shadow of this block's gate, the upstream sums are probed
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) sk[j][r] = 0.f;
+              if (li > 0) skip_block(sk, 0);
+              if (!first) sk_ok = try_wait_once(&skfull[g], step & 1);
+            }
             GEN_TS(2 + 4 * li);
             {
               const float z0 = gate_z((c0[0] + c1[0]) + (c2[0] + c3[0]), (c0[2] + c1[2]) + (c2[2] + c3[2]));
@@ -809,10 +821,9 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             if (last_block && to_head) {
               // the last block CTA: what the head waits for is the skip sum, so it goes first - relu and the fp16 conversion applied
               // here, sent as the B fragments of post_process_1's MMAs straight from the accumulators
-              float sk[2][4];
-              skip_mmas(sk);
+              skip_block(sk, li);
               GEN_TS(10);
-              if (!first) wait_token(&skfull[g], step & 1);
+              if (!sk_ok) wait_token(&skfull[g], step & 1);
               GEN_TS(11);
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
@@ -828,6 +839,11 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               GEN_TS(12);
             }
             if (warp < 4) {
+              if (li == 0 && !first) {      // the fp32 residual travels behind the fragments, on its own barrier (probed one phase ago)
+                if (!res_ok) wait_token(&xrfull[g], step & 1);
+                const uint4 rv = lds128(sm_base + OFF_XIN + (uint32_t)(g * 128 + tid) * 16);
+                dn[0] = __uint_as_float(rv.x); dn[1] = __uint_as_float(rv.y); dn[2] = __uint_as_float(rv.z); dn[3] = __uint_as_float(rv.w);
+              }
               uint32_t bz[4][2];
 #pragma unroll
               for (int kt = 0; kt < 4; ++kt) {
@@ -844,11 +860,6 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               mma_f16(d1, w2w[li][1], bz[1][0], bz[1][1]);
               mma_f16(d2, w2w[li][2], bz[2][0], bz[2][1]);
               mma_f16(d3, w2w[li][3], bz[3][0], bz[3][1]);
-              if (li == 0 && !first) {      // the fp32 residual travels behind the fragments, on its own barrier; fetched behind the MMAs
-                if (!res_ok) wait_token(&xrfull[g], step & 1);
-                const uint4 rv = lds128(sm_base + OFF_XIN + (uint32_t)(g * 128 + tid) * 16);
-                dn[0] = __uint_as_float(rv.x); dn[1] = __uint_as_float(rv.y); dn[2] = __uint_as_float(rv.z); dn[3] = __uint_as_float(rv.w);
-              }
               const float xi[4] = {dn[0], dn[1], dn[2], dn[3]};
 #pragma unroll
               for (int r = 0; r < 4; ++r) dn[r] = ((d0[r] + d1[r]) + (d2[r] + d3[r])) + dn[r];
