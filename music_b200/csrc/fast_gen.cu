@@ -42,7 +42,6 @@ constexpr int FRAG_HEAD = 16 * 16 * 32;
 
 struct FastGenParams {
   int n_layers, n_streams, n_steps, push, has_bias;
-  int lpc;                         // gen_pipe_kernel: blocks per CTA (2; 1 in timing experiments)
   int gpc;                         // gen_pipe_kernel: groups of 8 streams per cluster (1..NG)
   int trace;                       // WN_TS=1: clock64 stamps (GEN_TS)
   int dil[GEN_MAXL];
@@ -458,31 +457,44 @@ namespace pipe {
 constexpr uint32_t XR_BYTES = 128 * 16, XF_BYTES = 4 * 32 * 8;      // one group's x: fp32 residual (the dense warps' accumulator fragments),
                                                                       // fp16 B fragments [k-tile 4][lane 32] of every warp's MMAs
 constexpr uint32_t X_BYTES = G * XS * 4, SK_BYTES = G * HS * 4;      // a group's taps of one block (fp32 rows), its skip sums
-constexpr uint32_t OFF_BAR = 0;                                   // xhfull[NG], xrfull[NG], skfull[NG], notefull[NG]
-constexpr uint32_t OFF_NOTE = 256;                                // int note[NG][G], last[NG][G]
-constexpr uint32_t OFF_SLOT = OFF_NOTE + 2 * NG * G * 4;          // int slot[NG][2][G]
-constexpr uint32_t XH_BYTES = G * XH * 2;                         // 8 streams x 64 channels of fp16, rows padded to 72 (conflict-free fragment loads)
-constexpr uint32_t OFF_ZF = OFF_SLOT + NG * 2 * G * 4;            // __half zh[2][G][XH]: gated activations of the two blocks
-constexpr uint32_t OFF_XL = OFF_ZF + 2 * XH_BYTES;                // __half xl[G][XH]: block 0's output (CTA 0: also the embedding)
-constexpr uint32_t OFF_SKIN = (OFF_XL + XH_BYTES + 127) & ~127u;  // float skin[NG][G][HS]  (same offset in every role but CTA 0)
-constexpr uint32_t OFF_XIN = OFF_SKIN + NG * SK_BYTES;            // block CTAs: float4 xr[NG][128]   (same offset in all of them)
-constexpr uint32_t OFF_XHIN = OFF_XIN + NG * XR_BYTES;            //             uint2 xf[NG][4][32]
-constexpr uint32_t OFF_TAPS = OFF_XHIN + NG * XF_BYTES;           //             float taps[NG][2][G][XS]
-constexpr uint32_t BLOCK_BYTES = OFF_TAPS + NG * 2 * X_BYTES;
-constexpr uint32_t OFF_WC = OFF_SKIN;                             // CTA 0 (nothing arrives but notes): float wc[2][256][64]
-constexpr uint32_t OFF_TAPS0 = OFF_WC + 2 * 256 * 64 * 4;         //        its taps
-constexpr uint32_t OFF_STG0 = OFF_TAPS0 + NG * 2 * X_BYTES;       //        two staging sets of outgoing skip sums
-constexpr uint32_t STG_BYTES = SK_BYTES;
-constexpr uint32_t CTA0_BYTES = OFF_STG0 + 2 * STG_BYTES;
-constexpr uint32_t HF_BYTES = 16 * 32 * 8;                            // a group's relu(skip sums), fp16 B fragments [k-tile 16][lane 32]
-constexpr uint32_t OFF_HF = OFF_SKIN;                             // head: uint2 hf[NG][16][32] (what the last block CTA sends)
-constexpr uint32_t OFF_P2 = OFF_HF + NG * HF_BYTES;               //       uint4 p2[FRAG_HEAD]
-constexpr uint32_t OFF_HH = OFF_P2 + FRAG_HEAD * 16;              //       __half hh[2][G][HH]
-constexpr uint32_t OFF_LG = OFF_HH + 2 * G * HH * 2;              //       float lg[G][HS]
-constexpr uint32_t HEAD_BYTES = OFF_LG + G * HS * 4;
-constexpr uint32_t TOTAL = HEAD_BYTES > CTA0_BYTES ? (HEAD_BYTES > BLOCK_BYTES ? HEAD_BYTES : BLOCK_BYTES) : (CTA0_BYTES > BLOCK_BYTES ? CTA0_BYTES : BLOCK_BYTES);
-static_assert(TOTAL <= 227 * 1024, "pipeline generation kernel: shared memory");
-static_assert(SK_BYTES % 16 == 0 && OFF_SKIN % 16 == 0 && OFF_STG0 % 16 == 0 && OFF_XIN % 16 == 0 && OFF_XHIN % 16 == 0, "16-byte units");
+constexpr uint32_t XH_BYTES = G * XH * 2;                            // 8 streams x 64 channels of fp16, rows padded to 72 (conflict-free fragment loads)
+constexpr uint32_t HF_BYTES = 16 * 32 * 8;                           // a group's relu(skip sums), fp16 B fragments [k-tile 16][lane 32]
+constexpr uint32_t WS_BLOCK = 12 * 256 * 16;                         // one block's off-critical-path A fragments in shared memory: per thread
+                                                                      // 4 of W0 (the old tap) and 8 of the skip convolution, [fragment 12][thread 256]
+// Shared-memory map for NGv group slots per CTA and up to NBv blocks per CTA (CTA 0 always has two).  The slots other CTAs write into
+// (notes, x, skip sums, the head's fragments) sit at the same offsets in every role.
+template <int NGv, int NBv>
+struct PipeL {
+  static constexpr uint32_t OFF_BAR = 0;                                   // xhfull[NGv], xrfull[NGv], skfull[NGv], notefull[NGv]
+  static constexpr uint32_t OFF_NOTE = 256;                                // int note[NGv][G], last[NGv][G]
+  static constexpr uint32_t OFF_SLOT = OFF_NOTE + 2 * NGv * G * 4;         // int slot[NGv][NBv][G]
+  static constexpr uint32_t OFF_ZF = OFF_SLOT + NGv * NBv * G * 4;         // __half zh[NBv][G][XH]: gated activations of the CTA's blocks
+  static constexpr uint32_t OFF_XL = OFF_ZF + NBv * XH_BYTES;              // __half xl[G][XH]: a block's output (CTA 0: also the embedding)
+  static constexpr uint32_t OFF_SKIN = (OFF_XL + XH_BYTES + 127) & ~127u;  // float skin[NGv][G][HS]  (same offset in every role but CTA 0)
+  static constexpr uint32_t OFF_XIN = OFF_SKIN + NGv * SK_BYTES;           // block CTAs: float4 xr[NGv][128]
+  static constexpr uint32_t OFF_XHIN = OFF_XIN + NGv * XR_BYTES;           //             uint2 xf[NGv][4][32]
+  static constexpr uint32_t OFF_TAPS = OFF_XHIN + NGv * XF_BYTES;          //             float taps[NGv][NBv][G][XS]
+  static constexpr uint32_t OFF_WS = OFF_TAPS + NGv * NBv * X_BYTES;       //             uint4 ws[NBv][12][256] (NBv > 2 only)
+  static constexpr uint32_t OFF_SKIN2 = OFF_WS;                            // the last block CTA (two blocks, no ws): float skin2[NGv][G][HS]
+  static constexpr uint32_t BLOCK_BYTES = OFF_WS + (NBv > 2 ? NBv * WS_BLOCK : 0);
+  static constexpr uint32_t OFF_WC = OFF_SKIN;                             // CTA 0 (nothing arrives but notes): float wc[2][256][64]
+  static constexpr uint32_t OFF_TAPS0 = OFF_WC + 2 * 256 * 64 * 4;         //        its taps [NGv][2][G][XS]
+  static constexpr uint32_t OFF_STG0 = OFF_TAPS0 + NGv * 2 * X_BYTES;      //        two staging sets of outgoing skip sums
+  static constexpr uint32_t STG_BYTES = SK_BYTES;
+  static constexpr uint32_t CTA0_BYTES = OFF_STG0 + 2 * STG_BYTES;
+  static constexpr uint32_t OFF_HF = OFF_SKIN;                             // head: uint2 hf[NGv][16][32] (what the last block CTA sends)
+  static constexpr uint32_t OFF_P2 = OFF_HF + NGv * HF_BYTES;              //       uint4 p2[FRAG_HEAD]
+  static constexpr uint32_t OFF_HH = OFF_P2 + FRAG_HEAD * 16;              //       relu(post_process_1) fragments, greedy candidates
+  static constexpr uint32_t OFF_LG = OFF_HH + 2 * G * HH * 2;              //       float lg[G][HS]
+  static constexpr uint32_t HEAD_BYTES = OFF_LG + G * HS * 4;
+  static constexpr uint32_t TOTAL =
+      HEAD_BYTES > CTA0_BYTES ? (HEAD_BYTES > BLOCK_BYTES ? HEAD_BYTES : BLOCK_BYTES) : (CTA0_BYTES > BLOCK_BYTES ? CTA0_BYTES : BLOCK_BYTES);
+  static_assert(TOTAL <= 227 * 1024, "pipeline generation kernel: shared memory");
+  static_assert(4 * NGv * 8 + 8 <= 256 || NBv == 2, "barriers");
+  static_assert(NBv == 2 || NGv == 1, "the second skip slot is for one group");
+  static_assert(SK_BYTES % 16 == 0 && OFF_SKIN % 16 == 0 && OFF_STG0 % 16 == 0 && OFF_XIN % 16 == 0 && OFF_XHIN % 16 == 0 && OFF_WS % 16 == 0, "16-byte units");
+};
+constexpr int pipe_groups(int bpc) { return bpc == 2 ? 8 : 1; }      // group slots per cluster
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
@@ -576,11 +588,20 @@ __device__ __forceinline__ void cp_wait_dyn(int n) {      // all but the newest 
 
 // HAS_BIAS / PUSH_OUT are compile-time: every block of the ring is a chain of ~400 dependent-latency instructions per warp, and the
 // run-time tests (and the predicated bias loads behind them) were a measurable part of it
-template <bool HAS_BIAS, bool PUSH_OUT, bool TRACE>
+// BPC = blocks per CTA behind CTA 0 (which always has two).  2: every fragment in registers, 8 group slots per cluster.  4: only what the
+// token waits for stays in registers (W1 of [f|g], the dense convolution); W0 and the skip convolution, which run behind / ahead of
+// the token, are read from shared memory - 8 block CTAs instead of 15, seven hops less per step, one group per cluster.
+template <bool HAS_BIAS, bool PUSH_OUT, bool TRACE, int BPC>
 __global__ void __launch_bounds__(256, 1)
 gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __restrict__ first_note, const float* __restrict__ uniforms,
                 int64_t* __restrict__ out, float* __restrict__ logits_out) {
   using namespace pipe;
+  constexpr int NGV = pipe_groups(BPC);
+  using L = PipeL<NGV, BPC>;
+  constexpr uint32_t OFF_BAR = L::OFF_BAR, OFF_NOTE = L::OFF_NOTE, OFF_SLOT = L::OFF_SLOT, OFF_ZF = L::OFF_ZF, OFF_XL = L::OFF_XL,
+                     OFF_SKIN = L::OFF_SKIN, OFF_XIN = L::OFF_XIN, OFF_XHIN = L::OFF_XHIN, OFF_TAPS = L::OFF_TAPS, OFF_WS = L::OFF_WS,
+                     OFF_WC = L::OFF_WC, OFF_TAPS0 = L::OFF_TAPS0, OFF_STG0 = L::OFF_STG0, STG_BYTES = L::STG_BYTES, OFF_HF = L::OFF_HF,
+                     OFF_P2 = L::OFF_P2, OFF_HH = L::OFF_HH, OFF_LG = L::OFF_LG, OFF_SKIN2 = L::OFF_SKIN2;
   extern __shared__ __align__(128) uint8_t sm[];
   const int N = p.n_layers;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -590,31 +611,40 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
   const int g0 = cid * p.gpc, ng = min(p.gpc, groups_total - g0);
   const bool is_head = rank == CS - 1;
   uint64_t* xhfull = reinterpret_cast<uint64_t*>(sm + OFF_BAR);    // a group's x has arrived, fp16 fragments (what the first MMAs need): tx bytes
-  uint64_t* xrfull = xhfull + NG;                                   // its fp32 residual (needed one exchange phase later)
-  uint64_t* skfull = xhfull + 2 * NG;                               // its running skip sums (a bulk copy, behind the token)
-  uint64_t* notefull = xhfull + 3 * NG;                             // CTA 0: the head's picks of a group
+  uint64_t* xrfull = xhfull + NGV;                                  // its fp32 residual (needed one exchange phase later)
+  uint64_t* skfull = xhfull + 2 * NGV;                              // its running skip sums (a bulk copy, behind the token)
+  uint64_t* notefull = xhfull + 3 * NGV;                            // CTA 0: the head's picks of a group
   int (*note)[G] = reinterpret_cast<int (*)[G]>(sm + OFF_NOTE);
-  int (*last)[G] = reinterpret_cast<int (*)[G]>(sm + OFF_NOTE + NG * G * 4);
-  int (*slot)[2][G] = reinterpret_cast<int (*)[2][G]>(sm + OFF_SLOT);
+  int (*last)[G] = reinterpret_cast<int (*)[G]>(sm + OFF_NOTE + NGV * G * 4);
+  int (*slot)[BPC][G] = reinterpret_cast<int (*)[BPC][G]>(sm + OFF_SLOT);
   float (*skin)[G][HS] = reinterpret_cast<float (*)[G][HS]>(sm + OFF_SKIN);
+  // BPC > 2, blocks that do not divide: the CTA before the last has at most two blocks ("small", register-resident).  The chain of
+  // running skip sums then bypasses it - the CTA before it sends to the last block CTA directly, and the small CTA sends its own
+  // contribution there too (second slot) - because a CTA with shared-memory skip weights emits its sums too late for a short hop.
+  const int n_last_b = N > 2 ? min(2, N - 2) : 0, n_mid_b = max(0, N - 2 - n_last_b);
+  const bool has_small = BPC > 2 && n_mid_b > 0 && (n_mid_b % BPC == 1 || n_mid_b % BPC == 2);
+  uint64_t* skfull2 = xhfull + 4 * NGV;                             // the last block CTA: the small CTA's own skip sums (has_small)
+  float (*skin2)[HS] = reinterpret_cast<float (*)[HS]>(sm + OFF_SKIN2);
   const uint32_t sm_base = smem_u32(sm);
   if (tid == 0) {
-    for (int g = 0; g < NG; ++g) {
+    for (int g = 0; g < NGV; ++g) {
       mbar_init(&xhfull[g], 1);       // the consumer's own arming arrival; the data arrive as tx bytes
       mbar_init(&xrfull[g], 1);
       mbar_init(&skfull[g], 1);
+      if (BPC > 2) mbar_init(&skfull2[g], 1);
       mbar_init(&notefull[g], 1);     // CTA 0: the 8 picks of the head arrive as 32 tx bytes
     }
     fence_barrier_init();
     if (rank == 0)
-      for (int g = 0; g < NG; ++g) mbar_expect_tx(&notefull[g], G * 4);
+      for (int g = 0; g < NGV; ++g) mbar_expect_tx(&notefull[g], G * 4);
     if (rank > 0)
-      for (int g = 0; g < NG; ++g) {      // armed for step 0
+      for (int g = 0; g < NGV; ++g) {      // armed for step 0
         if (!is_head) {
           mbar_expect_tx(&xhfull[g], XF_BYTES);
           mbar_expect_tx(&xrfull[g], XR_BYTES);
         }
-        mbar_expect_tx(&skfull[g], is_head ? HF_BYTES : SK_BYTES);
+        if (!(has_small && rank == CS - 3)) mbar_expect_tx(&skfull[g], is_head ? HF_BYTES : SK_BYTES);      // (nothing is sent to the small CTA)
+        if (has_small && rank == CS - 2) mbar_expect_tx(&skfull2[g], SK_BYTES);
       }
   }
   auto stream_of = [&](int g, int s) { return min((g0 + g) * G + s, p.n_streams - 1); };
@@ -630,31 +660,54 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     // ============================================================ block CTA: blocks l0, l0 + 1
     // The CTA's role (first: gathers the embedding, nothing arrives but notes; to_head: its skip sums go to the head) is a compile-time
     // constant of the body: the role tests sat on the token's critical path as taken branches.
-    auto block_cta = [&](auto first_c, auto to_head_c) {
-    constexpr bool first = decltype(first_c)::value, to_head = decltype(to_head_c)::value;
-    const int l0 = p.lpc * rank, nl = min(p.lpc, N - l0);
+    auto block_cta = [&](auto first_c, auto to_head_c, auto small_c) {
+    constexpr bool first = decltype(first_c)::value, to_head = decltype(to_head_c)::value, small = decltype(small_c)::value;
+    // CTA 0 and the last block CTA have two blocks with every fragment in registers (CTA 0's shared memory holds the embedding table;
+    // the last CTA's skip MMAs are what the head waits for).  The CTAs in between have up to BPC.
+    // A CTA in between with at most two blocks (the one before the last, when the blocks do not divide) keeps them in registers too:
+    // its skip sums then reach the last CTA before that one needs them.
+    constexpr int NB = (first || to_head || small) ? 2 : BPC;           // this role's blocks (at most)
+    constexpr bool SMEMW = !first && !to_head && !small && BPC > 2;      // W0 and skip fragments in shared memory
+    const int n_last = first ? 0 : min(2, N - 2);              // (a model of one or two blocks has CTA 0 only)
+    const int l0 = first ? 0 : to_head ? N - n_last : 2 + BPC * (rank - 1);
+    const int nl = first ? min(2, N) : to_head ? n_last : min(BPC, N - n_last - l0);
     // exchanges inside the CTA go through [stream][channel] rows of fp16: the producers scatter halves, the consumers read B fragments
     // as 32-bit words (the transposing movmatrix costs 25 cycles of latency: only the token that leaves the CTA pays it)
     __half (*zh)[G][XH] = reinterpret_cast<__half (*)[G][XH]>(sm + OFF_ZF);      // [block][stream][channel]
     __half (*xl)[XH] = reinterpret_cast<__half (*)[XH]>(sm + OFF_XL);            // [stream][channel]
-    float* taps = reinterpret_cast<float*>(sm + (first ? OFF_TAPS0 : OFF_TAPS));      // [NG][2][G][XS]
+    float* taps = reinterpret_cast<float*>(sm + (first ? OFF_TAPS0 : OFF_TAPS));      // [NGV][NB][G][XS]
     float* wc = reinterpret_cast<float*>(sm + OFF_WC);                                 // CTA 0
-    // ---- resident A fragments (same per-warp ownership as gen_steps_bf16_kernel)
-    uint4 fgw[2][8], w2w[2][12];
+    uint4* const wsm = reinterpret_cast<uint4*>(sm + OFF_WS) + tid;                    // SMEMW: [block][fragment 12][thread]
+    // ---- resident A fragments (same per-warp ownership as gen_steps_bf16_kernel): fgw = [f|g] rows 8w..8w+7 (k-tiles 0..3 of the old
+    // tap W0, 4..7 of the current sample W1); w2w = dense m-tile w (warps 0-3), then skip m-tiles 2w, 2w+1
+    uint4 fgw[NB][8], w2w[NB][12];
     {
       const uint4* const fbase = p.frag + lane;
 #pragma unroll
-      for (int li = 0; li < 2; ++li) {
+      for (int li = 0; li < NB; ++li) {
         const int i = min(l0 + li, N - 1);
         const uint4* base = fbase + (int64_t)i * FRAG_LAYER;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) fgw[li][k] = base[FRAG_FG + (warp * 8 + k) * 32];
+        for (int k = 0; k < 4; ++k) {
+          const uint4 v = base[FRAG_FG + (warp * 8 + k) * 32];
+          if (SMEMW) wsm[(li * 12 + k) * 256] = v;
+          else fgw[li][k] = v;
+        }
+#pragma unroll
+        for (int k = 4; k < 8; ++k) fgw[li][k] = base[FRAG_FG + (warp * 8 + k) * 32];
 #pragma unroll
         for (int k = 0; k < 4; ++k) w2w[li][k] = warp < 4 ? base[FRAG_D + (warp * 4 + k) * 32] : make_uint4(0u, 0u, 0u, 0u);      // dense: warps 0-3
 #pragma unroll
-        for (int k = 0; k < 8; ++k) w2w[li][4 + k] = base[FRAG_S + (2 * warp * 4 + k) * 32];      // skip: m-tiles 2w, 2w+1
+        for (int k = 0; k < 8; ++k) {
+          const uint4 v = base[FRAG_S + (2 * warp * 4 + k) * 32];      // skip: m-tiles 2w, 2w+1
+          if (SMEMW) wsm[(li * 12 + 4 + k) * 256] = v;
+          else w2w[li][4 + k] = v;
+        }
       }
     }
+    // (every thread reads back only the shared-memory fragments it wrote itself)
+    auto w0_frag = [&](int li, int k) -> uint4 { return SMEMW ? wsm[(li * 12 + k) * 256] : fgw[li][k]; };
+    auto sk_frag = [&](int li, int k) -> uint4 { return SMEMW ? wsm[(li * 12 + 4 + k) * 256] : w2w[li][4 + k]; };
     for (int e = tid; e < ng * nl * G; e += 256) {
       const int s = e % G, li = (e / G) % nl, g = e / (G * nl);
       slot[g][li][s] = (int)(reinterpret_cast<const int64_t*>(sptr(g, s))[0] % p.dil[l0 + li]);
@@ -678,7 +731,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
           if (c4 == 0) slot[g][li][s] = sl;
         }
         const float* src = reinterpret_cast<const float*>(sptr(g, s) + 16) + ((int64_t)p.ring_off[l0 + li] + sl) * 64 + c4;
-        __pipeline_memcpy_async(taps + ((size_t)(g * 2 + li) * G + s) * XS + c4, src, 16);
+        __pipeline_memcpy_async(taps + ((size_t)(g * NB + li) * G + s) * XS + c4, src, 16);
       }
       __pipeline_commit();
     };
@@ -686,9 +739,10 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     for (int g = ng; g < NG; ++g) __pipeline_commit();      // always NG commit groups per ring period: the wait below is a constant
     // remote addresses of the next CTA's slots (same offsets there)
     const uint32_t r_xr = map_to(sm_base + OFF_XIN, rank + 1), r_xf = map_to(sm_base + OFF_XHIN, rank + 1);
-    const uint32_t r_skin = map_to(sm_base + OFF_SKIN, rank + 1);
+    const int sk_dst = rank + ((has_small && rank == CS - 4) ? 2 : 1);      // where this CTA's running skip sums go
+    const uint32_t r_skin = small ? map_to(sm_base + OFF_SKIN2, rank + 1) : map_to(sm_base + OFF_SKIN, sk_dst);
     const uint32_t r_xhfull = map_to(smem_u32(xhfull), rank + 1), r_xrfull = map_to(smem_u32(xrfull), rank + 1);
-    const uint32_t r_skfull = map_to(smem_u32(skfull), rank + 1);
+    const uint32_t r_skfull = small ? map_to(smem_u32(skfull2), rank + 1) : map_to(smem_u32(skfull), to_head ? rank + 1 : sk_dst);
     const uint32_t r_hf = map_to(sm_base + OFF_HF, rank + 1);      // (the last block CTA: the head's fragment slots)
     // skip MMAs of this CTA's blocks: warp w owns skip channels 32w..32w+31 (m-tiles 2w, 2w+1)
     auto skip_block = [&](float (&sk)[2][4], int li) {
@@ -696,8 +750,8 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
       for (int kt = 0; kt < 4; ++kt) {
         const __half* zr = &zh[li][n8][kt * 16 + 2 * q];
         const uint32_t b0 = *reinterpret_cast<const uint32_t*>(zr), b1 = *reinterpret_cast<const uint32_t*>(zr + 8);
-        mma_f16(sk[0], w2w[li][4 + kt], b0, b1);
-        mma_f16(sk[1], w2w[li][8 + kt], b0, b1);
+        mma_f16(sk[0], sk_frag(li, kt), b0, b1);
+        mma_f16(sk[1], sk_frag(li, 4 + kt), b0, b1);
       }
     };
     auto skip_mmas = [&](float (&sk)[2][4]) {
@@ -706,21 +760,21 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
 #pragma unroll
         for (int r = 0; r < 4; ++r) sk[j][r] = 0.f;
 #pragma unroll
-      for (int li = 0; li < 2; ++li)
+      for (int li = 0; li < NB; ++li)
         if (li < nl) skip_block(sk, li);
     };
 
     // W0 . old of both blocks of group gg (the taps are known one ring period ahead): computed while the group's token is still
     // on its way, so that the token's critical path is four independent MMAs per block instead of four chains of two
-    float pre[2][4];
+    float pre[NB][4];
     auto compute_pre = [&](int gg) {
 #pragma unroll
-      for (int li = 0; li < 2; ++li) {
+      for (int li = 0; li < NB; ++li) {
         if (li < nl) {
           const int ch = 8 * warp + n8;
           const float bf = HAS_BIAS ? p.bias_fg[(l0 + li) * 128 + ch] : 0.f, bg = HAS_BIAS ? p.bias_fg[(l0 + li) * 128 + 64 + ch] : 0.f;
           float c[4] = {bf, bf, bg, bg}, e[4] = {0.f, 0.f, 0.f, 0.f};
-          const float* orow = taps + ((size_t)(gg * 2 + li) * G + n8) * XS + 2 * q;
+          const float* orow = taps + ((size_t)(gg * NB + li) * G + n8) * XS + 2 * q;
           uint32_t bo[4][2];
 #pragma unroll
           for (int kt = 0; kt < 4; ++kt) {
@@ -728,10 +782,10 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             bo[kt][0] = pack_h2(v0.x, v0.y);
             bo[kt][1] = pack_h2(v1.x, v1.y);
           }
-          mma_f16(c, fgw[li][0], bo[0][0], bo[0][1]);
-          mma_f16(e, fgw[li][1], bo[1][0], bo[1][1]);
-          mma_f16(c, fgw[li][2], bo[2][0], bo[2][1]);
-          mma_f16(e, fgw[li][3], bo[3][0], bo[3][1]);
+          mma_f16(c, w0_frag(li, 0), bo[0][0], bo[0][1]);
+          mma_f16(e, w0_frag(li, 1), bo[1][0], bo[1][1]);
+          mma_f16(c, w0_frag(li, 2), bo[2][0], bo[2][1]);
+          mma_f16(e, w0_frag(li, 3), bo[3][0], bo[3][1]);
 #pragma unroll
           for (int r = 0; r < 4; ++r) pre[li][r] = c[r] + e[r];
         }
@@ -773,9 +827,10 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
           if (TRACE && g == 0 && tid == 0 && step < 64 && cid == 0) g_gen_ts[1024 + step * 16 + rank] = (long long)global_ns();
           sko = skin[g];
         }
-        float pv[2][4];      // what the two blocks push into their queues (dense warps)
+        float pv[NB][4];      // what the blocks push into their queues (dense warps)
+        float sk[2][4];       // (the last block CTA: skip sums, accumulated block by block)
 #pragma unroll
-        for (int li = 0; li < 2; ++li) {
+        for (int li = 0; li < NB; ++li) {
           if (li < nl) {
             const int i = l0 + li;
             const bool last_block = li == nl - 1;
@@ -798,18 +853,20 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             mma_f16(c3, fgw[li][7], bx[3].x, bx[3].y);
             uint32_t res_ok = 1;
             if (li == 0 && !first && warp < 4) res_ok = try_wait_once(&xrfull[g], step & 1);      // (the answer is read behind the barrier below)
-            float sk[2][4];
             uint32_t sk_ok = 1;
-            if (last_block && to_head) {
-              // the last block CTA: the earlier block's skip MMAs run in the shadow of this block's gate, the upstream sums are probed
+            if (to_head) {
+              // the last block CTA: the previous block's skip MMAs run in the shadow of this block's gate; the upstream sums are probed
+              if (li == 0) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) sk[j][r] = 0.f;
-              if (li > 0) skip_block(sk, 0);
-              if (!first) sk_ok = try_wait_once(&skfull[g], step & 1);
+                  for (int r = 0; r < 4; ++r) sk[j][r] = 0.f;
+              } else {
+                skip_block(sk, li - 1);
+              }
+              if (last_block && !first) sk_ok = try_wait_once(&skfull[g], step & 1);
             }
-            GEN_TS(2 + 4 * li);
+            GEN_TS(2 + 4 * (li ? 1 : 0));
             {
               const float z0 = gate_z((c0[0] + c1[0]) + (c2[0] + c3[0]), (c0[2] + c1[2]) + (c2[2] + c3[2]));
               const float z1 = gate_z((c0[1] + c1[1]) + (c2[1] + c3[1]), (c0[3] + c1[3]) + (c2[3] + c3[3]));
@@ -817,13 +874,14 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               zh[li][2 * q + 1][8 * warp + n8] = __float2half_rn(z1);
             }
             __syncthreads();
-            GEN_TS(3 + 4 * li);
+            GEN_TS(3 + 4 * (li ? 1 : 0));
             if (last_block && to_head) {
               // the last block CTA: what the head waits for is the skip sum, so it goes first - relu and the fp16 conversion applied
               // here, sent as the B fragments of post_process_1's MMAs straight from the accumulators
               skip_block(sk, li);
               GEN_TS(10);
               if (!sk_ok) wait_token(&skfull[g], step & 1);
+              if (has_small) wait_token(&skfull2[g], step & 1);
               GEN_TS(11);
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
@@ -831,7 +889,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                   const int row = 16 * (2 * warp + j) + n8 + 8 * (r >> 1), s_ = 2 * q + (r & 1);
-                  v[r] = fmaxf(sk[j][r] + (first ? 0.f : skin[g][s_][row]) + (HAS_BIAS ? p.bias_skip[row] : 0.f), 0.f);
+                  v[r] = fmaxf(sk[j][r] + (first ? 0.f : skin[g][s_][row]) + (has_small ? skin2[s_][row] : 0.f) + (HAS_BIAS ? p.bias_skip[row] : 0.f), 0.f);
                 }
                 st_async_u2(r_hf + (uint32_t)((g * 16 + 2 * warp + j) * 32 + lane) * 8, movm_t(pack_h2(v[0], v[1])), movm_t(pack_h2(v[2], v[3])),
                             r_skfull + g * 8);
@@ -863,7 +921,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               const float xi[4] = {dn[0], dn[1], dn[2], dn[3]};
 #pragma unroll
               for (int r = 0; r < 4; ++r) dn[r] = ((d0[r] + d1[r]) + (d2[r] + d3[r])) + dn[r];
-              GEN_TS(4 + 4 * li);
+              GEN_TS(4 + 4 * (li ? 1 : 0));
 #pragma unroll
               for (int r = 0; r < 4; ++r) pv[li][r] = PUSH_OUT ? dn[r] : xi[r];      // fast_generate.py:128-129
               if (!last_block) {
@@ -879,22 +937,21 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
             if (!last_block) {
               __syncthreads();      // block li + 1 reads what the dense warps wrote
             }
-            GEN_TS(5 + 4 * li);
+            GEN_TS(5 + 4 * (li ? 1 : 0));
           }
         }
         // ================= behind the token: skip MMAs of both blocks, running skip sums, queue pushes, next taps, next W0 . old
         if (!to_head) {
-          float sk[2][4];
           skip_mmas(sk);
           GEN_TS(10);
-          if (!first) wait_token(&skfull[g], step & 1);
+          if (!first && !small) wait_token(&skfull[g], step & 1);
           GEN_TS(11);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               const int row = 16 * (2 * warp + j) + n8 + 8 * (r >> 1), s = 2 * q + (r & 1);
-              sko[s][row] = sk[j][r] + (first ? 0.f : skin[g][s][row]);      // (in place behind CTA 0)
+              sko[s][row] = sk[j][r] + ((first || small) ? 0.f : skin[g][s][row]);      // (in place behind CTA 0)
             }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the bulk copy below reads these generic-proxy writes
         }
@@ -910,14 +967,15 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
           if (!first && step + 1 < p.n_steps) {
             mbar_expect_tx(&xhfull[g], XF_BYTES);
             mbar_expect_tx(&xrfull[g], XR_BYTES);
-            mbar_expect_tx(&skfull[g], SK_BYTES);
+            if (!small) mbar_expect_tx(&skfull[g], SK_BYTES);
+            if (to_head && has_small) mbar_expect_tx(&skfull2[g], SK_BYTES);
           }
         }
         if (warp < 4) {
           float* const ring0 = reinterpret_cast<float*>(sptr(g, s0) + 16);
           float* const ring1 = reinterpret_cast<float*>(sptr(g, s1) + 16);
 #pragma unroll
-          for (int li = 0; li < 2; ++li)
+          for (int li = 0; li < NB; ++li)
             if (li < nl) {
               const int i = l0 + li;
               const int o0 = (p.ring_off[i] + slot[g][li][s0]) * 64 + chd, o1 = (p.ring_off[i] + slot[g][li][s1]) * 64 + chd;
@@ -954,12 +1012,14 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     }
     };
     if (rank == 0) {
-      if (CS == 2) block_cta(std::true_type{}, std::true_type{});
-      else block_cta(std::true_type{}, std::false_type{});
+      if (CS == 2) block_cta(std::true_type{}, std::true_type{}, std::false_type{});
+      else block_cta(std::true_type{}, std::false_type{}, std::false_type{});
     } else if (rank == CS - 2) {
-      block_cta(std::false_type{}, std::true_type{});
+      block_cta(std::false_type{}, std::true_type{}, std::false_type{});
+    } else if (BPC > 2 && N - std::min(2, N - 2) - (2 + BPC * (rank - 1)) <= 2) {
+      block_cta(std::false_type{}, std::false_type{}, std::true_type{});
     } else {
-      block_cta(std::false_type{}, std::false_type{});
+      block_cta(std::false_type{}, std::false_type{}, std::false_type{});
     }
   } else {
     // ============================================================ head CTA: relu(sum skips) -> P1 -> relu -> P2 -> pick
@@ -1180,50 +1240,62 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
   p.frag = reinterpret_cast<const uint4*>(P + pl.gen_frag);
   static const bool pipe_off = [] { const char* e = getenv("WN_GEN_PIPE"); return e && e[0] == '0'; }();
   if (!pipe_off && m.n_layers <= 30) {
-    // weights-stationary cluster pipeline: ceil(N / 2) block CTAs + the head CTA per cluster, 8 groups of 8 streams per cluster
-    static const int lpc_env = [] { const char* e = getenv("WN_GEN_LPC"); return e && e[0] == '1' ? 1 : 2; }();
-    p.lpc = (lpc_env == 1 && m.n_layers <= 15) ? 1 : 2;
+    // Weights-stationary cluster pipeline.  The step is the ring's latency (one group's token through every CTA and back), so the
+    // groups are spread over as many clusters as fit on the GPU at once: a cluster serving one group never makes a token wait for
+    // another group's tail work.  Two geometries: 4 blocks per CTA (9 CTAs for 30 layers, one group per cluster, up to 16 clusters)
+    // when every group gets its own cluster, else 2 blocks per CTA (16 CTAs, up to 8 groups per cluster, up to 9 clusters).  With more
+    // groups than that the clusters would run in waves, and the one-CTA-per-8-streams kernel below (same step time for any number
+    // of streams up to 8 x 148) has the higher throughput.
     p.trace = [] { const char* e = getenv("WN_TS_RANK"); return e ? atoi(e) : 1; }();      // (the CTA whose timeline WN_TS=1 records)
-    const int cs = (m.n_layers + p.lpc - 1) / p.lpc + 1;
     const int groups = (int)ceil_div(n_streams, G);
     const bool out_push = push == WN_PUSH_OUTPUT;
     static const bool ts_env = getenv("WN_TS") != nullptr;
-    auto kp = ts_env ? (m.use_bias ? (out_push ? gen_pipe_kernel<true, true, true> : gen_pipe_kernel<true, false, true>)
-                                   : (out_push ? gen_pipe_kernel<false, true, true> : gen_pipe_kernel<false, false, true>))
-                     : (m.use_bias ? (out_push ? gen_pipe_kernel<true, true, false> : gen_pipe_kernel<true, false, false>)
-                                   : (out_push ? gen_pipe_kernel<false, true, false> : gen_pipe_kernel<false, false, false>));
-    static bool pipe_once[4] = {false, false, false, false};
-    const int ki = (m.use_bias ? 2 : 0) + (out_push ? 1 : 0);
-    if (!pipe_once[ki]) {
-      WN_CHECK_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe::TOTAL));
-      WN_CHECK_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      pipe_once[ki] = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)cs); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = pipe::TOTAL; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    // The step is the ring's latency (one group's token through every CTA and back), so the groups are spread over as many clusters
-    // as fit on the GPU at once (9 of 16 CTAs): a cluster serving one group never makes a token wait for another group's tail work.
-    // With more groups than NG per resident cluster the clusters would run in waves, and the one-CTA-per-8-streams kernel below
-    // (same step time for any number of streams up to 8 x 148) has the higher throughput.
-    static int max_clusters[32] = {};
-    if (max_clusters[cs] == 0) {
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kp, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = -1; }
-      max_clusters[cs] = n > 0 ? n : -1;
-    }
     static const bool pipe_force = [] { const char* e = getenv("WN_GEN_PIPE"); return e && e[0] == '1'; }();
     static const int gpc_env = [] { const char* e = getenv("WN_GEN_GPC"); return e ? atoi(e) : 0; }();      // (timing experiments)
-    int gpc = max_clusters[cs] > 0 ? (int)ceil_div(groups, max_clusters[cs]) : NG + 1;
-    if (gpc_env >= 1 && gpc_env <= NG && gpc_env >= gpc) gpc = gpc_env;
-    if (pipe_force && gpc > NG) gpc = NG;
-    if (gpc <= NG) {
+    static const int bpc_env = [] { const char* e = getenv("WN_GEN_BPC"); return e ? atoi(e) : 0; }();      // (timing experiments: 2 or 4)
+    using Kern = void (*)(FastGenParams, char*, const int64_t*, const float*, int64_t*, float*);
+    const int ki = (ts_env ? 4 : 0) + (m.use_bias ? 2 : 0) + (out_push ? 1 : 0);
+    static const Kern kerns[2][8] = {
+        {gen_pipe_kernel<false, false, false, 2>, gen_pipe_kernel<false, true, false, 2>, gen_pipe_kernel<true, false, false, 2>,
+         gen_pipe_kernel<true, true, false, 2>, gen_pipe_kernel<false, false, true, 2>, gen_pipe_kernel<false, true, true, 2>,
+         gen_pipe_kernel<true, false, true, 2>, gen_pipe_kernel<true, true, true, 2>},
+        {gen_pipe_kernel<false, false, false, 4>, gen_pipe_kernel<false, true, false, 4>, gen_pipe_kernel<true, false, false, 4>,
+         gen_pipe_kernel<true, true, false, 4>, gen_pipe_kernel<false, false, true, 4>, gen_pipe_kernel<false, true, true, 4>,
+         gen_pipe_kernel<true, false, true, 4>, gen_pipe_kernel<true, true, true, 4>}};
+    static const size_t smem_of[2] = {pipe::PipeL<pipe::pipe_groups(2), 2>::TOTAL, pipe::PipeL<pipe::pipe_groups(4), 4>::TOTAL};
+    static bool pipe_once[2][8] = {};
+    static int max_clusters[2][32] = {};
+    for (int v = 1; v >= 0; --v) {      // 4 blocks per CTA first
+      const int bpc = v ? 4 : 2;
+      if (bpc_env && bpc_env != bpc) continue;
+      const Kern kp = kerns[v][ki];
+      // CTA 0 (two blocks), the CTAs in between (bpc blocks), the last block CTA (two blocks), the head
+      const int n_last = m.n_layers > 2 ? std::min(2, m.n_layers - 2) : 0, n_mid = std::max(0, m.n_layers - 2 - n_last);
+      const int cs = 1 + (int)ceil_div(n_mid, bpc) + (n_last ? 1 : 0) + 1;
+      if (!pipe_once[v][ki]) {
+        WN_CHECK_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of[v]));
+        WN_CHECK_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        pipe_once[v][ki] = true;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)cs); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem_of[v]; cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (max_clusters[v][cs] == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kp, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = -1; }
+        max_clusters[v][cs] = n > 0 ? n : -1;
+      }
+      const int slots = pipe::pipe_groups(bpc);
+      int gpc = max_clusters[v][cs] > 0 ? (int)ceil_div(groups, max_clusters[v][cs]) : slots + 1;
+      if (gpc_env >= 1 && gpc_env <= slots && gpc_env >= gpc) gpc = gpc_env;
+      if (pipe_force && v == 0 && gpc > slots) gpc = slots;
+      if (gpc > slots) continue;
       p.gpc = gpc;
       cfg.gridDim = dim3((unsigned)(cs * (int)ceil_div(groups, gpc)));
-      WN_PROF("gen_pipe", s);
+      WN_PROF(v ? "gen_pipe4" : "gen_pipe", s);
       WN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kp, p, reinterpret_cast<char*>(d_state), d_first_note, d_uniforms, d_out, d_logits));
       WN_CHECK_LAUNCH();
       return WN_OK;
