@@ -1238,7 +1238,9 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
   p.bias_p1 = reinterpret_cast<const float*>(P + pl.bias_p1);
   p.bias_p2 = reinterpret_cast<const float*>(P + pl.bias_p2);
   p.frag = reinterpret_cast<const uint4*>(P + pl.gen_frag);
-  static const bool pipe_off = [] { const char* e = getenv("WN_GEN_PIPE"); return e && e[0] == '0'; }();
+  // (the WN_GEN_* switches are read on every call: the geometry tests flip them inside one process)
+  const char* const pipe_env = getenv("WN_GEN_PIPE");
+  const bool pipe_off = pipe_env && pipe_env[0] == '0';
   if (!pipe_off && m.n_layers <= 30) {
     // Weights-stationary cluster pipeline.  The step is the ring's latency (one group's token through every CTA and back), so the
     // groups are spread over as many clusters as fit on the GPU at once: a cluster serving one group never makes a token wait for
@@ -1250,9 +1252,9 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
     const int groups = (int)ceil_div(n_streams, G);
     const bool out_push = push == WN_PUSH_OUTPUT;
     static const bool ts_env = getenv("WN_TS") != nullptr;
-    static const bool pipe_force = [] { const char* e = getenv("WN_GEN_PIPE"); return e && e[0] == '1'; }();
-    static const int gpc_env = [] { const char* e = getenv("WN_GEN_GPC"); return e ? atoi(e) : 0; }();      // (timing experiments)
-    static const int bpc_env = [] { const char* e = getenv("WN_GEN_BPC"); return e ? atoi(e) : 0; }();      // (timing experiments: 2 or 4)
+    const bool pipe_force = pipe_env && pipe_env[0] == '1';
+    const int gpc_env = [] { const char* e = getenv("WN_GEN_GPC"); return e ? atoi(e) : 0; }();      // groups per cluster, at least
+    const int bpc_env = [] { const char* e = getenv("WN_GEN_BPC"); return e ? atoi(e) : 0; }();      // 2 or 4: that geometry only
     using Kern = void (*)(FastGenParams, char*, const int64_t*, const float*, int64_t*, float*);
     const int ki = (ts_env ? 4 : 0) + (m.use_bias ? 2 : 0) + (out_push ? 1 : 0);
     static const Kern kerns[2][8] = {

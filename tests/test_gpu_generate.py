@@ -137,6 +137,56 @@ def test_bf16_generation_kernel_teacher_forced_vs_oracle():
         assert agree >= 0.9 * 3 * n, agree
 
 
+@pytest.mark.parametrize("n_layers", [1, 2, 3, 4, 5, 7, 8, 11, 12, 15])
+def test_pipeline_geometries_agree_with_the_one_cta_kernel(n_layers, monkeypatch):
+    """The cluster pipeline in both geometries (2 and 4 blocks per CTA; every role split the layer count produces: CTA 0 alone,
+    CTA 0 + last, a short CTA in between with the skip-sum bypass, full CTAs with shared-memory fragments; one group per cluster
+    and several) against the one-CTA-per-8-streams kernel on the same weights and primes: same picks, logits within 5e-3 relative
+    up to the first step where a pick differs (the kernels accumulate in different orders; both round x and z to fp16 once)."""
+    from music_b200.wavenet.fast_generate import generate_codes
+    dil = [2 ** (i % 5) for i in range(n_layers)]
+    Q, bias = 256, bool(n_layers % 2)
+    st = O.init_wavenet_state(dil, 64, 64, 256, Q, bias, seed=20 + n_layers, scale=1.5)
+    rf = O.receptive_field(2, dil)
+    net = build_net(dil, 64, 64, 256, Q, bias, st, mode="bf16")
+    g = torch.Generator().manual_seed(11)
+    n = 10
+    for streams in (5, 19):      # 1 and 3 groups
+        primes = torch.randint(0, Q, (streams, rf), generator=g).cuda()
+        monkeypatch.setenv("WN_GEN_PIPE", "0")
+        ref_codes, ref_logits = generate_codes(net, n, primes, return_logits=True)
+        ref_codes, ref_logits = ref_codes.cpu(), ref_logits.cpu()
+        u = torch.rand(n, streams, generator=g)
+        ref_sampled = generate_codes(net, n, primes, uniforms=u).cpu()
+        for bpc, gpc in (("2", "1"), ("2", "3"), ("4", "1")):
+            monkeypatch.setenv("WN_GEN_PIPE", "1")
+            monkeypatch.setenv("WN_GEN_BPC", bpc)
+            monkeypatch.setenv("WN_GEN_GPC", gpc)
+            codes, logits = generate_codes(net, n, primes, return_logits=True)
+            codes, logits = codes.cpu(), logits.cpu()
+            agree = 0
+            for s in range(streams):
+                for i in range(n):
+                    assert max_rel(logits[i, s].numpy(), ref_logits[i, s].numpy()) < 5e-3, (bpc, gpc, streams, s, i)
+                    if int(codes[i, s]) != int(ref_codes[i, s]):
+                        break
+                    agree += 1
+                else:
+                    continue
+            assert agree >= 0.9 * streams * n, (bpc, gpc, streams, agree)
+            sampled = generate_codes(net, n, primes, uniforms=u).cpu()      # inverse-CDF picks with the same uniforms
+            same = 0
+            for s in range(streams):
+                for i in range(n):
+                    if int(sampled[i, s]) != int(ref_sampled[i, s]):
+                        break
+                    same += 1
+            assert same >= 0.7 * streams * n, (bpc, gpc, streams, same)      # (a sample next to a CDF step may flip; the stream then differs)
+        monkeypatch.delenv("WN_GEN_BPC")
+        monkeypatch.delenv("WN_GEN_GPC")
+        monkeypatch.delenv("WN_GEN_PIPE")
+
+
 def _save_reference_checkpoint(tmp_path, dil, R, D, S, Q, bias, st, name="wavenet7.model", dataparallel=False):
     """params JSON + a checkpoint in the reference's format (train.py:45-50: torch.save of the state_dict; files saved from
     nn.DataParallel carry a 'module.' prefix, train.py:61-69)."""
