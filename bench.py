@@ -187,9 +187,10 @@ def bench_generation(net, n_streams, n_steps, dev):
     per stream on the device (CUDA events).
     `roofline` follows SURVEY.md 8(d): ALGORITHMIC bytes per step = streams x 15 368 B (ring read + write of 30 x 64 fp32 per
     stream-step + 8 B of I/O) + the 2.54 MB weight set once, over the step time, against the measured HBM copy peak.
-    Up to 64 streams per resident cluster run on the weights-stationary cluster pipeline (gen_pipe_kernel: `kernel` says which
-    kernel served the run); its only per-step L2 traffic is the ring state.  Larger stream counts run on the one-CTA-per-8-streams
-    kernel, whose L2 -> SM traffic (every CTA streams the weight-fragment image each step) is reported in `l2` against an L2 read
+    Stream counts whose groups of 8 all fit into resident clusters run on the weights-stationary cluster pipeline (gen_pipe_kernel;
+    `kernel` says which kernel and geometry served the run: gen_pipe4 = 4 blocks per CTA, one group per 10-CTA cluster, up to 128
+    streams; gen_pipe = 2 blocks per CTA, up to 8 groups per 16-CTA cluster); its only per-step L2 traffic is the ring state.
+    Larger stream counts run on the one-CTA-per-8-streams kernel, whose L2 -> SM traffic (every CTA streams the weight-fragment image each step) is reported in `l2` against an L2 read
     peak measured in this run with the same number of CTAs.
     Also timed: a throughput configuration with 8 streams on every SM-sized slice of the GPU (1024 streams)."""
     import torch
@@ -275,13 +276,14 @@ def bench_generation(net, n_streams, n_steps, dev):
             "l2": ({"achieved_gbs": l2_rate(n_streams, n_steps, ms), "measured_peak_gbs": l2_peak, "frac": l2_rate(n_streams, n_steps, ms) / l2_peak,
                     "ctas": n_ctas, "note": "bytes the kernel requests from L2 (weight-fragment image per CTA of 8 streams per step + "
                                             "ring vectors) against the L2 read rate the same number of CTAs reach in wn_bench_l2_read"}
-                   if k_small != "gen_pipe" else
+                   if not k_small.startswith("gen_pipe") else
                    {"achieved_gbs": n_steps * n_streams * (ring_algo - 8) / (ms * 1e-3) / 1e9, "measured_peak_gbs": None, "frac": None,
-                    "ctas": n_layers // 2 + 1,
-                    "note": "gen_pipe: the weights are resident in the registers of a 16-CTA cluster, so the only per-step L2 traffic is the "
-                            "ring vectors (one fp32 vector read and written per block and stream) = the algorithmic state bytes; tokens "
-                            "move CTA to CTA through distributed shared memory (12 KB per hop and group).  The step is the ring latency "
-                            "(30 blocks of ~1200 cycles + 15 hops + head), not a bandwidth"})}
+                    "ctas": ((n_streams + 7) // 8) * (10 if k_small == "gen_pipe4" else n_layers // 2 + 1),
+                    "note": "gen_pipe: the weights are resident in the registers and shared memory of a cluster (10 CTAs per group of 8 "
+                            "streams in the 4-blocks-per-CTA geometry), so the only per-step L2 traffic is the ring vectors (one fp32 "
+                            "vector read and written per block and stream) = the algorithmic state bytes; tokens move CTA to CTA "
+                            "through distributed shared memory (3 KB st.async per hop and group, 8 KB of skip sums behind it).  The "
+                            "step is the ring latency (30 blocks of ~480 cycles + 9 hops of ~280 + head ~2400 cycles), not a bandwidth"})}
 
 
 def bench_gpu_incumbent(dev, B, steps=3):

@@ -461,8 +461,6 @@ static int ae_forward_impl(wn_ae* a, int32_t B, int32_t L, const float* d_x, con
     WN_PROPAGATE(launch_cond_pack16(ctab_fg, base + fl.ctab_fg16, (int64_t)B * frames * N, frames, N, s));
     Model& d = a->dec;
     d.cond_fg = ctab_fg; d.cond_fg16 = base + fl.ctab_fg16; d.cond_head = ctab_head; d.cond_frames = frames;
-    static const bool nocond_env = getenv("WN_AE_NOCOND") != nullptr;      // timing experiment: WRONG results, no conditioning loads
-    if (nocond_env) { d.cond_fg = nullptr; d.cond_fg16 = nullptr; }
     d.cond_fg_grad = nullptr; d.cond_head_grad = nullptr;
     WN_PROPAGATE(fast_pack(d, d_params, base + fl.packed, s));
     return fast_forward(d, B, L, d_x, d_idx, base + fl.packed, base + fl.ws, d_logits, s);
