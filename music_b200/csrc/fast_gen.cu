@@ -1032,11 +1032,11 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int k = 0; k < 16; ++k) p1w[j][k] = headA[((2 * warp + j) * 16 + k) * 32 + lane];
-    uint4 p2w[2][6];       // post_process_2: k-tiles 0..5 of the two m-tiles resident too; k-tiles 6..15 come from shared memory
+    uint4 p2w[2][8];       // post_process_2: k-tiles 0..7 of the two m-tiles resident too; k-tiles 8..15 come from shared memory
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
-      for (int k = 0; k < 6; ++k) p2w[j][k] = headA[FRAG_HEAD + ((2 * warp + j) * 16 + k) * 32 + lane];
+      for (int k = 0; k < 8; ++k) p2w[j][k] = headA[FRAG_HEAD + ((2 * warp + j) * 16 + k) * 32 + lane];
     for (int e = tid; e < FRAG_HEAD; e += 256) p2s[e] = headA[FRAG_HEAD + e];
     __syncthreads();
     const uint32_t r_note = map_to(sm_base + OFF_NOTE, 0), r_notefull = map_to(smem_u32(notefull), 0);
@@ -1050,7 +1050,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
         wait_token(&skfull[g], step & 1);
         HEAD_TS(1);
         if (TRACE && g == 0 && tid == 0 && step < 64 && cid == 0) g_gen_ts[1024 + step * 16 + rank] = (long long)global_ns();
-        float c[2][4][4];      // [m-tile][chain][fragment]: four chains of four MMAs per m-tile
+        float c[2][2][4];      // [m-tile][chain][fragment]: two chains of eight MMAs per m-tile (the pipe's issue rate bounds a phase)
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
 #pragma unroll
@@ -1060,29 +1060,29 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               const int row = 16 * (2 * warp + j) + n8 + 8 * (r >> 1);
               const float* bias = which == 0 ? p.bias_p1 : p.bias_p2;
               c[j][0][r] = HAS_BIAS ? bias[row] : 0.f;
-              c[j][1][r] = c[j][2][r] = c[j][3][r] = 0.f;
+              c[j][1][r] = 0.f;
             }
           const uint2* bsrc = (which == 0 ? hf + g * 16 * 32 : h1f) + lane;
 #pragma unroll
           for (int kt = 0; kt < 16; ++kt) {
             const uint2 b = bsrc[kt * 32];
             if (which == 0) {
-              mma_f16(c[0][kt & 3], p1w[0][kt], b.x, b.y);
-              mma_f16(c[1][kt & 3], p1w[1][kt], b.x, b.y);
-            } else if (kt < 6) {
-              mma_f16(c[0][kt & 3], p2w[0][kt], b.x, b.y);
-              mma_f16(c[1][kt & 3], p2w[1][kt], b.x, b.y);
+              mma_f16(c[0][kt & 1], p1w[0][kt], b.x, b.y);
+              mma_f16(c[1][kt & 1], p1w[1][kt], b.x, b.y);
+            } else if (kt < 8) {
+              mma_f16(c[0][kt & 1], p2w[0][kt], b.x, b.y);
+              mma_f16(c[1][kt & 1], p2w[1][kt], b.x, b.y);
             } else {
               const uint4 a0 = p2s[((2 * warp) * 16 + kt) * 32 + lane], a1 = p2s[((2 * warp + 1) * 16 + kt) * 32 + lane];
-              mma_f16(c[0][kt & 3], a0, b.x, b.y);
-              mma_f16(c[1][kt & 3], a1, b.x, b.y);
+              mma_f16(c[0][kt & 1], a0, b.x, b.y);
+              mma_f16(c[1][kt & 1], a1, b.x, b.y);
             }
           }
           HEAD_TS(3 + 2 * which);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) c[j][0][r] = (c[j][0][r] + c[j][1][r]) + (c[j][2][r] + c[j][3][r]);
+            for (int r = 0; r < 4; ++r) c[j][0][r] = c[j][0][r] + c[j][1][r];
           if (which == 0) {
             // relu, fp16, and the accumulator fragment transposed into the B fragment of k-tile 2w + j of post_process_2
 #pragma unroll
@@ -1117,19 +1117,22 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
               const float v = c[k >> 1][0][2 * (k & 1) + b];
               if (v > bv[b]) { bv[b] = v; bi[b] = 32 * warp + 16 * (k >> 1) + 8 * (k & 1) + n8; }
             }
-            // over the 8 row lanes by shuffles (a partial-mask redux.sync measured 5x slower); floats compared as ordered unsigned keys
-            uint32_t key = ordered_key(bv[b]);
+          }
+          // over the 8 row lanes by shuffles, floats compared as ordered unsigned keys (measured: a partial-mask redux.sync costs 350
+          // cycles, and eight full-mask ones with neutral elements for the other streams ~90 each: CREDUX does not pipeline)
+          uint32_t key[2] = {ordered_key(bv[0]), ordered_key(bv[1])};
 #pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-              const uint32_t ok = __shfl_xor_sync(0xffffffffu, key, o);
+          for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const uint32_t ok = __shfl_xor_sync(0xffffffffu, key[b], o);
               const int oi = __shfl_xor_sync(0xffffffffu, bi[b], o);
-              if (ok > key || (ok == key && oi < bi[b])) { key = ok; bi[b] = oi; }
+              if (ok > key[b] || (ok == key[b] && oi < bi[b])) { key[b] = ok; bi[b] = oi; }
             }
-            bv[b] = __uint_as_float(key);      // (the key; compared as a key below)
           }
           if (n8 == 0) {
-            cand[warp * G + 2 * q] = make_float2(bv[0], __int_as_float(bi[0]));
-            cand[warp * G + 2 * q + 1] = make_float2(bv[1], __int_as_float(bi[1]));
+            cand[warp * G + 2 * q] = make_float2(__uint_as_float(key[0]), __int_as_float(bi[0]));
+            cand[warp * G + 2 * q + 1] = make_float2(__uint_as_float(key[1]), __int_as_float(bi[1]));
           }
           __syncthreads();
           HEAD_TS(6);
