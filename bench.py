@@ -283,7 +283,7 @@ def bench_generation(net, n_streams, n_steps, dev):
                             "streams in the 4-blocks-per-CTA geometry), so the only per-step L2 traffic is the ring vectors (one fp32 "
                             "vector read and written per block and stream) = the algorithmic state bytes; tokens move CTA to CTA "
                             "through distributed shared memory (3 KB st.async per hop and group, 8 KB of skip sums behind it).  The "
-                            "step is the ring latency (30 blocks of ~480 cycles + 9 hops of ~280 + head ~2400 cycles), not a bandwidth"})}
+                            "step is the ring latency (30 blocks of ~480 cycles + 9 hops of ~280 + head ~2150 cycles), not a bandwidth"})}
 
 
 def bench_gpu_incumbent(dev, B, steps=3):
