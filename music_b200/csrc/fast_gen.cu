@@ -726,6 +726,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
       for (int e = tid; e < nl * G * 16; e += 256) {
         const int c4 = (e & 15) * 4, s = (e >> 4) % G, li = (e >> 4) / G;
         int sl = slot[g][li][s];
+        __syncwarp();      // the 16 lanes of a (block, stream) pair have read the slot before one of them advances it
         if (advance) {
           sl = sl + 1 == p.dil[l0 + li] ? 0 : sl + 1;
           if (c4 == 0) slot[g][li][s] = sl;
