@@ -179,7 +179,7 @@ int wn_gen_import(const wn_model* m, int32_t mode, int32_t n_streams, void* d_st
 /* ---- conditioned generation (extension; SURVEY.md 8f rank 3: incremental generation for the autoencoder's decoder) ----
  * The decoder of wavenet_autoencoder (model1.py:158-225) is a WaveNet stack whose block pre-activations and head receive an
  * additive, per-frame conditioning vector (`_conditon`, :227-247).  With a descriptor installed, wn_forward (fp32),
- * wn_gen_prime and wn_gen_steps (fp32) add  d_fg[stream, frame_i(t), block i, :]  to the [f|g] pre-activations of block i and
+ * wn_gen_prime and wn_gen_steps (fp32, and the half-precision cluster pipeline of the 64/64/256/256 shape) add  d_fg[stream, frame_i(t), block i, :]  to the [f|g] pre-activations of block i and
  * d_head[stream, frame(t), :]  to post_process_1's output, where frame follows the reference rule on the TOTAL sequence:
  * len % frames == 0 ? t_local / (len / frames) : t_local % frames, with len = total_len - (first valid index of that tensor).
  * gate_first != 0 means channels [0,D) of d_fg belong to the gate and [D,2D) to the filter (the autoencoder's split, :188-192).

@@ -55,7 +55,17 @@ struct FastGenParams {
   const float* bias_p1;
   const float* bias_p2;
   const uint4* frag;               // A fragments: [N][FRAG_LAYER] then P1 [FRAG_HEAD], P2 [FRAG_HEAD]
+  // optional conditioning (wn_set_conditioning; the autoencoder's decoder): per-frame additive terms of every block's [f|g]
+  // pre-activation, [stream][frame][layer][128], and of post_process_1's, [stream][frame][256]; the frame of a time step follows
+  // model1.py:233-246 (gen.cu cond_frame_of).  gen_pipe_kernel only.
+  const float* cond_fg;
+  const float* cond_head;
+  int cond_frames, cond_total, cond_gate_first, rf;
+  int s_out[GEN_MAXL];             // first valid output index of every block (the frame rule's origin)
 };
+__device__ __forceinline__ int gen_cond_frame(int t_local, int len, int frames) {
+  return (len % frames == 0) ? t_local / (len / frames) : t_local % frames;      // model1.py:233-246
+}
 
 // ---------------------------------------------------------------- fragment image
 struct FragPackArgs {
@@ -467,8 +477,8 @@ template <int NGv, int NBv>
 struct PipeL {
   static constexpr uint32_t OFF_BAR = 0;                                   // xhfull[NGv], xrfull[NGv], skfull[NGv], notefull[NGv]
   static constexpr uint32_t OFF_NOTE = 256;                                // int note[NGv][G], last[NGv][G]
-  static constexpr uint32_t OFF_SLOT = OFF_NOTE + 2 * NGv * G * 4;         // int slot[NGv][NBv][G]
-  static constexpr uint32_t OFF_ZF = OFF_SLOT + NGv * NBv * G * 4;         // __half zh[NBv][G][XH]: gated activations of the CTA's blocks
+  static constexpr uint32_t OFF_SLOT = OFF_NOTE + 3 * NGv * G * 4;         // (+ int tb[NGv][G]: step counters at launch) int slot[2][NGv][NBv][G]
+  static constexpr uint32_t OFF_ZF = OFF_SLOT + 2 * NGv * NBv * G * 4;         // __half zh[NBv][G][XH]: gated activations of the CTA's blocks
   static constexpr uint32_t OFF_XL = OFF_ZF + NBv * XH_BYTES;              // __half xl[G][XH]: a block's output (CTA 0: also the embedding)
   static constexpr uint32_t OFF_SKIN = (OFF_XL + XH_BYTES + 127) & ~127u;  // float skin[NGv][G][HS]  (same offset in every role but CTA 0)
   static constexpr uint32_t OFF_XIN = OFF_SKIN + NGv * SK_BYTES;           // block CTAs: float4 xr[NGv][128]
@@ -486,7 +496,8 @@ struct PipeL {
   static constexpr uint32_t OFF_P2 = OFF_HF + NGv * HF_BYTES;              //       uint4 p2[FRAG_HEAD]
   static constexpr uint32_t OFF_HH = OFF_P2 + FRAG_HEAD * 16;              //       relu(post_process_1) fragments, greedy candidates
   static constexpr uint32_t OFF_LG = OFF_HH + 2 * G * HH * 2;              //       float lg[G][HS]
-  static constexpr uint32_t HEAD_BYTES = OFF_LG + G * HS * 4;
+  static constexpr uint32_t OFF_CH = OFF_LG + G * HS * 4;                  //       float condh[8][256]: a step's post_process_1 conditioning
+  static constexpr uint32_t HEAD_BYTES = OFF_CH + 8 * 256 * 4;
   static constexpr uint32_t TOTAL =
       HEAD_BYTES > CTA0_BYTES ? (HEAD_BYTES > BLOCK_BYTES ? HEAD_BYTES : BLOCK_BYTES) : (CTA0_BYTES > BLOCK_BYTES ? CTA0_BYTES : BLOCK_BYTES);
   static_assert(TOTAL <= 227 * 1024, "pipeline generation kernel: shared memory");
@@ -591,7 +602,7 @@ __device__ __forceinline__ void cp_wait_dyn(int n) {      // all but the newest 
 // BPC = blocks per CTA behind CTA 0 (which always has two).  2: every fragment in registers, 8 group slots per cluster.  4: only what the
 // token waits for stays in registers (W1 of [f|g], the dense convolution); W0 and the skip convolution, which run behind / ahead of
 // the token, are read from shared memory - 8 block CTAs instead of 15, seven hops less per step, one group per cluster.
-template <bool HAS_BIAS, bool PUSH_OUT, bool TRACE, int BPC>
+template <bool HAS_BIAS, bool PUSH_OUT, bool TRACE, int BPC, bool COND = false>
 __global__ void __launch_bounds__(256, 1)
 gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __restrict__ first_note, const float* __restrict__ uniforms,
                 int64_t* __restrict__ out, float* __restrict__ logits_out) {
@@ -601,7 +612,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
   constexpr uint32_t OFF_BAR = L::OFF_BAR, OFF_NOTE = L::OFF_NOTE, OFF_SLOT = L::OFF_SLOT, OFF_ZF = L::OFF_ZF, OFF_XL = L::OFF_XL,
                      OFF_SKIN = L::OFF_SKIN, OFF_XIN = L::OFF_XIN, OFF_XHIN = L::OFF_XHIN, OFF_TAPS = L::OFF_TAPS, OFF_WS = L::OFF_WS,
                      OFF_WC = L::OFF_WC, OFF_TAPS0 = L::OFF_TAPS0, OFF_STG0 = L::OFF_STG0, STG_BYTES = L::STG_BYTES, OFF_HF = L::OFF_HF,
-                     OFF_P2 = L::OFF_P2, OFF_HH = L::OFF_HH, OFF_LG = L::OFF_LG, OFF_SKIN2 = L::OFF_SKIN2;
+                     OFF_P2 = L::OFF_P2, OFF_HH = L::OFF_HH, OFF_LG = L::OFF_LG, OFF_SKIN2 = L::OFF_SKIN2, OFF_CH = L::OFF_CH;
   extern __shared__ __align__(128) uint8_t sm[];
   const int N = p.n_layers;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -616,7 +627,8 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
   uint64_t* notefull = xhfull + 3 * NGV;                            // CTA 0: the head's picks of a group
   int (*note)[G] = reinterpret_cast<int (*)[G]>(sm + OFF_NOTE);
   int (*last)[G] = reinterpret_cast<int (*)[G]>(sm + OFF_NOTE + NGV * G * 4);
-  int (*slot)[BPC][G] = reinterpret_cast<int (*)[BPC][G]>(sm + OFF_SLOT);
+  int (*tb)[G] = reinterpret_cast<int (*)[G]>(sm + OFF_NOTE + 2 * NGV * G * 4);      // every stream's step counter at launch (conditioning)
+  int (*slot)[NGV][BPC][G] = reinterpret_cast<int (*)[NGV][BPC][G]>(sm + OFF_SLOT);      // [step parity]: ring slot t mod d of every block and stream
   float (*skin)[G][HS] = reinterpret_cast<float (*)[G][HS]>(sm + OFF_SKIN);
   // BPC > 2, blocks that do not divide: the CTA before the last has at most two blocks ("small", register-resident).  The chain of
   // running skip sums then bypasses it - the CTA before it sends to the last block CTA directly, and the small CTA sends its own
@@ -650,6 +662,8 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
   auto stream_of = [&](int g, int s) { return min((g0 + g) * G + s, p.n_streams - 1); };
   auto sptr = [&](int g, int s) { return state + (int64_t)stream_of(g, s) * p.state_stride; };
   auto n_act_of = [&](int g) { return min(G, p.n_streams - (g0 + g) * G); };
+  if (COND)
+    for (int e = tid; e < max(ng, 0) * G; e += 256) tb[e / G][e % G] = (int)reinterpret_cast<const int64_t*>(sptr(e / G, e % G))[0];
   cluster_sync_all();
   if (ng <= 0) {      // (cannot happen with the launch geometry of fast_gen_steps; all CTAs of the cluster agree)
     cluster_sync_all();
@@ -710,7 +724,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     auto sk_frag = [&](int li, int k) -> uint4 { return SMEMW ? wsm[(li * 12 + 4 + k) * 256] : w2w[li][4 + k]; };
     for (int e = tid; e < ng * nl * G; e += 256) {
       const int s = e % G, li = (e / G) % nl, g = e / (G * nl);
-      slot[g][li][s] = (int)(reinterpret_cast<const int64_t*>(sptr(g, s))[0] % p.dil[l0 + li]);
+      slot[0][g][li][s] = (int)(reinterpret_cast<const int64_t*>(sptr(g, s))[0] % p.dil[l0 + li]);
     }
     if (first) {
       for (int e = tid; e < ng * G; e += 256) {
@@ -721,22 +735,22 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
       for (int e = tid; e < 2 * 256 * 64 / 4; e += 256) reinterpret_cast<float4*>(wc)[e] = reinterpret_cast<const float4*>(p.wc_t)[e];
     }
     __syncthreads();
-    // taps of (group g, its next use): slot as stored (advance = 0) or slot + 1 (advance = 1, also stored)
-    auto prefetch_taps = [&](int g, int advance) {
+    // taps of (group g, its next use): slot as stored for step parity par (advance = 0) or slot + 1 (advance = 1, stored for the other
+    // parity: the 16 lanes that read a slot and the one that advances it never touch the same word)
+    auto prefetch_taps = [&](int g, int advance, int par) {
       for (int e = tid; e < nl * G * 16; e += 256) {
         const int c4 = (e & 15) * 4, s = (e >> 4) % G, li = (e >> 4) / G;
-        int sl = slot[g][li][s];
-        __syncwarp();      // the 16 lanes of a (block, stream) pair have read the slot before one of them advances it
+        int sl = slot[par][g][li][s];
         if (advance) {
           sl = sl + 1 == p.dil[l0 + li] ? 0 : sl + 1;
-          if (c4 == 0) slot[g][li][s] = sl;
+          if (c4 == 0) slot[par ^ 1][g][li][s] = sl;
         }
         const float* src = reinterpret_cast<const float*>(sptr(g, s) + 16) + ((int64_t)p.ring_off[l0 + li] + sl) * 64 + c4;
         __pipeline_memcpy_async(taps + ((size_t)(g * NB + li) * G + s) * XS + c4, src, 16);
       }
       __pipeline_commit();
     };
-    for (int g = 0; g < ng; ++g) prefetch_taps(g, 0);
+    for (int g = 0; g < ng; ++g) prefetch_taps(g, 0, 0);
     for (int g = ng; g < NG; ++g) __pipeline_commit();      // always NG commit groups per ring period: the wait below is a constant
     // remote addresses of the next CTA's slots (same offsets there)
     const uint32_t r_xr = map_to(sm_base + OFF_XIN, rank + 1), r_xf = map_to(sm_base + OFF_XHIN, rank + 1);
@@ -768,13 +782,26 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     // W0 . old of both blocks of group gg (the taps are known one ring period ahead): computed while the group's token is still
     // on its way, so that the token's critical path is four independent MMAs per block instead of four chains of two
     float pre[NB][4];
-    auto compute_pre = [&](int gg) {
+    auto compute_pre = [&](int gg, int step_of) {      // step_of: the step the token of group gg will belong to
 #pragma unroll
       for (int li = 0; li < NB; ++li) {
         if (li < nl) {
           const int ch = 8 * warp + n8;
           const float bf = HAS_BIAS ? p.bias_fg[(l0 + li) * 128 + ch] : 0.f, bg = HAS_BIAS ? p.bias_fg[(l0 + li) * 128 + 64 + ch] : 0.f;
           float c[4] = {bf, bf, bg, bg}, e[4] = {0.f, 0.f, 0.f, 0.f};
+          if (COND) {      // this block's conditioning vector for the time step being consumed (gen.cu, same indexing)
+            const int i = l0 + li, so = p.s_out[i];
+            const int fi = p.cond_gate_first ? 64 + ch : ch, gi = p.cond_gate_first ? ch : 64 + ch;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const int s_ = 2 * q + b;
+              const int tau = p.rf + tb[gg][s_] + step_of;
+              const int f = gen_cond_frame(tau - so, p.cond_total - so, p.cond_frames);
+              const float* cv = p.cond_fg + (((int64_t)stream_of(gg, s_) * p.cond_frames + f) * N + i) * 128;
+              c[b] += cv[fi];
+              c[2 + b] += cv[gi];
+            }
+          }
           const float* orow = taps + ((size_t)(gg * NB + li) * G + n8) * XS + 2 * q;
           uint32_t bo[4][2];
 #pragma unroll
@@ -794,7 +821,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     };
     cp_wait<NG - 1>();      // group 0's taps
     __syncthreads();
-    compute_pre(0);
+    compute_pre(0, 0);
 
     for (int step = 0; step < p.n_steps; ++step) {
       for (int g = 0; g < ng; ++g) {
@@ -979,13 +1006,13 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
           for (int li = 0; li < NB; ++li)
             if (li < nl) {
               const int i = l0 + li;
-              const int o0 = (p.ring_off[i] + slot[g][li][s0]) * 64 + chd, o1 = (p.ring_off[i] + slot[g][li][s1]) * 64 + chd;
+              const int o0 = (p.ring_off[i] + slot[step & 1][g][li][s0]) * 64 + chd, o1 = (p.ring_off[i] + slot[step & 1][g][li][s1]) * 64 + chd;
               if (s0 < n_act) { ring0[o0] = pv[li][0]; ring0[o0 + 8] = pv[li][2]; }
               if (s1 < n_act) { ring1[o1] = pv[li][1]; ring1[o1 + 8] = pv[li][3]; }
             }
         }
         __syncthreads();      // the queue pushes above happen before the tap requests below (a queue of dilation 1 is read back at once)
-        if (step + 1 < p.n_steps) prefetch_taps(g, 1);
+        if (step + 1 < p.n_steps) prefetch_taps(g, 1, step & 1);
         else __pipeline_commit();               // (keeps the commit-group accounting uniform)
         if (g == ng - 1)
           for (int k = ng; k < NG; ++k) __pipeline_commit();
@@ -993,7 +1020,7 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
         if (g + 1 < ng || step + 1 < p.n_steps) {
           cp_wait<NG - 1>();      // the next group's taps were requested NG commit groups ago
           __syncthreads();
-          compute_pre(g + 1 < ng ? g + 1 : 0);
+          compute_pre(g + 1 < ng ? g + 1 : 0, g + 1 < ng ? step : step + 1);
         }
         GEN_TS(14);
       }
@@ -1044,9 +1071,21 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
     const uint2* const hf = reinterpret_cast<const uint2*>(sm + OFF_HF);      // [group][k-tile 16][lane]: relu(skip sums), B fragments
     uint2* const h1f = reinterpret_cast<uint2*>(sm + OFF_HH);                  // [k-tile 16][lane]: relu(post_process_1), B fragments
     float2* const cand = reinterpret_cast<float2*>(sm + OFF_HH + 16 * 32 * 8);  // [warp 8][stream 8]: greedy candidates (value, row)
+    float* const condh = reinterpret_cast<float*>(sm + OFF_CH);                  // [8][256 threads]: a step's conditioning, each thread's own
     for (int step = 0; step < p.n_steps; ++step) {
       for (int g = 0; g < ng; ++g) {
         const int n_act = n_act_of(g);
+        if (COND) {      // this step's conditioning of post_process_1, fetched while the token is on its way; parked in shared memory
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const int row = 16 * (2 * warp + j) + n8 + 8 * (r >> 1), s_ = 2 * q + (r & 1);
+              const int tau = p.rf + tb[g][s_] + step;
+              const int f = gen_cond_frame(tau - (p.rf - 1), p.cond_total - (p.rf - 1), p.cond_frames);
+              condh[(j * 4 + r) * 256 + tid] = p.cond_head[((int64_t)stream_of(g, s_) * p.cond_frames + f) * 256 + row];
+            }
+        }
         HEAD_TS(0);
         wait_token(&skfull[g], step & 1);
         HEAD_TS(1);
@@ -1084,6 +1123,12 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int r = 0; r < 4; ++r) c[j][0][r] = c[j][0][r] + c[j][1][r];
+          if (which == 0 && COND) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) c[j][0][r] += condh[(j * 4 + r) * 256 + tid];      // (the thread's own values: no barrier)
+          }
           if (which == 0) {
             // relu, fp16, and the accumulator fragment transposed into the B fragment of k-tile 2w + j of post_process_2
 #pragma unroll
@@ -1220,7 +1265,7 @@ int fast_gen_pack(const Model& m, const float* d_params, uint8_t* P, cudaStream_
 }
 
 int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t* d_first_note, const void* d_packed, void* d_state,
-                   const float* d_uniforms, int64_t* d_out, float* d_logits, cudaStream_t s) {
+                   const float* d_uniforms, int64_t* d_out, float* d_logits, cudaStream_t s, const wn_gen_cond* cond) {
   WN_REQUIRE(fast_gen_supported(m) && m.n_layers <= GEN_MAXL, WN_ERR_UNSUPPORTED,
              "bf16 generation is specialised for 64/64/256/256 channels and <= %d layers; use mode fp32", GEN_MAXL);
   const PackLayout pl = pack_layout(m);
@@ -1242,6 +1287,14 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
   p.bias_p1 = reinterpret_cast<const float*>(P + pl.bias_p1);
   p.bias_p2 = reinterpret_cast<const float*>(P + pl.bias_p2);
   p.frag = reinterpret_cast<const uint4*>(P + pl.gen_frag);
+  const bool conditioned = cond && cond->d_fg;
+  p.cond_fg = conditioned ? cond->d_fg : nullptr;
+  p.cond_head = conditioned ? cond->d_head : nullptr;
+  p.cond_frames = conditioned ? cond->frames : 0;
+  p.cond_total = conditioned ? cond->total_len : 0;
+  p.cond_gate_first = conditioned ? cond->gate_first : 0;
+  p.rf = m.rf;
+  for (int i = 0; i < m.n_layers; ++i) p.s_out[i] = m.layers[i].start;
   // (the WN_GEN_* switches are read on every call: the geometry tests flip them inside one process)
   const char* const pipe_env = getenv("WN_GEN_PIPE");
   const bool pipe_off = pipe_env && pipe_env[0] == '0';
@@ -1268,20 +1321,26 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
         {gen_pipe_kernel<false, false, false, 4>, gen_pipe_kernel<false, true, false, 4>, gen_pipe_kernel<true, false, false, 4>,
          gen_pipe_kernel<true, true, false, 4>, gen_pipe_kernel<false, false, true, 4>, gen_pipe_kernel<false, true, true, 4>,
          gen_pipe_kernel<true, false, true, 4>, gen_pipe_kernel<true, true, true, 4>}};
+    static const Kern kerns_cond[2][4] = {
+        {gen_pipe_kernel<false, false, false, 2, true>, gen_pipe_kernel<false, true, false, 2, true>, gen_pipe_kernel<true, false, false, 2, true>,
+         gen_pipe_kernel<true, true, false, 2, true>},
+        {gen_pipe_kernel<false, false, false, 4, true>, gen_pipe_kernel<false, true, false, 4, true>, gen_pipe_kernel<true, false, false, 4, true>,
+         gen_pipe_kernel<true, true, false, 4, true>}};
     static const size_t smem_of[2] = {pipe::PipeL<pipe::pipe_groups(2), 2>::TOTAL, pipe::PipeL<pipe::pipe_groups(4), 4>::TOTAL};
-    static bool pipe_once[2][8] = {};
+    static bool pipe_once[2][12] = {};
     static int max_clusters[2][32] = {};
     for (int v = 1; v >= 0; --v) {      // 4 blocks per CTA first
       const int bpc = v ? 4 : 2;
       if (bpc_env && bpc_env != bpc) continue;
-      const Kern kp = kerns[v][ki];
+      const Kern kp = conditioned ? kerns_cond[v][ki & 3] : kerns[v][ki];
+      const int oi = conditioned ? 8 + (ki & 3) : ki;
       // CTA 0 (two blocks), the CTAs in between (bpc blocks), the last block CTA (two blocks), the head
       const int n_last = m.n_layers > 2 ? std::min(2, m.n_layers - 2) : 0, n_mid = std::max(0, m.n_layers - 2 - n_last);
       const int cs = 1 + (int)ceil_div(n_mid, bpc) + (n_last ? 1 : 0) + 1;
-      if (!pipe_once[v][ki]) {
+      if (!pipe_once[v][oi]) {
         WN_CHECK_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of[v]));
         WN_CHECK_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        pipe_once[v][ki] = true;
+        pipe_once[v][oi] = true;
       }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)cs); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem_of[v]; cfg.stream = s;
@@ -1307,6 +1366,8 @@ int fast_gen_steps(Model& m, int n_streams, int n_steps, int push, const int64_t
       return WN_OK;
     }
   }
+  WN_REQUIRE(!conditioned, WN_ERR_UNSUPPORTED,
+             "conditioned half-precision generation runs on the cluster pipeline only (at most 30 blocks, %d streams on this GPU)", 9 * NG * G);
   const size_t smem = gen_smem_bytes(m.n_layers);
   static bool once = false;
   if (!once) {

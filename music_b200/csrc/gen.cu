@@ -321,8 +321,7 @@ extern "C" int wn_gen_steps(wn_model* h, int32_t mode, int32_t n_streams, int32_
   const Model& m = h->m;
   cudaStream_t s = (cudaStream_t)stream;
   if (mode == WN_MODE_BF16) {
-    WN_REQUIRE(h->cond.d_fg == nullptr, WN_ERR_UNSUPPORTED, "conditioned generation is implemented in fp32 mode only");
-    return fast_gen_steps(h->m, n_streams, n_steps, push, d_first_note, d_packed, d_state, d_uniforms, d_out, d_logits, s);
+    return fast_gen_steps(h->m, n_streams, n_steps, push, d_first_note, d_packed, d_state, d_uniforms, d_out, d_logits, s, &h->cond);
   }
   WN_REQUIRE(mode == WN_MODE_FP32, WN_ERR_INVALID, "wn_gen_steps: unknown mode %d", mode);
   GenParams gp;

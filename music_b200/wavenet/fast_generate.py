@@ -99,6 +99,8 @@ def _prime(net, codes, uniforms=None, want_logits=False):
     params = net._params()
     e.ensure_flat(params)
     n, rf = codes.shape
+    if uniforms is not None:
+        uniforms = uniforms.to(codes.device, torch.float32).contiguous()
     mode32 = L.MODE_FP32                  # the prime is one full forward; it runs in fp32
     packed = e.packed(mode32, params)
     nbytes = C.c_size_t()

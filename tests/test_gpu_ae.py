@@ -195,6 +195,39 @@ def test_incremental_decoder_generation_equals_full_forward(W, pool, bias):
     assert torch.equal(free, again)
 
 
+@pytest.mark.parametrize("n_layers,W,bias", [(9, 24, False), (12, 26, True), (4, 24, False)])
+def test_half_precision_pipeline_decoder_generation_vs_fp32_kernel(n_layers, W, bias):
+    """mode="bf16" of the incremental decoder generation: the conditioned 64/64/256/256 decoder on the weights-stationary cluster
+    pipeline (fp16 weight fragments; the per-frame conditioning of every block is folded into the W0.old term that is computed
+    ahead of the token, post_process_1's is fetched by the head while the token travels).  Teacher-forced with the same samples,
+    its logits stay within 1e-2 relative of the fp32 kernel's (which equals the full forward, test above) at every step, in both
+    frame-rule branches (W = 24: 6 frames; 26: ragged) and for layer counts that produce every CTA-role split; free-running
+    generation in ONE launch equals the step-by-step replay of its own picks."""
+    from music_b200.wavenet_autoencoder.generate import fast_generate_codes
+    dil = [2 ** (i % 4) for i in range(n_layers)]
+    cfg = dict(Re=16, De=16, BW=16, pool=4, Rd=64, Dd=64, Sd=256)
+    B = 3
+    net, st, cond, idx, tgt = _ae_case(dil, cfg, bias, B, W, seed=W + n_layers)
+    cond = {k: v.detach() for k, v in cond.items()}
+    rf = O.receptive_field(2, dil)
+    L = rf + W - 1
+    enc = torch.randn(B, cfg["BW"], W // cfg["pool"])
+    net = net.cuda()
+    forced = idx[:, rf:].t().contiguous()
+    c32, l32 = fast_generate_codes(net, enc, L, W, idx[:, :rf], cond_weights=cond, forced=forced, return_logits=True)
+    c16, l16 = fast_generate_codes(net, enc, L, W, idx[:, :rf], cond_weights=cond, forced=forced, return_logits=True, mode="bf16")
+    for j in range(W):
+        assert max_rel(l16[j].cpu().numpy(), l32[j].cpu().numpy()) < 1e-2, j
+    assert (c16 == c32).float().mean().item() >= 0.9
+    free = fast_generate_codes(net, enc, L, 12, idx[:, :rf], cond_weights=cond, mode="bf16")
+    again = fast_generate_codes(net, enc, L, 12, idx[:, :rf], cond_weights=cond, forced=free[:-1], mode="bf16")
+    assert torch.equal(free, again)
+    u = torch.rand(12, B)
+    sampled = fast_generate_codes(net, enc, L, 12, idx[:, :rf], cond_weights=cond, uniforms=u, mode="bf16")
+    replay = fast_generate_codes(net, enc, L, 12, idx[:, :rf], cond_weights=cond, uniforms=u, forced=sampled[:-1], mode="bf16")
+    assert torch.equal(sampled, replay)
+
+
 # ------------------------------------------------------------------------------------------ bf16 tensor-core decoder
 @pytest.mark.parametrize("W,Sd,dense", [(96, 512, False), (100, 256, False), (61, 512, True)])
 def test_bf16_decoder_forward_backward_vs_oracle(W, Sd, dense):
