@@ -436,21 +436,30 @@ gen_steps_bf16_kernel(FastGenParams p, char* __restrict__ state, const int64_t* 
 
 
 // ================================================================================================ weights-stationary pipeline
-// gen_pipe_kernel: ONE thread-block cluster of ceil(N / 2) + 1 CTAs (16 for the 30-layer model) serves up to NG = 8 groups of
-// G = 8 streams.  CTA r < CS - 1 keeps the A fragments of blocks 2r and 2r + 1 (144 KB of fp16) in its REGISTERS for the whole
-// launch; the last CTA keeps post_process_1 in registers and post_process_2 in shared memory.  Nothing is re-read from L2 per
-// step any more.  A group's state hops from CTA to CTA through distributed shared memory as ONE token: after the last barrier
-// of its second block a CTA issues three bulk copies (cp.async.bulk shared::cta -> shared::cluster: x fp32, x fp16, the running
-// skip sums) into the next CTA's slot of that group; they complete on that slot's mbarrier there (complete_tx), which the
-// consumer has armed with the byte count.  (The first version wrote the slot with per-thread st.shared::cluster: 36 cycles per
-// warp store, 1150 + 1400 cycles per hop.)  The head picks the sample and sends it to CTA 0, which gathers the causal layer's two
-// embedding rows from its shared-memory copy of the table.  Every group owns one slot per CTA and carries exactly one token
-// around the ring, so there is no back-pressure and no barrier between groups: while group g is in CTA r, groups g - 1, g - 2,
-// ... are in CTAs r + 1, r + 2, ...  Ring-buffer state stays in global memory (L2); the taps of a group's next step are requested
-// with cp.async right after its token has left.
-// Measured (tools/ts_gen.py): a dependent mma.sync.m16n8k16 chain costs ~85 cycles per link on B200, so every accumulation is
-// split into chains of two; a block is then two exchange phases of ~350-400 cycles.  The step is the ring latency
-// (30 blocks + 15 hops + head), the same for 8 and for 64 streams per cluster; independent clusters serve more streams.
+// gen_pipe_kernel: a thread-block cluster holds the whole model for the whole launch and serves groups of G = 8 streams (the N
+// dimension of m16n8k16).  Block CTAs keep the A fragments of their residual blocks resident, the last CTA ("head") keeps
+// post_process_1 and half of post_process_2 in registers and the rest in shared memory: nothing is re-read from L2 per step but
+// the ring state.  Two geometries (template BPC, chosen by fast_gen_steps):
+//   BPC = 4  CTA 0 and the last block CTA have 2 blocks with every fragment in registers; the CTAs in between have 4 blocks with
+//            W1 (current-sample tap of [f|g]) and the dense convolution in registers - what the token waits for - and W0 (old tap)
+//            and the skip convolution, which run ahead of / behind the token, in shared memory.  10 CTAs for 30 blocks, ONE group
+//            per cluster, as many clusters as fit on the GPU (up to 16 = 128 streams).
+//   BPC = 2  every CTA 2 blocks, everything in registers, 16 CTAs for 30 blocks, up to NG = 8 groups per cluster (576 streams).
+// A group's state is a token that hops CTA -> CTA through distributed shared memory.  Its critical path per block is
+//   LDS x fragments -> 4 independent MMAs (W1 x, on top of the precomputed W0 old + bias + conditioning) -> gate -> STS z, barrier ->
+//   (4 dense warps) LDS z fragments -> 4 independent MMAs -> + residual (kept in registers from block to block) -> STS x, barrier
+// and after a CTA's last block the 4 dense warps send the token straight from their registers with st.async (data and mbarrier
+// complete_tx travel together): 1 KB of fp16 B fragments (the accumulator fragments transposed by movmatrix: exactly what the next
+// CTA's MMAs load) on one mbarrier, then 2 KB of fp32 accumulator fragments (the residual) on a second one that the consumer probes
+// a phase early.  Everything else is off that path: W0.old of a group's next token is computed as soon as its taps (cp.async,
+// requested one ring period ahead) have landed; skip MMAs, queue pushes and the running skip sums (an 8 KB bulk copy behind the
+// token) come after the token has left; barriers are re-armed in the tail.  The last block CTA does its skip MMAs first and sends
+// relu(sum + bias) as post_process_1's fp16 B fragments; the head finds the greedy pick in registers (shuffles, then one exchange
+// through 512 B of shared memory) and st.asyncs it to CTA 0, which gathers the causal layer's two embedding rows from its
+// shared-memory copy of the table.  Every group owns one slot per CTA and carries exactly one token around the ring, so there is no
+// back-pressure and no barrier between groups.  The CTA's role (first / in between / short in between / last) is a compile-time
+// parameter of the loop body; waits use CTA-scope acquires (a cluster-scope acquire compiles to CCTL.IVALL per token).
+// Measured history and the micro-benchmarks behind these choices: profiles/r2_summary.md (32.1 -> 9.8 us per step).
 constexpr int NG = 8;
 // timing experiments (WN_TS=1): clock64 stamps of CTA 1 of cluster 0, group 0, 16 per step (wn_debug_ts with n < 0 reads them)
 __device__ long long g_gen_ts[3 * 16 * 64];      // [0,1024): clock64 stamps of CTA 1; [1024,2048): globaltimer at token arrival, per rank; [2048,3072): clock64 stamps of the head

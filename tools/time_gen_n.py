@@ -1,4 +1,4 @@
-"""Step time of the generation kernel for models of N blocks (timing experiments: WN_GEN_LPC, WN_GEN_PIPE)."""
+"""Step time of the generation kernel for models of N blocks (timing experiments: WN_GEN_BPC, WN_GEN_GPC, WN_GEN_PIPE)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
