@@ -526,10 +526,6 @@ __device__ __forceinline__ uint32_t map_to(uint32_t local_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_remote_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void arrive_remote(uint32_t bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
-}
 // local shared memory -> another CTA's shared memory; the bytes complete on THAT CTA's mbarrier
 __device__ __forceinline__ void bulk_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster), "r"(src_cta),
@@ -592,18 +588,6 @@ __device__ __forceinline__ uint32_t try_wait_once(uint64_t* bar, uint32_t parity
 }
 template <int N_>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
-__device__ __forceinline__ void cp_wait_dyn(int n) {      // all but the newest n committed groups are complete
-  switch (n) {
-    case 0: cp_wait<0>(); break;
-    case 1: cp_wait<1>(); break;
-    case 2: cp_wait<2>(); break;
-    case 3: cp_wait<3>(); break;
-    case 4: cp_wait<4>(); break;
-    case 5: cp_wait<5>(); break;
-    case 6: cp_wait<6>(); break;
-    default: cp_wait<7>(); break;
-  }
-}
 }  // namespace pipe
 
 // HAS_BIAS / PUSH_OUT are compile-time: every block of the ring is a chain of ~400 dependent-latency instructions per warp, and the
@@ -1061,7 +1045,6 @@ gen_pipe_kernel(FastGenParams p, char* __restrict__ state, const int64_t* __rest
   } else {
     // ============================================================ head CTA: relu(sum skips) -> P1 -> relu -> P2 -> pick
     uint4* p2s = reinterpret_cast<uint4*>(sm + OFF_P2);
-    __half (*hh)[G][HH] = reinterpret_cast<__half (*)[G][HH]>(sm + OFF_HH);
     float (*lg)[HS] = reinterpret_cast<float (*)[HS]>(sm + OFF_LG);
     const uint4* const headA = p.frag + (int64_t)N * FRAG_LAYER;
     uint4 p1w[2][16];      // post_process_1: this warp's two m-tiles, resident
